@@ -1,0 +1,314 @@
+/*
+ * mrmd_b200.h -- C ABI of the B200-native MRMD force + neighbour hot path.
+ *
+ * The reference (XzzX/mrmd) has no FFI: its boundary is the public C++ API of
+ * namespace mrmd.  Every entry point below replaces the
+ * Kokkos/Cabana kernel(s) behind one reference member function; the citation
+ * after "replaces" is the reference file:line.  include/mrmd/ holds the C++20
+ * mirror of the reference classes that forwards to these functions and
+ * INTEGRATION.md shows the binding a maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - plain C types only; all handles are opaque; no torch / Kokkos types.
+ *   - every function returns 0 on success, a positive cudaError_t, or a negative
+ *     MRMD_B200_E* code; mrmd_b200_last_error() gives the message.
+ *   - "stream" is a cudaStream_t passed as void* (NULL = default stream).  Work is
+ *     enqueued asynchronously unless the function returns a host scalar (the
+ *     reference's equivalents all fence: every Kokkos kernel is followed by
+ *     Kokkos::fence()).
+ *   - device memory is owned by the handles; the library never frees caller memory.
+ *   - there is NO CPU fallback: without a CUDA device every call fails with
+ *     MRMD_B200_ENODEVICE.
+ */
+#ifndef MRMD_B200_H
+#define MRMD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRMD_B200_EINVAL (-1)
+#define MRMD_B200_ENODEVICE (-2)
+#define MRMD_B200_ECAPACITY (-3)
+#define MRMD_B200_ENOMEM (-4)
+
+typedef struct mrmd_b200_atoms mrmd_b200_atoms;         /* data::Atoms            (data/Atoms.hpp:33-147) */
+typedef struct mrmd_b200_molecules mrmd_b200_molecules; /* data::Molecules        (data/Molecules.hpp:27-148) */
+typedef struct mrmd_b200_verlet mrmd_b200_verlet;       /* Half/FullVerletList    (datatypes.hpp:184-191) */
+typedef struct mrmd_b200_ghost mrmd_b200_ghost;         /* communication::GhostLayer / MultiResGhostLayer */
+typedef struct mrmd_b200_lj mrmd_b200_lj;               /* action::LennardJones   (action/LennardJones.hpp:98-133) */
+typedef struct mrmd_b200_adress mrmd_b200_adress;       /* action::LJ_IdealGas    (action/LJ_IdealGas.hpp:34-104) */
+typedef struct mrmd_b200_thermo mrmd_b200_thermo;       /* action::ThermodynamicForce (ThermodynamicForce.hpp:32-96) */
+
+/* data::Subdomain (data/Subdomain.hpp:37-110); fill with mrmd_b200_subdomain_init */
+typedef struct
+{
+    double minCorner[3];
+    double maxCorner[3];
+    double ghostLayerThickness[3];
+    double minGhostCorner[3];
+    double maxGhostCorner[3];
+    double minInnerCorner[3];
+    double maxInnerCorner[3];
+    double diameter[3];
+    double diameterWithGhostLayer[3];
+} mrmd_b200_subdomain;
+
+/* Parametric stand-in for the reference's predicate lambdas (device lambdas cannot cross a C ABI):
+ * util::IsInSymmetricSlab (util/IsInSymmetricSlab.hpp:24-64) alone or combined over two positions as in
+ * examples/04_LennardJones_IdealGas_LocalCap.cpp:206-227. */
+enum
+{
+    MRMD_B200_PRED_ALWAYS = 0,
+    MRMD_B200_PRED_NEVER = 1,
+    MRMD_B200_PRED_SLAB = 2,        /* slabMin-tol <= |x[axis]-center| <= slabMax+tol            */
+    MRMD_B200_PRED_SLAB_EITHER = 3, /* two positions: slab(p1) || slab(p2)                       */
+    MRMD_B200_PRED_SLAB_BOTH = 4,   /* two positions: slab(p1) && slab(p2)                       */
+    MRMD_B200_PRED_INTERVAL = 5     /* slabMin < x[axis] < slabMax (ThermodynamicForce.test.cpp:29-40) */
+};
+typedef struct
+{
+    int32_t kind;
+    int32_t axis;
+    double center;
+    double slabMin;
+    double slabMax;
+    double tolerance;
+} mrmd_b200_pred;
+
+/* weighting_function::Slab (Slab.hpp:27-201) / Spherical (Spherical.hpp:25-99, lambda^mod := lambda) */
+enum
+{
+    MRMD_B200_WEIGHT_SLAB = 0,
+    MRMD_B200_WEIGHT_SPHERICAL = 1
+};
+typedef struct
+{
+    int32_t kind;
+    int32_t abrupt;   /* Slab::InterfaceType::ABRUPT */
+    double center[3];
+    double atRegion;  /* Slab: atomistic region DIAMETER; Spherical: atomistic RADIUS */
+    double hyRegion;  /* hybrid region width */
+    int64_t exponent; /* Slab: nu (exponent 2 nu); Spherical: exponent */
+} mrmd_b200_weight;
+
+enum
+{
+    MRMD_B200_ATOM_POS = 0,
+    MRMD_B200_ATOM_VEL = 1,
+    MRMD_B200_ATOM_FORCE = 2,
+    MRMD_B200_ATOM_TYPE = 3, /* int64 */
+    MRMD_B200_ATOM_MASS = 4,
+    MRMD_B200_ATOM_CHARGE = 5,
+    MRMD_B200_ATOM_RELATIVE_MASS = 6
+};
+enum
+{
+    MRMD_B200_MOL_POS = 0,
+    MRMD_B200_MOL_FORCE = 1,
+    MRMD_B200_MOL_LAMBDA = 2,
+    MRMD_B200_MOL_MODULATED_LAMBDA = 3,
+    MRMD_B200_MOL_GRAD_LAMBDA = 4,
+    MRMD_B200_MOL_ATOMS_OFFSET = 5, /* int64 */
+    MRMD_B200_MOL_NUM_ATOMS = 6     /* int64 */
+};
+enum
+{
+    MRMD_B200_MEM_HOST = 0,
+    MRMD_B200_MEM_DEVICE = 1
+};
+
+const char* mrmd_b200_last_error(void);
+int mrmd_b200_device_count(void);
+int mrmd_b200_set_device(int device);
+int mrmd_b200_sync(void* stream);
+/* number of kernels this library launched since load (bench.py's gpu_launches) */
+int64_t mrmd_b200_launch_count(void);
+
+void mrmd_b200_subdomain_init(mrmd_b200_subdomain* s, const double* minCorner, const double* maxCorner,
+                              const double* ghostLayerThickness);
+/* Subdomain::scaleDim (data/Subdomain.cpp:24-32) */
+void mrmd_b200_subdomain_scale_dim(mrmd_b200_subdomain* s, double factor, int axis);
+
+/* ---- data::Atoms ---------------------------------------------------------------------------- */
+/* replaces GeneralAtoms(numAtoms) (data/Atoms.hpp:123-133): zero-filled container of `size` atoms */
+int mrmd_b200_atoms_create(mrmd_b200_atoms** out, int64_t size);
+int mrmd_b200_atoms_destroy(mrmd_b200_atoms* a);
+/* replaces resize() (:89-93); contents are preserved, new entries are zero */
+int mrmd_b200_atoms_resize(mrmd_b200_atoms* a, int64_t size, void* stream);
+int mrmd_b200_atoms_reserve(mrmd_b200_atoms* a, int64_t capacity, void* stream);
+int64_t mrmd_b200_atoms_size(const mrmd_b200_atoms* a);
+/* numLocalAtoms / numGhostAtoms (:120-121) */
+int mrmd_b200_atoms_set_counts(mrmd_b200_atoms* a, int64_t numLocal, int64_t numGhost);
+int mrmd_b200_atoms_get_counts(const mrmd_b200_atoms* a, int64_t* numLocal, int64_t* numGhost);
+/* slice transfer.  Element (i, d) of the caller's buffer sits at
+ *   buf[((first_in_buf + i) / vlen) * stride + d * vlen + ((first_in_buf + i) % vlen)]
+ * which is a Cabana slice (data(), stride(0), vector length); a dense (n, ncomp) array is
+ * stride = ncomp, vlen = 1; the reference's default AoSoA (MRMD_VECTOR_LENGTH=1) is stride 13.
+ * Replaces deep_copy host<->device (data/Atoms.hpp:150-159). */
+int mrmd_b200_atoms_write(mrmd_b200_atoms* a, int field, const void* src, int64_t first, int64_t count,
+                          int64_t stride, int64_t vlen, int memKind, void* stream);
+int mrmd_b200_atoms_read(const mrmd_b200_atoms* a, int field, void* dst, int64_t first, int64_t count,
+                         int64_t stride, int64_t vlen, int memKind, void* stream);
+/* Cabana::deep_copy(slice, value) / Atoms::setForce (data/Atoms.hpp:72, examples/02:174-175) */
+int mrmd_b200_atoms_fill(mrmd_b200_atoms* a, int field, double value, void* stream);
+/* deep_copy(dst, src) between two device containers */
+int mrmd_b200_atoms_copy(mrmd_b200_atoms* dst, const mrmd_b200_atoms* src, void* stream);
+
+/* ---- data::Molecules ------------------------------------------------------------------------ */
+int mrmd_b200_molecules_create(mrmd_b200_molecules** out, int64_t size);
+int mrmd_b200_molecules_destroy(mrmd_b200_molecules* m);
+int mrmd_b200_molecules_resize(mrmd_b200_molecules* m, int64_t size, void* stream);
+int64_t mrmd_b200_molecules_size(const mrmd_b200_molecules* m);
+int mrmd_b200_molecules_set_counts(mrmd_b200_molecules* m, int64_t numLocal, int64_t numGhost);
+int mrmd_b200_molecules_get_counts(const mrmd_b200_molecules* m, int64_t* numLocal, int64_t* numGhost);
+int mrmd_b200_molecules_write(mrmd_b200_molecules* m, int field, const void* src, int64_t first, int64_t count,
+                              int64_t stride, int64_t vlen, int memKind, void* stream);
+int mrmd_b200_molecules_read(const mrmd_b200_molecules* m, int field, void* dst, int64_t first, int64_t count,
+                             int64_t stride, int64_t vlen, int memKind, void* stream);
+int mrmd_b200_molecules_fill(mrmd_b200_molecules* m, int field, double value, void* stream);
+/* replaces data::createMoleculeForEachAtom (data/MoleculesFromAtoms.cpp:19-39) */
+int mrmd_b200_molecules_for_each_atom(mrmd_b200_molecules** out, const mrmd_b200_atoms* a, void* stream);
+
+/* ---- integrators ---------------------------------------------------------------------------- */
+/* replaces VelocityVerlet::preForceIntegrate (action/VelocityVerlet.cpp:26-67).  The maximum
+ * displacement is accumulated in a device scalar; *maxDisplacement (host, may be NULL) receives
+ * sqrt(max |dx|^2) after a stream sync, exactly what the reference returns. */
+int mrmd_b200_vv_pre(mrmd_b200_atoms* a, double dt, double* maxDisplacement, void* stream);
+/* replaces VelocityVerlet::postForceIntegrate (action/VelocityVerlet.cpp:69-90) */
+int mrmd_b200_vv_post(mrmd_b200_atoms* a, double dt, void* stream);
+/* replaces VelocityVerletLangevinThermostat::preForceIntegrate(_apply_if)
+ * (action/VelocityVerletLangevinThermostat.hpp:48-52,63-136).  Random numbers: Philox4x32-10,
+ * key = seed, counter = (atom index, step); the reference's XorShift1024 pool stream is scheduling
+ * dependent and unpinned, so only the statistics are comparable. */
+int mrmd_b200_langevin_pre(mrmd_b200_atoms* a, double dt, double zeta, double temperature, uint64_t seed,
+                           uint64_t step, const mrmd_b200_pred* pred, double* maxDisplacement, void* stream);
+
+/* ---- communication::GhostLayer -------------------------------------------------------------- */
+int mrmd_b200_ghost_create(mrmd_b200_ghost** out);
+int mrmd_b200_ghost_destroy(mrmd_b200_ghost* g);
+/* replaces GhostLayer::exchangeRealAtoms -> PeriodicMapping::mapIntoDomain (PeriodicMapping.cpp:30-58) */
+int mrmd_b200_ghost_map_into_domain(mrmd_b200_atoms* a, const mrmd_b200_subdomain* s, void* stream);
+/* replaces GhostExchange::resetCorrespondingRealAtoms + createGhostAtoms(axis) (GhostExchange.cpp:59-169,183-187).
+ * axis < 0: reset + X, Y, Z = createGhostAtomsXYZ (:171-181) = GhostLayer::createGhostAtoms.  Grows `a`. */
+int mrmd_b200_ghost_create_atoms(mrmd_b200_ghost* g, mrmd_b200_atoms* a, const mrmd_b200_subdomain* s, int axis,
+                                 void* stream);
+int mrmd_b200_ghost_reset(mrmd_b200_ghost* g, mrmd_b200_atoms* a, void* stream);
+/* replaces GhostLayer::updateGhostAtoms -> UpdateGhostAtoms::updateOnlyPos (UpdateGhostAtoms.cpp:31-68) */
+int mrmd_b200_ghost_update(mrmd_b200_ghost* g, mrmd_b200_atoms* a, const mrmd_b200_subdomain* s, void* stream);
+/* replaces GhostLayer::contributeBackGhostToReal -> AccumulateForce::ghostToReal (AccumulateForce.cpp:25-47) */
+int mrmd_b200_ghost_contribute_back(mrmd_b200_ghost* g, mrmd_b200_atoms* a, void* stream);
+/* correspondingRealAtom view (int64, -1 for real atoms); count entries starting at first */
+int mrmd_b200_ghost_read_corresponding(const mrmd_b200_ghost* g, int64_t* dst, int64_t first, int64_t count,
+                                       int memKind, void* stream);
+int mrmd_b200_ghost_write_corresponding(mrmd_b200_ghost* g, const int64_t* src, int64_t first, int64_t count,
+                                        int memKind, void* stream);
+/* MultiResGhostLayer (communication/MultiResGhostLayer.hpp:29-61):
+ * replaces realAtomsExchange (MultiResRealAtomsExchange.cpp:23-73) */
+int mrmd_b200_ghost_mr_map_into_domain(mrmd_b200_molecules* m, mrmd_b200_atoms* a, const mrmd_b200_subdomain* s,
+                                       void* stream);
+/* replaces MultiResPeriodicGhostExchange::createGhostAtoms / XYZ (MultiResPeriodicGhostExchange.cpp:60-265) */
+int mrmd_b200_ghost_mr_create_atoms(mrmd_b200_ghost* g, mrmd_b200_molecules* m, mrmd_b200_atoms* a,
+                                    const mrmd_b200_subdomain* s, int axis, void* stream);
+
+/* ---- Cabana::LinkedCellList + permute, Cabana::VerletList ----------------------------------- */
+/* replaces LinkedCellList(pos, begin, end, delta, min, max) + atoms.permute(list)
+ * (tests/NVT/NVT.cpp:136-144, data/Atoms.hpp:95): stable, atomic-free radix sort by cell index, all
+ * members reordered.  cellIdOut (device, int32[end], optional) receives the cell index of every particle
+ * BEFORE the permutation (for parity checks). */
+int mrmd_b200_atoms_cell_sort(mrmd_b200_atoms* a, int64_t begin, int64_t end, const double* delta,
+                              const double* gridMin, const double* gridMax, int32_t* cellIdOut, void* stream);
+/* same for molecules (data/Molecules.hpp:91-95); atoms are not moved */
+int mrmd_b200_molecules_cell_sort(mrmd_b200_molecules* m, int64_t begin, int64_t end, const double* delta,
+                                  const double* gridMin, const double* gridMax, void* stream);
+
+int mrmd_b200_verlet_create(mrmd_b200_verlet** out, int half);
+int mrmd_b200_verlet_destroy(mrmd_b200_verlet* v);
+/* replaces VerletList::build(pos, begin, end, radius, cellRatio, gridMin, gridMax, maxNeigh)
+ * (call sites examples/02_LennardJones_NVE.cpp:156-163, tests/LennardJones/LennardJones.cpp:112-118,
+ * action/LJ_IdealGas.test.cpp:113-120).  All size() particles are candidates, rows exist for [begin,end).
+ * If a row overflows maxNeigh the table is widened and refilled (as Cabana does). */
+int mrmd_b200_verlet_build_atoms(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, int64_t begin, int64_t end,
+                                 double radius, double cellRatio, const double* gridMin, const double* gridMax,
+                                 int64_t maxNeigh, void* stream);
+int mrmd_b200_verlet_build_molecules(mrmd_b200_verlet* v, const mrmd_b200_molecules* m, int64_t begin, int64_t end,
+                                     double radius, double cellRatio, const double* gridMin, const double* gridMax,
+                                     int64_t maxNeigh, void* stream);
+/* list._data.counts / neighbors as a Cabana VerletLayout2D table: counts[numParticles] int32 and
+ * neighbors[numParticles][width] int32 (row-major).  Pass NULL to query sizes only. */
+int mrmd_b200_verlet_info(const mrmd_b200_verlet* v, int64_t* numParticles, int64_t* width, int64_t* totalPairs,
+                          int* half);
+int mrmd_b200_verlet_read(const mrmd_b200_verlet* v, int32_t* counts, int32_t* neighbors, int memKind, void* stream);
+
+/* ---- action::LennardJones ------------------------------------------------------------------- */
+/* replaces LennardJones(cappingDistance[], rc[], sigma[], epsilon[], numTypes, isShifted)
+ * (action/LennardJones.cpp:46-56, :81-116); arrays hold numTypes^2 entries */
+int mrmd_b200_lj_create(mrmd_b200_lj** out, const double* cappingDistance, const double* rc, const double* sigma,
+                        const double* epsilon, int64_t numTypes, int isShifted);
+int mrmd_b200_lj_destroy(mrmd_b200_lj* lj);
+/* replaces LennardJones::apply / apply_if (action/LennardJones.hpp:135-206).  pred == NULL: apply.
+ * With a half list forces are scattered to both partners (ghosts included, fold them back with
+ * mrmd_b200_ghost_contribute_back); with a full list only row owners receive force and energy/virial
+ * are halved (extension, same post-fold-back result).  Energy and virial are kept on the device until
+ * mrmd_b200_lj_get is called. */
+int mrmd_b200_lj_apply(mrmd_b200_lj* lj, mrmd_b200_atoms* a, const mrmd_b200_verlet* v, const mrmd_b200_pred* pred,
+                       void* stream);
+/* getEnergy()/getVirial() (action/LennardJones.cpp:35-36); numPairs = pairs that reached the force
+ * evaluation in the last apply (the pair-interactions/s numerator).  Syncs the stream. */
+int mrmd_b200_lj_get(mrmd_b200_lj* lj, double* energy, double* virial, int64_t* numPairs, void* stream);
+/* CappedLennardJonesPotential::computeForceAndEnergy on the device for n squared distances (unit tests) */
+int mrmd_b200_lj_eval(const mrmd_b200_lj* lj, int64_t typeIdx, const double* distSqrHost, int64_t n,
+                      double* forceFactorHost, double* energyHost, void* stream);
+
+/* ---- AdResS --------------------------------------------------------------------------------- */
+/* replaces UpdateMolecules::update (action/UpdateMolecules.hpp:24-70) */
+int mrmd_b200_molecules_update(mrmd_b200_molecules* m, const mrmd_b200_atoms* a, const mrmd_b200_weight* w,
+                               void* stream);
+/* replaces ContributeMoleculeForceToAtoms::update (action/ContributeMoleculeForceToAtoms.cpp:23-48) */
+int mrmd_b200_molecules_contribute_force(const mrmd_b200_molecules* m, mrmd_b200_atoms* a, void* stream);
+/* evaluates the weighting function on the device for n host positions (unit tests) */
+int mrmd_b200_weight_eval(const mrmd_b200_weight* w, const double* posHost, int64_t n, double* lambdaHost,
+                          double* modLambdaHost, double* gradHost, void* stream);
+/* replaces LJ_IdealGas(...) ctors (action/LJ_IdealGas.cpp:262-292) */
+int mrmd_b200_adress_create(mrmd_b200_adress** out, const double* cappingDistance, const double* rc,
+                            const double* sigma, const double* epsilon, int64_t numTypes, int doShift);
+int mrmd_b200_adress_destroy(mrmd_b200_adress* ad);
+/* setCompensationEnergySamplingInterval / UpdateInterval (action/LJ_IdealGas.hpp:73-80) */
+int mrmd_b200_adress_set_intervals(mrmd_b200_adress* ad, int64_t samplingInterval, int64_t updateInterval);
+/* replaces LJ_IdealGas::run (action/LJ_IdealGas.cpp:227-260); *energy (host, optional) after a sync */
+int mrmd_b200_adress_run(mrmd_b200_adress* ad, mrmd_b200_molecules* m, const mrmd_b200_verlet* v,
+                         mrmd_b200_atoms* a, double* energy, int64_t* numPairs, void* stream);
+/* getMeanCompensationEnergy() and the two accumulation histograms, 200 x numTypes doubles each
+ * (kind 0 mean, 1 compensationEnergy, 2 compensationEnergyCounter) */
+int mrmd_b200_adress_read_histogram(const mrmd_b200_adress* ad, int kind, double* dstHost, void* stream);
+
+/* ---- action::ThermodynamicForce ------------------------------------------------------------- */
+/* replaces the ctor (action/ThermodynamicForce.cpp:25-57) */
+int mrmd_b200_thermo_create(mrmd_b200_thermo** out, const double* targetDensity, int64_t numTypes,
+                            const mrmd_b200_subdomain* s, double requestedDensityBinWidth,
+                            const double* modulation, int enforceSymmetry, int usePeriodicity);
+int mrmd_b200_thermo_destroy(mrmd_b200_thermo* t);
+int mrmd_b200_thermo_info(const mrmd_b200_thermo* t, int64_t* numBins, int64_t* numTypes, double* binSize,
+                          int64_t* samples);
+/* replaces sample() (ThermodynamicForce.cpp:74-86) = analysis::getAxialDensityProfile (AxialDensityProfile.cpp:21-51) */
+int mrmd_b200_thermo_sample(mrmd_b200_thermo* t, const mrmd_b200_atoms* a, void* stream);
+/* replaces update / update_if (ThermodynamicForce.hpp:124-152, .cpp:88-91); pred on the bin centre */
+int mrmd_b200_thermo_update(mrmd_b200_thermo* t, double smoothingSigma, double smoothingIntensity,
+                            const mrmd_b200_pred* pred, void* stream);
+/* replaces apply / apply_if (ThermodynamicForce.hpp:98-122) and applyInterpolated_if (:154-216) */
+int mrmd_b200_thermo_apply(const mrmd_b200_thermo* t, mrmd_b200_atoms* a, const mrmd_b200_pred* pred,
+                           int interpolated, void* stream);
+/* getForce()/setForce()/getDensityProfile(): numBins x numTypes doubles, host buffers (kind 0 force, 1 density) */
+int mrmd_b200_thermo_read(const mrmd_b200_thermo* t, int kind, double* dstHost, void* stream);
+int mrmd_b200_thermo_write_force(mrmd_b200_thermo* t, const double* srcHost, void* stream);
+/* all-reduce hooks for the x-slab decomposition: raw device pointer of the density histogram */
+int mrmd_b200_thermo_density_ptr(mrmd_b200_thermo* t, double** devicePtr, int64_t* count);
+/* getMuLeft / getMuRight (ThermodynamicForce.cpp:98-130) */
+int mrmd_b200_thermo_mu(const mrmd_b200_thermo* t, double* muLeftHost, double* muRightHost, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRMD_B200_H */

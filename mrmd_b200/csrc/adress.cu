@@ -1,0 +1,442 @@
+// adress.cu -- AdResS path: molecule update with inlined weighting function, lambda-weighted LJ / ideal-gas
+// force interpolation with drift force and drift-compensation histograms, molecule -> atom force scatter
+// (SURVEY.md K13-K16).
+// Reference: mrmd/action/UpdateMolecules.hpp:24-70, mrmd/weighting_function/Slab.hpp:27-201,
+//            Spherical.hpp:25-99, CheckRegion.hpp:25-38, mrmd/action/LJ_IdealGas.hpp:34-104,
+//            LJ_IdealGas.cpp:21-292, mrmd/action/ContributeMoleculeForceToAtoms.cpp:23-48, util/math.hpp:31-46.
+#include <algorithm>
+
+#include "common.cuh"
+
+struct mrmd_b200_adress
+{
+    int64_t numTypes = 1;
+    double rcSqr = 0.0;
+    mrmd_b200::LJTable table{};
+    int64_t runCounter = 0;
+    int64_t samplingInterval = 200;  // LJ_IdealGas.hpp:69
+    int64_t updateInterval = 20000;  // :70
+    double* hist = nullptr;          // 3 x (200 x numTypes): compensationEnergy, counter, mean
+    mrmd_b200::DevBuf partials;
+    double* dResult = nullptr;
+    unsigned int* dTicket = nullptr;
+    double* hResult = nullptr;
+};
+
+namespace mrmd_b200
+{
+int buildLJTable(LJTable& table, const double* cappingDistance, const double* rc, const double* sigma,
+                 const double* epsilon, int64_t numTypes, int isShifted, double* rcSqrMax);
+
+constexpr int COMPENSATION_ENERGY_BINS = 200;  // LJ_IdealGas.hpp:54
+constexpr double PI = 3.14159265358979323846;
+constexpr int AD_THREADS = 128;
+
+// util/math.hpp:31-46: square-and-multiply in the reference's multiplication order
+__device__ __forceinline__ double powInt(double x, long long n)
+{
+    double ww = x;
+    double yy = 1.0;
+    for (long long nn = (n > 0) ? n : -n; nn != 0; nn >>= 1)
+    {
+        if ((nn & 1) == 1) yy *= ww;
+        ww *= ww;
+    }
+    return (n > 0) ? yy : 1.0 / yy;
+}
+
+// Slab::operator() (Slab.hpp:161-187) / Spherical::operator() (Spherical.hpp:37-75)
+__device__ __forceinline__ void weightEval(const mrmd_b200_weight& w, double x, double y, double z, double& lambda,
+                                           double& modLambda, double& gx, double& gy, double& gz)
+{
+    gx = gy = gz = 0.0;
+    if (w.kind == MRMD_B200_WEIGHT_SLAB)
+    {
+        const double atHalf = 0.5 * w.atRegion;
+        const long long exponent = 2 * w.exponent;
+        const double dx = x - w.center[0];
+        const double absDx = fabs(dx);
+        if (absDx < atHalf || (w.abrupt && !(absDx > atHalf + w.hyRegion)))
+        {
+            lambda = 1.0;
+            modLambda = 1.0;
+        }
+        else if (absDx > atHalf + w.hyRegion)
+        {
+            lambda = 0.0;
+            modLambda = 0.0;
+        }
+        else
+        {
+            const double arg = PI / (2.0 * w.hyRegion) * (absDx - atHalf);
+            const double base = cos(arg);
+            lambda = base * base;
+            modLambda = powInt(base, exponent);
+            const double factor =
+                -PI / (2.0 * w.hyRegion) * double(exponent) * sin(arg) * powInt(base, exponent - 1) / absDx;
+            gx = factor * dx;
+        }
+        return;
+    }
+    const double atRadiusSqr = w.atRegion * w.atRegion;
+    const double cgRadiusSqr = (w.atRegion + w.hyRegion) * (w.atRegion + w.hyRegion);
+    const double dx = x - w.center[0], dy = y - w.center[1], dz = z - w.center[2];
+    const double dxSqr = dx * dx + dy * dy + dz * dz;
+    if (dxSqr < atRadiusSqr)
+    {
+        lambda = 1.0;
+        modLambda = 1.0;
+        return;
+    }
+    if (dxSqr > cgRadiusSqr)
+    {
+        lambda = 0.0;
+        modLambda = 0.0;
+        return;
+    }
+    const double r = sqrt(dxSqr);
+    const double arg = PI / (2.0 * w.hyRegion) * (r - w.atRegion);
+    const double base = cos(arg);
+    lambda = powInt(base, w.exponent);
+    modLambda = lambda;
+    const double factor = -PI / (2.0 * w.hyRegion) * double(w.exponent) * sin(arg) * powInt(base, w.exponent - 1) / r;
+    gx = factor * dx;
+    gy = factor * dy;
+    gz = factor * dz;
+}
+
+// UpdateMolecules::update, UpdateMolecules.hpp:41-67
+__global__ void updateMoleculesKernel(MolsView m, AtomsView a, int64_t numAll, mrmd_b200_weight w)
+{
+    const int64_t mi = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (mi >= numAll) return;
+    const longlong2 oc = m.oc[mi];
+    double X = 0.0, Y = 0.0, Z = 0.0;
+    for (long long ai = oc.x; ai < oc.x + oc.y; ++ai)
+    {
+        const double4 p = ld4nc(a.pos + ai);
+        const double rm = a.relMass[ai];
+        X += p.x * rm;
+        Y += p.y * rm;
+        Z += p.z * rm;
+    }
+    double lambda, modLambda, gx, gy, gz;
+    weightEval(w, X, Y, Z, lambda, modLambda, gx, gy, gz);
+    st4(m.pos + mi, make_double4(X, Y, Z, 0.0));
+    st4(m.w + mi, make_double4(modLambda, gx, gy, gz));
+    m.lambda[mi] = lambda;
+}
+
+// ContributeMoleculeForceToAtoms::update, ContributeMoleculeForceToAtoms.cpp:34-45
+__global__ void contributeMoleculeForceKernel(MolsView m, AtomsView a, int64_t numAll)
+{
+    const int64_t mi = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (mi >= numAll) return;
+    const longlong2 oc = m.oc[mi];
+    const double fx = m.force[0][mi], fy = m.force[1][mi], fz = m.force[2][mi];
+    for (long long ai = oc.x; ai < oc.x + oc.y; ++ai)
+    {
+        const double rm = a.relMass[ai];
+        a.force[0][ai] += rm * fx;
+        a.force[1][ai] += rm * fy;
+        a.force[2][ai] += rm * fz;
+    }
+}
+
+__global__ void weightEvalKernel(mrmd_b200_weight w, const double* pos, int64_t n, double* lambda, double* modLambda,
+                                 double* grad)
+{
+    const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    double l, ml, gx, gy, gz;
+    weightEval(w, pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], l, ml, gx, gy, gz);
+    lambda[i] = l;
+    modLambda[i] = ml;
+    grad[3 * i] = gx;
+    grad[3 * i + 1] = gy;
+    grad[3 * i + 2] = gz;
+}
+
+// LJ_IdealGas::operator()(alpha, sumEnergy), LJ_IdealGas.cpp:52-225.  One thread per local molecule.
+// The partner's {lambda^mod, grad lambda} come in one 256-bit gather; CG-CG pairs leave after it.
+// hist: [0] compensationEnergy, [1] compensationEnergyCounter, [2] meanCompensationEnergy.
+template <bool SAMPLING>
+__global__ void __launch_bounds__(AD_THREADS)
+    adressForceKernel(MolsView m, AtomsView a, int64_t numLocalMols, const int32_t* __restrict__ counts,
+                      const int32_t* __restrict__ neigh, int64_t pitch, LJTable table, double rcSqr, int64_t numTypes,
+                      double* hist, double* partials, double* result, unsigned int* ticket)
+{
+    const int64_t alpha = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    double sumEnergy = 0.0, pairs = 0.0;
+    if (alpha < numLocalMols)
+    {
+        const int64_t T = numTypes;
+        double* compensationEnergy = hist;
+        double* compensationEnergyCounter = hist + COMPENSATION_ENERGY_BINS * T;
+        const double* meanCompensationEnergy = hist + 2 * COMPENSATION_ENERGY_BINS * T;
+        const double inverseBinSize = 1.0 / ((1.0 - 0.0) / double(COMPENSATION_ENERGY_BINS));
+
+        double fAx = 0.0, fAy = 0.0, fAz = 0.0;
+        const double4 wA = ld4nc(m.w + alpha);
+        const double modLambdaAlpha = wA.x;
+        const bool hyAlpha = inHY(modLambdaAlpha);
+        const bool cgAlpha = inCG(modLambdaAlpha);
+        long long binAlpha = -1;
+        if (hyAlpha) binAlpha = histBin(0.0, inverseBinSize, COMPENSATION_ENERGY_BINS, m.lambda[alpha]);
+        const longlong2 ocA = m.oc[alpha];
+        const long long startAlpha = ocA.x, endAlpha = ocA.x + ocA.y;
+
+        const int numNeighbors = counts[alpha];
+        const int32_t* row = neigh + alpha;
+        for (int n = 0; n < numNeighbors; ++n)
+        {
+            const int64_t beta = row[int64_t(n) * pitch];
+            const double4 wB = ld4nc(m.w + beta);
+            const double modLambdaBeta = wB.x;
+            if (cgAlpha && inCG(modLambdaBeta)) continue;  // ideal gas, :102-107
+            const double weighting = 0.5 * (modLambdaAlpha + modLambdaBeta);
+            const bool hyBeta = inHY(modLambdaBeta);
+            const bool drift = hyAlpha || hyBeta;
+            double fBx = 0.0, fBy = 0.0, fBz = 0.0;
+            const longlong2 ocB = m.oc[beta];
+            const long long startBeta = ocB.x, endBeta = ocB.x + ocB.y;
+            long long binBeta = -1;
+            if (SAMPLING && hyBeta) binBeta = histBin(0.0, inverseBinSize, COMPENSATION_ENERGY_BINS, m.lambda[beta]);
+
+            for (long long idx = startAlpha; idx < endAlpha; ++idx)
+            {
+                const double4 pi = ld4nc(a.pos + idx);
+                double fx = 0.0, fy = 0.0, fz = 0.0;
+                for (long long jdx = startBeta; jdx < endBeta; ++jdx)
+                {
+                    const double4 pj = ld4nc(a.pos + jdx);
+                    const double dx = pi.x - pj.x;
+                    const double dy = pi.y - pj.y;
+                    const double dz = pi.z - pj.z;
+                    const double distSqr = distSqrExact(dx, dy, dz);
+                    if (distSqr > rcSqr) continue;  // :137
+                    double ff, e;
+                    ljForceEnergy(table.t[typeOf(pi) * T + typeOf(pj)], distSqr, ff, e);
+                    const double ffactor = ff * weighting;
+                    pairs += 1.0;
+                    fx += dx * ffactor;
+                    fy += dy * ffactor;
+                    fz += dz * ffactor;
+                    atomicAdd(a.force[0] + jdx, -(dx * ffactor));
+                    atomicAdd(a.force[1] + jdx, -(dy * ffactor));
+                    atomicAdd(a.force[2] + jdx, -(dz * ffactor));
+                    sumEnergy += e * weighting;
+                    const double Vij = 0.5 * e;
+                    if (drift)
+                    {
+                        fAx += -Vij * wA.y;  // drift force, :163-169
+                        fAy += -Vij * wA.z;
+                        fAz += -Vij * wA.w;
+                        fBx += -Vij * wB.y;
+                        fBy += -Vij * wB.z;
+                        fBz += -Vij * wB.w;
+                        if (SAMPLING)
+                        {
+                            if (hyAlpha && binAlpha != -1) atomicAdd(compensationEnergy + binAlpha * T + typeOf(pi), Vij);
+                            if (hyBeta && binBeta != -1) atomicAdd(compensationEnergy + binBeta * T + typeOf(pj), Vij);
+                        }
+                    }
+                }
+                atomicAdd(a.force[0] + idx, fx);
+                atomicAdd(a.force[1] + idx, fy);
+                atomicAdd(a.force[2] + idx, fz);
+            }
+            if (fBx != 0.0 || fBy != 0.0 || fBz != 0.0)
+            {
+                atomicAdd(m.force[0] + beta, fBx);
+                atomicAdd(m.force[1] + beta, fBy);
+                atomicAdd(m.force[2] + beta, fBz);
+            }
+        }
+        if (SAMPLING && hyAlpha && binAlpha != -1)
+        {
+            // the reference increments non-atomically from a parallel loop (a race, LJ_IdealGas.cpp:207);
+            // atomics give the serial result
+            for (long long ai = startAlpha; ai < endAlpha; ++ai)
+                atomicAdd(compensationEnergyCounter + binAlpha * T + typeOf(ld4nc(a.pos + ai)), 1.0);
+        }
+        if (hyAlpha && binAlpha != -1)
+        {
+            const double mean = meanCompensationEnergy[binAlpha * T + typeOf(ld4nc(a.pos + startAlpha))];  // :212-220
+            fAx += mean * wA.y;
+            fAy += mean * wA.z;
+            fAz += mean * wA.w;
+        }
+        if (fAx != 0.0 || fAy != 0.0 || fAz != 0.0)
+        {
+            atomicAdd(m.force[0] + alpha, fAx);
+            atomicAdd(m.force[1] + alpha, fAy);
+            atomicAdd(m.force[2] + alpha, fAz);
+        }
+    }
+    gridReduce3<AD_THREADS>(sumEnergy, pairs, 0.0, partials, result, ticket);
+}
+
+// updateMeanCompensationEnergy, LJ_IdealGas.cpp:21-50 (runningAverageFactor = 10)
+__global__ void updateMeanCompensationKernel(double* hist, int64_t n, double runningAverageFactor)
+{
+    const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    double* energy = hist;
+    double* counter = hist + n;
+    double* mean = hist + 2 * n;
+    if (counter[i] < 0.5) return;
+    const double e = energy[i] / counter[i];
+    mean[i] = (runningAverageFactor * mean[i] + e) / (runningAverageFactor + 1.0);
+    energy[i] = 0.0;
+    counter[i] = 0.0;
+}
+}  // namespace mrmd_b200
+
+using namespace mrmd_b200;
+
+extern "C" {
+
+int mrmd_b200_molecules_update(mrmd_b200_molecules* m, const mrmd_b200_atoms* a, const mrmd_b200_weight* w, void* stream)
+{
+    MB_TRY(checkDevice());
+    MB_REQUIRE(m != nullptr && a != nullptr && w != nullptr, "molecules_update");
+    const int64_t n = m->numLocal + m->numGhost;
+    if (n == 0) return 0;
+    updateMoleculesKernel<<<gridFor(n, 256), 256, 0, S(stream)>>>(m->v, a->v, n, *w);
+    MB_LAUNCHED();
+    return 0;
+}
+
+int mrmd_b200_molecules_contribute_force(const mrmd_b200_molecules* m, mrmd_b200_atoms* a, void* stream)
+{
+    MB_TRY(checkDevice());
+    MB_REQUIRE(m != nullptr && a != nullptr, "molecules_contribute_force");
+    const int64_t n = m->numLocal + m->numGhost;
+    if (n == 0) return 0;
+    contributeMoleculeForceKernel<<<gridFor(n, 256), 256, 0, S(stream)>>>(m->v, a->v, n);
+    MB_LAUNCHED();
+    return 0;
+}
+
+int mrmd_b200_weight_eval(const mrmd_b200_weight* w, const double* posHost, int64_t n, double* lambdaHost,
+                          double* modLambdaHost, double* gradHost, void* stream)
+{
+    MB_TRY(checkDevice());
+    MB_REQUIRE(w && posHost && lambdaHost && modLambdaHost && gradHost && n >= 0, "weight_eval");
+    if (n == 0) return 0;
+    cudaStream_t st = S(stream);
+    double* d = nullptr;
+    MB_CUDA(cudaMalloc(&d, size_t(n) * 8 * 8));
+    MB_CUDA(cudaMemcpyAsync(d, posHost, size_t(n) * 24, cudaMemcpyHostToDevice, st));
+    weightEvalKernel<<<gridFor(n, 128), 128, 0, st>>>(*w, d, n, d + 3 * n, d + 4 * n, d + 5 * n);
+    g_launchCount.fetch_add(1);
+    cudaMemcpyAsync(lambdaHost, d + 3 * n, size_t(n) * 8, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(modLambdaHost, d + 4 * n, size_t(n) * 8, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(gradHost, d + 5 * n, size_t(n) * 24, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    MB_CUDA(e);
+    return 0;
+}
+
+int mrmd_b200_adress_create(mrmd_b200_adress** out, const double* cappingDistance, const double* rc,
+                            const double* sigma, const double* epsilon, int64_t numTypes, int doShift)
+{
+    MB_TRY(checkDevice());
+    MB_REQUIRE(out != nullptr, "adress_create");
+    auto* ad = new mrmd_b200_adress;
+    int rc_ = buildLJTable(ad->table, cappingDistance, rc, sigma, epsilon, numTypes, doShift, &ad->rcSqr);
+    const size_t histBytes = size_t(3) * COMPENSATION_ENERGY_BINS * size_t(std::max<int64_t>(numTypes, 1)) * 8;
+    if (rc_ == 0 && cudaMalloc(&ad->hist, histBytes) != cudaSuccess) rc_ = MRMD_B200_ENOMEM;
+    if (rc_ == 0 && cudaMalloc(&ad->dResult, 24) != cudaSuccess) rc_ = MRMD_B200_ENOMEM;
+    if (rc_ == 0 && cudaMalloc(&ad->dTicket, 4) != cudaSuccess) rc_ = MRMD_B200_ENOMEM;
+    if (rc_ == 0 && cudaMallocHost(&ad->hResult, 24) != cudaSuccess) rc_ = MRMD_B200_ENOMEM;
+    if (rc_ != 0)
+    {
+        delete ad;
+        return rc_;
+    }
+    cudaMemset(ad->hist, 0, histBytes);
+    cudaMemset(ad->dResult, 0, 24);
+    cudaMemset(ad->dTicket, 0, 4);
+    ad->numTypes = numTypes;
+    *out = ad;
+    return 0;
+}
+
+int mrmd_b200_adress_destroy(mrmd_b200_adress* ad)
+{
+    if (ad == nullptr) return 0;
+    cudaDeviceSynchronize();
+    if (ad->hist) cudaFree(ad->hist);
+    if (ad->dResult) cudaFree(ad->dResult);
+    if (ad->dTicket) cudaFree(ad->dTicket);
+    if (ad->hResult) cudaFreeHost(ad->hResult);
+    ad->partials.release();
+    delete ad;
+    return 0;
+}
+
+int mrmd_b200_adress_set_intervals(mrmd_b200_adress* ad, int64_t samplingInterval, int64_t updateInterval)
+{
+    MB_REQUIRE(ad != nullptr && samplingInterval > 0 && updateInterval > 0, "adress_set_intervals");
+    ad->samplingInterval = samplingInterval;
+    ad->updateInterval = updateInterval;
+    return 0;
+}
+
+// LJ_IdealGas::run, LJ_IdealGas.cpp:227-260
+int mrmd_b200_adress_run(mrmd_b200_adress* ad, mrmd_b200_molecules* m, const mrmd_b200_verlet* v, mrmd_b200_atoms* a,
+                         double* energy, int64_t* numPairs, void* stream)
+{
+    MB_TRY(checkDevice());
+    MB_REQUIRE(ad != nullptr && m != nullptr && v != nullptr && a != nullptr, "adress_run");
+    MB_REQUIRE(v->half == 1, "adress_run: LJ_IdealGas takes a half Verlet list of molecules");
+    MB_REQUIRE(m->numLocal <= v->numParticles || m->numLocal == 0, "adress_run: list has fewer rows than molecules");
+    cudaStream_t st = S(stream);
+    const bool sampling = (ad->runCounter % ad->samplingInterval) == 0;
+    MB_CUDA(cudaMemsetAsync(ad->dResult, 0, 24, st));
+    if (m->numLocal > 0)
+    {
+        const int blocks = gridFor(m->numLocal, AD_THREADS);
+        MB_TRY(ad->partials.reserve(size_t(blocks) * 3 * 8));
+        if (sampling)
+            adressForceKernel<true><<<blocks, AD_THREADS, 0, st>>>(
+                m->v, a->v, m->numLocal, v->counts.as<int32_t>(), v->neigh.as<int32_t>(), v->pitch, ad->table, ad->rcSqr,
+                ad->numTypes, ad->hist, ad->partials.as<double>(), ad->dResult, ad->dTicket);
+        else
+            adressForceKernel<false><<<blocks, AD_THREADS, 0, st>>>(
+                m->v, a->v, m->numLocal, v->counts.as<int32_t>(), v->neigh.as<int32_t>(), v->pitch, ad->table, ad->rcSqr,
+                ad->numTypes, ad->hist, ad->partials.as<double>(), ad->dResult, ad->dTicket);
+        MB_LAUNCHED();
+    }
+    if (ad->runCounter % ad->updateInterval == 0)
+    {
+        const int64_t n = COMPENSATION_ENERGY_BINS * ad->numTypes;
+        updateMeanCompensationKernel<<<gridFor(n, 128), 128, 0, st>>>(ad->hist, n, 10.0);
+        MB_LAUNCHED();
+    }
+    ad->runCounter += 1;
+    if (energy != nullptr || numPairs != nullptr)
+    {
+        MB_CUDA(cudaMemcpyAsync(ad->hResult, ad->dResult, 24, cudaMemcpyDeviceToHost, st));
+        MB_CUDA(cudaStreamSynchronize(st));
+        if (energy) *energy = ad->hResult[0];
+        if (numPairs) *numPairs = static_cast<int64_t>(ad->hResult[1] + 0.5);
+    }
+    return 0;
+}
+
+int mrmd_b200_adress_read_histogram(const mrmd_b200_adress* ad, int kind, double* dstHost, void* stream)
+{
+    MB_TRY(checkDevice());
+    MB_REQUIRE(ad != nullptr && dstHost != nullptr && kind >= 0 && kind <= 2, "adress_read_histogram");
+    const int64_t n = COMPENSATION_ENERGY_BINS * ad->numTypes;
+    const int slot = (kind == 0) ? 2 : (kind == 1 ? 0 : 1);
+    MB_CUDA(cudaMemcpyAsync(dstHost, ad->hist + slot * n, size_t(n) * 8, cudaMemcpyDeviceToHost, S(stream)));
+    MB_CUDA(cudaStreamSynchronize(S(stream)));
+    return 0;
+}
+
+}  // extern "C"
