@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- atom-steps/s (and pair-interactions/s) of the MRMD force + neighbour hot path on B200.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (hand-written sm_100a kernels via the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU path (OpenMP restatement: the
+                                                           reference itself needs Kokkos/Cabana, unbuildable offline)
+
+A "step" is one MD time step of the workload (pre-force integrate, ghost refresh or neighbour rebuild, force
+zero, LJ force, ghost fold-back, post-force integrate).  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "atom-steps/s"
+PHYS = dict(dt=0.002, rc=2.5, skin=0.1, sigma=1.0, epsilon=1.0, cap=0.7, max_neigh=60, zeta=20.0, temperature=1.5,
+            seed=1234)
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=2000)
+    p.add_argument("--warmup", type=int, default=300)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--side", type=int, default=100, help="lattice sites per box edge per GPU (100 -> 1M atoms)")
+    p.add_argument("--equil", type=int, default=300, help="untimed equilibration steps that melt the lattice")
+    p.add_argument("--full-list", type=int, default=0, help="1: FullVerletList fast path instead of the half list")
+    p.add_argument("--e2e-steps", type=int, default=100)
+    p.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    return p.parse_args()
+
+
+def env_rank():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the force kernel from the committed ncu capture, if any."""
+    path = os.path.join(ROOT, "profiles", "force_kernel_traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path))
+        except Exception:
+            pass
+    return None
+
+
+def cpu_loop(pos, vel, box, steps, warmup, threads):
+    """The reference path's OpenMP restatement on the host cores (oracle/ is only ever the baseline/checker)."""
+    from oracle import pyoracle as orc
+    from oracle.md_loop import OracleMD
+
+    orc.build()
+    orc.lib().or_set_threads(threads)
+    md = OracleMD(pos, vel, box, dt=PHYS["dt"], rc=PHYS["rc"], skin=PHYS["skin"], sigma=PHYS["sigma"],
+                  epsilon=PHYS["epsilon"], cap=PHYS["cap"], max_neigh=PHYS["max_neigh"], langevin=True,
+                  zeta=PHYS["zeta"], temperature=PHYS["temperature"], seed=PHYS["seed"], cell_sort=True)
+    md.run(warmup)
+    return md.run(steps), md
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    """--impl reference: rank 0 only; a bounded sample (smaller periodic system at the same state point) so that
+    --steps K --warmup W ends within a few minutes; atom-steps/s is size normalised."""
+    rank, _, world = env_rank()
+    if rank != 0:
+        return
+    from mrmd_b200.workloads import lattice_system
+
+    threads = host_threads()
+    # probe the host rate on a 32^3 system, then size the sample for ~150 s of CPU work
+    pos, vel, box = lattice_system(32)
+    probe, _ = cpu_loop(pos, vel, box, 6, 2, threads)
+    rate = 32 ** 3 * probe["steps"] / probe["seconds"]
+    budget_atoms = rate * 150.0 / max(args.steps + args.warmup, 1)
+    side = int(max(16, min(args.side, np.floor(budget_atoms ** (1.0 / 3.0)))))
+    pos, vel, box = lattice_system(side)
+    n = len(pos)
+    res, md = cpu_loop(pos, vel, box, args.steps, args.warmup, threads)
+    value = n * res["steps"] / res["seconds"]
+    sample = (f"periodic sc-lattice system of {n} atoms ({side}^3, same rho/T/dt/skin as the {args.side}^3 workload), "
+              f"{args.warmup} warm-up + {args.steps} timed steps, {res['rebuilds']} neighbour rebuilds")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "atom-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * res["seconds"] / max(res["steps"], 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, n_atoms_per_gpu=args.side ** 3),
+        "pair_interactions_per_s": res["pairInteractions"] / res["seconds"],
+        "cpu_baseline": {"value": value, "unit": "atom-steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "atom-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "OpenMP restatement of the reference path (Kokkos 4.7.1 / Cabana 0.7 un-vendored: the reference "
+                "cannot be built offline)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n_atoms_per_gpu):
+    return {
+        "workload": "Lennard-Jones NVT (examples/01 physics, examples/02 rebuild loop, tests/NVT spatial sort) scaled "
+                    "to 1M atoms per GPU: sc lattice, rho=0.512, rc=2.5 sigma, skin 0.1, r_cap 0.7, Langevin gamma=20 "
+                    "T=1.5, dt=0.002, maxNeighbors 60",
+        "atoms_per_gpu": n_atoms_per_gpu, "box_per_gpu": [args.side * 1.25] * 3, "equilibration_steps": args.equil,
+        "list": "full" if args.full_list else "half",
+        "l2": "inputs larger than L2 (per step: 104 B/atom state + neighbour table ~ 4 B x 19-38 slots/atom > 126 MB "
+              "at 1M atoms); no explicit flush",
+        "parallelism": "1 GPU" if args.gpus == 1 else f"{args.gpus} independent periodic replicas, one per GPU (x-slab "
+                                                       "halo exchange: see DESIGN.md multi-GPU status)",
+    }
+
+
+def run_b200(args):
+    import torch
+
+    rank, local_rank, world = env_rank()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from mrmd_b200 import api
+    from mrmd_b200.workloads import lattice_system
+
+    api.L().mrmd_b200_set_device(local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    pos, vel, box = lattice_system(args.side, seed=PHYS["seed"] + rank)
+    n = len(pos)
+    sub = api.Subdomain([0, 0, 0], box, PHYS["rc"] + PHYS["skin"])
+    atoms = api.Atoms.from_arrays(pos, vel, mass=1.0)
+
+    def make_md(a):
+        return api.MolecularDynamics(a, sub, dt=PHYS["dt"], rc=PHYS["rc"], skin=PHYS["skin"], sigma=PHYS["sigma"],
+                                     epsilon=PHYS["epsilon"], cappingDistance=PHYS["cap"],
+                                     maxNeighbors=PHYS["max_neigh"], langevin=True, zeta=PHYS["zeta"],
+                                     temperature=PHYS["temperature"], seed=PHYS["seed"], cellSort=True,
+                                     fullList=bool(args.full_list))
+
+    md = make_md(atoms)
+    md.run(args.equil, stream=stream)       # untimed: melt the lattice
+    md.run(max(args.warmup, 3), stream=stream)  # warm-up
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    launches0 = api.launch_count()
+    sampler.start()
+    ev0.record()
+    stats = md.run(args.steps, timeForceKernel=True, stream=stream)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = api.launch_count() - launches0
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms, float(stats["pairInteractions"]), float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        import torch.distributed as dist
+
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms_max, pairs_total = float(tmax[0]), float(tsum[1])
+    else:
+        ms_max, pairs_total = ms, float(stats["pairInteractions"])
+    value = world * n * args.steps / (ms_max * 1e-3)
+
+    # roofline of the dominant kernel (LJ force): algorithmic bytes 60 N + 52 P_stored per launch
+    peak, peak_src = measured_peak()
+    # the contract figure is the half-list one whichever variant is timed (a full list stores every pair twice)
+    stored_half = stats["storedPairs"] / (2.0 if args.full_list else 1.0)
+    algo_bytes = 60.0 * n * args.steps + 52.0 * stored_half
+    force_ms = stats["forceKernelMs"]
+    achieved = algo_bytes / (force_ms * 1e-3) / 1e9 if force_ms > 0 else None
+    traffic = ncu_traffic()
+    roofline = {
+        "bound": "hbm", "kernel": "ljForceKernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": (achieved / peak) if achieved else None, "peak_source": peak_src,
+        "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+        "algorithmic_bytes_per_launch": algo_bytes / args.steps,
+        "kernel_ms_per_launch": force_ms / args.steps, "kernel_share_of_step": force_ms / ms,
+        "stored_pairs_per_atom": stats["storedPairs"] / args.steps / n,
+    }
+
+    # end to end through the C ABI with HOST buffers: per step H2D pos+vel, one step, D2H pos+vel+scalars
+    e2e = None
+    if not args.no_e2e:
+        hpos, hvel, hsc = api.PinnedBuffer((n, 3)), api.PinnedBuffer((n, 3)), api.PinnedBuffer((3,))
+        hpos.array[:] = atoms.get("pos")[:n]
+        hvel.array[:] = atoms.get("vel")[:n]
+        md.run_host(3, hpos.ptr, hvel.ptr, hsc.ptr, stream=stream)
+        k = max(1, min(args.e2e_steps, args.steps))
+        barrier()
+        t0 = time.perf_counter()
+        md.run_host(k, hpos.ptr, hvel.ptr, hsc.ptr, stream=stream)
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * n * k / float(tt[0]), "unit": "atom-steps/s", "h2d_bytes_per_step": 48 * n,
+               "d2h_bytes_per_step": 48 * n + 24, "steps": k,
+               "path": "mrmd_b200_md_run_host: pinned host pos+vel -> device, one step, pos+vel+{E,virial,maxDisp} back"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = host_threads()
+        cpos, cvel = atoms.get("pos")[:n], atoms.get("vel")[:n]
+        t0 = time.perf_counter()
+        probe, omd = cpu_loop(cpos, cvel, box, 3, 1, threads)
+        per_step = probe["seconds"] / 3
+        more = int(max(3, min(200, (args.cpu_seconds - (time.perf_counter() - t0)) / max(per_step, 1e-6))))
+        res = omd.run(more)
+        cpu = {"value": n * res["steps"] / res["seconds"], "unit": "atom-steps/s", "cores": threads, "kind": "port",
+               "sample": f"{res['steps']} steps of the same 1M-atom state (downloaded from the GPU after the timed "
+                         f"region), {res['rebuilds']} rebuilds, OpenMP restatement of the reference path",
+               "pair_interactions_per_s": res["pairInteractions"] / res["seconds"]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "atom-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, n),
+            "pair_interactions_per_s": pairs_total / (ms_max * 1e-3),
+            "rebuild_interval_steps": args.steps / max(stats["rebuilds"], 1),
+            "ghosts_per_gpu": stats["numGhost"], "energy_per_atom": stats["energy"] / n,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -308,6 +308,60 @@ int mrmd_b200_thermo_density_ptr(mrmd_b200_thermo* t, double** devicePtr, int64_
 /* getMuLeft / getMuRight (ThermodynamicForce.cpp:98-130) */
 int mrmd_b200_thermo_mu(const mrmd_b200_thermo* t, double* muLeftHost, double* muRightHost, void* stream);
 
+/* ---- step loop of the reference's drivers ----------------------------------------------------
+ * The hot loop of examples/02_LennardJones_NVE.cpp:135-216 (rebuild policy :141-171), with the Langevin
+ * integrator of examples/01_LennardJones_NVT.cpp:121,142 and the LinkedCellList + permute spatial sort of
+ * tests/NVT/NVT.cpp:136-144 at every rebuild, as one host-side C++ driver so that the only per-step
+ * host<->device traffic is the displacement scalar the reference reads too.  AdResS mode assembles the
+ * step of SURVEY.md section 3.5 (UpdateMolecules -> LJ_IdealGas -> ThermodynamicForce ->
+ * ContributeMoleculeForceToAtoms -> MultiResGhostLayer) from the same operators. */
+typedef struct mrmd_b200_md mrmd_b200_md;
+typedef struct
+{
+    double dt;
+    double rc, skin;                /* neighborCutoff = rc + skin */
+    double sigma, epsilon, cappingDistance;
+    int64_t maxNeighbors;           /* estimatedMaxNeighbors */
+    int32_t integrator;             /* 0 VelocityVerlet, 1 VelocityVerletLangevinThermostat */
+    int32_t cellSort;               /* 1: LinkedCellList + permute at every rebuild (tests/NVT) */
+    int32_t fullList;               /* 0: HalfVerletList (reference), 1: FullVerletList fast path */
+    int32_t adress;                 /* 0: LennardJones::apply, 1: AdResS step (one molecule per atom) */
+    double zeta, temperature;       /* Langevin: gamma and T */
+    uint64_t seed;
+    /* AdResS only */
+    mrmd_b200_weight weight;
+    int32_t doShift;
+    int32_t useThermoForce;
+    double thermoTargetDensity, thermoBinWidth, thermoModulation;
+    int64_t thermoSampleInterval, thermoUpdateInterval;
+    double thermoSmoothingSigma, thermoSmoothingIntensity;
+} mrmd_b200_md_config;
+typedef struct
+{
+    int64_t steps;          /* steps executed by this call */
+    int64_t rebuilds;       /* neighbour rebuilds in this call */
+    int64_t pairInteractions; /* pairs that reached the force evaluation, summed over the steps */
+    int64_t storedPairs;    /* stored list pairs summed over the steps (roofline P) */
+    int64_t numLocal, numGhost;
+    double energy, virial;  /* of the last step */
+    double forceKernelMs;   /* CUDA-event time of the force kernel summed over the steps (0 if not timed) */
+    double maxDisplacement;
+} mrmd_b200_md_stats;
+
+int mrmd_b200_md_create(mrmd_b200_md** out, const mrmd_b200_md_config* cfg, const mrmd_b200_subdomain* s,
+                        mrmd_b200_atoms* atoms);
+int mrmd_b200_md_destroy(mrmd_b200_md* md);
+/* nsteps device-resident steps.  timeForceKernel != 0 brackets every force launch with CUDA events. */
+int mrmd_b200_md_run(mrmd_b200_md* md, int64_t nsteps, int timeForceKernel, mrmd_b200_md_stats* stats,
+                     void* stream);
+/* nsteps steps through HOST buffers: every step copies pos and vel (numLocal x 3 doubles each, pinned or
+ * pageable) to the device, runs one step and copies pos, vel and {energy, virial, maxDisplacement} back. */
+int mrmd_b200_md_run_host(mrmd_b200_md* md, int64_t nsteps, double* posHost, double* velHost,
+                          double* scalarsHost, mrmd_b200_md_stats* stats, void* stream);
+/* pinned host memory for the host-buffer path */
+int mrmd_b200_host_alloc(void** ptr, int64_t bytes);
+int mrmd_b200_host_free(void* ptr);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,6 +26,23 @@ class Weight(C.Structure):
                 ("hyRegion", C.c_double), ("exponent", C.c_int64)]
 
 
+class MdConfig(C.Structure):
+    _fields_ = [("dt", C.c_double), ("rc", C.c_double), ("skin", C.c_double), ("sigma", C.c_double),
+                ("epsilon", C.c_double), ("cappingDistance", C.c_double), ("maxNeighbors", C.c_int64),
+                ("integrator", C.c_int32), ("cellSort", C.c_int32), ("fullList", C.c_int32), ("adress", C.c_int32),
+                ("zeta", C.c_double), ("temperature", C.c_double), ("seed", C.c_uint64), ("weight", Weight),
+                ("doShift", C.c_int32), ("useThermoForce", C.c_int32), ("thermoTargetDensity", C.c_double),
+                ("thermoBinWidth", C.c_double), ("thermoModulation", C.c_double),
+                ("thermoSampleInterval", C.c_int64), ("thermoUpdateInterval", C.c_int64),
+                ("thermoSmoothingSigma", C.c_double), ("thermoSmoothingIntensity", C.c_double)]
+
+
+class MdStats(C.Structure):
+    _fields_ = [("steps", C.c_int64), ("rebuilds", C.c_int64), ("pairInteractions", C.c_int64),
+                ("storedPairs", C.c_int64), ("numLocal", C.c_int64), ("numGhost", C.c_int64), ("energy", C.c_double),
+                ("virial", C.c_double), ("forceKernelMs", C.c_double), ("maxDisplacement", C.c_double)]
+
+
 vp = C.c_void_p
 i64 = C.c_int64
 dbl = C.c_double
@@ -112,6 +129,12 @@ SIGNATURES = {
     "mrmd_b200_thermo_write_force": (C.c_int, [vp, vp, vp]),
     "mrmd_b200_thermo_density_ptr": (C.c_int, [vp, pvp, pi64]),
     "mrmd_b200_thermo_mu": (C.c_int, [vp, vp, vp, vp]),
+    "mrmd_b200_md_create": (C.c_int, [pvp, C.POINTER(MdConfig), pSub, vp]),
+    "mrmd_b200_md_destroy": (C.c_int, [vp]),
+    "mrmd_b200_md_run": (C.c_int, [vp, i64, C.c_int, C.POINTER(MdStats), vp]),
+    "mrmd_b200_md_run_host": (C.c_int, [vp, i64, vp, vp, vp, C.POINTER(MdStats), vp]),
+    "mrmd_b200_host_alloc": (C.c_int, [pvp, i64]),
+    "mrmd_b200_host_free": (C.c_int, [vp]),
 }
 
 

@@ -599,6 +599,67 @@ class ThermodynamicForce:
                 pass
 
 
+class MolecularDynamics:
+    """The step loop of examples/02 (rebuild policy), examples/01 (Langevin) and tests/NVT (spatial sort at
+    rebuild) as one C++ driver inside the library: mrmd_b200_md_* in include/mrmd_b200.h."""
+
+    def __init__(self, atoms, subdomain, dt=0.002, rc=2.5, skin=0.1, sigma=1.0, epsilon=1.0, cappingDistance=0.7,
+                 maxNeighbors=60, langevin=False, zeta=20.0, temperature=1.5, seed=1234, cellSort=True, fullList=False,
+                 adress=False, weight=None, doShift=True, thermo=None):
+        cfg = _lib.MdConfig()
+        cfg.dt, cfg.rc, cfg.skin, cfg.sigma, cfg.epsilon, cfg.cappingDistance = dt, rc, skin, sigma, epsilon, cappingDistance
+        cfg.maxNeighbors, cfg.integrator, cfg.cellSort, cfg.fullList = maxNeighbors, int(langevin), int(cellSort), int(fullList)
+        cfg.adress, cfg.zeta, cfg.temperature, cfg.seed, cfg.doShift = int(adress), zeta, temperature, seed, int(doShift)
+        if weight is not None:
+            C.memmove(C.byref(cfg.weight), C.byref(weight), C.sizeof(Weight))
+        if thermo is not None:
+            cfg.useThermoForce = 1
+            cfg.thermoTargetDensity, cfg.thermoBinWidth, cfg.thermoModulation = thermo["targetDensity"], thermo["binWidth"], thermo["modulation"]
+            cfg.thermoSampleInterval, cfg.thermoUpdateInterval = thermo["sampleInterval"], thermo["updateInterval"]
+            cfg.thermoSmoothingSigma, cfg.thermoSmoothingIntensity = thermo["sigma"], thermo["range"]
+        self.cfg, self.atoms, self.subdomain = cfg, atoms, subdomain
+        self.h = C.c_void_p()
+        check(L().mrmd_b200_md_create(C.byref(self.h), C.byref(cfg), C.byref(subdomain), atoms.h))
+
+    def run(self, nsteps, timeForceKernel=False, stream=None):
+        st = _lib.MdStats()
+        check(L().mrmd_b200_md_run(self.h, nsteps, int(timeForceKernel), C.byref(st), _stream(stream)))
+        return {f: getattr(st, f) for f, _ in st._fields_}
+
+    def run_host(self, nsteps, posHostPtr, velHostPtr, scalarsHostPtr=None, stream=None):
+        st = _lib.MdStats()
+        check(L().mrmd_b200_md_run_host(self.h, nsteps, posHostPtr, velHostPtr, scalarsHostPtr, C.byref(st), _stream(stream)))
+        return {f: getattr(st, f) for f, _ in st._fields_}
+
+    def __del__(self):
+        h, self.h = getattr(self, "h", None), None
+        if h:
+            try:
+                L().mrmd_b200_md_destroy(h)
+            except Exception:
+                pass
+
+
+class PinnedBuffer:
+    """cudaMallocHost-backed numpy array (host side of the host-buffer path)."""
+
+    def __init__(self, shape, dtype=np.float64):
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = C.c_void_p()
+        check(L().mrmd_b200_host_alloc(C.byref(self.ptr), self.nbytes))
+        buf = (C.c_char * self.nbytes).from_address(self.ptr.value)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def __del__(self):
+        p, self.ptr = getattr(self, "ptr", None), None
+        if p:
+            try:
+                self.array = None
+                L().mrmd_b200_host_free(p)
+            except Exception:
+                pass
+
+
 def sync(stream=None):
     check(L().mrmd_b200_sync(_stream(stream)))
 

@@ -6,22 +6,7 @@
 //            LJ_IdealGas.cpp:21-292, mrmd/action/ContributeMoleculeForceToAtoms.cpp:23-48, util/math.hpp:31-46.
 #include <algorithm>
 
-#include "common.cuh"
-
-struct mrmd_b200_adress
-{
-    int64_t numTypes = 1;
-    double rcSqr = 0.0;
-    mrmd_b200::LJTable table{};
-    int64_t runCounter = 0;
-    int64_t samplingInterval = 200;  // LJ_IdealGas.hpp:69
-    int64_t updateInterval = 20000;  // :70
-    double* hist = nullptr;          // 3 x (200 x numTypes): compensationEnergy, counter, mean
-    mrmd_b200::DevBuf partials;
-    double* dResult = nullptr;
-    unsigned int* dTicket = nullptr;
-    double* hResult = nullptr;
-};
+#include "handles.cuh"
 
 namespace mrmd_b200
 {
@@ -349,16 +334,16 @@ int mrmd_b200_adress_create(mrmd_b200_adress** out, const double* cappingDistanc
     int rc_ = buildLJTable(ad->table, cappingDistance, rc, sigma, epsilon, numTypes, doShift, &ad->rcSqr);
     const size_t histBytes = size_t(3) * COMPENSATION_ENERGY_BINS * size_t(std::max<int64_t>(numTypes, 1)) * 8;
     if (rc_ == 0 && cudaMalloc(&ad->hist, histBytes) != cudaSuccess) rc_ = MRMD_B200_ENOMEM;
-    if (rc_ == 0 && cudaMalloc(&ad->dResult, 24) != cudaSuccess) rc_ = MRMD_B200_ENOMEM;
+    if (rc_ == 0 && cudaMalloc(&ad->dResult, 48) != cudaSuccess) rc_ = MRMD_B200_ENOMEM;
     if (rc_ == 0 && cudaMalloc(&ad->dTicket, 4) != cudaSuccess) rc_ = MRMD_B200_ENOMEM;
-    if (rc_ == 0 && cudaMallocHost(&ad->hResult, 24) != cudaSuccess) rc_ = MRMD_B200_ENOMEM;
+    if (rc_ == 0 && cudaMallocHost(&ad->hResult, 48) != cudaSuccess) rc_ = MRMD_B200_ENOMEM;
     if (rc_ != 0)
     {
         delete ad;
         return rc_;
     }
     cudaMemset(ad->hist, 0, histBytes);
-    cudaMemset(ad->dResult, 0, 24);
+    cudaMemset(ad->dResult, 0, 48);
     cudaMemset(ad->dTicket, 0, 4);
     ad->numTypes = numTypes;
     *out = ad;

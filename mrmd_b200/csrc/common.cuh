@@ -328,7 +328,7 @@ __device__ __forceinline__ long long warpSumLL(long long v)
 
 // Deterministic grid-wide sum of three per-thread scalars: warp shuffle -> block -> per-block partial;
 // the last block to arrive (ticket counter) adds the partials in a fixed order and resets the ticket.
-// partials holds 3 * gridDim.x doubles, result 3 doubles.
+// partials holds 3 * gridDim.x doubles; result 6 doubles: [0..2] this launch, [3..5] running sums.
 template <int THREADS>
 __device__ __forceinline__ void gridReduce3(double e, double v, double c, double* partials, double* result,
                                             unsigned int* ticket)
@@ -385,6 +385,7 @@ __device__ __forceinline__ void gridReduce3(double e, double v, double c, double
             double s = 0;
             for (int w = 0; w < THREADS / 32; ++w) s += sRed[k][w];
             result[k] = s;
+            result[3 + k] += s;  // running sums over launches (pair-interactions/s numerator)
         }
         *ticket = 0;
     }

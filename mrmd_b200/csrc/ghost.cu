@@ -8,16 +8,8 @@
 // (shifted -L).  Selection and copy are fused: block counts -> one-block scan -> ranked copy, no atomics.
 #include <algorithm>
 
-#include "common.cuh"
+#include "handles.cuh"
 
-struct mrmd_b200_ghost
-{
-    int64_t* corr = nullptr;  // correspondingRealAtom, -1 for real atoms
-    int64_t corrCapacity = 0;
-    mrmd_b200::DevBuf blockCounts;  // int64[4 * numBlocks]
-    int64_t* dTotals = nullptr;     // int64[4]
-    int64_t* hTotals = nullptr;     // pinned
-};
 
 namespace mrmd_b200
 {

@@ -1,0 +1,55 @@
+// handles.cuh -- host-side state behind the opaque operator handles of include/mrmd_b200.h.
+#pragma once
+
+#include "common.cuh"
+
+struct mrmd_b200_ghost
+{
+    int64_t* corr = nullptr;  // correspondingRealAtom, -1 for real atoms
+    int64_t corrCapacity = 0;
+    mrmd_b200::DevBuf blockCounts;  // int64[4 * numBlocks]
+    int64_t* dTotals = nullptr;     // int64[4]
+    int64_t* hTotals = nullptr;     // pinned
+};
+
+struct mrmd_b200_lj
+{
+    int64_t numTypes = 1;
+    int64_t numTypesQuirk = 1;  // LennardJones::numTypes_ is hard-wired to 1 (LennardJones.cpp:52)
+    double rcSqr = 0.0;
+    mrmd_b200::LJTable table{};
+    mrmd_b200::DevBuf partials;  // double[3 * maxBlocks]
+    double* dResult = nullptr;   // [0..2] energy, virial, pairs of the last apply; [3..5] running sums
+    unsigned int* dTicket = nullptr;
+    double* hResult = nullptr;  // pinned, 6 doubles
+};
+
+struct mrmd_b200_adress
+{
+    int64_t numTypes = 1;
+    double rcSqr = 0.0;
+    mrmd_b200::LJTable table{};
+    int64_t runCounter = 0;
+    int64_t samplingInterval = 200;  // LJ_IdealGas.hpp:69
+    int64_t updateInterval = 20000;  // :70
+    double* hist = nullptr;          // 3 x (200 x numTypes): compensationEnergy, counter, mean
+    mrmd_b200::DevBuf partials;
+    double* dResult = nullptr;  // [0..2] energy, pairs, - of the last run; [3..5] running sums
+    unsigned int* dTicket = nullptr;
+    double* hResult = nullptr;
+};
+
+struct mrmd_b200_thermo
+{
+    double min = 0, max = 0;
+    int64_t numBins = 0, numTypes = 0;
+    double binSize = 0, inverseBinSize = 0;
+    double binVolume = 0;
+    int64_t samples = 0;
+    int enforceSymmetry = 0, usePeriodicity = 0;
+    double* force = nullptr;        // numBins x numTypes
+    double* density = nullptr;      // numBins x numTypes
+    double* tmpA = nullptr;
+    double* tmpB = nullptr;
+    double* forceFactor = nullptr;  // numTypes
+};

@@ -11,19 +11,7 @@
 #include <algorithm>
 #include <vector>
 
-#include "common.cuh"
-
-struct mrmd_b200_lj
-{
-    int64_t numTypes = 1;
-    int64_t numTypesQuirk = 1;  // LennardJones::numTypes_ is hard-wired to 1 (LennardJones.cpp:52)
-    double rcSqr = 0.0;
-    mrmd_b200::LJTable table{};
-    mrmd_b200::DevBuf partials;  // double[3 * maxBlocks]
-    double* dResult = nullptr;   // energy, virial, pairs
-    unsigned int* dTicket = nullptr;
-    double* hResult = nullptr;  // pinned
-};
+#include "handles.cuh"
 
 namespace mrmd_b200
 {
@@ -170,15 +158,15 @@ int mrmd_b200_lj_create(mrmd_b200_lj** out, const double* cappingDistance, const
     MB_REQUIRE(out != nullptr, "lj_create");
     auto* lj = new mrmd_b200_lj;
     int rc_ = buildLJTable(lj->table, cappingDistance, rc, sigma, epsilon, numTypes, isShifted, &lj->rcSqr);
-    if (rc_ == 0 && cudaMalloc(&lj->dResult, 24) != cudaSuccess) rc_ = MRMD_B200_ENOMEM;
+    if (rc_ == 0 && cudaMalloc(&lj->dResult, 48) != cudaSuccess) rc_ = MRMD_B200_ENOMEM;
     if (rc_ == 0 && cudaMalloc(&lj->dTicket, 4) != cudaSuccess) rc_ = MRMD_B200_ENOMEM;
-    if (rc_ == 0 && cudaMallocHost(&lj->hResult, 24) != cudaSuccess) rc_ = MRMD_B200_ENOMEM;
+    if (rc_ == 0 && cudaMallocHost(&lj->hResult, 48) != cudaSuccess) rc_ = MRMD_B200_ENOMEM;
     if (rc_ != 0)
     {
         delete lj;
         return rc_;
     }
-    cudaMemset(lj->dResult, 0, 24);
+    cudaMemset(lj->dResult, 0, 48);
     cudaMemset(lj->dTicket, 0, 4);
     lj->numTypes = numTypes;
     *out = lj;

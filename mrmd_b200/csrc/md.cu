@@ -1,0 +1,318 @@
+// md.cu -- the step loop of the reference's drivers as one host-side C++ driver over the operators of
+// this library (no new arithmetic).  Reference: examples/02_LennardJones_NVE/02_LennardJones_NVE.cpp:135-216
+// (rebuild policy :141-171), examples/01_LennardJones_NVT/01_LennardJones_NVT.cpp:121,142 (Langevin),
+// tests/NVT/NVT.cpp:136-144 (LinkedCellList + permute at rebuild), and the AdResS step assembled from the
+// unit-test usage of the operators.
+#include <algorithm>
+#include <cfloat>
+#include <vector>
+
+#include "handles.cuh"
+
+struct mrmd_b200_md
+{
+    mrmd_b200_md_config cfg{};
+    mrmd_b200_subdomain sub{};
+    mrmd_b200_atoms* atoms = nullptr;  // not owned
+    mrmd_b200_molecules* mols = nullptr;
+    mrmd_b200_ghost* ghost = nullptr;
+    mrmd_b200_verlet* list = nullptr;
+    mrmd_b200_lj* lj = nullptr;
+    mrmd_b200_adress* adress = nullptr;
+    mrmd_b200_thermo* thermo = nullptr;
+    double maxDisplacement = DBL_MAX;  // examples/02:110
+    int64_t step = 0;
+    int64_t rebuilds = 0;
+    int64_t storedPairsNow = 0;
+    std::vector<cudaEvent_t> events;
+};
+
+namespace mrmd_b200
+{
+__global__ void moleculePerAtomInitKernel(MolsView m, int64_t n)
+{
+    const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (i < n) m.oc[i] = make_longlong2(i, 1);
+}
+
+static int rebuild(mrmd_b200_md* md, cudaStream_t st)
+{
+    const mrmd_b200_md_config& c = md->cfg;
+    mrmd_b200_atoms* a = md->atoms;
+    const double cutoff = c.rc + c.skin;
+    const double delta[3] = {cutoff, cutoff, cutoff};
+    if (c.adress)
+    {
+        // MultiResGhostLayer::exchangeRealAtoms (needs the current centres of mass),
+        // optional spatial sort, MultiResGhostLayer::createGhostAtoms, molecule Verlet list on the COMs.
+        mrmd_b200_molecules* m = md->mols;
+        m->numGhost = 0;
+        m->size = m->numLocal;
+        a->numGhost = 0;
+        a->size = a->numLocal;
+        MB_TRY(mrmd_b200_molecules_update(m, a, &c.weight, st));
+        MB_TRY(mrmd_b200_ghost_mr_map_into_domain(m, a, &md->sub, st));
+        if (c.cellSort)
+        {
+            // one atom per molecule (data::createMoleculeForEachAtom): sorting the atoms sorts the molecules
+            MB_TRY(mrmd_b200_atoms_cell_sort(a, 0, a->numLocal, delta, md->sub.minCorner, md->sub.maxCorner, nullptr, st));
+            MB_TRY(mrmd_b200_molecules_update(m, a, &c.weight, st));
+        }
+        MB_TRY(mrmd_b200_ghost_mr_create_atoms(md->ghost, m, a, &md->sub, -1, st));
+        MB_TRY(mrmd_b200_molecules_update(m, a, &c.weight, st));
+        MB_TRY(mrmd_b200_verlet_build_molecules(md->list, m, 0, m->numLocal, cutoff, 1.0, md->sub.minGhostCorner,
+                                                md->sub.maxGhostCorner, c.maxNeighbors, st));
+    }
+    else
+    {
+        MB_TRY(mrmd_b200_ghost_map_into_domain(a, &md->sub, st));  // ghostLayer.exchangeRealAtoms (examples/02:150)
+        a->numGhost = 0;
+        a->size = a->numLocal;
+        if (c.cellSort)  // tests/NVT/NVT.cpp:136-144
+            MB_TRY(mrmd_b200_atoms_cell_sort(a, 0, a->numLocal, delta, md->sub.minCorner, md->sub.maxCorner, nullptr, st));
+        MB_TRY(mrmd_b200_ghost_create_atoms(md->ghost, a, &md->sub, -1, st));  // examples/02:153
+        MB_TRY(mrmd_b200_verlet_build_atoms(md->list, a, 0, a->numLocal, cutoff, 1.0, md->sub.minGhostCorner,
+                                            md->sub.maxGhostCorner, c.maxNeighbors, st));  // examples/02:156-163
+    }
+    int64_t total = 0;
+    MB_TRY(mrmd_b200_verlet_info(md->list, nullptr, nullptr, &total, nullptr));
+    md->storedPairsNow = total;
+    md->rebuilds += 1;
+    return 0;
+}
+
+// one step; evStart/evStop (optional) bracket the force kernel
+static int oneStep(mrmd_b200_md* md, cudaStream_t st, cudaEvent_t evStart, cudaEvent_t evStop, bool needRebuildHint)
+{
+    const mrmd_b200_md_config& c = md->cfg;
+    mrmd_b200_atoms* a = md->atoms;
+    double disp = 0.0;
+    if (c.integrator == 1)
+        MB_TRY(mrmd_b200_langevin_pre(a, c.dt, c.zeta, c.temperature, c.seed, uint64_t(md->step), nullptr, &disp, st));
+    else
+        MB_TRY(mrmd_b200_vv_pre(a, c.dt, &disp, st));
+    md->maxDisplacement += disp;  // examples/02:138
+    if (needRebuildHint || md->maxDisplacement >= c.skin * 0.5)  // :141-143
+    {
+        md->maxDisplacement = 0.0;
+        MB_TRY(rebuild(md, st));
+    }
+    else
+    {
+        MB_TRY(mrmd_b200_ghost_update(md->ghost, a, &md->sub, st));  // :170
+        if (c.adress) MB_TRY(mrmd_b200_molecules_update(md->mols, a, &c.weight, st));
+    }
+    MB_TRY(mrmd_b200_atoms_fill(a, MRMD_B200_ATOM_FORCE, 0.0, st));  // :174-175
+    if (c.adress)
+    {
+        MB_TRY(mrmd_b200_molecules_fill(md->mols, MRMD_B200_MOL_FORCE, 0.0, st));
+        if (evStart) MB_CUDA(cudaEventRecord(evStart, st));
+        MB_TRY(mrmd_b200_adress_run(md->adress, md->mols, md->list, a, nullptr, nullptr, st));
+        if (evStop) MB_CUDA(cudaEventRecord(evStop, st));
+        if (md->thermo != nullptr)
+        {
+            if (c.thermoSampleInterval > 0 && md->step % c.thermoSampleInterval == 0)
+                MB_TRY(mrmd_b200_thermo_sample(md->thermo, a, st));
+            if (c.thermoUpdateInterval > 0 && md->step > 0 && md->step % c.thermoUpdateInterval == 0 &&
+                md->thermo->samples > 0)
+                MB_TRY(mrmd_b200_thermo_update(md->thermo, c.thermoSmoothingSigma, c.thermoSmoothingIntensity, nullptr, st));
+            MB_TRY(mrmd_b200_thermo_apply(md->thermo, a, nullptr, 0, st));
+        }
+        MB_TRY(mrmd_b200_molecules_contribute_force(md->mols, a, st));
+        MB_TRY(mrmd_b200_ghost_contribute_back(md->ghost, a, st));
+    }
+    else
+    {
+        if (evStart) MB_CUDA(cudaEventRecord(evStart, st));
+        MB_TRY(mrmd_b200_lj_apply(md->lj, a, md->list, nullptr, st));  // :178
+        if (evStop) MB_CUDA(cudaEventRecord(evStop, st));
+        if (!c.fullList) MB_TRY(mrmd_b200_ghost_contribute_back(md->ghost, a, st));  // :181 (no-op for a full list)
+    }
+    MB_TRY(mrmd_b200_vv_post(a, c.dt, st));  // :184
+    md->step += 1;
+    return 0;
+}
+
+static int collectStats(mrmd_b200_md* md, int64_t nsteps, int64_t rebuilds0, int64_t storedSum, double pairs0,
+                        int nTimed, mrmd_b200_md_stats* stats, cudaStream_t st)
+{
+    double* dRes = md->cfg.adress ? md->adress->dResult : md->lj->dResult;
+    double* hRes = md->cfg.adress ? md->adress->hResult : md->lj->hResult;
+    MB_CUDA(cudaMemcpyAsync(hRes, dRes, 48, cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaStreamSynchronize(st));
+    if (stats == nullptr) return 0;
+    stats->steps = nsteps;
+    stats->rebuilds = md->rebuilds - rebuilds0;
+    stats->storedPairs = storedSum;
+    stats->numLocal = md->atoms->numLocal;
+    stats->numGhost = md->atoms->numGhost;
+    stats->maxDisplacement = md->maxDisplacement;
+    if (md->cfg.adress)
+    {
+        stats->energy = hRes[0];
+        stats->virial = 0.0;
+        stats->pairInteractions = static_cast<int64_t>(hRes[4] - pairs0 + 0.5);
+    }
+    else
+    {
+        stats->energy = hRes[0];
+        stats->virial = hRes[1];
+        stats->pairInteractions = static_cast<int64_t>(hRes[5] - pairs0 + 0.5);
+    }
+    double ms = 0.0;
+    for (int i = 0; i < nTimed; ++i)
+    {
+        float t = 0.f;
+        MB_CUDA(cudaEventElapsedTime(&t, md->events[2 * i], md->events[2 * i + 1]));
+        ms += t;
+    }
+    stats->forceKernelMs = ms;
+    return 0;
+}
+
+static int runningPairs(mrmd_b200_md* md, double* out, cudaStream_t st)
+{
+    double* dRes = md->cfg.adress ? md->adress->dResult : md->lj->dResult;
+    double* hRes = md->cfg.adress ? md->adress->hResult : md->lj->hResult;
+    MB_CUDA(cudaMemcpyAsync(hRes, dRes, 48, cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaStreamSynchronize(st));
+    *out = md->cfg.adress ? hRes[4] : hRes[5];
+    return 0;
+}
+}  // namespace mrmd_b200
+
+using namespace mrmd_b200;
+
+extern "C" {
+
+int mrmd_b200_md_create(mrmd_b200_md** out, const mrmd_b200_md_config* cfg, const mrmd_b200_subdomain* s,
+                        mrmd_b200_atoms* atoms)
+{
+    MB_TRY(checkDevice());
+    MB_REQUIRE(out != nullptr && cfg != nullptr && s != nullptr && atoms != nullptr, "md_create");
+    MB_REQUIRE(cfg->dt > 0.0 && cfg->rc > 0.0 && cfg->skin >= 0.0 && cfg->maxNeighbors > 0, "md_create: bad config");
+    MB_REQUIRE(!(cfg->adress && cfg->fullList), "md_create: LJ_IdealGas takes a half list");
+    auto* md = new mrmd_b200_md;
+    md->cfg = *cfg;
+    md->sub = *s;
+    md->atoms = atoms;
+    int rc = mrmd_b200_ghost_create(&md->ghost);
+    if (rc == 0) rc = mrmd_b200_verlet_create(&md->list, cfg->fullList ? 0 : 1);
+    if (rc == 0 && !cfg->adress)
+        rc = mrmd_b200_lj_create(&md->lj, &cfg->cappingDistance, &cfg->rc, &cfg->sigma, &cfg->epsilon, 1, 0);
+    if (rc == 0 && cfg->adress)
+    {
+        rc = mrmd_b200_adress_create(&md->adress, &cfg->cappingDistance, &cfg->rc, &cfg->sigma, &cfg->epsilon, 1,
+                                     cfg->doShift);
+        if (rc == 0) rc = mrmd_b200_molecules_create(&md->mols, std::max<int64_t>(atoms->numLocal, 1));
+        if (rc == 0 && atoms->numLocal > 0)
+        {
+            // data::createMoleculeForEachAtom (data/MoleculesFromAtoms.cpp:19-39) for the local atoms
+            md->mols->size = atoms->numLocal;
+            md->mols->numLocal = atoms->numLocal;
+            moleculePerAtomInitKernel<<<gridFor(atoms->numLocal, 256), 256>>>(md->mols->v, atoms->numLocal);
+            g_launchCount.fetch_add(1);
+            if (cudaDeviceSynchronize() != cudaSuccess) rc = MRMD_B200_EINVAL;
+        }
+        if (rc == 0 && cfg->useThermoForce)
+            rc = mrmd_b200_thermo_create(&md->thermo, &cfg->thermoTargetDensity, 1, s, cfg->thermoBinWidth,
+                                         &cfg->thermoModulation, 0, 0);
+    }
+    if (rc != 0)
+    {
+        mrmd_b200_md_destroy(md);
+        return rc;
+    }
+    *out = md;
+    return 0;
+}
+
+int mrmd_b200_md_destroy(mrmd_b200_md* md)
+{
+    if (md == nullptr) return 0;
+    cudaDeviceSynchronize();
+    for (auto e : md->events) cudaEventDestroy(e);
+    mrmd_b200_ghost_destroy(md->ghost);
+    mrmd_b200_verlet_destroy(md->list);
+    mrmd_b200_lj_destroy(md->lj);
+    mrmd_b200_adress_destroy(md->adress);
+    mrmd_b200_thermo_destroy(md->thermo);
+    mrmd_b200_molecules_destroy(md->mols);
+    delete md;
+    return 0;
+}
+
+int mrmd_b200_md_run(mrmd_b200_md* md, int64_t nsteps, int timeForceKernel, mrmd_b200_md_stats* stats, void* stream)
+{
+    MB_TRY(checkDevice());
+    MB_REQUIRE(md != nullptr && nsteps >= 0, "md_run");
+    cudaStream_t st = S(stream);
+    const int64_t rebuilds0 = md->rebuilds;
+    double pairs0 = 0.0;
+    MB_TRY(runningPairs(md, &pairs0, st));
+    const int nTimed = timeForceKernel ? static_cast<int>(std::min<int64_t>(nsteps, 1 << 16)) : 0;
+    while (static_cast<int>(md->events.size()) < 2 * nTimed)
+    {
+        cudaEvent_t e;
+        MB_CUDA(cudaEventCreate(&e));
+        md->events.push_back(e);
+    }
+    int64_t storedSum = 0;
+    for (int64_t i = 0; i < nsteps; ++i)
+    {
+        cudaEvent_t e0 = (i < nTimed) ? md->events[2 * i] : nullptr;
+        cudaEvent_t e1 = (i < nTimed) ? md->events[2 * i + 1] : nullptr;
+        MB_TRY(oneStep(md, st, e0, e1, false));
+        storedSum += md->storedPairsNow;
+    }
+    return collectStats(md, nsteps, rebuilds0, storedSum, pairs0, nTimed, stats, st);
+}
+
+int mrmd_b200_md_run_host(mrmd_b200_md* md, int64_t nsteps, double* posHost, double* velHost, double* scalarsHost,
+                          mrmd_b200_md_stats* stats, void* stream)
+{
+    MB_TRY(checkDevice());
+    MB_REQUIRE(md != nullptr && nsteps >= 0 && posHost != nullptr && velHost != nullptr, "md_run_host");
+    cudaStream_t st = S(stream);
+    mrmd_b200_atoms* a = md->atoms;
+    const int64_t rebuilds0 = md->rebuilds;
+    double pairs0 = 0.0;
+    MB_TRY(runningPairs(md, &pairs0, st));
+    int64_t storedSum = 0;
+    const int64_t n = a->numLocal;
+    for (int64_t i = 0; i < nsteps; ++i)
+    {
+        // host -> device: this step's inputs
+        MB_TRY(mrmd_b200_atoms_write(a, MRMD_B200_ATOM_POS, posHost, 0, n, 3, 1, MRMD_B200_MEM_HOST, st));
+        MB_TRY(mrmd_b200_atoms_write(a, MRMD_B200_ATOM_VEL, velHost, 0, n, 3, 1, MRMD_B200_MEM_HOST, st));
+        MB_TRY(oneStep(md, st, nullptr, nullptr, false));
+        storedSum += md->storedPairsNow;
+        // device -> host: the step's results
+        MB_TRY(mrmd_b200_atoms_read(a, MRMD_B200_ATOM_POS, posHost, 0, n, 3, 1, MRMD_B200_MEM_HOST, st));
+        MB_TRY(mrmd_b200_atoms_read(a, MRMD_B200_ATOM_VEL, velHost, 0, n, 3, 1, MRMD_B200_MEM_HOST, st));
+        if (scalarsHost != nullptr)
+        {
+            double* dRes = md->cfg.adress ? md->adress->dResult : md->lj->dResult;
+            MB_CUDA(cudaMemcpyAsync(scalarsHost, dRes, 16, cudaMemcpyDeviceToHost, st));
+            MB_CUDA(cudaStreamSynchronize(st));
+            scalarsHost[2] = md->maxDisplacement;
+        }
+    }
+    return collectStats(md, nsteps, rebuilds0, storedSum, pairs0, 0, stats, st);
+}
+
+int mrmd_b200_host_alloc(void** ptr, int64_t bytes)
+{
+    MB_TRY(checkDevice());
+    MB_REQUIRE(ptr != nullptr && bytes >= 0, "host_alloc");
+    MB_CUDA(cudaMallocHost(ptr, size_t(std::max<int64_t>(bytes, 1))));
+    return 0;
+}
+
+int mrmd_b200_host_free(void* ptr)
+{
+    if (ptr != nullptr) cudaFreeHost(ptr);
+    return 0;
+}
+
+}  // extern "C"

@@ -6,22 +6,8 @@
 #include <cmath>
 #include <vector>
 
-#include "common.cuh"
+#include "handles.cuh"
 
-struct mrmd_b200_thermo
-{
-    double min = 0, max = 0;
-    int64_t numBins = 0, numTypes = 0;
-    double binSize = 0, inverseBinSize = 0;
-    double binVolume = 0;
-    int64_t samples = 0;
-    int enforceSymmetry = 0, usePeriodicity = 0;
-    double* force = nullptr;        // numBins x numTypes
-    double* density = nullptr;      // numBins x numTypes
-    double* tmpA = nullptr;
-    double* tmpB = nullptr;
-    double* forceFactor = nullptr;  // numTypes
-};
 
 namespace mrmd_b200
 {

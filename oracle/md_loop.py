@@ -1,0 +1,90 @@
+"""The reference's step loop driven through the CPU oracle (TEST INFRASTRUCTURE / CPU baseline only).
+
+Same loop as mrmd_b200/csrc/md.cu: examples/02_LennardJones_NVE.cpp:135-216 with the Langevin integrator of
+examples/01 and the LinkedCellList + permute of tests/NVT/NVT.cpp:136-144 at every rebuild.  Used by
+bench.py (cpu_baseline leg and --impl reference) and by tests/; never by the product.
+"""
+import ctypes as C
+import time
+
+import numpy as np
+
+from . import pyoracle as orc
+
+
+class OracleMD:
+    def __init__(self, pos, vel, box, dt=0.002, rc=2.5, skin=0.1, sigma=1.0, epsilon=1.0, cap=0.7, max_neigh=60,
+                 langevin=False, zeta=20.0, temperature=1.5, seed=1234, cell_sort=True, ghost_capacity_factor=None):
+        self.L = orc.lib()
+        self.n = n = len(pos)
+        self.box = np.asarray(box, dtype=np.float64)
+        self.cutoff = rc + skin
+        self.sub = orc.subdomain([0, 0, 0], self.box, self.cutoff)
+        frac = float(np.prod(self.box + 2 * self.cutoff) / np.prod(self.box)) - 1.0
+        cap_atoms = int(n * (1.0 + (ghost_capacity_factor or (1.3 * frac + 0.05)))) + 1024
+        self.atoms = np.zeros(cap_atoms, dtype=orc.ATOM)
+        self.atoms["pos"][:n] = pos
+        self.atoms["vel"][:n] = vel
+        self.atoms["mass"][:n] = 1.0
+        self.atoms["relMass"][:n] = 1.0
+        self.corr = np.full(cap_atoms, -1, dtype=np.int64)
+        self.table = orc.lj_table(cap, rc, sigma, epsilon)
+        self.rc, self.skin, self.dt = rc, skin, dt
+        self.langevin, self.zeta, self.temperature, self.seed = langevin, zeta, temperature, seed
+        self.cell_sort, self.max_neigh = cell_sort, max_neigh
+        self.max_disp = np.finfo(np.float64).max
+        self.step = 0
+        self.ng = 0
+        self.counts = self.neigh = None
+        self.rebuilds = 0
+        self.pairs = 0
+        self.energy_virial = np.zeros(2)
+        self._cid = np.zeros(n, dtype=np.int32)
+        self._perm = np.zeros(n, dtype=np.int64)
+
+    def _rebuild(self):
+        L, a, n = self.L, self.atoms, self.n
+        L.or_periodic_map(a.ctypes.data, n, C.byref(self.sub))
+        if self.cell_sort:
+            delta = np.full(3, self.cutoff)
+            lo, hi = np.zeros(3), self.box
+            nc = L.or_cell_ids(a.ctypes.data, 13, 0, n, delta.ctypes.data, lo.ctypes.data, hi.ctypes.data,
+                               self._cid.ctypes.data, None)
+            off = np.zeros(nc + 1, dtype=np.int64)
+            L.or_cell_perm(self._cid.ctypes.data, 0, n, nc, self._perm.ctypes.data, off.ctypes.data)
+            L.or_permute_atoms(a.ctypes.data, 0, n, self._perm.ctypes.data)
+        self.ng = L.or_ghost_create_xyz(a.ctypes.data, n, len(a), C.byref(self.sub), self.corr.ctypes.data)
+        assert self.ng >= 0, "oracle ghost capacity exceeded"
+        self.counts, self.neigh = orc.verlet_build(a, 13, n + self.ng, 0, n, self.cutoff, 1.0,
+                                                   np.array(self.sub.minGhostCorner), np.array(self.sub.maxGhostCorner),
+                                                   half=True, width=self.max_neigh)
+        self.rebuilds += 1
+
+    def one_step(self):
+        L, a, n = self.L, self.atoms, self.n
+        if self.langevin:
+            d = L.or_langevin_pre(a.ctypes.data, n, self.dt, self.zeta, self.temperature, self.seed, self.step, None)
+        else:
+            d = L.or_vv_pre(a.ctypes.data, n, self.dt)
+        self.max_disp += d
+        if self.max_disp >= self.skin * 0.5:
+            self.max_disp = 0.0
+            self._rebuild()
+        else:
+            L.or_ghost_update_pos(a.ctypes.data, n, self.ng, self.corr.ctypes.data, C.byref(self.sub))
+        L.or_zero_force(a.ctypes.data, n + self.ng)
+        self.pairs += L.or_lj_apply(a.ctypes.data, n, self.counts.ctypes.data, self.neigh.ctypes.data,
+                                    self.neigh.shape[1], C.addressof(self.table), self.rc * self.rc, 1, None,
+                                    self.energy_virial.ctypes.data)
+        L.or_ghost_fold_force(a.ctypes.data, n, self.ng, self.corr.ctypes.data)
+        L.or_vv_post(a.ctypes.data, n, self.dt)
+        self.step += 1
+
+    def run(self, nsteps):
+        t0 = time.perf_counter()
+        p0, r0 = self.pairs, self.rebuilds
+        for _ in range(nsteps):
+            self.one_step()
+        dt = time.perf_counter() - t0
+        return {"seconds": dt, "steps": nsteps, "pairInteractions": self.pairs - p0, "rebuilds": self.rebuilds - r0,
+                "energy": float(self.energy_virial[0])}

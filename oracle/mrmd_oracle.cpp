@@ -526,6 +526,13 @@ void or_ghost_update_pos(or_atom_t* atoms, int64_t numLocal, int64_t numGhost, c
     }
 }
 
+// Cabana::deep_copy(force, 0) of the drivers (examples/02_LennardJones_NVE.cpp:174-175)
+void or_zero_force(or_atom_t* atoms, int64_t n)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) atoms[i].force[0] = atoms[i].force[1] = atoms[i].force[2] = 0.0;
+}
+
 // communication/AccumulateForce.cpp:25-47
 void or_ghost_fold_force(or_atom_t* atoms, int64_t numLocal, int64_t numGhost, const int64_t* corr)
 {

@@ -159,6 +159,7 @@ int64_t or_ghost_create_xyz(or_atom_t* atoms, int64_t numLocal, int64_t capacity
 void or_ghost_update_pos(or_atom_t* atoms, int64_t numLocal, int64_t numGhost, const int64_t* corr,
                          const or_subdomain_t* s);
 void or_ghost_fold_force(or_atom_t* atoms, int64_t numLocal, int64_t numGhost, const int64_t* corr);
+void or_zero_force(or_atom_t* atoms, int64_t n);
 
 /* multi-resolution (molecule granular) variants */
 void or_mr_periodic_map(or_molecule_t* mols, int64_t numLocalMols, or_atom_t* atoms, const or_subdomain_t* s);

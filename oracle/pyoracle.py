@@ -106,6 +106,7 @@ def lib():
         "or_ghost_create_xyz": (i64, [vp, i64, i64, C.POINTER(Subdomain), vp]),
         "or_ghost_update_pos": (None, [vp, i64, i64, vp, C.POINTER(Subdomain)]),
         "or_ghost_fold_force": (None, [vp, i64, i64, vp]),
+        "or_zero_force": (None, [vp, i64]),
         "or_mr_periodic_map": (None, [vp, i64, vp, C.POINTER(Subdomain)]),
         "or_mr_ghost_create_axis": (C.c_int, [vp, i64, i64, i64, vp, i64, i64, i64, C.POINTER(Subdomain), C.c_int,
                                               vp, vp]),
