@@ -33,7 +33,7 @@ def parse_args():
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--side", type=int, default=100, help="lattice sites per box edge per GPU (100 -> 1M atoms)")
     p.add_argument("--equil", type=int, default=300, help="untimed equilibration steps that melt the lattice")
-    p.add_argument("--full-list", type=int, default=0, help="1: FullVerletList fast path instead of the half list")
+    p.add_argument("--full-list", type=int, default=2, help="0 half list, 1 full list, 2 tiled periodic full list (fast path)")
     p.add_argument("--e2e-steps", type=int, default=100)
     p.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -180,7 +180,7 @@ def workload_config(args, n_atoms_per_gpu):
                     "to 1M atoms per GPU: sc lattice, rho=0.512, rc=2.5 sigma, skin 0.1, r_cap 0.7, Langevin gamma=20 "
                     "T=1.5, dt=0.002, maxNeighbors 60",
         "atoms_per_gpu": n_atoms_per_gpu, "box_per_gpu": [args.side * 1.25] * 3, "equilibration_steps": args.equil,
-        "list": "full" if args.full_list else "half",
+        "list": {0: "half (reference semantics, fp64 RED scatter)", 1: "full (generic gather kernel)", 2: "full, periodic tiles staged in shared memory (mrmd_b200_verlet_build_periodic)"}[args.full_list],
         "l2": "inputs larger than L2 (per step: 104 B/atom state + neighbour table ~ 4 B x 19-38 slots/atom > 126 MB "
               "at 1M atoms); no explicit flush",
         "parallelism": "1 GPU" if args.gpus == 1 else f"{args.gpus} independent periodic replicas, one per GPU (x-slab "
@@ -213,7 +213,7 @@ def run_b200(args):
                                      epsilon=PHYS["epsilon"], cappingDistance=PHYS["cap"],
                                      maxNeighbors=PHYS["max_neigh"], langevin=True, zeta=PHYS["zeta"],
                                      temperature=PHYS["temperature"], seed=PHYS["seed"], cellSort=True,
-                                     fullList=bool(args.full_list))
+                                     fullList=int(args.full_list))
 
     md = make_md(atoms)
     md.run(args.equil, stream=stream)       # untimed: melt the lattice

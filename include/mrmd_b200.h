@@ -236,6 +236,20 @@ int mrmd_b200_verlet_build_atoms(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, 
 int mrmd_b200_verlet_build_molecules(mrmd_b200_verlet* v, const mrmd_b200_molecules* m, int64_t begin, int64_t end,
                                      double radius, double cellRatio, const double* gridMin, const double* gridMax,
                                      int64_t maxNeigh, void* stream);
+/* B200 fast path for periodic subdomains: equivalent to GhostLayer::createGhostAtoms followed by
+ * VerletList::build(pos, 0, numLocalAtoms, radius, cellRatio, minGhostCorner, maxGhostCorner, maxNeigh) as far as
+ * the local atoms are concerned -- the same pairs (partner = a local atom or one of its periodic images, which
+ * are exactly the reference's ghost atoms) -- but built on shared-memory tiles of the cell-sorted local atoms.
+ * Requires LinkedCellList + permute over [0, numLocalAtoms) with the subdomain corners as grid (tests/NVT/NVT.cpp:136-144)
+ * since the last change of the atom order.  The list is stored as 16-bit tile slots; mrmd_b200_lj_apply
+ * recognises it and runs the tiled force kernel (full list: forces on row owners only). */
+int mrmd_b200_verlet_build_periodic(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, const mrmd_b200_subdomain* s,
+                                    double radius, double cellRatio, int64_t maxNeigh, void* stream);
+/* decodes a periodic list to Cabana's row-major layout: partner[i][n] = local index of the partner,
+ * shiftCode[i][n] = (sx+1) + 3 (sy+1) + 9 (sz+1) with the image shift s_d in {-1,0,+1} (x subdomain.diameter);
+ * host buffers of numLocal (x width) int32, -1 padded */
+int mrmd_b200_verlet_read_periodic(const mrmd_b200_verlet* v, const mrmd_b200_atoms* a, int32_t* countsHost,
+                                   int32_t* partnerHost, int32_t* shiftCodeHost, void* stream);
 /* list._data.counts / neighbors as a Cabana VerletLayout2D table: counts[numParticles] int32 and
  * neighbors[numParticles][width] int32 (row-major).  Pass NULL to query sizes only. */
 int mrmd_b200_verlet_info(const mrmd_b200_verlet* v, int64_t* numParticles, int64_t* width, int64_t* totalPairs,

@@ -104,6 +104,8 @@ SIGNATURES = {
     "mrmd_b200_verlet_destroy": (C.c_int, [vp]),
     "mrmd_b200_verlet_build_atoms": (C.c_int, [vp, vp, i64, i64, dbl, dbl, vp, vp, i64, vp]),
     "mrmd_b200_verlet_build_molecules": (C.c_int, [vp, vp, i64, i64, dbl, dbl, vp, vp, i64, vp]),
+    "mrmd_b200_verlet_build_periodic": (C.c_int, [vp, vp, pSub, dbl, dbl, i64, vp]),
+    "mrmd_b200_verlet_read_periodic": (C.c_int, [vp, vp, vp, vp, vp, vp]),
     "mrmd_b200_verlet_info": (C.c_int, [vp, pi64, pi64, pi64, pint]),
     "mrmd_b200_verlet_read": (C.c_int, [vp, vp, vp, C.c_int, vp]),
     "mrmd_b200_lj_create": (C.c_int, [pvp, vp, vp, vp, vp, i64, C.c_int]),

@@ -255,6 +255,23 @@ class _VerletList:
         check(fn(self.h, particles.h, begin, end, radius, cellRatio, gmin.ctypes.data, gmax.ctypes.data, maxNeigh,
                  _stream(stream)))
 
+    def build_periodic(self, atoms, subdomain, radius, cellRatio=1.0, maxNeigh=60, stream=None):
+        """B200 fast path: createGhostAtoms + build over the ghosts in one tiled pass (atoms must be cell-sorted
+        over [0, numLocalAtoms) on the subdomain grid)."""
+        check(L().mrmd_b200_verlet_build_periodic(self.h, atoms.h, C.byref(subdomain), radius, cellRatio, maxNeigh,
+                                                  _stream(stream)))
+
+    def to_host_periodic(self, atoms):
+        """(counts[n], partner[n, width], shiftCode[n, width]) of a periodic (tiled) list"""
+        i = self.info()
+        n, w = i["numParticles"], max(i["width"], 1)
+        counts = np.zeros(n, dtype=np.int32)
+        partner = np.full((n, w), -1, dtype=np.int32)
+        code = np.full((n, w), -1, dtype=np.int32)
+        check(L().mrmd_b200_verlet_read_periodic(self.h, atoms.h, counts.ctypes.data, partner.ctypes.data,
+                                                 code.ctypes.data, None))
+        return counts, partner, code
+
     def info(self):
         n, w, t, h = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int()
         check(L().mrmd_b200_verlet_info(self.h, C.byref(n), C.byref(w), C.byref(t), C.byref(h)))

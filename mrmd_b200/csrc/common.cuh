@@ -184,6 +184,15 @@ struct mrmd_b200_atoms
     mrmd_b200::DevBuf sortScratch;
     double* dMaxDisp = nullptr;  // device scalar for the integrators
     double* hMaxDisp = nullptr;  // pinned
+    // linked-cell structure left behind by the last cell sort (LinkedCellList + permute): atoms
+    // [lcBegin, lcEnd) are ordered by cell of lcGrid; lcCellStart[c] is the absolute index of the first atom
+    // of cell c (numCells + 1 entries).  Index ranges stay valid until the next sort / shrinking resize.
+    bool lcValid = false;
+    mrmd_b200::GridDev lcGrid{};
+    int64_t lcBegin = 0, lcEnd = 0;
+    int64_t lcNumCells = 0;
+    int64_t lcEpoch = 0;
+    mrmd_b200::DevBuf lcCellStart;  // int32[numCells + 1]
 };
 
 struct mrmd_b200_molecules
@@ -209,6 +218,14 @@ struct mrmd_b200_verlet
     int64_t buildCount = 0;
     mrmd_b200::DevBuf counts;   // int32[pitch]
     mrmd_b200::DevBuf neigh;    // int32[width * pitch]
+    // tiled flavour (tiled.cu): neighbours as 16-bit shared-memory slots of the owner's tile
+    bool tiled = false;
+    mrmd_b200::DevBuf enc;       // uint16[numParticles][width], rows in slot order
+    mrmd_b200::DevBuf tileDesc;  // int[tiles][64], see tiled.cu
+    mrmd_b200_subdomain tiledSub{};
+    int64_t tiledEpoch = -1;
+    int tiledCH = 0;
+    int tiledSlots = 0;
     mrmd_b200::DevBuf keys[2];  // radix sort ping-pong
     mrmd_b200::DevBuf vals[2];
     mrmd_b200::DevBuf scratch;

@@ -449,6 +449,7 @@ int mrmd_b200_atoms_destroy(mrmd_b200_atoms* a)
     if (a->hMaxDisp) cudaFreeHost(a->hMaxDisp);
     a->staging.release();
     a->sortScratch.release();
+    a->lcCellStart.release();
     delete a;
     return 0;
 }
@@ -466,6 +467,7 @@ int mrmd_b200_atoms_resize(mrmd_b200_atoms* a, int64_t size, void* stream)
     MB_REQUIRE(a != nullptr && size >= 0, "atoms_resize");
     MB_TRY(atomsEnsureCapacity(a, size, S(stream)));
     a->size = size;
+    if (size < a->lcEnd) a->lcValid = false;
     return 0;
 }
 

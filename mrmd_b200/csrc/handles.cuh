@@ -53,3 +53,10 @@ struct mrmd_b200_thermo
     double* tmpB = nullptr;
     double* forceFactor = nullptr;  // numTypes
 };
+
+namespace mrmd_b200
+{
+// tiled.cu: LennardJones::apply over a tiled (periodic, shared-memory staged) full list
+int ljApplyTiled(mrmd_b200_lj* lj, mrmd_b200_atoms* a, const mrmd_b200_verlet* v, bool accumulate, bool energy,
+                 cudaStream_t st);
+}  // namespace mrmd_b200

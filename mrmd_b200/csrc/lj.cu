@@ -191,6 +191,11 @@ int mrmd_b200_lj_apply(mrmd_b200_lj* lj, mrmd_b200_atoms* a, const mrmd_b200_ver
     MB_TRY(checkDevice());
     MB_REQUIRE(lj != nullptr && a != nullptr && v != nullptr, "lj_apply");
     cudaStream_t st = S(stream);
+    if (v->tiled)
+    {
+        MB_REQUIRE(pred == nullptr || pred->kind == MRMD_B200_PRED_ALWAYS, "lj_apply: predicates need a generic Verlet list");
+        return ljApplyTiled(lj, a, v, true, true, st);
+    }
     const int32_t* counts = v->counts.as<int32_t>();
     const int32_t* neigh = v->neigh.as<int32_t>();
     const int64_t pitch = v->pitch, numParticles = v->numParticles;

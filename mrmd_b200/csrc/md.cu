@@ -24,6 +24,7 @@ struct mrmd_b200_md
     int64_t step = 0;
     int64_t rebuilds = 0;
     int64_t storedPairsNow = 0;
+    bool ghostsStale = false;  // tiled fast path: ghost positions / forces are refreshed when a run returns
     std::vector<cudaEvent_t> events;
 };
 
@@ -71,6 +72,17 @@ static int rebuild(mrmd_b200_md* md, cudaStream_t st)
         if (c.cellSort)  // tests/NVT/NVT.cpp:136-144
             MB_TRY(mrmd_b200_atoms_cell_sort(a, 0, a->numLocal, delta, md->sub.minCorner, md->sub.maxCorner, nullptr, st));
         MB_TRY(mrmd_b200_ghost_create_atoms(md->ghost, a, &md->sub, -1, st));  // examples/02:153
+        if (c.fullList == 2)
+        {
+            // fast path: the same pair set as the list over local + ghost atoms, built on shared-memory tiles
+            // of the freshly sorted local atoms with the periodic images generated on the fly (tiled.cu)
+            MB_TRY(mrmd_b200_verlet_build_periodic(md->list, a, &md->sub, cutoff, 1.0, c.maxNeighbors, st));
+            int64_t total = 0;
+            MB_TRY(mrmd_b200_verlet_info(md->list, nullptr, nullptr, &total, nullptr));
+            md->storedPairsNow = total;
+            md->rebuilds += 1;
+            return 0;
+        }
         MB_TRY(mrmd_b200_verlet_build_atoms(md->list, a, 0, a->numLocal, cutoff, 1.0, md->sub.minGhostCorner,
                                             md->sub.maxGhostCorner, c.maxNeighbors, st));  // examples/02:156-163
     }
@@ -82,7 +94,8 @@ static int rebuild(mrmd_b200_md* md, cudaStream_t st)
 }
 
 // one step; evStart/evStop (optional) bracket the force kernel
-static int oneStep(mrmd_b200_md* md, cudaStream_t st, cudaEvent_t evStart, cudaEvent_t evStop, bool needRebuildHint)
+static int oneStep(mrmd_b200_md* md, cudaStream_t st, cudaEvent_t evStart, cudaEvent_t evStop, bool needRebuildHint,
+                   bool wantEnergy)
 {
     const mrmd_b200_md_config& c = md->cfg;
     mrmd_b200_atoms* a = md->atoms;
@@ -97,10 +110,23 @@ static int oneStep(mrmd_b200_md* md, cudaStream_t st, cudaEvent_t evStart, cudaE
         md->maxDisplacement = 0.0;
         MB_TRY(rebuild(md, st));
     }
-    else
+    else if (c.fullList != 2)
     {
         MB_TRY(mrmd_b200_ghost_update(md->ghost, a, &md->sub, st));  // :170
         if (c.adress) MB_TRY(mrmd_b200_molecules_update(md->mols, a, &c.weight, st));
+    }
+    if (c.fullList == 2)
+    {
+        // tiled fast path: images come from the staged local atoms, the force is stored (not accumulated) and
+        // no ghost atom receives force: no ghost refresh, no force reset, no fold-back inside the loop
+        if (evStart) MB_CUDA(cudaEventRecord(evStart, st));
+        // energy and virial are only observable after the run returns: accumulate them on its last step
+        MB_TRY(ljApplyTiled(md->lj, a, md->list, false, wantEnergy, st));
+        if (evStop) MB_CUDA(cudaEventRecord(evStop, st));
+        MB_TRY(mrmd_b200_vv_post(a, c.dt, st));
+        md->step += 1;
+        md->ghostsStale = true;
+        return 0;
     }
     MB_TRY(mrmd_b200_atoms_fill(a, MRMD_B200_ATOM_FORCE, 0.0, st));  // :174-175
     if (c.adress)
@@ -136,6 +162,15 @@ static int oneStep(mrmd_b200_md* md, cudaStream_t st, cudaEvent_t evStart, cudaE
 static int collectStats(mrmd_b200_md* md, int64_t nsteps, int64_t rebuilds0, int64_t storedSum, double pairs0,
                         int nTimed, mrmd_b200_md_stats* stats, cudaStream_t st)
 {
+    if (md->ghostsStale)
+    {
+        // leave the container as the reference loop would: ghosts at their real atom's image, zero ghost force
+        mrmd_b200_atoms* a = md->atoms;
+        MB_TRY(mrmd_b200_ghost_update(md->ghost, a, &md->sub, st));
+        for (int d = 0; d < 3 && a->numGhost > 0; ++d)
+            MB_CUDA(cudaMemsetAsync(a->v.force[d] + a->numLocal, 0, size_t(a->numGhost) * 8, st));
+        md->ghostsStale = false;
+    }
     double* dRes = md->cfg.adress ? md->adress->dResult : md->lj->dResult;
     double* hRes = md->cfg.adress ? md->adress->hResult : md->lj->hResult;
     MB_CUDA(cudaMemcpyAsync(hRes, dRes, 48, cudaMemcpyDeviceToHost, st));
@@ -262,7 +297,7 @@ int mrmd_b200_md_run(mrmd_b200_md* md, int64_t nsteps, int timeForceKernel, mrmd
     {
         cudaEvent_t e0 = (i < nTimed) ? md->events[2 * i] : nullptr;
         cudaEvent_t e1 = (i < nTimed) ? md->events[2 * i + 1] : nullptr;
-        MB_TRY(oneStep(md, st, e0, e1, false));
+        MB_TRY(oneStep(md, st, e0, e1, false, i == nsteps - 1));
         storedSum += md->storedPairsNow;
     }
     return collectStats(md, nsteps, rebuilds0, storedSum, pairs0, nTimed, stats, st);
@@ -285,7 +320,7 @@ int mrmd_b200_md_run_host(mrmd_b200_md* md, int64_t nsteps, double* posHost, dou
         // host -> device: this step's inputs
         MB_TRY(mrmd_b200_atoms_write(a, MRMD_B200_ATOM_POS, posHost, 0, n, 3, 1, MRMD_B200_MEM_HOST, st));
         MB_TRY(mrmd_b200_atoms_write(a, MRMD_B200_ATOM_VEL, velHost, 0, n, 3, 1, MRMD_B200_MEM_HOST, st));
-        MB_TRY(oneStep(md, st, nullptr, nullptr, false));
+        MB_TRY(oneStep(md, st, nullptr, nullptr, false, true));
         storedSum += md->storedPairsNow;
         // device -> host: the step's results
         MB_TRY(mrmd_b200_atoms_read(a, MRMD_B200_ATOM_POS, posHost, 0, n, 3, 1, MRMD_B200_MEM_HOST, st));

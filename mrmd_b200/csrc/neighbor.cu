@@ -85,18 +85,20 @@ __global__ void __launch_bounds__(RS_THREADS) rsHistogramKernel(const uint32_t* 
     blockHist[size_t(threadIdx.x) * numBlocks + blockIdx.x] = sum;  // digit-major
 }
 
-// exclusive scan of blockHist (digit-major) by a single block
-__global__ void __launch_bounds__(1024) rsScanKernel(uint32_t* data, int64_t total)
+// exclusive scan of every digit row of blockHist (digit-major: row d holds the numBlocks per-block counts
+// of digit d); block d scans row d and leaves the row total in digitTotals[d]
+__global__ void __launch_bounds__(RS_THREADS) rsScanRowsKernel(uint32_t* blockHist, int numBlocks, uint32_t* digitTotals)
 {
-    __shared__ uint32_t sWarpSum[32];
+    __shared__ uint32_t sWarpSum[RS_WARPS];
     __shared__ uint32_t sCarry;
+    uint32_t* row = blockHist + size_t(blockIdx.x) * numBlocks;
     if (threadIdx.x == 0) sCarry = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int64_t base = 0; base < total; base += 1024)
+    for (int base = 0; base < numBlocks; base += RS_THREADS)
     {
-        const int64_t i = base + threadIdx.x;
-        const uint32_t v = (i < total) ? data[i] : 0;
+        const int i = base + threadIdx.x;
+        const uint32_t v = (i < numBlocks) ? row[i] : 0;
         uint32_t x = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1)
@@ -106,38 +108,55 @@ __global__ void __launch_bounds__(1024) rsScanKernel(uint32_t* data, int64_t tot
         }
         if (lane == 31) sWarpSum[warp] = x;
         __syncthreads();
-        if (warp == 0)
-        {
-            uint32_t w = sWarpSum[lane];
+        uint32_t warpOffset = 0, total = 0;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1)
-            {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += y;
-            }
-            sWarpSum[lane] = w;  // inclusive
+        for (int w = 0; w < RS_WARPS; ++w)
+        {
+            const uint32_t c = sWarpSum[w];
+            if (w < warp) warpOffset += c;
+            total += c;
         }
-        __syncthreads();
-        const uint32_t warpOffset = (warp > 0) ? sWarpSum[warp - 1] : 0;
         const uint32_t carry = sCarry;
-        if (i < total) data[i] = carry + warpOffset + x - v;
+        if (i < numBlocks) row[i] = carry + warpOffset + x - v;
         __syncthreads();
-        if (threadIdx.x == 1023) sCarry = carry + warpOffset + x;
+        if (threadIdx.x == 0) sCarry = carry + total;
         __syncthreads();
     }
+    if (threadIdx.x == 0) digitTotals[blockIdx.x] = sCarry;
 }
 
 __global__ void __launch_bounds__(RS_THREADS)
     rsScatterKernel(const uint32_t* keysIn, const uint32_t* valsIn, uint32_t* keysOut, uint32_t* valsOut, int64_t n,
-                    int shift, const uint32_t* scannedHist, int numBlocks)
+                    int shift, const uint32_t* scannedHist, const uint32_t* digitTotals, int numBlocks)
 {
     __shared__ uint32_t sWarp[RS_WARPS][RS_BINS];
+    __shared__ uint32_t sDigitWarp[RS_WARPS];
     uint32_t digits[RS_ITEMS], ranks[RS_ITEMS];
     const int64_t tileBase = int64_t(blockIdx.x) * RS_TILE;
+    // exclusive scan of the 256 digit totals (thread t <-> digit t)
+    uint32_t digitBase;
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const uint32_t v = digitTotals[threadIdx.x];
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) sDigitWarp[warp] = x;
+        __syncthreads();
+        uint32_t off = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w)
+            if (w < warp) off += sDigitWarp[w];
+        digitBase = off + x - v;
+    }
     rankTile(keysIn, n, shift, tileBase, sWarp, digits, ranks);
     {
         // per digit: exclusive prefix over warps plus the global offset of (digit, block)
-        uint32_t run = scannedHist[size_t(threadIdx.x) * numBlocks + blockIdx.x];
+        uint32_t run = digitBase + scannedHist[size_t(threadIdx.x) * numBlocks + blockIdx.x];
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w)
         {
@@ -165,7 +184,7 @@ __global__ void __launch_bounds__(RS_THREADS)
 size_t radixSortScratchBytes(int64_t n)
 {
     const int64_t numBlocks = (n + RS_TILE - 1) / RS_TILE;
-    return size_t(RS_BINS) * size_t(std::max<int64_t>(numBlocks, 1)) * 4;
+    return size_t(RS_BINS) * size_t(std::max<int64_t>(numBlocks, 1) + 1) * 4;
 }
 
 int radixSortPairs(uint32_t* keysIn, uint32_t* valsIn, uint32_t* keysTmp, uint32_t* valsTmp, uint32_t* scratch,
@@ -180,9 +199,11 @@ int radixSortPairs(uint32_t* keysIn, uint32_t* valsIn, uint32_t* keysTmp, uint32
         {
             rsHistogramKernel<<<numBlocks, RS_THREADS, 0, st>>>(kIn, n, 8 * p, scratch, numBlocks);
             MB_LAUNCHED();
-            rsScanKernel<<<1, 1024, 0, st>>>(scratch, int64_t(RS_BINS) * numBlocks);
+            uint32_t* digitTotals = scratch + size_t(RS_BINS) * numBlocks;
+            rsScanRowsKernel<<<RS_BINS, RS_THREADS, 0, st>>>(scratch, numBlocks, digitTotals);
             MB_LAUNCHED();
-            rsScatterKernel<<<numBlocks, RS_THREADS, 0, st>>>(kIn, vIn, kOut, vOut, n, 8 * p, scratch, numBlocks);
+            rsScatterKernel<<<numBlocks, RS_THREADS, 0, st>>>(kIn, vIn, kOut, vOut, n, 8 * p, scratch, digitTotals,
+                                                              numBlocks);
             MB_LAUNCHED();
             std::swap(kIn, kOut);
             std::swap(vIn, vOut);
@@ -247,7 +268,8 @@ __global__ void permuteMolsKernel(MolsView dst, MolsView src, const uint32_t* pe
 }
 
 // cellStart[c] = first sorted slot whose key is >= c, c in [0, numCells]
-__global__ void cellStartKernel(const uint32_t* sortedKeys, int64_t n, int64_t numCells, int32_t* cellStart)
+__global__ void cellStartKernel(const uint32_t* sortedKeys, int64_t n, int64_t numCells, int32_t* cellStart,
+                                int32_t offset)
 {
     const int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
     if (c > numCells) return;
@@ -258,7 +280,7 @@ __global__ void cellStartKernel(const uint32_t* sortedKeys, int64_t n, int64_t n
         if (int64_t(sortedKeys[mid]) < c) lo = mid + 1;
         else hi = mid;
     }
-    cellStart[c] = static_cast<int32_t>(lo);
+    cellStart[c] = static_cast<int32_t>(lo) + offset;
 }
 
 __global__ void gatherSortedPosKernel(const double4* pos, const uint32_t* sortedIdx, int64_t n, double4* sortedPos)
@@ -390,6 +412,7 @@ static int verletBuild(mrmd_b200_verlet* v, const double4* pos, int64_t nAll, in
     const int cellRange = static_cast<int>(std::ceil(1.0 / cellRatio));
     const double rsqr = radius * radius;
 
+    v->tiled = false;
     v->numParticles = nAll;
     v->begin = begin;
     v->end = end;
@@ -421,7 +444,7 @@ static int verletBuild(mrmd_b200_verlet* v, const double4* pos, int64_t nAll, in
     MB_TRY(radixSortPairs(v->keys[0].as<uint32_t>(), v->vals[0].as<uint32_t>(), v->keys[1].as<uint32_t>(),
                           v->vals[1].as<uint32_t>(), v->scratch.as<uint32_t>(), nAll, bitsFor(numCells), &sortedKeys,
                           &sortedIdx, st));
-    cellStartKernel<<<gridFor(numCells + 1, 256), 256, 0, st>>>(sortedKeys, nAll, numCells, v->cellStart.as<int32_t>());
+    cellStartKernel<<<gridFor(numCells + 1, 256), 256, 0, st>>>(sortedKeys, nAll, numCells, v->cellStart.as<int32_t>(), 0);
     MB_LAUNCHED();
     gatherSortedPosKernel<<<gridFor(nAll, 256), 256, 0, st>>>(pos, sortedIdx, nAll, v->sortedPos.as<double4>());
     MB_LAUNCHED();
@@ -478,6 +501,17 @@ int mrmd_b200_atoms_cell_sort(mrmd_b200_atoms* a, int64_t begin, int64_t end, co
     permuteAtomsKernel<<<gridFor(a->size, 256), 256, 0, st>>>(a->alt, a->v, perm, begin, end, a->size);
     MB_LAUNCHED();
     std::swap(a->v, a->alt);
+    // keep the linked-cell structure for the tiled (shared-memory staged) neighbour and force kernels
+    MB_TRY(a->lcCellStart.reserve(size_t(numCells + 1) * 4));
+    cellStartKernel<<<gridFor(numCells + 1, 256), 256, 0, st>>>(sortedKeys, count, numCells, a->lcCellStart.as<int32_t>(),
+                                                                static_cast<int32_t>(begin));
+    MB_LAUNCHED();
+    a->lcValid = true;
+    a->lcGrid = g;
+    a->lcBegin = begin;
+    a->lcEnd = end;
+    a->lcNumCells = numCells;
+    a->lcEpoch += 1;
     return 0;
 }
 
@@ -521,6 +555,8 @@ int mrmd_b200_verlet_destroy(mrmd_b200_verlet* v)
     cudaDeviceSynchronize();
     v->counts.release();
     v->neigh.release();
+    v->enc.release();
+    v->tileDesc.release();
     for (int b = 0; b < 2; ++b)
     {
         v->keys[b].release();

@@ -1,0 +1,687 @@
+// tiled.cu -- shared-memory tiled neighbour build and Lennard-Jones force for cell-sorted, periodic systems:
+// the B200 fast path behind Cabana::VerletList::build + LennardJones::apply.
+//
+// Why: a thread-per-atom walk over a Verlet list issues one divergent 32-byte gather per pair.  ncu
+// (profiles/r01_lj_generic_*.txt) shows the L1 address stage saturating at ~2.3 cycles per lane-gather (and
+// ~1.3 cycles per lane for the fp64 RED scatter of the half list): the list kernels are LSU-wavefront bound,
+// far from HBM.  Here a block owns a tile = one (x,y) cell column x CH cells along z of the linked-cell grid
+// left behind by LinkedCellList + permute.  Atoms are stored in cell order (z fastest), so the 3x3 neighbour
+// columns are nine contiguous index ranges: they are copied once, coalesced, into shared memory as SoA
+// x[], y[], z[] (periodic images are produced on the fly by adding +-L exactly as GhostExchange /
+// UpdateGhostAtoms do, so the staged coordinates are bit-identical to the ghost atoms' coordinates) and every
+// neighbour of a home atom becomes a 16-bit shared-memory slot.  Eight lanes share one home atom: they read
+// eight consecutive list entries (one 16-byte segment) and, because rows are kept in slot order, mostly
+// consecutive slots -> conflict-free LDS.64; the three force components are combined with warp shuffles.
+// No atomics (full list: an atom accumulates only its own force), no ghost refresh / fold-back in the step,
+// 2 bytes of list traffic per pair.
+//
+// Pair set: identical to the reference's list over local + ghost atoms (same criterion, same uncontracted
+// distance arithmetic, Cabana's stencil pruning re-checked on accepted pairs): tests decode the slots back to
+// (local partner, image shift) and compare with the oracle's list mapped through correspondingRealAtom.
+#include <algorithm>
+#include <cmath>
+
+#include "handles.cuh"
+
+namespace mrmd_b200
+{
+constexpr int TL_THREADS = 256;
+constexpr int TL_GROUP = 8;                       // lanes per home atom
+constexpr int TL_GROUPS = TL_THREADS / TL_GROUP;  // home atoms in flight per block
+constexpr int TL_PIECES = 27;                     // 9 columns x {low z-wrap, main, high z-wrap}
+constexpr int TL_MAX_CH = 16;                     // home cells per tile along z
+constexpr int TL_CELLS = TL_MAX_CH + 3;
+constexpr int TL_DESC_INTS = 64;                  // per-tile descriptor in global memory
+
+struct TileParams
+{
+    GridDev g;  // linked-cell grid of the sorted local atoms
+    int CH;
+    int numChunks;
+    int periodic[3];  // ghost layer thickness > 0 on that axis
+    double L[3];      // subdomain.diameter
+    double minInner[3], maxInner[3];
+    int cap;  // shared-memory slots per tile
+};
+
+// descriptor layout (ints): [0..26] pieceStart, [27..53] pieceLen, [54] homeStart, [55] homeCount,
+// [56] slot of the first home atom, [57] total slots
+struct TileDesc
+{
+    int pieceStart[TL_PIECES];
+    int pieceLen[TL_PIECES];
+    int pieceSlot[TL_PIECES + 1];
+    int homeStart, homeCount, selfSlot0, totalSlots;
+};
+
+// image shift of piece p = (column r = p / 3, z part w = p % 3) of the tile at (ci, cj)
+__device__ __forceinline__ void pieceShift(const TileParams& tp, int ci, int cj, int p, int& sx, int& sy, int& sz)
+{
+    const int r = p / 3, w = p % 3;
+    const int ii = ci + r / 3 - 1, jj = cj + r % 3 - 1;
+    sx = (ii < 0) ? -1 : ((ii >= tp.g.n[0]) ? 1 : 0);
+    sy = (jj < 0) ? -1 : ((jj >= tp.g.n[1]) ? 1 : 0);
+    sz = (w == 0) ? -1 : ((w == 2) ? 1 : 0);
+}
+
+// one block per tile: writes the descriptor (once per rebuild)
+__global__ void __launch_bounds__(32) tileDescKernel(TileParams tp, const int32_t* __restrict__ cellStart, int* desc,
+                                                     int* maxSlots)
+{
+    const int tile = blockIdx.x;
+    const int col = tile / tp.numChunks, chunk = tile % tp.numChunks;
+    const int ci = col / tp.g.n[1], cj = col % tp.g.n[1];
+    const int nz = tp.g.n[2];
+    const int k0 = chunk * tp.CH;
+    const int k1 = min(k0 + tp.CH, nz) - 1;
+    const int t = threadIdx.x;
+    int start = 0, len = 0;
+    if (t < TL_PIECES)
+    {
+        const int r = t / 3, w = t % 3;
+        int sx, sy, sz;
+        pieceShift(tp, ci, cj, t, sx, sy, sz);
+        int ii = ci + r / 3 - 1 - sx * tp.g.n[0], jj = cj + r % 3 - 1 - sy * tp.g.n[1];
+        bool exists = !((sx != 0 && !tp.periodic[0]) || (sy != 0 && !tp.periodic[1]));
+        int klo, khi;
+        if (w == 1) { klo = max(k0 - 1, 0); khi = min(k1 + 1, nz - 1); }
+        else if (w == 0) { klo = khi = nz - 1; exists = exists && (k0 == 0) && tp.periodic[2]; }
+        else { klo = khi = 0; exists = exists && (k1 == nz - 1) && tp.periodic[2]; }
+        if (exists)
+        {
+            start = cellStart[cardinal(tp.g, ii, jj, klo)];
+            len = cellStart[cardinal(tp.g, ii, jj, khi) + 1] - start;
+        }
+        desc[tile * TL_DESC_INTS + t] = start;
+        desc[tile * TL_DESC_INTS + TL_PIECES + t] = len;
+    }
+    // total slots and the slot of the first home atom (pieces before the centre main piece + offset inside it)
+    int before = (t < 13) ? len : 0, total = (t < TL_PIECES) ? len : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        before += __shfl_xor_sync(0xffffffffu, before, o);
+        total += __shfl_xor_sync(0xffffffffu, total, o);
+    }
+    if (t == 0)
+    {
+        const int homeStart = cellStart[cardinal(tp.g, ci, cj, k0)];
+        const int homeCount = cellStart[cardinal(tp.g, ci, cj, k1) + 1] - homeStart;
+        const int centreStart = cellStart[cardinal(tp.g, ci, cj, max(k0 - 1, 0))];
+        desc[tile * TL_DESC_INTS + 54] = homeStart;
+        desc[tile * TL_DESC_INTS + 55] = homeCount;
+        desc[tile * TL_DESC_INTS + 56] = before + (homeStart - centreStart);
+        desc[tile * TL_DESC_INTS + 57] = total;
+        atomicMax(maxSlots, total);
+    }
+}
+
+__device__ __forceinline__ void loadTileDesc(const int* __restrict__ desc, TileDesc& td)
+{
+    const int t = threadIdx.x;
+    const int* d = desc + size_t(blockIdx.x) * TL_DESC_INTS;
+    if (t < TL_PIECES)
+    {
+        td.pieceStart[t] = d[t];
+        const int len = d[TL_PIECES + t];
+        td.pieceLen[t] = len;
+        int x = len;  // inclusive scan over the 27 pieces (warp 0)
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const int y = __shfl_up_sync(0x07ffffffu, x, o);
+            if (t >= o) x += y;
+        }
+        td.pieceSlot[t + 1] = x;
+        if (t == 0) td.pieceSlot[0] = 0;
+    }
+    else if (t == 32)
+    {
+        td.homeStart = d[54];
+        td.homeCount = d[55];
+        td.selfSlot0 = d[56];
+        td.totalSlots = d[57];
+    }
+    __syncthreads();
+}
+
+// copies the tile's atoms into shared memory (SoA), image shifts applied with one addition per shifted axis.
+// BUILD: also records the source index, or -1 when the atom does not qualify as a ghost image for the piece's
+// shift (x < minInner for +L, x >= maxInner for -L: GhostExchange.cpp:80,89).
+template <bool BUILD, bool TYPES>
+__device__ __forceinline__ void stageTile(const TileParams& tp, const TileDesc& td, const double4* __restrict__ pos,
+                                          double* sx_, double* sy_, double* sz_, int* sIdx, unsigned char* sType)
+{
+    const int tile = blockIdx.x;
+    const int col = tile / tp.numChunks;
+    const int ci = col / tp.g.n[1], cj = col % tp.g.n[1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int p = warp; p < TL_PIECES; p += TL_THREADS / 32)
+    {
+        const int len = td.pieceLen[p];
+        if (len == 0) continue;
+        int ix, iy, iz;
+        pieceShift(tp, ci, cj, p, ix, iy, iz);
+        // x + (+-L) is the ghost layer's single addition; x + 0.0 leaves x bit-identical
+        const double shx = double(ix) * tp.L[0], shy = double(iy) * tp.L[1], shz = double(iz) * tp.L[2];
+        const int start = td.pieceStart[p], slot0 = td.pieceSlot[p];
+        for (int k = lane; k < len; k += 32)
+        {
+            const double4 raw = ld4nc(pos + start + k);
+            double qx = raw.x + shx;
+            if (BUILD)
+            {
+                // an atom that the reference would not have turned into this ghost image is parked at
+                // x = +inf: it fails every distance test without a separate flag
+                bool ok = true;
+                if (ix > 0) ok = ok && (raw.x < tp.minInner[0]);
+                if (ix < 0) ok = ok && (raw.x >= tp.maxInner[0]);
+                if (iy > 0) ok = ok && (raw.y < tp.minInner[1]);
+                if (iy < 0) ok = ok && (raw.y >= tp.maxInner[1]);
+                if (iz > 0) ok = ok && (raw.z < tp.minInner[2]);
+                if (iz < 0) ok = ok && (raw.z >= tp.maxInner[2]);
+                if (!ok) qx = __longlong_as_double(0x7ff0000000000000LL);
+            }
+            sx_[3 * (slot0 + k)] = qx;
+            sy_[3 * (slot0 + k)] = raw.y + shy;
+            sz_[3 * (slot0 + k)] = raw.z + shz;
+            if (TYPES) sType[slot0 + k] = static_cast<unsigned char>(typeOf(raw));
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ double minDist1T(const GridDev& g, double x, int c, int d)
+{
+    const double xc = __dadd_rn(g.min[d], __dmul_rn(double(c) + 0.5, g.dx[d]));
+    const double rr = __dsub_rn(fabs(__dsub_rn(x, xc)), __dmul_rn(0.5, g.dx[d]));
+    return (rr > 0.0) ? rr : 0.0;
+}
+
+// Cabana's stencil pruning for an accepted pair: the stencil cell that holds n must be within r of p
+__device__ __forceinline__ bool cabanaCellReachable(const GridDev& cg, double px, double py, double pz, double qx,
+                                                    double qy, double qz, double rsqr)
+{
+    const int a = locate1(cg, qx, 0), b = locate1(cg, qy, 1), c = locate1(cg, qz, 2);
+    const double rx = minDist1T(cg, px, a, 0), ry = minDist1T(cg, py, b, 1), rz = minDist1T(cg, pz, c, 2);
+    return __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz)) <= rsqr;
+}
+
+// Neighbour build on tiles: eight lanes scan the candidates of one home atom (the three cells around its
+// own cell in each of the nine columns are one contiguous slot range per column), accepted slots are
+// appended in slot order through a ballot over the group -> deterministic rows, no atomics.
+template <bool HALF>
+__global__ void __launch_bounds__(TL_THREADS)
+    verletBuildTiledKernel(TileParams tp, GridDev cabanaGrid, const double4* __restrict__ pos,
+                           const int32_t* __restrict__ cellStart, const int* __restrict__ desc, double rsqr, int width,
+                           int32_t* __restrict__ counts, uint16_t* __restrict__ enc, int32_t* stats)
+{
+    extern __shared__ double sTile[];
+    __shared__ TileDesc td;
+    __shared__ int cellSlot[9][TL_CELLS];  // slot where virtual cell v (= k0 - 1 + v) of column r starts
+    loadTileDesc(desc, td);
+    double* sx_ = sTile;
+    double* sy_ = sx_ + 1;  // interleaved {x, y, z} records: one address per slot, conflict-free for consecutive slots
+    double* sz_ = sx_ + 2;
+    int* sIdx = reinterpret_cast<int*>(sx_ + 3 * tp.cap);
+    const int tile = blockIdx.x;
+    const int col = tile / tp.numChunks, chunk = tile % tp.numChunks;
+    const int ci = col / tp.g.n[1], cj = col % tp.g.n[1];
+    const int nz = tp.g.n[2];
+    const int k0 = chunk * tp.CH;
+    const int k1 = min(k0 + tp.CH, nz) - 1;
+    const int nk = k1 - k0 + 1;
+    const int nv = nk + 3;  // virtual cells k0-1 .. k1+1 plus the end sentinel
+    for (int e = threadIdx.x; e < 9 * nv; e += TL_THREADS)
+    {
+        const int r = e / nv, v = e % nv;
+        const int kv = k0 - 1 + v;
+        int slot;
+        if (v == nv - 1) slot = td.pieceSlot[r * 3 + 3];
+        else if (kv < 0) slot = td.pieceSlot[r * 3 + 0];
+        else if (kv >= nz) slot = td.pieceSlot[r * 3 + 2];
+        else if (td.pieceLen[r * 3 + 1] == 0) slot = td.pieceSlot[r * 3 + 1];
+        else
+        {
+            int ii = ci + r / 3 - 1, jj = cj + r % 3 - 1;
+            if (ii < 0) ii += tp.g.n[0]; else if (ii >= tp.g.n[0]) ii -= tp.g.n[0];
+            if (jj < 0) jj += tp.g.n[1]; else if (jj >= tp.g.n[1]) jj -= tp.g.n[1];
+            slot = td.pieceSlot[r * 3 + 1] + (cellStart[cardinal(tp.g, ii, jj, kv)] - td.pieceStart[r * 3 + 1]);
+        }
+        cellSlot[r][v] = slot;
+    }
+    stageTile<true, false>(tp, td, pos, sx_, sy_, sz_, sIdx, nullptr);
+
+    // all control flow below is warp uniform (trip counts are the maximum over the warp's four groups, lanes are
+    // predicated): sub-warp *_sync masks that differ between groups would be serialised by the compiler
+    const int group = threadIdx.x / TL_GROUP, gl = threadIdx.x % TL_GROUP;
+    const int shiftInWarp = (threadIdx.x & 31) - gl;  // first lane of the group inside its warp
+    constexpr unsigned GROUP_BITS = (1u << TL_GROUP) - 1u;
+    int mx = 0;
+    long long total = 0;
+    const double rsqrSafe = rsqr * (1.0 - 1e-9);
+    for (int hBase = 0; hBase < td.homeCount; hBase += TL_GROUPS)
+    {
+        const int h = hBase + group;
+        const bool active = h < td.homeCount;
+        const int i = td.homeStart + h;
+        const int selfSlot = active ? td.selfSlot0 + h : -1;
+        const int safeSlot = active ? selfSlot : 0;
+        int v = 1;  // virtual cell of the home atom: cellSlot[4][v] <= selfSlot < cellSlot[4][v+1]
+        if (active)
+            while (v < nk && cellSlot[4][v + 1] <= selfSlot) ++v;
+        const double px = active ? sx_[3 * selfSlot] : 0.0, py = active ? sy_[3 * selfSlot] : 0.0, pz = active ? sz_[3 * selfSlot] : 0.0;
+        int count = 0;
+        uint16_t* row = enc + size_t(active ? i : 0) * width;
+#pragma unroll 1
+        for (int r = 0; r < 9; ++r)
+        {
+            const int s0 = active ? cellSlot[r][v - 1] : 0, s1 = active ? cellSlot[r][v + 2] : 0;
+            const int iters = __reduce_max_sync(0xffffffffu, (s1 - s0 + TL_GROUP - 1) / TL_GROUP);
+            for (int it = 0; it < iters; ++it)
+            {
+                const int s = s0 + it * TL_GROUP + gl;
+                const bool inRange = s < s1;
+                const double* q = sx_ + 3 * (inRange ? s : safeSlot);  // always a valid record: no branch
+                const double qx = q[0], qy = q[1], qz = q[2];
+                const double d2 = distSqrExact(px - qx, py - qy, pz - qz);
+                bool ok = inRange && (s != selfSlot) && (d2 <= rsqr);
+                if (HALF) ok = ok && ((qx > px) || ((qx == px) && ((qy > py) || ((qy == py) && (qz > pz)))));
+                // Cabana prunes stencil cells by their distance to p; the cell holding n can only fail that test
+                // when d2 is within rounding of r^2 (the cell contains n), so the exact re-check is needed for
+                // d2 > (1 - 1e-9) r^2 only
+                if (ok && d2 > rsqrSafe) ok = cabanaCellReachable(cabanaGrid, px, py, pz, qx, qy, qz, rsqr);
+                const unsigned m = (__ballot_sync(0xffffffffu, ok) >> shiftInWarp) & GROUP_BITS;
+                if (ok)
+                {
+                    const int at = count + __popc(m & ((1u << gl) - 1u));
+                    if (at < width) row[at] = static_cast<uint16_t>(s);
+                }
+                count += __popc(m);
+            }
+        }
+        if (active && gl == 0)
+        {
+            counts[i] = count;
+            mx = max(mx, count);
+            total += count;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        total += __shfl_xor_sync(0xffffffffu, total, o);
+    }
+    if ((threadIdx.x & 31) == 0 && total > 0)
+    {
+        atomicMax(stats, mx);
+        atomicAdd(reinterpret_cast<unsigned long long*>(stats + 2), static_cast<unsigned long long>(total));
+    }
+}
+
+// reciprocal with two Newton steps on the hardware seed: <= 1 ulp, no slow-path branch (the force is compared
+// to 1e-10 relative; the cutoff decisions never use it)
+__device__ __forceinline__ double fastRcp(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
+constexpr int LJT_PREFETCH = 8;  // list steps (of TL_GROUP entries) held in registers: rows up to 64 entries
+
+// one pair of LennardJones::apply_if's inner loop (LennardJones.hpp:176-196) against a staged partner
+template <bool SINGLE_TYPE, bool ENERGY>
+__device__ __forceinline__ void ljPair(const double* sx_, const double* sy_, const double* sz_,
+                                       const unsigned char* sType, int slot, double xi, double yi, double zi, int typeI,
+                                       const LJType& t0, const LJTable& table, int64_t numTypesQuirk, double rcSqr,
+                                       double& fx, double& fy, double& fz, double& energy, double& virial, double& pairs)
+{
+    const double dx = xi - sx_[3 * slot];
+    const double dy = yi - sy_[3 * slot];
+    const double dz = zi - sz_[3 * slot];
+    const double distSqr = distSqrExact(dx, dy, dz);
+    if (distSqr <= rcSqr)  // LennardJones.hpp:182 skips distSqr > rcSqr
+    {
+        const LJType& t = SINGLE_TYPE ? t0 : table.t[typeI * numTypesQuirk + sType[slot]];
+        double ff, e;
+        if (distSqr >= t.cappingDistanceSqr)  // LennardJones.hpp:56-67
+        {
+            const double frac2 = fastRcp(distSqr);
+            const double frac6 = frac2 * frac2 * frac2;
+            ff = frac6 * (t.ff1 * frac6 - t.ff2) * frac2;
+            e = frac6 * (t.ef1 * frac6 - t.ef2) - t.shift;
+        }
+        else
+            ljForceEnergy(t, distSqr, ff, e);
+        if (ENERGY)
+        {
+            energy += e;
+            virial -= 0.5 * ff * distSqr;
+        }
+        pairs += 1.0;
+        fx += dx * ff;
+        fy += dy * ff;
+        fz += dz * ff;
+    }
+}
+
+// LennardJones::apply over the tiled list (full list: row owners only).  ACCUMULATE = false stores the force
+// (the driver then skips the force reset); true adds like the reference.  ENERGY = false skips the energy /
+// virial accumulation (the driver asks for them on the last step of a run only).
+template <bool SINGLE_TYPE, bool ACCUMULATE, bool ENERGY>
+__global__ void __launch_bounds__(TL_THREADS)
+    ljForceTiledKernel(TileParams tp, AtomsView a, const int* __restrict__ desc, const int32_t* __restrict__ counts,
+                       const uint16_t* __restrict__ enc, int width, LJTable table, double rcSqr, int64_t numTypesQuirk,
+                       double* partials, double* result, unsigned int* ticket)
+{
+    extern __shared__ double sTile[];
+    __shared__ TileDesc td;
+    loadTileDesc(desc, td);
+    double* sx_ = sTile;
+    double* sy_ = sx_ + 1;  // interleaved {x, y, z} records: one address per slot, conflict-free for consecutive slots
+    double* sz_ = sx_ + 2;
+    unsigned char* sType = reinterpret_cast<unsigned char*>(sx_ + 3 * tp.cap);
+    stageTile<false, !SINGLE_TYPE>(tp, td, a.pos, sx_, sy_, sz_, nullptr, sType);
+
+    // warp-uniform control flow, see verletBuildTiledKernel
+    const int group = threadIdx.x / TL_GROUP, gl = threadIdx.x % TL_GROUP;
+    double energy = 0.0, virial = 0.0, pairs = 0.0;
+    const LJType t0 = table.t[0];
+    for (int hBase = 0; hBase < td.homeCount; hBase += TL_GROUPS)
+    {
+        const int h = hBase + group;
+        const bool active = h < td.homeCount;
+        const int i = td.homeStart + h;
+        const int selfSlot = active ? td.selfSlot0 + h : 0;
+        const double xi = sx_[3 * selfSlot], yi = sy_[3 * selfSlot], zi = sz_[3 * selfSlot];
+        const int typeI = SINGLE_TYPE ? 0 : sType[selfSlot];
+        double fx = 0.0, fy = 0.0, fz = 0.0;
+        const int numNeighbors = active ? min(counts[i], width) : 0;
+        const uint16_t* row = enc + size_t(active ? i : 0) * width;
+        const int iters = __reduce_max_sync(0xffffffffu, (numNeighbors + TL_GROUP - 1) / TL_GROUP);
+        // every list entry of the row is requested before the first one is used (one 16-byte segment per group
+        // and step; LJT_PREFETCH steps live in registers)
+        int slots[LJT_PREFETCH];
+#pragma unroll
+        for (int it = 0; it < LJT_PREFETCH; ++it)
+        {
+            const int n = it * TL_GROUP + gl;
+            slots[it] = (n < numNeighbors) ? int(row[n]) : -1;
+        }
+#pragma unroll
+        for (int it = 0; it < LJT_PREFETCH; ++it)
+        {
+            if (it < iters && slots[it] >= 0)
+                ljPair<SINGLE_TYPE, ENERGY>(sx_, sy_, sz_, sType, slots[it], xi, yi, zi, typeI, t0, table, numTypesQuirk,
+                                            rcSqr, fx, fy, fz, energy, virial, pairs);
+        }
+        for (int it = LJT_PREFETCH; it < iters; ++it)
+        {
+            const int n = it * TL_GROUP + gl;
+            if (n < numNeighbors)
+                ljPair<SINGLE_TYPE, ENERGY>(sx_, sy_, sz_, sType, row[n], xi, yi, zi, typeI, t0, table, numTypesQuirk,
+                                            rcSqr, fx, fy, fz, energy, virial, pairs);
+        }
+#pragma unroll
+        for (int o = TL_GROUP / 2; o > 0; o >>= 1)
+        {
+            fx += __shfl_xor_sync(0xffffffffu, fx, o);
+            fy += __shfl_xor_sync(0xffffffffu, fy, o);
+            fz += __shfl_xor_sync(0xffffffffu, fz, o);
+        }
+        if (active && gl == 0)
+        {
+            if (ACCUMULATE)
+            {
+                a.force[0][i] += fx;
+                a.force[1][i] += fy;
+                a.force[2][i] += fz;
+            }
+            else
+            {
+                a.force[0][i] = fx;
+                a.force[1][i] = fy;
+                a.force[2][i] = fz;
+            }
+        }
+    }
+    // every pair is visited from both sides
+    gridReduce3<TL_THREADS>(0.5 * energy, 0.5 * virial, 0.5 * pairs, partials, result, ticket);
+}
+
+// decode the 16-bit slots back to (local partner index, image shift code) in Cabana's row-major layout
+__global__ void __launch_bounds__(TL_THREADS)
+    decodeTiledKernel(TileParams tp, const int* __restrict__ desc, const int32_t* __restrict__ counts,
+                      const uint16_t* __restrict__ enc, int width, int32_t* partner, int32_t* shiftCode)
+{
+    __shared__ TileDesc td;
+    loadTileDesc(desc, td);
+    const int col = blockIdx.x / tp.numChunks;
+    const int ci = col / tp.g.n[1], cj = col % tp.g.n[1];
+    for (int h = threadIdx.x; h < td.homeCount; h += TL_THREADS)
+    {
+        const int i = td.homeStart + h;
+        const int cnt = min(counts[i], width);
+        for (int n = 0; n < width; ++n)
+        {
+            int j = -1, code = -1;
+            if (n < cnt)
+            {
+                const int slot = enc[size_t(i) * width + n];
+                int p = 0;
+                while (p + 1 < TL_PIECES && td.pieceSlot[p + 1] <= slot) ++p;
+                j = td.pieceStart[p] + (slot - td.pieceSlot[p]);
+                int sx, sy, sz;
+                pieceShift(tp, ci, cj, p, sx, sy, sz);
+                code = (sx + 1) + 3 * (sy + 1) + 9 * (sz + 1);
+            }
+            partner[size_t(i) * width + n] = j;
+            shiftCode[size_t(i) * width + n] = code;
+        }
+    }
+}
+
+static int makeTileParams(const mrmd_b200_atoms* a, const mrmd_b200_subdomain* s, int CH, int cap, TileParams& tp)
+{
+    tp.g = a->lcGrid;
+    tp.CH = CH;
+    tp.numChunks = (tp.g.n[2] + CH - 1) / CH;
+    tp.cap = cap;
+    for (int d = 0; d < 3; ++d)
+    {
+        tp.periodic[d] = s->ghostLayerThickness[d] > 0.0 ? 1 : 0;
+        tp.L[d] = s->diameter[d];
+        tp.minInner[d] = s->minInnerCorner[d];
+        tp.maxInner[d] = s->maxInnerCorner[d];
+    }
+    return 0;
+}
+
+constexpr int TL_SMEM_PER_SLOT_BUILD = 24;  // x, y, z
+constexpr int TL_SMEM_PER_SLOT_FORCE = 25;  // x, y, z + type byte
+constexpr int TL_SMEM_BUDGET = 48 * 1024;   // preferred per-tile budget (several tiles per SM)
+constexpr int TL_SMEM_MAX = 200 * 1024;
+
+int tiledConfigure()
+{
+    static bool done = false;
+    if (done) return 0;
+#define TL_SET(K) MB_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, TL_SMEM_MAX))
+    TL_SET((verletBuildTiledKernel<true>));
+    TL_SET((verletBuildTiledKernel<false>));
+    TL_SET((ljForceTiledKernel<true, true, true>));
+    TL_SET((ljForceTiledKernel<true, true, false>));
+    TL_SET((ljForceTiledKernel<true, false, true>));
+    TL_SET((ljForceTiledKernel<true, false, false>));
+    TL_SET((ljForceTiledKernel<false, true, true>));
+    TL_SET((ljForceTiledKernel<false, true, false>));
+    TL_SET((ljForceTiledKernel<false, false, true>));
+    TL_SET((ljForceTiledKernel<false, false, false>));
+#undef TL_SET
+    done = true;
+    return 0;
+}
+
+int ljApplyTiled(mrmd_b200_lj* lj, mrmd_b200_atoms* a, const mrmd_b200_verlet* v, bool accumulate, bool energy,
+                 cudaStream_t st)
+{
+    MB_REQUIRE(a->lcValid && a->lcEpoch == v->tiledEpoch, "lj_apply: the atoms were re-sorted after this tiled list was built");
+    MB_REQUIRE(!v->half, "lj_apply: tiled lists are full lists");
+    MB_TRY(tiledConfigure());
+    TileParams tp;
+    MB_TRY(makeTileParams(a, &v->tiledSub, v->tiledCH, v->tiledSlots, tp));
+    const int tiles = tp.g.n[0] * tp.g.n[1] * tp.numChunks;
+    MB_TRY(lj->partials.reserve(size_t(tiles) * 3 * 8));
+    MB_CUDA(cudaMemsetAsync(lj->dResult, 0, 24, st));
+    const size_t smem = size_t(v->tiledSlots) * TL_SMEM_PER_SLOT_FORCE + 16;
+    const bool single = (lj->numTypes == 1);
+#define LJT_LAUNCH(S1, ACC, EN)                                                                                       \
+    ljForceTiledKernel<S1, ACC, EN><<<tiles, TL_THREADS, smem, st>>>(                                                 \
+        tp, a->v, v->tileDesc.as<int>(), v->counts.as<int32_t>(), v->enc.as<uint16_t>(), static_cast<int>(v->width), \
+        lj->table, lj->rcSqr, lj->numTypesQuirk, lj->partials.as<double>(), lj->dResult, lj->dTicket)
+    if (single)
+    {
+        if (accumulate) { if (energy) LJT_LAUNCH(true, true, true); else LJT_LAUNCH(true, true, false); }
+        else { if (energy) LJT_LAUNCH(true, false, true); else LJT_LAUNCH(true, false, false); }
+    }
+    else
+    {
+        if (accumulate) { if (energy) LJT_LAUNCH(false, true, true); else LJT_LAUNCH(false, true, false); }
+        else { if (energy) LJT_LAUNCH(false, false, true); else LJT_LAUNCH(false, false, false); }
+    }
+#undef LJT_LAUNCH
+    MB_LAUNCHED();
+    return 0;
+}
+}  // namespace mrmd_b200
+
+using namespace mrmd_b200;
+
+extern "C" {
+
+int mrmd_b200_verlet_build_periodic(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, const mrmd_b200_subdomain* s,
+                                    double radius, double cellRatio, int64_t maxNeigh, void* stream)
+{
+    MB_TRY(checkDevice());
+    MB_REQUIRE(v != nullptr && a != nullptr && s != nullptr, "verlet_build_periodic");
+    MB_REQUIRE(radius > 0.0 && cellRatio > 0.0 && maxNeigh > 0, "verlet_build_periodic: bad radius / ratio / width");
+    MB_REQUIRE(a->lcValid && a->lcBegin == 0 && a->lcEnd == a->numLocal,
+               "verlet_build_periodic: sort the local atoms first (LinkedCellList + permute over [0, numLocalAtoms))");
+    const GridDev& g = a->lcGrid;
+    for (int d = 0; d < 3; ++d)
+    {
+        MB_REQUIRE(g.min[d] == s->minCorner[d] && std::fabs(g.dx[d] * g.n[d] - s->diameter[d]) <= 1e-9 * s->diameter[d],
+                   "verlet_build_periodic: the linked-cell grid must span the subdomain");
+        MB_REQUIRE(g.dx[d] >= radius, "verlet_build_periodic: linked cells smaller than the list radius");
+        MB_REQUIRE(g.n[d] >= 3 || s->ghostLayerThickness[d] == 0.0, "verlet_build_periodic: fewer than 3 cells on a periodic axis");
+        MB_REQUIRE(s->ghostLayerThickness[d] == 0.0 || s->ghostLayerThickness[d] <= g.dx[d],
+                   "verlet_build_periodic: ghost layer thicker than a linked cell");
+    }
+    MB_TRY(tiledConfigure());
+    cudaStream_t st = S(stream);
+    const int64_t n = a->numLocal;
+    if (v->hStats == nullptr) MB_CUDA(cudaMallocHost(&v->hStats, 16));
+    MB_TRY(v->stats.reserve(16));
+    v->numParticles = n;
+    v->begin = 0;
+    v->end = n;
+    v->pitch = n;
+    MB_TRY(v->counts.reserve(size_t(std::max<int64_t>(n, 1)) * 4));
+    v->buildCount += 1;
+    v->tiled = true;
+    v->tiledSub = *s;
+    v->tiledEpoch = a->lcEpoch;
+    // Cabana's grid for the stencil-pruning check (grid_min/max = ghost corners, delta = radius * ratio)
+    const double gs = radius * cellRatio;
+    const double delta[3] = {gs, gs, gs};
+    const GridDev cabanaGrid = makeGrid(s->minGhostCorner, s->maxGhostCorner, delta);
+
+    // choose CH: ~110 home atoms per tile, at least ~2 tiles per SM, staged slots within the smem budget
+    const double perCell = double(n) / double(std::max<int64_t>(a->lcNumCells, 1));
+    int CH = std::max(1, std::min({TL_MAX_CH, g.n[2], static_cast<int>(std::ceil(110.0 / std::max(perCell, 0.1)))}));
+    while (CH > 1 && int64_t(g.n[0]) * g.n[1] * ((g.n[2] + CH - 1) / CH) < 2 * 148) CH = (CH + 1) / 2;
+    TileParams tp;
+    int tiles = 0;
+    for (;;)
+    {
+        MB_TRY(makeTileParams(a, s, CH, 0, tp));
+        tiles = g.n[0] * g.n[1] * tp.numChunks;
+        MB_TRY(v->tileDesc.reserve(size_t(tiles) * TL_DESC_INTS * 4));
+        MB_CUDA(cudaMemsetAsync(v->stats.p, 0, 16, st));
+        tileDescKernel<<<tiles, 32, 0, st>>>(tp, a->lcCellStart.as<int32_t>(), v->tileDesc.as<int>(), v->stats.as<int>());
+        MB_LAUNCHED();
+        MB_CUDA(cudaMemcpyAsync(v->hStats, v->stats.p, 4, cudaMemcpyDeviceToHost, st));
+        MB_CUDA(cudaStreamSynchronize(st));
+        const int slots = v->hStats[0];
+        if (slots * TL_SMEM_PER_SLOT_BUILD <= TL_SMEM_BUDGET || CH == 1)
+        {
+            MB_REQUIRE(slots * TL_SMEM_PER_SLOT_BUILD + 64 <= TL_SMEM_MAX && slots < 65535,
+                       "verlet_build_periodic: a tile exceeds shared memory");
+            v->tiledSlots = (std::max(slots, 1) + 1) & ~1;  // even: keeps the int / byte arrays 8-byte aligned
+            break;
+        }
+        CH = (CH + 1) / 2;
+    }
+    v->tiledCH = CH;
+    tp.cap = v->tiledSlots;
+    const double rsqr = radius * radius;
+    int64_t width = (std::max<int64_t>(maxNeigh, 1) + 7) & ~int64_t(7);  // rows of 16-byte segments
+    if (v->width > width && v->enc.bytes >= size_t(v->width) * std::max<int64_t>(n, 1) * 2) width = v->width;
+    for (int attempt = 0; attempt < 3; ++attempt)
+    {
+        MB_TRY(v->enc.reserve(size_t(width) * std::max<int64_t>(n, 1) * 2));
+        v->width = width;
+        MB_CUDA(cudaMemsetAsync(v->stats.p, 0, 16, st));
+        const size_t smem = size_t(v->tiledSlots) * TL_SMEM_PER_SLOT_BUILD + 16;
+        if (v->half)
+            verletBuildTiledKernel<true><<<tiles, TL_THREADS, smem, st>>>(
+                tp, cabanaGrid, a->v.pos, a->lcCellStart.as<int32_t>(), v->tileDesc.as<int>(), rsqr,
+                static_cast<int>(width), v->counts.as<int32_t>(), v->enc.as<uint16_t>(), v->stats.as<int32_t>());
+        else
+            verletBuildTiledKernel<false><<<tiles, TL_THREADS, smem, st>>>(
+                tp, cabanaGrid, a->v.pos, a->lcCellStart.as<int32_t>(), v->tileDesc.as<int>(), rsqr,
+                static_cast<int>(width), v->counts.as<int32_t>(), v->enc.as<uint16_t>(), v->stats.as<int32_t>());
+        MB_LAUNCHED();
+        MB_CUDA(cudaMemcpyAsync(v->hStats, v->stats.p, 16, cudaMemcpyDeviceToHost, st));
+        MB_CUDA(cudaStreamSynchronize(st));
+        if (v->hStats[0] <= width) return 0;
+        width = (int64_t(v->hStats[0]) + 7) & ~int64_t(7);
+    }
+    setLastError("verlet_build_periodic: neighbour table overflow after refill");
+    return MRMD_B200_ECAPACITY;
+}
+
+int mrmd_b200_verlet_read_periodic(const mrmd_b200_verlet* v, const mrmd_b200_atoms* a, int32_t* countsHost,
+                                   int32_t* partnerHost, int32_t* shiftCodeHost, void* stream)
+{
+    MB_TRY(checkDevice());
+    MB_REQUIRE(v != nullptr && a != nullptr && v->tiled, "verlet_read_periodic: not a tiled list");
+    MB_REQUIRE(a->lcValid && a->lcEpoch == v->tiledEpoch, "verlet_read_periodic: atoms were re-sorted since the build");
+    cudaStream_t st = S(stream);
+    const int64_t n = v->numParticles;
+    if (n == 0) return 0;
+    TileParams tp;
+    MB_TRY(makeTileParams(a, &v->tiledSub, v->tiledCH, v->tiledSlots, tp));
+    const int tiles = tp.g.n[0] * tp.g.n[1] * tp.numChunks;
+    int32_t* d = nullptr;
+    MB_CUDA(cudaMalloc(&d, size_t(n) * v->width * 8));
+    decodeTiledKernel<<<tiles, TL_THREADS, 0, st>>>(tp, v->tileDesc.as<int>(), v->counts.as<int32_t>(),
+                                                    v->enc.as<uint16_t>(), static_cast<int>(v->width), d,
+                                                    d + n * v->width);
+    g_launchCount.fetch_add(1);
+    if (countsHost) cudaMemcpyAsync(countsHost, v->counts.p, size_t(n) * 4, cudaMemcpyDeviceToHost, st);
+    if (partnerHost) cudaMemcpyAsync(partnerHost, d, size_t(n) * v->width * 4, cudaMemcpyDeviceToHost, st);
+    if (shiftCodeHost) cudaMemcpyAsync(shiftCodeHost, d + n * v->width, size_t(n) * v->width * 4, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    MB_CUDA(e);
+    return 0;
+}
+
+}  // extern "C"
