@@ -38,6 +38,7 @@ def parse_args():
     p.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--replicas", action="store_true", help="N>1: independent periodic replicas instead of x-slabs")
     return p.parse_args()
 
 
@@ -183,8 +184,11 @@ def workload_config(args, n_atoms_per_gpu):
         "list": {0: "half (reference semantics, fp64 RED scatter)", 1: "full (generic gather kernel)", 2: "full, periodic tiles staged in shared memory (mrmd_b200_verlet_build_periodic)"}[args.full_list],
         "l2": "inputs larger than L2 (per step: 104 B/atom state + neighbour table ~ 4 B x 19-38 slots/atom > 126 MB "
               "at 1M atoms); no explicit flush",
-        "parallelism": "1 GPU" if args.gpus == 1 else f"{args.gpus} independent periodic replicas, one per GPU (x-slab "
-                                                       "halo exchange: see DESIGN.md multi-GPU status)",
+        "parallelism": "1 GPU" if args.gpus == 1 else (
+            f"{args.gpus} independent periodic replicas, one per GPU" if getattr(args, "replicas", False) else
+            f"{args.gpus} x-slabs of one {args.gpus * args.side * 1.25:g} x {args.side * 1.25:g} x {args.side * 1.25:g} box, "
+            "one process per GPU, NCCL halos (positions every step, full records at rebuild), ncclAllReduce(max) "
+            "rebuild decision"),
     }
 
 
@@ -206,9 +210,22 @@ def run_b200(args):
     pos, vel, box = lattice_system(args.side, seed=PHYS["seed"] + rank)
     n = len(pos)
     sub = api.Subdomain([0, 0, 0], box, PHYS["rc"] + PHYS["skin"])
+    slab_mode = world > 1 and not args.replicas
+    if slab_mode:
+        # weak scaling over x-slabs: one global box of world * side x side x side sites, rank r owns slab r
+        pos = pos + np.array([rank * box[0], 0.0, 0.0])
     atoms = api.Atoms.from_arrays(pos, vel, mass=1.0)
 
     def make_md(a):
+        if slab_mode:
+            from mrmd_b200 import slabs
+
+            uid = slabs.broadcast_unique_id(rank)
+            return slabs.SlabMolecularDynamics(a, np.zeros(3), np.array([world * box[0], box[1], box[2]]), rank, world,
+                                               uid, dt=PHYS["dt"], rc=PHYS["rc"], skin=PHYS["skin"], sigma=PHYS["sigma"],
+                                               epsilon=PHYS["epsilon"], cappingDistance=PHYS["cap"],
+                                               maxNeighbors=PHYS["max_neigh"], langevin=True, zeta=PHYS["zeta"],
+                                               temperature=PHYS["temperature"], seed=PHYS["seed"])
         return api.MolecularDynamics(a, sub, dt=PHYS["dt"], rc=PHYS["rc"], skin=PHYS["skin"], sigma=PHYS["sigma"],
                                      epsilon=PHYS["epsilon"], cappingDistance=PHYS["cap"],
                                      maxNeighbors=PHYS["max_neigh"], langevin=True, zeta=PHYS["zeta"],
@@ -261,7 +278,7 @@ def run_b200(args):
     achieved = algo_bytes / (force_ms * 1e-3) / 1e9 if force_ms > 0 else None
     traffic = ncu_traffic()
     roofline = {
-        "bound": "hbm", "kernel": "ljForceKernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "bound": "hbm", "kernel": "ljForceTiledKernel" if args.full_list == 2 else "ljForceKernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": (achieved / peak) if achieved else None, "peak_source": peak_src,
         "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
         "algorithmic_bytes_per_launch": algo_bytes / args.steps,
@@ -271,7 +288,33 @@ def run_b200(args):
 
     # end to end through the C ABI with HOST buffers: per step H2D pos+vel, one step, D2H pos+vel+scalars
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and slab_mode:
+        # same contract on every rank's slab: the number of resident atoms changes when atoms migrate, so the
+        # host mirror is re-sized from the step's own statistics
+        cap = int(1.25 * n) + 1024
+        hpos, hvel = api.PinnedBuffer((cap, 3)), api.PinnedBuffer((cap, 3))
+        nl = md.run(0)["numLocal"]
+        hpos.array[:nl] = atoms.get("pos")[:nl]
+        hvel.array[:nl] = atoms.get("vel")[:nl]
+
+        def host_step(nl):
+            atoms.write_ptr("pos", hpos.ptr, 0, nl, 3, 1, api.HOST, stream)
+            atoms.write_ptr("vel", hvel.ptr, 0, nl, 3, 1, api.HOST, stream)
+            nl = md.run(1, stream=stream)["numLocal"]
+            atoms.read_ptr("pos", hpos.ptr, 0, nl, 3, 1, api.HOST, stream)
+            atoms.read_ptr("vel", hvel.ptr, 0, nl, 3, 1, api.HOST, stream)
+            return nl
+
+        for _ in range(3):
+            nl = host_step(nl)
+        k = max(1, min(args.e2e_steps, args.steps))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(k):
+            nl = host_step(nl)
+        barrier()
+        dt = time.perf_counter() - t0
+    elif not args.no_e2e:
         hpos, hvel, hsc = api.PinnedBuffer((n, 3)), api.PinnedBuffer((n, 3)), api.PinnedBuffer((3,))
         hpos.array[:] = atoms.get("pos")[:n]
         hvel.array[:] = atoms.get("vel")[:n]
@@ -282,6 +325,7 @@ def run_b200(args):
         md.run_host(k, hpos.ptr, hvel.ptr, hsc.ptr, stream=stream)
         barrier()
         dt = time.perf_counter() - t0
+    if not args.no_e2e:
         tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
         if world > 1:
             import torch.distributed as dist
@@ -289,7 +333,9 @@ def run_b200(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * n * k / float(tt[0]), "unit": "atom-steps/s", "h2d_bytes_per_step": 48 * n,
                "d2h_bytes_per_step": 48 * n + 24, "steps": k,
-               "path": "mrmd_b200_md_run_host: pinned host pos+vel -> device, one step, pos+vel+{E,virial,maxDisp} back"}
+               "path": ("per rank: pinned host pos+vel of the resident atoms -> device (mrmd_b200_atoms_write), one "
+                        "mrmd_b200_slab_run step, pos+vel back (mrmd_b200_atoms_read)") if slab_mode else
+                       "mrmd_b200_md_run_host: pinned host pos+vel -> device, one step, pos+vel+{E,virial,maxDisp} back"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -372,6 +372,24 @@ int mrmd_b200_md_run(mrmd_b200_md* md, int64_t nsteps, int timeForceKernel, mrmd
  * pageable) to the device, runs one step and copies pos, vel and {energy, virial, maxDisplacement} back. */
 int mrmd_b200_md_run_host(mrmd_b200_md* md, int64_t nsteps, double* posHost, double* velHost,
                           double* scalarsHost, mrmd_b200_md_stats* stats, void* stream);
+/* ---- x-slab decomposition over the GPUs of one node ---------------------------------------------
+ * New functionality (the reference's communication layer is single-process periodic self-ghosting,
+ * communication/MultiResRealAtomsExchange.hpp:26): one process per GPU, rank r owns the slab
+ * [xmin + r W, xmin + (r+1) W) of the global box.  y / z stay locally periodic, the x pass of
+ * GhostExchange::createGhostAtoms (communication/GhostExchange.cpp:59-169) becomes an NCCL halo over NVLink:
+ * full records migrate at a rebuild, positions of the face atoms are sent every step, no reverse force halo
+ * (full list).  The displacement criterion of examples/02:141-143 is evaluated on the ncclAllReduce(max).
+ * uniqueId128: the 128 bytes of mrmd_b200_nccl_unique_id from rank 0, broadcast by the caller. */
+typedef struct mrmd_b200_slab mrmd_b200_slab;
+int mrmd_b200_nccl_unique_id(void* out128);
+int mrmd_b200_slab_create(mrmd_b200_slab** out, const mrmd_b200_md_config* cfg, const double* globalMin,
+                          const double* globalMax, int rank, int nranks, const void* uniqueId128, mrmd_b200_atoms* atoms,
+                          void* stream);
+int mrmd_b200_slab_destroy(mrmd_b200_slab* sl);
+/* nsteps collective steps; stats: energy / virial summed over the ranks, the other fields are per rank */
+int mrmd_b200_slab_run(mrmd_b200_slab* sl, int64_t nsteps, int timeForceKernel, mrmd_b200_md_stats* stats,
+                       void* stream);
+
 /* pinned host memory for the host-buffer path */
 int mrmd_b200_host_alloc(void** ptr, int64_t bytes);
 int mrmd_b200_host_free(void* ptr);

@@ -222,6 +222,8 @@ struct mrmd_b200_verlet
     bool tiled = false;
     mrmd_b200::DevBuf enc;       // uint16[numParticles][width], rows in slot order
     mrmd_b200::DevBuf tileDesc;  // int[tiles][64], see tiled.cu
+    mrmd_b200::DevBuf cellLoHi;  // int32[2][extended cells]: first / one-past-last atom of every cell
+    int tiledHaloX = 0;          // x-slab decomposition: halo columns at i = -1 and i = nx
     mrmd_b200_subdomain tiledSub{};
     int64_t tiledEpoch = -1;
     int tiledCH = 0;

@@ -59,4 +59,7 @@ namespace mrmd_b200
 // tiled.cu: LennardJones::apply over a tiled (periodic, shared-memory staged) full list
 int ljApplyTiled(mrmd_b200_lj* lj, mrmd_b200_atoms* a, const mrmd_b200_verlet* v, bool accumulate, bool energy,
                  cudaStream_t st);
+int verletBuildTiled(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, const mrmd_b200_subdomain* s, double radius,
+                     double cellRatio, int64_t maxNeigh, const int32_t* haloLeft, const int32_t* haloRight,
+                     cudaStream_t st);
 }  // namespace mrmd_b200

@@ -222,13 +222,17 @@ static int bitsFor(int64_t numCells)
 }
 
 // ---------------------------------------------------------------------------------------------
+// dropFlags (optional): atoms flagged non-zero get the key numCells and sort behind the last cell (atoms that
+// migrated to another rank, slab.cu)
 __global__ void cellKeyKernel(const double4* pos, int64_t first, int64_t count, GridDev g, uint32_t* keys,
-                              uint32_t* vals, int32_t* cellIdOut)
+                              uint32_t* vals, int32_t* cellIdOut, const signed char* dropFlags = nullptr,
+                              uint32_t dropKey = 0)
 {
     const int64_t j = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
     if (j >= count) return;
     const double4 p = ld4nc(pos + first + j);
-    const int c = cardinal(g, locate1(g, p.x, 0), locate1(g, p.y, 1), locate1(g, p.z, 2));
+    int c = cardinal(g, locate1(g, p.x, 0), locate1(g, p.y, 1), locate1(g, p.z, 2));
+    if (dropFlags != nullptr && dropFlags[first + j] != 0) c = static_cast<int>(dropKey);
     keys[j] = static_cast<uint32_t>(c);
     vals[j] = static_cast<uint32_t>(first + j);
     if (cellIdOut != nullptr) cellIdOut[first + j] = c;
@@ -479,25 +483,47 @@ using namespace mrmd_b200;
 
 extern "C" {
 
-int mrmd_b200_atoms_cell_sort(mrmd_b200_atoms* a, int64_t begin, int64_t end, const double* delta,
-                              const double* gridMin, const double* gridMax, int32_t* cellIdOut, void* stream)
+}  // extern "C"
+
+namespace mrmd_b200
 {
-    MB_TRY(checkDevice());
+static int atomsCellSortImpl(mrmd_b200_atoms* a, int64_t begin, int64_t end, const double* delta, const double* gridMin,
+                             const double* gridMax, int32_t* cellIdOut, const signed char* dropFlags, cudaStream_t st);
+
+// cell sort that also removes the atoms flagged in dropFlags: they end up behind lcCellStart[numCells]
+int atomsCellSortDrop(mrmd_b200_atoms* a, int64_t begin, int64_t end, const double* delta, const double* gridMin,
+                      const double* gridMax, const signed char* dropFlags, cudaStream_t st)
+{
+    return atomsCellSortImpl(a, begin, end, delta, gridMin, gridMax, nullptr, dropFlags, st);
+}
+
+// prefix array of n sorted keys: cellStart[c] = offset + first position with key >= c, c in [0, numCells]
+int cellStartFromKeys(const uint32_t* sortedKeys, int64_t n, int64_t numCells, int32_t* cellStart, int32_t offset,
+                      cudaStream_t st)
+{
+    cellStartKernel<<<gridFor(numCells + 1, 256), 256, 0, st>>>(sortedKeys, n, numCells, cellStart, offset);
+    MB_LAUNCHED();
+    return 0;
+}
+
+static int atomsCellSortImpl(mrmd_b200_atoms* a, int64_t begin, int64_t end, const double* delta, const double* gridMin,
+                             const double* gridMax, int32_t* cellIdOut, const signed char* dropFlags, cudaStream_t st)
+{
     MB_REQUIRE(a != nullptr && delta != nullptr && gridMin != nullptr && gridMax != nullptr, "atoms_cell_sort");
     MB_REQUIRE(begin >= 0 && begin <= end && end <= a->size, "atoms_cell_sort: range outside the container");
     const int64_t count = end - begin;
     if (count == 0) return 0;
-    cudaStream_t st = S(stream);
     const GridDev g = makeGrid(gridMin, gridMax, delta);
     const int64_t numCells = int64_t(g.n[0]) * g.n[1] * g.n[2];
-    MB_REQUIRE(numCells < (int64_t(1) << 31), "atoms_cell_sort: too many cells");
+    MB_REQUIRE(numCells < (int64_t(1) << 31) - 1, "atoms_cell_sort: too many cells");
     uint32_t *k0, *v0, *k1, *v1, *hist;
     MB_TRY(cellSortPrepare(a->sortScratch, count, &k0, &v0, &k1, &v1, &hist));
     MB_TRY(atomsEnsureAlt(a, st));
-    cellKeyKernel<<<gridFor(count, 256), 256, 0, st>>>(a->v.pos, begin, count, g, k0, v0, cellIdOut);
+    cellKeyKernel<<<gridFor(count, 256), 256, 0, st>>>(a->v.pos, begin, count, g, k0, v0, cellIdOut, dropFlags,
+                                                       static_cast<uint32_t>(numCells));
     MB_LAUNCHED();
     uint32_t *sortedKeys, *perm;
-    MB_TRY(radixSortPairs(k0, v0, k1, v1, hist, count, bitsFor(numCells), &sortedKeys, &perm, st));
+    MB_TRY(radixSortPairs(k0, v0, k1, v1, hist, count, bitsFor(numCells + 1), &sortedKeys, &perm, st));
     permuteAtomsKernel<<<gridFor(a->size, 256), 256, 0, st>>>(a->alt, a->v, perm, begin, end, a->size);
     MB_LAUNCHED();
     std::swap(a->v, a->alt);
@@ -513,6 +539,16 @@ int mrmd_b200_atoms_cell_sort(mrmd_b200_atoms* a, int64_t begin, int64_t end, co
     a->lcNumCells = numCells;
     a->lcEpoch += 1;
     return 0;
+}
+}  // namespace mrmd_b200
+
+extern "C" {
+
+int mrmd_b200_atoms_cell_sort(mrmd_b200_atoms* a, int64_t begin, int64_t end, const double* delta,
+                              const double* gridMin, const double* gridMax, int32_t* cellIdOut, void* stream)
+{
+    MB_TRY(checkDevice());
+    return atomsCellSortImpl(a, begin, end, delta, gridMin, gridMax, cellIdOut, nullptr, S(stream));
 }
 
 int mrmd_b200_molecules_cell_sort(mrmd_b200_molecules* m, int64_t begin, int64_t end, const double* delta,
@@ -557,6 +593,7 @@ int mrmd_b200_verlet_destroy(mrmd_b200_verlet* v)
     v->neigh.release();
     v->enc.release();
     v->tileDesc.release();
+    v->cellLoHi.release();
     for (int b = 0; b < 2; ++b)
     {
         v->keys[b].release();

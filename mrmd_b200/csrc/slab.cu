@@ -1,0 +1,724 @@
+// slab.cu -- one-GPU-per-process x-slab decomposition of the LJ step loop.
+//
+// The reference has no inter-rank communication (mrmd/communication is single-process periodic self-ghosting,
+// MultiResRealAtomsExchange.hpp:26); this is the multi-GPU extension the north star asks for.  Each rank owns
+// the slab [xlo, xhi) of the global box.  y / z stay locally periodic (the tiled kernels generate those images
+// on the fly), the x pass of GhostExchange becomes an NCCL halo:
+//   rebuild   atoms that left the slab migrate to the neighbour rank (full records), the rank sorts its atoms
+//             by linked cell, the atoms within rc+skin of each x face are sent as halo atoms (they arrive in
+//             (j,k) cell order because the sender's atoms are cell sorted) and the tiled neighbour build treats
+//             them as two extra cell columns;
+//   step      positions of the halo atoms only (32 B per atom, ncclSend/ncclRecv straight into the position
+//             array), no reverse force halo: with the full list every rank computes the complete force of
+//             its own atoms;
+//   decision  the displacement criterion (examples/02:141-143) uses the ncclAllReduce(max) over the ranks, so
+//             all ranks rebuild together.
+// The periodic wrap in x is applied by the two end ranks when they send across the global boundary.
+// NCCL is resolved at run time with dlopen (single-GPU users do not need it).
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <vector>
+
+#include "handles.cuh"
+
+namespace mrmd_b200
+{
+struct NcclApi
+{
+    void* lib = nullptr;
+    decltype(&ncclGetUniqueId) getUniqueId = nullptr;
+    decltype(&ncclCommInitRank) commInitRank = nullptr;
+    decltype(&ncclCommDestroy) commDestroy = nullptr;
+    decltype(&ncclSend) send = nullptr;
+    decltype(&ncclRecv) recv = nullptr;
+    decltype(&ncclGroupStart) groupStart = nullptr;
+    decltype(&ncclGroupEnd) groupEnd = nullptr;
+    decltype(&ncclAllReduce) allReduce = nullptr;
+    decltype(&ncclGetErrorString) getErrorString = nullptr;
+};
+
+static NcclApi g_nccl;
+
+static int loadNccl()
+{
+    if (g_nccl.lib != nullptr) return 0;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (lib == nullptr) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (lib == nullptr)
+    {
+        setLastError(std::string("cannot load NCCL: ") + dlerror());
+        return MRMD_B200_EINVAL;
+    }
+#define NCCL_SYM(field, name)                                                  \
+    g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(lib, name)); \
+    if (g_nccl.field == nullptr)                                               \
+    {                                                                          \
+        setLastError(std::string("NCCL symbol missing: ") + name);             \
+        return MRMD_B200_EINVAL;                                               \
+    }
+    NCCL_SYM(getUniqueId, "ncclGetUniqueId");
+    NCCL_SYM(commInitRank, "ncclCommInitRank");
+    NCCL_SYM(commDestroy, "ncclCommDestroy");
+    NCCL_SYM(send, "ncclSend");
+    NCCL_SYM(recv, "ncclRecv");
+    NCCL_SYM(groupStart, "ncclGroupStart");
+    NCCL_SYM(groupEnd, "ncclGroupEnd");
+    NCCL_SYM(allReduce, "ncclAllReduce");
+    NCCL_SYM(getErrorString, "ncclGetErrorString");
+#undef NCCL_SYM
+    g_nccl.lib = lib;
+    return 0;
+}
+
+#define MB_NCCL(expr)                                                                                       \
+    do                                                                                                      \
+    {                                                                                                       \
+        ncclResult_t _r = (expr);                                                                           \
+        if (_r != ncclSuccess)                                                                              \
+        {                                                                                                   \
+            ::mrmd_b200::setLastError(std::string(#expr) + ": " + g_nccl.getErrorString(_r));               \
+            return MRMD_B200_EINVAL;                                                                        \
+        }                                                                                                   \
+    } while (0)
+
+constexpr int SL_THREADS = 256;
+constexpr int SL_RECORD = 13;  // doubles per migrating atom: pos3, type bits, vel3, force3, mass, charge, relMass
+
+// y / z periodic wrap (PeriodicMapping.cpp:36-51 arithmetic) and the x migration flag: -1 left, +1 right, 0 stays
+__global__ void slabWrapFlagKernel(double4* pos, int64_t n, SubdomainDev s, signed char* flag)
+{
+    const int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (idx >= n) return;
+    double4 p = ld4(pos + idx);
+    double* x = &p.x;
+#pragma unroll
+    for (int dim = 1; dim < 3; ++dim)
+    {
+        if (s.maxCorner[dim] <= x[dim])
+        {
+            x[dim] -= s.diameter[dim];
+            x[dim] = fmax(x[dim], s.minCorner[dim]);
+        }
+        if (x[dim] < s.minCorner[dim])
+        {
+            x[dim] += s.diameter[dim];
+            if (s.maxCorner[dim] <= x[dim]) x[dim] = s.minCorner[dim];
+        }
+    }
+    st4(pos + idx, p);
+    flag[idx] = (p.x < s.minCorner[0]) ? -1 : ((p.x >= s.maxCorner[0]) ? 1 : 0);
+}
+
+// stable selection of two subsets of [first, first + n): block counts -> scan -> ranked index lists
+template <int MODE>  // 0: migration flags, 1: halo faces by position
+__device__ __forceinline__ void selectPredicates(const double4* pos, const signed char* flag, int64_t idx, double lowBound,
+                                                 double highBound, bool& lo, bool& hi)
+{
+    if (MODE == 0)
+    {
+        const signed char f = flag[idx];
+        lo = f < 0;
+        hi = f > 0;
+    }
+    else
+    {
+        const double x = ld4nc(pos + idx).x;
+        lo = x < lowBound;    // GhostExchange.cpp:80 (x < minInnerCorner)
+        hi = x >= highBound;  // :89 (x >= maxInnerCorner)
+    }
+}
+
+__device__ __forceinline__ void blockScan2(long long (&v)[2], long long (&total)[2])
+{
+    __shared__ long long sWarp[2][SL_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long incl[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+    {
+        long long x = v[k];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const long long y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        incl[k] = x;
+        if (lane == 31) sWarp[k][warp] = x;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+    {
+        long long off = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < SL_THREADS / 32; ++w)
+        {
+            const long long c = sWarp[k][w];
+            if (w < warp) off += c;
+            tot += c;
+        }
+        v[k] = off + incl[k] - v[k];
+        total[k] = tot;
+    }
+    __syncthreads();
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(SL_THREADS)
+    selectCountKernel(const double4* pos, const signed char* flag, int64_t first, int64_t n, double lowBound,
+                      double highBound, int64_t* blockCounts)
+{
+    const int64_t j = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    long long v[2] = {0, 0}, total[2];
+    if (j < n)
+    {
+        bool lo, hi;
+        selectPredicates<MODE>(pos, flag, first + j, lowBound, highBound, lo, hi);
+        v[0] = lo;
+        v[1] = hi;
+    }
+    blockScan2(v, total);
+    if (threadIdx.x == 0)
+    {
+        blockCounts[2 * blockIdx.x] = total[0];
+        blockCounts[2 * blockIdx.x + 1] = total[1];
+    }
+}
+
+__global__ void __launch_bounds__(SL_THREADS) selectScanKernel(int64_t* blockCounts, int64_t numBlocks, int64_t* totals)
+{
+    __shared__ long long sCarry[2];
+    if (threadIdx.x < 2) sCarry[threadIdx.x] = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < numBlocks; base += SL_THREADS)
+    {
+        const int64_t b = base + threadIdx.x;
+        long long v[2], total[2];
+        v[0] = (b < numBlocks) ? blockCounts[2 * b] : 0;
+        v[1] = (b < numBlocks) ? blockCounts[2 * b + 1] : 0;
+        blockScan2(v, total);
+        if (b < numBlocks)
+        {
+            blockCounts[2 * b] = v[0] + sCarry[0];
+            blockCounts[2 * b + 1] = v[1] + sCarry[1];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            sCarry[0] += total[0];
+            sCarry[1] += total[1];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 2) totals[threadIdx.x] = sCarry[threadIdx.x];
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(SL_THREADS)
+    selectIndexKernel(const double4* pos, const signed char* flag, int64_t first, int64_t n, double lowBound,
+                      double highBound, const int64_t* blockOffsets, int32_t* lowIdx, int32_t* highIdx)
+{
+    const int64_t j = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    long long v[2] = {0, 0}, total[2];
+    bool lo = false, hi = false;
+    if (j < n)
+    {
+        selectPredicates<MODE>(pos, flag, first + j, lowBound, highBound, lo, hi);
+        v[0] = lo;
+        v[1] = hi;
+    }
+    blockScan2(v, total);
+    if (lo) lowIdx[blockOffsets[2 * blockIdx.x] + v[0]] = static_cast<int32_t>(first + j);
+    if (hi) highIdx[blockOffsets[2 * blockIdx.x + 1] + v[1]] = static_cast<int32_t>(first + j);
+}
+
+// full records of the migrating atoms, x shifted by `shift` (periodic wrap at the global ends)
+__global__ void packRecordsKernel(AtomsView a, const int32_t* idx, int64_t n, double shift, double* buf)
+{
+    const int64_t k = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (k >= n) return;
+    const int64_t i = idx[k];
+    const double4 p = ld4(a.pos + i);
+    double* r = buf + k * SL_RECORD;
+    r[0] = p.x + shift;
+    r[1] = p.y;
+    r[2] = p.z;
+    r[3] = p.w;
+    for (int d = 0; d < 3; ++d)
+    {
+        r[4 + d] = a.vel[d][i];
+        r[7 + d] = a.force[d][i];
+    }
+    r[10] = a.mass[i];
+    r[11] = a.charge[i];
+    r[12] = a.relMass[i];
+}
+
+__global__ void unpackRecordsKernel(AtomsView a, int64_t first, int64_t n, const double* buf, signed char* flag)
+{
+    const int64_t k = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (k >= n) return;
+    const int64_t i = first + k;
+    const double* r = buf + k * SL_RECORD;
+    st4(a.pos + i, make_double4(r[0], r[1], r[2], r[3]));
+    for (int d = 0; d < 3; ++d)
+    {
+        a.vel[d][i] = r[4 + d];
+        a.force[d][i] = r[7 + d];
+    }
+    a.mass[i] = r[10];
+    a.charge[i] = r[11];
+    a.relMass[i] = r[12];
+    flag[i] = 0;
+}
+
+// positions (+ type bits) of the halo atoms, x shifted by `shift`
+__global__ void packPositionsKernel(const double4* pos, const int32_t* idx, int64_t n, double shift, double4* buf)
+{
+    const int64_t k = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (k >= n) return;
+    double4 p = ld4(pos + idx[k]);
+    p.x += shift;
+    st4(buf + k, p);
+}
+
+// (j, k) cell of a halo atom in the receiver's grid (identical y / z grid on every rank)
+__global__ void haloKeyKernel(const double4* pos, int64_t first, int64_t n, GridDev g, uint32_t* keys)
+{
+    const int64_t k = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (k >= n) return;
+    const double4 p = ld4nc(pos + first + k);
+    keys[k] = static_cast<uint32_t>(locate1(g, p.y, 1) * g.n[2] + locate1(g, p.z, 2));
+}
+
+// defined in neighbor.cu
+int atomsCellSortDrop(mrmd_b200_atoms* a, int64_t begin, int64_t end, const double* delta, const double* gridMin,
+                      const double* gridMax, const signed char* dropFlags, cudaStream_t st);
+int cellStartFromKeys(const uint32_t* sortedKeys, int64_t n, int64_t numCells, int32_t* cellStart, int32_t offset,
+                      cudaStream_t st);
+}  // namespace mrmd_b200
+
+struct mrmd_b200_slab
+{
+    mrmd_b200_md_config cfg{};
+    int rank = 0, nranks = 1, left = 0, right = 0;
+    double globalMin[3]{}, globalMax[3]{};
+    double shiftToLeft = 0.0, shiftToRight = 0.0;  // added to x when sending across the global boundary
+    mrmd_b200_subdomain sub{};                     // this rank's slab
+    ncclComm_t comm = nullptr;
+    mrmd_b200_atoms* atoms = nullptr;  // not owned
+    mrmd_b200_verlet* list = nullptr;
+    mrmd_b200_lj* lj = nullptr;
+    double maxDisplacement = DBL_MAX;
+    int64_t step = 0, rebuilds = 0, storedPairsNow = 0;
+    int64_t haloLeftCount = 0, haloRightCount = 0;   // received
+    int64_t sendLeftCount = 0, sendRightCount = 0;   // boundary atoms sent every step
+    mrmd_b200::DevBuf flags, blockCounts, idxLow, idxHigh, sendBuf, recvBuf, haloKeys, haloStartLeft, haloStartRight;
+    int64_t* dTotals = nullptr;  // [0..1] select totals, [2..5] exchanged counts
+    int64_t* hTotals = nullptr;  // pinned, 8 entries
+    double* dScalars = nullptr;  // allreduce scratch
+    double* hScalars = nullptr;  // pinned
+    std::vector<cudaEvent_t> events;
+};
+
+namespace mrmd_b200
+{
+template <int MODE>
+static int selectTwo(mrmd_b200_slab* sl, int64_t first, int64_t n, double lowBound, double highBound, int64_t* nLow,
+                     int64_t* nHigh, cudaStream_t st)
+{
+    mrmd_b200_atoms* a = sl->atoms;
+    *nLow = *nHigh = 0;
+    if (n <= 0) return 0;
+    const int blocks = gridFor(n, SL_THREADS);
+    MB_TRY(sl->blockCounts.reserve(size_t(blocks) * 16));
+    int64_t* bc = sl->blockCounts.as<int64_t>();
+    const signed char* flag = sl->flags.as<signed char>();
+    selectCountKernel<MODE><<<blocks, SL_THREADS, 0, st>>>(a->v.pos, flag, first, n, lowBound, highBound, bc);
+    MB_LAUNCHED();
+    selectScanKernel<<<1, SL_THREADS, 0, st>>>(bc, blocks, sl->dTotals);
+    MB_LAUNCHED();
+    MB_CUDA(cudaMemcpyAsync(sl->hTotals, sl->dTotals, 16, cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaStreamSynchronize(st));
+    *nLow = sl->hTotals[0];
+    *nHigh = sl->hTotals[1];
+    MB_TRY(sl->idxLow.reserve(size_t(std::max<int64_t>(*nLow, 1)) * 4));
+    MB_TRY(sl->idxHigh.reserve(size_t(std::max<int64_t>(*nHigh, 1)) * 4));
+    if (*nLow + *nHigh > 0)
+    {
+        selectIndexKernel<MODE><<<blocks, SL_THREADS, 0, st>>>(a->v.pos, flag, first, n, lowBound, highBound, bc,
+                                                               sl->idxLow.as<int32_t>(), sl->idxHigh.as<int32_t>());
+        MB_LAUNCHED();
+    }
+    return 0;
+}
+
+// counts to the neighbours: I tell left how many atoms come from its right side and vice versa
+static int exchangeCounts(mrmd_b200_slab* sl, int64_t toLeft, int64_t toRight, int64_t* fromLeft, int64_t* fromRight,
+                          cudaStream_t st)
+{
+    sl->hTotals[2] = toLeft;
+    sl->hTotals[3] = toRight;
+    MB_CUDA(cudaMemcpyAsync(sl->dTotals + 2, sl->hTotals + 2, 16, cudaMemcpyHostToDevice, st));
+    MB_NCCL(g_nccl.groupStart());
+    MB_NCCL(g_nccl.send(sl->dTotals + 2, 1, ncclInt64, sl->left, sl->comm, st));
+    MB_NCCL(g_nccl.send(sl->dTotals + 3, 1, ncclInt64, sl->right, sl->comm, st));
+    MB_NCCL(g_nccl.recv(sl->dTotals + 5, 1, ncclInt64, sl->right, sl->comm, st));  // the right rank's "toLeft"
+    MB_NCCL(g_nccl.recv(sl->dTotals + 4, 1, ncclInt64, sl->left, sl->comm, st));   // the left rank's "toRight"
+    MB_NCCL(g_nccl.groupEnd());
+    MB_CUDA(cudaMemcpyAsync(sl->hTotals + 4, sl->dTotals + 4, 16, cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaStreamSynchronize(st));
+    *fromLeft = sl->hTotals[4];
+    *fromRight = sl->hTotals[5];
+    return 0;
+}
+
+static int migrate(mrmd_b200_slab* sl, cudaStream_t st)
+{
+    mrmd_b200_atoms* a = sl->atoms;
+    const int64_t n = a->numLocal;
+    a->numGhost = 0;
+    a->size = n;
+    MB_TRY(sl->flags.reserve(size_t(a->capacity) + 64));
+    if (n > 0)
+    {
+        slabWrapFlagKernel<<<gridFor(n, 256), 256, 0, st>>>(a->v.pos, n, toDev(sl->sub), sl->flags.as<signed char>());
+        MB_LAUNCHED();
+    }
+    int64_t toLeft = 0, toRight = 0, fromLeft = 0, fromRight = 0;
+    MB_TRY(selectTwo<0>(sl, 0, n, 0.0, 0.0, &toLeft, &toRight, st));
+    MB_TRY(exchangeCounts(sl, toLeft, toRight, &fromLeft, &fromRight, st));
+    const int64_t nSend = toLeft + toRight, nRecv = fromLeft + fromRight;
+    MB_TRY(sl->sendBuf.reserve(size_t(std::max<int64_t>(nSend, 1)) * SL_RECORD * 8));
+    MB_TRY(sl->recvBuf.reserve(size_t(std::max<int64_t>(nRecv, 1)) * SL_RECORD * 8));
+    double* sb = sl->sendBuf.as<double>();
+    double* rb = sl->recvBuf.as<double>();
+    if (toLeft > 0)
+    {
+        packRecordsKernel<<<gridFor(toLeft, 256), 256, 0, st>>>(a->v, sl->idxLow.as<int32_t>(), toLeft, sl->shiftToLeft, sb);
+        MB_LAUNCHED();
+    }
+    if (toRight > 0)
+    {
+        packRecordsKernel<<<gridFor(toRight, 256), 256, 0, st>>>(a->v, sl->idxHigh.as<int32_t>(), toRight,
+                                                                sl->shiftToRight, sb + toLeft * SL_RECORD);
+        MB_LAUNCHED();
+    }
+    MB_NCCL(g_nccl.groupStart());
+    if (toLeft > 0) MB_NCCL(g_nccl.send(sb, size_t(toLeft) * SL_RECORD, ncclDouble, sl->left, sl->comm, st));
+    if (toRight > 0)
+        MB_NCCL(g_nccl.send(sb + toLeft * SL_RECORD, size_t(toRight) * SL_RECORD, ncclDouble, sl->right, sl->comm, st));
+    if (fromRight > 0) MB_NCCL(g_nccl.recv(rb, size_t(fromRight) * SL_RECORD, ncclDouble, sl->right, sl->comm, st));
+    if (fromLeft > 0)
+        MB_NCCL(g_nccl.recv(rb + fromRight * SL_RECORD, size_t(fromLeft) * SL_RECORD, ncclDouble, sl->left, sl->comm, st));
+    MB_NCCL(g_nccl.groupEnd());
+    // arrivals are appended, leavers are dropped by the cell sort (they sort behind the last cell)
+    MB_TRY(atomsEnsureCapacity(a, n + nRecv, st));
+    if (sl->flags.bytes < size_t(n + nRecv) + 64)
+    {
+        // grow the flag array keeping the flags of the n resident atoms
+        mrmd_b200::DevBuf bigger;
+        MB_TRY(bigger.reserve(size_t(a->capacity) * 2 + 64));
+        if (n > 0) MB_CUDA(cudaMemcpyAsync(bigger.p, sl->flags.p, size_t(n), cudaMemcpyDeviceToDevice, st));
+        MB_CUDA(cudaStreamSynchronize(st));
+        sl->flags.release();
+        sl->flags = bigger;
+    }
+    a->size = n + nRecv;
+    if (nRecv > 0)
+    {
+        unpackRecordsKernel<<<gridFor(nRecv, 256), 256, 0, st>>>(a->v, n, nRecv, rb, sl->flags.as<signed char>());
+        MB_LAUNCHED();
+    }
+    const double cutoff = sl->cfg.rc + sl->cfg.skin;
+    const double delta[3] = {cutoff, cutoff, cutoff};
+    MB_TRY(atomsCellSortDrop(a, 0, n + nRecv, delta, sl->sub.minCorner, sl->sub.maxCorner, sl->flags.as<signed char>(), st));
+    a->numLocal = n + nRecv - nSend;
+    a->size = a->numLocal;
+    a->lcEnd = a->numLocal;
+    return 0;
+}
+
+static int haloExchange(mrmd_b200_slab* sl, cudaStream_t st)
+{
+    mrmd_b200_atoms* a = sl->atoms;
+    const GridDev& g = a->lcGrid;
+    const int64_t perX = int64_t(g.n[1]) * g.n[2];
+    const int64_t n = a->numLocal;
+    // boundary atoms live in the first / last cell column (ghost layer thickness <= cell size)
+    MB_CUDA(cudaMemcpyAsync(sl->hTotals + 6, a->lcCellStart.as<int32_t>() + perX, 4, cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaMemcpyAsync(reinterpret_cast<int32_t*>(sl->hTotals + 6) + 1,
+                            a->lcCellStart.as<int32_t>() + (int64_t(g.n[0]) - 1) * perX, 4, cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaStreamSynchronize(st));
+    const int64_t firstColEnd = reinterpret_cast<int32_t*>(sl->hTotals + 6)[0];
+    const int64_t lastColStart = reinterpret_cast<int32_t*>(sl->hTotals + 6)[1];
+    int64_t nl = 0, dummy = 0, nh = 0;
+    // low face: x < minInner within column 0 ; high face: x >= maxInner within column nx-1
+    MB_TRY(selectTwo<1>(sl, 0, firstColEnd, sl->sub.minInnerCorner[0], DBL_MAX, &nl, &dummy, st));
+    // keep the low list: copy it aside before the second selection reuses the buffers
+    MB_TRY(sl->sendBuf.reserve(size_t(std::max<int64_t>(nl, 1)) * 4 + 64));
+    if (nl > 0) MB_CUDA(cudaMemcpyAsync(sl->sendBuf.p, sl->idxLow.p, size_t(nl) * 4, cudaMemcpyDeviceToDevice, st));
+    MB_TRY(selectTwo<1>(sl, lastColStart, n - lastColStart, -DBL_MAX, sl->sub.maxInnerCorner[0], &dummy, &nh, st));
+    if (nl > 0)
+    {
+        MB_TRY(sl->idxLow.reserve(size_t(nl) * 4));
+        MB_CUDA(cudaMemcpyAsync(sl->idxLow.p, sl->sendBuf.p, size_t(nl) * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    sl->sendLeftCount = nl;
+    sl->sendRightCount = nh;
+    int64_t fromLeft = 0, fromRight = 0;
+    MB_TRY(exchangeCounts(sl, nl, nh, &fromLeft, &fromRight, st));
+    sl->haloLeftCount = fromLeft;
+    sl->haloRightCount = fromRight;
+    MB_TRY(atomsEnsureCapacity(a, n + fromLeft + fromRight, st));
+    a->numGhost = fromLeft + fromRight;
+    a->size = n + a->numGhost;
+    return 0;
+}
+
+// positions of the boundary atoms -> neighbours' halo slots [n, n + haloLeft) and [n + haloLeft, ...)
+static int haloRefresh(mrmd_b200_slab* sl, cudaStream_t st)
+{
+    mrmd_b200_atoms* a = sl->atoms;
+    const int64_t n = a->numLocal, nl = sl->sendLeftCount, nh = sl->sendRightCount;
+    MB_TRY(sl->sendBuf.reserve(size_t(std::max<int64_t>(nl + nh, 1)) * 32));
+    double4* sb = sl->sendBuf.as<double4>();
+    if (nl > 0)
+    {
+        packPositionsKernel<<<gridFor(nl, 256), 256, 0, st>>>(a->v.pos, sl->idxLow.as<int32_t>(), nl, sl->shiftToLeft, sb);
+        MB_LAUNCHED();
+    }
+    if (nh > 0)
+    {
+        packPositionsKernel<<<gridFor(nh, 256), 256, 0, st>>>(a->v.pos, sl->idxHigh.as<int32_t>(), nh, sl->shiftToRight,
+                                                              sb + nl);
+        MB_LAUNCHED();
+    }
+    MB_NCCL(g_nccl.groupStart());
+    if (nl > 0) MB_NCCL(g_nccl.send(sb, size_t(nl) * 4, ncclDouble, sl->left, sl->comm, st));
+    if (nh > 0) MB_NCCL(g_nccl.send(sb + nl, size_t(nh) * 4, ncclDouble, sl->right, sl->comm, st));
+    if (sl->haloRightCount > 0)
+        MB_NCCL(g_nccl.recv(a->v.pos + n + sl->haloLeftCount, size_t(sl->haloRightCount) * 4, ncclDouble, sl->right,
+                            sl->comm, st));
+    if (sl->haloLeftCount > 0)
+        MB_NCCL(g_nccl.recv(a->v.pos + n, size_t(sl->haloLeftCount) * 4, ncclDouble, sl->left, sl->comm, st));
+    MB_NCCL(g_nccl.groupEnd());
+    return 0;
+}
+
+static int slabRebuild(mrmd_b200_slab* sl, cudaStream_t st)
+{
+    mrmd_b200_atoms* a = sl->atoms;
+    MB_TRY(migrate(sl, st));
+    MB_TRY(haloExchange(sl, st));
+    MB_TRY(haloRefresh(sl, st));
+    // linked cells of the received halo atoms: they arrive in (j, k) order
+    const GridDev& g = a->lcGrid;
+    const int64_t perX = int64_t(g.n[1]) * g.n[2];
+    const int64_t n = a->numLocal;
+    MB_TRY(sl->haloKeys.reserve(size_t(std::max<int64_t>(a->numGhost, 1)) * 4));
+    MB_TRY(sl->haloStartLeft.reserve(size_t(perX + 1) * 4));
+    MB_TRY(sl->haloStartRight.reserve(size_t(perX + 1) * 4));
+    uint32_t* keys = sl->haloKeys.as<uint32_t>();
+    if (a->numGhost > 0)
+    {
+        haloKeyKernel<<<gridFor(a->numGhost, 256), 256, 0, st>>>(a->v.pos, n, a->numGhost, g, keys);
+        MB_LAUNCHED();
+    }
+    MB_TRY(cellStartFromKeys(keys, sl->haloLeftCount, perX, sl->haloStartLeft.as<int32_t>(), static_cast<int32_t>(n), st));
+    MB_TRY(cellStartFromKeys(keys + sl->haloLeftCount, sl->haloRightCount, perX, sl->haloStartRight.as<int32_t>(),
+                             static_cast<int32_t>(n + sl->haloLeftCount), st));
+    const double cutoff = sl->cfg.rc + sl->cfg.skin;
+    MB_TRY(verletBuildTiled(sl->list, a, &sl->sub, cutoff, 1.0, sl->cfg.maxNeighbors, sl->haloStartLeft.as<int32_t>(),
+                            sl->haloStartRight.as<int32_t>(), st));
+    int64_t total = 0;
+    MB_TRY(mrmd_b200_verlet_info(sl->list, nullptr, nullptr, &total, nullptr));
+    sl->storedPairsNow = total;
+    sl->rebuilds += 1;
+    return 0;
+}
+
+static int slabStep(mrmd_b200_slab* sl, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, bool wantEnergy)
+{
+    const mrmd_b200_md_config& c = sl->cfg;
+    mrmd_b200_atoms* a = sl->atoms;
+    if (c.integrator == 1)
+        MB_TRY(mrmd_b200_langevin_pre(a, c.dt, c.zeta, c.temperature, c.seed + uint64_t(sl->rank), uint64_t(sl->step),
+                                      nullptr, nullptr, st));
+    else
+        MB_TRY(mrmd_b200_vv_pre(a, c.dt, nullptr, st));
+    // the rebuild decision is collective: global maximum of the squared displacement
+    MB_NCCL(g_nccl.allReduce(a->dMaxDisp, a->dMaxDisp, 1, ncclDouble, ncclMax, sl->comm, st));
+    MB_CUDA(cudaMemcpyAsync(a->hMaxDisp, a->dMaxDisp, 8, cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaStreamSynchronize(st));
+    sl->maxDisplacement += std::sqrt(*a->hMaxDisp);
+    if (sl->maxDisplacement >= c.skin * 0.5)
+    {
+        sl->maxDisplacement = 0.0;
+        MB_TRY(slabRebuild(sl, st));
+    }
+    else
+        MB_TRY(haloRefresh(sl, st));
+    if (e0) MB_CUDA(cudaEventRecord(e0, st));
+    MB_TRY(ljApplyTiled(sl->lj, a, sl->list, false, wantEnergy, st));
+    if (e1) MB_CUDA(cudaEventRecord(e1, st));
+    MB_TRY(mrmd_b200_vv_post(a, c.dt, st));
+    sl->step += 1;
+    return 0;
+}
+}  // namespace mrmd_b200
+
+using namespace mrmd_b200;
+
+extern "C" {
+
+int mrmd_b200_nccl_unique_id(void* out128)
+{
+    MB_TRY(checkDevice());
+    MB_REQUIRE(out128 != nullptr, "nccl_unique_id");
+    MB_TRY(loadNccl());
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    MB_NCCL(g_nccl.getUniqueId(&id));
+    std::memcpy(out128, &id, 128);
+    return 0;
+}
+
+int mrmd_b200_slab_create(mrmd_b200_slab** out, const mrmd_b200_md_config* cfg, const double* globalMin,
+                          const double* globalMax, int rank, int nranks, const void* uniqueId128, mrmd_b200_atoms* atoms,
+                          void* stream)
+{
+    MB_TRY(checkDevice());
+    MB_REQUIRE(out && cfg && globalMin && globalMax && uniqueId128 && atoms, "slab_create");
+    MB_REQUIRE(nranks >= 2 && rank >= 0 && rank < nranks, "slab_create: needs at least two ranks");
+    MB_REQUIRE(!cfg->adress, "slab_create: the x-slab driver covers the Lennard-Jones step loop");
+    MB_TRY(loadNccl());
+    auto* sl = new mrmd_b200_slab;
+    sl->cfg = *cfg;
+    sl->rank = rank;
+    sl->nranks = nranks;
+    sl->left = (rank - 1 + nranks) % nranks;
+    sl->right = (rank + 1) % nranks;
+    const double cutoff = cfg->rc + cfg->skin;
+    const double lx = globalMax[0] - globalMin[0];
+    const double width = lx / nranks;
+    double mn[3] = {globalMin[0] + rank * width, globalMin[1], globalMin[2]};
+    double mx[3] = {(rank == nranks - 1) ? globalMax[0] : globalMin[0] + (rank + 1) * width, globalMax[1], globalMax[2]};
+    const double th[3] = {cutoff, cutoff, cutoff};
+    mrmd_b200_subdomain_init(&sl->sub, mn, mx, th);
+    for (int d = 0; d < 3; ++d)
+    {
+        sl->globalMin[d] = globalMin[d];
+        sl->globalMax[d] = globalMax[d];
+    }
+    sl->shiftToLeft = (rank == 0) ? lx : 0.0;             // crossing the low end of the box: x + Lx
+    sl->shiftToRight = (rank == nranks - 1) ? -lx : 0.0;  // crossing the high end: x - Lx
+    sl->atoms = atoms;
+    int rc = 0;
+    if (width < cutoff)
+    {
+        setLastError("slab_create: slab narrower than rc + skin");
+        rc = MRMD_B200_EINVAL;
+    }
+    ncclUniqueId id;
+    std::memcpy(&id, uniqueId128, 128);
+    if (rc == 0 && g_nccl.commInitRank(&sl->comm, nranks, id, rank) != ncclSuccess)
+    {
+        setLastError("slab_create: ncclCommInitRank failed");
+        rc = MRMD_B200_EINVAL;
+    }
+    if (rc == 0) rc = mrmd_b200_verlet_create(&sl->list, 0);
+    if (rc == 0) rc = mrmd_b200_lj_create(&sl->lj, &cfg->cappingDistance, &cfg->rc, &cfg->sigma, &cfg->epsilon, 1, 0);
+    if (rc == 0 && cudaMalloc(&sl->dTotals, 64) != cudaSuccess) rc = MRMD_B200_ENOMEM;
+    if (rc == 0 && cudaMallocHost(&sl->hTotals, 64) != cudaSuccess) rc = MRMD_B200_ENOMEM;
+    if (rc == 0 && cudaMalloc(&sl->dScalars, 64) != cudaSuccess) rc = MRMD_B200_ENOMEM;
+    if (rc == 0 && cudaMallocHost(&sl->hScalars, 64) != cudaSuccess) rc = MRMD_B200_ENOMEM;
+    if (rc != 0)
+    {
+        mrmd_b200_slab_destroy(sl);
+        return rc;
+    }
+    (void)stream;
+    *out = sl;
+    return 0;
+}
+
+int mrmd_b200_slab_destroy(mrmd_b200_slab* sl)
+{
+    if (sl == nullptr) return 0;
+    cudaDeviceSynchronize();
+    for (auto e : sl->events) cudaEventDestroy(e);
+    if (sl->comm != nullptr) g_nccl.commDestroy(sl->comm);
+    mrmd_b200_verlet_destroy(sl->list);
+    mrmd_b200_lj_destroy(sl->lj);
+    if (sl->dTotals) cudaFree(sl->dTotals);
+    if (sl->hTotals) cudaFreeHost(sl->hTotals);
+    if (sl->dScalars) cudaFree(sl->dScalars);
+    if (sl->hScalars) cudaFreeHost(sl->hScalars);
+    for (mrmd_b200::DevBuf* b : {&sl->flags, &sl->blockCounts, &sl->idxLow, &sl->idxHigh, &sl->sendBuf, &sl->recvBuf,
+                                 &sl->haloKeys, &sl->haloStartLeft, &sl->haloStartRight})
+        b->release();
+    delete sl;
+    return 0;
+}
+
+int mrmd_b200_slab_run(mrmd_b200_slab* sl, int64_t nsteps, int timeForceKernel, mrmd_b200_md_stats* stats, void* stream)
+{
+    MB_TRY(checkDevice());
+    MB_REQUIRE(sl != nullptr && nsteps >= 0, "slab_run");
+    cudaStream_t st = S(stream);
+    const int64_t rebuilds0 = sl->rebuilds;
+    MB_CUDA(cudaMemcpyAsync(sl->lj->hResult, sl->lj->dResult, 48, cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaStreamSynchronize(st));
+    const double pairs0 = sl->lj->hResult[5];
+    const int nTimed = timeForceKernel ? static_cast<int>(std::min<int64_t>(nsteps, 1 << 16)) : 0;
+    while (static_cast<int>(sl->events.size()) < 2 * nTimed)
+    {
+        cudaEvent_t e;
+        MB_CUDA(cudaEventCreate(&e));
+        sl->events.push_back(e);
+    }
+    int64_t storedSum = 0;
+    for (int64_t i = 0; i < nsteps; ++i)
+    {
+        MB_TRY(slabStep(sl, st, i < nTimed ? sl->events[2 * i] : nullptr, i < nTimed ? sl->events[2 * i + 1] : nullptr,
+                        i == nsteps - 1));
+        storedSum += sl->storedPairsNow;
+    }
+    MB_CUDA(cudaMemcpyAsync(sl->lj->hResult, sl->lj->dResult, 48, cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaStreamSynchronize(st));
+    if (stats != nullptr)
+    {
+        // energy and virial of the last step summed over the ranks
+        sl->hScalars[0] = sl->lj->hResult[0];
+        sl->hScalars[1] = sl->lj->hResult[1];
+        MB_CUDA(cudaMemcpyAsync(sl->dScalars, sl->hScalars, 16, cudaMemcpyHostToDevice, st));
+        MB_NCCL(g_nccl.allReduce(sl->dScalars, sl->dScalars, 2, ncclDouble, ncclSum, sl->comm, st));
+        MB_CUDA(cudaMemcpyAsync(sl->hScalars, sl->dScalars, 16, cudaMemcpyDeviceToHost, st));
+        MB_CUDA(cudaStreamSynchronize(st));
+        stats->steps = nsteps;
+        stats->rebuilds = sl->rebuilds - rebuilds0;
+        stats->storedPairs = storedSum;
+        stats->numLocal = sl->atoms->numLocal;
+        stats->numGhost = sl->atoms->numGhost;
+        stats->energy = sl->hScalars[0];
+        stats->virial = sl->hScalars[1];
+        stats->pairInteractions = static_cast<int64_t>(sl->lj->hResult[5] - pairs0 + 0.5);
+        stats->maxDisplacement = sl->maxDisplacement;
+        double ms = 0.0;
+        for (int i = 0; i < nTimed; ++i)
+        {
+            float t = 0.f;
+            MB_CUDA(cudaEventElapsedTime(&t, sl->events[2 * i], sl->events[2 * i + 1]));
+            ms += t;
+        }
+        stats->forceKernelMs = ms;
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -41,8 +41,16 @@ struct TileParams
     int periodic[3];  // ghost layer thickness > 0 on that axis
     double L[3];      // subdomain.diameter
     double minInner[3], maxInner[3];
-    int cap;  // shared-memory slots per tile
+    int cap;    // shared-memory slots per tile
+    int haloX;  // x-slab decomposition: columns -1 and nx hold the halo atoms received from the neighbour ranks
 };
+
+// cell ranges are looked up in cellLo / cellHi (absolute atom indices) indexed over the grid extended by the
+// two halo columns when haloX is set
+__device__ __forceinline__ int extCell(const TileParams& tp, int i, int j, int k)
+{
+    return ((i + tp.haloX) * tp.g.n[1] + j) * tp.g.n[2] + k;
+}
 
 // descriptor layout (ints): [0..26] pieceStart, [27..53] pieceLen, [54] homeStart, [55] homeCount,
 // [56] slot of the first home atom, [57] total slots
@@ -59,14 +67,14 @@ __device__ __forceinline__ void pieceShift(const TileParams& tp, int ci, int cj,
 {
     const int r = p / 3, w = p % 3;
     const int ii = ci + r / 3 - 1, jj = cj + r % 3 - 1;
-    sx = (ii < 0) ? -1 : ((ii >= tp.g.n[0]) ? 1 : 0);
+    sx = tp.haloX ? 0 : ((ii < 0) ? -1 : ((ii >= tp.g.n[0]) ? 1 : 0));  // halo atoms arrive already shifted
     sy = (jj < 0) ? -1 : ((jj >= tp.g.n[1]) ? 1 : 0);
     sz = (w == 0) ? -1 : ((w == 2) ? 1 : 0);
 }
 
 // one block per tile: writes the descriptor (once per rebuild)
-__global__ void __launch_bounds__(32) tileDescKernel(TileParams tp, const int32_t* __restrict__ cellStart, int* desc,
-                                                     int* maxSlots)
+__global__ void __launch_bounds__(32) tileDescKernel(TileParams tp, const int32_t* __restrict__ cellLo,
+                                                     const int32_t* __restrict__ cellHi, int* desc, int* maxSlots)
 {
     const int tile = blockIdx.x;
     const int col = tile / tp.numChunks, chunk = tile % tp.numChunks;
@@ -89,8 +97,8 @@ __global__ void __launch_bounds__(32) tileDescKernel(TileParams tp, const int32_
         else { klo = khi = 0; exists = exists && (k1 == nz - 1) && tp.periodic[2]; }
         if (exists)
         {
-            start = cellStart[cardinal(tp.g, ii, jj, klo)];
-            len = cellStart[cardinal(tp.g, ii, jj, khi) + 1] - start;
+            start = cellLo[extCell(tp, ii, jj, klo)];
+            len = cellHi[extCell(tp, ii, jj, khi)] - start;
         }
         desc[tile * TL_DESC_INTS + t] = start;
         desc[tile * TL_DESC_INTS + TL_PIECES + t] = len;
@@ -105,9 +113,9 @@ __global__ void __launch_bounds__(32) tileDescKernel(TileParams tp, const int32_
     }
     if (t == 0)
     {
-        const int homeStart = cellStart[cardinal(tp.g, ci, cj, k0)];
-        const int homeCount = cellStart[cardinal(tp.g, ci, cj, k1) + 1] - homeStart;
-        const int centreStart = cellStart[cardinal(tp.g, ci, cj, max(k0 - 1, 0))];
+        const int homeStart = cellLo[extCell(tp, ci, cj, k0)];
+        const int homeCount = cellHi[extCell(tp, ci, cj, k1)] - homeStart;
+        const int centreStart = cellLo[extCell(tp, ci, cj, max(k0 - 1, 0))];
         desc[tile * TL_DESC_INTS + 54] = homeStart;
         desc[tile * TL_DESC_INTS + 55] = homeCount;
         desc[tile * TL_DESC_INTS + 56] = before + (homeStart - centreStart);
@@ -213,7 +221,7 @@ __device__ __forceinline__ bool cabanaCellReachable(const GridDev& cg, double px
 template <bool HALF>
 __global__ void __launch_bounds__(TL_THREADS)
     verletBuildTiledKernel(TileParams tp, GridDev cabanaGrid, const double4* __restrict__ pos,
-                           const int32_t* __restrict__ cellStart, const int* __restrict__ desc, double rsqr, int width,
+                           const int32_t* __restrict__ cellLo, const int* __restrict__ desc, double rsqr, int width,
                            int32_t* __restrict__ counts, uint16_t* __restrict__ enc, int32_t* stats)
 {
     extern __shared__ double sTile[];
@@ -244,9 +252,12 @@ __global__ void __launch_bounds__(TL_THREADS)
         else
         {
             int ii = ci + r / 3 - 1, jj = cj + r % 3 - 1;
-            if (ii < 0) ii += tp.g.n[0]; else if (ii >= tp.g.n[0]) ii -= tp.g.n[0];
+            if (!tp.haloX)
+            {
+                if (ii < 0) ii += tp.g.n[0]; else if (ii >= tp.g.n[0]) ii -= tp.g.n[0];
+            }
             if (jj < 0) jj += tp.g.n[1]; else if (jj >= tp.g.n[1]) jj -= tp.g.n[1];
-            slot = td.pieceSlot[r * 3 + 1] + (cellStart[cardinal(tp.g, ii, jj, kv)] - td.pieceStart[r * 3 + 1]);
+            slot = td.pieceSlot[r * 3 + 1] + (cellLo[extCell(tp, ii, jj, kv)] - td.pieceStart[r * 3 + 1]);
         }
         cellSlot[r][v] = slot;
     }
@@ -487,9 +498,28 @@ __global__ void __launch_bounds__(TL_THREADS)
     }
 }
 
-static int makeTileParams(const mrmd_b200_atoms* a, const mrmd_b200_subdomain* s, int CH, int cap, TileParams& tp)
+// cellLo / cellHi over the extended grid: local cells from the linked-cell prefix array, halo columns (x-slab
+// decomposition) from the per-column prefix arrays of the received halo atoms
+__global__ void extCellRangesKernel(const int32_t* __restrict__ localStart, int64_t numLocalCells,
+                                    const int32_t* __restrict__ haloLeft, const int32_t* __restrict__ haloRight,
+                                    int64_t cellsPerColumnX, int32_t* cellLo, int32_t* cellHi)
+{
+    const int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    const int64_t haloCells = (haloLeft != nullptr) ? cellsPerColumnX : 0;
+    if (c >= numLocalCells + 2 * haloCells) return;
+    int32_t lo, hi;
+    if (c < haloCells) { lo = haloLeft[c]; hi = haloLeft[c + 1]; }
+    else if (c < haloCells + numLocalCells) { lo = localStart[c - haloCells]; hi = localStart[c - haloCells + 1]; }
+    else { lo = haloRight[c - haloCells - numLocalCells]; hi = haloRight[c - haloCells - numLocalCells + 1]; }
+    cellLo[c] = lo;
+    cellHi[c] = hi;
+}
+
+static int makeTileParams(const mrmd_b200_atoms* a, const mrmd_b200_subdomain* s, int CH, int cap, int haloX,
+                          TileParams& tp)
 {
     tp.g = a->lcGrid;
+    tp.haloX = haloX;
     tp.CH = CH;
     tp.numChunks = (tp.g.n[2] + CH - 1) / CH;
     tp.cap = cap;
@@ -535,7 +565,7 @@ int ljApplyTiled(mrmd_b200_lj* lj, mrmd_b200_atoms* a, const mrmd_b200_verlet* v
     MB_REQUIRE(!v->half, "lj_apply: tiled lists are full lists");
     MB_TRY(tiledConfigure());
     TileParams tp;
-    MB_TRY(makeTileParams(a, &v->tiledSub, v->tiledCH, v->tiledSlots, tp));
+    MB_TRY(makeTileParams(a, &v->tiledSub, v->tiledCH, v->tiledSlots, v->tiledHaloX, tp));
     const int tiles = tp.g.n[0] * tp.g.n[1] * tp.numChunks;
     MB_TRY(lj->partials.reserve(size_t(tiles) * 3 * 8));
     MB_CUDA(cudaMemsetAsync(lj->dResult, 0, 24, st));
@@ -561,14 +591,15 @@ int ljApplyTiled(mrmd_b200_lj* lj, mrmd_b200_atoms* a, const mrmd_b200_verlet* v
 }
 }  // namespace mrmd_b200
 
-using namespace mrmd_b200;
-
-extern "C" {
-
-int mrmd_b200_verlet_build_periodic(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, const mrmd_b200_subdomain* s,
-                                    double radius, double cellRatio, int64_t maxNeigh, void* stream)
+namespace mrmd_b200
 {
-    MB_TRY(checkDevice());
+// haloLeft / haloRight (device, ny * nz + 1 absolute prefix indices each, or nullptr): x-slab decomposition, the
+// atoms received from the left / right neighbour rank sit behind the local atoms in (j, k) cell order
+int verletBuildTiled(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, const mrmd_b200_subdomain* s, double radius,
+                     double cellRatio, int64_t maxNeigh, const int32_t* haloLeft, const int32_t* haloRight,
+                     cudaStream_t st)
+{
+    const int haloX = (haloLeft != nullptr && haloRight != nullptr) ? 1 : 0;
     MB_REQUIRE(v != nullptr && a != nullptr && s != nullptr, "verlet_build_periodic");
     MB_REQUIRE(radius > 0.0 && cellRatio > 0.0 && maxNeigh > 0, "verlet_build_periodic: bad radius / ratio / width");
     MB_REQUIRE(a->lcValid && a->lcBegin == 0 && a->lcEnd == a->numLocal,
@@ -579,12 +610,12 @@ int mrmd_b200_verlet_build_periodic(mrmd_b200_verlet* v, const mrmd_b200_atoms* 
         MB_REQUIRE(g.min[d] == s->minCorner[d] && std::fabs(g.dx[d] * g.n[d] - s->diameter[d]) <= 1e-9 * s->diameter[d],
                    "verlet_build_periodic: the linked-cell grid must span the subdomain");
         MB_REQUIRE(g.dx[d] >= radius, "verlet_build_periodic: linked cells smaller than the list radius");
-        MB_REQUIRE(g.n[d] >= 3 || s->ghostLayerThickness[d] == 0.0, "verlet_build_periodic: fewer than 3 cells on a periodic axis");
+        MB_REQUIRE(g.n[d] >= 3 || s->ghostLayerThickness[d] == 0.0 || (d == 0 && haloX),
+                   "verlet_build_periodic: fewer than 3 cells on a periodic axis");
         MB_REQUIRE(s->ghostLayerThickness[d] == 0.0 || s->ghostLayerThickness[d] <= g.dx[d],
                    "verlet_build_periodic: ghost layer thicker than a linked cell");
     }
     MB_TRY(tiledConfigure());
-    cudaStream_t st = S(stream);
     const int64_t n = a->numLocal;
     if (v->hStats == nullptr) MB_CUDA(cudaMallocHost(&v->hStats, 16));
     MB_TRY(v->stats.reserve(16));
@@ -597,6 +628,19 @@ int mrmd_b200_verlet_build_periodic(mrmd_b200_verlet* v, const mrmd_b200_atoms* 
     v->tiled = true;
     v->tiledSub = *s;
     v->tiledEpoch = a->lcEpoch;
+    v->tiledHaloX = haloX;
+    {
+        const int64_t perX = int64_t(g.n[1]) * g.n[2];
+        const int64_t extCells = a->lcNumCells + (haloX ? 2 * perX : 0);
+        MB_TRY(v->cellLoHi.reserve(size_t(extCells) * 8));
+        extCellRangesKernel<<<gridFor(extCells, 256), 256, 0, st>>>(a->lcCellStart.as<int32_t>(), a->lcNumCells,
+                                                                   haloX ? haloLeft : nullptr, haloX ? haloRight : nullptr,
+                                                                   perX, v->cellLoHi.as<int32_t>(),
+                                                                   v->cellLoHi.as<int32_t>() + extCells);
+        MB_LAUNCHED();
+    }
+    const int32_t* cellLo = v->cellLoHi.as<int32_t>();
+    const int32_t* cellHi = cellLo + (a->lcNumCells + (haloX ? 2 * int64_t(g.n[1]) * g.n[2] : 0));
     // Cabana's grid for the stencil-pruning check (grid_min/max = ghost corners, delta = radius * ratio)
     const double gs = radius * cellRatio;
     const double delta[3] = {gs, gs, gs};
@@ -610,11 +654,11 @@ int mrmd_b200_verlet_build_periodic(mrmd_b200_verlet* v, const mrmd_b200_atoms* 
     int tiles = 0;
     for (;;)
     {
-        MB_TRY(makeTileParams(a, s, CH, 0, tp));
+        MB_TRY(makeTileParams(a, s, CH, 0, haloX, tp));
         tiles = g.n[0] * g.n[1] * tp.numChunks;
         MB_TRY(v->tileDesc.reserve(size_t(tiles) * TL_DESC_INTS * 4));
         MB_CUDA(cudaMemsetAsync(v->stats.p, 0, 16, st));
-        tileDescKernel<<<tiles, 32, 0, st>>>(tp, a->lcCellStart.as<int32_t>(), v->tileDesc.as<int>(), v->stats.as<int>());
+        tileDescKernel<<<tiles, 32, 0, st>>>(tp, cellLo, cellHi, v->tileDesc.as<int>(), v->stats.as<int>());
         MB_LAUNCHED();
         MB_CUDA(cudaMemcpyAsync(v->hStats, v->stats.p, 4, cudaMemcpyDeviceToHost, st));
         MB_CUDA(cudaStreamSynchronize(st));
@@ -641,11 +685,11 @@ int mrmd_b200_verlet_build_periodic(mrmd_b200_verlet* v, const mrmd_b200_atoms* 
         const size_t smem = size_t(v->tiledSlots) * TL_SMEM_PER_SLOT_BUILD + 16;
         if (v->half)
             verletBuildTiledKernel<true><<<tiles, TL_THREADS, smem, st>>>(
-                tp, cabanaGrid, a->v.pos, a->lcCellStart.as<int32_t>(), v->tileDesc.as<int>(), rsqr,
+                tp, cabanaGrid, a->v.pos, cellLo, v->tileDesc.as<int>(), rsqr,
                 static_cast<int>(width), v->counts.as<int32_t>(), v->enc.as<uint16_t>(), v->stats.as<int32_t>());
         else
             verletBuildTiledKernel<false><<<tiles, TL_THREADS, smem, st>>>(
-                tp, cabanaGrid, a->v.pos, a->lcCellStart.as<int32_t>(), v->tileDesc.as<int>(), rsqr,
+                tp, cabanaGrid, a->v.pos, cellLo, v->tileDesc.as<int>(), rsqr,
                 static_cast<int>(width), v->counts.as<int32_t>(), v->enc.as<uint16_t>(), v->stats.as<int32_t>());
         MB_LAUNCHED();
         MB_CUDA(cudaMemcpyAsync(v->hStats, v->stats.p, 16, cudaMemcpyDeviceToHost, st));
@@ -655,6 +699,18 @@ int mrmd_b200_verlet_build_periodic(mrmd_b200_verlet* v, const mrmd_b200_atoms* 
     }
     setLastError("verlet_build_periodic: neighbour table overflow after refill");
     return MRMD_B200_ECAPACITY;
+}
+}  // namespace mrmd_b200
+
+using namespace mrmd_b200;
+
+extern "C" {
+
+int mrmd_b200_verlet_build_periodic(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, const mrmd_b200_subdomain* s,
+                                    double radius, double cellRatio, int64_t maxNeigh, void* stream)
+{
+    MB_TRY(checkDevice());
+    return verletBuildTiled(v, a, s, radius, cellRatio, maxNeigh, nullptr, nullptr, S(stream));
 }
 
 int mrmd_b200_verlet_read_periodic(const mrmd_b200_verlet* v, const mrmd_b200_atoms* a, int32_t* countsHost,
@@ -667,7 +723,7 @@ int mrmd_b200_verlet_read_periodic(const mrmd_b200_verlet* v, const mrmd_b200_at
     const int64_t n = v->numParticles;
     if (n == 0) return 0;
     TileParams tp;
-    MB_TRY(makeTileParams(a, &v->tiledSub, v->tiledCH, v->tiledSlots, tp));
+    MB_TRY(makeTileParams(a, &v->tiledSub, v->tiledCH, v->tiledSlots, v->tiledHaloX, tp));
     const int tiles = tp.g.n[0] * tp.g.n[1] * tp.numChunks;
     int32_t* d = nullptr;
     MB_CUDA(cudaMalloc(&d, size_t(n) * v->width * 8));

@@ -1,0 +1,99 @@
+"""x-slab decomposition over the GPUs of one node: host-side geometry and the Python face of
+mrmd_b200_slab_* (include/mrmd_b200.h).  One process per GPU; torch.distributed is only used to hand the NCCL
+unique id of rank 0 to the other ranks (any backend: nccl on the GPU box, gloo in the CPU tests)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+
+
+def slab_bounds(global_min, global_max, rank, nranks):
+    """[xlo, xhi) of rank `rank`: equal-width slabs, the last one ends exactly at the global maximum
+    (same arithmetic as mrmd_b200_slab_create)."""
+    gmin, gmax = float(global_min[0]), float(global_max[0])
+    width = (gmax - gmin) / nranks
+    lo = gmin + rank * width
+    hi = gmax if rank == nranks - 1 else gmin + (rank + 1) * width
+    return lo, hi
+
+
+def neighbours(rank, nranks):
+    """(left, right) ranks of the periodic chain"""
+    return (rank - 1 + nranks) % nranks, (rank + 1) % nranks
+
+
+def boundary_shifts(global_min, global_max, rank, nranks):
+    """x shifts applied when an atom is sent (to the left, to the right): the periodic wrap is done by the two
+    end ranks"""
+    lx = float(global_max[0]) - float(global_min[0])
+    return (lx if rank == 0 else 0.0), (-lx if rank == nranks - 1 else 0.0)
+
+
+def owner_of(x, global_min, global_max, nranks):
+    """rank that owns coordinate(s) x (x already wrapped into the global box)"""
+    owners = np.zeros(np.shape(x), dtype=np.int64)
+    for r in range(nranks):
+        lo, hi = slab_bounds(global_min, global_max, r, nranks)
+        owners[(np.asarray(x) >= lo) & (np.asarray(x) < hi)] = r
+    return owners
+
+
+def select_slab(pos, global_min, global_max, rank, nranks):
+    """indices of the atoms of a global configuration that belong to `rank`"""
+    lo, hi = slab_bounds(global_min, global_max, rank, nranks)
+    return np.nonzero((pos[:, 0] >= lo) & (pos[:, 0] < hi))[0]
+
+
+def broadcast_unique_id(rank):
+    """128-byte NCCL unique id of rank 0 on every rank (torch.distributed must be initialised)"""
+    import torch
+    import torch.distributed as dist
+
+    buf = np.zeros(128, dtype=np.uint8)
+    if rank == 0:
+        check(_lib.load().mrmd_b200_nccl_unique_id(buf.ctypes.data))
+    t = torch.from_numpy(buf)
+    backend = dist.get_backend()
+    if backend == "nccl":
+        t = t.cuda()
+    dist.broadcast(t, src=0)
+    return t.cpu().numpy().copy()
+
+
+class SlabMolecularDynamics:
+    """The LJ step loop of MolecularDynamics on this rank's x-slab (mrmd_b200_slab_*)."""
+
+    def __init__(self, atoms, global_min, global_max, rank, nranks, unique_id, dt=0.002, rc=2.5, skin=0.1, sigma=1.0,
+                 epsilon=1.0, cappingDistance=0.7, maxNeighbors=60, langevin=False, zeta=20.0, temperature=1.5,
+                 seed=1234):
+        cfg = _lib.MdConfig()
+        cfg.dt, cfg.rc, cfg.skin, cfg.sigma, cfg.epsilon, cfg.cappingDistance = dt, rc, skin, sigma, epsilon, cappingDistance
+        cfg.maxNeighbors, cfg.integrator, cfg.cellSort, cfg.fullList = maxNeighbors, int(langevin), 1, 2
+        cfg.zeta, cfg.temperature, cfg.seed = zeta, temperature, seed
+        self.cfg, self.atoms = cfg, atoms
+        gmin = np.ascontiguousarray(global_min, dtype=np.float64)
+        gmax = np.ascontiguousarray(global_max, dtype=np.float64)
+        uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
+        assert uid.size == 128
+        self.h = C.c_void_p()
+        check(_lib.load().mrmd_b200_slab_create(C.byref(self.h), C.byref(cfg), gmin.ctypes.data, gmax.ctypes.data, rank,
+                                               nranks, uid.ctypes.data, atoms.h, None))
+
+    def run(self, nsteps, timeForceKernel=False, stream=None):
+        st = _lib.MdStats()
+        check(_lib.load().mrmd_b200_slab_run(self.h, nsteps, int(timeForceKernel), C.byref(st),
+                                            C.c_void_p(stream) if stream else None))
+        return {f: getattr(st, f) for f, _ in st._fields_}
+
+    def close(self):
+        h, self.h = getattr(self, "h", None), None
+        if h:
+            _lib.load().mrmd_b200_slab_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
