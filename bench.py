@@ -172,7 +172,7 @@ def run_reference(args):
         "note": "OpenMP restatement of the reference path (Kokkos 4.7.1 / Cabana 0.7 un-vendored: the reference "
                 "cannot be built offline)",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, n_atoms_per_gpu):
@@ -359,18 +359,32 @@ def run_b200(args):
             "config": workload_config(args, n),
             "pair_interactions_per_s": pairs_total / (ms_max * 1e-3),
             "rebuild_interval_steps": args.steps / max(stats["rebuilds"], 1),
-            "ghosts_per_gpu": stats["numGhost"], "energy_per_atom": stats["energy"] / n,
+            "ghosts_per_gpu": stats["numGhost"], "energy_per_atom": stats["energy"] / (n * (world if slab_mode else 1)),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         import torch.distributed as dist
 
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the one JSON line goes to the process's original stdout"""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    # libraries (NCCL_DEBUG=VERSION, torchrun banners) may print to fd 1: keep stdout for the JSON line only
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
