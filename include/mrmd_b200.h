@@ -143,9 +143,11 @@ int64_t mrmd_b200_atoms_size(const mrmd_b200_atoms* a);
 /* numLocalAtoms / numGhostAtoms (:120-121) */
 int mrmd_b200_atoms_set_counts(mrmd_b200_atoms* a, int64_t numLocal, int64_t numGhost);
 int mrmd_b200_atoms_get_counts(const mrmd_b200_atoms* a, int64_t* numLocal, int64_t* numGhost);
-/* slice transfer.  Element (i, d) of the caller's buffer sits at
- *   buf[((first_in_buf + i) / vlen) * stride + d * vlen + ((first_in_buf + i) % vlen)]
- * which is a Cabana slice (data(), stride(0), vector length); a dense (n, ncomp) array is
+/* slice transfer of atoms [first, first + count).  The caller's buffer starts at atom `first`: element
+ * (j, d), j = 0 .. count-1 (atom first + j), sits at
+ *   buf[(j / vlen) * stride + d * vlen + (j % vlen)]
+ * which is a Cabana slice (data(), stride(0), vector length) offset to tuple `first` (first a multiple
+ * of vlen); a dense (n, ncomp) array is
  * stride = ncomp, vlen = 1; the reference's default AoSoA (MRMD_VECTOR_LENGTH=1) is stride 13.
  * Replaces deep_copy host<->device (data/Atoms.hpp:150-159). */
 int mrmd_b200_atoms_write(mrmd_b200_atoms* a, int field, const void* src, int64_t first, int64_t count,
@@ -338,7 +340,8 @@ typedef struct
     int64_t maxNeighbors;           /* estimatedMaxNeighbors */
     int32_t integrator;             /* 0 VelocityVerlet, 1 VelocityVerletLangevinThermostat */
     int32_t cellSort;               /* 1: LinkedCellList + permute at every rebuild (tests/NVT) */
-    int32_t fullList;               /* 0: HalfVerletList (reference), 1: FullVerletList fast path */
+    int32_t fullList;               /* 0: HalfVerletList (reference), 1: FullVerletList over ghost atoms,
+                                       2: tiled periodic list (mrmd_b200_verlet_build_periodic), no ghost atoms */
     int32_t adress;                 /* 0: LennardJones::apply, 1: AdResS step (one molecule per atom) */
     double zeta, temperature;       /* Langevin: gamma and T */
     uint64_t seed;
