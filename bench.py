@@ -39,6 +39,9 @@ def parse_args():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--replicas", action="store_true", help="N>1: independent periodic replicas instead of x-slabs")
+    p.add_argument("--workload", default="lj", choices=["lj", "adress"],
+                   help="lj: configs[1] (the headline line); adress: configs[2]/[4] physics (LJ / ideal-gas AdResS slab "
+                        "with thermodynamic force, one molecule per atom; use --side 200 for 8M atoms per GPU)")
     return p.parse_args()
 
 
@@ -176,10 +179,15 @@ def run_reference(args):
 
 
 def workload_config(args, n_atoms_per_gpu):
+    lj = ("Lennard-Jones NVT (examples/01 physics, examples/02 rebuild loop, tests/NVT spatial sort) scaled "
+          "to 1M atoms per GPU: sc lattice, rho=0.512, rc=2.5 sigma, skin 0.1, r_cap 0.7, Langevin gamma=20 "
+          "T=1.5, dt=0.002, maxNeighbors 60")
+    ad = ("LJ / ideal-gas AdResS slab (examples/04 physics + the section 3.5 AdResS step): one molecule per atom, sc "
+          "lattice rho=0.512, Slab(centre, AT 0.2 Lx, HY 0.1 Lx, nu 1), LJ_IdealGas(cap 0.7, rc 2.5, shift), "
+          "ThermodynamicForce(rho 0.512, bin 0.25, modulation 2, sample/10, update/1000), Langevin gamma=20 T=1.5, "
+          "dt=0.002, skin 0.1, maxNeighbors 60")
     return {
-        "workload": "Lennard-Jones NVT (examples/01 physics, examples/02 rebuild loop, tests/NVT spatial sort) scaled "
-                    "to 1M atoms per GPU: sc lattice, rho=0.512, rc=2.5 sigma, skin 0.1, r_cap 0.7, Langevin gamma=20 "
-                    "T=1.5, dt=0.002, maxNeighbors 60",
+        "workload": ad if getattr(args, "workload", "lj") == "adress" else lj,
         "atoms_per_gpu": n_atoms_per_gpu, "box_per_gpu": [args.side * 1.25] * 3, "equilibration_steps": args.equil,
         "list": {0: "half (reference semantics, fp64 RED scatter)", 1: "full (generic gather kernel)", 2: "full, periodic tiles staged in shared memory (mrmd_b200_verlet_build_periodic)"}[args.full_list],
         "l2": "inputs larger than L2 (per step: 104 B/atom state + neighbour table ~ 4 B x 19-38 slots/atom > 126 MB "
@@ -214,7 +222,18 @@ def run_b200(args):
     if slab_mode:
         # weak scaling over x-slabs: one global box of world * side x side x side sites, rank r owns slab r
         pos = pos + np.array([rank * box[0], 0.0, 0.0])
-    atoms = api.Atoms.from_arrays(pos, vel, mass=1.0)
+    atoms = api.Atoms.from_arrays(pos, vel, mass=1.0, relativeMass=1.0)
+
+    adress = args.workload == "adress"
+    extra = {}
+    if adress:
+        # configs[2] / configs[4] physics: Slab(centre of the global box, AT diameter 0.2 Lx, HY width 0.1 Lx, nu = 1),
+        # LJ_IdealGas(cap 0.7, rc 2.5, shift on), ThermodynamicForce(rho 0.512, bin 0.25, modulation 2; sample every
+        # 10 steps, update(sigma 2, range 2) every 1000 steps), one molecule per atom
+        lx = box[0] * (world if slab_mode else 1)
+        extra = dict(adress=True, weight=api.Slab([lx / 2, box[1] / 2, box[2] / 2], 0.2 * lx, 0.1 * lx, 1), doShift=True,
+                     thermo=dict(targetDensity=0.512, binWidth=0.25, modulation=2.0, sampleInterval=10,
+                                 updateInterval=1000, sigma=2.0, range=2.0))
 
     def make_md(a):
         if slab_mode:
@@ -225,12 +244,12 @@ def run_b200(args):
                                                uid, dt=PHYS["dt"], rc=PHYS["rc"], skin=PHYS["skin"], sigma=PHYS["sigma"],
                                                epsilon=PHYS["epsilon"], cappingDistance=PHYS["cap"],
                                                maxNeighbors=PHYS["max_neigh"], langevin=True, zeta=PHYS["zeta"],
-                                               temperature=PHYS["temperature"], seed=PHYS["seed"])
+                                               temperature=PHYS["temperature"], seed=PHYS["seed"], **extra)
         return api.MolecularDynamics(a, sub, dt=PHYS["dt"], rc=PHYS["rc"], skin=PHYS["skin"], sigma=PHYS["sigma"],
                                      epsilon=PHYS["epsilon"], cappingDistance=PHYS["cap"],
                                      maxNeighbors=PHYS["max_neigh"], langevin=True, zeta=PHYS["zeta"],
                                      temperature=PHYS["temperature"], seed=PHYS["seed"], cellSort=True,
-                                     fullList=int(args.full_list))
+                                     fullList=int(args.full_list), **extra)
 
     md = make_md(atoms)
     md.run(args.equil, stream=stream)       # untimed: melt the lattice
@@ -274,13 +293,18 @@ def run_b200(args):
     # the contract figure is the half-list one whichever variant is timed (a full list stores every pair twice)
     stored_half = stats["storedPairs"] / (2.0 if args.full_list else 1.0)
     algo_bytes = 60.0 * n * args.steps + 52.0 * stored_half
+    kernel_name = "ljForceTiledKernel" if args.full_list == 2 else "ljForceKernel"
+    if adress:
+        # SURVEY 8d, K14 with a = 1 atom per molecule: 84 M + 56 M a + 12 P_mol + (64 + 56 a) P_act
+        algo_bytes = 140.0 * n * args.steps + 12.0 * stored_half + 120.0 * stats["activePairs"]
+        kernel_name = "adressForceTiledKernel" if args.full_list == 2 else "adressForceKernel"
     force_ms = stats["forceKernelMs"]
     achieved = algo_bytes / (force_ms * 1e-3) / 1e9 if force_ms > 0 else None
     traffic = ncu_traffic()
     roofline = {
-        "bound": "hbm", "kernel": "ljForceTiledKernel" if args.full_list == 2 else "ljForceKernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": (achieved / peak) if achieved else None, "peak_source": peak_src,
-        "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+        "traffic": traffic["dram_bytes_per_launch"] if (traffic and not adress and n == 1000000) else None,
         "algorithmic_bytes_per_launch": algo_bytes / args.steps,
         "kernel_ms_per_launch": force_ms / args.steps, "kernel_share_of_step": force_ms / ms,
         "stored_pairs_per_atom": stats["storedPairs"] / args.steps / n,
@@ -338,7 +362,7 @@ def run_b200(args):
                        "mrmd_b200_md_run_host: pinned host pos+vel -> device, one step, pos+vel+{E,virial,maxDisp} back"}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not adress:
         threads = host_threads()
         cpos, cvel = atoms.get("pos")[:n], atoms.get("vel")[:n]
         t0 = time.perf_counter()

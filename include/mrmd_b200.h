@@ -296,6 +296,14 @@ int mrmd_b200_adress_set_intervals(mrmd_b200_adress* ad, int64_t samplingInterva
 /* replaces LJ_IdealGas::run (action/LJ_IdealGas.cpp:227-260); *energy (host, optional) after a sync */
 int mrmd_b200_adress_run(mrmd_b200_adress* ad, mrmd_b200_molecules* m, const mrmd_b200_verlet* v,
                          mrmd_b200_atoms* a, double* energy, int64_t* numPairs, void* stream);
+/* B200 fast path for one-atom molecules (data::createMoleculeForEachAtom, relativeMass 1) on a list from
+ * mrmd_b200_verlet_build_periodic: UpdateMolecules::update (the weighting function is evaluated inline at the
+ * atom = molecule position, images at their image position), LJ_IdealGas::run and
+ * ContributeMoleculeForceToAtoms::update in one kernel without atomics on forces; the atoms' force is
+ * accumulated (+=).  Requires the AT + HY region to stay at least the ghost layer thickness away from the
+ * periodic faces the weight depends on (x for Slab, all for Spherical); otherwise MRMD_B200_EINVAL. */
+int mrmd_b200_adress_run_periodic(mrmd_b200_adress* ad, mrmd_b200_atoms* a, const mrmd_b200_verlet* v,
+                                  const mrmd_b200_weight* w, double* energy, int64_t* numPairs, void* stream);
 /* getMeanCompensationEnergy() and the two accumulation histograms, 200 x numTypes doubles each
  * (kind 0 mean, 1 compensationEnergy, 2 compensationEnergyCounter) */
 int mrmd_b200_adress_read_histogram(const mrmd_b200_adress* ad, int kind, double* dstHost, void* stream);
@@ -363,6 +371,7 @@ typedef struct
     double energy, virial;  /* of the last step */
     double forceKernelMs;   /* CUDA-event time of the force kernel summed over the steps (0 if not timed) */
     double maxDisplacement;
+    int64_t activePairs;    /* AdResS: stored half pairs that were not skipped as CG-CG, summed over the steps */
 } mrmd_b200_md_stats;
 
 int mrmd_b200_md_create(mrmd_b200_md** out, const mrmd_b200_md_config* cfg, const mrmd_b200_subdomain* s,

@@ -40,7 +40,7 @@ class MdConfig(C.Structure):
 class MdStats(C.Structure):
     _fields_ = [("steps", C.c_int64), ("rebuilds", C.c_int64), ("pairInteractions", C.c_int64),
                 ("storedPairs", C.c_int64), ("numLocal", C.c_int64), ("numGhost", C.c_int64), ("energy", C.c_double),
-                ("virial", C.c_double), ("forceKernelMs", C.c_double), ("maxDisplacement", C.c_double)]
+                ("virial", C.c_double), ("forceKernelMs", C.c_double), ("maxDisplacement", C.c_double), ("activePairs", C.c_int64)]
 
 
 vp = C.c_void_p
@@ -120,6 +120,7 @@ SIGNATURES = {
     "mrmd_b200_adress_destroy": (C.c_int, [vp]),
     "mrmd_b200_adress_set_intervals": (C.c_int, [vp, i64, i64]),
     "mrmd_b200_adress_run": (C.c_int, [vp, vp, vp, vp, pdbl, pi64, vp]),
+    "mrmd_b200_adress_run_periodic": (C.c_int, [vp, vp, vp, vp, pdbl, pi64, vp]),
     "mrmd_b200_adress_read_histogram": (C.c_int, [vp, C.c_int, vp, vp]),
     "mrmd_b200_thermo_create": (C.c_int, [pvp, vp, i64, pSub, dbl, vp, C.c_int, C.c_int]),
     "mrmd_b200_thermo_destroy": (C.c_int, [vp]),

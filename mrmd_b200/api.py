@@ -513,6 +513,16 @@ class LJ_IdealGas:
         self.lastNumPairs = p.value
         return e.value
 
+    def run_periodic(self, atoms, verletList, weight, stream=None, fetch=True):
+        """B200 fast path for one-atom molecules on a build_periodic list: UpdateMolecules + run +
+        ContributeMoleculeForceToAtoms in one kernel (mrmd_b200_adress_run_periodic)."""
+        e, p = C.c_double(), C.c_int64()
+        check(L().mrmd_b200_adress_run_periodic(self.h, atoms.h, verletList.h, C.byref(weight),
+                                                C.byref(e) if fetch else None, C.byref(p) if fetch else None,
+                                                _stream(stream)))
+        self.lastNumPairs = p.value
+        return e.value
+
     def _hist(self, kind):
         out = np.zeros((200, self.numTypes))
         check(L().mrmd_b200_adress_read_histogram(self.h, kind, out.ctypes.data, None))

@@ -7,6 +7,7 @@
 #include <algorithm>
 
 #include "handles.cuh"
+#include "weight.cuh"
 
 namespace mrmd_b200
 {
@@ -14,81 +15,7 @@ int buildLJTable(LJTable& table, const double* cappingDistance, const double* rc
                  const double* epsilon, int64_t numTypes, int isShifted, double* rcSqrMax);
 
 constexpr int COMPENSATION_ENERGY_BINS = 200;  // LJ_IdealGas.hpp:54
-constexpr double PI = 3.14159265358979323846;
 constexpr int AD_THREADS = 128;
-
-// util/math.hpp:31-46: square-and-multiply in the reference's multiplication order
-__device__ __forceinline__ double powInt(double x, long long n)
-{
-    double ww = x;
-    double yy = 1.0;
-    for (long long nn = (n > 0) ? n : -n; nn != 0; nn >>= 1)
-    {
-        if ((nn & 1) == 1) yy *= ww;
-        ww *= ww;
-    }
-    return (n > 0) ? yy : 1.0 / yy;
-}
-
-// Slab::operator() (Slab.hpp:161-187) / Spherical::operator() (Spherical.hpp:37-75)
-__device__ __forceinline__ void weightEval(const mrmd_b200_weight& w, double x, double y, double z, double& lambda,
-                                           double& modLambda, double& gx, double& gy, double& gz)
-{
-    gx = gy = gz = 0.0;
-    if (w.kind == MRMD_B200_WEIGHT_SLAB)
-    {
-        const double atHalf = 0.5 * w.atRegion;
-        const long long exponent = 2 * w.exponent;
-        const double dx = x - w.center[0];
-        const double absDx = fabs(dx);
-        if (absDx < atHalf || (w.abrupt && !(absDx > atHalf + w.hyRegion)))
-        {
-            lambda = 1.0;
-            modLambda = 1.0;
-        }
-        else if (absDx > atHalf + w.hyRegion)
-        {
-            lambda = 0.0;
-            modLambda = 0.0;
-        }
-        else
-        {
-            const double arg = PI / (2.0 * w.hyRegion) * (absDx - atHalf);
-            const double base = cos(arg);
-            lambda = base * base;
-            modLambda = powInt(base, exponent);
-            const double factor =
-                -PI / (2.0 * w.hyRegion) * double(exponent) * sin(arg) * powInt(base, exponent - 1) / absDx;
-            gx = factor * dx;
-        }
-        return;
-    }
-    const double atRadiusSqr = w.atRegion * w.atRegion;
-    const double cgRadiusSqr = (w.atRegion + w.hyRegion) * (w.atRegion + w.hyRegion);
-    const double dx = x - w.center[0], dy = y - w.center[1], dz = z - w.center[2];
-    const double dxSqr = dx * dx + dy * dy + dz * dz;
-    if (dxSqr < atRadiusSqr)
-    {
-        lambda = 1.0;
-        modLambda = 1.0;
-        return;
-    }
-    if (dxSqr > cgRadiusSqr)
-    {
-        lambda = 0.0;
-        modLambda = 0.0;
-        return;
-    }
-    const double r = sqrt(dxSqr);
-    const double arg = PI / (2.0 * w.hyRegion) * (r - w.atRegion);
-    const double base = cos(arg);
-    lambda = powInt(base, w.exponent);
-    modLambda = lambda;
-    const double factor = -PI / (2.0 * w.hyRegion) * double(w.exponent) * sin(arg) * powInt(base, w.exponent - 1) / r;
-    gx = factor * dx;
-    gy = factor * dy;
-    gz = factor * dz;
-}
 
 // UpdateMolecules::update, UpdateMolecules.hpp:41-67
 __global__ void updateMoleculesKernel(MolsView m, AtomsView a, int64_t numAll, mrmd_b200_weight w)
@@ -152,7 +79,7 @@ __global__ void __launch_bounds__(AD_THREADS)
                       double* hist, double* partials, double* result, unsigned int* ticket)
 {
     const int64_t alpha = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-    double sumEnergy = 0.0, pairs = 0.0;
+    double sumEnergy = 0.0, pairs = 0.0, activePairs = 0.0;
     if (alpha < numLocalMols)
     {
         const int64_t T = numTypes;
@@ -179,6 +106,7 @@ __global__ void __launch_bounds__(AD_THREADS)
             const double4 wB = ld4nc(m.w + beta);
             const double modLambdaBeta = wB.x;
             if (cgAlpha && inCG(modLambdaBeta)) continue;  // ideal gas, :102-107
+            activePairs += 1.0;
             const double weighting = 0.5 * (modLambdaAlpha + modLambdaBeta);
             const bool hyBeta = inHY(modLambdaBeta);
             const bool drift = hyAlpha || hyBeta;
@@ -259,7 +187,7 @@ __global__ void __launch_bounds__(AD_THREADS)
             atomicAdd(m.force[2] + alpha, fAz);
         }
     }
-    gridReduce3<AD_THREADS>(sumEnergy, pairs, 0.0, partials, result, ticket);
+    gridReduce3<AD_THREADS>(sumEnergy, pairs, activePairs, partials, result, ticket);
 }
 
 // updateMeanCompensationEnergy, LJ_IdealGas.cpp:21-50 (runningAverageFactor = 10)
@@ -399,6 +327,40 @@ int mrmd_b200_adress_run(mrmd_b200_adress* ad, mrmd_b200_molecules* m, const mrm
     if (ad->runCounter % ad->updateInterval == 0)
     {
         const int64_t n = COMPENSATION_ENERGY_BINS * ad->numTypes;
+        if (ad->preUpdateHook != nullptr) MB_TRY(ad->preUpdateHook(ad->hookCtx, ad->hist, 2 * n, st));
+        updateMeanCompensationKernel<<<gridFor(n, 128), 128, 0, st>>>(ad->hist, n, 10.0);
+        MB_LAUNCHED();
+    }
+    ad->runCounter += 1;
+    if (energy != nullptr || numPairs != nullptr)
+    {
+        MB_CUDA(cudaMemcpyAsync(ad->hResult, ad->dResult, 24, cudaMemcpyDeviceToHost, st));
+        MB_CUDA(cudaStreamSynchronize(st));
+        if (energy) *energy = ad->hResult[0];
+        if (numPairs) *numPairs = static_cast<int64_t>(ad->hResult[1] + 0.5);
+    }
+    return 0;
+}
+
+// UpdateMolecules::update + LJ_IdealGas::run + ContributeMoleculeForceToAtoms::update for one-atom molecules on a
+// tiled periodic list (tiled.cu); run counter, sampling and mean update exactly as LJ_IdealGas.cpp:227-260
+int mrmd_b200_adress_run_periodic(mrmd_b200_adress* ad, mrmd_b200_atoms* a, const mrmd_b200_verlet* v,
+                                  const mrmd_b200_weight* w, double* energy, int64_t* numPairs, void* stream)
+{
+    MB_TRY(checkDevice());
+    MB_REQUIRE(ad != nullptr && a != nullptr && v != nullptr && w != nullptr, "adress_run_periodic");
+    MB_REQUIRE(v->tiled, "adress_run_periodic: needs a list from mrmd_b200_verlet_build_periodic");
+    MB_REQUIRE(v->numParticles == a->numLocal, "adress_run_periodic: list rows != local atoms");
+    cudaStream_t st = S(stream);
+    const bool sampling = (ad->runCounter % ad->samplingInterval) == 0;
+    if (a->numLocal > 0)
+        MB_TRY(adressApplyTiled(ad, a, v, w, sampling, st));
+    else
+        MB_CUDA(cudaMemsetAsync(ad->dResult, 0, 24, st));
+    if (ad->runCounter % ad->updateInterval == 0)
+    {
+        const int64_t n = COMPENSATION_ENERGY_BINS * ad->numTypes;
+        if (ad->preUpdateHook != nullptr) MB_TRY(ad->preUpdateHook(ad->hookCtx, ad->hist, 2 * n, st));
         updateMeanCompensationKernel<<<gridFor(n, 128), 128, 0, st>>>(ad->hist, n, 10.0);
         MB_LAUNCHED();
     }

@@ -33,6 +33,10 @@ struct mrmd_b200_adress
     int64_t samplingInterval = 200;  // LJ_IdealGas.hpp:69
     int64_t updateInterval = 20000;  // :70
     double* hist = nullptr;          // 3 x (200 x numTypes): compensationEnergy, counter, mean
+    // x-slab decomposition: called on {compensationEnergy, counter} (count doubles) right before the mean update
+    // so that the ranks can sum their samples
+    int (*preUpdateHook)(void* ctx, double* sums, int64_t count, cudaStream_t st) = nullptr;
+    void* hookCtx = nullptr;
     mrmd_b200::DevBuf partials;
     double* dResult = nullptr;  // [0..2] energy, pairs, - of the last run; [3..5] running sums
     unsigned int* dTicket = nullptr;
@@ -59,6 +63,8 @@ namespace mrmd_b200
 // tiled.cu: LennardJones::apply over a tiled (periodic, shared-memory staged) full list
 int ljApplyTiled(mrmd_b200_lj* lj, mrmd_b200_atoms* a, const mrmd_b200_verlet* v, bool accumulate, bool energy,
                  cudaStream_t st);
+int adressApplyTiled(mrmd_b200_adress* ad, mrmd_b200_atoms* a, const mrmd_b200_verlet* v, const mrmd_b200_weight* w,
+                     bool sampling, cudaStream_t st);
 int verletBuildTiled(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, const mrmd_b200_subdomain* s, double radius,
                      double cellRatio, int64_t maxNeigh, const int32_t* haloLeft, const int32_t* haloRight,
                      cudaStream_t st);

@@ -24,6 +24,7 @@ struct mrmd_b200_md
     int64_t step = 0;
     int64_t rebuilds = 0;
     int64_t storedPairsNow = 0;
+    double active0 = 0.0;  // running active-pair count when the current run started
     bool ghostsStale = false;  // tiled fast path: ghost positions / forces are refreshed when a run returns
     std::vector<cudaEvent_t> events;
 };
@@ -53,6 +54,18 @@ static int rebuild(mrmd_b200_md* md, cudaStream_t st)
         a->size = a->numLocal;
         MB_TRY(mrmd_b200_molecules_update(m, a, &c.weight, st));
         MB_TRY(mrmd_b200_ghost_mr_map_into_domain(m, a, &md->sub, st));
+        if (c.fullList == 2)
+        {
+            // fast path: one-atom molecules are their atoms, the tiled list over the sorted atoms is the molecule
+            // list, images are generated while staging: no ghost molecules / atoms are materialised
+            MB_TRY(mrmd_b200_atoms_cell_sort(a, 0, a->numLocal, delta, md->sub.minCorner, md->sub.maxCorner, nullptr, st));
+            MB_TRY(mrmd_b200_verlet_build_periodic(md->list, a, &md->sub, cutoff, 1.0, c.maxNeighbors, st));
+            int64_t total = 0;
+            MB_TRY(mrmd_b200_verlet_info(md->list, nullptr, nullptr, &total, nullptr));
+            md->storedPairsNow = total;
+            md->rebuilds += 1;
+            return 0;
+        }
         if (c.cellSort)
         {
             // one atom per molecule (data::createMoleculeForEachAtom): sorting the atoms sorts the molecules
@@ -114,6 +127,27 @@ static int oneStep(mrmd_b200_md* md, cudaStream_t st, cudaEvent_t evStart, cudaE
     {
         MB_TRY(mrmd_b200_ghost_update(md->ghost, a, &md->sub, st));  // :170
         if (c.adress) MB_TRY(mrmd_b200_molecules_update(md->mols, a, &c.weight, st));
+    }
+    if (c.fullList == 2 && c.adress)
+    {
+        // tiled AdResS step: thermodynamic force on the zeroed force, then UpdateMolecules + LJ_IdealGas +
+        // ContributeMoleculeForceToAtoms as one kernel (mrmd_b200_adress_run_periodic)
+        MB_TRY(mrmd_b200_atoms_fill(a, MRMD_B200_ATOM_FORCE, 0.0, st));
+        if (md->thermo != nullptr)
+        {
+            if (c.thermoSampleInterval > 0 && md->step % c.thermoSampleInterval == 0)
+                MB_TRY(mrmd_b200_thermo_sample(md->thermo, a, st));
+            if (c.thermoUpdateInterval > 0 && md->step > 0 && md->step % c.thermoUpdateInterval == 0 &&
+                md->thermo->samples > 0)
+                MB_TRY(mrmd_b200_thermo_update(md->thermo, c.thermoSmoothingSigma, c.thermoSmoothingIntensity, nullptr, st));
+            MB_TRY(mrmd_b200_thermo_apply(md->thermo, a, nullptr, 0, st));
+        }
+        if (evStart) MB_CUDA(cudaEventRecord(evStart, st));
+        MB_TRY(mrmd_b200_adress_run_periodic(md->adress, a, md->list, &c.weight, nullptr, nullptr, st));
+        if (evStop) MB_CUDA(cudaEventRecord(evStop, st));
+        MB_TRY(mrmd_b200_vv_post(a, c.dt, st));
+        md->step += 1;
+        return 0;
     }
     if (c.fullList == 2)
     {
@@ -182,11 +216,13 @@ static int collectStats(mrmd_b200_md* md, int64_t nsteps, int64_t rebuilds0, int
     stats->numLocal = md->atoms->numLocal;
     stats->numGhost = md->atoms->numGhost;
     stats->maxDisplacement = md->maxDisplacement;
+    stats->activePairs = 0;
     if (md->cfg.adress)
     {
         stats->energy = hRes[0];
         stats->virial = 0.0;
         stats->pairInteractions = static_cast<int64_t>(hRes[4] - pairs0 + 0.5);
+        stats->activePairs = static_cast<int64_t>(hRes[5] - md->active0 + 0.5);
     }
     else
     {
@@ -212,6 +248,7 @@ static int runningPairs(mrmd_b200_md* md, double* out, cudaStream_t st)
     MB_CUDA(cudaMemcpyAsync(hRes, dRes, 48, cudaMemcpyDeviceToHost, st));
     MB_CUDA(cudaStreamSynchronize(st));
     *out = md->cfg.adress ? hRes[4] : hRes[5];
+    md->active0 = md->cfg.adress ? hRes[5] : 0.0;
     return 0;
 }
 }  // namespace mrmd_b200
@@ -226,7 +263,7 @@ int mrmd_b200_md_create(mrmd_b200_md** out, const mrmd_b200_md_config* cfg, cons
     MB_TRY(checkDevice());
     MB_REQUIRE(out != nullptr && cfg != nullptr && s != nullptr && atoms != nullptr, "md_create");
     MB_REQUIRE(cfg->dt > 0.0 && cfg->rc > 0.0 && cfg->skin >= 0.0 && cfg->maxNeighbors > 0, "md_create: bad config");
-    MB_REQUIRE(!(cfg->adress && cfg->fullList), "md_create: LJ_IdealGas takes a half list");
+    MB_REQUIRE(!(cfg->adress && cfg->fullList == 1), "md_create: LJ_IdealGas takes a half list (0) or the tiled list (2)");
     auto* md = new mrmd_b200_md;
     md->cfg = *cfg;
     md->sub = *s;

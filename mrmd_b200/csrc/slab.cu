@@ -313,6 +313,8 @@ struct mrmd_b200_slab
     mrmd_b200_atoms* atoms = nullptr;  // not owned
     mrmd_b200_verlet* list = nullptr;
     mrmd_b200_lj* lj = nullptr;
+    mrmd_b200_adress* adress = nullptr;  // AdResS mode (one-atom molecules, tiled kernel)
+    mrmd_b200_thermo* thermo = nullptr;  // bins over the GLOBAL box, density all-reduced before every update
     double maxDisplacement = DBL_MAX;
     int64_t step = 0, rebuilds = 0, storedPairsNow = 0;
     int64_t haloLeftCount = 0, haloRightCount = 0;   // received
@@ -542,6 +544,14 @@ static int slabRebuild(mrmd_b200_slab* sl, cudaStream_t st)
     return 0;
 }
 
+// mrmd_b200_adress::preUpdateHook: the compensation-energy samples of all slabs enter the mean
+static int sumOverRanks(void* ctx, double* sums, int64_t count, cudaStream_t st)
+{
+    auto* sl = static_cast<mrmd_b200_slab*>(ctx);
+    MB_NCCL(g_nccl.allReduce(sums, sums, size_t(count), ncclDouble, ncclSum, sl->comm, st));
+    return 0;
+}
+
 static int slabStep(mrmd_b200_slab* sl, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, bool wantEnergy)
 {
     const mrmd_b200_md_config& c = sl->cfg;
@@ -563,9 +573,34 @@ static int slabStep(mrmd_b200_slab* sl, cudaStream_t st, cudaEvent_t e0, cudaEve
     }
     else
         MB_TRY(haloRefresh(sl, st));
-    if (e0) MB_CUDA(cudaEventRecord(e0, st));
-    MB_TRY(ljApplyTiled(sl->lj, a, sl->list, false, wantEnergy, st));
-    if (e1) MB_CUDA(cudaEventRecord(e1, st));
+    if (c.adress)
+    {
+        // SURVEY.md section 3.5 on a slab: thermodynamic force (density histogram all-reduced over the ranks
+        // before an update, table replicated), then the tiled AdResS kernel over local + halo atoms
+        for (int d = 0; d < 3; ++d) MB_CUDA(cudaMemsetAsync(a->v.force[d], 0, size_t(a->numLocal) * 8, st));
+        if (sl->thermo != nullptr)
+        {
+            mrmd_b200_thermo* t = sl->thermo;
+            if (c.thermoSampleInterval > 0 && sl->step % c.thermoSampleInterval == 0)
+                MB_TRY(mrmd_b200_thermo_sample(t, a, st));
+            if (c.thermoUpdateInterval > 0 && sl->step > 0 && sl->step % c.thermoUpdateInterval == 0 && t->samples > 0)
+            {
+                MB_NCCL(g_nccl.allReduce(t->density, t->density, size_t(t->numBins * t->numTypes), ncclDouble, ncclSum,
+                                         sl->comm, st));
+                MB_TRY(mrmd_b200_thermo_update(t, c.thermoSmoothingSigma, c.thermoSmoothingIntensity, nullptr, st));
+            }
+            MB_TRY(mrmd_b200_thermo_apply(t, a, nullptr, 0, st));
+        }
+        if (e0) MB_CUDA(cudaEventRecord(e0, st));
+        MB_TRY(mrmd_b200_adress_run_periodic(sl->adress, a, sl->list, &c.weight, nullptr, nullptr, st));
+        if (e1) MB_CUDA(cudaEventRecord(e1, st));
+    }
+    else
+    {
+        if (e0) MB_CUDA(cudaEventRecord(e0, st));
+        MB_TRY(ljApplyTiled(sl->lj, a, sl->list, false, wantEnergy, st));
+        if (e1) MB_CUDA(cudaEventRecord(e1, st));
+    }
     MB_TRY(mrmd_b200_vv_post(a, c.dt, st));
     sl->step += 1;
     return 0;
@@ -595,7 +630,16 @@ int mrmd_b200_slab_create(mrmd_b200_slab** out, const mrmd_b200_md_config* cfg, 
     MB_TRY(checkDevice());
     MB_REQUIRE(out && cfg && globalMin && globalMax && uniqueId128 && atoms, "slab_create");
     MB_REQUIRE(nranks >= 2 && rank >= 0 && rank < nranks, "slab_create: needs at least two ranks");
-    MB_REQUIRE(!cfg->adress, "slab_create: the x-slab driver covers the Lennard-Jones step loop");
+    if (cfg->adress)
+    {
+        // the tiled AdResS kernel evaluates lambda at image positions: across the global periodic x faces (and y, z
+        // for a spherical region, checked per launch) the AT + HY region must stay a list radius away
+        const mrmd_b200_weight& w = cfg->weight;
+        const double reach = (w.kind == MRMD_B200_WEIGHT_SLAB) ? 0.5 * w.atRegion + w.hyRegion : w.atRegion + w.hyRegion;
+        const double cut = cfg->rc + cfg->skin;
+        MB_REQUIRE(w.center[0] - reach >= globalMin[0] + cut && w.center[0] + reach <= globalMax[0] - cut,
+                   "slab_create: the AT/HY region reaches the periodic x boundary of the global box");
+    }
     MB_TRY(loadNccl());
     auto* sl = new mrmd_b200_slab;
     sl->cfg = *cfg;
@@ -633,6 +677,23 @@ int mrmd_b200_slab_create(mrmd_b200_slab** out, const mrmd_b200_md_config* cfg, 
     }
     if (rc == 0) rc = mrmd_b200_verlet_create(&sl->list, 0);
     if (rc == 0) rc = mrmd_b200_lj_create(&sl->lj, &cfg->cappingDistance, &cfg->rc, &cfg->sigma, &cfg->epsilon, 1, 0);
+    if (rc == 0 && cfg->adress)
+    {
+        rc = mrmd_b200_adress_create(&sl->adress, &cfg->cappingDistance, &cfg->rc, &cfg->sigma, &cfg->epsilon, 1,
+                                     cfg->doShift);
+        if (rc == 0)
+        {
+            sl->adress->preUpdateHook = sumOverRanks;
+            sl->adress->hookCtx = sl;
+        }
+        if (rc == 0 && cfg->useThermoForce)
+        {
+            mrmd_b200_subdomain global;
+            mrmd_b200_subdomain_init(&global, globalMin, globalMax, th);
+            rc = mrmd_b200_thermo_create(&sl->thermo, &cfg->thermoTargetDensity, 1, &global, cfg->thermoBinWidth,
+                                         &cfg->thermoModulation, 0, 0);
+        }
+    }
     if (rc == 0 && cudaMalloc(&sl->dTotals, 64) != cudaSuccess) rc = MRMD_B200_ENOMEM;
     if (rc == 0 && cudaMallocHost(&sl->hTotals, 64) != cudaSuccess) rc = MRMD_B200_ENOMEM;
     if (rc == 0 && cudaMalloc(&sl->dScalars, 64) != cudaSuccess) rc = MRMD_B200_ENOMEM;
@@ -655,6 +716,8 @@ int mrmd_b200_slab_destroy(mrmd_b200_slab* sl)
     if (sl->comm != nullptr) g_nccl.commDestroy(sl->comm);
     mrmd_b200_verlet_destroy(sl->list);
     mrmd_b200_lj_destroy(sl->lj);
+    mrmd_b200_adress_destroy(sl->adress);
+    mrmd_b200_thermo_destroy(sl->thermo);
     if (sl->dTotals) cudaFree(sl->dTotals);
     if (sl->hTotals) cudaFreeHost(sl->hTotals);
     if (sl->dScalars) cudaFree(sl->dScalars);
@@ -672,9 +735,13 @@ int mrmd_b200_slab_run(mrmd_b200_slab* sl, int64_t nsteps, int timeForceKernel, 
     MB_REQUIRE(sl != nullptr && nsteps >= 0, "slab_run");
     cudaStream_t st = S(stream);
     const int64_t rebuilds0 = sl->rebuilds;
-    MB_CUDA(cudaMemcpyAsync(sl->lj->hResult, sl->lj->dResult, 48, cudaMemcpyDeviceToHost, st));
+    const bool adress = sl->cfg.adress != 0;
+    double* dRes = adress ? sl->adress->dResult : sl->lj->dResult;
+    double* hRes = adress ? sl->adress->hResult : sl->lj->hResult;
+    MB_CUDA(cudaMemcpyAsync(hRes, dRes, 48, cudaMemcpyDeviceToHost, st));
     MB_CUDA(cudaStreamSynchronize(st));
-    const double pairs0 = sl->lj->hResult[5];
+    const double pairs0 = adress ? hRes[4] : hRes[5];
+    const double active0 = adress ? hRes[5] : 0.0;
     const int nTimed = timeForceKernel ? static_cast<int>(std::min<int64_t>(nsteps, 1 << 16)) : 0;
     while (static_cast<int>(sl->events.size()) < 2 * nTimed)
     {
@@ -689,13 +756,13 @@ int mrmd_b200_slab_run(mrmd_b200_slab* sl, int64_t nsteps, int timeForceKernel, 
                         i == nsteps - 1));
         storedSum += sl->storedPairsNow;
     }
-    MB_CUDA(cudaMemcpyAsync(sl->lj->hResult, sl->lj->dResult, 48, cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaMemcpyAsync(hRes, dRes, 48, cudaMemcpyDeviceToHost, st));
     MB_CUDA(cudaStreamSynchronize(st));
     if (stats != nullptr)
     {
         // energy and virial of the last step summed over the ranks
-        sl->hScalars[0] = sl->lj->hResult[0];
-        sl->hScalars[1] = sl->lj->hResult[1];
+        sl->hScalars[0] = hRes[0];
+        sl->hScalars[1] = adress ? 0.0 : hRes[1];
         MB_CUDA(cudaMemcpyAsync(sl->dScalars, sl->hScalars, 16, cudaMemcpyHostToDevice, st));
         MB_NCCL(g_nccl.allReduce(sl->dScalars, sl->dScalars, 2, ncclDouble, ncclSum, sl->comm, st));
         MB_CUDA(cudaMemcpyAsync(sl->hScalars, sl->dScalars, 16, cudaMemcpyDeviceToHost, st));
@@ -707,7 +774,8 @@ int mrmd_b200_slab_run(mrmd_b200_slab* sl, int64_t nsteps, int timeForceKernel, 
         stats->numGhost = sl->atoms->numGhost;
         stats->energy = sl->hScalars[0];
         stats->virial = sl->hScalars[1];
-        stats->pairInteractions = static_cast<int64_t>(sl->lj->hResult[5] - pairs0 + 0.5);
+        stats->pairInteractions = static_cast<int64_t>((adress ? hRes[4] : hRes[5]) - pairs0 + 0.5);
+        stats->activePairs = adress ? static_cast<int64_t>(hRes[5] - active0 + 0.5) : 0;
         stats->maxDisplacement = sl->maxDisplacement;
         double ms = 0.0;
         for (int i = 0; i < nTimed; ++i)

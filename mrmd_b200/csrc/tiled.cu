@@ -22,6 +22,7 @@
 #include <cmath>
 
 #include "handles.cuh"
+#include "weight.cuh"
 
 namespace mrmd_b200
 {
@@ -466,6 +467,196 @@ __global__ void __launch_bounds__(TL_THREADS)
     gridReduce3<TL_THREADS>(0.5 * energy, 0.5 * virial, 0.5 * pairs, partials, result, ticket);
 }
 
+// ---- AdResS on tiles ----------------------------------------------------------------------------------------
+// UpdateMolecules::update + LJ_IdealGas::run + ContributeMoleculeForceToAtoms::update for one-atom molecules
+// (data::createMoleculeForEachAtom, relativeMass 1: molecule i is atom i and its centre of mass is the atom's
+// position, bit for bit), as one kernel over the tiled full list.  Per stored half pair the reference adds
+// +-d*ff*w to both atoms, -V_ij*grad(lambda) to both molecules and V_ij to both compensation bins
+// (LJ_IdealGas.cpp:102-225); seen from both ends of a full list each row owner collects exactly its own share,
+// so there are no atomics on forces and the molecule force goes straight into the atom force.
+constexpr int TL_COMPENSATION_BINS = 200;  // LJ_IdealGas.hpp:54
+constexpr int TL_SMEM_PER_SLOT_ADRESS = 33;  // x, y, z, lambda^mod + type byte
+
+// stages {x, y, z, lambda^mod}; the weight is evaluated at the image position, as UpdateMolecules does for the
+// reference's ghost molecules
+template <bool TYPES>
+__device__ __forceinline__ void stageTileAdress(const TileParams& tp, const TileDesc& td, const double4* __restrict__ pos,
+                                                const mrmd_b200_weight& w, double* rec, unsigned char* sType)
+{
+    const int tile = blockIdx.x;
+    const int col = tile / tp.numChunks;
+    const int ci = col / tp.g.n[1], cj = col % tp.g.n[1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int p = warp; p < TL_PIECES; p += TL_THREADS / 32)
+    {
+        const int len = td.pieceLen[p];
+        if (len == 0) continue;
+        int ix, iy, iz;
+        pieceShift(tp, ci, cj, p, ix, iy, iz);
+        const double shx = double(ix) * tp.L[0], shy = double(iy) * tp.L[1], shz = double(iz) * tp.L[2];
+        const int start = td.pieceStart[p], slot0 = td.pieceSlot[p];
+        for (int k = lane; k < len; k += 32)
+        {
+            const double4 raw = ld4nc(pos + start + k);
+            const double qx = raw.x + shx, qy = raw.y + shy, qz = raw.z + shz;
+            double* r = rec + 4 * (slot0 + k);
+            r[0] = qx;
+            r[1] = qy;
+            r[2] = qz;
+            r[3] = weightModLambda(w, qx, qy, qz);
+            if (TYPES) sType[slot0 + k] = static_cast<unsigned char>(typeOf(raw));
+        }
+    }
+    __syncthreads();
+}
+
+// one molecule pair of LJ_IdealGas::operator() (LJ_IdealGas.cpp:96-205) seen from the row owner alpha
+template <bool SINGLE_TYPE>
+__device__ __forceinline__ void adressPair(const double* rec, const unsigned char* sType, int slot, double xi, double yi,
+                                           double zi, int typeI, double modA, bool cgA, bool hyA, const LJType& t0,
+                                           const LJTable& table, int64_t numTypes, double rcSqr, double& fx, double& fy,
+                                           double& fz, double& energy, double& vsum, double& pairs, double& activePairs)
+{
+    const double* q = rec + 4 * slot;
+    const double modB = q[3];
+    if (cgA && inCG(modB)) return;  // ideal gas, :102-107
+    activePairs += 1.0;
+    const double dx = xi - q[0];
+    const double dy = yi - q[1];
+    const double dz = zi - q[2];
+    const double distSqr = distSqrExact(dx, dy, dz);
+    if (distSqr > rcSqr) return;  // :137
+    const LJType& t = SINGLE_TYPE ? t0 : table.t[typeI * numTypes + sType[slot]];
+    double ff, e;
+    if (distSqr >= t.cappingDistanceSqr)
+    {
+        const double frac2 = fastRcp(distSqr);
+        const double frac6 = frac2 * frac2 * frac2;
+        ff = frac6 * (t.ff1 * frac6 - t.ff2) * frac2;
+        e = frac6 * (t.ef1 * frac6 - t.ef2) - t.shift;
+    }
+    else
+        ljForceEnergy(t, distSqr, ff, e);
+    const double weighting = 0.5 * (modA + modB);
+    const double ffactor = ff * weighting;
+    fx += dx * ffactor;
+    fy += dy * ffactor;
+    fz += dz * ffactor;
+    energy += e * weighting;
+    pairs += 1.0;
+    if (hyA) vsum += 0.5 * e;  // V_ij of the drift force and of the compensation sampling, :160-200
+}
+
+template <bool SINGLE_TYPE, bool SAMPLING>
+__global__ void __launch_bounds__(TL_THREADS)
+    adressForceTiledKernel(TileParams tp, AtomsView a, const int* __restrict__ desc, const int32_t* __restrict__ counts,
+                           const uint16_t* __restrict__ enc, int width, LJTable table, double rcSqr, int64_t numTypes,
+                           mrmd_b200_weight w, double* hist, double* partials, double* result, unsigned int* ticket)
+{
+    extern __shared__ double sTile[];
+    __shared__ TileDesc td;
+    double energy = 0.0, pairs = 0.0, activePairs = 0.0;
+    // slab weighting: when the three staged columns (padded by one more cell on each side for the drift since the
+    // last sort) lie beyond the hybrid region, every pair of the tile is an ideal-gas pair
+    bool skip = false;
+    if (w.kind == MRMD_B200_WEIGHT_SLAB)
+    {
+        const int ci = (blockIdx.x / tp.numChunks) / tp.g.n[1];
+        const double lo = tp.g.min[0] + double(ci - 2) * tp.g.dx[0];
+        const double hi = tp.g.min[0] + double(ci + 3) * tp.g.dx[0];
+        const double reach = 0.5 * w.atRegion + w.hyRegion;
+        skip = (lo - w.center[0] > reach) || (w.center[0] - hi > reach);
+    }
+    if (!skip)
+    {
+        loadTileDesc(desc, td);
+        double* rec = sTile;
+        unsigned char* sType = reinterpret_cast<unsigned char*>(rec + 4 * tp.cap);
+        stageTileAdress<!SINGLE_TYPE>(tp, td, a.pos, w, rec, sType);
+
+        const int group = threadIdx.x / TL_GROUP, gl = threadIdx.x % TL_GROUP;
+        const LJType t0 = table.t[0];
+        const int64_t T = numTypes;
+        const double inverseBinSize = 1.0 / ((1.0 - 0.0) / double(TL_COMPENSATION_BINS));
+        for (int hBase = 0; hBase < td.homeCount; hBase += TL_GROUPS)
+        {
+            const int h = hBase + group;
+            const bool active = h < td.homeCount;
+            const int i = td.homeStart + h;
+            const int selfSlot = active ? td.selfSlot0 + h : 0;
+            const double xi = rec[4 * selfSlot], yi = rec[4 * selfSlot + 1], zi = rec[4 * selfSlot + 2];
+            const int typeI = SINGLE_TYPE ? 0 : sType[selfSlot];
+            double lambda, modA, gx, gy, gz;
+            weightEval(w, xi, yi, zi, lambda, modA, gx, gy, gz);
+            const bool hyA = inHY(modA), cgA = inCG(modA);
+            double fx = 0.0, fy = 0.0, fz = 0.0, vsum = 0.0;
+            const int numNeighbors = active ? min(counts[i], width) : 0;
+            const uint16_t* row = enc + size_t(active ? i : 0) * width;
+            const int iters = __reduce_max_sync(0xffffffffu, (numNeighbors + TL_GROUP - 1) / TL_GROUP);
+            int slots[LJT_PREFETCH];
+#pragma unroll
+            for (int it = 0; it < LJT_PREFETCH; ++it)
+            {
+                const int n = it * TL_GROUP + gl;
+                slots[it] = (n < numNeighbors) ? int(row[n]) : -1;
+            }
+#pragma unroll
+            for (int it = 0; it < LJT_PREFETCH; ++it)
+            {
+                if (it < iters && slots[it] >= 0)
+                    adressPair<SINGLE_TYPE>(rec, sType, slots[it], xi, yi, zi, typeI, modA, cgA, hyA, t0, table, T, rcSqr, fx,
+                                            fy, fz, energy, vsum, pairs, activePairs);
+            }
+            for (int it = LJT_PREFETCH; it < iters; ++it)
+            {
+                const int n = it * TL_GROUP + gl;
+                if (n < numNeighbors)
+                    adressPair<SINGLE_TYPE>(rec, sType, row[n], xi, yi, zi, typeI, modA, cgA, hyA, t0, table, T, rcSqr, fx, fy,
+                                            fz, energy, vsum, pairs, activePairs);
+            }
+#pragma unroll
+            for (int o = TL_GROUP / 2; o > 0; o >>= 1)
+            {
+                fx += __shfl_xor_sync(0xffffffffu, fx, o);
+                fy += __shfl_xor_sync(0xffffffffu, fy, o);
+                fz += __shfl_xor_sync(0xffffffffu, fz, o);
+                vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
+            }
+            if (active && gl == 0)
+            {
+                if (hyA)
+                {
+                    // molecule force: drift force -sum(V_ij) grad(lambda) (:163-169) plus the drift compensation
+                    // mean[bin] grad(lambda) (:209-222); with one atom of relativeMass 1 per molecule
+                    // ContributeMoleculeForceToAtoms adds it to the atom unchanged
+                    double scale = -vsum;
+                    const long long bin = histBin(0.0, inverseBinSize, TL_COMPENSATION_BINS, lambda);
+                    if (bin != -1)
+                    {
+                        scale += hist[2 * TL_COMPENSATION_BINS * T + bin * T + typeI];
+                        if (SAMPLING)
+                        {
+                            atomicAdd(hist + bin * T + typeI, vsum);
+                            atomicAdd(hist + TL_COMPENSATION_BINS * T + bin * T + typeI, 1.0);
+                        }
+                    }
+                    fx += scale * gx;
+                    fy += scale * gy;
+                    fz += scale * gz;
+                }
+                if (fx != 0.0 || fy != 0.0 || fz != 0.0)
+                {
+                    a.force[0][i] += fx;
+                    a.force[1][i] += fy;
+                    a.force[2][i] += fz;
+                }
+            }
+        }
+    }
+    // every pair is visited from both sides
+    gridReduce3<TL_THREADS>(0.5 * energy, 0.5 * pairs, 0.5 * activePairs, partials, result, ticket);
+}
+
 // decode the 16-bit slots back to (local partner index, image shift code) in Cabana's row-major layout
 __global__ void __launch_bounds__(TL_THREADS)
     decodeTiledKernel(TileParams tp, const int* __restrict__ desc, const int32_t* __restrict__ counts,
@@ -553,6 +744,10 @@ int tiledConfigure()
     TL_SET((ljForceTiledKernel<false, true, false>));
     TL_SET((ljForceTiledKernel<false, false, true>));
     TL_SET((ljForceTiledKernel<false, false, false>));
+    TL_SET((adressForceTiledKernel<true, true>));
+    TL_SET((adressForceTiledKernel<true, false>));
+    TL_SET((adressForceTiledKernel<false, true>));
+    TL_SET((adressForceTiledKernel<false, false>));
 #undef TL_SET
     done = true;
     return 0;
@@ -586,6 +781,49 @@ int ljApplyTiled(mrmd_b200_lj* lj, mrmd_b200_atoms* a, const mrmd_b200_verlet* v
         else { if (energy) LJT_LAUNCH(false, false, true); else LJT_LAUNCH(false, false, false); }
     }
 #undef LJT_LAUNCH
+    MB_LAUNCHED();
+    return 0;
+}
+
+// the force kernel of mrmd_b200_adress_run_periodic (adress.cu owns the run counter and the histogram update)
+int adressApplyTiled(mrmd_b200_adress* ad, mrmd_b200_atoms* a, const mrmd_b200_verlet* v, const mrmd_b200_weight* w,
+                     bool sampling, cudaStream_t st)
+{
+    MB_REQUIRE(a->lcValid && a->lcEpoch == v->tiledEpoch,
+               "adress_run_periodic: the atoms were re-sorted after this tiled list was built");
+    MB_REQUIRE(!v->half, "adress_run_periodic: tiled lists are full lists");
+    MB_REQUIRE(ad->numTypes <= 255, "adress_run_periodic: more than 255 atom types");
+    // the row owner evaluates lambda at its own position and at the partner's IMAGE position; that equals the
+    // reference's half-list evaluation only if images near a periodic boundary are coarse grained like their
+    // originals: the AT + HY region has to stay a list radius away from the periodic faces it depends on
+    {
+        const mrmd_b200_subdomain& s = v->tiledSub;
+        const int axes = (w->kind == MRMD_B200_WEIGHT_SLAB) ? 1 : 3;
+        const double reach = (w->kind == MRMD_B200_WEIGHT_SLAB) ? 0.5 * w->atRegion + w->hyRegion : w->atRegion + w->hyRegion;
+        for (int d = 0; d < axes; ++d)
+        {
+            if (s.ghostLayerThickness[d] == 0.0 || (d == 0 && v->tiledHaloX)) continue;
+            MB_REQUIRE(w->center[d] - reach >= s.minCorner[d] + s.ghostLayerThickness[d] &&
+                           w->center[d] + reach <= s.maxCorner[d] - s.ghostLayerThickness[d],
+                       "adress_run_periodic: the AT/HY region reaches a periodic boundary (use the generic path)");
+        }
+    }
+    MB_TRY(tiledConfigure());
+    TileParams tp;
+    MB_TRY(makeTileParams(a, &v->tiledSub, v->tiledCH, v->tiledSlots, v->tiledHaloX, tp));
+    const int tiles = tp.g.n[0] * tp.g.n[1] * tp.numChunks;
+    MB_TRY(ad->partials.reserve(size_t(tiles) * 3 * 8));
+    MB_CUDA(cudaMemsetAsync(ad->dResult, 0, 24, st));
+    const size_t smem = size_t(v->tiledSlots) * TL_SMEM_PER_SLOT_ADRESS + 16;
+    MB_REQUIRE(smem <= size_t(TL_SMEM_MAX), "adress_run_periodic: a tile exceeds shared memory");
+    const bool single = (ad->numTypes == 1);
+#define ADT_LAUNCH(S1, SAMP)                                                                                          \
+    adressForceTiledKernel<S1, SAMP><<<tiles, TL_THREADS, smem, st>>>(                                                \
+        tp, a->v, v->tileDesc.as<int>(), v->counts.as<int32_t>(), v->enc.as<uint16_t>(), static_cast<int>(v->width), \
+        ad->table, ad->rcSqr, ad->numTypes, *w, ad->hist, ad->partials.as<double>(), ad->dResult, ad->dTicket)
+    if (single) { if (sampling) ADT_LAUNCH(true, true); else ADT_LAUNCH(true, false); }
+    else { if (sampling) ADT_LAUNCH(false, true); else ADT_LAUNCH(false, false); }
+#undef ADT_LAUNCH
     MB_LAUNCHED();
     return 0;
 }

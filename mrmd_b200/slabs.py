@@ -67,11 +67,19 @@ class SlabMolecularDynamics:
 
     def __init__(self, atoms, global_min, global_max, rank, nranks, unique_id, dt=0.002, rc=2.5, skin=0.1, sigma=1.0,
                  epsilon=1.0, cappingDistance=0.7, maxNeighbors=60, langevin=False, zeta=20.0, temperature=1.5,
-                 seed=1234):
+                 seed=1234, adress=False, weight=None, doShift=True, thermo=None):
         cfg = _lib.MdConfig()
         cfg.dt, cfg.rc, cfg.skin, cfg.sigma, cfg.epsilon, cfg.cappingDistance = dt, rc, skin, sigma, epsilon, cappingDistance
         cfg.maxNeighbors, cfg.integrator, cfg.cellSort, cfg.fullList = maxNeighbors, int(langevin), 1, 2
         cfg.zeta, cfg.temperature, cfg.seed = zeta, temperature, seed
+        cfg.adress, cfg.doShift = int(adress), int(doShift)
+        if weight is not None:
+            C.memmove(C.byref(cfg.weight), C.byref(weight), C.sizeof(_lib.Weight))
+        if thermo is not None:
+            cfg.useThermoForce = 1
+            cfg.thermoTargetDensity, cfg.thermoBinWidth, cfg.thermoModulation = thermo["targetDensity"], thermo["binWidth"], thermo["modulation"]
+            cfg.thermoSampleInterval, cfg.thermoUpdateInterval = thermo["sampleInterval"], thermo["updateInterval"]
+            cfg.thermoSmoothingSigma, cfg.thermoSmoothingIntensity = thermo["sigma"], thermo["range"]
         self.cfg, self.atoms = cfg, atoms
         gmin = np.ascontiguousarray(global_min, dtype=np.float64)
         gmax = np.ascontiguousarray(global_max, dtype=np.float64)

@@ -21,6 +21,7 @@ def main():
 
     api.L().mrmd_b200_set_device(local)
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+    adress = len(sys.argv) > 2 and sys.argv[2] == "adress"
     # global system: jittered sc lattice, x-elongated box (world * 12 x 10 x 10 sites)
     nx, ny = 12 * world, 10
     rng = np.random.default_rng(42)
@@ -31,10 +32,16 @@ def main():
     gmin, gmax = np.zeros(3), np.array([nx, ny, ny]) * 1.25
     phys = dict(dt=0.002, rc=2.5, skin=0.1, sigma=1.0, epsilon=1.0, cappingDistance=0.7, maxNeighbors=60)
 
+    extra = {}
+    if adress:
+        # AT region across the rank boundary in the middle of the box, thermodynamic force updated during the run
+        extra = dict(adress=True, weight=api.Slab(gmax / 2, 0.2 * gmax[0], 0.1 * gmax[0], 2), doShift=True,
+                     thermo=dict(targetDensity=0.512, binWidth=0.5, modulation=2.0, sampleInterval=2, updateInterval=10,
+                                 sigma=2.0, range=2.0))
     mine = slabs.select_slab(pos, gmin, gmax, rank, world)
-    atoms = api.Atoms.from_arrays(pos[mine], vel[mine], mass=1.0)
+    atoms = api.Atoms.from_arrays(pos[mine], vel[mine], mass=1.0, relativeMass=1.0)
     uid = slabs.broadcast_unique_id(rank)
-    md = slabs.SlabMolecularDynamics(atoms, gmin, gmax, rank, world, uid, langevin=False, **phys)
+    md = slabs.SlabMolecularDynamics(atoms, gmin, gmax, rank, world, uid, langevin=False, **phys, **extra)
     st = md.run(steps)
     n = st["numLocal"]
     my_pos, my_vel = atoms.getPos()[:n], atoms.getVel()[:n]
@@ -52,8 +59,8 @@ def main():
         pairs = sum(x[2] for x in gathered)
         # single-GPU periodic reference run of the same global system
         sub = api.Subdomain(gmin, gmax, phys["rc"] + phys["skin"])
-        ref_atoms = api.Atoms.from_arrays(pos, vel, mass=1.0)
-        ref = api.MolecularDynamics(ref_atoms, sub, langevin=False, cellSort=True, fullList=2, **phys)
+        ref_atoms = api.Atoms.from_arrays(pos, vel, mass=1.0, relativeMass=1.0)
+        ref = api.MolecularDynamics(ref_atoms, sub, langevin=False, cellSort=True, fullList=2, **phys, **extra)
         rst = ref.run(steps)
         rp, rv = ref_atoms.getPos()[:len(pos)], ref_atoms.getVel()[:len(pos)]
         from scipy.spatial import cKDTree

@@ -18,13 +18,14 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def test_two_gpu_slabs_match_single_gpu():
+@pytest.mark.parametrize("mode", ["lj", "adress"])
+def test_two_gpu_slabs_match_single_gpu(mode):
     import torch
 
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "mgpu_check.py"), "40"]
+           "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "mgpu_check.py"), "40", mode]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
     assert res.returncode == 0, (res.stdout[-2000:], res.stderr[-2000:])
