@@ -32,6 +32,8 @@ def parse_args():
     p.add_argument("--warmup", type=int, default=300)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--side", type=int, default=100, help="lattice sites per box edge per GPU (100 -> 1M atoms)")
+    p.add_argument("--side-x", type=int, default=None, help="lattice sites per GPU along x if different from --side "
+                   "(configs[4]: --workload adress --side 400 --side-x 50 --gpus 8 = 64M atoms in a 500^3 box)")
     p.add_argument("--equil", type=int, default=300, help="untimed equilibration steps that melt the lattice")
     p.add_argument("--full-list", type=int, default=2, help="0 half list, 1 full list, 2 tiled periodic full list (fast path)")
     p.add_argument("--e2e-steps", type=int, default=100)
@@ -188,13 +190,13 @@ def workload_config(args, n_atoms_per_gpu):
           "dt=0.002, skin 0.1, maxNeighbors 60")
     return {
         "workload": ad if getattr(args, "workload", "lj") == "adress" else lj,
-        "atoms_per_gpu": n_atoms_per_gpu, "box_per_gpu": [args.side * 1.25] * 3, "equilibration_steps": args.equil,
+        "atoms_per_gpu": n_atoms_per_gpu, "box_per_gpu": [(getattr(args, "side_x", None) or args.side) * 1.25, args.side * 1.25, args.side * 1.25], "equilibration_steps": args.equil,
         "list": {0: "half (reference semantics, fp64 RED scatter)", 1: "full (generic gather kernel)", 2: "full, periodic tiles staged in shared memory (mrmd_b200_verlet_build_periodic)"}[args.full_list],
         "l2": "inputs larger than L2 (per step: 104 B/atom state + neighbour table ~ 4 B x 19-38 slots/atom > 126 MB "
               "at 1M atoms); no explicit flush",
         "parallelism": "1 GPU" if args.gpus == 1 else (
             f"{args.gpus} independent periodic replicas, one per GPU" if getattr(args, "replicas", False) else
-            f"{args.gpus} x-slabs of one {args.gpus * args.side * 1.25:g} x {args.side * 1.25:g} x {args.side * 1.25:g} box, "
+            f"{args.gpus} x-slabs of one {args.gpus * (getattr(args, 'side_x', None) or args.side) * 1.25:g} x {args.side * 1.25:g} x {args.side * 1.25:g} box, "
             "one process per GPU, NCCL halos (positions every step, full records at rebuild), ncclAllReduce(max) "
             "rebuild decision"),
     }
@@ -215,7 +217,7 @@ def run_b200(args):
     api.L().mrmd_b200_set_device(local_rank)
     stream = torch.cuda.current_stream().cuda_stream
 
-    pos, vel, box = lattice_system(args.side, seed=PHYS["seed"] + rank)
+    pos, vel, box = lattice_system(args.side, seed=PHYS["seed"] + rank, n_side_x=args.side_x)
     n = len(pos)
     sub = api.Subdomain([0, 0, 0], box, PHYS["rc"] + PHYS["skin"])
     slab_mode = world > 1 and not args.replicas

@@ -348,13 +348,31 @@ int mrmd_b200_adress_run_periodic(mrmd_b200_adress* ad, mrmd_b200_atoms* a, cons
                                   const mrmd_b200_weight* w, double* energy, int64_t* numPairs, void* stream)
 {
     MB_TRY(checkDevice());
+    cudaStream_t st = S(stream);
+    MB_TRY(adressRunPeriodic(ad, a, v, w, energy != nullptr, st));
+    if (energy != nullptr || numPairs != nullptr)
+    {
+        MB_CUDA(cudaMemcpyAsync(ad->hResult, ad->dResult, 24, cudaMemcpyDeviceToHost, st));
+        MB_CUDA(cudaStreamSynchronize(st));
+        if (energy) *energy = ad->hResult[0];
+        if (numPairs) *numPairs = static_cast<int64_t>(ad->hResult[1] + 0.5);
+    }
+    return 0;
+}
+
+}  // extern "C"
+
+namespace mrmd_b200
+{
+int adressRunPeriodic(mrmd_b200_adress* ad, mrmd_b200_atoms* a, const mrmd_b200_verlet* v, const mrmd_b200_weight* w,
+                      bool energy, cudaStream_t st)
+{
     MB_REQUIRE(ad != nullptr && a != nullptr && v != nullptr && w != nullptr, "adress_run_periodic");
     MB_REQUIRE(v->tiled, "adress_run_periodic: needs a list from mrmd_b200_verlet_build_periodic");
     MB_REQUIRE(v->numParticles == a->numLocal, "adress_run_periodic: list rows != local atoms");
-    cudaStream_t st = S(stream);
     const bool sampling = (ad->runCounter % ad->samplingInterval) == 0;
     if (a->numLocal > 0)
-        MB_TRY(adressApplyTiled(ad, a, v, w, sampling, st));
+        MB_TRY(adressApplyTiled(ad, a, v, w, sampling, energy, st));
     else
         MB_CUDA(cudaMemsetAsync(ad->dResult, 0, 24, st));
     if (ad->runCounter % ad->updateInterval == 0)
@@ -365,15 +383,11 @@ int mrmd_b200_adress_run_periodic(mrmd_b200_adress* ad, mrmd_b200_atoms* a, cons
         MB_LAUNCHED();
     }
     ad->runCounter += 1;
-    if (energy != nullptr || numPairs != nullptr)
-    {
-        MB_CUDA(cudaMemcpyAsync(ad->hResult, ad->dResult, 24, cudaMemcpyDeviceToHost, st));
-        MB_CUDA(cudaStreamSynchronize(st));
-        if (energy) *energy = ad->hResult[0];
-        if (numPairs) *numPairs = static_cast<int64_t>(ad->hResult[1] + 0.5);
-    }
     return 0;
 }
+}  // namespace mrmd_b200
+
+extern "C" {
 
 int mrmd_b200_adress_read_histogram(const mrmd_b200_adress* ad, int kind, double* dstHost, void* stream)
 {

@@ -64,7 +64,11 @@ namespace mrmd_b200
 int ljApplyTiled(mrmd_b200_lj* lj, mrmd_b200_atoms* a, const mrmd_b200_verlet* v, bool accumulate, bool energy,
                  cudaStream_t st);
 int adressApplyTiled(mrmd_b200_adress* ad, mrmd_b200_atoms* a, const mrmd_b200_verlet* v, const mrmd_b200_weight* w,
-                     bool sampling, cudaStream_t st);
+                     bool sampling, bool energy, cudaStream_t st);
+// adress.cu: mrmd_b200_adress_run_periodic with the energy accumulation optional (the drivers want it on the last
+// step of a run only)
+int adressRunPeriodic(mrmd_b200_adress* ad, mrmd_b200_atoms* a, const mrmd_b200_verlet* v, const mrmd_b200_weight* w,
+                      bool energy, cudaStream_t st);
 int verletBuildTiled(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, const mrmd_b200_subdomain* s, double radius,
                      double cellRatio, int64_t maxNeigh, const int32_t* haloLeft, const int32_t* haloRight,
                      cudaStream_t st);

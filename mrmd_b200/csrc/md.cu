@@ -143,7 +143,7 @@ static int oneStep(mrmd_b200_md* md, cudaStream_t st, cudaEvent_t evStart, cudaE
             MB_TRY(mrmd_b200_thermo_apply(md->thermo, a, nullptr, 0, st));
         }
         if (evStart) MB_CUDA(cudaEventRecord(evStart, st));
-        MB_TRY(mrmd_b200_adress_run_periodic(md->adress, a, md->list, &c.weight, nullptr, nullptr, st));
+        MB_TRY(adressRunPeriodic(md->adress, a, md->list, &c.weight, wantEnergy, st));
         if (evStop) MB_CUDA(cudaEventRecord(evStop, st));
         MB_TRY(mrmd_b200_vv_post(a, c.dt, st));
         md->step += 1;

@@ -592,7 +592,7 @@ static int slabStep(mrmd_b200_slab* sl, cudaStream_t st, cudaEvent_t e0, cudaEve
             MB_TRY(mrmd_b200_thermo_apply(t, a, nullptr, 0, st));
         }
         if (e0) MB_CUDA(cudaEventRecord(e0, st));
-        MB_TRY(mrmd_b200_adress_run_periodic(sl->adress, a, sl->list, &c.weight, nullptr, nullptr, st));
+        MB_TRY(adressRunPeriodic(sl->adress, a, sl->list, &c.weight, wantEnergy, st));
         if (e1) MB_CUDA(cudaEventRecord(e1, st));
     }
     else

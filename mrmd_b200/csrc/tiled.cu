@@ -511,7 +511,7 @@ __device__ __forceinline__ void stageTileAdress(const TileParams& tp, const Tile
 }
 
 // one molecule pair of LJ_IdealGas::operator() (LJ_IdealGas.cpp:96-205) seen from the row owner alpha
-template <bool SINGLE_TYPE>
+template <bool SINGLE_TYPE, bool ENERGY>
 __device__ __forceinline__ void adressPair(const double* rec, const unsigned char* sType, int slot, double xi, double yi,
                                            double zi, int typeI, double modA, bool cgA, bool hyA, const LJType& t0,
                                            const LJTable& table, int64_t numTypes, double rcSqr, double& fx, double& fy,
@@ -527,13 +527,14 @@ __device__ __forceinline__ void adressPair(const double* rec, const unsigned cha
     const double distSqr = distSqrExact(dx, dy, dz);
     if (distSqr > rcSqr) return;  // :137
     const LJType& t = SINGLE_TYPE ? t0 : table.t[typeI * numTypes + sType[slot]];
-    double ff, e;
+    double ff, e = 0.0;
     if (distSqr >= t.cappingDistanceSqr)
     {
         const double frac2 = fastRcp(distSqr);
         const double frac6 = frac2 * frac2 * frac2;
         ff = frac6 * (t.ff1 * frac6 - t.ff2) * frac2;
-        e = frac6 * (t.ef1 * frac6 - t.ef2) - t.shift;
+        // the pair energy is only needed for the drift terms of a hybrid row owner and for the returned total
+        if (ENERGY || hyA) e = frac6 * (t.ef1 * frac6 - t.ef2) - t.shift;
     }
     else
         ljForceEnergy(t, distSqr, ff, e);
@@ -542,13 +543,13 @@ __device__ __forceinline__ void adressPair(const double* rec, const unsigned cha
     fx += dx * ffactor;
     fy += dy * ffactor;
     fz += dz * ffactor;
-    energy += e * weighting;
+    if (ENERGY) energy += e * weighting;
     pairs += 1.0;
     if (hyA) vsum += 0.5 * e;  // V_ij of the drift force and of the compensation sampling, :160-200
 }
 
-template <bool SINGLE_TYPE, bool SAMPLING>
-__global__ void __launch_bounds__(TL_THREADS)
+template <bool SINGLE_TYPE, bool SAMPLING, bool ENERGY>
+__global__ void __launch_bounds__(TL_THREADS, 3)
     adressForceTiledKernel(TileParams tp, AtomsView a, const int* __restrict__ desc, const int32_t* __restrict__ counts,
                            const uint16_t* __restrict__ enc, int width, LJTable table, double rcSqr, int64_t numTypes,
                            mrmd_b200_weight w, double* hist, double* partials, double* result, unsigned int* ticket)
@@ -604,14 +605,14 @@ __global__ void __launch_bounds__(TL_THREADS)
             for (int it = 0; it < LJT_PREFETCH; ++it)
             {
                 if (it < iters && slots[it] >= 0)
-                    adressPair<SINGLE_TYPE>(rec, sType, slots[it], xi, yi, zi, typeI, modA, cgA, hyA, t0, table, T, rcSqr, fx,
+                    adressPair<SINGLE_TYPE, ENERGY>(rec, sType, slots[it], xi, yi, zi, typeI, modA, cgA, hyA, t0, table, T, rcSqr, fx,
                                             fy, fz, energy, vsum, pairs, activePairs);
             }
             for (int it = LJT_PREFETCH; it < iters; ++it)
             {
                 const int n = it * TL_GROUP + gl;
                 if (n < numNeighbors)
-                    adressPair<SINGLE_TYPE>(rec, sType, row[n], xi, yi, zi, typeI, modA, cgA, hyA, t0, table, T, rcSqr, fx, fy,
+                    adressPair<SINGLE_TYPE, ENERGY>(rec, sType, row[n], xi, yi, zi, typeI, modA, cgA, hyA, t0, table, T, rcSqr, fx, fy,
                                             fz, energy, vsum, pairs, activePairs);
             }
 #pragma unroll
@@ -733,7 +734,11 @@ int tiledConfigure()
 {
     static bool done = false;
     if (done) return 0;
-#define TL_SET(K) MB_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, TL_SMEM_MAX))
+    // the tiles live in shared memory and barely use L1: ask for the largest carveout so that residency is set by
+    // registers, not by the default shared-memory split
+#define TL_SET(K)                                                                                    \
+    MB_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, TL_SMEM_MAX));     \
+    MB_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))
     TL_SET((verletBuildTiledKernel<true>));
     TL_SET((verletBuildTiledKernel<false>));
     TL_SET((ljForceTiledKernel<true, true, true>));
@@ -744,10 +749,14 @@ int tiledConfigure()
     TL_SET((ljForceTiledKernel<false, true, false>));
     TL_SET((ljForceTiledKernel<false, false, true>));
     TL_SET((ljForceTiledKernel<false, false, false>));
-    TL_SET((adressForceTiledKernel<true, true>));
-    TL_SET((adressForceTiledKernel<true, false>));
-    TL_SET((adressForceTiledKernel<false, true>));
-    TL_SET((adressForceTiledKernel<false, false>));
+    TL_SET((adressForceTiledKernel<true, true, true>));
+    TL_SET((adressForceTiledKernel<true, true, false>));
+    TL_SET((adressForceTiledKernel<true, false, true>));
+    TL_SET((adressForceTiledKernel<true, false, false>));
+    TL_SET((adressForceTiledKernel<false, true, true>));
+    TL_SET((adressForceTiledKernel<false, true, false>));
+    TL_SET((adressForceTiledKernel<false, false, true>));
+    TL_SET((adressForceTiledKernel<false, false, false>));
 #undef TL_SET
     done = true;
     return 0;
@@ -787,7 +796,7 @@ int ljApplyTiled(mrmd_b200_lj* lj, mrmd_b200_atoms* a, const mrmd_b200_verlet* v
 
 // the force kernel of mrmd_b200_adress_run_periodic (adress.cu owns the run counter and the histogram update)
 int adressApplyTiled(mrmd_b200_adress* ad, mrmd_b200_atoms* a, const mrmd_b200_verlet* v, const mrmd_b200_weight* w,
-                     bool sampling, cudaStream_t st)
+                     bool sampling, bool energy, cudaStream_t st)
 {
     MB_REQUIRE(a->lcValid && a->lcEpoch == v->tiledEpoch,
                "adress_run_periodic: the atoms were re-sorted after this tiled list was built");
@@ -817,12 +826,20 @@ int adressApplyTiled(mrmd_b200_adress* ad, mrmd_b200_atoms* a, const mrmd_b200_v
     const size_t smem = size_t(v->tiledSlots) * TL_SMEM_PER_SLOT_ADRESS + 16;
     MB_REQUIRE(smem <= size_t(TL_SMEM_MAX), "adress_run_periodic: a tile exceeds shared memory");
     const bool single = (ad->numTypes == 1);
-#define ADT_LAUNCH(S1, SAMP)                                                                                          \
-    adressForceTiledKernel<S1, SAMP><<<tiles, TL_THREADS, smem, st>>>(                                                \
+#define ADT_LAUNCH(S1, SAMP, EN)                                                                                      \
+    adressForceTiledKernel<S1, SAMP, EN><<<tiles, TL_THREADS, smem, st>>>(                                            \
         tp, a->v, v->tileDesc.as<int>(), v->counts.as<int32_t>(), v->enc.as<uint16_t>(), static_cast<int>(v->width), \
         ad->table, ad->rcSqr, ad->numTypes, *w, ad->hist, ad->partials.as<double>(), ad->dResult, ad->dTicket)
-    if (single) { if (sampling) ADT_LAUNCH(true, true); else ADT_LAUNCH(true, false); }
-    else { if (sampling) ADT_LAUNCH(false, true); else ADT_LAUNCH(false, false); }
+    if (single)
+    {
+        if (sampling) { if (energy) ADT_LAUNCH(true, true, true); else ADT_LAUNCH(true, true, false); }
+        else { if (energy) ADT_LAUNCH(true, false, true); else ADT_LAUNCH(true, false, false); }
+    }
+    else
+    {
+        if (sampling) { if (energy) ADT_LAUNCH(false, true, true); else ADT_LAUNCH(false, true, false); }
+        else { if (energy) ADT_LAUNCH(false, false, true); else ADT_LAUNCH(false, false, false); }
+    }
 #undef ADT_LAUNCH
     MB_LAUNCHED();
     return 0;
