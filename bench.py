@@ -285,7 +285,8 @@ def run_b200(args):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms_max, pairs_total = float(tmax[0]), float(tsum[1])
+        # the slab driver already reports the pair interactions summed over the ranks
+        ms_max, pairs_total = float(tmax[0]), (float(stats["pairInteractions"]) if slab_mode else float(tsum[1]))
     else:
         ms_max, pairs_total = ms, float(stats["pairInteractions"])
     value = world * n * args.steps / (ms_max * 1e-3)
@@ -301,6 +302,18 @@ def run_b200(args):
         algo_bytes = 140.0 * n * args.steps + 12.0 * stored_half + 120.0 * stats["activePairs"]
         kernel_name = "adressForceTiledKernel" if args.full_list == 2 else "adressForceKernel"
     force_ms = stats["forceKernelMs"]
+    n_kernel, kernel_rank, stored_kernel = n, rank, stats["storedPairs"]
+    if world > 1:
+        # report the rank whose force kernel ran longest (AdResS slabs carry very different work)
+        import torch.distributed as dist
+
+        mine = torch.tensor([force_ms, algo_bytes, float(stats["numLocal"]), float(stats["storedPairs"])],
+                            dtype=torch.float64, device="cuda")
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        kernel_rank = int(np.argmax([float(e[0]) for e in every]))
+        force_ms, algo_bytes = float(every[kernel_rank][0]), float(every[kernel_rank][1])
+        n_kernel, stored_kernel = int(every[kernel_rank][2]), float(every[kernel_rank][3])
     achieved = algo_bytes / (force_ms * 1e-3) / 1e9 if force_ms > 0 else None
     traffic = ncu_traffic()
     roofline = {
@@ -308,8 +321,8 @@ def run_b200(args):
         "frac": (achieved / peak) if achieved else None, "peak_source": peak_src,
         "traffic": traffic["dram_bytes_per_launch"] if (traffic and not adress and n == 1000000) else None,
         "algorithmic_bytes_per_launch": algo_bytes / args.steps,
-        "kernel_ms_per_launch": force_ms / args.steps, "kernel_share_of_step": force_ms / ms,
-        "stored_pairs_per_atom": stats["storedPairs"] / args.steps / n,
+        "kernel_ms_per_launch": force_ms / args.steps, "kernel_share_of_step": force_ms / ms_max,
+        "stored_pairs_per_atom": stored_kernel / args.steps / max(n_kernel, 1), "rank": kernel_rank,
     }
 
     # end to end through the C ABI with HOST buffers: per step H2D pos+vel, one step, D2H pos+vel+scalars

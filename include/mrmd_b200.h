@@ -398,7 +398,8 @@ int mrmd_b200_slab_create(mrmd_b200_slab** out, const mrmd_b200_md_config* cfg, 
                           const double* globalMax, int rank, int nranks, const void* uniqueId128, mrmd_b200_atoms* atoms,
                           void* stream);
 int mrmd_b200_slab_destroy(mrmd_b200_slab* sl);
-/* nsteps collective steps; stats: energy / virial summed over the ranks, the other fields are per rank */
+/* nsteps collective steps; stats: energy, virial and pairInteractions are summed over the ranks (a pair across
+ * a slab face counts one half on either side), the other fields are per rank */
 int mrmd_b200_slab_run(mrmd_b200_slab* sl, int64_t nsteps, int timeForceKernel, mrmd_b200_md_stats* stats,
                        void* stream);
 

@@ -760,12 +760,15 @@ int mrmd_b200_slab_run(mrmd_b200_slab* sl, int64_t nsteps, int timeForceKernel, 
     MB_CUDA(cudaStreamSynchronize(st));
     if (stats != nullptr)
     {
-        // energy and virial of the last step summed over the ranks
+        // energy and virial of the last step and the pair counters summed over the ranks (a pair across a slab
+        // face counts one half on either side, so only the global sums are whole numbers)
         sl->hScalars[0] = hRes[0];
         sl->hScalars[1] = adress ? 0.0 : hRes[1];
-        MB_CUDA(cudaMemcpyAsync(sl->dScalars, sl->hScalars, 16, cudaMemcpyHostToDevice, st));
-        MB_NCCL(g_nccl.allReduce(sl->dScalars, sl->dScalars, 2, ncclDouble, ncclSum, sl->comm, st));
-        MB_CUDA(cudaMemcpyAsync(sl->hScalars, sl->dScalars, 16, cudaMemcpyDeviceToHost, st));
+        sl->hScalars[2] = (adress ? hRes[4] : hRes[5]) - pairs0;
+        sl->hScalars[3] = adress ? hRes[5] - active0 : 0.0;
+        MB_CUDA(cudaMemcpyAsync(sl->dScalars, sl->hScalars, 32, cudaMemcpyHostToDevice, st));
+        MB_NCCL(g_nccl.allReduce(sl->dScalars, sl->dScalars, 4, ncclDouble, ncclSum, sl->comm, st));
+        MB_CUDA(cudaMemcpyAsync(sl->hScalars, sl->dScalars, 32, cudaMemcpyDeviceToHost, st));
         MB_CUDA(cudaStreamSynchronize(st));
         stats->steps = nsteps;
         stats->rebuilds = sl->rebuilds - rebuilds0;
@@ -774,8 +777,8 @@ int mrmd_b200_slab_run(mrmd_b200_slab* sl, int64_t nsteps, int timeForceKernel, 
         stats->numGhost = sl->atoms->numGhost;
         stats->energy = sl->hScalars[0];
         stats->virial = sl->hScalars[1];
-        stats->pairInteractions = static_cast<int64_t>((adress ? hRes[4] : hRes[5]) - pairs0 + 0.5);
-        stats->activePairs = adress ? static_cast<int64_t>(hRes[5] - active0 + 0.5) : 0;
+        stats->pairInteractions = static_cast<int64_t>(sl->hScalars[2] + 0.5);
+        stats->activePairs = adress ? static_cast<int64_t>(hRes[5] - active0 + 0.5) : 0;  // this rank's rows
         stats->maxDisplacement = sl->maxDisplacement;
         double ms = 0.0;
         for (int i = 0; i < nTimed; ++i)

@@ -56,7 +56,8 @@ def main():
     if rank == 0:
         all_pos = np.concatenate([x[0] for x in gathered])
         all_vel = np.concatenate([x[1] for x in gathered])
-        pairs = sum(x[2] for x in gathered)
+        pairs = gathered[0][2]  # already the sum over the ranks
+        assert all(x[2] == pairs for x in gathered)
         # single-GPU periodic reference run of the same global system
         sub = api.Subdomain(gmin, gmax, phys["rc"] + phys["skin"])
         ref_atoms = api.Atoms.from_arrays(pos, vel, mass=1.0, relativeMass=1.0)
