@@ -270,9 +270,15 @@ def run_b200(args):
     barrier()
     launches0 = api.launch_count()
     sampler.start()
+    profile_range = bool(os.environ.get("MRMD_PROFILE_RANGE"))  # ncu --profile-from-start off: timed region only
+    if profile_range:
+        torch.cuda.profiler.start()
     ev0.record()
     stats = md.run(args.steps, timeForceKernel=True, stream=stream)
     ev1.record()
+    if profile_range:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     barrier()
     clocks = sampler.stop()
     launches = api.launch_count() - launches0

@@ -226,6 +226,7 @@ struct mrmd_b200_verlet
     int tiledHaloX = 0;          // x-slab decomposition: halo columns at i = -1 and i = nx
     mrmd_b200_subdomain tiledSub{};
     int64_t tiledEpoch = -1;
+    int tiledR = 1;  // cells along z spanned by the list radius
     int tiledCH = 0;
     int tiledSlots = 0;
     mrmd_b200::DevBuf keys[2];  // radix sort ping-pong

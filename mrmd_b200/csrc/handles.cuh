@@ -60,6 +60,10 @@ struct mrmd_b200_thermo
 
 namespace mrmd_b200
 {
+// integrate.cu: preForceIntegrate, optionally with the previous step's postForceIntegrate fused in front; the
+// squared maximum displacement is left in a->dMaxDisp
+int integratePre(mrmd_b200_atoms* a, double dt, bool langevin, double zeta, double temperature, uint64_t seed,
+                 uint64_t step, const mrmd_b200_pred* pred, bool fusedPost, cudaStream_t st);
 // tiled.cu: LennardJones::apply over a tiled (periodic, shared-memory staged) full list
 int ljApplyTiled(mrmd_b200_lj* lj, mrmd_b200_atoms* a, const mrmd_b200_verlet* v, bool accumulate, bool energy,
                  cudaStream_t st);

@@ -73,7 +73,9 @@ __device__ __forceinline__ void blockMaxToGlobal(double v, double* dMax)
 }
 
 // LANGEVIN = false: VelocityVerlet::preForceIntegrate;  true: ...LangevinThermostat::preForceIntegrate_apply_if
-template <bool LANGEVIN>
+// FUSED_POST: the previous step's postForceIntegrate (same dt, same force) is applied first, as its own rounded
+// addition, so the step loops save one pass over vel / force / mass per step
+template <bool LANGEVIN, bool FUSED_POST>
 __global__ void __launch_bounds__(256)
     integratePreKernel(AtomsView a, int64_t n, double dt, double zeta, double temperature, uint64_t seed,
                        uint64_t step, mrmd_b200_pred pred, double* dMax)
@@ -88,9 +90,18 @@ __global__ void __launch_bounds__(256)
         double vx = a.vel[0][idx], vy = a.vel[1][idx], vz = a.vel[2][idx];
         const double m = a.mass[idx];
         const double dtfm = dtHalf / m;  // updateKick, UpdateSteps.hpp:36-39
-        vx += dtfm * a.force[0][idx];
-        vy += dtfm * a.force[1][idx];
-        vz += dtfm * a.force[2][idx];
+        // explicit rounding (no FMA contraction): the fused and the separate kick give identical bits
+        const double kx = __dmul_rn(dtfm, a.force[0][idx]), ky = __dmul_rn(dtfm, a.force[1][idx]),
+                     kz = __dmul_rn(dtfm, a.force[2][idx]);
+        if (FUSED_POST)
+        {
+            vx = __dadd_rn(vx, kx);  // postForceIntegrate of the previous step, VelocityVerlet.cpp:69-90
+            vy = __dadd_rn(vy, ky);
+            vz = __dadd_rn(vz, kz);
+        }
+        vx = __dadd_rn(vx, kx);
+        vy = __dadd_rn(vy, ky);
+        vz = __dadd_rn(vz, kz);
         if (!LANGEVIN)
         {
             p.x += dt * vx;  // updateDrift, UpdateSteps.hpp:51-53
@@ -135,9 +146,9 @@ __global__ void __launch_bounds__(256) integratePostKernel(AtomsView a, int64_t 
     const int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
     if (idx >= n) return;
     const double dtfm = (0.5 * dt) / a.mass[idx];
-    a.vel[0][idx] += dtfm * a.force[0][idx];
-    a.vel[1][idx] += dtfm * a.force[1][idx];
-    a.vel[2][idx] += dtfm * a.force[2][idx];
+    a.vel[0][idx] = __dadd_rn(a.vel[0][idx], __dmul_rn(dtfm, a.force[0][idx]));
+    a.vel[1][idx] = __dadd_rn(a.vel[1][idx], __dmul_rn(dtfm, a.force[1][idx]));
+    a.vel[2][idx] = __dadd_rn(a.vel[2][idx], __dmul_rn(dtfm, a.force[2][idx]));
 }
 
 static int fetchMaxDisp(mrmd_b200_atoms* a, double* maxDisplacement, cudaStream_t st)
@@ -146,6 +157,24 @@ static int fetchMaxDisp(mrmd_b200_atoms* a, double* maxDisplacement, cudaStream_
     MB_CUDA(cudaMemcpyAsync(a->hMaxDisp, a->dMaxDisp, 8, cudaMemcpyDeviceToHost, st));
     MB_CUDA(cudaStreamSynchronize(st));
     *maxDisplacement = std::sqrt(*a->hMaxDisp);  // VelocityVerlet.cpp:66
+    return 0;
+}
+
+// shared by the C ABI and the step-loop drivers (fusedPost: see integratePreKernel)
+int integratePre(mrmd_b200_atoms* a, double dt, bool langevin, double zeta, double temperature, uint64_t seed,
+                 uint64_t step, const mrmd_b200_pred* pred, bool fusedPost, cudaStream_t st)
+{
+    MB_CUDA(cudaMemsetAsync(a->dMaxDisp, 0, 8, st));
+    if (a->numLocal == 0) return 0;
+    mrmd_b200_pred p{};
+    if (pred != nullptr) p = *pred;
+    const int blocks = gridFor(a->numLocal, 256);
+#define PRE_LAUNCH(L, F) \
+    integratePreKernel<L, F><<<blocks, 256, 0, st>>>(a->v, a->numLocal, dt, zeta, temperature, seed, step, p, a->dMaxDisp)
+    if (langevin) { if (fusedPost) PRE_LAUNCH(true, true); else PRE_LAUNCH(true, false); }
+    else { if (fusedPost) PRE_LAUNCH(false, true); else PRE_LAUNCH(false, false); }
+#undef PRE_LAUNCH
+    MB_LAUNCHED();
     return 0;
 }
 }  // namespace mrmd_b200
@@ -159,14 +188,7 @@ int mrmd_b200_vv_pre(mrmd_b200_atoms* a, double dt, double* maxDisplacement, voi
     MB_TRY(checkDevice());
     MB_REQUIRE(a != nullptr, "vv_pre");
     cudaStream_t st = S(stream);
-    MB_CUDA(cudaMemsetAsync(a->dMaxDisp, 0, 8, st));
-    if (a->numLocal > 0)
-    {
-        mrmd_b200_pred none{};
-        integratePreKernel<false><<<gridFor(a->numLocal, 256), 256, 0, st>>>(a->v, a->numLocal, dt, 0.0, 0.0, 0, 0,
-                                                                             none, a->dMaxDisp);
-        MB_LAUNCHED();
-    }
+    MB_TRY(integratePre(a, dt, false, 0.0, 0.0, 0, 0, nullptr, false, st));
     return fetchMaxDisp(a, maxDisplacement, st);
 }
 
@@ -186,15 +208,7 @@ int mrmd_b200_langevin_pre(mrmd_b200_atoms* a, double dt, double zeta, double te
     MB_TRY(checkDevice());
     MB_REQUIRE(a != nullptr, "langevin_pre");
     cudaStream_t st = S(stream);
-    MB_CUDA(cudaMemsetAsync(a->dMaxDisp, 0, 8, st));
-    if (a->numLocal > 0)
-    {
-        mrmd_b200_pred p{};
-        if (pred != nullptr) p = *pred;
-        integratePreKernel<true><<<gridFor(a->numLocal, 256), 256, 0, st>>>(a->v, a->numLocal, dt, zeta, temperature,
-                                                                            seed, step, p, a->dMaxDisp);
-        MB_LAUNCHED();
-    }
+    MB_TRY(integratePre(a, dt, true, zeta, temperature, seed, step, pred, false, st));
     return fetchMaxDisp(a, maxDisplacement, st);
 }
 

@@ -25,7 +25,7 @@ struct mrmd_b200_md
     int64_t rebuilds = 0;
     int64_t storedPairsNow = 0;
     double active0 = 0.0;  // running active-pair count when the current run started
-    bool ghostsStale = false;  // tiled fast path: ghost positions / forces are refreshed when a run returns
+    bool postPending = false;  // the last step's postForceIntegrate is fused into the next preForceIntegrate
     std::vector<cudaEvent_t> events;
 };
 
@@ -42,7 +42,9 @@ static int rebuild(mrmd_b200_md* md, cudaStream_t st)
     const mrmd_b200_md_config& c = md->cfg;
     mrmd_b200_atoms* a = md->atoms;
     const double cutoff = c.rc + c.skin;
-    const double delta[3] = {cutoff, cutoff, cutoff};
+    // LinkedCellList gridDelta of the spatial sort: one list radius along x and y, a quarter along z (atoms of a
+    // cell column end up in fine z order, which the tiled neighbour build exploits)
+    const double delta[3] = {cutoff, cutoff, 0.25 * cutoff};
     if (c.adress)
     {
         // MultiResGhostLayer::exchangeRealAtoms (needs the current centres of mass),
@@ -84,11 +86,11 @@ static int rebuild(mrmd_b200_md* md, cudaStream_t st)
         a->size = a->numLocal;
         if (c.cellSort)  // tests/NVT/NVT.cpp:136-144
             MB_TRY(mrmd_b200_atoms_cell_sort(a, 0, a->numLocal, delta, md->sub.minCorner, md->sub.maxCorner, nullptr, st));
-        MB_TRY(mrmd_b200_ghost_create_atoms(md->ghost, a, &md->sub, -1, st));  // examples/02:153
         if (c.fullList == 2)
         {
             // fast path: the same pair set as the list over local + ghost atoms, built on shared-memory tiles
-            // of the freshly sorted local atoms with the periodic images generated on the fly (tiled.cu)
+            // of the freshly sorted local atoms with the periodic images generated on the fly (tiled.cu); ghost
+            // atoms are never materialised: the container holds the local atoms only
             MB_TRY(mrmd_b200_verlet_build_periodic(md->list, a, &md->sub, cutoff, 1.0, c.maxNeighbors, st));
             int64_t total = 0;
             MB_TRY(mrmd_b200_verlet_info(md->list, nullptr, nullptr, &total, nullptr));
@@ -96,6 +98,7 @@ static int rebuild(mrmd_b200_md* md, cudaStream_t st)
             md->rebuilds += 1;
             return 0;
         }
+        MB_TRY(mrmd_b200_ghost_create_atoms(md->ghost, a, &md->sub, -1, st));  // examples/02:153
         MB_TRY(mrmd_b200_verlet_build_atoms(md->list, a, 0, a->numLocal, cutoff, 1.0, md->sub.minGhostCorner,
                                             md->sub.maxGhostCorner, c.maxNeighbors, st));  // examples/02:156-163
     }
@@ -107,18 +110,29 @@ static int rebuild(mrmd_b200_md* md, cudaStream_t st)
 }
 
 // one step; evStart/evStop (optional) bracket the force kernel
-static int oneStep(mrmd_b200_md* md, cudaStream_t st, cudaEvent_t evStart, cudaEvent_t evStop, bool needRebuildHint,
+static int postIntegrate(mrmd_b200_md* md, bool deferPost, cudaStream_t st)
+{
+    if (deferPost)
+    {
+        md->postPending = true;
+        return 0;
+    }
+    return mrmd_b200_vv_post(md->atoms, md->cfg.dt, st);
+}
+
+// deferPost: leave postForceIntegrate to the next step's fused kernel (the caller flushes it when the run ends)
+static int oneStep(mrmd_b200_md* md, cudaStream_t st, cudaEvent_t evStart, cudaEvent_t evStop, bool deferPost,
                    bool wantEnergy)
 {
     const mrmd_b200_md_config& c = md->cfg;
     mrmd_b200_atoms* a = md->atoms;
-    double disp = 0.0;
-    if (c.integrator == 1)
-        MB_TRY(mrmd_b200_langevin_pre(a, c.dt, c.zeta, c.temperature, c.seed, uint64_t(md->step), nullptr, &disp, st));
-    else
-        MB_TRY(mrmd_b200_vv_pre(a, c.dt, &disp, st));
-    md->maxDisplacement += disp;  // examples/02:138
-    if (needRebuildHint || md->maxDisplacement >= c.skin * 0.5)  // :141-143
+    MB_TRY(integratePre(a, c.dt, c.integrator == 1, c.zeta, c.temperature, c.seed, uint64_t(md->step), nullptr,
+                        md->postPending, st));
+    md->postPending = false;
+    MB_CUDA(cudaMemcpyAsync(a->hMaxDisp, a->dMaxDisp, 8, cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaStreamSynchronize(st));
+    md->maxDisplacement += std::sqrt(*a->hMaxDisp);  // examples/02:138, VelocityVerlet.cpp:66
+    if (md->maxDisplacement >= c.skin * 0.5)  // :141-143
     {
         md->maxDisplacement = 0.0;
         MB_TRY(rebuild(md, st));
@@ -145,7 +159,7 @@ static int oneStep(mrmd_b200_md* md, cudaStream_t st, cudaEvent_t evStart, cudaE
         if (evStart) MB_CUDA(cudaEventRecord(evStart, st));
         MB_TRY(adressRunPeriodic(md->adress, a, md->list, &c.weight, wantEnergy, st));
         if (evStop) MB_CUDA(cudaEventRecord(evStop, st));
-        MB_TRY(mrmd_b200_vv_post(a, c.dt, st));
+        MB_TRY(postIntegrate(md, deferPost, st));
         md->step += 1;
         return 0;
     }
@@ -157,9 +171,8 @@ static int oneStep(mrmd_b200_md* md, cudaStream_t st, cudaEvent_t evStart, cudaE
         // energy and virial are only observable after the run returns: accumulate them on its last step
         MB_TRY(ljApplyTiled(md->lj, a, md->list, false, wantEnergy, st));
         if (evStop) MB_CUDA(cudaEventRecord(evStop, st));
-        MB_TRY(mrmd_b200_vv_post(a, c.dt, st));
+        MB_TRY(postIntegrate(md, deferPost, st));
         md->step += 1;
-        md->ghostsStale = true;
         return 0;
     }
     MB_TRY(mrmd_b200_atoms_fill(a, MRMD_B200_ATOM_FORCE, 0.0, st));  // :174-175
@@ -188,7 +201,7 @@ static int oneStep(mrmd_b200_md* md, cudaStream_t st, cudaEvent_t evStart, cudaE
         if (evStop) MB_CUDA(cudaEventRecord(evStop, st));
         if (!c.fullList) MB_TRY(mrmd_b200_ghost_contribute_back(md->ghost, a, st));  // :181 (no-op for a full list)
     }
-    MB_TRY(mrmd_b200_vv_post(a, c.dt, st));  // :184
+    MB_TRY(postIntegrate(md, deferPost, st));  // :184
     md->step += 1;
     return 0;
 }
@@ -196,15 +209,6 @@ static int oneStep(mrmd_b200_md* md, cudaStream_t st, cudaEvent_t evStart, cudaE
 static int collectStats(mrmd_b200_md* md, int64_t nsteps, int64_t rebuilds0, int64_t storedSum, double pairs0,
                         int nTimed, mrmd_b200_md_stats* stats, cudaStream_t st)
 {
-    if (md->ghostsStale)
-    {
-        // leave the container as the reference loop would: ghosts at their real atom's image, zero ghost force
-        mrmd_b200_atoms* a = md->atoms;
-        MB_TRY(mrmd_b200_ghost_update(md->ghost, a, &md->sub, st));
-        for (int d = 0; d < 3 && a->numGhost > 0; ++d)
-            MB_CUDA(cudaMemsetAsync(a->v.force[d] + a->numLocal, 0, size_t(a->numGhost) * 8, st));
-        md->ghostsStale = false;
-    }
     double* dRes = md->cfg.adress ? md->adress->dResult : md->lj->dResult;
     double* hRes = md->cfg.adress ? md->adress->hResult : md->lj->hResult;
     MB_CUDA(cudaMemcpyAsync(hRes, dRes, 48, cudaMemcpyDeviceToHost, st));
@@ -334,8 +338,13 @@ int mrmd_b200_md_run(mrmd_b200_md* md, int64_t nsteps, int timeForceKernel, mrmd
     {
         cudaEvent_t e0 = (i < nTimed) ? md->events[2 * i] : nullptr;
         cudaEvent_t e1 = (i < nTimed) ? md->events[2 * i + 1] : nullptr;
-        MB_TRY(oneStep(md, st, e0, e1, false, i == nsteps - 1));
+        MB_TRY(oneStep(md, st, e0, e1, true, i == nsteps - 1));
         storedSum += md->storedPairsNow;
+    }
+    if (md->postPending)
+    {
+        MB_TRY(mrmd_b200_vv_post(md->atoms, md->cfg.dt, st));
+        md->postPending = false;
     }
     return collectStats(md, nsteps, rebuilds0, storedSum, pairs0, nTimed, stats, st);
 }

@@ -316,6 +316,7 @@ struct mrmd_b200_slab
     mrmd_b200_adress* adress = nullptr;  // AdResS mode (one-atom molecules, tiled kernel)
     mrmd_b200_thermo* thermo = nullptr;  // bins over the GLOBAL box, density all-reduced before every update
     double maxDisplacement = DBL_MAX;
+    bool postPending = false;
     int64_t step = 0, rebuilds = 0, storedPairsNow = 0;
     int64_t haloLeftCount = 0, haloRightCount = 0;   // received
     int64_t sendLeftCount = 0, sendRightCount = 0;   // boundary atoms sent every step
@@ -437,7 +438,7 @@ static int migrate(mrmd_b200_slab* sl, cudaStream_t st)
         MB_LAUNCHED();
     }
     const double cutoff = sl->cfg.rc + sl->cfg.skin;
-    const double delta[3] = {cutoff, cutoff, cutoff};
+    const double delta[3] = {cutoff, cutoff, 0.25 * cutoff};  // as md.cu: fine z order inside a cell column
     MB_TRY(atomsCellSortDrop(a, 0, n + nRecv, delta, sl->sub.minCorner, sl->sub.maxCorner, sl->flags.as<signed char>(), st));
     a->numLocal = n + nRecv - nSend;
     a->size = a->numLocal;
@@ -556,11 +557,10 @@ static int slabStep(mrmd_b200_slab* sl, cudaStream_t st, cudaEvent_t e0, cudaEve
 {
     const mrmd_b200_md_config& c = sl->cfg;
     mrmd_b200_atoms* a = sl->atoms;
-    if (c.integrator == 1)
-        MB_TRY(mrmd_b200_langevin_pre(a, c.dt, c.zeta, c.temperature, c.seed + uint64_t(sl->rank), uint64_t(sl->step),
-                                      nullptr, nullptr, st));
-    else
-        MB_TRY(mrmd_b200_vv_pre(a, c.dt, nullptr, st));
+    // the previous step's postForceIntegrate rides in front of this kick (flushed when a run returns)
+    MB_TRY(integratePre(a, c.dt, c.integrator == 1, c.zeta, c.temperature, c.seed + uint64_t(sl->rank),
+                        uint64_t(sl->step), nullptr, sl->postPending, st));
+    sl->postPending = false;
     // the rebuild decision is collective: global maximum of the squared displacement
     MB_NCCL(g_nccl.allReduce(a->dMaxDisp, a->dMaxDisp, 1, ncclDouble, ncclMax, sl->comm, st));
     MB_CUDA(cudaMemcpyAsync(a->hMaxDisp, a->dMaxDisp, 8, cudaMemcpyDeviceToHost, st));
@@ -601,7 +601,7 @@ static int slabStep(mrmd_b200_slab* sl, cudaStream_t st, cudaEvent_t e0, cudaEve
         MB_TRY(ljApplyTiled(sl->lj, a, sl->list, false, wantEnergy, st));
         if (e1) MB_CUDA(cudaEventRecord(e1, st));
     }
-    MB_TRY(mrmd_b200_vv_post(a, c.dt, st));
+    sl->postPending = true;
     sl->step += 1;
     return 0;
 }
@@ -755,6 +755,11 @@ int mrmd_b200_slab_run(mrmd_b200_slab* sl, int64_t nsteps, int timeForceKernel, 
         MB_TRY(slabStep(sl, st, i < nTimed ? sl->events[2 * i] : nullptr, i < nTimed ? sl->events[2 * i + 1] : nullptr,
                         i == nsteps - 1));
         storedSum += sl->storedPairsNow;
+    }
+    if (sl->postPending)
+    {
+        MB_TRY(mrmd_b200_vv_post(sl->atoms, sl->cfg.dt, st));
+        sl->postPending = false;
     }
     MB_CUDA(cudaMemcpyAsync(hRes, dRes, 48, cudaMemcpyDeviceToHost, st));
     MB_CUDA(cudaStreamSynchronize(st));

@@ -30,13 +30,15 @@ constexpr int TL_THREADS = 256;
 constexpr int TL_GROUP = 8;                       // lanes per home atom
 constexpr int TL_GROUPS = TL_THREADS / TL_GROUP;  // home atoms in flight per block
 constexpr int TL_PIECES = 27;                     // 9 columns x {low z-wrap, main, high z-wrap}
-constexpr int TL_MAX_CH = 16;                     // home cells per tile along z
-constexpr int TL_CELLS = TL_MAX_CH + 3;
+constexpr int TL_MAX_CH = 64;                     // home cells per tile along z
+constexpr int TL_MAX_R = 4;                       // the list radius spans at most this many cells along z
+constexpr int TL_CELLS = TL_MAX_CH + 2 * TL_MAX_R + 1;
 constexpr int TL_DESC_INTS = 64;                  // per-tile descriptor in global memory
 
 struct TileParams
 {
-    GridDev g;  // linked-cell grid of the sorted local atoms
+    GridDev g;  // linked-cell grid of the sorted local atoms: cells >= radius along x and y, any size along z
+    int R;      // cells along z that the list radius spans: ceil(radius / g.dx[2]) (1 for cubic cells)
     int CH;
     int numChunks;
     int periodic[3];  // ghost layer thickness > 0 on that axis
@@ -93,9 +95,10 @@ __global__ void __launch_bounds__(32) tileDescKernel(TileParams tp, const int32_
         int ii = ci + r / 3 - 1 - sx * tp.g.n[0], jj = cj + r % 3 - 1 - sy * tp.g.n[1];
         bool exists = !((sx != 0 && !tp.periodic[0]) || (sy != 0 && !tp.periodic[1]));
         int klo, khi;
-        if (w == 1) { klo = max(k0 - 1, 0); khi = min(k1 + 1, nz - 1); }
-        else if (w == 0) { klo = khi = nz - 1; exists = exists && (k0 == 0) && tp.periodic[2]; }
-        else { klo = khi = 0; exists = exists && (k1 == nz - 1) && tp.periodic[2]; }
+        const int R = tp.R;
+        if (w == 1) { klo = max(k0 - R, 0); khi = min(k1 + R, nz - 1); }
+        else if (w == 0) { klo = nz + (k0 - R); khi = nz - 1; exists = exists && (k0 - R < 0) && tp.periodic[2]; }
+        else { klo = 0; khi = k1 + R - nz; exists = exists && (k1 + R > nz - 1) && tp.periodic[2]; }
         if (exists)
         {
             start = cellLo[extCell(tp, ii, jj, klo)];
@@ -116,7 +119,7 @@ __global__ void __launch_bounds__(32) tileDescKernel(TileParams tp, const int32_
     {
         const int homeStart = cellLo[extCell(tp, ci, cj, k0)];
         const int homeCount = cellHi[extCell(tp, ci, cj, k1)] - homeStart;
-        const int centreStart = cellLo[extCell(tp, ci, cj, max(k0 - 1, 0))];
+        const int centreStart = cellLo[extCell(tp, ci, cj, max(k0 - tp.R, 0))];
         desc[tile * TL_DESC_INTS + 54] = homeStart;
         desc[tile * TL_DESC_INTS + 55] = homeCount;
         desc[tile * TL_DESC_INTS + 56] = before + (homeStart - centreStart);
@@ -220,7 +223,7 @@ __device__ __forceinline__ bool cabanaCellReachable(const GridDev& cg, double px
 // own cell in each of the nine columns are one contiguous slot range per column), accepted slots are
 // appended in slot order through a ballot over the group -> deterministic rows, no atomics.
 template <bool HALF>
-__global__ void __launch_bounds__(TL_THREADS)
+__global__ void __launch_bounds__(TL_THREADS, 4)
     verletBuildTiledKernel(TileParams tp, GridDev cabanaGrid, const double4* __restrict__ pos,
                            const int32_t* __restrict__ cellLo, const int* __restrict__ desc, double rsqr, int width,
                            int32_t* __restrict__ counts, uint16_t* __restrict__ enc, int32_t* stats)
@@ -240,16 +243,17 @@ __global__ void __launch_bounds__(TL_THREADS)
     const int k0 = chunk * tp.CH;
     const int k1 = min(k0 + tp.CH, nz) - 1;
     const int nk = k1 - k0 + 1;
-    const int nv = nk + 3;  // virtual cells k0-1 .. k1+1 plus the end sentinel
+    const int R = tp.R;
+    const int nv = nk + 2 * R + 1;  // virtual cells k0-R .. k1+R plus the end sentinel
     for (int e = threadIdx.x; e < 9 * nv; e += TL_THREADS)
     {
         const int r = e / nv, v = e % nv;
-        const int kv = k0 - 1 + v;
+        const int kv = k0 - R + v;
+        // virtual cells below 0 / beyond nz-1 live in the low / high z-wrap piece (cells nz+kv / kv-nz of the column)
+        const int piece = r * 3 + ((kv < 0) ? 0 : ((kv >= nz) ? 2 : 1));
         int slot;
         if (v == nv - 1) slot = td.pieceSlot[r * 3 + 3];
-        else if (kv < 0) slot = td.pieceSlot[r * 3 + 0];
-        else if (kv >= nz) slot = td.pieceSlot[r * 3 + 2];
-        else if (td.pieceLen[r * 3 + 1] == 0) slot = td.pieceSlot[r * 3 + 1];
+        else if (td.pieceLen[piece] == 0) slot = td.pieceSlot[piece];
         else
         {
             int ii = ci + r / 3 - 1, jj = cj + r % 3 - 1;
@@ -258,7 +262,8 @@ __global__ void __launch_bounds__(TL_THREADS)
                 if (ii < 0) ii += tp.g.n[0]; else if (ii >= tp.g.n[0]) ii -= tp.g.n[0];
             }
             if (jj < 0) jj += tp.g.n[1]; else if (jj >= tp.g.n[1]) jj -= tp.g.n[1];
-            slot = td.pieceSlot[r * 3 + 1] + (cellLo[extCell(tp, ii, jj, kv)] - td.pieceStart[r * 3 + 1]);
+            const int kk = (kv < 0) ? kv + nz : ((kv >= nz) ? kv - nz : kv);
+            slot = td.pieceSlot[piece] + (cellLo[extCell(tp, ii, jj, kk)] - td.pieceStart[piece]);
         }
         cellSlot[r][v] = slot;
     }
@@ -279,16 +284,50 @@ __global__ void __launch_bounds__(TL_THREADS)
         const int i = td.homeStart + h;
         const int selfSlot = active ? td.selfSlot0 + h : -1;
         const int safeSlot = active ? selfSlot : 0;
-        int v = 1;  // virtual cell of the home atom: cellSlot[4][v] <= selfSlot < cellSlot[4][v+1]
-        if (active)
-            while (v < nk && cellSlot[4][v + 1] <= selfSlot) ++v;
         const double px = active ? sx_[3 * selfSlot] : 0.0, py = active ? sy_[3 * selfSlot] : 0.0, pz = active ? sz_[3 * selfSlot] : 0.0;
         int count = 0;
         uint16_t* row = enc + size_t(active ? i : 0) * width;
+        // A column is scanned only over the z interval that the sphere around the home atom cuts out of it: with
+        // (bx, by) the distance to the nearest face of the column, partners have |dz| <= sqrt(r^2 - bx^2 - by^2).
+        // Atoms are in cell order along z, so the interval is one slot range.  The margins (1e-6 relative) cover atoms
+        // that sit an ulp outside the cell they were binned into and the rounding of the image shifts.
+        // The interval is computed in single precision (this is bookkeeping, not the list criterion): positions are
+        // taken relative to the home column / tile so that the float error stays near 1e-6, and every bound is
+        // widened by 1e-3 of a cell or of the radius, far more than that error.
+        const float rPrune = static_cast<float>(rsqr) * 1.002f;
+        const double xlo = tp.g.min[0] + double(ci) * tp.g.dx[0], ylo = tp.g.min[1] + double(cj) * tp.g.dx[1];
+        const float fdx = static_cast<float>(tp.g.dx[0]), fdy = static_cast<float>(tp.g.dx[1]);
+        const float fx = static_cast<float>(px - xlo), fy = static_cast<float>(py - ylo);
+        const float dxl = fmaxf(fx, 0.f), dxh = fmaxf(fdx - fx, 0.f);
+        const float dyl = fmaxf(fy, 0.f), dyh = fmaxf(fdy - fy, 0.f);
+        const int vBase = k0 - R;  // cell index of virtual cell 0
+        // z in units of cells, relative to virtual cell 0
+        const float zCells = static_cast<float>((pz - (tp.g.min[2] + double(vBase) * tp.g.dx[2])) * tp.g.rdx[2]);
+        const float frdz = static_cast<float>(tp.g.rdx[2]);
 #pragma unroll 1
         for (int r = 0; r < 9; ++r)
         {
-            const int s0 = active ? cellSlot[r][v - 1] : 0, s1 = active ? cellSlot[r][v + 2] : 0;
+            const int ox = r / 3 - 1, oy = r % 3 - 1;
+            const float bx = (ox < 0) ? dxl : ((ox > 0) ? dxh : 0.f);
+            const float by = (oy < 0) ? dyl : ((oy > 0) ? dyh : 0.f);
+            const float h2 = rPrune - (bx * bx + by * by);
+            int s0 = 0, s1 = 0;
+            if (active && h2 >= 0.f)
+            {
+                const float hz = sqrtf(h2) * frdz + 1e-3f;  // in cells
+                int kA = static_cast<int>(floorf(zCells - hz)) + vBase;
+                int kB = static_cast<int>(floorf(zCells + hz)) + vBase;
+                if (!tp.periodic[2])
+                {
+                    // atoms beyond a non-periodic face are binned into the boundary cells
+                    kA = max(0, min(kA, nz - 1));
+                    kB = max(0, min(kB, nz - 1));
+                }
+                const int vA = max(kA - vBase, 0);
+                const int vB = min(kB - vBase, nv - 2);
+                s0 = cellSlot[r][vA];
+                s1 = cellSlot[r][max(vB + 1, vA)];
+            }
             const int iters = __reduce_max_sync(0xffffffffu, (s1 - s0 + TL_GROUP - 1) / TL_GROUP);
             for (int it = 0; it < iters; ++it)
             {
@@ -707,10 +746,11 @@ __global__ void extCellRangesKernel(const int32_t* __restrict__ localStart, int6
     cellHi[c] = hi;
 }
 
-static int makeTileParams(const mrmd_b200_atoms* a, const mrmd_b200_subdomain* s, int CH, int cap, int haloX,
+static int makeTileParams(const mrmd_b200_atoms* a, const mrmd_b200_subdomain* s, int CH, int cap, int haloX, int R,
                           TileParams& tp)
 {
     tp.g = a->lcGrid;
+    tp.R = R;
     tp.haloX = haloX;
     tp.CH = CH;
     tp.numChunks = (tp.g.n[2] + CH - 1) / CH;
@@ -769,7 +809,7 @@ int ljApplyTiled(mrmd_b200_lj* lj, mrmd_b200_atoms* a, const mrmd_b200_verlet* v
     MB_REQUIRE(!v->half, "lj_apply: tiled lists are full lists");
     MB_TRY(tiledConfigure());
     TileParams tp;
-    MB_TRY(makeTileParams(a, &v->tiledSub, v->tiledCH, v->tiledSlots, v->tiledHaloX, tp));
+    MB_TRY(makeTileParams(a, &v->tiledSub, v->tiledCH, v->tiledSlots, v->tiledHaloX, v->tiledR, tp));
     const int tiles = tp.g.n[0] * tp.g.n[1] * tp.numChunks;
     MB_TRY(lj->partials.reserve(size_t(tiles) * 3 * 8));
     MB_CUDA(cudaMemsetAsync(lj->dResult, 0, 24, st));
@@ -819,7 +859,7 @@ int adressApplyTiled(mrmd_b200_adress* ad, mrmd_b200_atoms* a, const mrmd_b200_v
     }
     MB_TRY(tiledConfigure());
     TileParams tp;
-    MB_TRY(makeTileParams(a, &v->tiledSub, v->tiledCH, v->tiledSlots, v->tiledHaloX, tp));
+    MB_TRY(makeTileParams(a, &v->tiledSub, v->tiledCH, v->tiledSlots, v->tiledHaloX, v->tiledR, tp));
     const int tiles = tp.g.n[0] * tp.g.n[1] * tp.numChunks;
     MB_TRY(ad->partials.reserve(size_t(tiles) * 3 * 8));
     MB_CUDA(cudaMemsetAsync(ad->dResult, 0, 24, st));
@@ -860,16 +900,23 @@ int verletBuildTiled(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, const mrmd_b
     MB_REQUIRE(a->lcValid && a->lcBegin == 0 && a->lcEnd == a->numLocal,
                "verlet_build_periodic: sort the local atoms first (LinkedCellList + permute over [0, numLocalAtoms))");
     const GridDev& g = a->lcGrid;
+    // cells are at least one radius wide along x and y (3 x 3 columns around a tile); along z they may be finer: a
+    // LinkedCellList with gridDelta = (r, r, r / 4) keeps the atoms of a column in finer z order and lets the
+    // builder scan only the z interval the cutoff sphere cuts out of each column
+    const int R = static_cast<int>(std::ceil(radius / g.dx[2] - 1e-12));
+    MB_REQUIRE(R >= 1 && R <= TL_MAX_R, "verlet_build_periodic: linked cells along z finer than radius / 4");
     for (int d = 0; d < 3; ++d)
     {
+        const int reach = (d == 2) ? R : 1;
         MB_REQUIRE(g.min[d] == s->minCorner[d] && std::fabs(g.dx[d] * g.n[d] - s->diameter[d]) <= 1e-9 * s->diameter[d],
                    "verlet_build_periodic: the linked-cell grid must span the subdomain");
-        MB_REQUIRE(g.dx[d] >= radius, "verlet_build_periodic: linked cells smaller than the list radius");
-        MB_REQUIRE(g.n[d] >= 3 || s->ghostLayerThickness[d] == 0.0 || (d == 0 && haloX),
-                   "verlet_build_periodic: fewer than 3 cells on a periodic axis");
-        MB_REQUIRE(s->ghostLayerThickness[d] == 0.0 || s->ghostLayerThickness[d] <= g.dx[d],
-                   "verlet_build_periodic: ghost layer thicker than a linked cell");
+        MB_REQUIRE(g.dx[d] * reach >= radius, "verlet_build_periodic: linked cells smaller than the list radius");
+        MB_REQUIRE(g.n[d] >= 2 * reach + 1 || s->ghostLayerThickness[d] == 0.0 || (d == 0 && haloX),
+                   "verlet_build_periodic: a periodic axis is shorter than three list radii");
+        MB_REQUIRE(s->ghostLayerThickness[d] == 0.0 || s->ghostLayerThickness[d] <= g.dx[d] * reach,
+                   "verlet_build_periodic: ghost layer thicker than the cells the list radius spans");
     }
+    v->tiledR = R;
     MB_TRY(tiledConfigure());
     const int64_t n = a->numLocal;
     if (v->hStats == nullptr) MB_CUDA(cudaMallocHost(&v->hStats, 16));
@@ -909,7 +956,7 @@ int verletBuildTiled(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, const mrmd_b
     int tiles = 0;
     for (;;)
     {
-        MB_TRY(makeTileParams(a, s, CH, 0, haloX, tp));
+        MB_TRY(makeTileParams(a, s, CH, 0, haloX, R, tp));
         tiles = g.n[0] * g.n[1] * tp.numChunks;
         MB_TRY(v->tileDesc.reserve(size_t(tiles) * TL_DESC_INTS * 4));
         MB_CUDA(cudaMemsetAsync(v->stats.p, 0, 16, st));
@@ -978,7 +1025,7 @@ int mrmd_b200_verlet_read_periodic(const mrmd_b200_verlet* v, const mrmd_b200_at
     const int64_t n = v->numParticles;
     if (n == 0) return 0;
     TileParams tp;
-    MB_TRY(makeTileParams(a, &v->tiledSub, v->tiledCH, v->tiledSlots, v->tiledHaloX, tp));
+    MB_TRY(makeTileParams(a, &v->tiledSub, v->tiledCH, v->tiledSlots, v->tiledHaloX, v->tiledR, tp));
     const int tiles = tp.g.n[0] * tp.g.n[1] * tp.numChunks;
     int32_t* d = nullptr;
     MB_CUDA(cudaMalloc(&d, size_t(n) * v->width * 8));

@@ -46,7 +46,7 @@ class OracleMD:
         L, a, n = self.L, self.atoms, self.n
         L.or_periodic_map(a.ctypes.data, n, C.byref(self.sub))
         if self.cell_sort:
-            delta = np.full(3, self.cutoff)
+            delta = np.array([self.cutoff, self.cutoff, 0.25 * self.cutoff])  # the driver's LinkedCellList gridDelta
             lo, hi = np.zeros(3), self.box
             nc = L.or_cell_ids(a.ctypes.data, 13, 0, n, delta.ctypes.data, lo.ctypes.data, hi.ctypes.data,
                                self._cid.ctypes.data, None)
