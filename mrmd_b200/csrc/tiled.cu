@@ -277,6 +277,18 @@ __global__ void __launch_bounds__(TL_THREADS, 4)
     int mx = 0;
     long long total = 0;
     const double rsqrSafe = rsqr * (1.0 - 1e-9);
+    // accepted slots are collected in a shared-memory row per group and leave with 16-byte stores
+    uint16_t* sRow = reinterpret_cast<uint16_t*>(sx_ + 3 * tp.cap) + group * width;
+    // The z interval of a column that the cutoff sphere reaches is bookkeeping, not the list criterion: it is computed
+    // in single precision on coordinates relative to the home column / tile (float error ~1e-6) and widened by 0.2 % of
+    // r^2 and 1e-3 of a cell, far more than that error and than the ulp by which an atom may sit outside its cell.
+    const float rPrune = static_cast<float>(rsqr) * 1.002f;
+    const double xlo = tp.g.min[0] + double(ci) * tp.g.dx[0], ylo = tp.g.min[1] + double(cj) * tp.g.dx[1];
+    const float fdx = static_cast<float>(tp.g.dx[0]), fdy = static_cast<float>(tp.g.dx[1]);
+    const float frdz = static_cast<float>(tp.g.rdx[2]);
+    const int vBase = k0 - R;  // cell index of virtual cell 0
+    const double zBase = tp.g.min[2] + double(vBase) * tp.g.dx[2];
+    const bool clampZ = !tp.periodic[2];  // atoms beyond a non-periodic face are binned into the boundary cells
     for (int hBase = 0; hBase < td.homeCount; hBase += TL_GROUPS)
     {
         const int h = hBase + group;
@@ -286,40 +298,26 @@ __global__ void __launch_bounds__(TL_THREADS, 4)
         const int safeSlot = active ? selfSlot : 0;
         const double px = active ? sx_[3 * selfSlot] : 0.0, py = active ? sy_[3 * selfSlot] : 0.0, pz = active ? sz_[3 * selfSlot] : 0.0;
         int count = 0;
-        uint16_t* row = enc + size_t(active ? i : 0) * width;
         // A column is scanned only over the z interval that the sphere around the home atom cuts out of it: with
         // (bx, by) the distance to the nearest face of the column, partners have |dz| <= sqrt(r^2 - bx^2 - by^2).
-        // Atoms are in cell order along z, so the interval is one slot range.  The margins (1e-6 relative) cover atoms
-        // that sit an ulp outside the cell they were binned into and the rounding of the image shifts.
-        // The interval is computed in single precision (this is bookkeeping, not the list criterion): positions are
-        // taken relative to the home column / tile so that the float error stays near 1e-6, and every bound is
-        // widened by 1e-3 of a cell or of the radius, far more than that error.
-        const float rPrune = static_cast<float>(rsqr) * 1.002f;
-        const double xlo = tp.g.min[0] + double(ci) * tp.g.dx[0], ylo = tp.g.min[1] + double(cj) * tp.g.dx[1];
-        const float fdx = static_cast<float>(tp.g.dx[0]), fdy = static_cast<float>(tp.g.dx[1]);
+        // Atoms are in cell order along z, so the interval is one slot range.
         const float fx = static_cast<float>(px - xlo), fy = static_cast<float>(py - ylo);
         const float dxl = fmaxf(fx, 0.f), dxh = fmaxf(fdx - fx, 0.f);
         const float dyl = fmaxf(fy, 0.f), dyh = fmaxf(fdy - fy, 0.f);
-        const int vBase = k0 - R;  // cell index of virtual cell 0
-        // z in units of cells, relative to virtual cell 0
-        const float zCells = static_cast<float>((pz - (tp.g.min[2] + double(vBase) * tp.g.dx[2])) * tp.g.rdx[2]);
-        const float frdz = static_cast<float>(tp.g.rdx[2]);
-#pragma unroll 1
+        const float bx2[3] = {dxl * dxl, 0.f, dxh * dxh}, by2[3] = {dyl * dyl, 0.f, dyh * dyh};
+        const float zCells = static_cast<float>((pz - zBase) * tp.g.rdx[2]);  // z in cells, relative to virtual cell 0
+#pragma unroll
         for (int r = 0; r < 9; ++r)
         {
-            const int ox = r / 3 - 1, oy = r % 3 - 1;
-            const float bx = (ox < 0) ? dxl : ((ox > 0) ? dxh : 0.f);
-            const float by = (oy < 0) ? dyl : ((oy > 0) ? dyh : 0.f);
-            const float h2 = rPrune - (bx * bx + by * by);
+            const float h2 = rPrune - (bx2[r / 3] + by2[r % 3]);
             int s0 = 0, s1 = 0;
             if (active && h2 >= 0.f)
             {
-                const float hz = sqrtf(h2) * frdz + 1e-3f;  // in cells
+                const float hz = h2 * rsqrtf(h2 + 1e-30f) * frdz + 1e-3f;  // sqrt(h2) in cells
                 int kA = static_cast<int>(floorf(zCells - hz)) + vBase;
                 int kB = static_cast<int>(floorf(zCells + hz)) + vBase;
-                if (!tp.periodic[2])
+                if (clampZ)
                 {
-                    // atoms beyond a non-periodic face are binned into the boundary cells
                     kA = max(0, min(kA, nz - 1));
                     kB = max(0, min(kB, nz - 1));
                 }
@@ -329,9 +327,9 @@ __global__ void __launch_bounds__(TL_THREADS, 4)
                 s1 = cellSlot[r][max(vB + 1, vA)];
             }
             const int iters = __reduce_max_sync(0xffffffffu, (s1 - s0 + TL_GROUP - 1) / TL_GROUP);
-            for (int it = 0; it < iters; ++it)
+#pragma unroll 1
+            for (int it = 0, s = s0 + gl; it < iters; ++it, s += TL_GROUP)
             {
-                const int s = s0 + it * TL_GROUP + gl;
                 const bool inRange = s < s1;
                 const double* q = sx_ + 3 * (inRange ? s : safeSlot);  // always a valid record: no branch
                 const double qx = q[0], qy = q[1], qz = q[2];
@@ -346,11 +344,20 @@ __global__ void __launch_bounds__(TL_THREADS, 4)
                 if (ok)
                 {
                     const int at = count + __popc(m & ((1u << gl) - 1u));
-                    if (at < width) row[at] = static_cast<uint16_t>(s);
+                    if (at < width) sRow[at] = static_cast<uint16_t>(s);
                 }
                 count += __popc(m);
             }
         }
+        // the group's row goes out as 16-byte segments (entries past count inside the last segment are never read)
+        __syncwarp();
+        {
+            const int segments = (min(count, width) + 7) >> 3;
+            uint4* dst = reinterpret_cast<uint4*>(enc + size_t(active ? i : 0) * width);
+            const uint4* src = reinterpret_cast<const uint4*>(sRow);
+            for (int c = gl; c < segments; c += TL_GROUP) dst[c] = src[c];
+        }
+        __syncwarp();
         if (active && gl == 0)
         {
             counts[i] = count;
@@ -984,7 +991,9 @@ int verletBuildTiled(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, const mrmd_b
         MB_TRY(v->enc.reserve(size_t(width) * std::max<int64_t>(n, 1) * 2));
         v->width = width;
         MB_CUDA(cudaMemsetAsync(v->stats.p, 0, 16, st));
-        const size_t smem = size_t(v->tiledSlots) * TL_SMEM_PER_SLOT_BUILD + 16;
+        MB_REQUIRE(width <= 1024, "verlet_build_periodic: more than 1024 neighbours per atom");
+        // positions + one staged row per group (TL_GROUPS x width x 2 bytes)
+        const size_t smem = size_t(v->tiledSlots) * TL_SMEM_PER_SLOT_BUILD + 16 + size_t(TL_GROUPS) * size_t(width) * 2;
         if (v->half)
             verletBuildTiledKernel<true><<<tiles, TL_THREADS, smem, st>>>(
                 tp, cabanaGrid, a->v.pos, cellLo, v->tileDesc.as<int>(), rsqr,
