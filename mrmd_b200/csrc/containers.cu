@@ -348,6 +348,24 @@ static int transfer(Handle* h, bool isAtoms, int field, void* buf, int64_t first
     }
     return 0;
 }
+
+// dense (n x ncomp) device buffer <-> the internal planes of one field; used by the pipelined host-buffer path of
+// md.cu, which owns its staging buffers and streams
+int atomsFieldToDense(const mrmd_b200_atoms* a, int field, double* devBuf, int64_t n, cudaStream_t st)
+{
+    if (n <= 0) return 0;
+    atomFieldKernel<false><<<gridFor(n, 256), 256, 0, st>>>(a->v, field, devBuf, 0, n, ncompOf(true, field), 1);
+    MB_LAUNCHED();
+    return 0;
+}
+int atomsFieldFromDense(mrmd_b200_atoms* a, int field, const double* devBuf, int64_t n, cudaStream_t st)
+{
+    if (n <= 0) return 0;
+    atomFieldKernel<true><<<gridFor(n, 256), 256, 0, st>>>(a->v, field, const_cast<double*>(devBuf), 0, n,
+                                                          ncompOf(true, field), 1);
+    MB_LAUNCHED();
+    return 0;
+}
 }  // namespace mrmd_b200
 
 using namespace mrmd_b200;

@@ -64,6 +64,9 @@ namespace mrmd_b200
 // squared maximum displacement is left in a->dMaxDisp
 int integratePre(mrmd_b200_atoms* a, double dt, bool langevin, double zeta, double temperature, uint64_t seed,
                  uint64_t step, const mrmd_b200_pred* pred, bool fusedPost, cudaStream_t st);
+// containers.cu: dense (n x ncomp) device buffer <-> one field of the container
+int atomsFieldToDense(const mrmd_b200_atoms* a, int field, double* devBuf, int64_t n, cudaStream_t st);
+int atomsFieldFromDense(mrmd_b200_atoms* a, int field, const double* devBuf, int64_t n, cudaStream_t st);
 // tiled.cu: LennardJones::apply over a tiled (periodic, shared-memory staged) full list
 int ljApplyTiled(mrmd_b200_lj* lj, mrmd_b200_atoms* a, const mrmd_b200_verlet* v, bool accumulate, bool energy,
                  cudaStream_t st);

@@ -27,6 +27,12 @@ struct mrmd_b200_md
     double active0 = 0.0;  // running active-pair count when the current run started
     bool postPending = false;  // the last step's postForceIntegrate is fused into the next preForceIntegrate
     std::vector<cudaEvent_t> events;
+    // host-buffer path (mrmd_b200_md_run_host): copy streams, staging buffers and the events that order them
+    cudaStream_t sIn = nullptr, sOut = nullptr;
+    cudaEvent_t evUpPos = nullptr, evUpVel = nullptr, evPosReady = nullptr, evStepDone = nullptr, evDownPos = nullptr,
+                evDownVel = nullptr;
+    bool recordPosReady = false;  // oneStep records evPosReady once the positions (and the atom order) are final
+    mrmd_b200::DevBuf posIn, velIn, posOut, velOut;
 };
 
 namespace mrmd_b200
@@ -142,6 +148,7 @@ static int oneStep(mrmd_b200_md* md, cudaStream_t st, cudaEvent_t evStart, cudaE
         MB_TRY(mrmd_b200_ghost_update(md->ghost, a, &md->sub, st));  // :170
         if (c.adress) MB_TRY(mrmd_b200_molecules_update(md->mols, a, &c.weight, st));
     }
+    if (md->recordPosReady) MB_CUDA(cudaEventRecord(md->evPosReady, st));
     if (c.fullList == 2 && c.adress)
     {
         // tiled AdResS step: thermodynamic force on the zeroed force, then UpdateMolecules + LJ_IdealGas +
@@ -308,6 +315,11 @@ int mrmd_b200_md_destroy(mrmd_b200_md* md)
     if (md == nullptr) return 0;
     cudaDeviceSynchronize();
     for (auto e : md->events) cudaEventDestroy(e);
+    for (cudaEvent_t e : {md->evUpPos, md->evUpVel, md->evPosReady, md->evStepDone, md->evDownPos, md->evDownVel})
+        if (e != nullptr) cudaEventDestroy(e);
+    if (md->sIn != nullptr) cudaStreamDestroy(md->sIn);
+    if (md->sOut != nullptr) cudaStreamDestroy(md->sOut);
+    for (mrmd_b200::DevBuf* b : {&md->posIn, &md->velIn, &md->posOut, &md->velOut}) b->release();
     mrmd_b200_ghost_destroy(md->ghost);
     mrmd_b200_verlet_destroy(md->list);
     mrmd_b200_lj_destroy(md->lj);
@@ -349,6 +361,10 @@ int mrmd_b200_md_run(mrmd_b200_md* md, int64_t nsteps, int timeForceKernel, mrmd
     return collectStats(md, nsteps, rebuilds0, storedSum, pairs0, nTimed, stats, st);
 }
 
+// Host-buffer path.  Per step: pos and vel come from the host buffers, one step runs, pos, vel and the scalars go
+// back.  PCIe is full duplex and the positions are final before the force kernel starts, so the copies run on two
+// extra streams: the download of the positions overlaps the force kernel, the upload of the next step's positions
+// overlaps the download of the velocities.  Every host buffer is read only after the previous step's write to it.
 int mrmd_b200_md_run_host(mrmd_b200_md* md, int64_t nsteps, double* posHost, double* velHost, double* scalarsHost,
                           mrmd_b200_md_stats* stats, void* stream)
 {
@@ -361,24 +377,57 @@ int mrmd_b200_md_run_host(mrmd_b200_md* md, int64_t nsteps, double* posHost, dou
     MB_TRY(runningPairs(md, &pairs0, st));
     int64_t storedSum = 0;
     const int64_t n = a->numLocal;
-    for (int64_t i = 0; i < nsteps; ++i)
+    const size_t bytes = size_t(n) * 24;
+    if (md->sIn == nullptr)
     {
-        // host -> device: this step's inputs
-        MB_TRY(mrmd_b200_atoms_write(a, MRMD_B200_ATOM_POS, posHost, 0, n, 3, 1, MRMD_B200_MEM_HOST, st));
-        MB_TRY(mrmd_b200_atoms_write(a, MRMD_B200_ATOM_VEL, velHost, 0, n, 3, 1, MRMD_B200_MEM_HOST, st));
-        MB_TRY(oneStep(md, st, nullptr, nullptr, false, true));
+        MB_CUDA(cudaStreamCreateWithFlags(&md->sIn, cudaStreamNonBlocking));
+        MB_CUDA(cudaStreamCreateWithFlags(&md->sOut, cudaStreamNonBlocking));
+        for (cudaEvent_t* e : {&md->evUpPos, &md->evUpVel, &md->evPosReady, &md->evStepDone, &md->evDownPos, &md->evDownVel})
+            MB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    }
+    for (mrmd_b200::DevBuf* b : {&md->posIn, &md->velIn, &md->posOut, &md->velOut}) MB_TRY(b->reserve(std::max<size_t>(bytes, 8)));
+    double* dRes = md->cfg.adress ? md->adress->dResult : md->lj->dResult;
+    md->recordPosReady = true;
+    int rc = 0;
+    auto step = [&](int64_t i) -> int
+    {
+        // host -> device: this step's inputs (the host buffers were last written by the previous step's download)
+        if (i > 0) MB_CUDA(cudaStreamWaitEvent(md->sIn, md->evDownPos, 0));
+        MB_CUDA(cudaMemcpyAsync(md->posIn.p, posHost, bytes, cudaMemcpyHostToDevice, md->sIn));
+        MB_CUDA(cudaEventRecord(md->evUpPos, md->sIn));
+        if (i > 0) MB_CUDA(cudaStreamWaitEvent(md->sIn, md->evDownVel, 0));
+        MB_CUDA(cudaMemcpyAsync(md->velIn.p, velHost, bytes, cudaMemcpyHostToDevice, md->sIn));
+        MB_CUDA(cudaEventRecord(md->evUpVel, md->sIn));
+        MB_CUDA(cudaStreamWaitEvent(st, md->evUpPos, 0));
+        MB_TRY(atomsFieldFromDense(a, MRMD_B200_ATOM_POS, md->posIn.as<double>(), n, st));
+        MB_CUDA(cudaStreamWaitEvent(st, md->evUpVel, 0));
+        MB_TRY(atomsFieldFromDense(a, MRMD_B200_ATOM_VEL, md->velIn.as<double>(), n, st));
+        MB_TRY(oneStep(md, st, nullptr, nullptr, false, true));  // records evPosReady in front of the force kernel
         storedSum += md->storedPairsNow;
-        // device -> host: the step's results
-        MB_TRY(mrmd_b200_atoms_read(a, MRMD_B200_ATOM_POS, posHost, 0, n, 3, 1, MRMD_B200_MEM_HOST, st));
-        MB_TRY(mrmd_b200_atoms_read(a, MRMD_B200_ATOM_VEL, velHost, 0, n, 3, 1, MRMD_B200_MEM_HOST, st));
+        // device -> host: positions while the force kernel runs ...
+        MB_CUDA(cudaStreamWaitEvent(md->sOut, md->evPosReady, 0));
+        MB_TRY(atomsFieldToDense(a, MRMD_B200_ATOM_POS, md->posOut.as<double>(), n, md->sOut));
+        MB_CUDA(cudaMemcpyAsync(posHost, md->posOut.p, bytes, cudaMemcpyDeviceToHost, md->sOut));
+        MB_CUDA(cudaEventRecord(md->evDownPos, md->sOut));
+        // ... velocities and scalars after postForceIntegrate
+        MB_CUDA(cudaEventRecord(md->evStepDone, st));
+        MB_CUDA(cudaStreamWaitEvent(md->sOut, md->evStepDone, 0));
+        MB_TRY(atomsFieldToDense(a, MRMD_B200_ATOM_VEL, md->velOut.as<double>(), n, md->sOut));
+        MB_CUDA(cudaMemcpyAsync(velHost, md->velOut.p, bytes, cudaMemcpyDeviceToHost, md->sOut));
         if (scalarsHost != nullptr)
         {
-            double* dRes = md->cfg.adress ? md->adress->dResult : md->lj->dResult;
-            MB_CUDA(cudaMemcpyAsync(scalarsHost, dRes, 16, cudaMemcpyDeviceToHost, st));
-            MB_CUDA(cudaStreamSynchronize(st));
+            MB_CUDA(cudaMemcpyAsync(scalarsHost, dRes, 16, cudaMemcpyDeviceToHost, md->sOut));
             scalarsHost[2] = md->maxDisplacement;
         }
-    }
+        MB_CUDA(cudaEventRecord(md->evDownVel, md->sOut));
+        return 0;
+    };
+    for (int64_t i = 0; i < nsteps && rc == 0; ++i) rc = step(i);
+    md->recordPosReady = false;
+    const cudaError_t e1 = cudaStreamSynchronize(md->sOut), e2 = cudaStreamSynchronize(md->sIn);
+    if (rc != 0) return rc;
+    MB_CUDA(e1);
+    MB_CUDA(e2);
     return collectStats(md, nsteps, rebuilds0, storedSum, pairs0, 0, stats, st);
 }
 
