@@ -65,6 +65,11 @@ struct TileDesc
     int homeStart, homeCount, selfSlot0, totalSlots;
 };
 
+// Row layout of the tiled list (width is a multiple of 64): the eight lanes that share a row owner take the entries
+// n = lane, lane + 8, ...; entry n sits at (n % 8) * (width / 8) + n / 8, so each lane's entries are contiguous and
+// its first eight are one aligned 16-byte word.
+__host__ __device__ __forceinline__ int tiledRowIndex(int n, int width) { return (n & 7) * (width >> 3) + (n >> 3); }
+
 // image shift of piece p = (column r = p / 3, z part w = p % 3) of the tile at (ci, cj)
 __device__ __forceinline__ void pieceShift(const TileParams& tp, int ci, int cj, int p, int& sx, int& sy, int& sz)
 {
@@ -344,18 +349,24 @@ __global__ void __launch_bounds__(TL_THREADS, 4)
                 if (ok)
                 {
                     const int at = count + __popc(m & ((1u << gl) - 1u));
-                    if (at < width) sRow[at] = static_cast<uint16_t>(s);
+                    if (at < width) sRow[tiledRowIndex(at, width)] = static_cast<uint16_t>(s);
                 }
                 count += __popc(m);
             }
         }
-        // the group's row goes out as 16-byte segments (entries past count inside the last segment are never read)
+        // the group's row goes out as 16-byte words: word c belongs to lane c / (width / 64) and holds its entries
+        // 8 (c % (width / 64)) ...; words without a stored entry are skipped, entries past count are never read
         __syncwarp();
         {
-            const int segments = (min(count, width) + 7) >> 3;
+            const int stored = min(count, width);
+            const int wordsPerLane = width >> 6;
             uint4* dst = reinterpret_cast<uint4*>(enc + size_t(active ? i : 0) * width);
             const uint4* src = reinterpret_cast<const uint4*>(sRow);
-            for (int c = gl; c < segments; c += TL_GROUP) dst[c] = src[c];
+            for (int c = gl; c < (width >> 3); c += TL_GROUP)
+            {
+                const int lane = c / wordsPerLane, first = (c % wordsPerLane) << 3;  // first entry index of that lane in the word
+                if (lane + 8 * first < stored) dst[c] = src[c];
+            }
         }
         __syncwarp();
         if (active && gl == 0)
@@ -389,6 +400,22 @@ __device__ __forceinline__ double fastRcp(double x)
     e = fma(-x, r, 1.0);
     r = fma(r, e, r);
     return r;
+}
+
+// Sums four per-lane values over the eight lanes of a group with four 64-bit shuffles (a plain butterfly per value
+// needs twelve): every step halves the number of values a lane carries.  Afterwards the lanes with (gl & 6) == 0
+// hold the total of v0, (gl & 6) == 2 of v1, (gl & 6) == 4 of v2 and (gl & 6) == 6 of v3.
+__device__ __forceinline__ double groupSum4(double v0, double v1, double v2, double v3, int gl)
+{
+    const bool b4 = (gl & 4) != 0, b2 = (gl & 2) != 0;
+    const double r0 = __shfl_xor_sync(0xffffffffu, b4 ? v0 : v2, 4);
+    const double r1 = __shfl_xor_sync(0xffffffffu, b4 ? v1 : v3, 4);
+    const double u0 = (b4 ? v2 : v0) + r0;
+    const double u1 = (b4 ? v3 : v1) + r1;
+    const double r2 = __shfl_xor_sync(0xffffffffu, b2 ? u0 : u1, 2);
+    double w = (b2 ? u1 : u0) + r2;
+    w += __shfl_xor_sync(0xffffffffu, w, 1);
+    return w;
 }
 
 constexpr int LJT_PREFETCH = 8;  // list steps (of TL_GROUP entries) held in registers: rows up to 64 entries
@@ -461,52 +488,34 @@ __global__ void __launch_bounds__(TL_THREADS)
         const int typeI = SINGLE_TYPE ? 0 : sType[selfSlot];
         double fx = 0.0, fy = 0.0, fz = 0.0;
         const int numNeighbors = active ? min(counts[i], width) : 0;
-        const uint16_t* row = enc + size_t(active ? i : 0) * width;
+        // lane gl owns the entries gl, gl + 8, ... of the row; the row layout keeps them contiguous (tiledRowIndex), so
+        // the first eight arrive with one 16-byte load per lane (128 contiguous bytes per group)
+        const uint16_t* mineRow = enc + size_t(active ? i : 0) * width + gl * (width >> 3);
+        const int mine = (numNeighbors - gl + TL_GROUP - 1) >> 3;  // entries of this lane, <= 0 for none
         const int iters = __reduce_max_sync(0xffffffffu, (numNeighbors + TL_GROUP - 1) / TL_GROUP);
-        // every list entry of the row is requested before the first one is used (one 16-byte segment per group
-        // and step; LJT_PREFETCH steps live in registers)
-        int slots[LJT_PREFETCH];
+        const uint4 head = *reinterpret_cast<const uint4*>(mineRow);
+        const unsigned words[4] = {head.x, head.y, head.z, head.w};
 #pragma unroll
         for (int it = 0; it < LJT_PREFETCH; ++it)
         {
-            const int n = it * TL_GROUP + gl;
-            slots[it] = (n < numNeighbors) ? int(row[n]) : -1;
-        }
-#pragma unroll
-        for (int it = 0; it < LJT_PREFETCH; ++it)
-        {
-            if (it < iters && slots[it] >= 0)
-                ljPair<SINGLE_TYPE, ENERGY>(sx_, sy_, sz_, sType, slots[it], xi, yi, zi, typeI, t0, table, numTypesQuirk,
-                                            rcSqr, fx, fy, fz, energy, virial, pairs);
+            const int slot = (words[it >> 1] >> (16 * (it & 1))) & 0xffffu;
+            if (it < mine)
+                ljPair<SINGLE_TYPE, ENERGY>(sx_, sy_, sz_, sType, slot, xi, yi, zi, typeI, t0, table, numTypesQuirk, rcSqr,
+                                            fx, fy, fz, energy, virial, pairs);
         }
         for (int it = LJT_PREFETCH; it < iters; ++it)
         {
-            const int n = it * TL_GROUP + gl;
-            if (n < numNeighbors)
-                ljPair<SINGLE_TYPE, ENERGY>(sx_, sy_, sz_, sType, row[n], xi, yi, zi, typeI, t0, table, numTypesQuirk,
+            if (it < mine)
+                ljPair<SINGLE_TYPE, ENERGY>(sx_, sy_, sz_, sType, mineRow[it], xi, yi, zi, typeI, t0, table, numTypesQuirk,
                                             rcSqr, fx, fy, fz, energy, virial, pairs);
         }
-#pragma unroll
-        for (int o = TL_GROUP / 2; o > 0; o >>= 1)
+        // lanes 0 / 2 / 4 of the group end up with the x / y / z total and store it
+        const double f = groupSum4(fx, fy, fz, 0.0, gl);
+        if (active && (gl & 1) == 0 && gl < 6)
         {
-            fx += __shfl_xor_sync(0xffffffffu, fx, o);
-            fy += __shfl_xor_sync(0xffffffffu, fy, o);
-            fz += __shfl_xor_sync(0xffffffffu, fz, o);
-        }
-        if (active && gl == 0)
-        {
-            if (ACCUMULATE)
-            {
-                a.force[0][i] += fx;
-                a.force[1][i] += fy;
-                a.force[2][i] += fz;
-            }
-            else
-            {
-                a.force[0][i] = fx;
-                a.force[1][i] = fy;
-                a.force[2][i] = fz;
-            }
+            double* plane = (gl == 0) ? a.force[0] : ((gl == 2) ? a.force[1] : a.force[2]);
+            if (ACCUMULATE) plane[i] += f;
+            else plane[i] = f;
         }
     }
     // every pair is visited from both sides
@@ -638,38 +647,31 @@ __global__ void __launch_bounds__(TL_THREADS, 3)
             const bool hyA = inHY(modA), cgA = inCG(modA);
             double fx = 0.0, fy = 0.0, fz = 0.0, vsum = 0.0;
             const int numNeighbors = active ? min(counts[i], width) : 0;
-            const uint16_t* row = enc + size_t(active ? i : 0) * width;
+            // row layout and per-lane 16-byte head load as in ljForceTiledKernel
+            const uint16_t* mineRow = enc + size_t(active ? i : 0) * width + gl * (width >> 3);
+            const int mine = (numNeighbors - gl + TL_GROUP - 1) >> 3;
             const int iters = __reduce_max_sync(0xffffffffu, (numNeighbors + TL_GROUP - 1) / TL_GROUP);
-            int slots[LJT_PREFETCH];
+            const uint4 head = *reinterpret_cast<const uint4*>(mineRow);
+            const unsigned words[4] = {head.x, head.y, head.z, head.w};
 #pragma unroll
             for (int it = 0; it < LJT_PREFETCH; ++it)
             {
-                const int n = it * TL_GROUP + gl;
-                slots[it] = (n < numNeighbors) ? int(row[n]) : -1;
-            }
-#pragma unroll
-            for (int it = 0; it < LJT_PREFETCH; ++it)
-            {
-                if (it < iters && slots[it] >= 0)
-                    adressPair<SINGLE_TYPE, ENERGY>(rec, sType, slots[it], xi, yi, zi, typeI, modA, cgA, hyA, t0, table, T, rcSqr, fx,
-                                            fy, fz, energy, vsum, pairs, activePairs);
+                const int slot = (words[it >> 1] >> (16 * (it & 1))) & 0xffffu;
+                if (it < mine)
+                    adressPair<SINGLE_TYPE, ENERGY>(rec, sType, slot, xi, yi, zi, typeI, modA, cgA, hyA, t0, table, T, rcSqr, fx,
+                                                    fy, fz, energy, vsum, pairs, activePairs);
             }
             for (int it = LJT_PREFETCH; it < iters; ++it)
             {
-                const int n = it * TL_GROUP + gl;
-                if (n < numNeighbors)
-                    adressPair<SINGLE_TYPE, ENERGY>(rec, sType, row[n], xi, yi, zi, typeI, modA, cgA, hyA, t0, table, T, rcSqr, fx, fy,
-                                            fz, energy, vsum, pairs, activePairs);
+                if (it < mine)
+                    adressPair<SINGLE_TYPE, ENERGY>(rec, sType, mineRow[it], xi, yi, zi, typeI, modA, cgA, hyA, t0, table, T, rcSqr,
+                                                    fx, fy, fz, energy, vsum, pairs, activePairs);
             }
-#pragma unroll
-            for (int o = TL_GROUP / 2; o > 0; o >>= 1)
-            {
-                fx += __shfl_xor_sync(0xffffffffu, fx, o);
-                fy += __shfl_xor_sync(0xffffffffu, fy, o);
-                fz += __shfl_xor_sync(0xffffffffu, fz, o);
-                vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
-            }
-            if (active && gl == 0)
+            // lanes 0 / 2 / 4 of the group end up with the x / y / z total, lane 6 with sum(V_ij), which the three
+            // storing lanes fetch from it
+            double f = groupSum4(fx, fy, fz, vsum, gl);
+            vsum = __shfl_sync(0xffffffffu, f, (threadIdx.x & 31) - gl + 6);
+            if (active && (gl & 1) == 0 && gl < 6)
             {
                 if (hyA)
                 {
@@ -681,21 +683,18 @@ __global__ void __launch_bounds__(TL_THREADS, 3)
                     if (bin != -1)
                     {
                         scale += hist[2 * TL_COMPENSATION_BINS * T + bin * T + typeI];
-                        if (SAMPLING)
+                        if (SAMPLING && gl == 0)
                         {
                             atomicAdd(hist + bin * T + typeI, vsum);
                             atomicAdd(hist + TL_COMPENSATION_BINS * T + bin * T + typeI, 1.0);
                         }
                     }
-                    fx += scale * gx;
-                    fy += scale * gy;
-                    fz += scale * gz;
+                    f += scale * ((gl == 0) ? gx : ((gl == 2) ? gy : gz));
                 }
-                if (fx != 0.0 || fy != 0.0 || fz != 0.0)
+                if (f != 0.0)
                 {
-                    a.force[0][i] += fx;
-                    a.force[1][i] += fy;
-                    a.force[2][i] += fz;
+                    double* plane = (gl == 0) ? a.force[0] : ((gl == 2) ? a.force[1] : a.force[2]);
+                    plane[i] += f;
                 }
             }
         }
@@ -722,7 +721,7 @@ __global__ void __launch_bounds__(TL_THREADS)
             int j = -1, code = -1;
             if (n < cnt)
             {
-                const int slot = enc[size_t(i) * width + n];
+                const int slot = enc[size_t(i) * width + tiledRowIndex(n, width)];
                 int p = 0;
                 while (p + 1 < TL_PIECES && td.pieceSlot[p + 1] <= slot) ++p;
                 j = td.pieceStart[p] + (slot - td.pieceSlot[p]);
@@ -984,7 +983,7 @@ int verletBuildTiled(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, const mrmd_b
     v->tiledCH = CH;
     tp.cap = v->tiledSlots;
     const double rsqr = radius * radius;
-    int64_t width = (std::max<int64_t>(maxNeigh, 1) + 7) & ~int64_t(7);  // rows of 16-byte segments
+    int64_t width = (std::max<int64_t>(maxNeigh, 1) + 63) & ~int64_t(63);  // tiledRowIndex: eight lanes x 16-byte words
     if (v->width > width && v->enc.bytes >= size_t(v->width) * std::max<int64_t>(n, 1) * 2) width = v->width;
     for (int attempt = 0; attempt < 3; ++attempt)
     {
@@ -1006,7 +1005,7 @@ int verletBuildTiled(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, const mrmd_b
         MB_CUDA(cudaMemcpyAsync(v->hStats, v->stats.p, 16, cudaMemcpyDeviceToHost, st));
         MB_CUDA(cudaStreamSynchronize(st));
         if (v->hStats[0] <= width) return 0;
-        width = (int64_t(v->hStats[0]) + 7) & ~int64_t(7);
+        width = (int64_t(v->hStats[0]) + 63) & ~int64_t(63);
     }
     setLastError("verlet_build_periodic: neighbour table overflow after refill");
     return MRMD_B200_ECAPACITY;
