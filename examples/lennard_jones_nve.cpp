@@ -13,6 +13,10 @@
 
 #include "action/LennardJones.hpp"
 #include "action/VelocityVerlet.hpp"
+#include "analysis/KineticEnergy.hpp"
+#include "analysis/MeanSquareDisplacement.hpp"
+#include "analysis/Pressure.hpp"
+#include "analysis/SystemMomentum.hpp"
 #include "communication/GhostLayer.hpp"
 #include "data/Atoms.hpp"
 #include "data/Subdomain.hpp"
@@ -85,6 +89,8 @@ int main(int argc, char* argv[])
     real_t maxAtomDisplacement = std::numeric_limits<real_t>::max();
     idx_t rebuildCounter = 0;
     action::LennardJones lennardJones(config.r_cut, config.sigma, config.epsilon, config.r_cap);
+    analysis::MeanSquareDisplacement meanSquareDisplacement;
+    meanSquareDisplacement.reset(atoms);
 
     for (idx_t step = 0; step < config.nsteps; ++step)
     {
@@ -109,19 +115,21 @@ int main(int argc, char* argv[])
         action::VelocityVerlet::postForceIntegrate(atoms, config.dt);
     }
 
+    // the statistics of the reference's table (examples/02:190-199)
+    const auto E0 = lennardJones.getEnergy();
+    const auto Ek = analysis::getKineticEnergy(atoms);
+    const auto T = (2_r / 3_r) * analysis::getMeanKineticEnergy(atoms);
+    const auto p = analysis::getPressure(atoms, subdomain);
+    const auto systemMomentum = analysis::getSystemMomentum(atoms);
+    const auto msd = meanSquareDisplacement.calc(atoms, subdomain);
+
     data::deep_copy(h_atoms, atoms);
-    real_t ek = 0_r;
-    {
-        auto vel = h_atoms.getVel();
-        auto mass = h_atoms.getMass();
-        for (idx_t i = 0; i < atoms.numLocalAtoms; ++i)
-            ek += 0.5_r * mass(i) * (vel(i, 0) * vel(i, 0) + vel(i, 1) * vel(i, 1) + vel(i, 2) * vel(i, 2));
-    }
     auto pos = h_atoms.getPos();
     std::printf("{\"atoms\": %lld, \"ghosts\": %lld, \"steps\": %lld, \"rebuilds\": %lld, \"pairs\": %zu, "
-                "\"E0\": %.17g, \"Ek\": %.17g, \"x0\": [%.17g, %.17g, %.17g]}\n",
+                "\"E0\": %.17g, \"Ek\": %.17g, \"T\": %.17g, \"p\": %.17g, \"msd\": %.17g, \"momentum\": [%.17g, %.17g, %.17g], "
+                "\"x0\": [%.17g, %.17g, %.17g]}\n",
                 static_cast<long long>(atoms.numLocalAtoms), static_cast<long long>(atoms.numGhostAtoms),
-                static_cast<long long>(config.nsteps), static_cast<long long>(rebuildCounter), verletList.totalPairs(),
-                lennardJones.getEnergy(), ek, pos(0, 0), pos(0, 1), pos(0, 2));
+                static_cast<long long>(config.nsteps), static_cast<long long>(rebuildCounter), verletList.totalPairs(), E0,
+                Ek, T, p, msd, systemMomentum[0], systemMomentum[1], systemMomentum[2], pos(0, 0), pos(0, 1), pos(0, 2));
     return 0;
 }

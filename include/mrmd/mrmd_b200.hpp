@@ -766,6 +766,77 @@ private:
     std::shared_ptr<mrmd_b200_thermo> h_;
 };
 }  // namespace action
+
+// ------------------------------------------------------------------------------------------------------
+namespace analysis
+{
+/// analysis::getKineticEnergy / getMeanKineticEnergy (analysis/KineticEnergy.hpp:26-47)
+inline real_t getKineticEnergy(data::Atoms& atoms)
+{
+    atoms.push();
+    real_t e = 0;
+    detail::check(mrmd_b200_kinetic_energy(atoms.handle(), &e, defaultStream), "getKineticEnergy");
+    return e;
+}
+inline real_t getMeanKineticEnergy(data::Atoms& atoms) { return getKineticEnergy(atoms) / real_c(atoms.numLocalAtoms); }
+/// analysis::getSystemMomentum (analysis/SystemMomentum.cpp:21-50)
+inline Vector3D getSystemMomentum(data::Atoms& atoms)
+{
+    atoms.push();
+    Vector3D p{};
+    detail::check(mrmd_b200_system_momentum(atoms.handle(), p.data(), defaultStream), "getSystemMomentum");
+    return p;
+}
+/// analysis::getPressure (analysis/Pressure.cpp:23-51)
+inline real_t getPressure(data::Atoms& atoms, const data::Subdomain& subdomain)
+{
+    atoms.push();
+    const auto s = subdomain.c();
+    real_t p = 0;
+    detail::check(mrmd_b200_pressure(atoms.handle(), &s, &p, defaultStream), "getPressure");
+    return p;
+}
+/// analysis::MeanSquareDisplacement (analysis/MeanSquareDisplacement.hpp:24-49)
+class MeanSquareDisplacement
+{
+public:
+    MeanSquareDisplacement()
+    {
+        mrmd_b200_msd* h = nullptr;
+        detail::check(mrmd_b200_msd_create(&h), "MeanSquareDisplacement");
+        h_.reset(h, [](mrmd_b200_msd* p) { mrmd_b200_msd_destroy(p); });
+    }
+    void reset(data::Atoms& atoms)
+    {
+        atoms.push();
+        detail::check(mrmd_b200_msd_reset_atoms(h_.get(), atoms.handle(), defaultStream), "MeanSquareDisplacement::reset");
+    }
+    void reset(data::Molecules& molecules)
+    {
+        molecules.push();
+        detail::check(mrmd_b200_msd_reset_molecules(h_.get(), molecules.handle(), defaultStream), "MeanSquareDisplacement::reset");
+    }
+    real_t calc(data::Atoms& atoms, const data::Subdomain& subdomain)
+    {
+        atoms.push();
+        const auto s = subdomain.c();
+        real_t v = 0;
+        detail::check(mrmd_b200_msd_calc_atoms(h_.get(), atoms.handle(), &s, &v, defaultStream), "MeanSquareDisplacement::calc");
+        return v;
+    }
+    real_t calc(data::Molecules& molecules, const data::Subdomain& subdomain)
+    {
+        molecules.push();
+        const auto s = subdomain.c();
+        real_t v = 0;
+        detail::check(mrmd_b200_msd_calc_molecules(h_.get(), molecules.handle(), &s, &v, defaultStream), "MeanSquareDisplacement::calc");
+        return v;
+    }
+
+private:
+    std::shared_ptr<mrmd_b200_msd> h_;
+};
+}  // namespace analysis
 }  // namespace mrmd
 
 /// stand-ins for the two third-party calls every reference driver makes

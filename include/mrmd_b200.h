@@ -332,6 +332,29 @@ int mrmd_b200_thermo_density_ptr(mrmd_b200_thermo* t, double** devicePtr, int64_
 /* getMuLeft / getMuRight (ThermodynamicForce.cpp:98-130) */
 int mrmd_b200_thermo_mu(const mrmd_b200_thermo* t, double* muLeftHost, double* muRightHost, void* stream);
 
+/* ---- analysis:: diagnostics of the drivers' statistics lines (examples/02:190-199) ------------- */
+typedef struct mrmd_b200_msd mrmd_b200_msd; /* analysis::MeanSquareDisplacement (MeanSquareDisplacement.hpp:24-49) */
+/* replaces analysis::getKineticEnergy (analysis/KineticEnergy.hpp:26-39): 0.5 sum m v^2 over the local atoms;
+ * getMeanKineticEnergy (:44-47) is this / numLocalAtoms */
+int mrmd_b200_kinetic_energy(const mrmd_b200_atoms* a, double* kineticEnergy, void* stream);
+/* replaces analysis::getSystemMomentum (analysis/SystemMomentum.cpp:21-50): the sum of the local atoms'
+ * VELOCITIES per component (the reference does not weight by mass) */
+int mrmd_b200_system_momentum(const mrmd_b200_atoms* a, double* momentum3, void* stream);
+/* replaces analysis::getPressure (analysis/Pressure.cpp:23-51): sum over local AND ghost atoms of
+ * m v^2 + F . x, divided by 3 V */
+int mrmd_b200_pressure(const mrmd_b200_atoms* a, const mrmd_b200_subdomain* s, double* pressure, void* stream);
+int mrmd_b200_msd_create(mrmd_b200_msd** out);
+int mrmd_b200_msd_destroy(mrmd_b200_msd* m);
+/* replaces MeanSquareDisplacement::reset (MeanSquareDisplacement.cpp:23-57) */
+int mrmd_b200_msd_reset_atoms(mrmd_b200_msd* m, const mrmd_b200_atoms* a, void* stream);
+int mrmd_b200_msd_reset_molecules(mrmd_b200_msd* m, const mrmd_b200_molecules* mol, void* stream);
+/* replaces MeanSquareDisplacement::calc (:59-113): |dx| folded by one box length when larger than half of it;
+ * items are matched by index, MRMD_B200_EINVAL if their number changed since reset */
+int mrmd_b200_msd_calc_atoms(const mrmd_b200_msd* m, const mrmd_b200_atoms* a, const mrmd_b200_subdomain* s,
+                             double* meanSquareDisplacement, void* stream);
+int mrmd_b200_msd_calc_molecules(const mrmd_b200_msd* m, const mrmd_b200_molecules* mol, const mrmd_b200_subdomain* s,
+                                 double* meanSquareDisplacement, void* stream);
+
 /* ---- step loop of the reference's drivers ----------------------------------------------------
  * The hot loop of examples/02_LennardJones_NVE.cpp:135-216 (rebuild policy :141-171), with the Langevin
  * integrator of examples/01_LennardJones_NVT.cpp:121,142 and the LinkedCellList + permute spatial sort of

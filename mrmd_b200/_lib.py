@@ -132,6 +132,15 @@ SIGNATURES = {
     "mrmd_b200_thermo_write_force": (C.c_int, [vp, vp, vp]),
     "mrmd_b200_thermo_density_ptr": (C.c_int, [vp, pvp, pi64]),
     "mrmd_b200_thermo_mu": (C.c_int, [vp, vp, vp, vp]),
+    "mrmd_b200_kinetic_energy": (C.c_int, [vp, pdbl, vp]),
+    "mrmd_b200_system_momentum": (C.c_int, [vp, vp, vp]),
+    "mrmd_b200_pressure": (C.c_int, [vp, pSub, pdbl, vp]),
+    "mrmd_b200_msd_create": (C.c_int, [pvp]),
+    "mrmd_b200_msd_destroy": (C.c_int, [vp]),
+    "mrmd_b200_msd_reset_atoms": (C.c_int, [vp, vp, vp]),
+    "mrmd_b200_msd_reset_molecules": (C.c_int, [vp, vp, vp]),
+    "mrmd_b200_msd_calc_atoms": (C.c_int, [vp, vp, pSub, pdbl, vp]),
+    "mrmd_b200_msd_calc_molecules": (C.c_int, [vp, vp, pSub, pdbl, vp]),
     "mrmd_b200_md_create": (C.c_int, [pvp, C.POINTER(MdConfig), pSub, vp]),
     "mrmd_b200_md_destroy": (C.c_int, [vp]),
     "mrmd_b200_md_run": (C.c_int, [vp, i64, C.c_int, C.POINTER(MdStats), vp]),

@@ -626,6 +626,61 @@ class ThermodynamicForce:
                 pass
 
 
+class analysis:
+    """namespace mrmd::analysis: the diagnostics of the drivers' statistics lines (examples/02:190-199)"""
+
+    @staticmethod
+    def getKineticEnergy(atoms, stream=None):
+        """analysis/KineticEnergy.hpp:26-39"""
+        e = C.c_double()
+        check(L().mrmd_b200_kinetic_energy(atoms.h, C.byref(e), _stream(stream)))
+        return e.value
+
+    @staticmethod
+    def getMeanKineticEnergy(atoms, stream=None):
+        """analysis/KineticEnergy.hpp:44-47"""
+        return analysis.getKineticEnergy(atoms, stream) / float(atoms.numLocalAtoms)
+
+    @staticmethod
+    def getSystemMomentum(atoms, stream=None):
+        """analysis/SystemMomentum.cpp:21-50 (sums velocities)"""
+        out = np.zeros(3)
+        check(L().mrmd_b200_system_momentum(atoms.h, out.ctypes.data, _stream(stream)))
+        return out
+
+    @staticmethod
+    def getPressure(atoms, subdomain, stream=None):
+        """analysis/Pressure.cpp:23-51"""
+        p = C.c_double()
+        check(L().mrmd_b200_pressure(atoms.h, C.byref(subdomain), C.byref(p), _stream(stream)))
+        return p.value
+
+    class MeanSquareDisplacement:
+        """analysis/MeanSquareDisplacement.hpp:24-49"""
+
+        def __init__(self):
+            self.h = C.c_void_p()
+            check(L().mrmd_b200_msd_create(C.byref(self.h)))
+
+        def reset(self, items, stream=None):
+            fn = L().mrmd_b200_msd_reset_atoms if isinstance(items, Atoms) else L().mrmd_b200_msd_reset_molecules
+            check(fn(self.h, items.h, _stream(stream)))
+
+        def calc(self, items, subdomain, stream=None):
+            fn = L().mrmd_b200_msd_calc_atoms if isinstance(items, Atoms) else L().mrmd_b200_msd_calc_molecules
+            out = C.c_double()
+            check(fn(self.h, items.h, C.byref(subdomain), C.byref(out), _stream(stream)))
+            return out.value
+
+        def __del__(self):
+            h, self.h = getattr(self, "h", None), None
+            if h:
+                try:
+                    L().mrmd_b200_msd_destroy(h)
+                except Exception:
+                    pass
+
+
 class MolecularDynamics:
     """The step loop of examples/02 (rebuild policy), examples/01 (Langevin) and tests/NVT (spatial sort at
     rebuild) as one C++ driver inside the library: mrmd_b200_md_* in include/mrmd_b200.h."""

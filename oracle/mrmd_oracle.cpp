@@ -1103,6 +1103,60 @@ void or_hist_smoothen(const double* in, double* out, double min, double max, int
         }
 }
 
+// analysis/KineticEnergy.hpp:26-39
+double or_kinetic_energy(const or_atom_t* atoms, int64_t numLocal)
+{
+    double velSqr = 0.0;
+    for (int64_t idx = 0; idx < numLocal; ++idx)
+    {
+        const double* v = atoms[idx].vel;
+        velSqr += atoms[idx].mass * (v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    }
+    return 0.5 * velSqr;
+}
+
+// analysis/SystemMomentum.cpp:21-50 (sums velocities, one reduction per component)
+void or_system_momentum(const or_atom_t* atoms, int64_t numLocal, double* out3)
+{
+    for (int dim = 0; dim < 3; ++dim)
+    {
+        double sum = 0.0;
+        for (int64_t idx = 0; idx < numLocal; ++idx) sum += atoms[idx].vel[dim];
+        out3[dim] = sum;
+    }
+}
+
+// analysis/Pressure.cpp:23-51 (local and ghost atoms)
+double or_pressure(const or_atom_t* atoms, int64_t numAll, const or_subdomain_t* s)
+{
+    double pressure = 0.0;
+    for (int64_t idx = 0; idx < numAll; ++idx)
+    {
+        const or_atom_t& a = atoms[idx];
+        pressure += a.mass * (a.vel[0] * a.vel[0] + a.vel[1] * a.vel[1] + a.vel[2] * a.vel[2]);
+        pressure += a.force[0] * a.pos[0] + a.force[1] * a.pos[1] + a.force[2] * a.pos[2];
+    }
+    const double volume = s->diameter[0] * s->diameter[1] * s->diameter[2];
+    return pressure / (3.0 * volume);
+}
+
+// analysis/MeanSquareDisplacement.cpp:59-84; initialPos: numItems x 3 doubles saved by reset (:23-40)
+double or_msd(const or_atom_t* atoms, const double* initialPos, int64_t numItems, const or_subdomain_t* s)
+{
+    double sq = 0.0;
+    for (int64_t idx = 0; idx < numItems; ++idx)
+    {
+        double dx[3];
+        for (int d = 0; d < 3; ++d)
+        {
+            dx[d] = std::abs(initialPos[3 * idx + d] - atoms[idx].pos[d]);
+            if (dx[d] > 0.5 * s->diameter[d]) dx[d] -= s->diameter[d];
+        }
+        sq += dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2];
+    }
+    return sq / double(numItems);
+}
+
 // analysis/AxialDensityProfile.cpp:21-51
 void or_density_profile(const or_atom_t* atoms, int64_t numAtoms, int64_t numTypes, double min, double max,
                         int64_t numBins, int axis, double* hist)

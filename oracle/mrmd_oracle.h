@@ -216,6 +216,10 @@ void or_hist_gradient(const double* in, double* out, double min, double max, int
                       int periodic);
 void or_hist_smoothen(const double* in, double* out, double min, double max, int64_t numBins, int64_t numHist,
                       double sigma, double range, int periodic);
+double or_kinetic_energy(const or_atom_t* atoms, int64_t numLocal);
+void or_system_momentum(const or_atom_t* atoms, int64_t numLocal, double* out3);
+double or_pressure(const or_atom_t* atoms, int64_t numAll, const or_subdomain_t* s);
+double or_msd(const or_atom_t* atoms, const double* initialPos, int64_t numItems, const or_subdomain_t* s);
 void or_density_profile(const or_atom_t* atoms, int64_t numAtoms, int64_t numTypes, double min, double max,
                         int64_t numBins, int axis, double* hist);
 

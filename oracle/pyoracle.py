@@ -129,6 +129,10 @@ def lib():
         "or_hist_make_symmetric": (None, [vp, i64, i64]),
         "or_hist_gradient": (None, [vp, vp, C.c_double, C.c_double, i64, i64, C.c_int]),
         "or_hist_smoothen": (None, [vp, vp, C.c_double, C.c_double, i64, i64, C.c_double, C.c_double, C.c_int]),
+        "or_kinetic_energy": (C.c_double, [vp, i64]),
+        "or_system_momentum": (None, [vp, i64, vp]),
+        "or_pressure": (C.c_double, [vp, i64, vp]),
+        "or_msd": (C.c_double, [vp, vp, i64, vp]),
         "or_density_profile": (None, [vp, i64, i64, C.c_double, C.c_double, i64, C.c_int, vp]),
         "or_thermo_create": (C.POINTER(Thermo), [vp, i64, C.POINTER(Subdomain), C.c_double, vp, C.c_int, C.c_int]),
         "or_thermo_destroy": (None, [C.POINTER(Thermo)]),

@@ -98,6 +98,19 @@ def test_nve_driver_matches_oracle(tmp_path):
     ek = 0.5 * float((v * v).sum())
     assert abs(out["Ek"] - ek) <= 1e-9 * ek
     assert np.allclose(out["x0"], md.atoms["pos"][0], rtol=0, atol=1e-9)
+    # the statistics line through the analysis:: mirror
+    import ctypes as C
+
+    from oracle import pyoracle as orc
+
+    L, n = orc.lib(), md.n
+    assert abs(out["T"] - (2.0 / 3.0) * ek / n) <= 1e-9 * ek / n
+    p = L.or_pressure(md.atoms.ctypes.data, n + md.ng, C.byref(md.sub))
+    assert abs(out["p"] - p) <= 1e-8 * abs(p)
+    init = np.ascontiguousarray(pos)
+    msd = L.or_msd(md.atoms.ctypes.data, init.ctypes.data, n, C.byref(md.sub))
+    assert abs(out["msd"] - msd) <= 1e-7 * msd
+    assert np.allclose(out["momentum"], v.sum(axis=0), rtol=0, atol=1e-9)
 
 
 @pytest.mark.gpu

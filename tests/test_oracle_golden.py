@@ -588,3 +588,30 @@ def test_cell_sort(oracle):
     same = np.diff(cid2) == 0
     assert np.all(np.diff(a["vel"][:, 0])[same] > 0)  # stable within a cell
     assert sorted(a["vel"][:, 0].astype(int)) == list(range(n))
+
+
+def test_analysis_kats(oracle):
+    """analysis:: diagnostics (row (f)1): mrmd/analysis/KineticEnergy.test.cpp:23-53, SystemMomentum.test.cpp:23-42,
+    MeanSquareDisplacement.test.cpp:28-35; pressure has no reference test: hand-computed from Pressure.cpp:23-51"""
+    import ctypes as C
+
+    L = oracle.lib()
+    a = np.zeros(3, dtype=oracle.ATOM)
+    a["vel"] = [(2, 0, 0), (0, -8, 0), (0, 0, 16)]
+    a["mass"] = [1.0, 2.0, 0.5]
+    assert float_eq(L.or_kinetic_energy(a.ctypes.data, 3), (4 + 2 * 64 + 0.5 * 256) * 0.5)
+    b = np.zeros(2, dtype=oracle.ATOM)
+    b["vel"] = [(2, 3, 4), (-4, -8, -16)]
+    mom = np.zeros(3)
+    L.or_system_momentum(b.ctypes.data, 2, mom.ctypes.data)
+    assert all(float_eq(mom[d], w) for d, w in enumerate((-2.0, -5.0, -12.0)))
+    sub = oracle.subdomain([0, 0, 0], [10, 10, 10], 1.0)
+    c = np.zeros(1, dtype=oracle.ATOM)
+    c["pos"] = [(1, 2, 3)]
+    init = np.array([1.0, 2.0, 3.0])
+    assert L.or_msd(c.ctypes.data, init.ctypes.data, 1, C.byref(sub)) == 0.0
+    # one fold: |dx| = 6 > L/2 -> 6 - 10 = -4
+    init = np.array([7.0, 2.0, 3.0])
+    assert float_eq(L.or_msd(c.ctypes.data, init.ctypes.data, 1, C.byref(sub)), 16.0)
+    c["vel"], c["force"], c["mass"] = [(1, 1, 1)], [(1, 0, -1)], 2.0
+    assert float_eq(L.or_pressure(c.ctypes.data, 1, C.byref(sub)), (2 * 3 + (1 - 3)) / 3000.0)
