@@ -724,6 +724,7 @@ public:
         detail::check(mrmd_b200_thermo_create(&h, targetDensity.data(), idx_c(targetDensity.size()), &s, requestedDensityBinWidth,
                                               thermodynamicForceModulation.data(), enforceSymmetry, usePeriodicity), "ThermodynamicForce");
         h_.reset(h, [](mrmd_b200_thermo* p) { mrmd_b200_thermo_destroy(p); });
+        gridMin_ = subdomain.minCorner[0];
     }
     ThermodynamicForce(const real_t targetDensity, const data::Subdomain& subdomain, const real_t& requestedDensityBinWidth,
                        const real_t thermodynamicForceModulation, const bool enforceSymmetry = false, const bool usePeriodicity = false)
@@ -739,6 +740,16 @@ public:
     void applyInterpolated_if(const data::Atoms& atoms, const util::IsInSymmetricSlab& pred) const { atoms.push(); detail::check(mrmd_b200_thermo_apply(h_.get(), atoms.handle(), &pred.desc(), 1, defaultStream), "applyInterpolated_if"); }
     idx_t getNumberOfDensityProfileSamples() const { int64_t s = 0; detail::check(mrmd_b200_thermo_info(h_.get(), nullptr, nullptr, nullptr, &s), "info"); return s; }
     idx_t numBins() const { int64_t n = 0; detail::check(mrmd_b200_thermo_info(h_.get(), &n, nullptr, nullptr, nullptr), "info"); return n; }
+    idx_t numTypes() const { int64_t n = 0; detail::check(mrmd_b200_thermo_info(h_.get(), nullptr, &n, nullptr, nullptr), "info"); return n; }
+    real_t binSize() const { real_t b = 0; detail::check(mrmd_b200_thermo_info(h_.get(), nullptr, nullptr, &b, nullptr), "info"); return b; }
+    /// data::createGrid(getForce()) (data/MultiHistogram.hpp): the bin centres min + (i + 1/2) binSize
+    std::vector<real_t> createGrid() const
+    {
+        std::vector<real_t> grid(static_cast<size_t>(numBins()));
+        const real_t b = binSize();
+        for (size_t i = 0; i < grid.size(); ++i) grid[i] = gridMin_ + (real_c(i) + 0.5_r) * b;
+        return grid;
+    }
     /// numBins x numTypes, row-major
     std::vector<real_t> getForce() const { return read(0); }
     std::vector<real_t> getDensityProfile() const { return read(1); }
@@ -764,6 +775,7 @@ private:
         return {l, r};
     }
     std::shared_ptr<mrmd_b200_thermo> h_;
+    real_t gridMin_ = 0;
 };
 }  // namespace action
 

@@ -41,14 +41,15 @@ def test_reference_header_paths_exist():
         assert os.path.exists(os.path.join(INC, h)), h
 
 
-@pytest.mark.parametrize("name", ["lennard_jones_nve", "adress_ideal_gas"])
+@pytest.mark.parametrize("name", ["lennard_jones_nve", "adress_ideal_gas", "restart_io"])
 def test_example_compiles_and_fails_loudly_without_gpu(name, tmp_path):
     import torch
 
     exe = _compile(name, tmp_path)
     if torch.cuda.is_available():
         pytest.skip("GPU present: covered by the gpu tests")
-    res = subprocess.run([exe, "4", "1"], capture_output=True, text=True, timeout=60)
+    args = ["4", "1"] if name != "restart_io" else [str(tmp_path / "a.gro"), str(tmp_path / "b.gro"), str(tmp_path / "t"), "1"]
+    res = subprocess.run([exe] + args, capture_output=True, text=True, timeout=60)
     assert res.returncode != 0
     assert "no CUDA device" in res.stderr
 
@@ -111,6 +112,53 @@ def test_nve_driver_matches_oracle(tmp_path):
     msd = L.or_msd(md.atoms.ctypes.data, init.ctypes.data, n, C.byref(md.sub))
     assert abs(out["msd"] - msd) <= 1e-7 * msd
     assert np.allclose(out["momentum"], v.sum(axis=0), rtol=0, atol=1e-9)
+
+
+def _write_gro(path, pos, vel, box):
+    """a .gro in the reference's format (mrmd/io/DumpGRO.cpp:26-89 with velocities)"""
+    with open(path, "w") as f:
+        f.write("golden, t=0\n%d\n" % len(pos))
+        for i, (p, v) in enumerate(zip(pos, vel)):
+            f.write("%5d%-5s%5s%5d%8.3f%8.3f%8.3f%8.4f%8.4f%8.4f\n" % (i + 1, "Argon", "Ar", i + 1, *p, *v))
+        f.write("    %g %g %g\n" % tuple(box))
+
+
+def _read_gro(path):
+    lines = open(path).read().splitlines()
+    n = int(lines[1])
+    rows = np.array([[float(ln[20 + 8 * k:28 + 8 * k]) for k in range(6)] for ln in lines[2:2 + n]])
+    return rows[:, :3], rows[:, 3:], np.array([float(x) for x in lines[2 + n].split()])
+
+
+@pytest.mark.gpu
+def test_gro_restart_and_thermo_force_files(tmp_path, golden_dir):
+    """io:: mirror (row (f)3): a reference-format .gro is restored, continued for 20 NVE steps and dumped; the dump equals
+    the oracle's continuation of the same (rounded) file contents to the file's precision; the thermodynamic-force profile
+    survives dumpThermoForce / restoreThermoForce (mrmd/io/GRO.test.cpp, ThermoForce.test.cpp)"""
+    from oracle.md_loop import OracleMD
+
+    g = np.load(f"{golden_dir}/lj_nvt_final.npz")
+    gin, gout, tf = str(tmp_path / "in.gro"), str(tmp_path / "out.gro"), str(tmp_path / "tf.txt")
+    _write_gro(gin, g["pos"], g["vel"], g["box"])
+    pos, vel, box = _read_gro(gin)  # what the file holds after rounding to %8.3f / %8.4f
+    steps = 20
+    exe = _compile("restart_io", tmp_path)
+    res = subprocess.run([exe, gin, gout, tf, str(steps)], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    out = json.loads(res.stdout.strip().splitlines()[-1])
+    assert out["atoms"] == len(pos) and np.allclose(out["box"], box)
+    assert abs(out["sumPos"] - pos.sum()) < 1e-9 * abs(pos.sum()) and abs(out["sumVel"] - vel.sum()) < 1e-9
+    md = OracleMD(pos, vel, box, langevin=False, cell_sort=False)
+    st = md.run(steps)
+    assert abs(out["E0"] - st["energy"]) <= 1e-9 * abs(st["energy"])
+    p2, v2, b2 = _read_gro(gout)
+    assert np.allclose(b2, box)
+    assert np.abs(p2 - md.atoms["pos"][:md.n]).max() <= 0.5e-3 + 1e-9
+    assert np.abs(v2 - md.atoms["vel"][:md.n]).max() <= 0.5e-4 + 1e-9
+    assert out["tfBins"] == out["tfBinsRestored"] == 100
+    assert out["maxForceDiff"] <= 1e-3 and out["maxGridDiff"] <= 1e-5  # default ostream precision: 6 significant digits
+    lines = open(tf).read().splitlines()
+    assert len(lines) == 3 and len(lines[0].split()) == 100
 
 
 @pytest.mark.gpu
