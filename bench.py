@@ -138,6 +138,26 @@ def cpu_loop(pos, vel, box, steps, warmup, threads):
     return md.run(steps), md
 
 
+ADRESS_THERMO = dict(targetDensity=0.512, binWidth=0.25, modulation=2.0, sampleInterval=10, updateInterval=1000,
+                     sigma=2.0, range=2.0)
+
+
+def cpu_loop_adress(pos, vel, box, steps, warmup, threads):
+    """--workload adress on the host cores: the section 3.5 AdResS step through the oracle (checker / baseline only)."""
+    from oracle import pyoracle as orc
+    from oracle.md_loop import OracleAdressMD
+
+    orc.build()
+    orc.lib().or_set_threads(threads)
+    lx = float(box[0])
+    weight = orc.make_weight(orc.WEIGHT_SLAB, [lx / 2, box[1] / 2, box[2] / 2], 0.2 * lx, 0.1 * lx, 1)
+    md = OracleAdressMD(pos, vel, box, weight, dt=PHYS["dt"], rc=PHYS["rc"], skin=PHYS["skin"], sigma=PHYS["sigma"],
+                        epsilon=PHYS["epsilon"], cap=PHYS["cap"], max_neigh=PHYS["max_neigh"], langevin=True,
+                        zeta=PHYS["zeta"], temperature=PHYS["temperature"], seed=PHYS["seed"], thermo=ADRESS_THERMO)
+    md.run(warmup)
+    return md.run(steps), md
+
+
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -155,14 +175,15 @@ def run_reference(args):
 
     threads = host_threads()
     # probe the host rate on a 32^3 system, then size the sample for ~150 s of CPU work
+    loop = cpu_loop_adress if args.workload == "adress" else cpu_loop
     pos, vel, box = lattice_system(32)
-    probe, _ = cpu_loop(pos, vel, box, 6, 2, threads)
+    probe, _ = loop(pos, vel, box, 6, 2, threads)
     rate = 32 ** 3 * probe["steps"] / probe["seconds"]
     budget_atoms = rate * 150.0 / max(args.steps + args.warmup, 1)
     side = int(max(16, min(args.side, np.floor(budget_atoms ** (1.0 / 3.0)))))
     pos, vel, box = lattice_system(side)
     n = len(pos)
-    res, md = cpu_loop(pos, vel, box, args.steps, args.warmup, threads)
+    res, md = loop(pos, vel, box, args.steps, args.warmup, threads)
     value = n * res["steps"] / res["seconds"]
     sample = (f"periodic sc-lattice system of {n} atoms ({side}^3, same rho/T/dt/skin as the {args.side}^3 workload), "
               f"{args.warmup} warm-up + {args.steps} timed steps, {res['rebuilds']} neighbour rebuilds")
@@ -383,17 +404,18 @@ def run_b200(args):
                        "mrmd_b200_md_run_host: pinned host pos+vel -> device, one step, pos+vel+{E,virial,maxDisp} back"}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and not adress:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
         cpos, cvel = atoms.get("pos")[:n], atoms.get("vel")[:n]
         t0 = time.perf_counter()
-        probe, omd = cpu_loop(cpos, cvel, box, 3, 1, threads)
+        probe, omd = (cpu_loop_adress if adress else cpu_loop)(cpos, cvel, box, 3, 1, threads)
         per_step = probe["seconds"] / 3
         more = int(max(3, min(200, (args.cpu_seconds - (time.perf_counter() - t0)) / max(per_step, 1e-6))))
         res = omd.run(more)
         cpu = {"value": n * res["steps"] / res["seconds"], "unit": "atom-steps/s", "cores": threads, "kind": "port",
-               "sample": f"{res['steps']} steps of the same 1M-atom state (downloaded from the GPU after the timed "
-                         f"region), {res['rebuilds']} rebuilds, OpenMP restatement of the reference path",
+               "sample": f"{res['steps']} steps of the same {n}-atom state (downloaded from the GPU after the timed "
+                         f"region), {res['rebuilds']} rebuilds, OpenMP restatement of the reference "
+                         f"{'AdResS ' if adress else ''}path",
                "pair_interactions_per_s": res["pairInteractions"] / res["seconds"]}
 
     if rank == 0:

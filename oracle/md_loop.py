@@ -88,3 +88,103 @@ class OracleMD:
         dt = time.perf_counter() - t0
         return {"seconds": dt, "steps": nsteps, "pairInteractions": self.pairs - p0, "rebuilds": self.rebuilds - r0,
                 "energy": float(self.energy_virial[0])}
+
+
+class OracleAdressMD:
+    """The AdResS step of SURVEY.md section 3.5 (one molecule per atom) driven through the CPU oracle, the loop of
+    mrmd_b200/csrc/md.cu in AdResS mode: UpdateMolecules -> LJ_IdealGas -> ThermodynamicForce ->
+    ContributeMoleculeForceToAtoms -> MultiResGhostLayer, Langevin integrator, spatial sort at every rebuild."""
+
+    def __init__(self, pos, vel, box, weight, dt=0.002, rc=2.5, skin=0.1, sigma=1.0, epsilon=1.0, cap=0.7,
+                 max_neigh=60, langevin=True, zeta=20.0, temperature=1.5, seed=1234, thermo=None, do_shift=True):
+        self.L = orc.lib()
+        self.n = n = len(pos)
+        self.box = np.asarray(box, dtype=np.float64)
+        self.cutoff = rc + skin
+        self.sub = orc.subdomain([0, 0, 0], self.box, self.cutoff)
+        frac = float(np.prod(self.box + 2 * self.cutoff) / np.prod(self.box)) - 1.0
+        cap_atoms = int(n * (1.0 + 1.3 * frac + 0.05)) + 1024
+        self.atoms = np.zeros(cap_atoms, dtype=orc.ATOM)
+        self.atoms["pos"][:n], self.atoms["vel"][:n] = pos, vel
+        self.atoms["mass"][:n] = self.atoms["relMass"][:n] = 1.0
+        self.mols = np.zeros(cap_atoms, dtype=orc.MOLECULE)
+        self.mols["atomsOffset"][:n], self.mols["numAtoms"][:n] = np.arange(n), 1
+        self.corr = np.full(cap_atoms, -1, dtype=np.int64)
+        self.weight = weight
+        one = [np.array([float(v)]) for v in (cap, rc, sigma, epsilon)]
+        self._keep = one
+        self.adress = self.L.or_adress_create(*[x.ctypes.data for x in one], 1, int(do_shift))
+        self.thermo, self.thermo_cfg = None, thermo
+        if thermo is not None:
+            td, tm = np.array([thermo["targetDensity"]]), np.array([thermo["modulation"]])
+            self._keep += [td, tm]
+            self.thermo = self.L.or_thermo_create(td.ctypes.data, 1, C.byref(self.sub), thermo["binWidth"], tm.ctypes.data, 0, 0)
+        self.rc, self.skin, self.dt = rc, skin, dt
+        self.langevin, self.zeta, self.temperature, self.seed, self.max_neigh = langevin, zeta, temperature, seed, max_neigh
+        self.max_disp = np.finfo(np.float64).max
+        self.step = self.ng = self.mg = self.rebuilds = self.pairs = 0
+        self.energy = 0.0
+        self._cid, self._perm = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int64)
+
+    def _rebuild(self):
+        L, a, m, n = self.L, self.atoms, self.mols, self.n
+        L.or_update_molecules(m.ctypes.data, n, a.ctypes.data, C.byref(self.weight))
+        L.or_mr_periodic_map(m.ctypes.data, n, a.ctypes.data, C.byref(self.sub))
+        delta = np.array([self.cutoff, self.cutoff, 0.25 * self.cutoff])
+        lo, hi = np.zeros(3), self.box
+        nc = L.or_cell_ids(a.ctypes.data, 13, 0, n, delta.ctypes.data, lo.ctypes.data, hi.ctypes.data,
+                           self._cid.ctypes.data, None)
+        off = np.zeros(nc + 1, dtype=np.int64)
+        L.or_cell_perm(self._cid.ctypes.data, 0, n, nc, self._perm.ctypes.data, off.ctypes.data)
+        L.or_permute_atoms(a.ctypes.data, 0, n, self._perm.ctypes.data)  # one atom per molecule: offsets stay i -> i
+        L.or_update_molecules(m.ctypes.data, n, a.ctypes.data, C.byref(self.weight))
+        out = np.zeros(2, dtype=np.int64)
+        rc = L.or_mr_ghost_create_xyz(m.ctypes.data, n, len(m), a.ctypes.data, n, len(a), C.byref(self.sub),
+                                      self.corr.ctypes.data, out.ctypes.data)
+        assert rc == 0, "oracle ghost capacity exceeded"
+        self.mg, self.ng = int(out[0]), int(out[1])
+        L.or_update_molecules(m.ctypes.data, n + self.mg, a.ctypes.data, C.byref(self.weight))
+        self.counts, self.neigh = orc.verlet_build(m, 13, n + self.mg, 0, n, self.cutoff, 1.0,
+                                                   np.array(self.sub.minGhostCorner), np.array(self.sub.maxGhostCorner),
+                                                   half=True, width=self.max_neigh)
+        self.rebuilds += 1
+
+    def one_step(self):
+        L, a, m, n = self.L, self.atoms, self.mols, self.n
+        if self.langevin:
+            d = L.or_langevin_pre(a.ctypes.data, n, self.dt, self.zeta, self.temperature, self.seed, self.step, None)
+        else:
+            d = L.or_vv_pre(a.ctypes.data, n, self.dt)
+        self.max_disp += d
+        if self.max_disp >= self.skin * 0.5:
+            self.max_disp = 0.0
+            self._rebuild()
+        else:
+            L.or_ghost_update_pos(a.ctypes.data, n, self.ng, self.corr.ctypes.data, C.byref(self.sub))
+            L.or_update_molecules(m.ctypes.data, n + self.mg, a.ctypes.data, C.byref(self.weight))
+        L.or_zero_force(a.ctypes.data, n + self.ng)
+        m["force"][:n + self.mg] = 0.0
+        nact = C.c_int64()
+        self.energy = L.or_adress_run(self.adress, m.ctypes.data, n, self.counts.ctypes.data, self.neigh.ctypes.data,
+                                      self.neigh.shape[1], a.ctypes.data, C.byref(nact))
+        self.pairs += nact.value
+        if self.thermo is not None:
+            t = self.thermo_cfg
+            if self.step % t["sampleInterval"] == 0:
+                L.or_thermo_sample(self.thermo, a.ctypes.data, n)
+            if self.step > 0 and self.step % t["updateInterval"] == 0 and self.thermo.contents.samples > 0:
+                L.or_thermo_update(self.thermo, t["sigma"], t["range"], None)
+            L.or_thermo_apply(self.thermo, a.ctypes.data, n, None, 0)
+        L.or_contribute_molecule_force(m.ctypes.data, n + self.mg, a.ctypes.data)
+        L.or_ghost_fold_force(a.ctypes.data, n, self.ng, self.corr.ctypes.data)
+        L.or_vv_post(a.ctypes.data, n, self.dt)
+        self.step += 1
+
+    def run(self, nsteps):
+        t0 = time.perf_counter()
+        p0, r0 = self.pairs, self.rebuilds
+        for _ in range(nsteps):
+            self.one_step()
+        dt = time.perf_counter() - t0
+        return {"seconds": dt, "steps": nsteps, "pairInteractions": self.pairs - p0, "rebuilds": self.rebuilds - r0,
+                "energy": float(self.energy)}

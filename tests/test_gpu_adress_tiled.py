@@ -114,6 +114,29 @@ def test_adress_run_periodic_rejects_region_at_boundary(api):
         lj.run_periodic(atoms, vl, w)
 
 
+@pytest.mark.parametrize("mode", [0, 2])
+def test_adress_md_vs_oracle_loop(api, oracle, mode):
+    """the AdResS step loop (Langevin, thermodynamic force sampled / updated / applied) against the oracle's loop of
+    the same operators (oracle/md_loop.py:OracleAdressMD), 30 steps"""
+    from oracle.md_loop import OracleAdressMD
+
+    pos, vel, box = system(14, 5)
+    n = len(pos)
+    sub = api.Subdomain([0, 0, 0], [box] * 3, 2.6)
+    w, ow = weights(api, oracle, "slab", box)
+    th = dict(targetDensity=0.512, binWidth=0.5, modulation=2.0, sampleInterval=2, updateInterval=10, sigma=2.0, range=2.0)
+    atoms = api.Atoms.from_arrays(pos, vel, mass=1.0, relativeMass=1.0)
+    md = api.MolecularDynamics(atoms, sub, langevin=True, zeta=20.0, temperature=1.5, seed=99, cellSort=True,
+                               fullList=mode, adress=True, weight=w, thermo=th)
+    omd = OracleAdressMD(pos, vel, [box] * 3, ow, langevin=True, zeta=20.0, temperature=1.5, seed=99, thermo=th)
+    st, res = md.run(30), omd.run(30)
+    assert st["rebuilds"] == res["rebuilds"] and st["rebuilds"] >= 2
+    assert st["pairInteractions"] == res["pairInteractions"]
+    assert abs(st["energy"] - res["energy"]) <= 1e-8 * abs(res["energy"])
+    assert np.abs(atoms.getPos()[:n] - omd.atoms["pos"][:n]).max() < 1e-9
+    assert np.abs(atoms.getVel()[:n] - omd.atoms["vel"][:n]).max() < 1e-8
+
+
 @pytest.mark.parametrize("thermo", [False, True])
 def test_adress_md_tiled_vs_generic(api, thermo):
     """40 NVE AdResS steps: tiled (fullList=2) against the generic operator sequence (half molecule list over ghost
