@@ -41,6 +41,9 @@ def parse_args():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--replicas", action="store_true", help="N>1: independent periodic replicas instead of x-slabs")
+    p.add_argument("--balance", action="store_true", help="adress workload on N>1 GPUs: cost-balanced slab widths")
+    p.add_argument("--force-cost-ratio", type=float, default=1.67,
+                   help="--balance: force-kernel time / rest of the step, per atom of the AT + HY region")
     p.add_argument("--workload", default="lj", choices=["lj", "adress"],
                    help="lj: configs[1] (the headline line); adress: configs[2]/[4] physics (LJ / ideal-gas AdResS slab "
                         "with thermodynamic force, one molecule per atom; use --side 200 for 8M atoms per GPU)")
@@ -238,16 +241,31 @@ def run_b200(args):
     api.L().mrmd_b200_set_device(local_rank)
     stream = torch.cuda.current_stream().cuda_stream
 
-    pos, vel, box = lattice_system(args.side, seed=PHYS["seed"] + rank, n_side_x=args.side_x)
-    n = len(pos)
-    sub = api.Subdomain([0, 0, 0], box, PHYS["rc"] + PHYS["skin"])
     slab_mode = world > 1 and not args.replicas
+    adress = args.workload == "adress"
+    sites_x = args.side_x or args.side          # lattice planes per GPU along x (equal-width slabs)
+    spacing = 1.25
+    global_lx = world * sites_x * spacing if slab_mode else sites_x * spacing
+    cuts = None
+    my_sites_x, x_offset = sites_x, (rank * sites_x * spacing if slab_mode else 0.0)
+    if slab_mode and adress and args.balance:
+        # cost-balanced slabs: the AT + HY region [0.3 Lx, 0.7 Lx] carries the force kernel, the
+        # coarse-grained rest only streams; boundaries on lattice planes so that every rank builds its own atoms
+        from mrmd_b200 import slabs
+
+        cuts = slabs.balanced_cuts([0.0], [global_lx], world, 0.3 * global_lx, 0.7 * global_lx, args.force_cost_ratio,
+                                   quantum=spacing, min_width=2 * (PHYS["rc"] + PHYS["skin"]))
+        my_sites_x = int(round((cuts[rank + 1] - cuts[rank]) / spacing))
+        x_offset = float(cuts[rank])
+    pos, vel, box = lattice_system(args.side, seed=PHYS["seed"] + rank, n_side_x=my_sites_x)
+    n = len(pos)
+    box = np.array([sites_x * spacing, box[1], box[2]])  # the equal-width slab: world * box[0] is the global length
+    sub = api.Subdomain([0, 0, 0], box, PHYS["rc"] + PHYS["skin"])
     if slab_mode:
-        # weak scaling over x-slabs: one global box of world * side x side x side sites, rank r owns slab r
-        pos = pos + np.array([rank * box[0], 0.0, 0.0])
+        # weak scaling over x-slabs: one global box of world * sites_x x side x side sites, rank r owns slab r
+        pos = pos + np.array([x_offset, 0.0, 0.0])
     atoms = api.Atoms.from_arrays(pos, vel, mass=1.0, relativeMass=1.0)
 
-    adress = args.workload == "adress"
     extra = {}
     if adress:
         # configs[2] / configs[4] physics: Slab(centre of the global box, AT diameter 0.2 Lx, HY width 0.1 Lx, nu = 1),
@@ -267,7 +285,7 @@ def run_b200(args):
                                                uid, dt=PHYS["dt"], rc=PHYS["rc"], skin=PHYS["skin"], sigma=PHYS["sigma"],
                                                epsilon=PHYS["epsilon"], cappingDistance=PHYS["cap"],
                                                maxNeighbors=PHYS["max_neigh"], langevin=True, zeta=PHYS["zeta"],
-                                               temperature=PHYS["temperature"], seed=PHYS["seed"], **extra)
+                                               temperature=PHYS["temperature"], seed=PHYS["seed"], cuts=cuts, **extra)
         return api.MolecularDynamics(a, sub, dt=PHYS["dt"], rc=PHYS["rc"], skin=PHYS["skin"], sigma=PHYS["sigma"],
                                      epsilon=PHYS["epsilon"], cappingDistance=PHYS["cap"],
                                      maxNeighbors=PHYS["max_neigh"], langevin=True, zeta=PHYS["zeta"],
@@ -304,7 +322,8 @@ def run_b200(args):
     clocks = sampler.stop()
     launches = api.launch_count() - launches0
     ms = ev0.elapsed_time(ev1)
-    t = torch.tensor([ms, float(stats["pairInteractions"]), float(launches)], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms, float(stats["pairInteractions"]), float(launches), float(n)], dtype=torch.float64, device="cuda")
+    total_atoms = float(n)
     if world > 1:
         import torch.distributed as dist
 
@@ -314,9 +333,10 @@ def run_b200(args):
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         # the slab driver already reports the pair interactions summed over the ranks
         ms_max, pairs_total = float(tmax[0]), (float(stats["pairInteractions"]) if slab_mode else float(tsum[1]))
+        total_atoms = float(tsum[3])
     else:
         ms_max, pairs_total = ms, float(stats["pairInteractions"])
-    value = world * n * args.steps / (ms_max * 1e-3)
+    value = total_atoms * args.steps / (ms_max * 1e-3)
 
     # roofline of the dominant kernel (LJ force): algorithmic bytes 60 N + 52 P_stored per launch
     peak, peak_src = measured_peak()
@@ -397,8 +417,9 @@ def run_b200(args):
             import torch.distributed as dist
 
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * n * k / float(tt[0]), "unit": "atom-steps/s", "h2d_bytes_per_step": 48 * n,
-               "d2h_bytes_per_step": 48 * n + 24, "steps": k,
+        e2e = {"value": total_atoms * k / float(tt[0]), "unit": "atom-steps/s",
+               "h2d_bytes_per_step": int(48 * total_atoms / world), "d2h_bytes_per_step": int(48 * total_atoms / world) + 24,
+               "steps": k,
                "path": ("per rank: pinned host pos+vel of the resident atoms -> device (mrmd_b200_atoms_write), one "
                         "mrmd_b200_slab_run step, pos+vel back (mrmd_b200_atoms_read)") if slab_mode else
                        "mrmd_b200_md_run_host: pinned host pos+vel -> device, one step, pos+vel+{E,virial,maxDisp} back"}
@@ -429,6 +450,9 @@ def run_b200(args):
             "ghosts_per_gpu": stats["numGhost"], "energy_per_atom": stats["energy"] / (n * (world if slab_mode else 1)),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         }
+        if cuts is not None:
+            line["config"]["slab_cuts"] = [float(c) for c in cuts]
+            line["config"]["parallelism"] += "; cost-balanced slab widths (narrow over AT + HY, wide over CG)"
         emit(line)
     if world > 1:
         import torch.distributed as dist

@@ -420,6 +420,12 @@ int mrmd_b200_nccl_unique_id(void* out128);
 int mrmd_b200_slab_create(mrmd_b200_slab** out, const mrmd_b200_md_config* cfg, const double* globalMin,
                           const double* globalMax, int rank, int nranks, const void* uniqueId128, mrmd_b200_atoms* atoms,
                           void* stream);
+/* same with caller-chosen slab boundaries: cuts[0] = globalMin[0] < cuts[1] < ... < cuts[nranks] = globalMax[0], rank r
+ * owns [cuts[r], cuts[r+1]); every slab at least rc + skin wide.  For cost-balanced slabs (narrow over the AT / HY
+ * region, wide over the coarse-grained region).  cuts == NULL: equal widths. */
+int mrmd_b200_slab_create_cuts(mrmd_b200_slab** out, const mrmd_b200_md_config* cfg, const double* globalMin,
+                               const double* globalMax, const double* cuts, int rank, int nranks,
+                               const void* uniqueId128, mrmd_b200_atoms* atoms, void* stream);
 int mrmd_b200_slab_destroy(mrmd_b200_slab* sl);
 /* nsteps collective steps; stats: energy, virial and pairInteractions are summed over the ranks (a pair across
  * a slab face counts one half on either side), the other fields are per rank */

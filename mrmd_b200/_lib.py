@@ -147,6 +147,7 @@ SIGNATURES = {
     "mrmd_b200_md_run_host": (C.c_int, [vp, i64, vp, vp, vp, C.POINTER(MdStats), vp]),
     "mrmd_b200_nccl_unique_id": (C.c_int, [vp]),
     "mrmd_b200_slab_create": (C.c_int, [pvp, C.POINTER(MdConfig), vp, vp, C.c_int, C.c_int, vp, vp, vp]),
+    "mrmd_b200_slab_create_cuts": (C.c_int, [pvp, C.POINTER(MdConfig), vp, vp, vp, C.c_int, C.c_int, vp, vp, vp]),
     "mrmd_b200_slab_destroy": (C.c_int, [vp]),
     "mrmd_b200_slab_run": (C.c_int, [vp, i64, C.c_int, C.POINTER(MdStats), vp]),
     "mrmd_b200_host_alloc": (C.c_int, [pvp, i64]),

@@ -627,6 +627,13 @@ int mrmd_b200_slab_create(mrmd_b200_slab** out, const mrmd_b200_md_config* cfg, 
                           const double* globalMax, int rank, int nranks, const void* uniqueId128, mrmd_b200_atoms* atoms,
                           void* stream)
 {
+    return mrmd_b200_slab_create_cuts(out, cfg, globalMin, globalMax, nullptr, rank, nranks, uniqueId128, atoms, stream);
+}
+
+int mrmd_b200_slab_create_cuts(mrmd_b200_slab** out, const mrmd_b200_md_config* cfg, const double* globalMin,
+                               const double* globalMax, const double* cuts, int rank, int nranks,
+                               const void* uniqueId128, mrmd_b200_atoms* atoms, void* stream)
+{
     MB_TRY(checkDevice());
     MB_REQUIRE(out && cfg && globalMin && globalMax && uniqueId128 && atoms, "slab_create");
     MB_REQUIRE(nranks >= 2 && rank >= 0 && rank < nranks, "slab_create: needs at least two ranks");
@@ -649,9 +656,18 @@ int mrmd_b200_slab_create(mrmd_b200_slab** out, const mrmd_b200_md_config* cfg, 
     sl->right = (rank + 1) % nranks;
     const double cutoff = cfg->rc + cfg->skin;
     const double lx = globalMax[0] - globalMin[0];
-    const double width = lx / nranks;
-    double mn[3] = {globalMin[0] + rank * width, globalMin[1], globalMin[2]};
-    double mx[3] = {(rank == nranks - 1) ? globalMax[0] : globalMin[0] + (rank + 1) * width, globalMax[1], globalMax[2]};
+    // equal-width slabs, or the caller's cuts (cost-balanced slabs: narrow over the AT / HY region, wide over CG)
+    if (cuts != nullptr)
+    {
+        MB_REQUIRE(cuts[0] == globalMin[0] && cuts[nranks] == globalMax[0], "slab_create: cuts must span the global box");
+        for (int r = 0; r < nranks; ++r) MB_REQUIRE(cuts[r + 1] - cuts[r] >= cutoff, "slab_create: slab narrower than rc + skin");
+    }
+    const double equalWidth = lx / nranks;
+    const double lo = cuts ? cuts[rank] : globalMin[0] + rank * equalWidth;
+    const double hi = cuts ? cuts[rank + 1] : ((rank == nranks - 1) ? globalMax[0] : globalMin[0] + (rank + 1) * equalWidth);
+    const double width = hi - lo;
+    double mn[3] = {lo, globalMin[1], globalMin[2]};
+    double mx[3] = {hi, globalMax[1], globalMax[2]};
     const double th[3] = {cutoff, cutoff, cutoff};
     mrmd_b200_subdomain_init(&sl->sub, mn, mx, th);
     for (int d = 0; d < 3; ++d)

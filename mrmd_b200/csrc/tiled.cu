@@ -27,7 +27,7 @@
 namespace mrmd_b200
 {
 constexpr int TL_THREADS = 256;
-constexpr int TL_GROUP = 8;                       // lanes per home atom
+constexpr int TL_GROUP = 4;                       // lanes per home atom
 constexpr int TL_GROUPS = TL_THREADS / TL_GROUP;  // home atoms in flight per block
 constexpr int TL_PIECES = 27;                     // 9 columns x {low z-wrap, main, high z-wrap}
 constexpr int TL_MAX_CH = 64;                     // home cells per tile along z
@@ -68,7 +68,10 @@ struct TileDesc
 // Row layout of the tiled list (width is a multiple of 64): the eight lanes that share a row owner take the entries
 // n = lane, lane + 8, ...; entry n sits at (n % 8) * (width / 8) + n / 8, so each lane's entries are contiguous and
 // its first eight are one aligned 16-byte word.
-__host__ __device__ __forceinline__ int tiledRowIndex(int n, int width) { return (n & 7) * (width >> 3) + (n >> 3); }
+__host__ __device__ __forceinline__ int tiledRowIndex(int n, int width)
+{
+    return (n % TL_GROUP) * (width / TL_GROUP) + (n / TL_GROUP);
+}
 
 // image shift of piece p = (column r = p / 3, z part w = p % 3) of the tile at (ci, cj)
 __device__ __forceinline__ void pieceShift(const TileParams& tp, int ci, int cj, int p, int& sx, int& sy, int& sz)
@@ -359,13 +362,14 @@ __global__ void __launch_bounds__(TL_THREADS, 4)
         __syncwarp();
         {
             const int stored = min(count, width);
-            const int wordsPerLane = width >> 6;
+            const int wordsPerLane = width / (8 * TL_GROUP);
             uint4* dst = reinterpret_cast<uint4*>(enc + size_t(active ? i : 0) * width);
             const uint4* src = reinterpret_cast<const uint4*>(sRow);
             for (int c = gl; c < (width >> 3); c += TL_GROUP)
             {
-                const int lane = c / wordsPerLane, first = (c % wordsPerLane) << 3;  // first entry index of that lane in the word
-                if (lane + 8 * first < stored) dst[c] = src[c];
+                // word c holds the entries lane + TL_GROUP * (first ... first + 7) of that lane
+                const int lane = c / wordsPerLane, first = (c % wordsPerLane) << 3;
+                if (lane + TL_GROUP * first < stored) dst[c] = src[c];
             }
         }
         __syncwarp();
@@ -407,18 +411,23 @@ __device__ __forceinline__ double fastRcp(double x)
 // hold the total of v0, (gl & 6) == 2 of v1, (gl & 6) == 4 of v2 and (gl & 6) == 6 of v3.
 __device__ __forceinline__ double groupSum4(double v0, double v1, double v2, double v3, int gl)
 {
-    const bool b4 = (gl & 4) != 0, b2 = (gl & 2) != 0;
-    const double r0 = __shfl_xor_sync(0xffffffffu, b4 ? v0 : v2, 4);
-    const double r1 = __shfl_xor_sync(0xffffffffu, b4 ? v1 : v3, 4);
-    const double u0 = (b4 ? v2 : v0) + r0;
-    const double u1 = (b4 ? v3 : v1) + r1;
-    const double r2 = __shfl_xor_sync(0xffffffffu, b2 ? u0 : u1, 2);
-    double w = (b2 ? u1 : u0) + r2;
-    w += __shfl_xor_sync(0xffffffffu, w, 1);
+    static_assert(TL_GROUP == 8 || TL_GROUP == 4, "groupSum4 is written for groups of 8 or 4 lanes");
+    constexpr int HI = TL_GROUP / 2, LO = TL_GROUP / 4;  // the two lane bits that select the value a lane ends up with
+    const bool bh = (gl & HI) != 0, bl = (gl & LO) != 0;
+    const double r0 = __shfl_xor_sync(0xffffffffu, bh ? v0 : v2, HI);
+    const double r1 = __shfl_xor_sync(0xffffffffu, bh ? v1 : v3, HI);
+    const double u0 = (bh ? v2 : v0) + r0;
+    const double u1 = (bh ? v3 : v1) + r1;
+    const double r2 = __shfl_xor_sync(0xffffffffu, bl ? u0 : u1, LO);
+    double w = (bl ? u1 : u0) + r2;
+    if (TL_GROUP == 8) w += __shfl_xor_sync(0xffffffffu, w, 1);
     return w;
 }
+// which of the four values of groupSum4 lane gl holds (-1: a duplicate), and the lane that holds value k
+__device__ __forceinline__ int groupSumValue(int gl) { return (TL_GROUP == 8) ? (((gl & 1) == 0) ? (gl >> 1) : -1) : gl; }
+__device__ __forceinline__ int groupSumLane(int k) { return (TL_GROUP == 8) ? 2 * k : k; }
 
-constexpr int LJT_PREFETCH = 8;  // list steps (of TL_GROUP entries) held in registers: rows up to 64 entries
+constexpr int LJT_PREFETCH = 64 / TL_GROUP;  // list steps (of TL_GROUP entries) held in registers: rows up to 64 entries
 
 // one pair of LennardJones::apply_if's inner loop (LennardJones.hpp:176-196) against a staged partner
 template <bool SINGLE_TYPE, bool ENERGY>
@@ -490,11 +499,19 @@ __global__ void __launch_bounds__(TL_THREADS)
         const int numNeighbors = active ? min(counts[i], width) : 0;
         // lane gl owns the entries gl, gl + 8, ... of the row; the row layout keeps them contiguous (tiledRowIndex), so
         // the first eight arrive with one 16-byte load per lane (128 contiguous bytes per group)
-        const uint16_t* mineRow = enc + size_t(active ? i : 0) * width + gl * (width >> 3);
-        const int mine = (numNeighbors - gl + TL_GROUP - 1) >> 3;  // entries of this lane, <= 0 for none
+        const uint16_t* mineRow = enc + size_t(active ? i : 0) * width + gl * (width / TL_GROUP);
+        const int mine = (numNeighbors - gl + TL_GROUP - 1) / TL_GROUP;  // entries of this lane
         const int iters = __reduce_max_sync(0xffffffffu, (numNeighbors + TL_GROUP - 1) / TL_GROUP);
-        const uint4 head = *reinterpret_cast<const uint4*>(mineRow);
-        const unsigned words[4] = {head.x, head.y, head.z, head.w};
+        unsigned words[LJT_PREFETCH / 2];
+#pragma unroll
+        for (int k = 0; k < LJT_PREFETCH / 8; ++k)
+        {
+            const uint4 head = reinterpret_cast<const uint4*>(mineRow)[k];
+            words[4 * k] = head.x;
+            words[4 * k + 1] = head.y;
+            words[4 * k + 2] = head.z;
+            words[4 * k + 3] = head.w;
+        }
 #pragma unroll
         for (int it = 0; it < LJT_PREFETCH; ++it)
         {
@@ -509,11 +526,12 @@ __global__ void __launch_bounds__(TL_THREADS)
                 ljPair<SINGLE_TYPE, ENERGY>(sx_, sy_, sz_, sType, mineRow[it], xi, yi, zi, typeI, t0, table, numTypesQuirk,
                                             rcSqr, fx, fy, fz, energy, virial, pairs);
         }
-        // lanes 0 / 2 / 4 of the group end up with the x / y / z total and store it
+        // three lanes of the group end up with the x / y / z total and store it
         const double f = groupSum4(fx, fy, fz, 0.0, gl);
-        if (active && (gl & 1) == 0 && gl < 6)
+        const int comp = groupSumValue(gl);
+        if (active && comp >= 0 && comp < 3)
         {
-            double* plane = (gl == 0) ? a.force[0] : ((gl == 2) ? a.force[1] : a.force[2]);
+            double* plane = (comp == 0) ? a.force[0] : ((comp == 1) ? a.force[1] : a.force[2]);
             if (ACCUMULATE) plane[i] += f;
             else plane[i] = f;
         }
@@ -648,11 +666,19 @@ __global__ void __launch_bounds__(TL_THREADS, 3)
             double fx = 0.0, fy = 0.0, fz = 0.0, vsum = 0.0;
             const int numNeighbors = active ? min(counts[i], width) : 0;
             // row layout and per-lane 16-byte head load as in ljForceTiledKernel
-            const uint16_t* mineRow = enc + size_t(active ? i : 0) * width + gl * (width >> 3);
-            const int mine = (numNeighbors - gl + TL_GROUP - 1) >> 3;
+            const uint16_t* mineRow = enc + size_t(active ? i : 0) * width + gl * (width / TL_GROUP);
+            const int mine = (numNeighbors - gl + TL_GROUP - 1) / TL_GROUP;
             const int iters = __reduce_max_sync(0xffffffffu, (numNeighbors + TL_GROUP - 1) / TL_GROUP);
-            const uint4 head = *reinterpret_cast<const uint4*>(mineRow);
-            const unsigned words[4] = {head.x, head.y, head.z, head.w};
+            unsigned words[LJT_PREFETCH / 2];
+#pragma unroll
+            for (int k = 0; k < LJT_PREFETCH / 8; ++k)
+            {
+                const uint4 head = reinterpret_cast<const uint4*>(mineRow)[k];
+                words[4 * k] = head.x;
+                words[4 * k + 1] = head.y;
+                words[4 * k + 2] = head.z;
+                words[4 * k + 3] = head.w;
+            }
 #pragma unroll
             for (int it = 0; it < LJT_PREFETCH; ++it)
             {
@@ -670,8 +696,9 @@ __global__ void __launch_bounds__(TL_THREADS, 3)
             // lanes 0 / 2 / 4 of the group end up with the x / y / z total, lane 6 with sum(V_ij), which the three
             // storing lanes fetch from it
             double f = groupSum4(fx, fy, fz, vsum, gl);
-            vsum = __shfl_sync(0xffffffffu, f, (threadIdx.x & 31) - gl + 6);
-            if (active && (gl & 1) == 0 && gl < 6)
+            vsum = __shfl_sync(0xffffffffu, f, (threadIdx.x & 31) - gl + groupSumLane(3));
+            const int comp = groupSumValue(gl);
+            if (active && comp >= 0 && comp < 3)
             {
                 if (hyA)
                 {
@@ -683,17 +710,17 @@ __global__ void __launch_bounds__(TL_THREADS, 3)
                     if (bin != -1)
                     {
                         scale += hist[2 * TL_COMPENSATION_BINS * T + bin * T + typeI];
-                        if (SAMPLING && gl == 0)
+                        if (SAMPLING && comp == 0)
                         {
                             atomicAdd(hist + bin * T + typeI, vsum);
                             atomicAdd(hist + TL_COMPENSATION_BINS * T + bin * T + typeI, 1.0);
                         }
                     }
-                    f += scale * ((gl == 0) ? gx : ((gl == 2) ? gy : gz));
+                    f += scale * ((comp == 0) ? gx : ((comp == 1) ? gy : gz));
                 }
                 if (f != 0.0)
                 {
-                    double* plane = (gl == 0) ? a.force[0] : ((gl == 2) ? a.force[1] : a.force[2]);
+                    double* plane = (comp == 0) ? a.force[0] : ((comp == 1) ? a.force[1] : a.force[2]);
                     plane[i] += f;
                 }
             }

@@ -9,9 +9,34 @@ from . import _lib
 from ._lib import check
 
 
-def slab_bounds(global_min, global_max, rank, nranks):
-    """[xlo, xhi) of rank `rank`: equal-width slabs, the last one ends exactly at the global maximum
-    (same arithmetic as mrmd_b200_slab_create)."""
+def balanced_cuts(global_min, global_max, nranks, active_lo, active_hi, force_cost_ratio, quantum=None,
+                  min_width=0.0):
+    """Slab boundaries cuts[0..nranks] with equal estimated cost per slab (narrow slabs over the
+    AT / HY region [active_lo, active_hi), wide ones over the coarse-grained rest).  Cost per unit length is 1 outside
+    the active region and 1 + force_cost_ratio inside (force kernel time / everything else, per atom).  Boundaries
+    are rounded to multiples of `quantum` (a lattice plane spacing) and kept at least min_width apart."""
+    gmin, gmax = float(global_min[0]), float(global_max[0])
+    xs = np.array([gmin, min(max(active_lo, gmin), gmax), min(max(active_hi, gmin), gmax), gmax])
+    dens = np.array([1.0, 1.0 + force_cost_ratio, 1.0])
+    cum = np.concatenate([[0.0], np.cumsum(dens * np.diff(xs))])
+    targets = cum[-1] * np.arange(1, nranks) / nranks
+    inner = np.interp(targets, cum, xs)
+    if quantum:
+        inner = gmin + np.round((inner - gmin) / quantum) * quantum
+    cuts = np.concatenate([[gmin], inner, [gmax]])
+    for r in range(1, nranks):  # enforce the minimum width from the left, then from the right
+        cuts[r] = max(cuts[r], cuts[r - 1] + min_width)
+    for r in range(nranks - 1, 0, -1):
+        cuts[r] = min(cuts[r], cuts[r + 1] - min_width)
+    assert np.all(np.diff(cuts) >= min_width - 1e-12), "box too short for that many slabs"
+    return cuts
+
+
+def slab_bounds(global_min, global_max, rank, nranks, cuts=None):
+    """[xlo, xhi) of rank `rank`: the caller's cuts, or equal-width slabs where the last one ends exactly at the
+    global maximum (same arithmetic as mrmd_b200_slab_create)."""
+    if cuts is not None:
+        return float(cuts[rank]), float(cuts[rank + 1])
     gmin, gmax = float(global_min[0]), float(global_max[0])
     width = (gmax - gmin) / nranks
     lo = gmin + rank * width
@@ -31,18 +56,18 @@ def boundary_shifts(global_min, global_max, rank, nranks):
     return (lx if rank == 0 else 0.0), (-lx if rank == nranks - 1 else 0.0)
 
 
-def owner_of(x, global_min, global_max, nranks):
+def owner_of(x, global_min, global_max, nranks, cuts=None):
     """rank that owns coordinate(s) x (x already wrapped into the global box)"""
     owners = np.zeros(np.shape(x), dtype=np.int64)
     for r in range(nranks):
-        lo, hi = slab_bounds(global_min, global_max, r, nranks)
+        lo, hi = slab_bounds(global_min, global_max, r, nranks, cuts)
         owners[(np.asarray(x) >= lo) & (np.asarray(x) < hi)] = r
     return owners
 
 
-def select_slab(pos, global_min, global_max, rank, nranks):
+def select_slab(pos, global_min, global_max, rank, nranks, cuts=None):
     """indices of the atoms of a global configuration that belong to `rank`"""
-    lo, hi = slab_bounds(global_min, global_max, rank, nranks)
+    lo, hi = slab_bounds(global_min, global_max, rank, nranks, cuts)
     return np.nonzero((pos[:, 0] >= lo) & (pos[:, 0] < hi))[0]
 
 
@@ -67,7 +92,7 @@ class SlabMolecularDynamics:
 
     def __init__(self, atoms, global_min, global_max, rank, nranks, unique_id, dt=0.002, rc=2.5, skin=0.1, sigma=1.0,
                  epsilon=1.0, cappingDistance=0.7, maxNeighbors=60, langevin=False, zeta=20.0, temperature=1.5,
-                 seed=1234, adress=False, weight=None, doShift=True, thermo=None):
+                 seed=1234, adress=False, weight=None, doShift=True, thermo=None, cuts=None):
         cfg = _lib.MdConfig()
         cfg.dt, cfg.rc, cfg.skin, cfg.sigma, cfg.epsilon, cfg.cappingDistance = dt, rc, skin, sigma, epsilon, cappingDistance
         cfg.maxNeighbors, cfg.integrator, cfg.cellSort, cfg.fullList = maxNeighbors, int(langevin), 1, 2
@@ -86,8 +111,11 @@ class SlabMolecularDynamics:
         uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
         assert uid.size == 128
         self.h = C.c_void_p()
-        check(_lib.load().mrmd_b200_slab_create(C.byref(self.h), C.byref(cfg), gmin.ctypes.data, gmax.ctypes.data, rank,
-                                               nranks, uid.ctypes.data, atoms.h, None))
+        cut_arr = None if cuts is None else np.ascontiguousarray(cuts, dtype=np.float64)
+        assert cut_arr is None or cut_arr.size == nranks + 1
+        check(_lib.load().mrmd_b200_slab_create_cuts(C.byref(self.h), C.byref(cfg), gmin.ctypes.data, gmax.ctypes.data,
+                                                    None if cut_arr is None else cut_arr.ctypes.data, rank, nranks,
+                                                    uid.ctypes.data, atoms.h, None))
 
     def run(self, nsteps, timeForceKernel=False, stream=None):
         st = _lib.MdStats()

@@ -21,7 +21,8 @@ def main():
 
     api.L().mrmd_b200_set_device(local)
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 40
-    adress = len(sys.argv) > 2 and sys.argv[2] == "adress"
+    adress = len(sys.argv) > 2 and sys.argv[2].startswith("adress")
+    balanced = len(sys.argv) > 2 and sys.argv[2] == "adress-cuts"
     # global system: jittered sc lattice, x-elongated box (world * 12 x 10 x 10 sites)
     nx, ny = 12 * world, 10
     rng = np.random.default_rng(42)
@@ -38,10 +39,17 @@ def main():
         extra = dict(adress=True, weight=api.Slab(gmax / 2, 0.2 * gmax[0], 0.1 * gmax[0], 2), doShift=True,
                      thermo=dict(targetDensity=0.512, binWidth=0.5, modulation=2.0, sampleInterval=2, updateInterval=10,
                                  sigma=2.0, range=2.0))
-    mine = slabs.select_slab(pos, gmin, gmax, rank, world)
+    cuts = None
+    if balanced:
+        # cost-balanced slab widths: narrow over the AT + HY region, wide over the coarse-grained rest
+        cuts = slabs.balanced_cuts(gmin, gmax, world, 0.3 * gmax[0], 0.7 * gmax[0], 2.0, quantum=1.25, min_width=5.2)
+        if world == 2:  # the balanced cut of a symmetric region is the middle: take an uneven one instead
+            cuts = np.array([0.0, round(0.4 * nx) * 1.25, gmax[0]])
+        assert not np.allclose(np.diff(cuts), np.diff(cuts)[0])
+    mine = slabs.select_slab(pos, gmin, gmax, rank, world, cuts)
     atoms = api.Atoms.from_arrays(pos[mine], vel[mine], mass=1.0, relativeMass=1.0)
     uid = slabs.broadcast_unique_id(rank)
-    md = slabs.SlabMolecularDynamics(atoms, gmin, gmax, rank, world, uid, langevin=False, **phys, **extra)
+    md = slabs.SlabMolecularDynamics(atoms, gmin, gmax, rank, world, uid, langevin=False, cuts=cuts, **phys, **extra)
     st = md.run(steps)
     n = st["numLocal"]
     my_pos, my_vel = atoms.getPos()[:n], atoms.getVel()[:n]

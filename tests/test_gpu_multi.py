@@ -18,7 +18,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("mode", ["lj", "adress"])
+@pytest.mark.parametrize("mode", ["lj", "adress", "adress-cuts"])
 def test_two_gpu_slabs_match_single_gpu(mode):
     import torch
 

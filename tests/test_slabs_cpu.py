@@ -56,6 +56,31 @@ def test_slab_host_logic_world2(tmp_path):
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
 
 
+def test_balanced_cuts():
+    """cost-balanced slab boundaries: equal estimated cost, on lattice planes, minimum width respected, a partition"""
+    from mrmd_b200 import slabs
+
+    gmin, gmax = np.array([0.0, 0, 0]), np.array([500.0, 500, 500])
+    ratio = 1.67
+    cuts = slabs.balanced_cuts(gmin, gmax, 8, 150.0, 350.0, ratio, quantum=1.25, min_width=5.2)
+    assert cuts[0] == 0.0 and cuts[-1] == 500.0 and np.all(np.diff(cuts) >= 5.2)
+    assert np.allclose(cuts / 1.25, np.round(cuts / 1.25))
+
+    def cost(a, b):
+        inside = max(0.0, min(b, 350.0) - max(a, 150.0))
+        return (b - a) + ratio * inside
+
+    costs = [cost(cuts[r], cuts[r + 1]) for r in range(8)]
+    assert max(costs) - min(costs) <= 2 * 1.25 * (1 + ratio)  # within the rounding to lattice planes
+    widths = np.diff(cuts)
+    assert widths[0] > widths[3] and widths[7] > widths[4]  # wide over CG, narrow over AT / HY
+    x = np.random.default_rng(1).random(1000) * 500.0
+    owners = slabs.owner_of(x, gmin, gmax, 8, cuts)
+    assert all(cuts[o] <= xi < cuts[o + 1] for xi, o in zip(x, owners))
+    # nothing to balance: equal widths
+    assert np.allclose(slabs.balanced_cuts(gmin, gmax, 4, 0.0, 0.0, ratio), [0, 125, 250, 375, 500])
+
+
 def test_slab_bounds_cover_the_box():
     from mrmd_b200 import slabs
 
