@@ -27,7 +27,7 @@
 namespace mrmd_b200
 {
 constexpr int TL_THREADS = 256;
-constexpr int TL_GROUP = 4;                       // lanes per home atom
+constexpr int TL_GROUP = 2;                       // lanes per home atom
 constexpr int TL_GROUPS = TL_THREADS / TL_GROUP;  // home atoms in flight per block
 constexpr int TL_PIECES = 27;                     // 9 columns x {low z-wrap, main, high z-wrap}
 constexpr int TL_MAX_CH = 64;                     // home cells per tile along z
@@ -406,28 +406,53 @@ __device__ __forceinline__ double fastRcp(double x)
     return r;
 }
 
-// Sums four per-lane values over the eight lanes of a group with four 64-bit shuffles (a plain butterfly per value
-// needs twelve): every step halves the number of values a lane carries.  Afterwards the lanes with (gl & 6) == 0
-// hold the total of v0, (gl & 6) == 2 of v1, (gl & 6) == 4 of v2 and (gl & 6) == 6 of v3.
-__device__ __forceinline__ double groupSum4(double v0, double v1, double v2, double v3, int gl)
+// Sums four per-lane values over the TL_GROUP lanes of a group.  Every step halves the number of values a lane carries
+// instead of running a butterfly per value (8 lanes: four 64-bit shuffles instead of twelve).  Afterwards a lane holds
+// TL_VPL of the four totals: out[k] of lane gl is value groupSumValue(gl, k) (-1: a duplicate another lane stores).
+constexpr int TL_VPL = (TL_GROUP >= 4) ? 1 : 4 / TL_GROUP;
+__device__ __forceinline__ void groupSum4(double v0, double v1, double v2, double v3, int gl, double (&out)[TL_VPL])
 {
-    static_assert(TL_GROUP == 8 || TL_GROUP == 4, "groupSum4 is written for groups of 8 or 4 lanes");
-    constexpr int HI = TL_GROUP / 2, LO = TL_GROUP / 4;  // the two lane bits that select the value a lane ends up with
-    const bool bh = (gl & HI) != 0, bl = (gl & LO) != 0;
-    const double r0 = __shfl_xor_sync(0xffffffffu, bh ? v0 : v2, HI);
-    const double r1 = __shfl_xor_sync(0xffffffffu, bh ? v1 : v3, HI);
-    const double u0 = (bh ? v2 : v0) + r0;
-    const double u1 = (bh ? v3 : v1) + r1;
-    const double r2 = __shfl_xor_sync(0xffffffffu, bl ? u0 : u1, LO);
-    double w = (bl ? u1 : u0) + r2;
-    if (TL_GROUP == 8) w += __shfl_xor_sync(0xffffffffu, w, 1);
-    return w;
+    static_assert(TL_GROUP == 8 || TL_GROUP == 4 || TL_GROUP == 2 || TL_GROUP == 1, "groupSum4: groups of 8, 4, 2 or 1 lanes");
+    if constexpr (TL_GROUP >= 4)
+    {
+        constexpr int HI = TL_GROUP / 2, LO = TL_GROUP / 4;  // the two lane bits that select the value a lane ends up with
+        const bool bh = (gl & HI) != 0, bl = (gl & LO) != 0;
+        const double r0 = __shfl_xor_sync(0xffffffffu, bh ? v0 : v2, HI);
+        const double r1 = __shfl_xor_sync(0xffffffffu, bh ? v1 : v3, HI);
+        const double u0 = (bh ? v2 : v0) + r0;
+        const double u1 = (bh ? v3 : v1) + r1;
+        const double r2 = __shfl_xor_sync(0xffffffffu, bl ? u0 : u1, LO);
+        double w = (bl ? u1 : u0) + r2;
+        if (TL_GROUP == 8) w += __shfl_xor_sync(0xffffffffu, w, 1);
+        out[0] = w;
+    }
+    else if constexpr (TL_GROUP == 1)
+    {
+        out[0] = v0;
+        out[1 % TL_VPL] = v1;
+        out[2 % TL_VPL] = v2;
+        out[3 % TL_VPL] = v3;
+    }
+    else
+    {
+        const bool b = (gl & 1) != 0;  // lane 0 ends up with (v0, v1), lane 1 with (v2, v3)
+        const double r0 = __shfl_xor_sync(0xffffffffu, b ? v0 : v2, 1);
+        const double r1 = __shfl_xor_sync(0xffffffffu, b ? v1 : v3, 1);
+        out[0] = (b ? v2 : v0) + r0;
+        out[TL_VPL - 1] = (b ? v3 : v1) + r1;
+    }
 }
-// which of the four values of groupSum4 lane gl holds (-1: a duplicate), and the lane that holds value k
-__device__ __forceinline__ int groupSumValue(int gl) { return (TL_GROUP == 8) ? (((gl & 1) == 0) ? (gl >> 1) : -1) : gl; }
-__device__ __forceinline__ int groupSumLane(int k) { return (TL_GROUP == 8) ? 2 * k : k; }
+__device__ __forceinline__ int groupSumValue(int gl, int k)
+{
+    if (TL_GROUP == 8) return ((gl & 1) == 0) ? (gl >> 1) : -1;
+    return gl * TL_VPL + k;
+}
+// lane and slot that hold value v
+__device__ __forceinline__ int groupSumLane(int v) { return (TL_GROUP == 8) ? 2 * v : v / TL_VPL; }
+__device__ __forceinline__ int groupSumSlot(int v) { return v % TL_VPL; }
 
-constexpr int LJT_PREFETCH = 64 / TL_GROUP;  // list steps (of TL_GROUP entries) held in registers: rows up to 64 entries
+// list steps (of TL_GROUP entries) whose slots are loaded into registers up front with 16-byte loads
+constexpr int LJT_PREFETCH = (64 / TL_GROUP < 16) ? 64 / TL_GROUP : 16;
 
 // one pair of LennardJones::apply_if's inner loop (LennardJones.hpp:176-196) against a staged partner
 template <bool SINGLE_TYPE, bool ENERGY>
@@ -527,13 +552,18 @@ __global__ void __launch_bounds__(TL_THREADS)
                                             rcSqr, fx, fy, fz, energy, virial, pairs);
         }
         // three lanes of the group end up with the x / y / z total and store it
-        const double f = groupSum4(fx, fy, fz, 0.0, gl);
-        const int comp = groupSumValue(gl);
-        if (active && comp >= 0 && comp < 3)
+        double f[TL_VPL];
+        groupSum4(fx, fy, fz, 0.0, gl, f);
+#pragma unroll
+        for (int k = 0; k < TL_VPL; ++k)
         {
-            double* plane = (comp == 0) ? a.force[0] : ((comp == 1) ? a.force[1] : a.force[2]);
-            if (ACCUMULATE) plane[i] += f;
-            else plane[i] = f;
+            const int comp = groupSumValue(gl, k);
+            if (active && comp >= 0 && comp < 3)
+            {
+                double* plane = (comp == 0) ? a.force[0] : ((comp == 1) ? a.force[1] : a.force[2]);
+                if (ACCUMULATE) plane[i] += f[k];
+                else plane[i] = f[k];
+            }
         }
     }
     // every pair is visited from both sides
@@ -693,35 +723,42 @@ __global__ void __launch_bounds__(TL_THREADS, 3)
                     adressPair<SINGLE_TYPE, ENERGY>(rec, sType, mineRow[it], xi, yi, zi, typeI, modA, cgA, hyA, t0, table, T, rcSqr,
                                                     fx, fy, fz, energy, vsum, pairs, activePairs);
             }
-            // lanes 0 / 2 / 4 of the group end up with the x / y / z total, lane 6 with sum(V_ij), which the three
-            // storing lanes fetch from it
-            double f = groupSum4(fx, fy, fz, vsum, gl);
-            vsum = __shfl_sync(0xffffffffu, f, (threadIdx.x & 31) - gl + groupSumLane(3));
-            const int comp = groupSumValue(gl);
-            if (active && comp >= 0 && comp < 3)
+            // three lanes (slots) of the group end up with the x / y / z total, a fourth with sum(V_ij), which the storing
+            // lanes fetch from it
+            double f[TL_VPL];
+            groupSum4(fx, fy, fz, vsum, gl, f);
+            vsum = __shfl_sync(0xffffffffu, f[groupSumSlot(3)], (threadIdx.x & 31) - gl + groupSumLane(3));
+            // molecule force: drift force -sum(V_ij) grad(lambda) (:163-169) plus the drift compensation
+            // mean[bin] grad(lambda) (:209-222); with one atom of relativeMass 1 per molecule
+            // ContributeMoleculeForceToAtoms adds it to the atom unchanged
+            double scale = 0.0;
+            if (active && hyA)
             {
-                if (hyA)
+                scale = -vsum;
+                const long long bin = histBin(0.0, inverseBinSize, TL_COMPENSATION_BINS, lambda);
+                if (bin != -1)
                 {
-                    // molecule force: drift force -sum(V_ij) grad(lambda) (:163-169) plus the drift compensation
-                    // mean[bin] grad(lambda) (:209-222); with one atom of relativeMass 1 per molecule
-                    // ContributeMoleculeForceToAtoms adds it to the atom unchanged
-                    double scale = -vsum;
-                    const long long bin = histBin(0.0, inverseBinSize, TL_COMPENSATION_BINS, lambda);
-                    if (bin != -1)
+                    scale += hist[2 * TL_COMPENSATION_BINS * T + bin * T + typeI];
+                    if (SAMPLING && gl == 0)
                     {
-                        scale += hist[2 * TL_COMPENSATION_BINS * T + bin * T + typeI];
-                        if (SAMPLING && comp == 0)
-                        {
-                            atomicAdd(hist + bin * T + typeI, vsum);
-                            atomicAdd(hist + TL_COMPENSATION_BINS * T + bin * T + typeI, 1.0);
-                        }
+                        atomicAdd(hist + bin * T + typeI, vsum);
+                        atomicAdd(hist + TL_COMPENSATION_BINS * T + bin * T + typeI, 1.0);
                     }
-                    f += scale * ((comp == 0) ? gx : ((comp == 1) ? gy : gz));
                 }
-                if (f != 0.0)
+            }
+#pragma unroll
+            for (int k = 0; k < TL_VPL; ++k)
+            {
+                const int comp = groupSumValue(gl, k);
+                if (active && comp >= 0 && comp < 3)
                 {
-                    double* plane = (comp == 0) ? a.force[0] : ((comp == 1) ? a.force[1] : a.force[2]);
-                    plane[i] += f;
+                    double out = f[k];
+                    if (hyA) out += scale * ((comp == 0) ? gx : ((comp == 1) ? gy : gz));
+                    if (out != 0.0)
+                    {
+                        double* plane = (comp == 0) ? a.force[0] : ((comp == 1) ? a.force[1] : a.force[2]);
+                        plane[i] += out;
+                    }
                 }
             }
         }
