@@ -457,37 +457,41 @@ constexpr int LJT_PREFETCH = (64 / TL_GROUP < 16) ? 64 / TL_GROUP : 16;
 // one pair of LennardJones::apply_if's inner loop (LennardJones.hpp:176-196) against a staged partner
 template <bool SINGLE_TYPE, bool ENERGY>
 __device__ __forceinline__ void ljPair(const double* sx_, const double* sy_, const double* sz_,
-                                       const unsigned char* sType, int slot, double xi, double yi, double zi, int typeI,
-                                       const LJType& t0, const LJTable& table, int64_t numTypesQuirk, double rcSqr,
-                                       double& fx, double& fy, double& fz, double& energy, double& virial, double& pairs)
+                                       const unsigned char* sType, int slot, bool valid, double xi, double yi, double zi,
+                                       int typeI, const LJType& t0, const LJTable& table, int64_t numTypesQuirk,
+                                       double rcSqr, double& fx, double& fy, double& fz, double& energy, double& virial,
+                                       double& pairs)
 {
-    const double dx = xi - sx_[3 * slot];
-    const double dy = yi - sy_[3 * slot];
-    const double dz = zi - sz_[3 * slot];
+    // predicated, not branched: consecutive list entries are independent, and without a branch around every pair
+    // the compiler interleaves their dependent FP64 chains (an invalid entry reads slot 0 and contributes zero)
+    const int s = valid ? slot : 0;
+    const double dx = xi - sx_[3 * s];
+    const double dy = yi - sy_[3 * s];
+    const double dz = zi - sz_[3 * s];
     const double distSqr = distSqrExact(dx, dy, dz);
-    if (distSqr <= rcSqr)  // LennardJones.hpp:182 skips distSqr > rcSqr
+    const bool in = valid && (distSqr <= rcSqr);  // LennardJones.hpp:182 skips distSqr > rcSqr
+    const LJType& t = SINGLE_TYPE ? t0 : table.t[typeI * numTypesQuirk + sType[s]];
+    const double d2 = in ? distSqr : rcSqr;  // keeps the arithmetic of a skipped pair finite
+    double ff, e;
+    if (d2 >= t.cappingDistanceSqr)  // LennardJones.hpp:56-67
     {
-        const LJType& t = SINGLE_TYPE ? t0 : table.t[typeI * numTypesQuirk + sType[slot]];
-        double ff, e;
-        if (distSqr >= t.cappingDistanceSqr)  // LennardJones.hpp:56-67
-        {
-            const double frac2 = fastRcp(distSqr);
-            const double frac6 = frac2 * frac2 * frac2;
-            ff = frac6 * (t.ff1 * frac6 - t.ff2) * frac2;
-            e = frac6 * (t.ef1 * frac6 - t.ef2) - t.shift;
-        }
-        else
-            ljForceEnergy(t, distSqr, ff, e);
-        if (ENERGY)
-        {
-            energy += e;
-            virial -= 0.5 * ff * distSqr;
-        }
-        pairs += 1.0;
-        fx += dx * ff;
-        fy += dy * ff;
-        fz += dz * ff;
+        const double frac2 = fastRcp(d2);
+        const double frac6 = frac2 * frac2 * frac2;
+        ff = frac6 * (t.ff1 * frac6 - t.ff2) * frac2;
+        e = frac6 * (t.ef1 * frac6 - t.ef2) - t.shift;
     }
+    else
+        ljForceEnergy(t, d2, ff, e);
+    ff = in ? ff : 0.0;
+    if (ENERGY)
+    {
+        energy += in ? e : 0.0;
+        virial -= 0.5 * ff * d2;
+    }
+    pairs += in ? 1.0 : 0.0;
+    fx += dx * ff;
+    fy += dy * ff;
+    fz += dz * ff;
 }
 
 // LennardJones::apply over the tiled list (full list: row owners only).  ACCUMULATE = false stores the force
@@ -541,15 +545,15 @@ __global__ void __launch_bounds__(TL_THREADS)
         for (int it = 0; it < LJT_PREFETCH; ++it)
         {
             const int slot = (words[it >> 1] >> (16 * (it & 1))) & 0xffffu;
-            if (it < mine)
-                ljPair<SINGLE_TYPE, ENERGY>(sx_, sy_, sz_, sType, slot, xi, yi, zi, typeI, t0, table, numTypesQuirk, rcSqr,
-                                            fx, fy, fz, energy, virial, pairs);
+            if (it < iters)  // warp uniform
+                ljPair<SINGLE_TYPE, ENERGY>(sx_, sy_, sz_, sType, slot, it < mine, xi, yi, zi, typeI, t0, table, numTypesQuirk,
+                                            rcSqr, fx, fy, fz, energy, virial, pairs);
         }
         for (int it = LJT_PREFETCH; it < iters; ++it)
         {
             if (it < mine)
-                ljPair<SINGLE_TYPE, ENERGY>(sx_, sy_, sz_, sType, mineRow[it], xi, yi, zi, typeI, t0, table, numTypesQuirk,
-                                            rcSqr, fx, fy, fz, energy, virial, pairs);
+                ljPair<SINGLE_TYPE, ENERGY>(sx_, sy_, sz_, sType, mineRow[it], true, xi, yi, zi, typeI, t0, table,
+                                            numTypesQuirk, rcSqr, fx, fy, fz, energy, virial, pairs);
         }
         // three lanes of the group end up with the x / y / z total and store it
         double f[TL_VPL];
