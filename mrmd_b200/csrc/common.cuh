@@ -227,6 +227,10 @@ struct mrmd_b200_verlet
     mrmd_b200_subdomain tiledSub{};
     int64_t tiledEpoch = -1;
     int tiledR = 1;  // cells along z spanned by the list radius
+    // AdResS step-loop drivers: tiles that lie entirely in the coarse-grained region of this (slab) weighting function
+    // get empty rows (no pair of theirs is ever evaluated); never set through the C ABI list builders
+    bool tiledCgSkip = false;
+    mrmd_b200_weight tiledCgWeight{};
     int tiledCH = 0;
     int tiledSlots = 0;
     mrmd_b200::DevBuf keys[2];  // radix sort ping-pong

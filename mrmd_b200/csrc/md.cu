@@ -281,6 +281,12 @@ int mrmd_b200_md_create(mrmd_b200_md** out, const mrmd_b200_md_config* cfg, cons
     md->atoms = atoms;
     int rc = mrmd_b200_ghost_create(&md->ghost);
     if (rc == 0) rc = mrmd_b200_verlet_create(&md->list, cfg->fullList ? 0 : 1);
+    if (rc == 0 && cfg->adress && cfg->fullList == 2)
+    {
+        // tiles in the coarse-grained region hold ideal-gas pairs only: the tiled build leaves their rows empty
+        md->list->tiledCgSkip = true;
+        md->list->tiledCgWeight = cfg->weight;
+    }
     if (rc == 0 && !cfg->adress)
         rc = mrmd_b200_lj_create(&md->lj, &cfg->cappingDistance, &cfg->rc, &cfg->sigma, &cfg->epsilon, 1, 0);
     if (rc == 0 && cfg->adress)

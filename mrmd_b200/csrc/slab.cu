@@ -692,6 +692,12 @@ int mrmd_b200_slab_create_cuts(mrmd_b200_slab** out, const mrmd_b200_md_config* 
         rc = MRMD_B200_EINVAL;
     }
     if (rc == 0) rc = mrmd_b200_verlet_create(&sl->list, 0);
+    if (rc == 0 && cfg->adress)
+    {
+        // tiles in the coarse-grained region hold ideal-gas pairs only: the tiled build leaves their rows empty
+        sl->list->tiledCgSkip = true;
+        sl->list->tiledCgWeight = cfg->weight;
+    }
     if (rc == 0) rc = mrmd_b200_lj_create(&sl->lj, &cfg->cappingDistance, &cfg->rc, &cfg->sigma, &cfg->epsilon, 1, 0);
     if (rc == 0 && cfg->adress)
     {

@@ -227,6 +227,20 @@ __device__ __forceinline__ bool cabanaCellReachable(const GridDev& cg, double px
     return __dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz)) <= rsqr;
 }
 
+// AdResS with a slab weighting function: true when the three staged columns of the tile (padded by one more cell on
+// each side for the drift until the next sort) lie beyond the hybrid region, i.e. every pair of the tile is an
+// ideal-gas pair (LJ_IdealGas.cpp:102-107).  The force kernel skips such tiles and, in the step-loop drivers, so does
+// the neighbour build (their rows stay empty); both use this one criterion.
+__device__ __forceinline__ bool tileAllCoarseGrained(const TileParams& tp, const mrmd_b200_weight& w, int tile)
+{
+    if (w.kind != MRMD_B200_WEIGHT_SLAB) return false;
+    const int ci = (tile / tp.numChunks) / tp.g.n[1];
+    const double lo = tp.g.min[0] + double(ci - 2) * tp.g.dx[0];
+    const double hi = tp.g.min[0] + double(ci + 3) * tp.g.dx[0];
+    const double reach = 0.5 * w.atRegion + w.hyRegion;
+    return (lo - w.center[0] > reach) || (w.center[0] - hi > reach);
+}
+
 // Neighbour build on tiles: eight lanes scan the candidates of one home atom (the three cells around its
 // own cell in each of the nine columns are one contiguous slot range per column), accepted slots are
 // appended in slot order through a ballot over the group -> deterministic rows, no atomics.
@@ -234,11 +248,20 @@ template <bool HALF>
 __global__ void __launch_bounds__(TL_THREADS, 4)
     verletBuildTiledKernel(TileParams tp, GridDev cabanaGrid, const double4* __restrict__ pos,
                            const int32_t* __restrict__ cellLo, const int* __restrict__ desc, double rsqr, int width,
-                           int32_t* __restrict__ counts, uint16_t* __restrict__ enc, int32_t* stats)
+                           int32_t* __restrict__ counts, uint16_t* __restrict__ enc, int32_t* stats, int cgSkip,
+                           mrmd_b200_weight cgWeight)
 {
     extern __shared__ double sTile[];
     __shared__ TileDesc td;
     __shared__ int cellSlot[9][TL_CELLS];  // slot where virtual cell v (= k0 - 1 + v) of column r starts
+    if (cgSkip && tileAllCoarseGrained(tp, cgWeight, blockIdx.x))
+    {
+        // AdResS step loops: no pair of this tile is ever evaluated, its rows stay empty
+        const int* d = desc + size_t(blockIdx.x) * TL_DESC_INTS;
+        const int homeStart = d[54], homeCount = d[55];
+        for (int h = threadIdx.x; h < homeCount; h += TL_THREADS) counts[homeStart + h] = 0;
+        return;
+    }
     loadTileDesc(desc, td);
     double* sx_ = sTile;
     double* sy_ = sx_ + 1;  // interleaved {x, y, z} records: one address per slot, conflict-free for consecutive slots
@@ -666,15 +689,7 @@ __global__ void __launch_bounds__(TL_THREADS, 3)
     double energy = 0.0, pairs = 0.0, activePairs = 0.0;
     // slab weighting: when the three staged columns (padded by one more cell on each side for the drift since the
     // last sort) lie beyond the hybrid region, every pair of the tile is an ideal-gas pair
-    bool skip = false;
-    if (w.kind == MRMD_B200_WEIGHT_SLAB)
-    {
-        const int ci = (blockIdx.x / tp.numChunks) / tp.g.n[1];
-        const double lo = tp.g.min[0] + double(ci - 2) * tp.g.dx[0];
-        const double hi = tp.g.min[0] + double(ci + 3) * tp.g.dx[0];
-        const double reach = 0.5 * w.atRegion + w.hyRegion;
-        skip = (lo - w.center[0] > reach) || (w.center[0] - hi > reach);
-    }
+    const bool skip = tileAllCoarseGrained(tp, w, blockIdx.x);
     if (!skip)
     {
         loadTileDesc(desc, td);
@@ -1064,11 +1079,13 @@ int verletBuildTiled(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, const mrmd_b
         if (v->half)
             verletBuildTiledKernel<true><<<tiles, TL_THREADS, smem, st>>>(
                 tp, cabanaGrid, a->v.pos, cellLo, v->tileDesc.as<int>(), rsqr,
-                static_cast<int>(width), v->counts.as<int32_t>(), v->enc.as<uint16_t>(), v->stats.as<int32_t>());
+                static_cast<int>(width), v->counts.as<int32_t>(), v->enc.as<uint16_t>(), v->stats.as<int32_t>(),
+                v->tiledCgSkip ? 1 : 0, v->tiledCgWeight);
         else
             verletBuildTiledKernel<false><<<tiles, TL_THREADS, smem, st>>>(
                 tp, cabanaGrid, a->v.pos, cellLo, v->tileDesc.as<int>(), rsqr,
-                static_cast<int>(width), v->counts.as<int32_t>(), v->enc.as<uint16_t>(), v->stats.as<int32_t>());
+                static_cast<int>(width), v->counts.as<int32_t>(), v->enc.as<uint16_t>(), v->stats.as<int32_t>(),
+                v->tiledCgSkip ? 1 : 0, v->tiledCgWeight);
         MB_LAUNCHED();
         MB_CUDA(cudaMemcpyAsync(v->hStats, v->stats.p, 16, cudaMemcpyDeviceToHost, st));
         MB_CUDA(cudaStreamSynchronize(st));
