@@ -42,7 +42,7 @@ def parse_args():
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--replicas", action="store_true", help="N>1: independent periodic replicas instead of x-slabs")
     p.add_argument("--balance", action="store_true", help="adress workload on N>1 GPUs: cost-balanced slab widths")
-    p.add_argument("--force-cost-ratio", type=float, default=1.67,
+    p.add_argument("--force-cost-ratio", type=float, default=4.5,
                    help="--balance: force-kernel time / rest of the step, per atom of the AT + HY region")
     p.add_argument("--workload", default="lj", choices=["lj", "adress"],
                    help="lj: configs[1] (the headline line); adress: configs[2]/[4] physics (LJ / ideal-gas AdResS slab "
