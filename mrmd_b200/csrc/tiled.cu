@@ -6,14 +6,19 @@
 // ~1.3 cycles per lane for the fp64 RED scatter of the half list): the list kernels are LSU-wavefront bound,
 // far from HBM.  Here a block owns a tile = one (x,y) cell column x CH cells along z of the linked-cell grid
 // left behind by LinkedCellList + permute.  Atoms are stored in cell order (z fastest), so the 3x3 neighbour
-// columns are nine contiguous index ranges: they are copied once, coalesced, into shared memory as SoA
-// x[], y[], z[] (periodic images are produced on the fly by adding +-L exactly as GhostExchange /
+// columns are nine contiguous index ranges: they are copied once, coalesced, into shared memory as 24-byte
+// {x, y, z} records (periodic images are produced on the fly by adding +-L exactly as GhostExchange /
 // UpdateGhostAtoms do, so the staged coordinates are bit-identical to the ghost atoms' coordinates) and every
-// neighbour of a home atom becomes a 16-bit shared-memory slot.  Eight lanes share one home atom: they read
-// eight consecutive list entries (one 16-byte segment) and, because rows are kept in slot order, mostly
-// consecutive slots -> conflict-free LDS.64; the three force components are combined with warp shuffles.
+// neighbour of a home atom becomes a 16-bit shared-memory slot.  TL_GROUP lanes share one home atom (measured on
+// B200 for 8 / 4 / 2 / 1 lanes: force kernel 225 / 203 / 200 / 308 us, build 553 / 510 / 462 / 628 us per 1M atoms;
+// fewer lanes amortise the per-home work over more homes per warp until shared-memory conflicts and row-length
+// imbalance take over): each lane owns every TL_GROUP-th list entry, stored contiguously (tiledRowIndex) so that
+// its first entries arrive with 16-byte loads; the force components are combined with warp shuffles.
 // No atomics (full list: an atom accumulates only its own force), no ghost refresh / fold-back in the step,
 // 2 bytes of list traffic per pair.
+// Tried and dropped (measured slower): dealing the staged slots round-robin over all threads instead of one piece
+// per warp; persistent blocks that prefetch the next tile's raw records with cp.async while computing (the extra
+// 32 B/slot of shared memory costs a resident block: 230 vs 194 us); tiles of 80 or 145 instead of 110 home atoms.
 //
 // Pair set: identical to the reference's list over local + ghost atoms (same criterion, same uncontracted
 // distance arithmetic, Cabana's stencil pruning re-checked on accepted pairs): tests decode the slots back to
@@ -65,9 +70,9 @@ struct TileDesc
     int homeStart, homeCount, selfSlot0, totalSlots;
 };
 
-// Row layout of the tiled list (width is a multiple of 64): the eight lanes that share a row owner take the entries
-// n = lane, lane + 8, ...; entry n sits at (n % 8) * (width / 8) + n / 8, so each lane's entries are contiguous and
-// its first eight are one aligned 16-byte word.
+// Row layout of the tiled list (width is a multiple of 64): the TL_GROUP lanes that share a row owner take the entries
+// n = lane, lane + TL_GROUP, ...; entry n sits at (n % TL_GROUP) * (width / TL_GROUP) + n / TL_GROUP, so each lane's
+// entries are contiguous and every eight of them are one aligned 16-byte word.
 __host__ __device__ __forceinline__ int tiledRowIndex(int n, int width)
 {
     return (n % TL_GROUP) * (width / TL_GROUP) + (n / TL_GROUP);
@@ -241,9 +246,9 @@ __device__ __forceinline__ bool tileAllCoarseGrained(const TileParams& tp, const
     return (lo - w.center[0] > reach) || (w.center[0] - hi > reach);
 }
 
-// Neighbour build on tiles: eight lanes scan the candidates of one home atom (the three cells around its
-// own cell in each of the nine columns are one contiguous slot range per column), accepted slots are
-// appended in slot order through a ballot over the group -> deterministic rows, no atomics.
+// Neighbour build on tiles: TL_GROUP lanes scan the candidates of one home atom (in each of the nine columns the z
+// interval the cutoff sphere reaches is one contiguous slot range), accepted slots are appended in scan order
+// through a ballot over the group -> deterministic rows, no atomics.
 template <bool HALF>
 __global__ void __launch_bounds__(TL_THREADS, 4)
     verletBuildTiledKernel(TileParams tp, GridDev cabanaGrid, const double4* __restrict__ pos,
