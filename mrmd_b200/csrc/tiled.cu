@@ -31,9 +31,9 @@
 
 namespace mrmd_b200
 {
-constexpr int TL_THREADS = 256;
+constexpr int TL_THREADS_BUILD = 256;  // neighbour build / decode (measured: 256 -> 461 us, 128 -> 568 us per 1M atoms)
+constexpr int TL_THREADS_FORCE = 128;  // force kernels (measured: 256 -> 194 us, 128 -> 184 us)
 constexpr int TL_GROUP = 2;                       // lanes per home atom
-constexpr int TL_GROUPS = TL_THREADS / TL_GROUP;  // home atoms in flight per block
 constexpr int TL_PIECES = 27;                     // 9 columns x {low z-wrap, main, high z-wrap}
 constexpr int TL_MAX_CH = 64;                     // home cells per tile along z
 constexpr int TL_MAX_R = 4;                       // the list radius spans at most this many cells along z
@@ -181,7 +181,7 @@ __device__ __forceinline__ void stageTile(const TileParams& tp, const TileDesc& 
     const int col = tile / tp.numChunks;
     const int ci = col / tp.g.n[1], cj = col % tp.g.n[1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int p = warp; p < TL_PIECES; p += TL_THREADS / 32)
+    for (int p = warp; p < TL_PIECES; p += blockDim.x / 32)
     {
         const int len = td.pieceLen[p];
         if (len == 0) continue;
@@ -250,7 +250,7 @@ __device__ __forceinline__ bool tileAllCoarseGrained(const TileParams& tp, const
 // interval the cutoff sphere reaches is one contiguous slot range), accepted slots are appended in scan order
 // through a ballot over the group -> deterministic rows, no atomics.
 template <bool HALF>
-__global__ void __launch_bounds__(TL_THREADS, 4)
+__global__ void __launch_bounds__(TL_THREADS_BUILD, 4)
     verletBuildTiledKernel(TileParams tp, GridDev cabanaGrid, const double4* __restrict__ pos,
                            const int32_t* __restrict__ cellLo, const int* __restrict__ desc, double rsqr, int width,
                            int32_t* __restrict__ counts, uint16_t* __restrict__ enc, int32_t* stats, int cgSkip,
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(TL_THREADS, 4)
         // AdResS step loops: no pair of this tile is ever evaluated, its rows stay empty
         const int* d = desc + size_t(blockIdx.x) * TL_DESC_INTS;
         const int homeStart = d[54], homeCount = d[55];
-        for (int h = threadIdx.x; h < homeCount; h += TL_THREADS) counts[homeStart + h] = 0;
+        for (int h = threadIdx.x; h < homeCount; h += blockDim.x) counts[homeStart + h] = 0;
         return;
     }
     loadTileDesc(desc, td);
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(TL_THREADS, 4)
     const int nk = k1 - k0 + 1;
     const int R = tp.R;
     const int nv = nk + 2 * R + 1;  // virtual cells k0-R .. k1+R plus the end sentinel
-    for (int e = threadIdx.x; e < 9 * nv; e += TL_THREADS)
+    for (int e = threadIdx.x; e < 9 * nv; e += blockDim.x)
     {
         const int r = e / nv, v = e % nv;
         const int kv = k0 - R + v;
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(TL_THREADS, 4)
     const int vBase = k0 - R;  // cell index of virtual cell 0
     const double zBase = tp.g.min[2] + double(vBase) * tp.g.dx[2];
     const bool clampZ = !tp.periodic[2];  // atoms beyond a non-periodic face are binned into the boundary cells
-    for (int hBase = 0; hBase < td.homeCount; hBase += TL_GROUPS)
+    for (int hBase = 0; hBase < td.homeCount; hBase += blockDim.x / TL_GROUP)
     {
         const int h = hBase + group;
         const bool active = h < td.homeCount;
@@ -526,7 +526,7 @@ __device__ __forceinline__ void ljPair(const double* sx_, const double* sy_, con
 // (the driver then skips the force reset); true adds like the reference.  ENERGY = false skips the energy /
 // virial accumulation (the driver asks for them on the last step of a run only).
 template <bool SINGLE_TYPE, bool ACCUMULATE, bool ENERGY>
-__global__ void __launch_bounds__(TL_THREADS)
+__global__ void __launch_bounds__(TL_THREADS_FORCE)
     ljForceTiledKernel(TileParams tp, AtomsView a, const int* __restrict__ desc, const int32_t* __restrict__ counts,
                        const uint16_t* __restrict__ enc, int width, LJTable table, double rcSqr, int64_t numTypesQuirk,
                        double* partials, double* result, unsigned int* ticket)
@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(TL_THREADS)
     const int group = threadIdx.x / TL_GROUP, gl = threadIdx.x % TL_GROUP;
     double energy = 0.0, virial = 0.0, pairs = 0.0;
     const LJType t0 = table.t[0];
-    for (int hBase = 0; hBase < td.homeCount; hBase += TL_GROUPS)
+    for (int hBase = 0; hBase < td.homeCount; hBase += blockDim.x / TL_GROUP)
     {
         const int h = hBase + group;
         const bool active = h < td.homeCount;
@@ -599,7 +599,7 @@ __global__ void __launch_bounds__(TL_THREADS)
         }
     }
     // every pair is visited from both sides
-    gridReduce3<TL_THREADS>(0.5 * energy, 0.5 * virial, 0.5 * pairs, partials, result, ticket);
+    gridReduce3<TL_THREADS_FORCE>(0.5 * energy, 0.5 * virial, 0.5 * pairs, partials, result, ticket);
 }
 
 // ---- AdResS on tiles ----------------------------------------------------------------------------------------
@@ -622,7 +622,7 @@ __device__ __forceinline__ void stageTileAdress(const TileParams& tp, const Tile
     const int col = tile / tp.numChunks;
     const int ci = col / tp.g.n[1], cj = col % tp.g.n[1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int p = warp; p < TL_PIECES; p += TL_THREADS / 32)
+    for (int p = warp; p < TL_PIECES; p += blockDim.x / 32)
     {
         const int len = td.pieceLen[p];
         if (len == 0) continue;
@@ -684,7 +684,7 @@ __device__ __forceinline__ void adressPair(const double* rec, const unsigned cha
 }
 
 template <bool SINGLE_TYPE, bool SAMPLING, bool ENERGY>
-__global__ void __launch_bounds__(TL_THREADS, 3)
+__global__ void __launch_bounds__(TL_THREADS_FORCE, 6)
     adressForceTiledKernel(TileParams tp, AtomsView a, const int* __restrict__ desc, const int32_t* __restrict__ counts,
                            const uint16_t* __restrict__ enc, int width, LJTable table, double rcSqr, int64_t numTypes,
                            mrmd_b200_weight w, double* hist, double* partials, double* result, unsigned int* ticket)
@@ -706,7 +706,7 @@ __global__ void __launch_bounds__(TL_THREADS, 3)
         const LJType t0 = table.t[0];
         const int64_t T = numTypes;
         const double inverseBinSize = 1.0 / ((1.0 - 0.0) / double(TL_COMPENSATION_BINS));
-        for (int hBase = 0; hBase < td.homeCount; hBase += TL_GROUPS)
+        for (int hBase = 0; hBase < td.homeCount; hBase += blockDim.x / TL_GROUP)
         {
             const int h = hBase + group;
             const bool active = h < td.homeCount;
@@ -788,11 +788,11 @@ __global__ void __launch_bounds__(TL_THREADS, 3)
         }
     }
     // every pair is visited from both sides
-    gridReduce3<TL_THREADS>(0.5 * energy, 0.5 * pairs, 0.5 * activePairs, partials, result, ticket);
+    gridReduce3<TL_THREADS_FORCE>(0.5 * energy, 0.5 * pairs, 0.5 * activePairs, partials, result, ticket);
 }
 
 // decode the 16-bit slots back to (local partner index, image shift code) in Cabana's row-major layout
-__global__ void __launch_bounds__(TL_THREADS)
+__global__ void __launch_bounds__(TL_THREADS_BUILD)
     decodeTiledKernel(TileParams tp, const int* __restrict__ desc, const int32_t* __restrict__ counts,
                       const uint16_t* __restrict__ enc, int width, int32_t* partner, int32_t* shiftCode)
 {
@@ -800,7 +800,7 @@ __global__ void __launch_bounds__(TL_THREADS)
     loadTileDesc(desc, td);
     const int col = blockIdx.x / tp.numChunks;
     const int ci = col / tp.g.n[1], cj = col % tp.g.n[1];
-    for (int h = threadIdx.x; h < td.homeCount; h += TL_THREADS)
+    for (int h = threadIdx.x; h < td.homeCount; h += blockDim.x)
     {
         const int i = td.homeStart + h;
         const int cnt = min(counts[i], width);
@@ -910,7 +910,7 @@ int ljApplyTiled(mrmd_b200_lj* lj, mrmd_b200_atoms* a, const mrmd_b200_verlet* v
     const size_t smem = size_t(v->tiledSlots) * TL_SMEM_PER_SLOT_FORCE + 16;
     const bool single = (lj->numTypes == 1);
 #define LJT_LAUNCH(S1, ACC, EN)                                                                                       \
-    ljForceTiledKernel<S1, ACC, EN><<<tiles, TL_THREADS, smem, st>>>(                                                 \
+    ljForceTiledKernel<S1, ACC, EN><<<tiles, TL_THREADS_FORCE, smem, st>>>(                                           \
         tp, a->v, v->tileDesc.as<int>(), v->counts.as<int32_t>(), v->enc.as<uint16_t>(), static_cast<int>(v->width), \
         lj->table, lj->rcSqr, lj->numTypesQuirk, lj->partials.as<double>(), lj->dResult, lj->dTicket)
     if (single)
@@ -961,7 +961,7 @@ int adressApplyTiled(mrmd_b200_adress* ad, mrmd_b200_atoms* a, const mrmd_b200_v
     MB_REQUIRE(smem <= size_t(TL_SMEM_MAX), "adress_run_periodic: a tile exceeds shared memory");
     const bool single = (ad->numTypes == 1);
 #define ADT_LAUNCH(S1, SAMP, EN)                                                                                      \
-    adressForceTiledKernel<S1, SAMP, EN><<<tiles, TL_THREADS, smem, st>>>(                                            \
+    adressForceTiledKernel<S1, SAMP, EN><<<tiles, TL_THREADS_FORCE, smem, st>>>(                                      \
         tp, a->v, v->tileDesc.as<int>(), v->counts.as<int32_t>(), v->enc.as<uint16_t>(), static_cast<int>(v->width), \
         ad->table, ad->rcSqr, ad->numTypes, *w, ad->hist, ad->partials.as<double>(), ad->dResult, ad->dTicket)
     if (single)
@@ -1079,15 +1079,16 @@ int verletBuildTiled(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, const mrmd_b
         v->width = width;
         MB_CUDA(cudaMemsetAsync(v->stats.p, 0, 16, st));
         MB_REQUIRE(width <= 1024, "verlet_build_periodic: more than 1024 neighbours per atom");
-        // positions + one staged row per group (TL_GROUPS x width x 2 bytes)
-        const size_t smem = size_t(v->tiledSlots) * TL_SMEM_PER_SLOT_BUILD + 16 + size_t(TL_GROUPS) * size_t(width) * 2;
+        // positions + one staged row per group of TL_GROUP lanes (width x 2 bytes each)
+        const size_t smem = size_t(v->tiledSlots) * TL_SMEM_PER_SLOT_BUILD + 16 +
+                            size_t(TL_THREADS_BUILD / TL_GROUP) * size_t(width) * 2;
         if (v->half)
-            verletBuildTiledKernel<true><<<tiles, TL_THREADS, smem, st>>>(
+            verletBuildTiledKernel<true><<<tiles, TL_THREADS_BUILD, smem, st>>>(
                 tp, cabanaGrid, a->v.pos, cellLo, v->tileDesc.as<int>(), rsqr,
                 static_cast<int>(width), v->counts.as<int32_t>(), v->enc.as<uint16_t>(), v->stats.as<int32_t>(),
                 v->tiledCgSkip ? 1 : 0, v->tiledCgWeight);
         else
-            verletBuildTiledKernel<false><<<tiles, TL_THREADS, smem, st>>>(
+            verletBuildTiledKernel<false><<<tiles, TL_THREADS_BUILD, smem, st>>>(
                 tp, cabanaGrid, a->v.pos, cellLo, v->tileDesc.as<int>(), rsqr,
                 static_cast<int>(width), v->counts.as<int32_t>(), v->enc.as<uint16_t>(), v->stats.as<int32_t>(),
                 v->tiledCgSkip ? 1 : 0, v->tiledCgWeight);
@@ -1127,7 +1128,7 @@ int mrmd_b200_verlet_read_periodic(const mrmd_b200_verlet* v, const mrmd_b200_at
     const int tiles = tp.g.n[0] * tp.g.n[1] * tp.numChunks;
     int32_t* d = nullptr;
     MB_CUDA(cudaMalloc(&d, size_t(n) * v->width * 8));
-    decodeTiledKernel<<<tiles, TL_THREADS, 0, st>>>(tp, v->tileDesc.as<int>(), v->counts.as<int32_t>(),
+    decodeTiledKernel<<<tiles, TL_THREADS_BUILD, 0, st>>>(tp, v->tileDesc.as<int>(), v->counts.as<int32_t>(),
                                                     v->enc.as<uint16_t>(), static_cast<int>(v->width), d,
                                                     d + n * v->width);
     g_launchCount.fetch_add(1);
