@@ -19,6 +19,8 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <cstdlib>
+#include <ctime>
 #include <cfloat>
 #include <vector>
 
@@ -286,6 +288,70 @@ __global__ void packPositionsKernel(const double4* pos, const int32_t* idx, int6
     st4(buf + k, p);
 }
 
+// ---- per-step position halo over peer memory ------------------------------------------------------------------
+// Every rank owns one IPC-shared buffer {flags, region for the left neighbour's atoms, region for the right
+// neighbour's}.  haloPushKernel packs this rank's face atoms (image shift applied) with plain stores straight into the
+// two neighbours' buffers over NVLink and then publishes a sequence number next to them; haloPullKernel on the
+// receiving rank waits for both numbers and copies the records behind its local atoms.  No NCCL call, no staging
+// buffer, no host involvement in the per-step exchange.  A region is only rewritten after the rank-wide allreduce of
+// the next step, which the reader's stream reaches only after its pull (and force kernel) have finished.
+constexpr int SL_P2P_HEADER = 2;  // double4 slots in front of the regions: flags {fromLeft, fromRight, -, -} + padding
+
+__global__ void __launch_bounds__(SL_THREADS)
+    haloPushKernel(const double4* __restrict__ pos, const int32_t* __restrict__ idxLow, int64_t nl, double shiftL,
+                   double4* dstL, unsigned long long* flagL, const int32_t* __restrict__ idxHigh, int64_t nh, double shiftR,
+                   double4* dstR, unsigned long long* flagR, unsigned long long seq, unsigned int* ticket)
+{
+    const int64_t k = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (k < nl)
+    {
+        double4 p = ld4(pos + idxLow[k]);
+        p.x += shiftL;
+        st4(dstL + k, p);
+    }
+    else if (k < nl + nh)
+    {
+        double4 p = ld4(pos + idxHigh[k - nl]);
+        p.x += shiftR;
+        st4(dstR + (k - nl), p);
+    }
+    // the last block to finish publishes: every block's records are visible system wide before the flags are
+    __threadfence_system();
+    __shared__ bool sLast;
+    __syncthreads();
+    if (threadIdx.x == 0) sLast = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (sLast && threadIdx.x == 0)
+    {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long*>(flagL) = seq;
+        *reinterpret_cast<volatile unsigned long long*>(flagR) = seq;
+        *ticket = 0;
+    }
+}
+
+__global__ void __launch_bounds__(SL_THREADS)
+    haloPullKernel(const double4* fromLeft, int64_t nLeft, const double4* fromRight, int64_t nRight,
+                   const unsigned long long* flags, unsigned long long seq, double4* dst)
+{
+    if (threadIdx.x == 0)
+    {
+        const volatile unsigned long long* f = flags;
+        while (f[0] < seq) {}
+        while (f[1] < seq) {}
+    }
+    __syncthreads();
+    __threadfence_system();
+    const int64_t k = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    // the records were written by another GPU: read them past L1
+    if (k < nLeft + nRight)
+    {
+        const double2* q = reinterpret_cast<const double2*>((k < nLeft) ? fromLeft + k : fromRight + (k - nLeft));
+        const double2 lo = __ldcv(q), hi = __ldcv(q + 1);
+        st4(dst + k, make_double4(lo.x, lo.y, hi.x, hi.y));
+    }
+}
+
 // (j, k) cell of a halo atom in the receiver's grid (identical y / z grid on every rank)
 __global__ void haloKeyKernel(const double4* pos, int64_t first, int64_t n, GridDev g, uint32_t* keys)
 {
@@ -317,12 +383,23 @@ struct mrmd_b200_slab
     mrmd_b200_thermo* thermo = nullptr;  // bins over the GLOBAL box, density all-reduced before every update
     double maxDisplacement = DBL_MAX;
     bool postPending = false;
+    // MRMD_B200_SLAB_PROFILE=1: phases separated by stream syncs, wall-clock sums printed at destroy (diagnostic only)
+    bool profile = false;
+    double prof[6] = {0, 0, 0, 0, 0, 0};  // pre, decision, rebuild, halo refresh, force, steps
     int64_t step = 0, rebuilds = 0, storedPairsNow = 0;
     int64_t haloLeftCount = 0, haloRightCount = 0;   // received
     int64_t sendLeftCount = 0, sendRightCount = 0;   // boundary atoms sent every step
     mrmd_b200::DevBuf flags, blockCounts, idxLow, idxHigh, sendBuf, recvBuf, haloKeys, haloStartLeft, haloStartRight;
     int64_t* dTotals = nullptr;  // [0..1] select totals, [2..5] exchanged counts
     int64_t* hTotals = nullptr;  // pinned, 8 entries
+    // per-step halo over peer memory (IPC): own buffer, the neighbours' buffers mapped into this process
+    bool p2p = false;
+    int64_t p2pCap = 0;  // atoms per region
+    double4* p2pBuf = nullptr;
+    double4* peerLeftBuf = nullptr;
+    double4* peerRightBuf = nullptr;
+    unsigned long long haloSeq = 0;
+    unsigned int* dPushTicket = nullptr;
     double* dScalars = nullptr;  // allreduce scratch
     double* hScalars = nullptr;  // pinned
     std::vector<cudaEvent_t> events;
@@ -488,6 +565,27 @@ static int haloRefresh(mrmd_b200_slab* sl, cudaStream_t st)
 {
     mrmd_b200_atoms* a = sl->atoms;
     const int64_t n = a->numLocal, nl = sl->sendLeftCount, nh = sl->sendRightCount;
+    if (sl->p2p)
+    {
+        MB_REQUIRE(nl <= sl->p2pCap && nh <= sl->p2pCap && sl->haloLeftCount <= sl->p2pCap && sl->haloRightCount <= sl->p2pCap,
+                   "slab: the position halo exceeds the peer buffer (density more than tripled since slab_create)");
+        const unsigned long long seq = ++sl->haloSeq;
+        // my low face goes to the left neighbour's "from right" region, my high face to the right neighbour's "from left"
+        double4* dstL = sl->peerLeftBuf + SL_P2P_HEADER + sl->p2pCap;
+        double4* dstR = sl->peerRightBuf + SL_P2P_HEADER;
+        unsigned long long* flagL = reinterpret_cast<unsigned long long*>(sl->peerLeftBuf) + 1;
+        unsigned long long* flagR = reinterpret_cast<unsigned long long*>(sl->peerRightBuf);
+        haloPushKernel<<<std::max(1, gridFor(nl + nh, SL_THREADS)), SL_THREADS, 0, st>>>(
+            a->v.pos, sl->idxLow.as<int32_t>(), nl, sl->shiftToLeft, dstL, flagL, sl->idxHigh.as<int32_t>(), nh,
+            sl->shiftToRight, dstR, flagR, seq, sl->dPushTicket);
+        MB_LAUNCHED();
+        const int64_t nIn = sl->haloLeftCount + sl->haloRightCount;
+        haloPullKernel<<<std::max(1, gridFor(nIn, SL_THREADS)), SL_THREADS, 0, st>>>(
+            sl->p2pBuf + SL_P2P_HEADER, sl->haloLeftCount, sl->p2pBuf + SL_P2P_HEADER + sl->p2pCap, sl->haloRightCount,
+            reinterpret_cast<const unsigned long long*>(sl->p2pBuf), seq, a->v.pos + n);
+        MB_LAUNCHED();
+        return 0;
+    }
     MB_TRY(sl->sendBuf.reserve(size_t(std::max<int64_t>(nl + nh, 1)) * 32));
     double4* sb = sl->sendBuf.as<double4>();
     if (nl > 0)
@@ -545,6 +643,65 @@ static int slabRebuild(mrmd_b200_slab* sl, cudaStream_t st)
     return 0;
 }
 
+// Peer-memory halo: allocate the IPC buffer, agree on its capacity, swap handles with the two neighbours through the
+// communicator and map their buffers.  Any failure (no peer access, IPC unavailable) leaves the NCCL halo in place.
+static int setupPeerHalo(mrmd_b200_slab* sl, double cutoff, double width)
+{
+    // face atoms ~ numLocal * cutoff / width; three times that, the same on every rank
+    const double estimate = 3.0 * double(sl->atoms->numLocal) * cutoff / std::max(width, cutoff) + 4096.0;
+    sl->hScalars[0] = estimate;
+    MB_CUDA(cudaMemcpy(sl->dScalars, sl->hScalars, 8, cudaMemcpyHostToDevice));
+    MB_NCCL(g_nccl.allReduce(sl->dScalars, sl->dScalars, 1, ncclDouble, ncclMax, sl->comm, nullptr));
+    MB_CUDA(cudaMemcpy(sl->hScalars, sl->dScalars, 8, cudaMemcpyDeviceToHost));
+    const int64_t cap = (static_cast<int64_t>(sl->hScalars[0]) + 63) & ~int64_t(63);
+    const size_t bytes = size_t(SL_P2P_HEADER + 2 * cap) * 32;
+    double4* buf = nullptr;
+    cudaIpcMemHandle_t mine, fromLeft, fromRight;
+    bool ok = cudaMalloc(&buf, bytes) == cudaSuccess && cudaMemset(buf, 0, bytes) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine, buf) == cudaSuccess;
+    // handles travel as bytes through the communicator (every rank takes part, also when its own setup failed)
+    unsigned char* dH = nullptr;
+    MB_CUDA(cudaMalloc(&dH, 3 * sizeof(cudaIpcMemHandle_t) + 8));
+    unsigned char okByte = ok ? 1 : 0;
+    if (ok) MB_CUDA(cudaMemcpy(dH, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+    const size_t hs = sizeof(cudaIpcMemHandle_t);
+    MB_NCCL(g_nccl.groupStart());
+    MB_NCCL(g_nccl.send(dH, hs, ncclUint8, sl->left, sl->comm, nullptr));
+    MB_NCCL(g_nccl.send(dH, hs, ncclUint8, sl->right, sl->comm, nullptr));
+    MB_NCCL(g_nccl.recv(dH + 2 * hs, hs, ncclUint8, sl->right, sl->comm, nullptr));
+    MB_NCCL(g_nccl.recv(dH + hs, hs, ncclUint8, sl->left, sl->comm, nullptr));
+    MB_NCCL(g_nccl.groupEnd());
+    MB_CUDA(cudaDeviceSynchronize());
+    MB_CUDA(cudaMemcpy(&fromLeft, dH + hs, hs, cudaMemcpyDeviceToHost));
+    MB_CUDA(cudaMemcpy(&fromRight, dH + 2 * hs, hs, cudaMemcpyDeviceToHost));
+    void *pl = nullptr, *pr = nullptr;
+    if (ok) ok = cudaIpcOpenMemHandle(&pl, fromLeft, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+    if (ok)
+    {
+        if (sl->left == sl->right) pr = pl;  // two slabs: both neighbours are the same rank, one mapping
+        else ok = cudaIpcOpenMemHandle(&pr, fromRight, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+    }
+    okByte = ok ? 1 : 0;
+    cudaGetLastError();  // a failed IPC call must not poison later launches
+    // everybody or nobody: the path is a property of the run, not of a rank
+    sl->hScalars[0] = okByte ? 1.0 : 0.0;
+    MB_CUDA(cudaMemcpy(sl->dScalars, sl->hScalars, 8, cudaMemcpyHostToDevice));
+    MB_NCCL(g_nccl.allReduce(sl->dScalars, sl->dScalars, 1, ncclDouble, ncclMin, sl->comm, nullptr));
+    MB_CUDA(cudaMemcpy(sl->hScalars, sl->dScalars, 8, cudaMemcpyDeviceToHost));
+    cudaFree(dH);
+    sl->p2pBuf = buf;
+    sl->peerLeftBuf = static_cast<double4*>(pl);
+    sl->peerRightBuf = static_cast<double4*>(pr);
+    sl->p2pCap = cap;
+    sl->p2p = sl->hScalars[0] > 0.5;
+    if (sl->p2p)
+    {
+        MB_CUDA(cudaMalloc(&sl->dPushTicket, 4));
+        MB_CUDA(cudaMemset(sl->dPushTicket, 0, 4));
+    }
+    return 0;
+}
+
 // mrmd_b200_adress::preUpdateHook: the compensation-energy samples of all slabs enter the mean
 static int sumOverRanks(void* ctx, double* sums, int64_t count, cudaStream_t st)
 {
@@ -553,26 +710,46 @@ static int sumOverRanks(void* ctx, double* sums, int64_t count, cudaStream_t st)
     return 0;
 }
 
+static double profMark(mrmd_b200_slab* sl, cudaStream_t st, double& last)
+{
+    if (!sl->profile) return 0.0;
+    cudaStreamSynchronize(st);
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    const double now = ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+    const double d = now - last;
+    last = now;
+    return d;
+}
+
 static int slabStep(mrmd_b200_slab* sl, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, bool wantEnergy)
 {
     const mrmd_b200_md_config& c = sl->cfg;
     mrmd_b200_atoms* a = sl->atoms;
+    double last = 0.0;
+    profMark(sl, st, last);
     // the previous step's postForceIntegrate rides in front of this kick (flushed when a run returns)
     MB_TRY(integratePre(a, c.dt, c.integrator == 1, c.zeta, c.temperature, c.seed + uint64_t(sl->rank),
                         uint64_t(sl->step), nullptr, sl->postPending, st));
     sl->postPending = false;
+    sl->prof[0] += profMark(sl, st, last);
     // the rebuild decision is collective: global maximum of the squared displacement
     MB_NCCL(g_nccl.allReduce(a->dMaxDisp, a->dMaxDisp, 1, ncclDouble, ncclMax, sl->comm, st));
     MB_CUDA(cudaMemcpyAsync(a->hMaxDisp, a->dMaxDisp, 8, cudaMemcpyDeviceToHost, st));
     MB_CUDA(cudaStreamSynchronize(st));
     sl->maxDisplacement += std::sqrt(*a->hMaxDisp);
+    sl->prof[1] += profMark(sl, st, last);
     if (sl->maxDisplacement >= c.skin * 0.5)
     {
         sl->maxDisplacement = 0.0;
         MB_TRY(slabRebuild(sl, st));
+        sl->prof[2] += profMark(sl, st, last);
     }
     else
+    {
         MB_TRY(haloRefresh(sl, st));
+        sl->prof[3] += profMark(sl, st, last);
+    }
     if (c.adress)
     {
         // SURVEY.md section 3.5 on a slab: thermodynamic force (density histogram all-reduced over the ranks
@@ -601,6 +778,8 @@ static int slabStep(mrmd_b200_slab* sl, cudaStream_t st, cudaEvent_t e0, cudaEve
         MB_TRY(ljApplyTiled(sl->lj, a, sl->list, false, wantEnergy, st));
         if (e1) MB_CUDA(cudaEventRecord(e1, st));
     }
+    sl->prof[4] += profMark(sl, st, last);
+    sl->prof[5] += 1.0;
     sl->postPending = true;
     sl->step += 1;
     return 0;
@@ -678,6 +857,7 @@ int mrmd_b200_slab_create_cuts(mrmd_b200_slab** out, const mrmd_b200_md_config* 
     sl->shiftToLeft = (rank == 0) ? lx : 0.0;             // crossing the low end of the box: x + Lx
     sl->shiftToRight = (rank == nranks - 1) ? -lx : 0.0;  // crossing the high end: x - Lx
     sl->atoms = atoms;
+    sl->profile = std::getenv("MRMD_B200_SLAB_PROFILE") != nullptr;
     int rc = 0;
     if (width < cutoff)
     {
@@ -720,6 +900,7 @@ int mrmd_b200_slab_create_cuts(mrmd_b200_slab** out, const mrmd_b200_md_config* 
     if (rc == 0 && cudaMallocHost(&sl->hTotals, 64) != cudaSuccess) rc = MRMD_B200_ENOMEM;
     if (rc == 0 && cudaMalloc(&sl->dScalars, 64) != cudaSuccess) rc = MRMD_B200_ENOMEM;
     if (rc == 0 && cudaMallocHost(&sl->hScalars, 64) != cudaSuccess) rc = MRMD_B200_ENOMEM;
+    if (rc == 0 && std::getenv("MRMD_B200_SLAB_NO_P2P") == nullptr) rc = setupPeerHalo(sl, cutoff, width);
     if (rc != 0)
     {
         mrmd_b200_slab_destroy(sl);
@@ -734,9 +915,19 @@ int mrmd_b200_slab_destroy(mrmd_b200_slab* sl)
 {
     if (sl == nullptr) return 0;
     cudaDeviceSynchronize();
+    if (sl->profile && sl->prof[5] > 0)
+        std::fprintf(stderr,
+                     "[mrmd_b200 slab rank %d] us/step over %.0f steps (%lld rebuilds): pre %.1f, decision %.1f, rebuild %.1f, "
+                     "halo refresh %.1f, force %.1f\n",
+                     sl->rank, sl->prof[5], static_cast<long long>(sl->rebuilds), sl->prof[0] / sl->prof[5],
+                     sl->prof[1] / sl->prof[5], sl->prof[2] / sl->prof[5], sl->prof[3] / sl->prof[5], sl->prof[4] / sl->prof[5]);
     for (auto e : sl->events) cudaEventDestroy(e);
     if (sl->comm != nullptr) g_nccl.commDestroy(sl->comm);
     mrmd_b200_verlet_destroy(sl->list);
+    if (sl->peerLeftBuf != nullptr) cudaIpcCloseMemHandle(sl->peerLeftBuf);
+    if (sl->peerRightBuf != nullptr && sl->peerRightBuf != sl->peerLeftBuf) cudaIpcCloseMemHandle(sl->peerRightBuf);
+    if (sl->p2pBuf != nullptr) cudaFree(sl->p2pBuf);
+    if (sl->dPushTicket != nullptr) cudaFree(sl->dPushTicket);
     mrmd_b200_lj_destroy(sl->lj);
     mrmd_b200_adress_destroy(sl->adress);
     mrmd_b200_thermo_destroy(sl->thermo);
