@@ -39,6 +39,7 @@ struct NcclApi
     decltype(&ncclGroupStart) groupStart = nullptr;
     decltype(&ncclGroupEnd) groupEnd = nullptr;
     decltype(&ncclAllReduce) allReduce = nullptr;
+    decltype(&ncclAllGather) allGather = nullptr;
     decltype(&ncclGetErrorString) getErrorString = nullptr;
 };
 
@@ -69,6 +70,7 @@ static int loadNccl()
     NCCL_SYM(groupStart, "ncclGroupStart");
     NCCL_SYM(groupEnd, "ncclGroupEnd");
     NCCL_SYM(allReduce, "ncclAllReduce");
+    NCCL_SYM(allGather, "ncclAllGather");
     NCCL_SYM(getErrorString, "ncclGetErrorString");
 #undef NCCL_SYM
     g_nccl.lib = lib;
@@ -295,7 +297,51 @@ __global__ void packPositionsKernel(const double4* pos, const int32_t* idx, int6
 // receiving rank waits for both numbers and copies the records behind its local atoms.  No NCCL call, no staging
 // buffer, no host involvement in the per-step exchange.  A region is only rewritten after the rank-wide allreduce of
 // the next step, which the reader's stream reaches only after its pull (and force kernel) have finished.
-constexpr int SL_P2P_HEADER = 2;  // double4 slots in front of the regions: flags {fromLeft, fromRight, -, -} + padding
+constexpr int SL_MAX_PEERS = 8;    // ranks of one node
+// double4 slots in front of the regions: [0] halo flags {fromLeft, fromRight}, [1 ..] the slots of the displacement
+// all-gather: 2 parities x SL_MAX_PEERS x {value, sequence number}
+constexpr int SL_P2P_HEADER = 1 + SL_MAX_PEERS;
+struct PeerBuffers
+{
+    double4* p[SL_MAX_PEERS];
+};
+
+// The rebuild decision needs the maximum displacement over all ranks every step.  Instead of an NCCL all-reduce (tens
+// of microseconds of launch and protocol latency for 8 bytes) every rank stores {value, step} into its slot of every
+// peer's buffer over NVLink, waits until its own buffer holds this step's value of every rank, and takes the maximum:
+// one single-warp kernel per step.  The result also goes to pinned host memory (zero copy) with the step number
+// behind it, so the host learns it without a stream synchronisation.  Slots alternate between two sets by step parity:
+// a rank can be at most one decision ahead of the slowest one (it needs that rank's value to finish its own).
+__global__ void maxDisplacementGatherKernel(const double* myMaxSqr, PeerBuffers peers, int rank, int nranks, double seq,
+                                            int parity, double* outDevice, volatile double* outHost)
+{
+    const int t = threadIdx.x;
+    const int slotBase = 4 * 1 + parity * 2 * SL_MAX_PEERS;  // in doubles from the start of the buffer (header slot 1 ...)
+    if (t < nranks)
+    {
+        volatile double* slot = reinterpret_cast<double*>(peers.p[t]) + slotBase + 2 * rank;
+        slot[0] = *myMaxSqr;
+        __threadfence_system();
+        slot[1] = seq;
+    }
+    double m = 0.0;
+    if (t < nranks)
+    {
+        const volatile double* mine = reinterpret_cast<double*>(peers.p[rank]) + slotBase + 2 * t;
+        while (mine[1] < seq) {}
+        __threadfence_system();
+        m = mine[0];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (t == 0)
+    {
+        *outDevice = m;
+        outHost[0] = m;
+        __threadfence_system();
+        outHost[1] = seq;
+    }
+}
 
 __global__ void __launch_bounds__(SL_THREADS)
     haloPushKernel(const double4* __restrict__ pos, const int32_t* __restrict__ idxLow, int64_t nl, double shiftL,
@@ -396,8 +442,11 @@ struct mrmd_b200_slab
     bool p2p = false;
     int64_t p2pCap = 0;  // atoms per region
     double4* p2pBuf = nullptr;
+    mrmd_b200::PeerBuffers peers{};  // every rank's buffer (own entry = p2pBuf)
     double4* peerLeftBuf = nullptr;
     double4* peerRightBuf = nullptr;
+    double* hDecide = nullptr;  // pinned, written by maxDisplacementGatherKernel: {max |dx|^2, step}
+    double decideSeq = 0.0;
     unsigned long long haloSeq = 0;
     unsigned int* dPushTicket = nullptr;
     double* dScalars = nullptr;  // allreduce scratch
@@ -656,31 +705,35 @@ static int setupPeerHalo(mrmd_b200_slab* sl, double cutoff, double width)
     const int64_t cap = (static_cast<int64_t>(sl->hScalars[0]) + 63) & ~int64_t(63);
     const size_t bytes = size_t(SL_P2P_HEADER + 2 * cap) * 32;
     double4* buf = nullptr;
-    cudaIpcMemHandle_t mine, fromLeft, fromRight;
+    cudaIpcMemHandle_t mine;
     bool ok = cudaMalloc(&buf, bytes) == cudaSuccess && cudaMemset(buf, 0, bytes) == cudaSuccess &&
               cudaIpcGetMemHandle(&mine, buf) == cudaSuccess;
     // handles travel as bytes through the communicator (every rank takes part, also when its own setup failed)
-    unsigned char* dH = nullptr;
-    MB_CUDA(cudaMalloc(&dH, 3 * sizeof(cudaIpcMemHandle_t) + 8));
-    unsigned char okByte = ok ? 1 : 0;
-    if (ok) MB_CUDA(cudaMemcpy(dH, &mine, sizeof(mine), cudaMemcpyHostToDevice));
     const size_t hs = sizeof(cudaIpcMemHandle_t);
-    MB_NCCL(g_nccl.groupStart());
-    MB_NCCL(g_nccl.send(dH, hs, ncclUint8, sl->left, sl->comm, nullptr));
-    MB_NCCL(g_nccl.send(dH, hs, ncclUint8, sl->right, sl->comm, nullptr));
-    MB_NCCL(g_nccl.recv(dH + 2 * hs, hs, ncclUint8, sl->right, sl->comm, nullptr));
-    MB_NCCL(g_nccl.recv(dH + hs, hs, ncclUint8, sl->left, sl->comm, nullptr));
-    MB_NCCL(g_nccl.groupEnd());
+    const int R = sl->nranks;
+    if (R > SL_MAX_PEERS) ok = false;
+    unsigned char* dH = nullptr;
+    MB_CUDA(cudaMalloc(&dH, size_t(R + 1) * hs));
+    unsigned char okByte = ok ? 1 : 0;
+    if (ok) MB_CUDA(cudaMemcpy(dH, &mine, hs, cudaMemcpyHostToDevice));
+    MB_NCCL(g_nccl.allGather(dH, dH + hs, hs, ncclUint8, sl->comm, nullptr));
     MB_CUDA(cudaDeviceSynchronize());
-    MB_CUDA(cudaMemcpy(&fromLeft, dH + hs, hs, cudaMemcpyDeviceToHost));
-    MB_CUDA(cudaMemcpy(&fromRight, dH + 2 * hs, hs, cudaMemcpyDeviceToHost));
-    void *pl = nullptr, *pr = nullptr;
-    if (ok) ok = cudaIpcOpenMemHandle(&pl, fromLeft, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
-    if (ok)
+    std::vector<cudaIpcMemHandle_t> all(static_cast<size_t>(R));
+    MB_CUDA(cudaMemcpy(all.data(), dH + hs, size_t(R) * hs, cudaMemcpyDeviceToHost));
+    for (int r = 0; r < R && r < SL_MAX_PEERS; ++r) sl->peers.p[r] = nullptr;
+    for (int r = 0; r < R && ok; ++r)
     {
-        if (sl->left == sl->right) pr = pl;  // two slabs: both neighbours are the same rank, one mapping
-        else ok = cudaIpcOpenMemHandle(&pr, fromRight, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+        if (r == sl->rank)
+        {
+            sl->peers.p[r] = buf;
+            continue;
+        }
+        void* q = nullptr;
+        ok = cudaIpcOpenMemHandle(&q, all[static_cast<size_t>(r)], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+        sl->peers.p[r] = static_cast<double4*>(q);
     }
+    void* pl = ok ? sl->peers.p[sl->left] : nullptr;
+    void* pr = ok ? sl->peers.p[sl->right] : nullptr;
     okByte = ok ? 1 : 0;
     cudaGetLastError();  // a failed IPC call must not poison later launches
     // everybody or nobody: the path is a property of the run, not of a rank
@@ -698,6 +751,8 @@ static int setupPeerHalo(mrmd_b200_slab* sl, double cutoff, double width)
     {
         MB_CUDA(cudaMalloc(&sl->dPushTicket, 4));
         MB_CUDA(cudaMemset(sl->dPushTicket, 0, 4));
+        MB_CUDA(cudaMallocHost(&sl->hDecide, 16));
+        sl->hDecide[0] = sl->hDecide[1] = 0.0;
     }
     return 0;
 }
@@ -734,9 +789,32 @@ static int slabStep(mrmd_b200_slab* sl, cudaStream_t st, cudaEvent_t e0, cudaEve
     sl->postPending = false;
     sl->prof[0] += profMark(sl, st, last);
     // the rebuild decision is collective: global maximum of the squared displacement
-    MB_NCCL(g_nccl.allReduce(a->dMaxDisp, a->dMaxDisp, 1, ncclDouble, ncclMax, sl->comm, st));
-    MB_CUDA(cudaMemcpyAsync(a->hMaxDisp, a->dMaxDisp, 8, cudaMemcpyDeviceToHost, st));
-    MB_CUDA(cudaStreamSynchronize(st));
+    if (sl->p2p)
+    {
+        sl->decideSeq += 1.0;
+        const int parity = static_cast<int>(static_cast<long long>(sl->decideSeq) & 1);
+        maxDisplacementGatherKernel<<<1, 32, 0, st>>>(a->dMaxDisp, sl->peers, sl->rank, sl->nranks, sl->decideSeq, parity,
+                                                      a->dMaxDisp, sl->hDecide);
+        MB_LAUNCHED();
+        // the kernel writes {max, step} into pinned memory: poll it instead of synchronising the stream
+        volatile double* h = sl->hDecide;
+        for (unsigned spin = 0; h[1] != sl->decideSeq; ++spin)
+        {
+            if ((spin & 0xfff) == 0xfff)
+            {
+                const cudaError_t q = cudaStreamQuery(st);
+                if (q != cudaSuccess && q != cudaErrorNotReady) MB_CUDA(q);
+                if (q == cudaSuccess && h[1] != sl->decideSeq) MB_REQUIRE(false, "slab: displacement gather finished without a result");
+            }
+        }
+        *a->hMaxDisp = h[0];
+    }
+    else
+    {
+        MB_NCCL(g_nccl.allReduce(a->dMaxDisp, a->dMaxDisp, 1, ncclDouble, ncclMax, sl->comm, st));
+        MB_CUDA(cudaMemcpyAsync(a->hMaxDisp, a->dMaxDisp, 8, cudaMemcpyDeviceToHost, st));
+        MB_CUDA(cudaStreamSynchronize(st));
+    }
     sl->maxDisplacement += std::sqrt(*a->hMaxDisp);
     sl->prof[1] += profMark(sl, st, last);
     if (sl->maxDisplacement >= c.skin * 0.5)
@@ -924,8 +1002,9 @@ int mrmd_b200_slab_destroy(mrmd_b200_slab* sl)
     for (auto e : sl->events) cudaEventDestroy(e);
     if (sl->comm != nullptr) g_nccl.commDestroy(sl->comm);
     mrmd_b200_verlet_destroy(sl->list);
-    if (sl->peerLeftBuf != nullptr) cudaIpcCloseMemHandle(sl->peerLeftBuf);
-    if (sl->peerRightBuf != nullptr && sl->peerRightBuf != sl->peerLeftBuf) cudaIpcCloseMemHandle(sl->peerRightBuf);
+    for (int r = 0; r < SL_MAX_PEERS && r < sl->nranks; ++r)
+        if (sl->peers.p[r] != nullptr && r != sl->rank) cudaIpcCloseMemHandle(sl->peers.p[r]);
+    if (sl->hDecide != nullptr) cudaFreeHost(sl->hDecide);
     if (sl->p2pBuf != nullptr) cudaFree(sl->p2pBuf);
     if (sl->dPushTicket != nullptr) cudaFree(sl->dPushTicket);
     mrmd_b200_lj_destroy(sl->lj);
