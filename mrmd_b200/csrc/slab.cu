@@ -8,13 +8,16 @@
 //             by linked cell, the atoms within rc+skin of each x face are sent as halo atoms (they arrive in
 //             (j,k) cell order because the sender's atoms are cell sorted) and the tiled neighbour build treats
 //             them as two extra cell columns;
-//   step      positions of the halo atoms only (32 B per atom, ncclSend/ncclRecv straight into the position
-//             array), no reverse force halo: with the full list every rank computes the complete force of
-//             its own atoms;
-//   decision  the displacement criterion (examples/02:141-143) uses the ncclAllReduce(max) over the ranks, so
-//             all ranks rebuild together.
+//   step      positions of the halo atoms only (32 B per atom), stored by haloPushKernel straight into the
+//             neighbours' IPC-mapped buffers over NVLink and collected by haloPullKernel (ncclSend/ncclRecv as the
+//             fallback); no reverse force halo: with the full list every rank computes the complete force of its
+//             own atoms;
+//   decision  the displacement criterion (examples/02:141-143) uses the maximum over the ranks, gathered through
+//             the same peer buffers by maxDisplacementGatherKernel (ncclAllReduce(max) as the fallback), so all
+//             ranks rebuild together.
 // The periodic wrap in x is applied by the two end ranks when they send across the global boundary.
-// NCCL is resolved at run time with dlopen (single-GPU users do not need it).
+// NCCL is resolved at run time with dlopen (single-GPU users do not need it); it bootstraps the peer mapping and
+// carries the rebuild-time traffic (migration records, counts) and the read-out reductions.
 #include <dlfcn.h>
 #include <nccl.h>
 
