@@ -779,6 +779,92 @@ private:
 };
 }  // namespace action
 
+namespace data
+{
+/// data::Bond (data/Bond.hpp:23-28)
+struct Bond
+{
+    idx_t idx;          ///< relative index of first atom
+    idx_t jdx;          ///< relative index of second atom
+    real_t eqDistance;  ///< equilibrium distance of the bond
+};
+using BondView = std::vector<Bond>;  ///< host side stand-in for Kokkos::View<Bond*> (and its host mirror)
+}  // namespace data
+
+namespace action
+{
+/// action::BerendsenThermostat::apply (action/BerendsenThermostat.cpp:25-50)
+namespace BerendsenThermostat
+{
+inline void apply(data::Atoms& atoms, const real_t& currentTemperature, const real_t& targetTemperature, const real_t& gamma)
+{
+    atoms.push();
+    detail::check(mrmd_b200_berendsen_thermostat(atoms.handle(), currentTemperature, targetTemperature, gamma, defaultStream),
+                  "BerendsenThermostat::apply");
+}
+}  // namespace BerendsenThermostat
+
+/// action::BerendsenBarostat::apply (action/BerendsenBarostat.cpp:23-50)
+namespace BerendsenBarostat
+{
+inline void apply(data::Atoms& atoms, const real_t& currentPressure, const real_t& targetPressure, const real_t& gamma,
+                  data::Subdomain& subdomain, bool stretchX = true, bool stretchY = true, bool stretchZ = true)
+{
+    atoms.push();
+    // the device scales the positions with the same mu the host applies to the subdomain (Subdomain::scaleDim)
+    auto s = subdomain.c();
+    detail::check(mrmd_b200_berendsen_barostat(atoms.handle(), currentPressure, targetPressure, gamma, &s, stretchX, stretchY,
+                                               stretchZ, defaultStream),
+                  "BerendsenBarostat::apply");
+    const real_t mu = std::cbrt(1_r + gamma * (currentPressure - targetPressure));
+    if (stretchX) subdomain.scaleDim(mu, AXIS::X);
+    if (stretchY) subdomain.scaleDim(mu, AXIS::Y);
+    if (stretchZ) subdomain.scaleDim(mu, AXIS::Z);
+}
+}  // namespace BerendsenBarostat
+
+/// action::MoleculeConstraints (action/Shake.hpp:159-251): SHAKE / RATTLE over the bonds of every local molecule
+class MoleculeConstraints
+{
+public:
+    MoleculeConstraints(idx_t atomsPerMolecule, idx_t numConstraintIterations)
+    {
+        mrmd_b200_constraints* h = nullptr;
+        detail::check(mrmd_b200_constraints_create(&h, atomsPerMolecule, numConstraintIterations), "MoleculeConstraints");
+        h_.reset(h, [](mrmd_b200_constraints* p) { mrmd_b200_constraints_destroy(p); });
+    }
+    void setConstraints(const data::BondView& bonds)
+    {
+        std::vector<int64_t> idx, jdx;
+        std::vector<real_t> eq;
+        for (const auto& b : bonds)
+        {
+            idx.push_back(b.idx);
+            jdx.push_back(b.jdx);
+            eq.push_back(b.eqDistance);
+        }
+        detail::check(mrmd_b200_constraints_set(h_.get(), idx.data(), jdx.data(), eq.data(), idx_c(bonds.size())), "setConstraints");
+    }
+    void enforcePositionalConstraints(data::Molecules& molecules, data::Atoms& atoms, const real_t dt)
+    {
+        molecules.push();
+        atoms.push();
+        detail::check(mrmd_b200_constraints_enforce_positional(h_.get(), molecules.handle(), atoms.handle(), dt, defaultStream),
+                      "enforcePositionalConstraints");
+    }
+    void enforceVelocityConstraints(data::Molecules& molecules, data::Atoms& atoms, const real_t dt)
+    {
+        molecules.push();
+        atoms.push();
+        detail::check(mrmd_b200_constraints_enforce_velocity(h_.get(), molecules.handle(), atoms.handle(), dt, defaultStream),
+                      "enforceVelocityConstraints");
+    }
+
+private:
+    std::shared_ptr<mrmd_b200_constraints> h_;
+};
+}  // namespace action
+
 // ------------------------------------------------------------------------------------------------------
 namespace analysis
 {

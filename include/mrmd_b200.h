@@ -355,6 +355,31 @@ int mrmd_b200_msd_calc_atoms(const mrmd_b200_msd* m, const mrmd_b200_atoms* a, c
 int mrmd_b200_msd_calc_molecules(const mrmd_b200_msd* m, const mrmd_b200_molecules* mol, const mrmd_b200_subdomain* s,
                                  double* meanSquareDisplacement, void* stream);
 
+/* ---- thermostat / barostat / constraints around the loop (tests/NVT, tests/NPT, tests/Constraints) ---- */
+typedef struct mrmd_b200_constraints mrmd_b200_constraints; /* action::MoleculeConstraints (action/Shake.hpp:159-251) */
+/* replaces BerendsenThermostat::apply (action/BerendsenThermostat.cpp:25-50): v *= sqrt(1 + gamma (T_target / T - 1))
+ * for the local atoms; no-op for T <= 0 */
+int mrmd_b200_berendsen_thermostat(mrmd_b200_atoms* a, double currentTemperature, double targetTemperature, double gamma,
+                                   void* stream);
+/* replaces BerendsenBarostat::apply (action/BerendsenBarostat.cpp:23-50): mu = cbrt(1 + gamma (P - P_target)) scales
+ * the chosen axes of the subdomain (Subdomain::scaleDim) and of the local atoms' positions */
+int mrmd_b200_berendsen_barostat(mrmd_b200_atoms* a, double currentPressure, double targetPressure, double gamma,
+                                 mrmd_b200_subdomain* s, int stretchX, int stretchY, int stretchZ, void* stream);
+/* MoleculeConstraints(atomsPerMolecule, numConstraintIterations) (:247-250) */
+int mrmd_b200_constraints_create(mrmd_b200_constraints** out, int64_t atomsPerMolecule, int64_t numConstraintIterations);
+int mrmd_b200_constraints_destroy(mrmd_b200_constraints* c);
+/* setConstraints (:236-245): bonds {idx, jdx, eqDistance} (data/Bond.hpp:23-28), indices relative to the molecule's
+ * first atom; host arrays */
+int mrmd_b200_constraints_set(mrmd_b200_constraints* c, const int64_t* idx, const int64_t* jdx, const double* eqDistance,
+                              int64_t numBonds);
+/* replaces enforcePositionalConstraints (:167-201): numConstraintIterations x (unconstrained update of all atoms,
+ * SHAKE force correction per bond of every local molecule, impl::Shake :84-137) */
+int mrmd_b200_constraints_enforce_positional(mrmd_b200_constraints* c, const mrmd_b200_molecules* m, mrmd_b200_atoms* a,
+                                             double dt, void* stream);
+/* replaces enforceVelocityConstraints (:203-233): RATTLE velocity projection per bond (impl::Shake :56-82) */
+int mrmd_b200_constraints_enforce_velocity(mrmd_b200_constraints* c, const mrmd_b200_molecules* m, mrmd_b200_atoms* a,
+                                           double dt, void* stream);
+
 /* ---- step loop of the reference's drivers ----------------------------------------------------
  * The hot loop of examples/02_LennardJones_NVE.cpp:135-216 (rebuild policy :141-171), with the Langevin
  * integrator of examples/01_LennardJones_NVT.cpp:121,142 and the LinkedCellList + permute spatial sort of

@@ -141,6 +141,13 @@ SIGNATURES = {
     "mrmd_b200_msd_reset_molecules": (C.c_int, [vp, vp, vp]),
     "mrmd_b200_msd_calc_atoms": (C.c_int, [vp, vp, pSub, pdbl, vp]),
     "mrmd_b200_msd_calc_molecules": (C.c_int, [vp, vp, pSub, pdbl, vp]),
+    "mrmd_b200_berendsen_thermostat": (C.c_int, [vp, dbl, dbl, dbl, vp]),
+    "mrmd_b200_berendsen_barostat": (C.c_int, [vp, dbl, dbl, dbl, pSub, C.c_int, C.c_int, C.c_int, vp]),
+    "mrmd_b200_constraints_create": (C.c_int, [pvp, i64, i64]),
+    "mrmd_b200_constraints_destroy": (C.c_int, [vp]),
+    "mrmd_b200_constraints_set": (C.c_int, [vp, vp, vp, vp, i64]),
+    "mrmd_b200_constraints_enforce_positional": (C.c_int, [vp, vp, vp, dbl, vp]),
+    "mrmd_b200_constraints_enforce_velocity": (C.c_int, [vp, vp, vp, dbl, vp]),
     "mrmd_b200_md_create": (C.c_int, [pvp, C.POINTER(MdConfig), pSub, vp]),
     "mrmd_b200_md_destroy": (C.c_int, [vp]),
     "mrmd_b200_md_run": (C.c_int, [vp, i64, C.c_int, C.POINTER(MdStats), vp]),

@@ -626,6 +626,54 @@ class ThermodynamicForce:
                 pass
 
 
+class BerendsenThermostat:
+    """action::BerendsenThermostat::apply (action/BerendsenThermostat.cpp:25-50)"""
+
+    @staticmethod
+    def apply(atoms, currentTemperature, targetTemperature, gamma, stream=None):
+        check(L().mrmd_b200_berendsen_thermostat(atoms.h, currentTemperature, targetTemperature, gamma, _stream(stream)))
+
+
+class BerendsenBarostat:
+    """action::BerendsenBarostat::apply (action/BerendsenBarostat.cpp:23-50); scales `subdomain` in place"""
+
+    @staticmethod
+    def apply(atoms, currentPressure, targetPressure, gamma, subdomain, stretchX=True, stretchY=True, stretchZ=True,
+              stream=None):
+        check(L().mrmd_b200_berendsen_barostat(atoms.h, currentPressure, targetPressure, gamma, C.byref(subdomain),
+                                               int(stretchX), int(stretchY), int(stretchZ), _stream(stream)))
+
+
+class MoleculeConstraints:
+    """action::MoleculeConstraints (action/Shake.hpp:159-251): SHAKE / RATTLE over the bonds of every local molecule"""
+
+    def __init__(self, atomsPerMolecule, numConstraintIterations):
+        self.h = C.c_void_p()
+        check(L().mrmd_b200_constraints_create(C.byref(self.h), atomsPerMolecule, numConstraintIterations))
+
+    def setConstraints(self, bonds):
+        """bonds: iterable of (idx, jdx, eqDistance) (data::Bond)"""
+        b = list(bonds)
+        idx = np.ascontiguousarray([x[0] for x in b], dtype=np.int64)
+        jdx = np.ascontiguousarray([x[1] for x in b], dtype=np.int64)
+        eq = np.ascontiguousarray([x[2] for x in b], dtype=np.float64)
+        check(L().mrmd_b200_constraints_set(self.h, idx.ctypes.data, jdx.ctypes.data, eq.ctypes.data, len(b)))
+
+    def enforcePositionalConstraints(self, molecules, atoms, dt, stream=None):
+        check(L().mrmd_b200_constraints_enforce_positional(self.h, molecules.h, atoms.h, dt, _stream(stream)))
+
+    def enforceVelocityConstraints(self, molecules, atoms, dt, stream=None):
+        check(L().mrmd_b200_constraints_enforce_velocity(self.h, molecules.h, atoms.h, dt, _stream(stream)))
+
+    def __del__(self):
+        h, self.h = getattr(self, "h", None), None
+        if h:
+            try:
+                L().mrmd_b200_constraints_destroy(h)
+            except Exception:
+                pass
+
+
 class analysis:
     """namespace mrmd::analysis: the diagnostics of the drivers' statistics lines (examples/02:190-199)"""
 

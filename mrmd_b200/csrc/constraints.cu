@@ -1,0 +1,268 @@
+// constraints.cu -- Berendsen thermostat / barostat and SHAKE / RATTLE molecule constraints (SURVEY.md section 8 row
+// (f)2: what the reference's NVT / NPT / Constraints integration tests and tetramer runs put around the hot loop).
+// Reference: mrmd/action/BerendsenThermostat.cpp:25-50, BerendsenBarostat.cpp:23-50,
+//            mrmd/action/Shake.hpp:35-157 (impl::Shake), :159-251 (MoleculeConstraints), mrmd/data/Bond.hpp:23-28.
+// Streaming kernels (24-56 B per atom); SHAKE walks the bonds of a molecule sequentially in one thread exactly like the
+// reference's per-molecule lambda, so no atomics are needed (a molecule's atoms belong to it alone).
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "handles.cuh"
+
+struct mrmd_b200_constraints
+{
+    int64_t atomsPerMolecule = 0;
+    int64_t numIterations = 0;
+    int64_t numBonds = 0;
+    mrmd_b200::DevBuf bondIdx;      // int64 {idx, jdx} per bond
+    mrmd_b200::DevBuf bondDist;     // double eqDistance per bond
+    mrmd_b200::DevBuf updatedPos;   // double4 per atom (impl::Shake::updatedPos_)
+};
+
+namespace mrmd_b200
+{
+__global__ void scaleVelocityKernel(AtomsView a, int64_t n, double beta)
+{
+    const int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (idx >= n) return;
+    a.vel[0][idx] *= beta;  // BerendsenThermostat.cpp:40-42
+    a.vel[1][idx] *= beta;
+    a.vel[2][idx] *= beta;
+}
+
+__global__ void scalePositionKernel(double4* pos, int64_t n, double mu, int sx, int sy, int sz)
+{
+    const int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (idx >= n) return;
+    double4 p = ld4(pos + idx);
+    if (sx) p.x *= mu;  // BerendsenBarostat.cpp:40-42
+    if (sy) p.y *= mu;
+    if (sz) p.z *= mu;
+    st4(pos + idx, p);
+}
+
+// Shake::operator()(UnconstraintUpdate, idx), Shake.hpp:131-137
+__global__ void shakeUnconstraintKernel(AtomsView a, int64_t n, double dtv, double dtf, double4* updatedPos)
+{
+    const int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (idx >= n) return;
+    const double4 p = ld4(a.pos + idx);
+    const double dtfm = dtf / a.mass[idx];
+    st4(updatedPos + idx, make_double4(p.x + dtv * a.vel[0][idx] + dtfm * a.force[0][idx],
+                                       p.y + dtv * a.vel[1][idx] + dtfm * a.force[1][idx],
+                                       p.z + dtv * a.vel[2][idx] + dtfm * a.force[2][idx], 0.0));
+}
+
+// MoleculeConstraints::enforcePositionalConstraints lambda (Shake.hpp:179-197) with
+// Shake::enforcePositionalConstraint (:84-128) inlined; one thread per molecule
+__global__ void shakePositionalKernel(MolsView m, AtomsView a, int64_t numLocalMols, const long long* __restrict__ bondIdx,
+                                      const double* __restrict__ bondDist, int64_t numBonds,
+                                      const double4* __restrict__ updatedPos, double dtf, int* error)
+{
+    const int64_t mol = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (mol >= numLocalMols) return;
+    const longlong2 oc = m.oc[mol];
+    for (int64_t b = 0; b < numBonds; ++b)
+    {
+        const long long bi = bondIdx[2 * b], bj = bondIdx[2 * b + 1];
+        if (bi >= oc.y || bj >= oc.y)  // MRMD_DEVICE_ASSERT_LESS: not enough atoms in molecule to satisfy bond
+        {
+            *error = 1;
+            return;
+        }
+        const long long idx = oc.x + bi, jdx = oc.x + bj;
+        const double eqDistance = bondDist[b];
+        const double4 pi = ld4(a.pos + idx), pj = ld4(a.pos + jdx);
+        const double dist[3] = {pi.x - pj.x, pi.y - pj.y, pi.z - pj.z};
+        const double distSq = dist[0] * dist[0] + dist[1] * dist[1] + dist[2] * dist[2];
+        const double4 ui = ld4(updatedPos + idx), uj = ld4(updatedPos + jdx);
+        const double upd[3] = {ui.x - uj.x, ui.y - uj.y, ui.z - uj.z};
+        const double updSq = upd[0] * upd[0] + upd[1] * upd[1] + upd[2] * upd[2];
+        const double invMassI = 1.0 / a.mass[idx], invMassJ = 1.0 / a.mass[jdx];
+        const double qa = (invMassI + invMassJ) * (invMassI + invMassJ) * distSq;
+        const double qb = 2.0 * (invMassI + invMassJ) * (upd[0] * dist[0] + upd[1] * dist[1] + upd[2] * dist[2]);
+        const double qc = updSq - eqDistance * eqDistance;
+        double determinant = qb * qb - 4.0 * qa * qc;
+        determinant = fmax(0.0, determinant);
+        const double root = sqrt(determinant);
+        const double lambda1 = (-qb + root) / (2.0 * qa);
+        const double lambda2 = (-qb - root) / (2.0 * qa);
+        double lambda = (fabs(lambda1) < fabs(lambda2)) ? lambda1 : lambda2;
+        lambda /= dtf;
+        for (int d = 0; d < 3; ++d)
+        {
+            a.force[d][idx] += lambda * dist[d];
+            a.force[d][jdx] -= lambda * dist[d];
+        }
+    }
+}
+
+// MoleculeConstraints::enforceVelocityConstraints lambda (Shake.hpp:215-231) with
+// Shake::enforceVelocityConstraint (:56-82) inlined
+__global__ void shakeVelocityKernel(MolsView m, AtomsView a, int64_t numLocalMols, const long long* __restrict__ bondIdx,
+                                    int64_t numBonds, int* error)
+{
+    const int64_t mol = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (mol >= numLocalMols) return;
+    const longlong2 oc = m.oc[mol];
+    for (int64_t b = 0; b < numBonds; ++b)
+    {
+        const long long bi = bondIdx[2 * b], bj = bondIdx[2 * b + 1];
+        if (bi >= oc.y || bj >= oc.y)
+        {
+            *error = 1;
+            return;
+        }
+        const long long idx = oc.x + bi, jdx = oc.x + bj;
+        const double4 pi = ld4(a.pos + idx), pj = ld4(a.pos + jdx);
+        const double dist[3] = {pi.x - pj.x, pi.y - pj.y, pi.z - pj.z};
+        const double distSq = dist[0] * dist[0] + dist[1] * dist[1] + dist[2] * dist[2];
+        const double invMassI = 1.0 / a.mass[idx], invMassJ = 1.0 / a.mass[jdx];
+        const double reducedMass = 1.0 / (invMassI + invMassJ);
+        const double relVel[3] = {a.vel[0][idx] - a.vel[0][jdx], a.vel[1][idx] - a.vel[1][jdx], a.vel[2][idx] - a.vel[2][jdx]};
+        const double factor = (relVel[0] * dist[0] + relVel[1] * dist[1] + relVel[2] * dist[2]) / distSq * reducedMass;
+        for (int d = 0; d < 3; ++d)
+        {
+            a.vel[d][idx] -= factor * dist[d] * invMassI;
+            a.vel[d][jdx] += factor * dist[d] * invMassJ;
+        }
+    }
+}
+
+static int checkBondError(int* dErr, cudaStream_t st)
+{
+    int h = 0;
+    MB_CUDA(cudaMemcpyAsync(&h, dErr, 4, cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaStreamSynchronize(st));  // the reference fences after every kernel too
+    cudaFree(dErr);
+    MB_REQUIRE(h == 0, "not enough atoms in molecule to satisfy bond");
+    return 0;
+}
+}  // namespace mrmd_b200
+
+using namespace mrmd_b200;
+
+extern "C" {
+
+int mrmd_b200_berendsen_thermostat(mrmd_b200_atoms* a, double currentTemperature, double targetTemperature, double gamma,
+                                   void* stream)
+{
+    MB_TRY(checkDevice());
+    MB_REQUIRE(a != nullptr, "berendsen_thermostat");
+    if (currentTemperature <= 0.0) return 0;  // BerendsenThermostat.cpp:30-33
+    MB_REQUIRE(targetTemperature > 0.0, "berendsen_thermostat: target temperature must be positive");
+    const double beta = std::sqrt(1.0 + gamma * (targetTemperature / currentTemperature - 1.0));
+    if (a->numLocal == 0) return 0;
+    scaleVelocityKernel<<<gridFor(a->numLocal, 256), 256, 0, S(stream)>>>(a->v, a->numLocal, beta);
+    MB_LAUNCHED();
+    return 0;
+}
+
+int mrmd_b200_berendsen_barostat(mrmd_b200_atoms* a, double currentPressure, double targetPressure, double gamma,
+                                 mrmd_b200_subdomain* s, int stretchX, int stretchY, int stretchZ, void* stream)
+{
+    MB_TRY(checkDevice());
+    MB_REQUIRE(a != nullptr && s != nullptr, "berendsen_barostat");
+    const double mu = std::cbrt(1.0 + gamma * (currentPressure - targetPressure));
+    if (stretchX) mrmd_b200_subdomain_scale_dim(s, mu, 0);
+    if (stretchY) mrmd_b200_subdomain_scale_dim(s, mu, 1);
+    if (stretchZ) mrmd_b200_subdomain_scale_dim(s, mu, 2);
+    if (a->numLocal == 0) return 0;
+    scalePositionKernel<<<gridFor(a->numLocal, 256), 256, 0, S(stream)>>>(a->v.pos, a->numLocal, mu, stretchX, stretchY,
+                                                                          stretchZ);
+    MB_LAUNCHED();
+    return 0;
+}
+
+int mrmd_b200_constraints_create(mrmd_b200_constraints** out, int64_t atomsPerMolecule, int64_t numConstraintIterations)
+{
+    MB_TRY(checkDevice());
+    MB_REQUIRE(out != nullptr && atomsPerMolecule > 0 && numConstraintIterations >= 0, "constraints_create");
+    auto* c = new mrmd_b200_constraints;
+    c->atomsPerMolecule = atomsPerMolecule;
+    c->numIterations = numConstraintIterations;
+    *out = c;
+    return 0;
+}
+
+int mrmd_b200_constraints_destroy(mrmd_b200_constraints* c)
+{
+    if (c == nullptr) return 0;
+    cudaDeviceSynchronize();
+    c->bondIdx.release();
+    c->bondDist.release();
+    c->updatedPos.release();
+    delete c;
+    return 0;
+}
+
+int mrmd_b200_constraints_set(mrmd_b200_constraints* c, const int64_t* idx, const int64_t* jdx, const double* eqDistance,
+                              int64_t numBonds)
+{
+    MB_TRY(checkDevice());
+    MB_REQUIRE(c != nullptr && numBonds >= 0 && (numBonds == 0 || (idx && jdx && eqDistance)), "constraints_set");
+    std::vector<long long> pairs(static_cast<size_t>(2 * numBonds));
+    for (int64_t b = 0; b < numBonds; ++b)
+    {
+        MB_REQUIRE(idx[b] >= 0 && jdx[b] >= 0, "constraints_set: negative atom index");
+        pairs[static_cast<size_t>(2 * b)] = idx[b];
+        pairs[static_cast<size_t>(2 * b + 1)] = jdx[b];
+    }
+    MB_TRY(c->bondIdx.reserve(std::max<size_t>(pairs.size() * 8, 16)));
+    MB_TRY(c->bondDist.reserve(std::max<size_t>(size_t(numBonds) * 8, 8)));
+    if (numBonds > 0)
+    {
+        MB_CUDA(cudaMemcpy(c->bondIdx.p, pairs.data(), pairs.size() * 8, cudaMemcpyHostToDevice));
+        MB_CUDA(cudaMemcpy(c->bondDist.p, eqDistance, size_t(numBonds) * 8, cudaMemcpyHostToDevice));
+    }
+    c->numBonds = numBonds;
+    return 0;
+}
+
+int mrmd_b200_constraints_enforce_positional(mrmd_b200_constraints* c, const mrmd_b200_molecules* m, mrmd_b200_atoms* a,
+                                             double dt, void* stream)
+{
+    MB_TRY(checkDevice());
+    MB_REQUIRE(c != nullptr && m != nullptr && a != nullptr, "constraints_enforce_positional");
+    cudaStream_t st = S(stream);
+    const int64_t nAll = a->numLocal + a->numGhost;
+    if (nAll == 0 || c->numIterations == 0) return 0;
+    MB_TRY(c->updatedPos.reserve(size_t(nAll) * 32));  // util::grow(updatedPos_, ...), Shake.hpp:146
+    const double dtv = dt, dtf = 0.5 * dt * dt;         // :148-149
+    int* dErr = nullptr;
+    MB_CUDA(cudaMalloc(&dErr, 4));
+    MB_CUDA(cudaMemsetAsync(dErr, 0, 4, st));
+    for (int64_t it = 0; it < c->numIterations; ++it)
+    {
+        shakeUnconstraintKernel<<<gridFor(nAll, 256), 256, 0, st>>>(a->v, nAll, dtv, dtf, c->updatedPos.as<double4>());
+        MB_LAUNCHED();
+        if (m->numLocal > 0 && c->numBonds > 0)
+        {
+            shakePositionalKernel<<<gridFor(m->numLocal, 128), 128, 0, st>>>(
+                m->v, a->v, m->numLocal, c->bondIdx.as<long long>(), c->bondDist.as<double>(), c->numBonds,
+                c->updatedPos.as<double4>(), dtf, dErr);
+            MB_LAUNCHED();
+        }
+    }
+    return checkBondError(dErr, st);
+}
+
+int mrmd_b200_constraints_enforce_velocity(mrmd_b200_constraints* c, const mrmd_b200_molecules* m, mrmd_b200_atoms* a,
+                                           double dt, void* stream)
+{
+    MB_TRY(checkDevice());
+    MB_REQUIRE(c != nullptr && m != nullptr && a != nullptr, "constraints_enforce_velocity");
+    (void)dt;  // Shake(atoms, dt) only feeds the positional update (Shake.hpp:139-150)
+    cudaStream_t st = S(stream);
+    if (m->numLocal == 0 || c->numBonds == 0) return 0;
+    int* dErr = nullptr;
+    MB_CUDA(cudaMalloc(&dErr, 4));
+    MB_CUDA(cudaMemsetAsync(dErr, 0, 4, st));
+    shakeVelocityKernel<<<gridFor(m->numLocal, 128), 128, 0, st>>>(m->v, a->v, m->numLocal, c->bondIdx.as<long long>(),
+                                                                   c->numBonds, dErr);
+    MB_LAUNCHED();
+    return checkBondError(dErr, st);
+}
+
+}  // extern "C"

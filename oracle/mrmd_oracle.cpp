@@ -1103,6 +1103,112 @@ void or_hist_smoothen(const double* in, double* out, double min, double max, int
         }
 }
 
+// action/BerendsenThermostat.cpp:25-50
+void or_berendsen_thermostat(or_atom_t* atoms, int64_t numLocal, double currentTemperature, double targetTemperature,
+                             double gamma)
+{
+    if (currentTemperature <= 0.0) return;
+    const double beta = std::sqrt(1.0 + gamma * (targetTemperature / currentTemperature - 1.0));
+    for (int64_t idx = 0; idx < numLocal; ++idx)
+        for (int d = 0; d < 3; ++d) atoms[idx].vel[d] *= beta;
+}
+
+// action/BerendsenBarostat.cpp:23-50
+void or_berendsen_barostat(or_atom_t* atoms, int64_t numLocal, double currentPressure, double targetPressure, double gamma,
+                           or_subdomain_t* s, int stretchX, int stretchY, int stretchZ)
+{
+    const double mu = std::cbrt(1.0 + gamma * (currentPressure - targetPressure));
+    const int stretch[3] = {stretchX, stretchY, stretchZ};
+    for (int d = 0; d < 3; ++d)
+        if (stretch[d]) or_subdomain_scale_dim(s, mu, d);
+    for (int64_t idx = 0; idx < numLocal; ++idx)
+        for (int d = 0; d < 3; ++d)
+            if (stretch[d]) atoms[idx].pos[d] *= mu;
+}
+
+// action/Shake.hpp:167-201 (MoleculeConstraints::enforcePositionalConstraints) with impl::Shake :84-137;
+// bonds: numBonds x {idx, jdx} relative to the molecule's first atom, eqDistance[numBonds]
+int or_shake_positional(const or_molecule_t* mols, int64_t numLocalMols, or_atom_t* atoms, int64_t numAllAtoms,
+                        const int64_t* bondIdx, const double* eqDistance, int64_t numBonds, int64_t numIterations,
+                        double dt)
+{
+    const double dtv = dt, dtf = 0.5 * dt * dt;
+    std::vector<double> updated(static_cast<size_t>(3 * numAllAtoms));
+    for (int64_t it = 0; it < numIterations; ++it)
+    {
+        for (int64_t idx = 0; idx < numAllAtoms; ++idx)
+        {
+            const double dtfm = dtf / atoms[idx].mass;
+            for (int d = 0; d < 3; ++d)
+                updated[3 * idx + d] = atoms[idx].pos[d] + dtv * atoms[idx].vel[d] + dtfm * atoms[idx].force[d];
+        }
+        for (int64_t mol = 0; mol < numLocalMols; ++mol)
+        {
+            const int64_t start = mols[mol].atomsOffset, count = mols[mol].numAtoms;
+            for (int64_t b = 0; b < numBonds; ++b)
+            {
+                if (bondIdx[2 * b] >= count || bondIdx[2 * b + 1] >= count) return -1;
+                const int64_t idx = start + bondIdx[2 * b], jdx = start + bondIdx[2 * b + 1];
+                double dist[3], upd[3];
+                for (int d = 0; d < 3; ++d)
+                {
+                    dist[d] = atoms[idx].pos[d] - atoms[jdx].pos[d];
+                    upd[d] = updated[3 * idx + d] - updated[3 * jdx + d];
+                }
+                const double distSq = dist[0] * dist[0] + dist[1] * dist[1] + dist[2] * dist[2];
+                const double updSq = upd[0] * upd[0] + upd[1] * upd[1] + upd[2] * upd[2];
+                const double invMassI = 1.0 / atoms[idx].mass, invMassJ = 1.0 / atoms[jdx].mass;
+                const double a = (invMassI + invMassJ) * (invMassI + invMassJ) * distSq;
+                const double bq = 2.0 * (invMassI + invMassJ) * (upd[0] * dist[0] + upd[1] * dist[1] + upd[2] * dist[2]);
+                const double c = updSq - eqDistance[b] * eqDistance[b];
+                double determinant = bq * bq - 4.0 * a * c;
+                determinant = std::max(0.0, determinant);
+                const double lambda1 = (-bq + std::sqrt(determinant)) / (2.0 * a);
+                const double lambda2 = (-bq - std::sqrt(determinant)) / (2.0 * a);
+                double lambda = std::abs(lambda1) < std::abs(lambda2) ? lambda1 : lambda2;
+                lambda /= dtf;
+                for (int d = 0; d < 3; ++d)
+                {
+                    atoms[idx].force[d] += lambda * dist[d];
+                    atoms[jdx].force[d] -= lambda * dist[d];
+                }
+            }
+        }
+    }
+    return 0;
+}
+
+// action/Shake.hpp:203-233 (enforceVelocityConstraints) with impl::Shake :56-82
+int or_shake_velocity(const or_molecule_t* mols, int64_t numLocalMols, or_atom_t* atoms, const int64_t* bondIdx,
+                      int64_t numBonds)
+{
+    for (int64_t mol = 0; mol < numLocalMols; ++mol)
+    {
+        const int64_t start = mols[mol].atomsOffset, count = mols[mol].numAtoms;
+        for (int64_t b = 0; b < numBonds; ++b)
+        {
+            if (bondIdx[2 * b] >= count || bondIdx[2 * b + 1] >= count) return -1;
+            const int64_t idx = start + bondIdx[2 * b], jdx = start + bondIdx[2 * b + 1];
+            double dist[3], relVel[3];
+            for (int d = 0; d < 3; ++d)
+            {
+                dist[d] = atoms[idx].pos[d] - atoms[jdx].pos[d];
+                relVel[d] = atoms[idx].vel[d] - atoms[jdx].vel[d];
+            }
+            const double distSq = dist[0] * dist[0] + dist[1] * dist[1] + dist[2] * dist[2];
+            const double invMassI = 1.0 / atoms[idx].mass, invMassJ = 1.0 / atoms[jdx].mass;
+            const double reducedMass = 1.0 / (invMassI + invMassJ);
+            const double factor = (relVel[0] * dist[0] + relVel[1] * dist[1] + relVel[2] * dist[2]) / distSq * reducedMass;
+            for (int d = 0; d < 3; ++d)
+            {
+                atoms[idx].vel[d] -= factor * dist[d] * invMassI;
+                atoms[jdx].vel[d] += factor * dist[d] * invMassJ;
+            }
+        }
+    }
+    return 0;
+}
+
 // analysis/KineticEnergy.hpp:26-39
 double or_kinetic_energy(const or_atom_t* atoms, int64_t numLocal)
 {

@@ -216,6 +216,15 @@ void or_hist_gradient(const double* in, double* out, double min, double max, int
                       int periodic);
 void or_hist_smoothen(const double* in, double* out, double min, double max, int64_t numBins, int64_t numHist,
                       double sigma, double range, int periodic);
+void or_berendsen_thermostat(or_atom_t* atoms, int64_t numLocal, double currentTemperature, double targetTemperature,
+                             double gamma);
+void or_berendsen_barostat(or_atom_t* atoms, int64_t numLocal, double currentPressure, double targetPressure, double gamma,
+                           or_subdomain_t* s, int stretchX, int stretchY, int stretchZ);
+int or_shake_positional(const or_molecule_t* mols, int64_t numLocalMols, or_atom_t* atoms, int64_t numAllAtoms,
+                        const int64_t* bondIdx, const double* eqDistance, int64_t numBonds, int64_t numIterations,
+                        double dt);
+int or_shake_velocity(const or_molecule_t* mols, int64_t numLocalMols, or_atom_t* atoms, const int64_t* bondIdx,
+                      int64_t numBonds);
 double or_kinetic_energy(const or_atom_t* atoms, int64_t numLocal);
 void or_system_momentum(const or_atom_t* atoms, int64_t numLocal, double* out3);
 double or_pressure(const or_atom_t* atoms, int64_t numAll, const or_subdomain_t* s);

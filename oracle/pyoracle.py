@@ -129,6 +129,11 @@ def lib():
         "or_hist_make_symmetric": (None, [vp, i64, i64]),
         "or_hist_gradient": (None, [vp, vp, C.c_double, C.c_double, i64, i64, C.c_int]),
         "or_hist_smoothen": (None, [vp, vp, C.c_double, C.c_double, i64, i64, C.c_double, C.c_double, C.c_int]),
+        "or_berendsen_thermostat": (None, [vp, i64, C.c_double, C.c_double, C.c_double]),
+        "or_berendsen_barostat": (None, [vp, i64, C.c_double, C.c_double, C.c_double, C.POINTER(Subdomain), C.c_int,
+                                        C.c_int, C.c_int]),
+        "or_shake_positional": (C.c_int, [vp, i64, vp, i64, vp, vp, i64, i64, C.c_double]),
+        "or_shake_velocity": (C.c_int, [vp, i64, vp, vp, i64]),
         "or_kinetic_energy": (C.c_double, [vp, i64]),
         "or_system_momentum": (None, [vp, i64, vp]),
         "or_pressure": (C.c_double, [vp, i64, vp]),

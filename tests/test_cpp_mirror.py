@@ -21,6 +21,10 @@ REFERENCE_HEADERS = [
     "action/VelocityVerletLangevinThermostat.hpp", "communication/GhostLayer.hpp",
     "communication/MultiResGhostLayer.hpp", "util/IsInSymmetricSlab.hpp", "weighting_function/Slab.hpp",
     "weighting_function/Spherical.hpp", "weighting_function/CheckRegion.hpp",
+    "analysis/KineticEnergy.hpp", "analysis/SystemMomentum.hpp", "analysis/Pressure.hpp",
+    "analysis/MeanSquareDisplacement.hpp", "io/RestoreGRO.hpp", "io/DumpGRO.hpp", "io/RestoreTXT.hpp",
+    "io/DumpThermoForce.hpp", "io/RestoreThermoForce.hpp", "action/BerendsenThermostat.hpp",
+    "action/BerendsenBarostat.hpp", "action/Shake.hpp", "data/Bond.hpp",
 ]
 
 
@@ -41,7 +45,7 @@ def test_reference_header_paths_exist():
         assert os.path.exists(os.path.join(INC, h)), h
 
 
-@pytest.mark.parametrize("name", ["lennard_jones_nve", "adress_ideal_gas", "restart_io"])
+@pytest.mark.parametrize("name", ["lennard_jones_nve", "adress_ideal_gas", "restart_io", "constraints_step"])
 def test_example_compiles_and_fails_loudly_without_gpu(name, tmp_path):
     import torch
 
@@ -159,6 +163,20 @@ def test_gro_restart_and_thermo_force_files(tmp_path, golden_dir):
     assert out["maxForceDiff"] <= 1e-3 and out["maxGridDiff"] <= 1e-5  # default ostream precision: 6 significant digits
     lines = open(tf).read().splitlines()
     assert len(lines) == 3 and len(lines[0].split()) == 100
+
+
+@pytest.mark.gpu
+def test_constrained_step(tmp_path):
+    """tests/Constraints/Constraints.cpp:25-72 of the reference through the mirror: after SHAKE + velocity Verlet +
+    RATTLE the bond has its length and no relative velocity along it; Berendsen calls as in tests/NVT, tests/NPT"""
+    exe = _compile("constraints_step", tmp_path)
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stderr[-2000:]
+    out = json.loads(res.stdout.strip().splitlines()[-1])
+    assert abs(out["dist"] - 1.0) < 1e-6  # EXPECT_FLOAT_EQ(calcDist(0, 1), 1_r)
+    assert abs(out["relVel"]) < 1e-6      # EXPECT_FLOAT_EQ(calcRelVel(0, 1) + 1_r, 1_r)
+    assert out["T0"] > 0 and abs(out["T1"] - 2.0 * out["T0"]) < 1e-12 * out["T0"]
+    assert np.isfinite(out["p"]) and abs(out["maxCorner"] - 2.0 * 2.0 ** (1.0 / 3.0)) < 1e-12
 
 
 @pytest.mark.gpu

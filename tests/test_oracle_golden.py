@@ -615,3 +615,79 @@ def test_analysis_kats(oracle):
     assert float_eq(L.or_msd(c.ctypes.data, init.ctypes.data, 1, C.byref(sub)), 16.0)
     c["vel"], c["force"], c["mass"] = [(1, 1, 1)], [(1, 0, -1)], 2.0
     assert float_eq(L.or_pressure(c.ctypes.data, 1, C.byref(sub)), (2 * 3 + (1 - 3)) / 3000.0)
+
+
+def _diamond(oracle):
+    """mrmd/test/DiamondFixture.hpp:26-106: two molecules of two atoms each"""
+    a = np.zeros(4, dtype=oracle.ATOM)
+    a["pos"] = [(1, 0, 0), (0, 1, 0), (-1, 0, 0), (0, -1, 0)]
+    a["mass"] = [1, 3, 1, 3]
+    a["relMass"] = [0.25, 0.75, 0.25, 0.75]
+    m = np.zeros(2, dtype=oracle.MOLECULE)
+    m["atomsOffset"], m["numAtoms"] = [0, 2], [2, 2]
+    return a, m
+
+
+def _integrate_position(a, dt):
+    """integratePosition of mrmd/action/Shake.test.cpp:27-46"""
+    a["pos"] += dt * a["vel"] + (0.5 * dt * dt / a["mass"])[:, None] * a["force"]
+
+
+def test_berendsen_and_shake_kats(oracle):
+    """row (f)2: mrmd/action/BerendsenThermostat.test.cpp:29-47, BerendsenBarostat.test.cpp:28-64,
+    Shake.test.cpp:59-249"""
+    import ctypes as C
+
+    L = oracle.lib()
+    one = np.zeros(1, dtype=oracle.ATOM)  # test::SingleAtom
+    one["pos"], one["vel"], one["force"], one["mass"] = [(2, 3, 4)], [(7, 5, 3)], [(9, 7, 8)], 1.5
+
+    def temperature(a):
+        return L.or_kinetic_energy(a.ctypes.data, 1) * (2.0 / 3.0)
+
+    a = one.copy()
+    L.or_berendsen_thermostat(a.ctypes.data, 1, temperature(a), 3.8, 0.0)
+    assert float_eq(temperature(a), 41.5)
+    L.or_berendsen_thermostat(a.ctypes.data, 1, temperature(a), 3.8, 1.0)
+    assert float_eq(temperature(a), 3.8)
+
+    a, sub = one.copy(), oracle.subdomain([0, 0, 0], [1, 1, 1], 0.1)
+    L.or_berendsen_barostat(a.ctypes.data, 1, 1.0, 3.8, 0.0, C.byref(sub), 1, 1, 1)
+    assert [float_eq(sub.maxCorner[d], 1.0) for d in range(3)] == [True] * 3 and np.allclose(a["pos"][0], [2, 3, 4])
+    L.or_berendsen_barostat(a.ctypes.data, 1, 2.0, 1.0, 1.0, C.byref(sub), 1, 1, 1)
+    mu = 2.0 ** (1.0 / 3.0)
+    assert all(float_eq(sub.maxCorner[d], mu) for d in range(3))
+    assert all(float_eq(a["pos"][0][d], w * mu) for d, w in enumerate((2, 3, 4)))
+
+    dt = 0.1
+    whole = np.zeros(1, dtype=oracle.MOLECULE)
+    whole["atomsOffset"], whole["numAtoms"] = 0, 4
+
+    def dist(a, i, j):
+        return float(np.linalg.norm(a["pos"][i] - a["pos"][j]))
+
+    for eq, sign in ((1.0, -1.0), (2.0, 1.0)):  # Attraction / Repulsion: one constraint between atoms 0 and 1
+        a, _ = _diamond(oracle)
+        bonds, eqs = np.array([0, 1], dtype=np.int64), np.array([eq])
+        assert L.or_shake_positional(whole.ctypes.data, 1, a.ctypes.data, 4, bonds.ctypes.data, eqs.ctypes.data, 1, 1, dt) == 0
+        assert np.allclose(a["force"][0], -a["force"][1]) and sign * a["force"][0][0] > 0 and sign * a["force"][0][1] < 0
+        _integrate_position(a, dt)
+        assert float_eq(dist(a, 0, 1), eq)
+    for eq in (1.0, 2.0):  # Shrink / Grow: the ring 0-1-2-3-0, ten iterations
+        a, _ = _diamond(oracle)
+        bonds, eqs = np.array([0, 1, 1, 2, 2, 3, 3, 0], dtype=np.int64), np.full(4, eq)
+        assert L.or_shake_positional(whole.ctypes.data, 1, a.ctypes.data, 4, bonds.ctypes.data, eqs.ctypes.data, 4, 10, dt) == 0
+        _integrate_position(a, dt)
+        assert all(float_eq(dist(a, i, (i + 1) % 4), eq) for i in range(4))
+    a, m = _diamond(oracle)  # Molecules: the bond 0-1 in both molecules
+    bonds, eqs = np.array([0, 1], dtype=np.int64), np.array([1.0])
+    assert L.or_shake_positional(m.ctypes.data, 2, a.ctypes.data, 4, bonds.ctypes.data, eqs.ctypes.data, 1, 1, dt) == 0
+    f = a["force"]
+    assert np.allclose(f[0], -f[1]) and f[0][0] < 0 < f[0][1] and np.allclose(f[2], -f[3]) and f[2][0] > 0 > f[2][1]
+    # RATTLE: after the projection the relative velocity has no component along the bond
+    a["vel"] = [(1, 2, 3), (-1, 0.5, 0), (0, 0, 1), (2, 2, 2)]
+    assert L.or_shake_velocity(m.ctypes.data, 2, a.ctypes.data, bonds.ctypes.data, 1) == 0
+    for i, j in ((0, 1), (2, 3)):
+        assert abs(np.dot(a["vel"][i] - a["vel"][j], a["pos"][i] - a["pos"][j])) < 1e-14
+    bad = np.array([0, 2], dtype=np.int64)  # MRMD_DEVICE_ASSERT_LESS: not enough atoms in molecule to satisfy bond
+    assert L.or_shake_velocity(m.ctypes.data, 2, a.ctypes.data, bad.ctypes.data, 1) == -1
