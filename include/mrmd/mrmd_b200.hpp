@@ -863,6 +863,102 @@ public:
 private:
     std::shared_ptr<mrmd_b200_constraints> h_;
 };
+
+namespace impl
+{
+/// action::impl::Coulomb (action/Coulomb.hpp:27-46), evaluated on the device
+class Coulomb
+{
+public:
+    real_t computeForce(const real_t& distSqr, const real_t q1, const real_t q2) const { return eval(distSqr, q1, q2, true); }
+    real_t computeEnergy(const real_t& distSqr, const real_t q1, const real_t q2) const { return eval(distSqr, q1, q2, false); }
+
+protected:
+    real_t eval(const real_t distSqr, const real_t q1, const real_t q2, const bool force) const
+    {
+        real_t f = 0_r, e = 0_r;
+        detail::check(mrmd_b200_coulomb_eval(kind_, rc_, alpha_, &distSqr, 1, q1, q2, &f, &e, defaultStream), "Coulomb");
+        return force ? f : e;
+    }
+    int kind_ = MRMD_B200_COULOMB_PLAIN;
+    real_t rc_ = 0_r, alpha_ = 0_r;
+};
+
+/// action::impl::CoulombDSF (action/CoulombDSF.hpp:42-84)
+class CoulombDSF : public Coulomb
+{
+public:
+    CoulombDSF(const real_t& rc, const real_t& alpha)
+    {
+        kind_ = MRMD_B200_COULOMB_DSF;
+        rc_ = rc;
+        alpha_ = alpha;
+    }
+};
+}  // namespace impl
+
+/// action::SPC (action/SPC.hpp:61-362)
+class SPC
+{
+public:
+    real_t sumEnergyLJ_ = 0_r;
+    real_t sumEnergyCoulomb_ = 0_r;
+    auto getEnergyLJ() const { return sumEnergyLJ_; }
+    auto getEnergyCoulomb() const { return sumEnergyCoulomb_; }
+
+    static constexpr real_t massO = 15.999_r;
+    static constexpr real_t chargeO = -0.82_r;
+    static constexpr real_t massH = 1.008_r;
+    static constexpr real_t chargeH = +0.41_r;
+    static constexpr real_t sigma = 0.31655578901998815_r;
+    static constexpr real_t epsilon = 0.6501695808187486_r;
+    static constexpr real_t rc = 1.2_r;
+    static constexpr real_t alpha = 2.0_r;
+    static constexpr real_t eqDistanceHO = 0.1_r;
+    static constexpr real_t angleHOH = 109.47_r / 180_r * 3.14159265358979323846;  // util::degToRad(109.47_r)
+    const real_t eqDistanceHH = eqDistanceHO * std::sqrt(2_r - 2_r * std::cos(angleHOH));
+
+    /// coulombKind MRMD_B200_COULOMB_PLAIN is the reference's member; MRMD_B200_COULOMB_DSF is an extension
+    explicit SPC(int coulombKind = MRMD_B200_COULOMB_PLAIN)
+    {
+        mrmd_b200_spc* h = nullptr;
+        detail::check(mrmd_b200_spc_create(&h, coulombKind), "SPC");
+        h_.reset(h, [](mrmd_b200_spc* p) { mrmd_b200_spc_destroy(p); });
+    }
+    void applyForces(data::Molecules& molecules, HalfVerletList& verletList, data::Atoms& atoms)
+    {
+        molecules.push();
+        atoms.push();
+        detail::check(mrmd_b200_spc_apply_forces(h_.get(), molecules.handle(), verletList.handle(), atoms.handle(), &sumEnergyLJ_,
+                                                 &sumEnergyCoulomb_, defaultStream), "SPC::applyForces");
+    }
+    real_t calcBondEnergy(data::Molecules& molecules, data::Atoms& atoms, const real_t& harmonicPreFactor)
+    {
+        molecules.push();
+        atoms.push();
+        real_t e = 0_r;
+        detail::check(mrmd_b200_spc_calc_bond_energy(h_.get(), molecules.handle(), atoms.handle(), harmonicPreFactor, &e, defaultStream),
+                      "SPC::calcBondEnergy");
+        return e;
+    }
+    void enforcePositionalConstraints(data::Molecules& molecules, data::Atoms& atoms, real_t dt)
+    {
+        molecules.push();
+        atoms.push();
+        detail::check(mrmd_b200_spc_enforce_positional_constraints(h_.get(), molecules.handle(), atoms.handle(), dt, defaultStream),
+                      "SPC::enforcePositionalConstraints");
+    }
+    void enforceVelocityConstraints(data::Molecules& molecules, data::Atoms& atoms, real_t dt)
+    {
+        molecules.push();
+        atoms.push();
+        detail::check(mrmd_b200_spc_enforce_velocity_constraints(h_.get(), molecules.handle(), atoms.handle(), dt, defaultStream),
+                      "SPC::enforceVelocityConstraints");
+    }
+
+private:
+    std::shared_ptr<mrmd_b200_spc> h_;
+};
 }  // namespace action
 
 // ------------------------------------------------------------------------------------------------------

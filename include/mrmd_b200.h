@@ -380,6 +380,35 @@ int mrmd_b200_constraints_enforce_positional(mrmd_b200_constraints* c, const mrm
 int mrmd_b200_constraints_enforce_velocity(mrmd_b200_constraints* c, const mrmd_b200_molecules* m, mrmd_b200_atoms* a,
                                            double dt, void* stream);
 
+/* ---- SPC water and the Coulomb pair potentials (action/SPC.hpp, Coulomb.hpp, CoulombDSF.hpp) ------------------- */
+typedef struct mrmd_b200_spc mrmd_b200_spc; /* action::SPC (action/SPC.hpp:61-362) */
+#define MRMD_B200_COULOMB_PLAIN 0 /* impl::Coulomb    (action/Coulomb.hpp:27-46): the member SPC holds */
+#define MRMD_B200_COULOMB_DSF 1   /* impl::CoulombDSF (action/CoulombDSF.hpp:42-84), approxErfc of util/math.hpp:57-76 */
+/* computeForce / computeEnergy of the chosen potential for n squared distances (host arrays), evaluated on the device;
+ * rc and alpha are the CoulombDSF constructor's arguments (ignored for the plain potential) */
+int mrmd_b200_coulomb_eval(int kind, double rc, double alpha, const double* distSqrHost, int64_t n, double q1, double q2,
+                           double* forceHost, double* energyHost, void* stream);
+/* SPC() (:346-362): capped (0.7 sigma), shifted O-O Lennard-Jones with rc = 1.2 nm, the three bonds H-O, H-O, H-H.
+ * coulombKind MRMD_B200_COULOMB_PLAIN reproduces the reference; MRMD_B200_COULOMB_DSF evaluates the charges with
+ * CoulombDSF(rc, alpha = 2 / nm) (the parameters SPC.hpp:110 declares) instead. */
+int mrmd_b200_spc_create(mrmd_b200_spc** out, int coulombKind);
+int mrmd_b200_spc_destroy(mrmd_b200_spc* spc);
+/* replaces SPC::applyForces(molecules, verletList, atoms) (:252-282, kernel :143-236): for every pair of the half
+ * Verlet list of molecules O-O Lennard-Jones between the first atoms (distSqr < rc^2) and Coulomb between all atom
+ * pairs (skipped for distSqr > rc^2), accumulated into the atoms' forces; getEnergyLJ / getEnergyCoulomb come back
+ * through the pointers (either may be NULL; both NULL skips the read-back and the fence) */
+int mrmd_b200_spc_apply_forces(mrmd_b200_spc* spc, const mrmd_b200_molecules* m, const mrmd_b200_verlet* v,
+                               mrmd_b200_atoms* a, double* energyLJ, double* energyCoulomb, void* stream);
+/* replaces SPC::calcBondEnergy (:284-344): harmonicPreFactor * sum over local + ghost molecules of the squared
+ * deviations of |O-H0|, |O-H1|, |H0-H1| from their equilibrium lengths / (local + ghost atoms) */
+int mrmd_b200_spc_calc_bond_energy(mrmd_b200_spc* spc, const mrmd_b200_molecules* m, const mrmd_b200_atoms* a,
+                                   double harmonicPreFactor, double* bondEnergy, void* stream);
+/* replace SPC::enforcePositionalConstraints / enforceVelocityConstraints (:238-250): MoleculeConstraints(3, 20) */
+int mrmd_b200_spc_enforce_positional_constraints(mrmd_b200_spc* spc, const mrmd_b200_molecules* m, mrmd_b200_atoms* a,
+                                                 double dt, void* stream);
+int mrmd_b200_spc_enforce_velocity_constraints(mrmd_b200_spc* spc, const mrmd_b200_molecules* m, mrmd_b200_atoms* a,
+                                               double dt, void* stream);
+
 /* ---- step loop of the reference's drivers ----------------------------------------------------
  * The hot loop of examples/02_LennardJones_NVE.cpp:135-216 (rebuild policy :141-171), with the Langevin
  * integrator of examples/01_LennardJones_NVT.cpp:121,142 and the LinkedCellList + permute spatial sort of

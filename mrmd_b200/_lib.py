@@ -148,6 +148,13 @@ SIGNATURES = {
     "mrmd_b200_constraints_set": (C.c_int, [vp, vp, vp, vp, i64]),
     "mrmd_b200_constraints_enforce_positional": (C.c_int, [vp, vp, vp, dbl, vp]),
     "mrmd_b200_constraints_enforce_velocity": (C.c_int, [vp, vp, vp, dbl, vp]),
+    "mrmd_b200_coulomb_eval": (C.c_int, [C.c_int, dbl, dbl, vp, i64, dbl, dbl, vp, vp, vp]),
+    "mrmd_b200_spc_create": (C.c_int, [pvp, C.c_int]),
+    "mrmd_b200_spc_destroy": (C.c_int, [vp]),
+    "mrmd_b200_spc_apply_forces": (C.c_int, [vp, vp, vp, vp, pdbl, pdbl, vp]),
+    "mrmd_b200_spc_calc_bond_energy": (C.c_int, [vp, vp, vp, dbl, pdbl, vp]),
+    "mrmd_b200_spc_enforce_positional_constraints": (C.c_int, [vp, vp, vp, dbl, vp]),
+    "mrmd_b200_spc_enforce_velocity_constraints": (C.c_int, [vp, vp, vp, dbl, vp]),
     "mrmd_b200_md_create": (C.c_int, [pvp, C.POINTER(MdConfig), pSub, vp]),
     "mrmd_b200_md_destroy": (C.c_int, [vp]),
     "mrmd_b200_md_run": (C.c_int, [vp, i64, C.c_int, C.POINTER(MdStats), vp]),

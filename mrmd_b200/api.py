@@ -674,6 +674,89 @@ class MoleculeConstraints:
                 pass
 
 
+class Coulomb:
+    """action::impl::Coulomb (action/Coulomb.hpp:27-46)"""
+
+    kind = 0
+
+    def __init__(self):
+        self.rc, self.alpha = 0.0, 0.0
+
+    def _eval(self, distSqr, q1, q2, stream=None):
+        d = np.ascontiguousarray(np.atleast_1d(np.asarray(distSqr, dtype=np.float64)))
+        f, e = np.zeros_like(d), np.zeros_like(d)
+        check(L().mrmd_b200_coulomb_eval(self.kind, self.rc, self.alpha, d.ctypes.data, d.size, q1, q2, f.ctypes.data,
+                                         e.ctypes.data, _stream(stream)))
+        return f, e
+
+    def computeForce(self, distSqr, q1, q2):
+        f = self._eval(distSqr, q1, q2)[0]
+        return f if np.ndim(distSqr) else float(f[0])
+
+    def computeEnergy(self, distSqr, q1, q2):
+        e = self._eval(distSqr, q1, q2)[1]
+        return e if np.ndim(distSqr) else float(e[0])
+
+
+class CoulombDSF(Coulomb):
+    """action::impl::CoulombDSF(rc, alpha) (action/CoulombDSF.hpp:42-84)"""
+
+    kind = 1
+
+    def __init__(self, rc, alpha):
+        self.rc, self.alpha = float(rc), float(alpha)
+
+
+class SPC:
+    """action::SPC (action/SPC.hpp:61-362).  coulombKind 0 is the reference's impl::Coulomb member, 1 evaluates the
+    charges with CoulombDSF(rc, alpha)."""
+
+    massO, chargeO = 15.999, -0.82
+    massH, chargeH = 1.008, +0.41
+    sigma, epsilon, rc = 0.31655578901998815, 0.6501695808187486, 1.2
+    alpha = 2.0
+    eqDistanceHO = 0.1
+    angleHOH = 109.47 / 180.0 * np.pi
+
+    def __init__(self, coulombKind=0):
+        self.h = C.c_void_p()
+        check(L().mrmd_b200_spc_create(C.byref(self.h), int(coulombKind)))
+        self.eqDistanceHH = self.eqDistanceHO * float(np.sqrt(2.0 - 2.0 * np.cos(self.angleHOH)))
+        self.sumEnergyLJ_ = 0.0
+        self.sumEnergyCoulomb_ = 0.0
+
+    def applyForces(self, molecules, verletList, atoms, stream=None):
+        eLJ, eC = C.c_double(), C.c_double()
+        check(L().mrmd_b200_spc_apply_forces(self.h, molecules.h, verletList.h, atoms.h, C.byref(eLJ), C.byref(eC),
+                                             _stream(stream)))
+        self.sumEnergyLJ_, self.sumEnergyCoulomb_ = eLJ.value, eC.value
+
+    def getEnergyLJ(self):
+        return self.sumEnergyLJ_
+
+    def getEnergyCoulomb(self):
+        return self.sumEnergyCoulomb_
+
+    def calcBondEnergy(self, molecules, atoms, harmonicPreFactor, stream=None):
+        e = C.c_double()
+        check(L().mrmd_b200_spc_calc_bond_energy(self.h, molecules.h, atoms.h, harmonicPreFactor, C.byref(e), _stream(stream)))
+        return e.value
+
+    def enforcePositionalConstraints(self, molecules, atoms, dt, stream=None):
+        check(L().mrmd_b200_spc_enforce_positional_constraints(self.h, molecules.h, atoms.h, dt, _stream(stream)))
+
+    def enforceVelocityConstraints(self, molecules, atoms, dt, stream=None):
+        check(L().mrmd_b200_spc_enforce_velocity_constraints(self.h, molecules.h, atoms.h, dt, _stream(stream)))
+
+    def __del__(self):
+        h, self.h = getattr(self, "h", None), None
+        if h:
+            try:
+                L().mrmd_b200_spc_destroy(h)
+            except Exception:
+                pass
+
+
 class analysis:
     """namespace mrmd::analysis: the diagnostics of the drivers' statistics lines (examples/02:190-199)"""
 

@@ -188,3 +188,96 @@ class OracleAdressMD:
         dt = time.perf_counter() - t0
         return {"seconds": dt, "steps": nsteps, "pairInteractions": self.pairs - p0, "rebuilds": self.rebuilds - r0,
                 "energy": float(self.energy)}
+
+
+def spc_water_box(sites, spacing=0.31, jitter=0.02, seed=5):
+    """sites^3 SPC molecules in their equilibrium geometry (mrmd/action/SPC.test.cpp:51-96) on a jittered lattice, each
+    turned about z by a random angle; returns pos[3M,3], vel[3M,3], mass, charge, relMass, type, box"""
+    rng = np.random.default_rng(seed)
+    m = sites ** 3
+    eq_ho, angle = 0.1, 109.47 / 180.0 * np.pi
+    g = (np.stack(np.meshgrid(*[np.arange(sites)] * 3, indexing="ij"), axis=-1).reshape(-1, 3) + 0.5) * spacing
+    o = g + (rng.random((m, 3)) - 0.5) * jitter
+    phi = rng.random(m) * 2 * np.pi
+    h0 = o + eq_ho * np.stack([np.cos(phi), np.sin(phi), np.zeros(m)], axis=1)
+    h1 = o + eq_ho * np.stack([np.cos(phi + angle), np.sin(phi + angle), np.zeros(m)], axis=1)
+    pos = np.stack([o, h0, h1], axis=1).reshape(-1, 3)
+    vel = np.repeat((rng.random((m, 3)) - 0.5) * 0.5, 3, axis=0)  # rigid translation: no velocity along the bonds
+    mass = np.tile([15.999, 1.008, 1.008], m)
+    charge = np.tile([-0.82, 0.41, 0.41], m)
+    typ = np.tile([0, 1, 1], m).astype(np.int64)
+    return pos, vel, mass, charge, mass / (15.999 + 2 * 1.008), typ, np.full(3, sites * spacing)
+
+
+class OracleSpcMD:
+    """A constrained SPC water step driven through the CPU oracle: SHAKE -> velocity Verlet -> MultiResGhostLayer ->
+    UpdateMolecules -> SPC::applyForces -> RATTLE, the call order of the reference's tests/Constraints/Constraints.cpp:
+    25-72 around the AdResS-style molecule loop.  Three atoms per molecule, no spatial sort."""
+
+    SPC_RC = 1.2
+
+    def __init__(self, pos, vel, mass, charge, rel_mass, typ, box, dt=0.0005, skin=0.1, max_neigh=220, coulomb_kind=0):
+        self.L = orc.lib()
+        self.n = n = len(pos)
+        self.nm = nm = n // 3
+        self.box = np.asarray(box, dtype=np.float64)
+        self.cutoff = self.SPC_RC + skin
+        self.sub = orc.subdomain([0, 0, 0], self.box, self.cutoff)
+        frac = float(np.prod(self.box + 2 * self.cutoff) / np.prod(self.box)) - 1.0
+        cap_mols = int(nm * (1.0 + 1.3 * frac + 0.05)) + 1024
+        self.atoms = np.zeros(3 * cap_mols, dtype=orc.ATOM)
+        a = self.atoms
+        a["pos"][:n], a["vel"][:n], a["mass"][:n], a["charge"][:n] = pos, vel, mass, charge
+        a["relMass"][:n], a["type"][:n] = rel_mass, typ
+        self.mols = np.zeros(cap_mols, dtype=orc.MOLECULE)
+        self.mols["atomsOffset"][:nm], self.mols["numAtoms"][:nm] = np.arange(nm) * 3, 3
+        self.corr = np.full(3 * cap_mols, -1, dtype=np.int64)
+        self.weight = orc.make_weight(orc.WEIGHT_SLAB, 0.5 * self.box, 10.0 * float(self.box[0]), 1.0, 7)  # lambda = 1
+        eq_ho, angle = 0.1, 109.47 / 180.0 * np.pi
+        self.bond_idx = np.array([0, 1, 0, 2, 1, 2], dtype=np.int64)
+        self.bond_eq = np.array([eq_ho, eq_ho, eq_ho * np.sqrt(2.0 - 2.0 * np.cos(angle))])
+        self.dt, self.skin, self.max_neigh, self.kind = dt, skin, max_neigh, coulomb_kind
+        self.max_disp = np.finfo(np.float64).max
+        self.step = self.ng = self.mg = self.rebuilds = 0
+        self.energies = np.zeros(2)
+
+    def _rebuild(self):
+        L, a, m, n, nm = self.L, self.atoms, self.mols, self.n, self.nm
+        L.or_update_molecules(m.ctypes.data, nm, a.ctypes.data, C.byref(self.weight))
+        L.or_mr_periodic_map(m.ctypes.data, nm, a.ctypes.data, C.byref(self.sub))
+        out = np.zeros(2, dtype=np.int64)
+        rc = L.or_mr_ghost_create_xyz(m.ctypes.data, nm, len(m), a.ctypes.data, n, len(a), C.byref(self.sub),
+                                      self.corr.ctypes.data, out.ctypes.data)
+        assert rc == 0, "oracle ghost capacity exceeded"
+        self.mg, self.ng = int(out[0]), int(out[1])
+        L.or_update_molecules(m.ctypes.data, nm + self.mg, a.ctypes.data, C.byref(self.weight))
+        self.counts, self.neigh = orc.verlet_build(m, 13, nm + self.mg, 0, nm, self.cutoff, 1.0,
+                                                   np.array(self.sub.minGhostCorner), np.array(self.sub.maxGhostCorner),
+                                                   half=True, width=self.max_neigh)
+        self.rebuilds += 1
+
+    def one_step(self):
+        L, a, m, n, nm = self.L, self.atoms, self.mols, self.n, self.nm
+        assert L.or_shake_positional(m.ctypes.data, nm, a.ctypes.data, n + self.ng, self.bond_idx.ctypes.data,
+                                     self.bond_eq.ctypes.data, 3, 20, self.dt) == 0
+        self.max_disp += L.or_vv_pre(a.ctypes.data, n, self.dt)
+        if self.max_disp >= self.skin * 0.5:
+            self.max_disp = 0.0
+            self._rebuild()
+        else:
+            L.or_ghost_update_pos(a.ctypes.data, n, self.ng, self.corr.ctypes.data, C.byref(self.sub))
+            L.or_update_molecules(m.ctypes.data, nm + self.mg, a.ctypes.data, C.byref(self.weight))
+        L.or_zero_force(a.ctypes.data, n + self.ng)
+        L.or_spc_apply_forces(m.ctypes.data, nm, self.counts.ctypes.data, self.neigh.ctypes.data, self.neigh.shape[1],
+                              a.ctypes.data, self.kind, self.energies.ctypes.data)
+        L.or_ghost_fold_force(a.ctypes.data, n, self.ng, self.corr.ctypes.data)
+        L.or_vv_post(a.ctypes.data, n, self.dt)
+        assert L.or_shake_velocity(m.ctypes.data, nm, a.ctypes.data, self.bond_idx.ctypes.data, 3) == 0
+        self.step += 1
+
+    def run(self, nsteps):
+        t0 = time.perf_counter()
+        for _ in range(nsteps):
+            self.one_step()
+        return {"seconds": time.perf_counter() - t0, "steps": nsteps, "rebuilds": self.rebuilds,
+                "energyLJ": float(self.energies[0]), "energyCoulomb": float(self.energies[1])}

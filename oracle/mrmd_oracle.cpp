@@ -19,6 +19,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <numbers>
 #include <vector>
 
 namespace
@@ -1207,6 +1208,162 @@ int or_shake_velocity(const or_molecule_t* mols, int64_t numLocalMols, or_atom_t
         }
     }
     return 0;
+}
+
+// ---------------------------------------------------------------------------
+// util/math.hpp:57-76 (Abramowitz & Stegun 7.1.27; returns exp(-x^2) through expX2)
+static inline double approxErfc(double x, double& expX2)
+{
+    constexpr double p = 0.3275911;
+    constexpr double a1 = 0.254829592;
+    constexpr double a2 = -0.284496736;
+    constexpr double a3 = 1.421413741;
+    constexpr double a4 = -1.453152027;
+    constexpr double a5 = 1.061405429;
+    const double t = 1.0 / (1.0 + p * x);
+    expX2 = std::exp(-x * x);
+    return t * (a1 + t * (a2 + t * (a3 + t * (a4 + t * a5)))) * expX2;
+}
+
+double or_approx_erfc(double x)
+{
+    double tmp;
+    return approxErfc(x, tmp);
+}
+
+// action/Coulomb.hpp:27-46 (kind 0) and action/CoulombDSF.hpp:42-84 (kind 1)
+struct CoulombParams
+{
+    int kind;
+    double alpha, rc, forceShift, energyShift;
+};
+static CoulombParams coulombInit(int kind, double rc, double alpha)
+{
+    CoulombParams c{kind, alpha, rc, 0.0, 0.0};
+    if (kind == 1)
+    {
+        const double rcSqr = rc * rc;
+        const double erfc = std::erfc(alpha * rc);
+        const double ex = std::exp(-alpha * alpha * rcSqr);
+        c.forceShift = -(erfc / rcSqr + 2.0 * std::numbers::inv_sqrtpi_v<double> * alpha * ex / rc);
+        c.energyShift = erfc / rc;
+    }
+    return c;
+}
+static inline double coulombForce(const CoulombParams& c, double distSqr, double q1, double q2)
+{
+    const double prefac = 138.935458 * q1 * q2;
+    if (c.kind == 0) return prefac / distSqr;
+    const double r = std::sqrt(distSqr);
+    double expX2;
+    const double erfc = approxErfc(c.alpha * r, expX2);
+    const double force = prefac * (erfc / r + 2.0 * c.alpha * std::numbers::inv_sqrtpi_v<double> * expX2 + r * c.forceShift);
+    return force / distSqr;
+}
+static inline double coulombEnergy(const CoulombParams& c, double distSqr, double q1, double q2)
+{
+    const double r = std::sqrt(distSqr);
+    const double prefac = 138.935458 * q1 * q2;
+    if (c.kind == 0) return prefac / r;
+    double tmp;
+    const double erfc = approxErfc(c.alpha * r, tmp);
+    return prefac * (erfc / r - c.energyShift - c.forceShift * (r - c.rc));
+}
+
+void or_coulomb_eval(int kind, double rc, double alpha, const double* distSqr, int64_t n, double q1, double q2,
+                     double* force, double* energy)
+{
+    const CoulombParams c = coulombInit(kind, rc, alpha);
+    for (int64_t i = 0; i < n; ++i)
+    {
+        force[i] = coulombForce(c, distSqr[i], q1, q2);
+        energy[i] = coulombEnergy(c, distSqr[i], q1, q2);
+    }
+}
+
+// action/SPC.hpp:143-236 (operator()(CalcInteractions) + applyForces): capped, shifted O-O Lennard-Jones between the
+// first atoms of two molecules (strict <) and Coulomb between all atom pairs (skipped only for >); energies[0] = LJ,
+// energies[1] = Coulomb.  coulombKind 0 is the reference's impl::Coulomb member; 1 swaps in CoulombDSF(rc, alpha).
+void or_spc_apply_forces(const or_molecule_t* mols, int64_t numLocalMols, const int32_t* counts, const int32_t* neigh,
+                         int64_t width, or_atom_t* atoms, int coulombKind, double* energies)
+{
+    constexpr double sigma = 0.31655578901998815, epsilon = 0.6501695808187486, rc = 1.2, alpha = 2.0;  // :105-110
+    const double cap = 0.7 * sigma;
+    or_lj_type_t lj;
+    or_lj_init(&lj, &cap, &rc, &sigma, &epsilon, 1, 1);  // SPC(): LJ_({0.7 sigma}, {rc}, {sigma}, {epsilon}, 1, true)
+    const CoulombParams cp = coulombInit(coulombKind, rc, alpha);
+    const double rcSqr = rc * rc;
+    double eLJ = 0.0, eC = 0.0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : eLJ, eC)
+    for (int64_t a = 0; a < numLocalMols; ++a)
+    {
+        const int64_t numNeighbors = counts[a];
+        for (int64_t n = 0; n < numNeighbors; ++n)
+        {
+            const int64_t b = neigh[a * width + n];
+            const int64_t startA = mols[a].atomsOffset, endA = startA + mols[a].numAtoms;
+            const int64_t startB = mols[b].atomsOffset, endB = startB + mols[b].numAtoms;
+            {
+                const double dx[3] = {atoms[startA].pos[0] - atoms[startB].pos[0], atoms[startA].pos[1] - atoms[startB].pos[1],
+                                      atoms[startA].pos[2] - atoms[startB].pos[2]};
+                const double distSqr = dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2];
+                if (distSqr < rcSqr)
+                {
+                    double ff, e;
+                    ljForceEnergy(lj, distSqr, ff, e);
+                    eLJ += e;
+                    for (int d = 0; d < 3; ++d) atomicAdd(atoms[startB].force[d], -(dx[d] * ff));
+                    for (int d = 0; d < 3; ++d) atomicAdd(atoms[startA].force[d], dx[d] * ff);
+                }
+            }
+            for (int64_t idx = startA; idx < endA; ++idx)
+            {
+                const double q1 = atoms[idx].charge;
+                double forceTmpIdx[3] = {0.0, 0.0, 0.0};
+                for (int64_t jdx = startB; jdx < endB; ++jdx)
+                {
+                    const double q2 = atoms[jdx].charge;
+                    const double dx[3] = {atoms[idx].pos[0] - atoms[jdx].pos[0], atoms[idx].pos[1] - atoms[jdx].pos[1],
+                                          atoms[idx].pos[2] - atoms[jdx].pos[2]};
+                    const double distSqr = dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2];
+                    if (distSqr > rcSqr) continue;
+                    const double ffactor = coulombForce(cp, distSqr, q1, q2);
+                    eC += coulombEnergy(cp, distSqr, q1, q2);
+                    for (int d = 0; d < 3; ++d) forceTmpIdx[d] += dx[d] * ffactor;
+                    for (int d = 0; d < 3; ++d) atomicAdd(atoms[jdx].force[d], -(dx[d] * ffactor));
+                }
+                for (int d = 0; d < 3; ++d) atomicAdd(atoms[idx].force[d], forceTmpIdx[d]);
+            }
+        }
+    }
+    energies[0] = eLJ;
+    energies[1] = eC;
+}
+
+// action/SPC.hpp:284-344 (BondEnergy + calcBondEnergy): O, H0, H1 are the first three atoms of every molecule
+double or_spc_bond_energy(const or_molecule_t* mols, int64_t numAllMols, const or_atom_t* atoms, int64_t numAllAtoms,
+                          double harmonicPreFactor)
+{
+    constexpr double eqDistanceHO = 0.1;
+    const double angleHOH = 109.47 / 180.0 * M_PI;  // util/angle.hpp:28
+    const double eqDistanceHH = eqDistanceHO * std::sqrt(2.0 - 2.0 * std::cos(angleHOH));
+    double energy = 0.0;
+    auto dist = [&](int64_t i, int64_t j)
+    {
+        const double dx[3] = {atoms[i].pos[0] - atoms[j].pos[0], atoms[i].pos[1] - atoms[j].pos[1], atoms[i].pos[2] - atoms[j].pos[2]};
+        return std::sqrt(dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2]);
+    };
+    for (int64_t m = 0; m < numAllMols; ++m)
+    {
+        const int64_t o = mols[m].atomsOffset, h0 = o + 1, h1 = o + 2;
+        double d = dist(o, h0) - eqDistanceHO;
+        energy += d * d;
+        d = dist(o, h1) - eqDistanceHO;
+        energy += d * d;
+        d = dist(h0, h1) - eqDistanceHH;
+        energy += d * d;
+    }
+    return harmonicPreFactor * energy / double(numAllAtoms);
 }
 
 // analysis/KineticEnergy.hpp:26-39

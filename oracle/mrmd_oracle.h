@@ -225,6 +225,14 @@ int or_shake_positional(const or_molecule_t* mols, int64_t numLocalMols, or_atom
                         double dt);
 int or_shake_velocity(const or_molecule_t* mols, int64_t numLocalMols, or_atom_t* atoms, const int64_t* bondIdx,
                       int64_t numBonds);
+/* util/math.hpp:57-76, action/Coulomb.hpp:27-46 (kind 0), action/CoulombDSF.hpp:42-84 (kind 1), action/SPC.hpp:143-344 */
+double or_approx_erfc(double x);
+void or_coulomb_eval(int kind, double rc, double alpha, const double* distSqr, int64_t n, double q1, double q2,
+                     double* force, double* energy);
+void or_spc_apply_forces(const or_molecule_t* mols, int64_t numLocalMols, const int32_t* counts, const int32_t* neigh,
+                         int64_t width, or_atom_t* atoms, int coulombKind, double* energies);
+double or_spc_bond_energy(const or_molecule_t* mols, int64_t numAllMols, const or_atom_t* atoms, int64_t numAllAtoms,
+                          double harmonicPreFactor);
 double or_kinetic_energy(const or_atom_t* atoms, int64_t numLocal);
 void or_system_momentum(const or_atom_t* atoms, int64_t numLocal, double* out3);
 double or_pressure(const or_atom_t* atoms, int64_t numAll, const or_subdomain_t* s);

@@ -134,6 +134,10 @@ def lib():
                                         C.c_int, C.c_int]),
         "or_shake_positional": (C.c_int, [vp, i64, vp, i64, vp, vp, i64, i64, C.c_double]),
         "or_shake_velocity": (C.c_int, [vp, i64, vp, vp, i64]),
+        "or_approx_erfc": (C.c_double, [C.c_double]),
+        "or_coulomb_eval": (None, [C.c_int, C.c_double, C.c_double, vp, i64, C.c_double, C.c_double, vp, vp]),
+        "or_spc_apply_forces": (None, [vp, i64, vp, vp, i64, vp, C.c_int, vp]),
+        "or_spc_bond_energy": (C.c_double, [vp, i64, vp, i64, C.c_double]),
         "or_kinetic_energy": (C.c_double, [vp, i64]),
         "or_system_momentum": (None, [vp, i64, vp]),
         "or_pressure": (C.c_double, [vp, i64, vp]),

@@ -24,7 +24,8 @@ REFERENCE_HEADERS = [
     "analysis/KineticEnergy.hpp", "analysis/SystemMomentum.hpp", "analysis/Pressure.hpp",
     "analysis/MeanSquareDisplacement.hpp", "io/RestoreGRO.hpp", "io/DumpGRO.hpp", "io/RestoreTXT.hpp",
     "io/DumpThermoForce.hpp", "io/RestoreThermoForce.hpp", "action/BerendsenThermostat.hpp",
-    "action/BerendsenBarostat.hpp", "action/Shake.hpp", "data/Bond.hpp",
+    "action/BerendsenBarostat.hpp", "action/Shake.hpp", "data/Bond.hpp", "action/SPC.hpp", "action/Coulomb.hpp",
+    "action/CoulombDSF.hpp",
 ]
 
 
@@ -45,7 +46,7 @@ def test_reference_header_paths_exist():
         assert os.path.exists(os.path.join(INC, h)), h
 
 
-@pytest.mark.parametrize("name", ["lennard_jones_nve", "adress_ideal_gas", "restart_io", "constraints_step"])
+@pytest.mark.parametrize("name", ["lennard_jones_nve", "adress_ideal_gas", "restart_io", "constraints_step", "spc_water"])
 def test_example_compiles_and_fails_loudly_without_gpu(name, tmp_path):
     import torch
 
@@ -190,3 +191,51 @@ def test_adress_driver_runs(tmp_path):
     assert out["numAT"] > 0 and out["numHY"] > 0 and out["numAT"] + out["numHY"] < out["atoms"]
     assert out["densitySamples"] == len(range(110, steps, 10))  # samples since the update at step 100
     assert np.isfinite(out["E"]) and np.isfinite(out["muLeft"])
+
+
+def _lcg_water(sites, spacing=0.31, jitter=0.02):
+    """the start configuration of examples/spc_water.cpp (48-bit LCG, same draw order)"""
+    state = [0x1234ABCD330E]
+
+    def rnd():
+        state[0] = (state[0] * 0x5DEECE66D + 0xB) & ((1 << 48) - 1)
+        return state[0] / float(1 << 48)
+
+    eq, ang = 0.1, 109.47 / 180.0 * 3.14159265358979323846
+    m = sites ** 3
+    pos, vel = np.zeros((3 * m, 3)), np.zeros((3 * m, 3))
+    idx = 0
+    for i in range(sites):
+        for j in range(sites):
+            for k in range(sites):
+                o = 3 * idx
+                for d, c in enumerate((i, j, k)):
+                    pos[o, d] = (c + 0.5) * spacing + (rnd() - 0.5) * jitter
+                phi = rnd() * 2.0 * np.pi
+                for h, a in enumerate((phi, phi + ang)):
+                    pos[o + 1 + h] = pos[o] + (eq * np.cos(a), eq * np.sin(a), 0.0)
+                for d in range(3):
+                    vel[o:o + 3, d] = (rnd() - 0.5) * 0.5
+                idx += 1
+    mass = np.tile([15.999, 1.008, 1.008], m)
+    return pos, vel, mass, np.tile([-0.82, 0.41, 0.41], m), mass / (15.999 + 2 * 1.008), np.tile([0, 1, 1], m), np.full(3, sites * spacing)
+
+
+@pytest.mark.gpu
+def test_spc_water_driver_matches_oracle(tmp_path):
+    """row (f)4 through the mirror: constrained SPC water, 30 steps with rebuilds, against the oracle's run"""
+    from oracle.md_loop import OracleSpcMD
+
+    sites, steps = 10, 30
+    exe = _compile("spc_water", tmp_path)
+    res = subprocess.run([exe, str(sites), str(steps)], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    out = json.loads(res.stdout.strip().splitlines()[-1])
+    md = OracleSpcMD(*_lcg_water(sites), dt=0.0005, skin=0.02)
+    st = md.run(steps)
+    assert out["molecules"] == sites ** 3 and out["rebuilds"] == st["rebuilds"] >= 2
+    assert out["ghostAtoms"] == md.ng and out["ghostMolecules"] == md.mg
+    assert abs(out["ELJ"] - st["energyLJ"]) <= 1e-8 * abs(st["energyLJ"])
+    assert abs(out["ECoulomb"] - st["energyCoulomb"]) <= 1e-8 * abs(st["energyCoulomb"])
+    assert np.allclose(out["x0"], md.atoms["pos"][0], rtol=0, atol=1e-9)
+    assert out["maxBondError"] < 1e-5 and 0 <= out["bondEnergy"] < 1e-6

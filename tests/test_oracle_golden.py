@@ -1,6 +1,7 @@
 """Pins the CPU oracle against every golden vector / known-answer test the reference holds for the
 hot path.  CPU only."""
 import ctypes as C
+import math
 
 import numpy as np
 import pytest
@@ -691,3 +692,107 @@ def test_berendsen_and_shake_kats(oracle):
         assert abs(np.dot(a["vel"][i] - a["vel"][j], a["pos"][i] - a["pos"][j])) < 1e-14
     bad = np.array([0, 2], dtype=np.int64)  # MRMD_DEVICE_ASSERT_LESS: not enough atoms in molecule to satisfy bond
     assert L.or_shake_velocity(m.ctypes.data, 2, a.ctypes.data, bad.ctypes.data, 1) == -1
+
+
+# ---------------------------------------------------------------------------------------------
+# row (f)4: Coulomb / CoulombDSF / SPC water
+def spc_water(oracle, origins):
+    """the molecule of mrmd/action/SPC.test.cpp:51-96, once per origin"""
+    eq_ho, angle = 0.1, 109.47 / 180.0 * math.pi
+    n = len(origins)
+    atoms = np.zeros(3 * n, dtype=oracle.ATOM)
+    mols = np.zeros(n, dtype=oracle.MOLECULE)
+    m_tot = 15.999 + 2 * 1.008
+    for i, o in enumerate(np.asarray(origins, dtype=np.float64)):
+        atoms["pos"][3 * i] = o
+        atoms["pos"][3 * i + 1] = o + (eq_ho, 0, 0)
+        atoms["pos"][3 * i + 2] = o + (eq_ho * math.cos(angle), eq_ho * math.sin(angle), 0)
+        atoms["type"][3 * i:3 * i + 3] = (0, 1, 1)
+        atoms["mass"][3 * i:3 * i + 3] = (15.999, 1.008, 1.008)
+        atoms["charge"][3 * i:3 * i + 3] = (-0.82, 0.41, 0.41)
+        atoms["relMass"][3 * i:3 * i + 3] = np.array((15.999, 1.008, 1.008)) / m_tot
+        mols["pos"][i] = o
+        mols["atomsOffset"][i], mols["numAtoms"][i] = 3 * i, 3
+    return atoms, mols
+
+
+def test_approx_erfc_and_coulomb_dsf_kats(oracle):
+    """mrmd/util/math.test.cpp:45-51, mrmd/action/CoulombDSF.test.cpp:63-117"""
+    L = oracle.lib()
+    for x in np.arange(0.1, 3.0, 0.1):
+        assert abs(math.erfc(x) - L.or_approx_erfc(float(x))) < 1e-6
+    isp = 1.0 / math.sqrt(math.pi)
+
+    def energy_dsf(r, q1, q2, alpha, rc):
+        b = math.erfc(alpha * r) / r - math.erfc(alpha * rc) / rc
+        b += (math.erfc(alpha * rc) / (rc * rc) + 2 * alpha * isp * math.exp(-alpha * alpha * rc * rc) / rc) * (r - rc)
+        return 138.935458 * q1 * q2 * b
+
+    def force_dsf(r, q1, q2, alpha, rc):
+        b = math.erfc(alpha * r) / (r * r) + 2 * alpha * isp * math.exp(-alpha * alpha * r * r) / r
+        b -= math.erfc(alpha * rc) / (rc * rc) + 2 * alpha * isp * math.exp(-alpha * alpha * rc * rc) / rc
+        return 138.935458 * q1 * q2 * b / r
+
+    def evaluate(kind, rc, alpha, x, q1, q2):
+        d = np.ascontiguousarray(np.asarray(x, dtype=np.float64) ** 2)
+        f, e = np.zeros_like(d), np.zeros_like(d)
+        L.or_coulomb_eval(kind, rc, alpha, d.ctypes.data, len(d), q1, q2, f.ctypes.data, e.ctypes.data)
+        return f, e
+
+    rc, alpha, q1, q2 = 5.0, 0.1, 1.2, -1.3
+    xs = np.arange(1e-8, rc, 0.01)
+    f, e = evaluate(1, rc, alpha, xs, q1, q2)
+    for x, fi, ei in zip(xs, f, e):
+        assert abs((fi - force_dsf(x, q1, q2, alpha, rc)) / force_dsf(x, q1, q2, alpha, rc)) < 1e-4  # ForceExplicitComparison
+        if x < rc - 1.0:
+            assert abs((ei - energy_dsf(x, q1, q2, alpha, rc)) / energy_dsf(x, q1, q2, alpha, rc)) < 1e-5  # Energy...
+    pp, mm, pm, mp = (evaluate(1, 1.0, 0.1, [1.0], a, b)[0][0] for a, b in ((1, 1), (-1, -1), (1, -1), (-1, 1)))
+    assert float_eq(pp, mm) and float_eq(pm, mp) and float_eq(pp, -pm)  # Symmetry
+    assert abs(evaluate(1, 1.5, 0.1, [1.5], 1.0, 1.0)[0][0]) < 1e-5  # shift
+    f, e = evaluate(0, 0.0, 0.0, [2.0], 0.5, -0.25)  # action/Coulomb.hpp:30-43
+    assert f[0] == 138.935458 * 0.5 * -0.25 / 4.0 and e[0] == 138.935458 * 0.5 * -0.25 / 2.0
+
+
+def test_spc_kats(oracle):
+    """mrmd/action/SPC.test.cpp:131-152 (an equilibrium molecule needs no constraint force) and SPC::applyForces /
+    calcBondEnergy (SPC.hpp:143-344) for two molecules against the formulas written out in numpy"""
+    L = oracle.lib()
+    eq_ho, angle = 0.1, 109.47 / 180.0 * math.pi
+    eq_hh = eq_ho * math.sqrt(2.0 - 2.0 * math.cos(angle))
+    atoms, mols = spc_water(oracle, [(0, 0, 0)])
+    bonds, eqs = np.array([0, 1, 0, 2, 1, 2], dtype=np.int64), np.array([eq_ho, eq_ho, eq_hh])
+    assert L.or_shake_positional(mols.ctypes.data, 1, atoms.ctypes.data, 3, bonds.ctypes.data, eqs.ctypes.data, 3, 20, 0.1) == 0
+    assert all(float_eq(v + 1.0, 1.0) for v in atoms["force"].ravel())
+    assert abs(L.or_spc_bond_energy(mols.ctypes.data, 1, atoms.ctypes.data, 3, 1000.0)) < 1e-25
+
+    atoms, mols = spc_water(oracle, [(0, 0, 0), (0.3, 0.1, -0.05)])
+    counts, neigh = np.array([1, 0], dtype=np.int32), np.array([[1], [0]], dtype=np.int32)
+    en = np.zeros(2)
+    L.or_spc_apply_forces(mols.ctypes.data, 2, counts.ctypes.data, neigh.ctypes.data, 1, atoms.ctypes.data, 0, en.ctypes.data)
+    sigma, eps, rcut = 0.31655578901998815, 0.6501695808187486, 1.2
+    table = oracle.lj_table(0.7 * sigma, rcut, sigma, eps, 1, True)
+    force = np.zeros((6, 3))
+    d = atoms["pos"][0] - atoms["pos"][3]
+    ff, e = C.c_double(), C.c_double()
+    L.or_lj_force_energy(C.addressof(table), 0, float(d @ d), C.byref(ff), C.byref(e))
+    force[0] += d * ff.value
+    force[3] -= d * ff.value
+    e_c = 0.0
+    for i in range(3):
+        for j in range(3, 6):
+            d = atoms["pos"][i] - atoms["pos"][j]
+            pre = 138.935458 * atoms["charge"][i] * atoms["charge"][j]
+            force[i] += d * pre / (d @ d)
+            force[j] -= d * pre / (d @ d)
+            e_c += pre / math.sqrt(d @ d)
+    assert abs(en[0] - e.value) <= 1e-14 * abs(e.value) and abs(en[1] - e_c) <= 1e-13 * abs(e_c)
+    assert np.allclose(atoms["force"], force, rtol=1e-13, atol=1e-12)
+    assert np.abs(atoms["force"].sum(axis=0)).max() < 1e-10  # Newton's third law
+    # the DSF flavour vanishes at the cutoff, the plain one does not
+    far, mfar = spc_water(oracle, [(0, 0, 0), (1.25, 0, 0)])
+    L.or_spc_apply_forces(mfar.ctypes.data, 2, counts.ctypes.data, neigh.ctypes.data, 1, far.ctypes.data, 1, en.ctypes.data)
+    assert en[0] == 0.0 and abs(en[1]) < 1e-2
+    plain = np.zeros(2)
+    far["force"] = 0.0
+    L.or_spc_apply_forces(mfar.ctypes.data, 2, counts.ctypes.data, neigh.ctypes.data, 1, far.ctypes.data, 0, plain.ctypes.data)
+    assert abs(plain[1]) > 1.0
