@@ -44,10 +44,17 @@ def parse_args():
     p.add_argument("--balance", action="store_true", help="adress workload on N>1 GPUs: cost-balanced slab widths")
     p.add_argument("--force-cost-ratio", type=float, default=4.5,
                    help="--balance: force-kernel time / rest of the step, per atom of the AT + HY region")
-    p.add_argument("--workload", default="lj", choices=["lj", "adress"],
+    p.add_argument("--workload", default="lj", choices=["lj", "adress", "tetramer"],
                    help="lj: configs[1] (the headline line); adress: configs[2]/[4] physics (LJ / ideal-gas AdResS slab "
-                        "with thermodynamic force, one molecule per atom; use --side 200 for 8M atoms per GPU)")
-    return p.parse_args()
+                        "with thermodynamic force, one molecule per atom; use --side 200 for 8M atoms per GPU); tetramer: "
+                        "configs[3] physics (AdResS LJ tetramers, spherical region, SHAKE / RATTLE; --side = molecules "
+                        "per edge, 160 -> 16.4M atoms; one GPU, or --replicas)")
+    args = p.parse_args()
+    if args.workload == "tetramer":
+        args.full_list = 0  # half Verlet list of molecules over materialised ghost molecules (reference semantics)
+        if args.gpus > 1 and not args.replicas:
+            p.error("--workload tetramer: the x-slab decomposition handles one-atom molecules only; use --replicas")
+    return args
 
 
 def env_rank():
@@ -161,6 +168,31 @@ def cpu_loop_adress(pos, vel, box, steps, warmup, threads):
     return md.run(steps), md
 
 
+TETRAMER = dict(constraint_iterations=3, bond_length=1.0, max_neigh=40)
+
+
+def tetramer_region(box):
+    """config 4: spherical region, centre = box centre, R = 60 and h = 30 in the 317.48 box (scaled with the box)"""
+    return 60.0 / 317.48 * float(box[0]), 30.0 / 317.48 * float(box[0])
+
+
+def cpu_loop_tetramer(pos, vel, box, steps, warmup, threads):
+    """--workload tetramer on the host cores (checker / baseline only)."""
+    from oracle import pyoracle as orc
+    from oracle.md_loop import OracleAdressMD
+
+    orc.build()
+    orc.lib().or_set_threads(threads)
+    radius, hybrid = tetramer_region(box)
+    weight = orc.make_weight(orc.WEIGHT_SPHERICAL, 0.5 * np.asarray(box), radius, hybrid, 2)
+    md = OracleAdressMD(pos, vel, box, weight, dt=PHYS["dt"], rc=PHYS["rc"], skin=PHYS["skin"], sigma=PHYS["sigma"],
+                        epsilon=PHYS["epsilon"], cap=PHYS["cap"], max_neigh=TETRAMER["max_neigh"], langevin=True,
+                        zeta=PHYS["zeta"], temperature=PHYS["temperature"], seed=PHYS["seed"], atoms_per_mol=4,
+                        constraint_iterations=TETRAMER["constraint_iterations"], bond_length=TETRAMER["bond_length"])
+    md.run(warmup)
+    return md.run(steps), md
+
+
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -178,11 +210,18 @@ def run_reference(args):
 
     threads = host_threads()
     # probe the host rate on a 32^3 system, then size the sample for ~150 s of CPU work
-    loop = cpu_loop_adress if args.workload == "adress" else cpu_loop
-    pos, vel, box = lattice_system(32)
+    loop = {"lj": cpu_loop, "adress": cpu_loop_adress, "tetramer": cpu_loop_tetramer}[args.workload]
+    if args.workload == "tetramer":
+        from mrmd_b200.workloads import tetramer_system
+
+        def lattice_system(side):  # noqa: F811  (molecules per edge; same probe / sizing logic in atoms)
+            return tetramer_system(side)
+    pos, vel, box = lattice_system(32 if args.workload != "tetramer" else 20)
     probe, _ = loop(pos, vel, box, 6, 2, threads)
-    rate = 32 ** 3 * probe["steps"] / probe["seconds"]
+    rate = len(pos) * probe["steps"] / probe["seconds"]
     budget_atoms = rate * 150.0 / max(args.steps + args.warmup, 1)
+    if args.workload == "tetramer":
+        budget_atoms /= 4.0
     side = int(max(16, min(args.side, np.floor(budget_atoms ** (1.0 / 3.0)))))
     pos, vel, box = lattice_system(side)
     n = len(pos)
@@ -194,7 +233,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "atom-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * res["seconds"] / max(res["steps"], 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, n_atoms_per_gpu=args.side ** 3),
+        "config": workload_config(args, n_atoms_per_gpu=args.side ** 3 * (4 if args.workload == "tetramer" else 1)),
         "pair_interactions_per_s": res["pairInteractions"] / res["seconds"],
         "cpu_baseline": {"value": value, "unit": "atom-steps/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "atom-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -212,9 +251,16 @@ def workload_config(args, n_atoms_per_gpu):
           "lattice rho=0.512, Slab(centre, AT 0.2 Lx, HY 0.1 Lx, nu 1), LJ_IdealGas(cap 0.7, rc 2.5, shift), "
           "ThermodynamicForce(rho 0.512, bin 0.25, modulation 2, sample/10, update/1000), Langevin gamma=20 T=1.5, "
           "dt=0.002, skin 0.1, maxNeighbors 60")
+    tet = ("AdResS Lennard-Jones tetramers (configs[3]): molecule centres on an sc lattice of spacing 1.98425 (atom density "
+           "0.512), regular tetrahedra of edge 1, 4 atoms per molecule (relMass 1/4), Spherical(centre, R 0.189 L, h 0.0945 "
+           "L, exponent 2) = R 60 / h 30 at 16.4M atoms, LJ_IdealGas(cap 0.7, rc 2.5, shift), MoleculeConstraints(4, 3) "
+           "on the six bonds (SHAKE / RATTLE), Langevin gamma=20 T=1.5, dt=0.002, skin 0.1, half Verlet list of molecules "
+           "over MultiResGhostLayer ghosts, maxNeighbors 40")
+    wl = getattr(args, "workload", "lj")
+    sp = 1.98425 if wl == "tetramer" else 1.25
     return {
-        "workload": ad if getattr(args, "workload", "lj") == "adress" else lj,
-        "atoms_per_gpu": n_atoms_per_gpu, "box_per_gpu": [(getattr(args, "side_x", None) or args.side) * 1.25, args.side * 1.25, args.side * 1.25], "equilibration_steps": args.equil,
+        "workload": {"lj": lj, "adress": ad, "tetramer": tet}[wl],
+        "atoms_per_gpu": n_atoms_per_gpu, "box_per_gpu": [(getattr(args, "side_x", None) or args.side) * sp, args.side * sp, args.side * sp], "equilibration_steps": args.equil,
         "list": {0: "half (reference semantics, fp64 RED scatter)", 1: "full (generic gather kernel)", 2: "full, periodic tiles staged in shared memory (mrmd_b200_verlet_build_periodic)"}[args.full_list],
         "l2": "inputs larger than L2 (per step: 104 B/atom state + neighbour table ~ 4 B x 19-38 slots/atom > 126 MB "
               "at 1M atoms); no explicit flush",
@@ -242,7 +288,8 @@ def run_b200(args):
     stream = torch.cuda.current_stream().cuda_stream
 
     slab_mode = world > 1 and not args.replicas
-    adress = args.workload == "adress"
+    tetramer = args.workload == "tetramer"
+    adress = args.workload in ("adress", "tetramer")
     sites_x = args.side_x or args.side          # lattice planes per GPU along x (equal-width slabs)
     spacing = 1.25
     global_lx = world * sites_x * spacing if slab_mode else sites_x * spacing
@@ -257,17 +304,26 @@ def run_b200(args):
                                    quantum=spacing, min_width=2 * (PHYS["rc"] + PHYS["skin"]))
         my_sites_x = int(round((cuts[rank + 1] - cuts[rank]) / spacing))
         x_offset = float(cuts[rank])
-    pos, vel, box = lattice_system(args.side, seed=PHYS["seed"] + rank, n_side_x=my_sites_x)
+    if tetramer:
+        from mrmd_b200.workloads import tetramer_system
+
+        pos, vel, box = tetramer_system(args.side, seed=PHYS["seed"] + rank)
+    else:
+        pos, vel, box = lattice_system(args.side, seed=PHYS["seed"] + rank, n_side_x=my_sites_x)
+        box = np.array([sites_x * spacing, box[1], box[2]])  # the equal-width slab: world * box[0] is the global length
     n = len(pos)
-    box = np.array([sites_x * spacing, box[1], box[2]])  # the equal-width slab: world * box[0] is the global length
     sub = api.Subdomain([0, 0, 0], box, PHYS["rc"] + PHYS["skin"])
     if slab_mode:
         # weak scaling over x-slabs: one global box of world * sites_x x side x side sites, rank r owns slab r
         pos = pos + np.array([x_offset, 0.0, 0.0])
-    atoms = api.Atoms.from_arrays(pos, vel, mass=1.0, relativeMass=1.0)
+    atoms = api.Atoms.from_arrays(pos, vel, mass=1.0, relativeMass=0.25 if tetramer else 1.0)
 
     extra = {}
-    if adress:
+    if tetramer:
+        radius, hybrid = tetramer_region(box)
+        extra = dict(adress=True, weight=api.Spherical(0.5 * box, radius, hybrid, 2), doShift=True, atomsPerMolecule=4,
+                     numConstraintIterations=TETRAMER["constraint_iterations"], bondLength=TETRAMER["bond_length"])
+    elif adress:
         # configs[2] / configs[4] physics: Slab(centre of the global box, AT diameter 0.2 Lx, HY width 0.1 Lx, nu = 1),
         # LJ_IdealGas(cap 0.7, rc 2.5, shift on), ThermodynamicForce(rho 0.512, bin 0.25, modulation 2; sample every
         # 10 steps, update(sigma 2, range 2) every 1000 steps), one molecule per atom
@@ -288,9 +344,9 @@ def run_b200(args):
                                                temperature=PHYS["temperature"], seed=PHYS["seed"], cuts=cuts, **extra)
         return api.MolecularDynamics(a, sub, dt=PHYS["dt"], rc=PHYS["rc"], skin=PHYS["skin"], sigma=PHYS["sigma"],
                                      epsilon=PHYS["epsilon"], cappingDistance=PHYS["cap"],
-                                     maxNeighbors=PHYS["max_neigh"], langevin=True, zeta=PHYS["zeta"],
-                                     temperature=PHYS["temperature"], seed=PHYS["seed"], cellSort=True,
-                                     fullList=int(args.full_list), **extra)
+                                     maxNeighbors=TETRAMER["max_neigh"] if tetramer else PHYS["max_neigh"], langevin=True,
+                                     zeta=PHYS["zeta"], temperature=PHYS["temperature"], seed=PHYS["seed"],
+                                     cellSort=not tetramer, fullList=int(args.full_list), **extra)
 
     md = make_md(atoms)
     md.run(args.equil, stream=stream)       # untimed: melt the lattice
@@ -348,6 +404,9 @@ def run_b200(args):
         # SURVEY 8d, K14 with a = 1 atom per molecule: 84 M + 56 M a + 12 P_mol + (64 + 56 a) P_act
         algo_bytes = 140.0 * n * args.steps + 12.0 * stored_half + 120.0 * stats["activePairs"]
         kernel_name = "adressForceTiledKernel" if args.full_list == 2 else "adressForceKernel"
+    if tetramer:
+        # the same formula with a = 4 and M = n / 4 molecules: 84 M + 56 M a + 12 P_mol + (64 + 56 a) P_act
+        algo_bytes = (84.0 + 224.0) * (n / 4) * args.steps + 12.0 * stats["storedPairs"] + 288.0 * stats["activePairs"]
     force_ms = stats["forceKernelMs"]
     n_kernel, kernel_rank, stored_kernel = n, rank, stats["storedPairs"]
     if world > 1:
@@ -429,7 +488,7 @@ def run_b200(args):
         threads = host_threads()
         cpos, cvel = atoms.get("pos")[:n], atoms.get("vel")[:n]
         t0 = time.perf_counter()
-        probe, omd = (cpu_loop_adress if adress else cpu_loop)(cpos, cvel, box, 3, 1, threads)
+        probe, omd = (cpu_loop_tetramer if tetramer else (cpu_loop_adress if adress else cpu_loop))(cpos, cvel, box, 3, 1, threads)
         per_step = probe["seconds"] / 3
         more = int(max(3, min(200, (args.cpu_seconds - (time.perf_counter() - t0)) / max(per_step, 1e-6))))
         res = omd.run(more)

@@ -293,6 +293,10 @@ int mrmd_b200_adress_create(mrmd_b200_adress** out, const double* cappingDistanc
 int mrmd_b200_adress_destroy(mrmd_b200_adress* ad);
 /* setCompensationEnergySamplingInterval / UpdateInterval (action/LJ_IdealGas.hpp:73-80) */
 int mrmd_b200_adress_set_intervals(mrmd_b200_adress* ad, int64_t samplingInterval, int64_t updateInterval);
+/* optional promise that every molecule has exactly atomsPerMolecule atoms (0: unknown, the default).  4 selects a kernel
+ * with four lanes per molecule (the tetramers of BASELINE.json configs[3]); a molecule that breaks the promise makes the
+ * next call that reads results back fail. */
+int mrmd_b200_adress_set_atoms_per_molecule(mrmd_b200_adress* ad, int64_t atomsPerMolecule);
 /* replaces LJ_IdealGas::run (action/LJ_IdealGas.cpp:227-260); *energy (host, optional) after a sync */
 int mrmd_b200_adress_run(mrmd_b200_adress* ad, mrmd_b200_molecules* m, const mrmd_b200_verlet* v,
                          mrmd_b200_atoms* a, double* energy, int64_t* numPairs, void* stream);
@@ -437,6 +441,15 @@ typedef struct
     double thermoTargetDensity, thermoBinWidth, thermoModulation;
     int64_t thermoSampleInterval, thermoUpdateInterval;
     double thermoSmoothingSigma, thermoSmoothingIntensity;
+    /* AdResS with the half list (fullList 0) only: molecules of atomsPerMolecule consecutive atoms (atomsOffset =
+     * atomsPerMolecule * m, relative masses taken from the atoms; 0 or 1: one molecule per atom) -- the tetramers of
+     * BASELINE.json configs[3].  numConstraintIterations > 0 adds MoleculeConstraints(atomsPerMolecule,
+     * numConstraintIterations) with a bond of length bondLength between every two atoms of a molecule: SHAKE in front
+     * of preForceIntegrate, RATTLE after postForceIntegrate (tests/Constraints/Constraints.cpp:53-64).  cellSort must
+     * be 0 for multi-atom molecules. */
+    int64_t atomsPerMolecule;
+    int64_t numConstraintIterations;
+    double bondLength;
 } mrmd_b200_md_config;
 typedef struct
 {

@@ -34,7 +34,8 @@ class MdConfig(C.Structure):
                 ("doShift", C.c_int32), ("useThermoForce", C.c_int32), ("thermoTargetDensity", C.c_double),
                 ("thermoBinWidth", C.c_double), ("thermoModulation", C.c_double),
                 ("thermoSampleInterval", C.c_int64), ("thermoUpdateInterval", C.c_int64),
-                ("thermoSmoothingSigma", C.c_double), ("thermoSmoothingIntensity", C.c_double)]
+                ("thermoSmoothingSigma", C.c_double), ("thermoSmoothingIntensity", C.c_double),
+                ("atomsPerMolecule", C.c_int64), ("numConstraintIterations", C.c_int64), ("bondLength", C.c_double)]
 
 
 class MdStats(C.Structure):
@@ -119,6 +120,7 @@ SIGNATURES = {
     "mrmd_b200_adress_create": (C.c_int, [pvp, vp, vp, vp, vp, i64, C.c_int]),
     "mrmd_b200_adress_destroy": (C.c_int, [vp]),
     "mrmd_b200_adress_set_intervals": (C.c_int, [vp, i64, i64]),
+    "mrmd_b200_adress_set_atoms_per_molecule": (C.c_int, [vp, i64]),
     "mrmd_b200_adress_run": (C.c_int, [vp, vp, vp, vp, pdbl, pi64, vp]),
     "mrmd_b200_adress_run_periodic": (C.c_int, [vp, vp, vp, vp, pdbl, pi64, vp]),
     "mrmd_b200_adress_read_histogram": (C.c_int, [vp, C.c_int, vp, vp]),

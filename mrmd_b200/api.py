@@ -498,6 +498,10 @@ class LJ_IdealGas:
         check(L().mrmd_b200_adress_create(C.byref(self.h), *[a.ctypes.data for a in arrs], numTypes, int(doShift)))
         self._sampling, self._update = 200, 20000
 
+    def setAtomsPerMolecule(self, atomsPerMolecule):
+        """mrmd_b200_adress_set_atoms_per_molecule (extension): 4 selects the four-lanes-per-molecule kernel"""
+        check(L().mrmd_b200_adress_set_atoms_per_molecule(self.h, int(atomsPerMolecule)))
+
     def setCompensationEnergySamplingInterval(self, interval):
         self._sampling = interval
         check(L().mrmd_b200_adress_set_intervals(self.h, self._sampling, self._update))
@@ -818,8 +822,10 @@ class MolecularDynamics:
 
     def __init__(self, atoms, subdomain, dt=0.002, rc=2.5, skin=0.1, sigma=1.0, epsilon=1.0, cappingDistance=0.7,
                  maxNeighbors=60, langevin=False, zeta=20.0, temperature=1.5, seed=1234, cellSort=True, fullList=False,
-                 adress=False, weight=None, doShift=True, thermo=None):
+                 adress=False, weight=None, doShift=True, thermo=None, atomsPerMolecule=1, numConstraintIterations=0,
+                 bondLength=1.0):
         cfg = _lib.MdConfig()
+        cfg.atomsPerMolecule, cfg.numConstraintIterations, cfg.bondLength = atomsPerMolecule, numConstraintIterations, bondLength
         cfg.dt, cfg.rc, cfg.skin, cfg.sigma, cfg.epsilon, cfg.cappingDistance = dt, rc, skin, sigma, epsilon, cappingDistance
         cfg.maxNeighbors, cfg.integrator, cfg.cellSort, cfg.fullList = maxNeighbors, int(langevin), int(cellSort), int(fullList)
         cfg.adress, cfg.zeta, cfg.temperature, cfg.seed, cfg.doShift = int(adress), zeta, temperature, seed, int(doShift)

@@ -69,19 +69,50 @@ __global__ void weightEvalKernel(mrmd_b200_weight w, const double* pos, int64_t 
     grad[3 * i + 2] = gz;
 }
 
-// LJ_IdealGas::operator()(alpha, sumEnergy), LJ_IdealGas.cpp:52-225.  One thread per local molecule.
+// Molecules whose row holds work: alpha outside the coarse-grained region, or any partner outside it (a CG-CG pair is
+// ideal gas, LJ_IdealGas.cpp:102-107).  Their indices are appended warp by warp to activeList, so that the force
+// kernels run on densely packed warps of working molecules instead of dragging the coarse-grained bulk along.
+__global__ void adressActiveMoleculesKernel(MolsView m, int64_t numLocalMols, const int32_t* __restrict__ counts,
+                                            const int32_t* __restrict__ neigh, int64_t pitch, int32_t* activeList,
+                                            int* activeCount)
+{
+    const int64_t alpha = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    bool active = false;
+    if (alpha < numLocalMols)
+    {
+        active = !inCG(reinterpret_cast<const double*>(m.w + alpha)[0]);
+        if (!active)
+        {
+            const int numNeighbors = counts[alpha];
+            const int32_t* row = neigh + alpha;
+            for (int n = 0; n < numNeighbors && !active; ++n)
+                active = !inCG(reinterpret_cast<const double*>(m.w + row[int64_t(n) * pitch])[0]);
+        }
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, active);
+    if (ballot == 0u) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(ballot) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(activeCount, __popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (active) activeList[base + __popc(ballot & ((1u << lane) - 1u))] = static_cast<int32_t>(alpha);
+}
+
+// LJ_IdealGas::operator()(alpha, sumEnergy), LJ_IdealGas.cpp:52-225.  One thread per working molecule (activeList).
 // The partner's {lambda^mod, grad lambda} come in one 256-bit gather; CG-CG pairs leave after it.
 // hist: [0] compensationEnergy, [1] compensationEnergyCounter, [2] meanCompensationEnergy.
 template <bool SAMPLING>
 __global__ void __launch_bounds__(AD_THREADS)
     adressForceKernel(MolsView m, AtomsView a, int64_t numLocalMols, const int32_t* __restrict__ counts,
                       const int32_t* __restrict__ neigh, int64_t pitch, LJTable table, double rcSqr, int64_t numTypes,
-                      double* hist, double* partials, double* result, unsigned int* ticket)
+                      double* hist, double* partials, double* result, unsigned int* ticket,
+                      const int32_t* __restrict__ activeList, const int* __restrict__ activeCount)
 {
-    const int64_t alpha = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    const int64_t slot = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
     double sumEnergy = 0.0, pairs = 0.0, activePairs = 0.0;
-    if (alpha < numLocalMols)
+    if (slot < min(numLocalMols, int64_t(*activeCount)))
     {
+        const int64_t alpha = activeList[slot];
         const int64_t T = numTypes;
         double* compensationEnergy = hist;
         double* compensationEnergyCounter = hist + COMPENSATION_ENERGY_BINS * T;
@@ -190,6 +221,171 @@ __global__ void __launch_bounds__(AD_THREADS)
     gridReduce3<AD_THREADS>(sumEnergy, pairs, activePairs, partials, result, ticket);
 }
 
+// The same operator for molecules of exactly four atoms (the tetramers of BASELINE.json configs[3]): four lanes share
+// one molecule alpha, lane i owns alpha's atom i (position and force accumulator in registers) and walks the four atoms
+// of the partner; the partner's forces are reduce-scattered over the four lanes (9 shuffles) so that lane j adds the
+// force on the partner's atom j: 4x the parallelism of the thread-per-molecule kernel inside the small atomistic
+// region and 8 instead of 20 force atomics per molecule pair.  A molecule with another atom count raises *error.
+constexpr int AD_LANES = 4;
+template <bool SAMPLING>
+__global__ void __launch_bounds__(AD_THREADS)
+    adressForceLanes4Kernel(MolsView m, AtomsView a, int64_t numLocalMols, const int32_t* __restrict__ counts,
+                            const int32_t* __restrict__ neigh, int64_t pitch, LJTable table, double rcSqr, int64_t numTypes,
+                            double* hist, double* partials, double* result, unsigned int* ticket, int* error,
+                            const int32_t* __restrict__ activeList, const int* __restrict__ activeCount)
+{
+    const int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    const int64_t slot = t / AD_LANES;
+    const int li = int(t % AD_LANES);
+    const unsigned gmask = 0xFu << ((threadIdx.x & 31) & ~3);
+    double sumEnergy = 0.0, pairs = 0.0, activePairs = 0.0;
+    bool valid = slot < min(numLocalMols, int64_t(*activeCount));
+    const int64_t alpha = valid ? activeList[slot] : 0;
+    longlong2 ocA = make_longlong2(0, 0);
+    if (valid)
+    {
+        ocA = m.oc[alpha];
+        if (ocA.y != AD_LANES)
+        {
+            *error = 1;
+            valid = false;
+        }
+    }
+    if (valid)
+    {
+        const int64_t T = numTypes;
+        double* compensationEnergy = hist;
+        double* compensationEnergyCounter = hist + COMPENSATION_ENERGY_BINS * T;
+        const double* meanCompensationEnergy = hist + 2 * COMPENSATION_ENERGY_BINS * T;
+        const double inverseBinSize = 1.0 / ((1.0 - 0.0) / double(COMPENSATION_ENERGY_BINS));
+
+        const double4 wA = ld4nc(m.w + alpha);
+        const double modLambdaAlpha = wA.x;
+        const bool hyAlpha = inHY(modLambdaAlpha);
+        const bool cgAlpha = inCG(modLambdaAlpha);
+        long long binAlpha = -1;
+        if (hyAlpha) binAlpha = histBin(0.0, inverseBinSize, COMPENSATION_ENERGY_BINS, m.lambda[alpha]);
+        const double4 pi = ld4nc(a.pos + ocA.x + li);
+        const int64_t typeI = typeOf(pi);
+        double fIx = 0.0, fIy = 0.0, fIz = 0.0;  // force on alpha's atom li
+        double sumVA = 0.0;                       // this lane's share of sum Vij over the drift pairs of alpha
+
+        const int numNeighbors = counts[alpha];
+        const int32_t* row = neigh + alpha;
+        for (int n = 0; n < numNeighbors; ++n)
+        {
+            const int64_t beta = row[int64_t(n) * pitch];
+            const double4 wB = ld4nc(m.w + beta);
+            const double modLambdaBeta = wB.x;
+            if (cgAlpha && inCG(modLambdaBeta)) continue;  // ideal gas, LJ_IdealGas.cpp:102-107
+            const longlong2 ocB = m.oc[beta];
+            if (ocB.y != AD_LANES)
+            {
+                *error = 1;
+                continue;
+            }
+            if (li == 0) activePairs += 1.0;
+            const double weighting = 0.5 * (modLambdaAlpha + modLambdaBeta);
+            const bool hyBeta = inHY(modLambdaBeta);
+            const bool drift = hyAlpha || hyBeta;
+            long long binBeta = -1;
+            if (SAMPLING && hyBeta) binBeta = histBin(0.0, inverseBinSize, COMPENSATION_ENERGY_BINS, m.lambda[beta]);
+            double fb[AD_LANES][3];
+            double sumV = 0.0;
+#pragma unroll
+            for (int j = 0; j < AD_LANES; ++j)
+            {
+                const double4 pj = ld4nc(a.pos + ocB.x + j);
+                const double dx = pi.x - pj.x;
+                const double dy = pi.y - pj.y;
+                const double dz = pi.z - pj.z;
+                const double distSqr = distSqrExact(dx, dy, dz);
+                fb[j][0] = fb[j][1] = fb[j][2] = 0.0;
+                if (distSqr > rcSqr) continue;  // :137
+                double ff, e;
+                ljForceEnergy(table.t[typeI * T + typeOf(pj)], distSqr, ff, e);
+                const double ffactor = ff * weighting;
+                pairs += 1.0;
+                fIx += dx * ffactor;
+                fIy += dy * ffactor;
+                fIz += dz * ffactor;
+                fb[j][0] = -(dx * ffactor);
+                fb[j][1] = -(dy * ffactor);
+                fb[j][2] = -(dz * ffactor);
+                sumEnergy += e * weighting;
+                const double Vij = 0.5 * e;
+                if (drift)
+                {
+                    sumV += Vij;  // drift force, :163-169
+                    if (SAMPLING && hyBeta && binBeta != -1) atomicAdd(compensationEnergy + binBeta * T + typeOf(pj), Vij);
+                }
+            }
+            // reduce-scatter of the partner's forces: lane j ends up with the sum over alpha's atoms for partner atom j
+            const bool hi = (li & 2) != 0, odd = (li & 1) != 0;
+            double keep[2][3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+            {
+                const double s0 = hi ? fb[0][d] : fb[2][d], s1 = hi ? fb[1][d] : fb[3][d];
+                keep[0][d] = (hi ? fb[2][d] : fb[0][d]) + __shfl_xor_sync(gmask, s0, 2);
+                keep[1][d] = (hi ? fb[3][d] : fb[1][d]) + __shfl_xor_sync(gmask, s1, 2);
+            }
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+            {
+                const double s = odd ? keep[0][d] : keep[1][d];
+                const double mine = (odd ? keep[1][d] : keep[0][d]) + __shfl_xor_sync(gmask, s, 1);
+                if (mine != 0.0) atomicAdd(a.force[d] + ocB.x + li, mine);
+            }
+            sumVA += sumV;
+            if (drift)
+            {
+                double v = sumV;
+                v += __shfl_xor_sync(gmask, v, 1);
+                v += __shfl_xor_sync(gmask, v, 2);
+                if (li == 0 && v != 0.0)
+                {
+                    atomicAdd(m.force[0] + beta, -v * wB.y);
+                    atomicAdd(m.force[1] + beta, -v * wB.z);
+                    atomicAdd(m.force[2] + beta, -v * wB.w);
+                }
+            }
+        }
+        if (fIx != 0.0 || fIy != 0.0 || fIz != 0.0)
+        {
+            atomicAdd(a.force[0] + ocA.x + li, fIx);
+            atomicAdd(a.force[1] + ocA.x + li, fIy);
+            atomicAdd(a.force[2] + ocA.x + li, fIz);
+        }
+        if (SAMPLING && hyAlpha && binAlpha != -1)
+        {
+            if (sumVA != 0.0) atomicAdd(compensationEnergy + binAlpha * T + typeI, sumVA);
+            atomicAdd(compensationEnergyCounter + binAlpha * T + typeI, 1.0);
+        }
+        double vA = sumVA;
+        vA += __shfl_xor_sync(gmask, vA, 1);
+        vA += __shfl_xor_sync(gmask, vA, 2);
+        if (li == 0)
+        {
+            double fAx = -vA * wA.y, fAy = -vA * wA.z, fAz = -vA * wA.w;
+            if (hyAlpha && binAlpha != -1)
+            {
+                const double mean = meanCompensationEnergy[binAlpha * T + typeI];  // type of alpha's first atom, :212-220
+                fAx += mean * wA.y;
+                fAy += mean * wA.z;
+                fAz += mean * wA.w;
+            }
+            if (fAx != 0.0 || fAy != 0.0 || fAz != 0.0)
+            {
+                atomicAdd(m.force[0] + alpha, fAx);
+                atomicAdd(m.force[1] + alpha, fAy);
+                atomicAdd(m.force[2] + alpha, fAz);
+            }
+        }
+    }
+    gridReduce3<AD_THREADS>(sumEnergy, pairs, activePairs, partials, result, ticket);
+}
+
 // updateMeanCompensationEnergy, LJ_IdealGas.cpp:21-50 (runningAverageFactor = 10)
 __global__ void updateMeanCompensationKernel(double* hist, int64_t n, double runningAverageFactor)
 {
@@ -265,6 +461,8 @@ int mrmd_b200_adress_create(mrmd_b200_adress** out, const double* cappingDistanc
     if (rc_ == 0 && cudaMalloc(&ad->dResult, 48) != cudaSuccess) rc_ = MRMD_B200_ENOMEM;
     if (rc_ == 0 && cudaMalloc(&ad->dTicket, 4) != cudaSuccess) rc_ = MRMD_B200_ENOMEM;
     if (rc_ == 0 && cudaMallocHost(&ad->hResult, 48) != cudaSuccess) rc_ = MRMD_B200_ENOMEM;
+    if (rc_ == 0 && cudaMalloc(&ad->dErr, 4) != cudaSuccess) rc_ = MRMD_B200_ENOMEM;
+    if (rc_ == 0 && cudaMallocHost(&ad->hErr, 4) != cudaSuccess) rc_ = MRMD_B200_ENOMEM;
     if (rc_ != 0)
     {
         delete ad;
@@ -273,6 +471,7 @@ int mrmd_b200_adress_create(mrmd_b200_adress** out, const double* cappingDistanc
     cudaMemset(ad->hist, 0, histBytes);
     cudaMemset(ad->dResult, 0, 48);
     cudaMemset(ad->dTicket, 0, 4);
+    cudaMemset(ad->dErr, 0, 4);
     ad->numTypes = numTypes;
     *out = ad;
     return 0;
@@ -286,7 +485,10 @@ int mrmd_b200_adress_destroy(mrmd_b200_adress* ad)
     if (ad->dResult) cudaFree(ad->dResult);
     if (ad->dTicket) cudaFree(ad->dTicket);
     if (ad->hResult) cudaFreeHost(ad->hResult);
+    if (ad->dErr) cudaFree(ad->dErr);
+    if (ad->hErr) cudaFreeHost(ad->hErr);
     ad->partials.release();
+    ad->activeList.release();
     delete ad;
     return 0;
 }
@@ -296,6 +498,13 @@ int mrmd_b200_adress_set_intervals(mrmd_b200_adress* ad, int64_t samplingInterva
     MB_REQUIRE(ad != nullptr && samplingInterval > 0 && updateInterval > 0, "adress_set_intervals");
     ad->samplingInterval = samplingInterval;
     ad->updateInterval = updateInterval;
+    return 0;
+}
+
+int mrmd_b200_adress_set_atoms_per_molecule(mrmd_b200_adress* ad, int64_t atomsPerMolecule)
+{
+    MB_REQUIRE(ad != nullptr && atomsPerMolecule >= 0, "adress_set_atoms_per_molecule");
+    ad->uniformAtoms = atomsPerMolecule;
     return 0;
 }
 
@@ -312,16 +521,34 @@ int mrmd_b200_adress_run(mrmd_b200_adress* ad, mrmd_b200_molecules* m, const mrm
     MB_CUDA(cudaMemsetAsync(ad->dResult, 0, 24, st));
     if (m->numLocal > 0)
     {
-        const int blocks = gridFor(m->numLocal, AD_THREADS);
+        // working molecules first (see adressActiveMoleculesKernel); the force grid is sized for the worst case and
+        // reads the count on the device
+        MB_TRY(ad->activeList.reserve(16 + size_t(m->numLocal) * 4));  // {count, pad[3], list[numLocal]}
+        int* activeCount = ad->activeList.as<int>();
+        int32_t* activeList = ad->activeList.as<int32_t>() + 4;
+        MB_CUDA(cudaMemsetAsync(activeCount, 0, 4, st));
+        adressActiveMoleculesKernel<<<gridFor(m->numLocal, 256), 256, 0, st>>>(
+            m->v, m->numLocal, v->counts.as<int32_t>(), v->neigh.as<int32_t>(), v->pitch, activeList, activeCount);
+        MB_LAUNCHED();
+        const bool lanes4 = ad->uniformAtoms == AD_LANES;
+        const int blocks = gridFor(m->numLocal * (lanes4 ? AD_LANES : 1), AD_THREADS);
         MB_TRY(ad->partials.reserve(size_t(blocks) * 3 * 8));
-        if (sampling)
+        if (lanes4 && sampling)
+            adressForceLanes4Kernel<true><<<blocks, AD_THREADS, 0, st>>>(
+                m->v, a->v, m->numLocal, v->counts.as<int32_t>(), v->neigh.as<int32_t>(), v->pitch, ad->table, ad->rcSqr,
+                ad->numTypes, ad->hist, ad->partials.as<double>(), ad->dResult, ad->dTicket, ad->dErr, activeList, activeCount);
+        else if (lanes4)
+            adressForceLanes4Kernel<false><<<blocks, AD_THREADS, 0, st>>>(
+                m->v, a->v, m->numLocal, v->counts.as<int32_t>(), v->neigh.as<int32_t>(), v->pitch, ad->table, ad->rcSqr,
+                ad->numTypes, ad->hist, ad->partials.as<double>(), ad->dResult, ad->dTicket, ad->dErr, activeList, activeCount);
+        else if (sampling)
             adressForceKernel<true><<<blocks, AD_THREADS, 0, st>>>(
                 m->v, a->v, m->numLocal, v->counts.as<int32_t>(), v->neigh.as<int32_t>(), v->pitch, ad->table, ad->rcSqr,
-                ad->numTypes, ad->hist, ad->partials.as<double>(), ad->dResult, ad->dTicket);
+                ad->numTypes, ad->hist, ad->partials.as<double>(), ad->dResult, ad->dTicket, activeList, activeCount);
         else
             adressForceKernel<false><<<blocks, AD_THREADS, 0, st>>>(
                 m->v, a->v, m->numLocal, v->counts.as<int32_t>(), v->neigh.as<int32_t>(), v->pitch, ad->table, ad->rcSqr,
-                ad->numTypes, ad->hist, ad->partials.as<double>(), ad->dResult, ad->dTicket);
+                ad->numTypes, ad->hist, ad->partials.as<double>(), ad->dResult, ad->dTicket, activeList, activeCount);
         MB_LAUNCHED();
     }
     if (ad->runCounter % ad->updateInterval == 0)
@@ -335,7 +562,10 @@ int mrmd_b200_adress_run(mrmd_b200_adress* ad, mrmd_b200_molecules* m, const mrm
     if (energy != nullptr || numPairs != nullptr)
     {
         MB_CUDA(cudaMemcpyAsync(ad->hResult, ad->dResult, 24, cudaMemcpyDeviceToHost, st));
-        MB_CUDA(cudaStreamSynchronize(st));
+        if (ad->uniformAtoms == AD_LANES)
+            MB_TRY(adressCheckUniform(ad, st));
+        else
+            MB_CUDA(cudaStreamSynchronize(st));
         if (energy) *energy = ad->hResult[0];
         if (numPairs) *numPairs = static_cast<int64_t>(ad->hResult[1] + 0.5);
     }
@@ -364,6 +594,18 @@ int mrmd_b200_adress_run_periodic(mrmd_b200_adress* ad, mrmd_b200_atoms* a, cons
 
 namespace mrmd_b200
 {
+int adressCheckUniform(mrmd_b200_adress* ad, cudaStream_t st)
+{
+    MB_CUDA(cudaMemcpyAsync(ad->hErr, ad->dErr, 4, cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaStreamSynchronize(st));
+    if (*ad->hErr != 0)
+    {
+        cudaMemsetAsync(ad->dErr, 0, 4, st);
+        MB_REQUIRE(false, "adress_run: a molecule does not have the atom count promised by adress_set_atoms_per_molecule");
+    }
+    return 0;
+}
+
 int adressRunPeriodic(mrmd_b200_adress* ad, mrmd_b200_atoms* a, const mrmd_b200_verlet* v, const mrmd_b200_weight* w,
                       bool energy, cudaStream_t st)
 {

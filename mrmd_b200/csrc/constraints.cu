@@ -15,9 +15,11 @@ struct mrmd_b200_constraints
     int64_t atomsPerMolecule = 0;
     int64_t numIterations = 0;
     int64_t numBonds = 0;
+    int64_t maxBondAtoms = 0;       // 1 + the largest atom index a bond names: <= 4 takes the fused SHAKE kernel
     mrmd_b200::DevBuf bondIdx;      // int64 {idx, jdx} per bond
     mrmd_b200::DevBuf bondDist;     // double eqDistance per bond
     mrmd_b200::DevBuf updatedPos;   // double4 per atom (impl::Shake::updatedPos_)
+    int* dErr = nullptr;            // set by a kernel that meets a bond outside its molecule
 };
 
 namespace mrmd_b200
@@ -98,6 +100,87 @@ __global__ void shakePositionalKernel(MolsView m, AtomsView a, int64_t numLocalM
     }
 }
 
+// All numConstraintIterations of enforcePositionalConstraints in one pass for bonds among the first NA <= 4 atoms of
+// a molecule: the unconstrained update of an iteration only feeds the bonds of the atom's own molecule, so a thread
+// keeps its molecule's {pos, pos + dtv vel, force, mass, updatedPos} in shared memory (slot-major, conflict free),
+// walks iterations x bonds like the two-kernel sequence does, and writes the forces back once: 112 B per atom of HBM
+// traffic instead of numIterations x (112 + gathers).
+constexpr int SHAKE_FUSED_THREADS = 64;
+constexpr int SHAKE_FUSED_SLOTS = 14;
+template <int NA>
+__global__ void __launch_bounds__(SHAKE_FUSED_THREADS)
+    shakeFusedKernel(MolsView m, AtomsView a, int64_t numLocalMols, const long long* __restrict__ bondIdx,
+                     const double* __restrict__ bondDist, int64_t numBonds, int64_t numIterations, double dtv, double dtf,
+                     int* error)
+{
+    __shared__ double sm[SHAKE_FUSED_SLOTS * NA * SHAKE_FUSED_THREADS];
+    const int64_t mol = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (mol >= numLocalMols) return;
+    const longlong2 oc = m.oc[mol];
+    if (oc.y < NA)  // some bond names an atom the molecule does not have
+    {
+        *error = 1;
+        return;
+    }
+    auto at = [&](int slot, long long atom) -> double& { return sm[(slot * NA + atom) * SHAKE_FUSED_THREADS + threadIdx.x]; };
+    enum { POS = 0, BASE = 3, FORCE = 6, MASS = 9, UPD = 10, INVMASS = 13 };
+#pragma unroll
+    for (int k = 0; k < NA; ++k)
+    {
+        const double4 p = ld4(a.pos + oc.x + k);
+        const double pk[3] = {p.x, p.y, p.z};
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+        {
+            at(POS + d, k) = pk[d];
+            at(BASE + d, k) = pk[d] + dtv * a.vel[d][oc.x + k];
+            at(FORCE + d, k) = a.force[d][oc.x + k];
+        }
+        at(MASS, k) = a.mass[oc.x + k];
+        at(INVMASS, k) = 1.0 / at(MASS, k);  // the same quotient for every bond of the atom
+    }
+    for (int64_t it = 0; it < numIterations; ++it)
+    {
+#pragma unroll
+        for (int k = 0; k < NA; ++k)  // Shake::operator()(UnconstraintUpdate, idx), Shake.hpp:131-137
+        {
+            const double dtfm = dtf / at(MASS, k);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) at(UPD + d, k) = at(BASE + d, k) + dtfm * at(FORCE + d, k);
+        }
+        for (int64_t b = 0; b < numBonds; ++b)  // Shake::enforcePositionalConstraint, :84-128
+        {
+            const long long i = bondIdx[2 * b], j = bondIdx[2 * b + 1];
+            const double eqDistance = bondDist[b];
+            const double dist[3] = {at(POS, i) - at(POS, j), at(POS + 1, i) - at(POS + 1, j), at(POS + 2, i) - at(POS + 2, j)};
+            const double distSq = dist[0] * dist[0] + dist[1] * dist[1] + dist[2] * dist[2];
+            const double upd[3] = {at(UPD, i) - at(UPD, j), at(UPD + 1, i) - at(UPD + 1, j), at(UPD + 2, i) - at(UPD + 2, j)};
+            const double updSq = upd[0] * upd[0] + upd[1] * upd[1] + upd[2] * upd[2];
+            const double invMassI = at(INVMASS, i), invMassJ = at(INVMASS, j);
+            const double qa = (invMassI + invMassJ) * (invMassI + invMassJ) * distSq;
+            const double qb = 2.0 * (invMassI + invMassJ) * (upd[0] * dist[0] + upd[1] * dist[1] + upd[2] * dist[2]);
+            const double qc = updSq - eqDistance * eqDistance;
+            double determinant = qb * qb - 4.0 * qa * qc;
+            determinant = fmax(0.0, determinant);
+            const double root = sqrt(determinant);
+            const double lambda1 = (-qb + root) / (2.0 * qa);
+            const double lambda2 = (-qb - root) / (2.0 * qa);
+            double lambda = (fabs(lambda1) < fabs(lambda2)) ? lambda1 : lambda2;
+            lambda /= dtf;
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+            {
+                at(FORCE + d, i) += lambda * dist[d];
+                at(FORCE + d, j) -= lambda * dist[d];
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NA; ++k)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) a.force[d][oc.x + k] = at(FORCE + d, k);
+}
+
 // MoleculeConstraints::enforceVelocityConstraints lambda (Shake.hpp:215-231) with
 // Shake::enforceVelocityConstraint (:56-82) inlined
 __global__ void shakeVelocityKernel(MolsView m, AtomsView a, int64_t numLocalMols, const long long* __restrict__ bondIdx,
@@ -130,13 +213,126 @@ __global__ void shakeVelocityKernel(MolsView m, AtomsView a, int64_t numLocalMol
     }
 }
 
+// enforceVelocityConstraints for bonds among the first NA <= 4 atoms of a molecule: {pos, vel, 1 / mass} of the
+// molecule in shared memory, the bonds walked in order, the velocities written back once
+template <int NA>
+__global__ void __launch_bounds__(SHAKE_FUSED_THREADS)
+    rattleFusedKernel(MolsView m, AtomsView a, int64_t numLocalMols, const long long* __restrict__ bondIdx, int64_t numBonds,
+                      int* error)
+{
+    __shared__ double sm[7 * NA * SHAKE_FUSED_THREADS];
+    const int64_t mol = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (mol >= numLocalMols) return;
+    const longlong2 oc = m.oc[mol];
+    if (oc.y < NA)
+    {
+        *error = 1;
+        return;
+    }
+    auto at = [&](int slot, long long atom) -> double& { return sm[(slot * NA + atom) * SHAKE_FUSED_THREADS + threadIdx.x]; };
+    enum { POS = 0, VEL = 3, INVMASS = 6 };
+#pragma unroll
+    for (int k = 0; k < NA; ++k)
+    {
+        const double4 p = ld4(a.pos + oc.x + k);
+        at(POS, k) = p.x;
+        at(POS + 1, k) = p.y;
+        at(POS + 2, k) = p.z;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) at(VEL + d, k) = a.vel[d][oc.x + k];
+        at(INVMASS, k) = 1.0 / a.mass[oc.x + k];
+    }
+    for (int64_t b = 0; b < numBonds; ++b)  // Shake::enforceVelocityConstraint, Shake.hpp:56-82
+    {
+        const long long i = bondIdx[2 * b], j = bondIdx[2 * b + 1];
+        const double dist[3] = {at(POS, i) - at(POS, j), at(POS + 1, i) - at(POS + 1, j), at(POS + 2, i) - at(POS + 2, j)};
+        const double distSq = dist[0] * dist[0] + dist[1] * dist[1] + dist[2] * dist[2];
+        const double invMassI = at(INVMASS, i), invMassJ = at(INVMASS, j);
+        const double reducedMass = 1.0 / (invMassI + invMassJ);
+        const double relVel[3] = {at(VEL, i) - at(VEL, j), at(VEL + 1, i) - at(VEL + 1, j), at(VEL + 2, i) - at(VEL + 2, j)};
+        const double factor = (relVel[0] * dist[0] + relVel[1] * dist[1] + relVel[2] * dist[2]) / distSq * reducedMass;
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+        {
+            at(VEL + d, i) -= factor * dist[d] * invMassI;
+            at(VEL + d, j) += factor * dist[d] * invMassJ;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NA; ++k)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) a.vel[d][oc.x + k] = at(VEL + d, k);
+}
+
 static int checkBondError(int* dErr, cudaStream_t st)
 {
     int h = 0;
     MB_CUDA(cudaMemcpyAsync(&h, dErr, 4, cudaMemcpyDeviceToHost, st));
     MB_CUDA(cudaStreamSynchronize(st));  // the reference fences after every kernel too
-    cudaFree(dErr);
     MB_REQUIRE(h == 0, "not enough atoms in molecule to satisfy bond");
+    return 0;
+}
+
+// the launches of enforcePositionalConstraints / enforceVelocityConstraints without the read-back of the bond-range
+// flag (step-loop drivers validate the bonds once and must not synchronise every step)
+int constraintsEnforcePositional(mrmd_b200_constraints* c, const mrmd_b200_molecules* m, mrmd_b200_atoms* a, double dt,
+                                 cudaStream_t st)
+{
+    MB_CUDA(cudaMemsetAsync(c->dErr, 0, 4, st));
+    const int64_t nAll = a->numLocal + a->numGhost;
+    if (nAll == 0 || c->numIterations == 0) return 0;
+    const double dtv = dt, dtf = 0.5 * dt * dt;  // Shake.hpp:148-149
+    if (c->maxBondAtoms >= 2 && c->maxBondAtoms <= 4)
+    {
+        if (m->numLocal == 0 || c->numBonds == 0) return 0;
+        const int blocks = gridFor(m->numLocal, SHAKE_FUSED_THREADS);
+#define MB_SHAKE_FUSED(NA)                                                                                              \
+    shakeFusedKernel<NA><<<blocks, SHAKE_FUSED_THREADS, 0, st>>>(m->v, a->v, m->numLocal, c->bondIdx.as<long long>(),   \
+                                                                 c->bondDist.as<double>(), c->numBonds, c->numIterations, \
+                                                                 dtv, dtf, c->dErr)
+        if (c->maxBondAtoms == 2) MB_SHAKE_FUSED(2);
+        else if (c->maxBondAtoms == 3) MB_SHAKE_FUSED(3);
+        else MB_SHAKE_FUSED(4);
+#undef MB_SHAKE_FUSED
+        MB_LAUNCHED();
+        return 0;
+    }
+    MB_TRY(c->updatedPos.reserve(size_t(nAll) * 32));  // util::grow(updatedPos_, ...), Shake.hpp:146
+    for (int64_t it = 0; it < c->numIterations; ++it)
+    {
+        shakeUnconstraintKernel<<<gridFor(nAll, 256), 256, 0, st>>>(a->v, nAll, dtv, dtf, c->updatedPos.as<double4>());
+        MB_LAUNCHED();
+        if (m->numLocal > 0 && c->numBonds > 0)
+        {
+            shakePositionalKernel<<<gridFor(m->numLocal, 128), 128, 0, st>>>(
+                m->v, a->v, m->numLocal, c->bondIdx.as<long long>(), c->bondDist.as<double>(), c->numBonds,
+                c->updatedPos.as<double4>(), dtf, c->dErr);
+            MB_LAUNCHED();
+        }
+    }
+    return 0;
+}
+
+int constraintsEnforceVelocity(mrmd_b200_constraints* c, const mrmd_b200_molecules* m, mrmd_b200_atoms* a, cudaStream_t st)
+{
+    MB_CUDA(cudaMemsetAsync(c->dErr, 0, 4, st));
+    if (m->numLocal == 0 || c->numBonds == 0) return 0;
+    if (c->maxBondAtoms >= 2 && c->maxBondAtoms <= 4)
+    {
+        const int blocks = gridFor(m->numLocal, SHAKE_FUSED_THREADS);
+#define MB_RATTLE_FUSED(NA)                                                                                            \
+    rattleFusedKernel<NA><<<blocks, SHAKE_FUSED_THREADS, 0, st>>>(m->v, a->v, m->numLocal, c->bondIdx.as<long long>(),  \
+                                                                  c->numBonds, c->dErr)
+        if (c->maxBondAtoms == 2) MB_RATTLE_FUSED(2);
+        else if (c->maxBondAtoms == 3) MB_RATTLE_FUSED(3);
+        else MB_RATTLE_FUSED(4);
+#undef MB_RATTLE_FUSED
+        MB_LAUNCHED();
+        return 0;
+    }
+    shakeVelocityKernel<<<gridFor(m->numLocal, 128), 128, 0, st>>>(m->v, a->v, m->numLocal, c->bondIdx.as<long long>(),
+                                                                   c->numBonds, c->dErr);
+    MB_LAUNCHED();
     return 0;
 }
 }  // namespace mrmd_b200
@@ -182,6 +378,12 @@ int mrmd_b200_constraints_create(mrmd_b200_constraints** out, int64_t atomsPerMo
     auto* c = new mrmd_b200_constraints;
     c->atomsPerMolecule = atomsPerMolecule;
     c->numIterations = numConstraintIterations;
+    if (cudaMalloc(&c->dErr, 4) != cudaSuccess)
+    {
+        delete c;
+        setLastError("constraints_create: out of device memory");
+        return MRMD_B200_ENOMEM;
+    }
     *out = c;
     return 0;
 }
@@ -193,6 +395,7 @@ int mrmd_b200_constraints_destroy(mrmd_b200_constraints* c)
     c->bondIdx.release();
     c->bondDist.release();
     c->updatedPos.release();
+    if (c->dErr) cudaFree(c->dErr);
     delete c;
     return 0;
 }
@@ -203,11 +406,13 @@ int mrmd_b200_constraints_set(mrmd_b200_constraints* c, const int64_t* idx, cons
     MB_TRY(checkDevice());
     MB_REQUIRE(c != nullptr && numBonds >= 0 && (numBonds == 0 || (idx && jdx && eqDistance)), "constraints_set");
     std::vector<long long> pairs(static_cast<size_t>(2 * numBonds));
+    c->maxBondAtoms = 0;
     for (int64_t b = 0; b < numBonds; ++b)
     {
         MB_REQUIRE(idx[b] >= 0 && jdx[b] >= 0, "constraints_set: negative atom index");
         pairs[static_cast<size_t>(2 * b)] = idx[b];
         pairs[static_cast<size_t>(2 * b + 1)] = jdx[b];
+        c->maxBondAtoms = std::max<int64_t>(c->maxBondAtoms, std::max(idx[b], jdx[b]) + 1);
     }
     MB_TRY(c->bondIdx.reserve(std::max<size_t>(pairs.size() * 8, 16)));
     MB_TRY(c->bondDist.reserve(std::max<size_t>(size_t(numBonds) * 8, 8)));
@@ -225,27 +430,8 @@ int mrmd_b200_constraints_enforce_positional(mrmd_b200_constraints* c, const mrm
 {
     MB_TRY(checkDevice());
     MB_REQUIRE(c != nullptr && m != nullptr && a != nullptr, "constraints_enforce_positional");
-    cudaStream_t st = S(stream);
-    const int64_t nAll = a->numLocal + a->numGhost;
-    if (nAll == 0 || c->numIterations == 0) return 0;
-    MB_TRY(c->updatedPos.reserve(size_t(nAll) * 32));  // util::grow(updatedPos_, ...), Shake.hpp:146
-    const double dtv = dt, dtf = 0.5 * dt * dt;         // :148-149
-    int* dErr = nullptr;
-    MB_CUDA(cudaMalloc(&dErr, 4));
-    MB_CUDA(cudaMemsetAsync(dErr, 0, 4, st));
-    for (int64_t it = 0; it < c->numIterations; ++it)
-    {
-        shakeUnconstraintKernel<<<gridFor(nAll, 256), 256, 0, st>>>(a->v, nAll, dtv, dtf, c->updatedPos.as<double4>());
-        MB_LAUNCHED();
-        if (m->numLocal > 0 && c->numBonds > 0)
-        {
-            shakePositionalKernel<<<gridFor(m->numLocal, 128), 128, 0, st>>>(
-                m->v, a->v, m->numLocal, c->bondIdx.as<long long>(), c->bondDist.as<double>(), c->numBonds,
-                c->updatedPos.as<double4>(), dtf, dErr);
-            MB_LAUNCHED();
-        }
-    }
-    return checkBondError(dErr, st);
+    MB_TRY(constraintsEnforcePositional(c, m, a, dt, S(stream)));
+    return checkBondError(c->dErr, S(stream));
 }
 
 int mrmd_b200_constraints_enforce_velocity(mrmd_b200_constraints* c, const mrmd_b200_molecules* m, mrmd_b200_atoms* a,
@@ -254,15 +440,8 @@ int mrmd_b200_constraints_enforce_velocity(mrmd_b200_constraints* c, const mrmd_
     MB_TRY(checkDevice());
     MB_REQUIRE(c != nullptr && m != nullptr && a != nullptr, "constraints_enforce_velocity");
     (void)dt;  // Shake(atoms, dt) only feeds the positional update (Shake.hpp:139-150)
-    cudaStream_t st = S(stream);
-    if (m->numLocal == 0 || c->numBonds == 0) return 0;
-    int* dErr = nullptr;
-    MB_CUDA(cudaMalloc(&dErr, 4));
-    MB_CUDA(cudaMemsetAsync(dErr, 0, 4, st));
-    shakeVelocityKernel<<<gridFor(m->numLocal, 128), 128, 0, st>>>(m->v, a->v, m->numLocal, c->bondIdx.as<long long>(),
-                                                                   c->numBonds, dErr);
-    MB_LAUNCHED();
-    return checkBondError(dErr, st);
+    MB_TRY(constraintsEnforceVelocity(c, m, a, S(stream)));
+    return checkBondError(c->dErr, S(stream));
 }
 
 }  // extern "C"

@@ -38,9 +38,15 @@ struct mrmd_b200_adress
     int (*preUpdateHook)(void* ctx, double* sums, int64_t count, cudaStream_t st) = nullptr;
     void* hookCtx = nullptr;
     mrmd_b200::DevBuf partials;
+    mrmd_b200::DevBuf activeList;  // int32[numLocalMolecules] + the count: molecules with work in the current run
     double* dResult = nullptr;  // [0..2] energy, pairs, - of the last run; [3..5] running sums
     unsigned int* dTicket = nullptr;
     double* hResult = nullptr;
+    // mrmd_b200_adress_set_atoms_per_molecule: 4 selects the four-lanes-per-molecule kernel; a molecule with another
+    // atom count raises *dErr, reported by the next call that reads results back
+    int64_t uniformAtoms = 0;
+    int* dErr = nullptr;
+    int* hErr = nullptr;  // pinned
 };
 
 struct mrmd_b200_thermo
@@ -74,8 +80,14 @@ int adressApplyTiled(mrmd_b200_adress* ad, mrmd_b200_atoms* a, const mrmd_b200_v
                      bool sampling, bool energy, cudaStream_t st);
 // adress.cu: mrmd_b200_adress_run_periodic with the energy accumulation optional (the drivers want it on the last
 // step of a run only)
+// adress.cu: reads the atoms-per-molecule flag of the four-lane kernel back (synchronises the stream)
+int adressCheckUniform(mrmd_b200_adress* ad, cudaStream_t st);
 int adressRunPeriodic(mrmd_b200_adress* ad, mrmd_b200_atoms* a, const mrmd_b200_verlet* v, const mrmd_b200_weight* w,
                       bool energy, cudaStream_t st);
+// constraints.cu: SHAKE / RATTLE launches without the bond-range read-back and its stream synchronisation
+int constraintsEnforcePositional(mrmd_b200_constraints* c, const mrmd_b200_molecules* m, mrmd_b200_atoms* a, double dt,
+                                 cudaStream_t st);
+int constraintsEnforceVelocity(mrmd_b200_constraints* c, const mrmd_b200_molecules* m, mrmd_b200_atoms* a, cudaStream_t st);
 int verletBuildTiled(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, const mrmd_b200_subdomain* s, double radius,
                      double cellRatio, int64_t maxNeigh, const int32_t* haloLeft, const int32_t* haloRight,
                      cudaStream_t st);

@@ -5,6 +5,7 @@
 // unit-test usage of the operators.
 #include <algorithm>
 #include <cfloat>
+#include <cstdlib>
 #include <vector>
 
 #include "handles.cuh"
@@ -20,6 +21,7 @@ struct mrmd_b200_md
     mrmd_b200_lj* lj = nullptr;
     mrmd_b200_adress* adress = nullptr;
     mrmd_b200_thermo* thermo = nullptr;
+    mrmd_b200_constraints* constraints = nullptr;  // multi-atom molecules with numConstraintIterations > 0
     double maxDisplacement = DBL_MAX;  // examples/02:110
     int64_t step = 0;
     int64_t rebuilds = 0;
@@ -37,10 +39,10 @@ struct mrmd_b200_md
 
 namespace mrmd_b200
 {
-__global__ void moleculePerAtomInitKernel(MolsView m, int64_t n)
+__global__ void moleculePerAtomInitKernel(MolsView m, int64_t n, int64_t atomsPerMolecule)
 {
     const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-    if (i < n) m.oc[i] = make_longlong2(i, 1);
+    if (i < n) m.oc[i] = make_longlong2(i * atomsPerMolecule, atomsPerMolecule);
 }
 
 static int rebuild(mrmd_b200_md* md, cudaStream_t st)
@@ -118,6 +120,12 @@ static int rebuild(mrmd_b200_md* md, cudaStream_t st)
 // one step; evStart/evStop (optional) bracket the force kernel
 static int postIntegrate(mrmd_b200_md* md, bool deferPost, cudaStream_t st)
 {
+    if (md->constraints != nullptr)
+    {
+        // RATTLE needs the kicked velocities: no deferral (tests/Constraints/Constraints.cpp:62-64)
+        MB_TRY(mrmd_b200_vv_post(md->atoms, md->cfg.dt, st));
+        return constraintsEnforceVelocity(md->constraints, md->mols, md->atoms, st);
+    }
     if (deferPost)
     {
         md->postPending = true;
@@ -132,6 +140,8 @@ static int oneStep(mrmd_b200_md* md, cudaStream_t st, cudaEvent_t evStart, cudaE
 {
     const mrmd_b200_md_config& c = md->cfg;
     mrmd_b200_atoms* a = md->atoms;
+    if (md->constraints != nullptr)  // tests/Constraints/Constraints.cpp:53-54
+        MB_TRY(constraintsEnforcePositional(md->constraints, md->mols, a, c.dt, st));
     MB_TRY(integratePre(a, c.dt, c.integrator == 1, c.zeta, c.temperature, c.seed, uint64_t(md->step), nullptr,
                         md->postPending, st));
     md->postPending = false;
@@ -220,6 +230,7 @@ static int collectStats(mrmd_b200_md* md, int64_t nsteps, int64_t rebuilds0, int
     double* hRes = md->cfg.adress ? md->adress->hResult : md->lj->hResult;
     MB_CUDA(cudaMemcpyAsync(hRes, dRes, 48, cudaMemcpyDeviceToHost, st));
     MB_CUDA(cudaStreamSynchronize(st));
+    if (md->cfg.adress && md->adress->uniformAtoms > 0) MB_TRY(adressCheckUniform(md->adress, st));
     if (stats == nullptr) return 0;
     stats->steps = nsteps;
     stats->rebuilds = md->rebuilds - rebuilds0;
@@ -275,6 +286,12 @@ int mrmd_b200_md_create(mrmd_b200_md** out, const mrmd_b200_md_config* cfg, cons
     MB_REQUIRE(out != nullptr && cfg != nullptr && s != nullptr && atoms != nullptr, "md_create");
     MB_REQUIRE(cfg->dt > 0.0 && cfg->rc > 0.0 && cfg->skin >= 0.0 && cfg->maxNeighbors > 0, "md_create: bad config");
     MB_REQUIRE(!(cfg->adress && cfg->fullList == 1), "md_create: LJ_IdealGas takes a half list (0) or the tiled list (2)");
+    const int64_t apm = std::max<int64_t>(cfg->atomsPerMolecule, 1);
+    MB_REQUIRE(apm == 1 || (cfg->adress && cfg->fullList == 0 && cfg->cellSort == 0),
+               "md_create: multi-atom molecules need adress = 1, fullList = 0, cellSort = 0");
+    MB_REQUIRE(atoms->numLocal % apm == 0, "md_create: local atoms are not a multiple of atomsPerMolecule");
+    MB_REQUIRE(cfg->numConstraintIterations >= 0 && (cfg->numConstraintIterations == 0 || (apm > 1 && cfg->bondLength > 0.0)),
+               "md_create: constraints need multi-atom molecules and a positive bond length");
     auto* md = new mrmd_b200_md;
     md->cfg = *cfg;
     md->sub = *s;
@@ -293,15 +310,34 @@ int mrmd_b200_md_create(mrmd_b200_md** out, const mrmd_b200_md_config* cfg, cons
     {
         rc = mrmd_b200_adress_create(&md->adress, &cfg->cappingDistance, &cfg->rc, &cfg->sigma, &cfg->epsilon, 1,
                                      cfg->doShift);
-        if (rc == 0) rc = mrmd_b200_molecules_create(&md->mols, std::max<int64_t>(atoms->numLocal, 1));
-        if (rc == 0 && atoms->numLocal > 0)
+        // four-lane kernel; MRMD_B200_ADRESS_NO_LANES=1 keeps the thread-per-molecule kernel (diagnostics)
+        if (rc == 0 && apm == 4 && std::getenv("MRMD_B200_ADRESS_NO_LANES") == nullptr)
+            rc = mrmd_b200_adress_set_atoms_per_molecule(md->adress, 4);
+        const int64_t numMols = atoms->numLocal / apm;
+        if (rc == 0) rc = mrmd_b200_molecules_create(&md->mols, std::max<int64_t>(numMols, 1));
+        if (rc == 0 && numMols > 0)
         {
-            // data::createMoleculeForEachAtom (data/MoleculesFromAtoms.cpp:19-39) for the local atoms
-            md->mols->size = atoms->numLocal;
-            md->mols->numLocal = atoms->numLocal;
-            moleculePerAtomInitKernel<<<gridFor(atoms->numLocal, 256), 256>>>(md->mols->v, atoms->numLocal);
+            // data::createMoleculeForEachAtom (data/MoleculesFromAtoms.cpp:19-39) for the local atoms, or molecules
+            // of atomsPerMolecule consecutive atoms
+            md->mols->size = numMols;
+            md->mols->numLocal = numMols;
+            moleculePerAtomInitKernel<<<gridFor(numMols, 256), 256>>>(md->mols->v, numMols, apm);
             g_launchCount.fetch_add(1);
             if (cudaDeviceSynchronize() != cudaSuccess) rc = MRMD_B200_EINVAL;
+        }
+        if (rc == 0 && cfg->numConstraintIterations > 0)
+        {
+            rc = mrmd_b200_constraints_create(&md->constraints, apm, cfg->numConstraintIterations);
+            std::vector<int64_t> bi, bj;
+            std::vector<double> eq;
+            for (int64_t i = 0; i < apm; ++i)
+                for (int64_t j = i + 1; j < apm; ++j)
+                {
+                    bi.push_back(i);
+                    bj.push_back(j);
+                    eq.push_back(cfg->bondLength);
+                }
+            if (rc == 0) rc = mrmd_b200_constraints_set(md->constraints, bi.data(), bj.data(), eq.data(), int64_t(eq.size()));
         }
         if (rc == 0 && cfg->useThermoForce)
             rc = mrmd_b200_thermo_create(&md->thermo, &cfg->thermoTargetDensity, 1, s, cfg->thermoBinWidth,
@@ -331,6 +367,7 @@ int mrmd_b200_md_destroy(mrmd_b200_md* md)
     mrmd_b200_lj_destroy(md->lj);
     mrmd_b200_adress_destroy(md->adress);
     mrmd_b200_thermo_destroy(md->thermo);
+    mrmd_b200_constraints_destroy(md->constraints);
     mrmd_b200_molecules_destroy(md->mols);
     delete md;
     return 0;

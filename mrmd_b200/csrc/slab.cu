@@ -897,6 +897,8 @@ int mrmd_b200_slab_create_cuts(mrmd_b200_slab** out, const mrmd_b200_md_config* 
     MB_TRY(checkDevice());
     MB_REQUIRE(out && cfg && globalMin && globalMax && uniqueId128 && atoms, "slab_create");
     MB_REQUIRE(nranks >= 2 && rank >= 0 && rank < nranks, "slab_create: needs at least two ranks");
+    MB_REQUIRE(cfg->atomsPerMolecule <= 1 && cfg->numConstraintIterations == 0,
+               "slab_create: the x-slab decomposition handles one-atom molecules only");
     if (cfg->adress)
     {
         // the tiled AdResS kernel evaluates lambda at image positions: across the global periodic x faces (and y, z

@@ -96,9 +96,12 @@ class OracleAdressMD:
     ContributeMoleculeForceToAtoms -> MultiResGhostLayer, Langevin integrator, spatial sort at every rebuild."""
 
     def __init__(self, pos, vel, box, weight, dt=0.002, rc=2.5, skin=0.1, sigma=1.0, epsilon=1.0, cap=0.7,
-                 max_neigh=60, langevin=True, zeta=20.0, temperature=1.5, seed=1234, thermo=None, do_shift=True):
+                 max_neigh=60, langevin=True, zeta=20.0, temperature=1.5, seed=1234, thermo=None, do_shift=True,
+                 atoms_per_mol=1, constraint_iterations=0, bond_length=1.0):
         self.L = orc.lib()
         self.n = n = len(pos)
+        self.apm = apm = atoms_per_mol
+        self.nm = nm = n // apm
         self.box = np.asarray(box, dtype=np.float64)
         self.cutoff = rc + skin
         self.sub = orc.subdomain([0, 0, 0], self.box, self.cutoff)
@@ -106,10 +109,15 @@ class OracleAdressMD:
         cap_atoms = int(n * (1.0 + 1.3 * frac + 0.05)) + 1024
         self.atoms = np.zeros(cap_atoms, dtype=orc.ATOM)
         self.atoms["pos"][:n], self.atoms["vel"][:n] = pos, vel
-        self.atoms["mass"][:n] = self.atoms["relMass"][:n] = 1.0
-        self.mols = np.zeros(cap_atoms, dtype=orc.MOLECULE)
-        self.mols["atomsOffset"][:n], self.mols["numAtoms"][:n] = np.arange(n), 1
+        self.atoms["mass"][:n], self.atoms["relMass"][:n] = 1.0, 1.0 / apm
+        self.mols = np.zeros(cap_atoms // apm + 1, dtype=orc.MOLECULE)
+        self.mols["atomsOffset"][:nm], self.mols["numAtoms"][:nm] = np.arange(nm) * apm, apm
         self.corr = np.full(cap_atoms, -1, dtype=np.int64)
+        # MoleculeConstraints(apm, constraint_iterations) with a bond between every two atoms of a molecule
+        self.constraint_iterations = constraint_iterations
+        pairs = [(i, j) for i in range(apm) for j in range(i + 1, apm)]
+        self.bond_idx = np.ascontiguousarray(pairs, dtype=np.int64).reshape(-1)
+        self.bond_eq = np.full(len(pairs), float(bond_length))
         self.weight = weight
         one = [np.array([float(v)]) for v in (cap, rc, sigma, epsilon)]
         self._keep = one
@@ -127,30 +135,34 @@ class OracleAdressMD:
         self._cid, self._perm = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int64)
 
     def _rebuild(self):
-        L, a, m, n = self.L, self.atoms, self.mols, self.n
-        L.or_update_molecules(m.ctypes.data, n, a.ctypes.data, C.byref(self.weight))
-        L.or_mr_periodic_map(m.ctypes.data, n, a.ctypes.data, C.byref(self.sub))
-        delta = np.array([self.cutoff, self.cutoff, 0.25 * self.cutoff])
-        lo, hi = np.zeros(3), self.box
-        nc = L.or_cell_ids(a.ctypes.data, 13, 0, n, delta.ctypes.data, lo.ctypes.data, hi.ctypes.data,
-                           self._cid.ctypes.data, None)
-        off = np.zeros(nc + 1, dtype=np.int64)
-        L.or_cell_perm(self._cid.ctypes.data, 0, n, nc, self._perm.ctypes.data, off.ctypes.data)
-        L.or_permute_atoms(a.ctypes.data, 0, n, self._perm.ctypes.data)  # one atom per molecule: offsets stay i -> i
-        L.or_update_molecules(m.ctypes.data, n, a.ctypes.data, C.byref(self.weight))
+        L, a, m, n, nm = self.L, self.atoms, self.mols, self.n, self.nm
+        L.or_update_molecules(m.ctypes.data, nm, a.ctypes.data, C.byref(self.weight))
+        L.or_mr_periodic_map(m.ctypes.data, nm, a.ctypes.data, C.byref(self.sub))
+        if self.apm == 1:
+            delta = np.array([self.cutoff, self.cutoff, 0.25 * self.cutoff])
+            lo, hi = np.zeros(3), self.box
+            nc = L.or_cell_ids(a.ctypes.data, 13, 0, n, delta.ctypes.data, lo.ctypes.data, hi.ctypes.data,
+                               self._cid.ctypes.data, None)
+            off = np.zeros(nc + 1, dtype=np.int64)
+            L.or_cell_perm(self._cid.ctypes.data, 0, n, nc, self._perm.ctypes.data, off.ctypes.data)
+            L.or_permute_atoms(a.ctypes.data, 0, n, self._perm.ctypes.data)  # one atom per molecule: offsets stay i -> i
+            L.or_update_molecules(m.ctypes.data, nm, a.ctypes.data, C.byref(self.weight))
         out = np.zeros(2, dtype=np.int64)
-        rc = L.or_mr_ghost_create_xyz(m.ctypes.data, n, len(m), a.ctypes.data, n, len(a), C.byref(self.sub),
+        rc = L.or_mr_ghost_create_xyz(m.ctypes.data, nm, len(m), a.ctypes.data, n, len(a), C.byref(self.sub),
                                       self.corr.ctypes.data, out.ctypes.data)
         assert rc == 0, "oracle ghost capacity exceeded"
         self.mg, self.ng = int(out[0]), int(out[1])
-        L.or_update_molecules(m.ctypes.data, n + self.mg, a.ctypes.data, C.byref(self.weight))
-        self.counts, self.neigh = orc.verlet_build(m, 13, n + self.mg, 0, n, self.cutoff, 1.0,
+        L.or_update_molecules(m.ctypes.data, nm + self.mg, a.ctypes.data, C.byref(self.weight))
+        self.counts, self.neigh = orc.verlet_build(m, 13, nm + self.mg, 0, nm, self.cutoff, 1.0,
                                                    np.array(self.sub.minGhostCorner), np.array(self.sub.maxGhostCorner),
                                                    half=True, width=self.max_neigh)
         self.rebuilds += 1
 
     def one_step(self):
-        L, a, m, n = self.L, self.atoms, self.mols, self.n
+        L, a, m, n, nm = self.L, self.atoms, self.mols, self.n, self.nm
+        if self.constraint_iterations > 0:
+            assert L.or_shake_positional(m.ctypes.data, nm, a.ctypes.data, n + self.ng, self.bond_idx.ctypes.data,
+                                         self.bond_eq.ctypes.data, len(self.bond_eq), self.constraint_iterations, self.dt) == 0
         if self.langevin:
             d = L.or_langevin_pre(a.ctypes.data, n, self.dt, self.zeta, self.temperature, self.seed, self.step, None)
         else:
@@ -161,11 +173,11 @@ class OracleAdressMD:
             self._rebuild()
         else:
             L.or_ghost_update_pos(a.ctypes.data, n, self.ng, self.corr.ctypes.data, C.byref(self.sub))
-            L.or_update_molecules(m.ctypes.data, n + self.mg, a.ctypes.data, C.byref(self.weight))
+            L.or_update_molecules(m.ctypes.data, nm + self.mg, a.ctypes.data, C.byref(self.weight))
         L.or_zero_force(a.ctypes.data, n + self.ng)
-        m["force"][:n + self.mg] = 0.0
+        m["force"][:nm + self.mg] = 0.0
         nact = C.c_int64()
-        self.energy = L.or_adress_run(self.adress, m.ctypes.data, n, self.counts.ctypes.data, self.neigh.ctypes.data,
+        self.energy = L.or_adress_run(self.adress, m.ctypes.data, nm, self.counts.ctypes.data, self.neigh.ctypes.data,
                                       self.neigh.shape[1], a.ctypes.data, C.byref(nact))
         self.pairs += nact.value
         if self.thermo is not None:
@@ -175,9 +187,11 @@ class OracleAdressMD:
             if self.step > 0 and self.step % t["updateInterval"] == 0 and self.thermo.contents.samples > 0:
                 L.or_thermo_update(self.thermo, t["sigma"], t["range"], None)
             L.or_thermo_apply(self.thermo, a.ctypes.data, n, None, 0)
-        L.or_contribute_molecule_force(m.ctypes.data, n + self.mg, a.ctypes.data)
+        L.or_contribute_molecule_force(m.ctypes.data, nm + self.mg, a.ctypes.data)
         L.or_ghost_fold_force(a.ctypes.data, n, self.ng, self.corr.ctypes.data)
         L.or_vv_post(a.ctypes.data, n, self.dt)
+        if self.constraint_iterations > 0:
+            assert L.or_shake_velocity(m.ctypes.data, nm, a.ctypes.data, self.bond_idx.ctypes.data, len(self.bond_eq)) == 0
         self.step += 1
 
     def run(self, nsteps):

@@ -111,10 +111,12 @@ def adress_system(n_side, atoms_per_mol, seed):
     return sites, apos, box, m
 
 
-@pytest.mark.parametrize("atoms_per_mol,weight_kind", [(1, "slab"), (4, "slab"), (4, "spherical")])
-def test_adress_step_vs_oracle(api, oracle, atoms_per_mol, weight_kind):
+@pytest.mark.parametrize("atoms_per_mol,weight_kind,lanes", [(1, "slab", 0), (4, "slab", 0), (4, "spherical", 0),
+                                                              (4, "slab", 4), (4, "spherical", 4)])
+def test_adress_step_vs_oracle(api, oracle, atoms_per_mol, weight_kind, lanes):
     """The assembled AdResS force step of SURVEY.md section 3.5 on both sides, two runs (run 0 samples and
-    updates the compensation histograms; run 1 applies the mean compensation energy)."""
+    updates the compensation histograms; run 1 applies the mean compensation energy).  lanes = 4: the kernel with four
+    lanes per four-atom molecule (mrmd_b200_adress_set_atoms_per_molecule)."""
     sites, apos, box, M = adress_system(10, atoms_per_mol, 21)
     a_per = atoms_per_mol
     N = M * a_per
@@ -145,6 +147,7 @@ def test_adress_step_vs_oracle(api, oracle, atoms_per_mol, weight_kind):
     vl = api.HalfVerletList()
     vl.build(mols, 0, M, rc + skin, 1.0, sub.minGhostCorner, sub.maxGhostCorner, 40)
     lj = api.LJ_IdealGas(capv, rcv, sig, eps, True, numTypes=nt)
+    lj.setAtomsPerMolecule(lanes)
 
     L = oracle.lib()
     osub = oracle.subdomain([0, 0, 0], [box] * 3, rc + skin)
@@ -299,3 +302,23 @@ def test_thermodynamic_force_vs_oracle(api, oracle, symmetric, periodic):
         assert np.abs(f - oa["force"]).max() <= 1e-13 * np.abs(oa["force"]).max()
         assert np.count_nonzero(f[:, 0]) > 0 and np.all(f[:, 1:] == 0)
     oracle.lib().or_thermo_destroy(ot)
+
+
+def test_atoms_per_molecule_promise_is_checked(api):
+    """a molecule that breaks mrmd_b200_adress_set_atoms_per_molecule(4) makes the run fail loudly"""
+    sites, apos, box, M = adress_system(6, 4, 3)
+    atoms = api.Atoms.from_arrays(apos, None, mass=1.0, relativeMass=0.25)
+    mols = api.Molecules(M)
+    na = np.full(M, 4)
+    na[M // 2] = 3
+    mols.set("atomsOffset", np.arange(M) * 4)
+    mols.set("numAtoms", na)
+    mols.numLocalMolecules = M
+    w = api.Slab([box / 2] * 3, 4.0, 3.0, 2)
+    api.UpdateMolecules.update(mols, atoms, w)
+    vl = api.HalfVerletList()
+    vl.build(mols, 0, M, 2.6, 1.0, [-0.5] * 3, [box + 0.5] * 3, 40)
+    lj = api.LJ_IdealGas(0.7, 2.5, 1.0, 1.0, True)
+    lj.setAtomsPerMolecule(4)
+    with pytest.raises(RuntimeError, match="atom count promised"):
+        lj.run(mols, vl, atoms)

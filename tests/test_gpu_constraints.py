@@ -118,17 +118,20 @@ def test_shake_molecules_kat(api):
         mc.enforcePositionalConstraints(mols, atoms, 0.1)
 
 
-def test_constraints_vs_oracle(api, oracle):
-    """20 000 tetramers with six bonds each, three SHAKE iterations and the RATTLE projection, against the oracle"""
+@pytest.mark.parametrize("a_per", [4, 6])
+def test_constraints_vs_oracle(api, oracle, a_per):
+    """20 000 tetramers with six bonds each, three SHAKE iterations and the RATTLE projection, against the oracle.
+    a_per = 4 takes the fused shared-memory kernels (bonds among the first four atoms of a molecule); a_per = 6 hangs
+    two more atoms on every tetramer (bonds 3-4, 4-5) and takes the kernel sequence of the reference."""
     rng = np.random.default_rng(8)
-    M, a_per = 20000, 4
+    M = 20000
     N = M * a_per
     centres = rng.random((M, 3)) * 60.0
-    tet = np.array([(1, 1, 1), (1, -1, -1), (-1, 1, -1), (-1, -1, 1)]) * (0.5 / np.sqrt(2.0))
-    pos = (centres[:, None, :] + tet[None, :, :] * (1.0 + 0.1 * rng.random((M, 4, 1)))).reshape(-1, 3)
+    tet = np.array([(1, 1, 1), (1, -1, -1), (-1, 1, -1), (-1, -1, 1), (-1.8, -1.9, 2.1), (-2.9, -2.8, 3.2)]) * (0.5 / np.sqrt(2.0))
+    pos = (centres[:, None, :] + tet[None, :a_per, :] * (1.0 + 0.1 * rng.random((M, a_per, 1)))).reshape(-1, 3)
     vel, force = rng.normal(size=(N, 3)), rng.normal(size=(N, 3)) * 3
     mass = 0.5 + rng.random(N)
-    bonds = [(i, j, 1.0) for i in range(4) for j in range(i + 1, 4)]
+    bonds = [(i, j, 1.0) for i in range(4) for j in range(i + 1, 4)] + [(i, i + 1, 0.6) for i in range(3, a_per - 1)]
     dt = 0.002
 
     atoms = api.Atoms.from_arrays(pos, vel, mass=mass)
