@@ -407,6 +407,7 @@ def run_b200(args):
     if tetramer:
         # the same formula with a = 4 and M = n / 4 molecules: 84 M + 56 M a + 12 P_mol + (64 + 56 a) P_act
         algo_bytes = (84.0 + 224.0) * (n / 4) * args.steps + 12.0 * stats["storedPairs"] + 288.0 * stats["activePairs"]
+        kernel_name = "adressActiveMoleculesKernel + adressForceLanes4Kernel"
     force_ms = stats["forceKernelMs"]
     n_kernel, kernel_rank, stored_kernel = n, rank, stats["storedPairs"]
     if world > 1:

@@ -46,6 +46,7 @@ __global__ void contributeMoleculeForceKernel(MolsView m, AtomsView a, int64_t n
     if (mi >= numAll) return;
     const longlong2 oc = m.oc[mi];
     const double fx = m.force[0][mi], fy = m.force[1][mi], fz = m.force[2][mi];
+    if (fx == 0.0 && fy == 0.0 && fz == 0.0) return;  // the coarse-grained bulk: nothing to distribute
     for (long long ai = oc.x; ai < oc.x + oc.y; ++ai)
     {
         const double rm = a.relMass[ai];
