@@ -3,8 +3,8 @@
 // Reference: mrmd/action/SPC.hpp:61-362 (class SPC), mrmd/action/Coulomb.hpp:27-46, mrmd/action/CoulombDSF.hpp:42-84,
 //            mrmd/util/math.hpp:57-76 (approxErfc), mrmd/util/angle.hpp:28.
 //
-// SPC_LANES lanes share one molecule alpha and stride over its neighbour row; alpha's three atoms (position + charge)
-// stay in registers, the force on them is reduced over the lanes with shuffles and leaves in one atomic per component,
+// SPC_LANES lanes share one molecule alpha and stride over its neighbour row; for three-atom molecules alpha's atoms
+// (position + charge) stay in registers, the force on them is reduced over the lanes with shuffles and leaves in one atomic per component,
 // the partner's force is collected over alpha's atoms before it is added (9 instead of 27 atomics per molecule pair).
 // Cutoff decisions use the uncontracted squared distance (distSqrExact), so they agree with the oracle bit for bit.
 #include <algorithm>
@@ -35,8 +35,6 @@ struct mrmd_b200_spc
     double* dResult = nullptr;  // [0..2] LJ energy, Coulomb energy, atom pairs inside the cutoff; [3..5] running sums
     unsigned int* dTicket = nullptr;
     double* hResult = nullptr;  // pinned
-    int* dFlag = nullptr;
-    int* hFlag = nullptr;  // pinned
 };
 
 namespace mrmd_b200
@@ -116,9 +114,61 @@ __device__ __forceinline__ double lanesSum(double v)
     return v;
 }
 
-// SPC::operator()(CalcInteractions, alpha, sumEnergy), SPC.hpp:143-236.  WATER: every molecule has three atoms (the
-// register-resident fast path); otherwise the atom ranges are walked as the reference does.
-template <bool DSF, bool WATER>
+// One molecule pair exactly as SPC.hpp:150-234 walks it (any atom counts, every contribution an atomic)
+template <bool DSF>
+__device__ __forceinline__ void spcGenericPair(const AtomsView& a, longlong2 ocA, longlong2 ocB, const LJType& lj,
+                                            const CoulombDev& coulomb, double rcSqr, double& eLJ, double& eC, double& pairs)
+{
+    const long long startAlpha = ocA.x, endAlpha = ocA.x + ocA.y;
+    const long long startBeta = ocB.x, endBeta = ocB.x + ocB.y;
+    {
+        const double4 pi = ld4nc(a.pos + startAlpha), pj = ld4nc(a.pos + startBeta);
+        const double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+        const double distSqr = distSqrExact(dx, dy, dz);
+        if (distSqr < rcSqr)
+        {
+            double ff, e;
+            ljForceEnergy(lj, distSqr, ff, e);
+            eLJ += e;
+            atomicAdd(a.force[0] + startBeta, -(dx * ff));
+            atomicAdd(a.force[1] + startBeta, -(dy * ff));
+            atomicAdd(a.force[2] + startBeta, -(dz * ff));
+            atomicAdd(a.force[0] + startAlpha, dx * ff);
+            atomicAdd(a.force[1] + startAlpha, dy * ff);
+            atomicAdd(a.force[2] + startAlpha, dz * ff);
+        }
+    }
+    for (long long idx = startAlpha; idx < endAlpha; ++idx)
+    {
+        const double4 pi = ld4nc(a.pos + idx);
+        const double q1 = a.charge[idx];
+        double fx = 0.0, fy = 0.0, fz = 0.0;
+        for (long long jdx = startBeta; jdx < endBeta; ++jdx)
+        {
+            const double4 pj = ld4nc(a.pos + jdx);
+            const double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+            const double distSqr = distSqrExact(dx, dy, dz);
+            if (distSqr > rcSqr) continue;
+            double ff, e;
+            coulombForceEnergy<DSF>(coulomb, distSqr, q1, a.charge[jdx], ff, e);
+            eC += e;
+            pairs += 1.0;
+            fx += dx * ff;
+            fy += dy * ff;
+            fz += dz * ff;
+            atomicAdd(a.force[0] + jdx, -(dx * ff));
+            atomicAdd(a.force[1] + jdx, -(dy * ff));
+            atomicAdd(a.force[2] + jdx, -(dz * ff));
+        }
+        atomicAdd(a.force[0] + idx, fx);
+        atomicAdd(a.force[1] + idx, fy);
+        atomicAdd(a.force[2] + idx, fz);
+    }
+}
+
+// SPC::operator()(CalcInteractions, alpha, sumEnergy), SPC.hpp:143-236.  Pairs of three-atom molecules (water) take
+// the register-resident path; any other pair is walked atom range by atom range as the reference does.
+template <bool DSF>
 __global__ void __launch_bounds__(SPC_THREADS)
     spcForceKernel(MolsView m, AtomsView a, int64_t numLocalMols, const int32_t* __restrict__ counts,
                    const int32_t* __restrict__ neigh, int64_t pitch, LJType lj, CoulombDev coulomb, double rcSqr,
@@ -130,149 +180,91 @@ __global__ void __launch_bounds__(SPC_THREADS)
     double eLJ = 0.0, eC = 0.0, pairs = 0.0;
     // lanes past the last molecule run with an empty row so that the shuffles below see full warps
     const bool valid = alpha < numLocalMols;
+    const longlong2 ocA = valid ? m.oc[alpha] : make_longlong2(0, 0);
+    const int numNeighbors = valid ? counts[alpha] : 0;
+    const int32_t* row = neigh + alpha;
+    const bool waterA = ocA.y == 3;
+    double4 pA[3];
+    double qA[3], fA[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
     {
-        const longlong2 ocA = valid ? m.oc[alpha] : make_longlong2(0, 0);
-        const int numNeighbors = valid ? counts[alpha] : 0;
-        const int32_t* row = neigh + alpha;
-        if (WATER)
-        {
-            double4 pA[3];
-            double qA[3], fA[3][3];
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-            {
-                pA[i] = valid ? ld4nc(a.pos + ocA.x + i) : make_double4(0.0, 0.0, 0.0, 0.0);
-                qA[i] = valid ? a.charge[ocA.x + i] : 0.0;
-                fA[i][0] = fA[i][1] = fA[i][2] = 0.0;
-            }
-            for (int n = sub; n < numNeighbors; n += SPC_LANES)
-            {
-                const int64_t beta = row[int64_t(n) * pitch];
-                const long long startBeta = m.oc[beta].x;
-                double4 pB[3];
-                double qB[3], fB[3][3];
-#pragma unroll
-                for (int j = 0; j < 3; ++j)
-                {
-                    pB[j] = ld4nc(a.pos + startBeta + j);
-                    qB[j] = a.charge[startBeta + j];
-                    fB[j][0] = fB[j][1] = fB[j][2] = 0.0;
-                }
-                {
-                    // LJ interaction between oxygen atoms, :165-190
-                    const double dx = pA[0].x - pB[0].x, dy = pA[0].y - pB[0].y, dz = pA[0].z - pB[0].z;
-                    const double distSqr = distSqrExact(dx, dy, dz);
-                    if (distSqr < rcSqr)
-                    {
-                        double ff, e;
-                        ljForceEnergy(lj, distSqr, ff, e);
-                        eLJ += e;
-                        fB[0][0] -= dx * ff;
-                        fB[0][1] -= dy * ff;
-                        fB[0][2] -= dz * ff;
-                        fA[0][0] += dx * ff;
-                        fA[0][1] += dy * ff;
-                        fA[0][2] += dz * ff;
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 3; ++i)
-                {
-#pragma unroll
-                    for (int j = 0; j < 3; ++j)
-                    {
-                        const double dx = pA[i].x - pB[j].x, dy = pA[i].y - pB[j].y, dz = pA[i].z - pB[j].z;
-                        const double distSqr = distSqrExact(dx, dy, dz);
-                        if (distSqr > rcSqr) continue;  // :214
-                        double ff, e;
-                        coulombForceEnergy<DSF>(coulomb, distSqr, qA[i], qB[j], ff, e);
-                        eC += e;
-                        pairs += 1.0;
-                        fA[i][0] += dx * ff;
-                        fA[i][1] += dy * ff;
-                        fA[i][2] += dz * ff;
-                        fB[j][0] -= dx * ff;
-                        fB[j][1] -= dy * ff;
-                        fB[j][2] -= dz * ff;
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 3; ++j)
-#pragma unroll
-                    for (int d = 0; d < 3; ++d)
-                        if (fB[j][d] != 0.0) atomicAdd(a.force[d] + startBeta + j, fB[j][d]);
-            }
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int d = 0; d < 3; ++d)
-                {
-                    const double f = lanesSum(fA[i][d]);
-                    if (valid && sub == 0 && f != 0.0) atomicAdd(a.force[d] + ocA.x + i, f);
-                }
-        }
-        else
-        {
-            const long long startAlpha = ocA.x, endAlpha = ocA.x + ocA.y;
-            for (int n = sub; n < numNeighbors; n += SPC_LANES)
-            {
-                const int64_t beta = row[int64_t(n) * pitch];
-                const longlong2 ocB = m.oc[beta];
-                const long long startBeta = ocB.x, endBeta = ocB.x + ocB.y;
-                {
-                    const double4 pi = ld4nc(a.pos + startAlpha), pj = ld4nc(a.pos + startBeta);
-                    const double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-                    const double distSqr = distSqrExact(dx, dy, dz);
-                    if (distSqr < rcSqr)
-                    {
-                        double ff, e;
-                        ljForceEnergy(lj, distSqr, ff, e);
-                        eLJ += e;
-                        atomicAdd(a.force[0] + startBeta, -(dx * ff));
-                        atomicAdd(a.force[1] + startBeta, -(dy * ff));
-                        atomicAdd(a.force[2] + startBeta, -(dz * ff));
-                        atomicAdd(a.force[0] + startAlpha, dx * ff);
-                        atomicAdd(a.force[1] + startAlpha, dy * ff);
-                        atomicAdd(a.force[2] + startAlpha, dz * ff);
-                    }
-                }
-                for (long long idx = startAlpha; idx < endAlpha; ++idx)
-                {
-                    const double4 pi = ld4nc(a.pos + idx);
-                    const double q1 = a.charge[idx];
-                    double fx = 0.0, fy = 0.0, fz = 0.0;
-                    for (long long jdx = startBeta; jdx < endBeta; ++jdx)
-                    {
-                        const double4 pj = ld4nc(a.pos + jdx);
-                        const double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-                        const double distSqr = distSqrExact(dx, dy, dz);
-                        if (distSqr > rcSqr) continue;
-                        double ff, e;
-                        coulombForceEnergy<DSF>(coulomb, distSqr, q1, a.charge[jdx], ff, e);
-                        eC += e;
-                        pairs += 1.0;
-                        fx += dx * ff;
-                        fy += dy * ff;
-                        fz += dz * ff;
-                        atomicAdd(a.force[0] + jdx, -(dx * ff));
-                        atomicAdd(a.force[1] + jdx, -(dy * ff));
-                        atomicAdd(a.force[2] + jdx, -(dz * ff));
-                    }
-                    atomicAdd(a.force[0] + idx, fx);
-                    atomicAdd(a.force[1] + idx, fy);
-                    atomicAdd(a.force[2] + idx, fz);
-                }
-            }
-        }
+        pA[i] = waterA ? ld4nc(a.pos + ocA.x + i) : make_double4(0.0, 0.0, 0.0, 0.0);
+        qA[i] = waterA ? a.charge[ocA.x + i] : 0.0;
+        fA[i][0] = fA[i][1] = fA[i][2] = 0.0;
     }
+    for (int n = sub; n < numNeighbors; n += SPC_LANES)
+    {
+        const int64_t beta = row[int64_t(n) * pitch];
+        const longlong2 ocB = m.oc[beta];
+        if (!waterA || ocB.y != 3)
+        {
+            spcGenericPair<DSF>(a, ocA, ocB, lj, coulomb, rcSqr, eLJ, eC, pairs);
+            continue;
+        }
+        const long long startBeta = ocB.x;
+        double4 pB[3];
+        double qB[3], fB[3][3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+        {
+            pB[j] = ld4nc(a.pos + startBeta + j);
+            qB[j] = a.charge[startBeta + j];
+            fB[j][0] = fB[j][1] = fB[j][2] = 0.0;
+        }
+        {
+            // LJ interaction between oxygen atoms, :165-190
+            const double dx = pA[0].x - pB[0].x, dy = pA[0].y - pB[0].y, dz = pA[0].z - pB[0].z;
+            const double distSqr = distSqrExact(dx, dy, dz);
+            if (distSqr < rcSqr)
+            {
+                double ff, e;
+                ljForceEnergy(lj, distSqr, ff, e);
+                eLJ += e;
+                fB[0][0] -= dx * ff;
+                fB[0][1] -= dy * ff;
+                fB[0][2] -= dz * ff;
+                fA[0][0] += dx * ff;
+                fA[0][1] += dy * ff;
+                fA[0][2] += dz * ff;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+        {
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+            {
+                const double dx = pA[i].x - pB[j].x, dy = pA[i].y - pB[j].y, dz = pA[i].z - pB[j].z;
+                const double distSqr = distSqrExact(dx, dy, dz);
+                if (distSqr > rcSqr) continue;  // :214
+                double ff, e;
+                coulombForceEnergy<DSF>(coulomb, distSqr, qA[i], qB[j], ff, e);
+                eC += e;
+                pairs += 1.0;
+                fA[i][0] += dx * ff;
+                fA[i][1] += dy * ff;
+                fA[i][2] += dz * ff;
+                fB[j][0] -= dx * ff;
+                fB[j][1] -= dy * ff;
+                fB[j][2] -= dz * ff;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+                if (fB[j][d] != 0.0) atomicAdd(a.force[d] + startBeta + j, fB[j][d]);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+        {
+            const double f = lanesSum(fA[i][d]);
+            if (waterA && sub == 0 && f != 0.0) atomicAdd(a.force[d] + ocA.x + i, f);
+        }
     gridReduce3<SPC_THREADS>(eLJ, eC, pairs, partials, result, ticket);
-}
-
-// numAtoms == 3 for every molecule in [0, n)?  flag stays 1 if so
-__global__ void spcAllWaterKernel(MolsView m, int64_t n, int* flag)
-{
-    const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-    if (i < n && m.oc[i].y != 3) *flag = 0;
 }
 
 // SPC::operator()(BondEnergy, alpha, sumEnergy), SPC.hpp:284-318
@@ -338,8 +330,6 @@ int mrmd_b200_spc_create(mrmd_b200_spc** out, int coulombKind)
     if (rc_ == 0 && cudaMalloc(&spc->dResult, 48) != cudaSuccess) rc_ = MRMD_B200_ENOMEM;
     if (rc_ == 0 && cudaMalloc(&spc->dTicket, 4) != cudaSuccess) rc_ = MRMD_B200_ENOMEM;
     if (rc_ == 0 && cudaMallocHost(&spc->hResult, 48) != cudaSuccess) rc_ = MRMD_B200_ENOMEM;
-    if (rc_ == 0 && cudaMalloc(&spc->dFlag, 4) != cudaSuccess) rc_ = MRMD_B200_ENOMEM;
-    if (rc_ == 0 && cudaMallocHost(&spc->hFlag, 4) != cudaSuccess) rc_ = MRMD_B200_ENOMEM;
     if (rc_ == 0) rc_ = mrmd_b200_constraints_create(&spc->constraints, 3, 20);
     if (rc_ == 0)
     {
@@ -366,8 +356,6 @@ int mrmd_b200_spc_destroy(mrmd_b200_spc* spc)
     if (spc->dResult) cudaFree(spc->dResult);
     if (spc->dTicket) cudaFree(spc->dTicket);
     if (spc->hResult) cudaFreeHost(spc->hResult);
-    if (spc->dFlag) cudaFree(spc->dFlag);
-    if (spc->hFlag) cudaFreeHost(spc->hFlag);
     spc->partials.release();
     delete spc;
     return 0;
@@ -385,29 +373,16 @@ int mrmd_b200_spc_apply_forces(mrmd_b200_spc* spc, const mrmd_b200_molecules* m,
     MB_CUDA(cudaMemsetAsync(spc->dResult, 0, 24, st));
     if (m->numLocal > 0)
     {
-        // the register-resident kernel needs three atoms in every molecule a row can name
-        const int64_t nAll = m->numLocal + m->numGhost;
-        *spc->hFlag = 1;
-        MB_CUDA(cudaMemcpyAsync(spc->dFlag, spc->hFlag, 4, cudaMemcpyHostToDevice, st));
-        spcAllWaterKernel<<<gridFor(nAll, 256), 256, 0, st>>>(m->v, nAll, spc->dFlag);
-        MB_LAUNCHED();
-        MB_CUDA(cudaMemcpyAsync(spc->hFlag, spc->dFlag, 4, cudaMemcpyDeviceToHost, st));
-        MB_CUDA(cudaStreamSynchronize(st));
-        const bool water = *spc->hFlag == 1;
-
         const int blocks = gridFor(m->numLocal * SPC_LANES, SPC_THREADS);
         MB_TRY(spc->partials.reserve(size_t(blocks) * 3 * 8));
-        const bool dsf = spc->coulomb.kind == 1;
-#define MB_SPC_LAUNCH(DSF, WATER)                                                                                      \
-    spcForceKernel<DSF, WATER><<<blocks, SPC_THREADS, 0, st>>>(m->v, a->v, m->numLocal, v->counts.as<int32_t>(),        \
-                                                               v->neigh.as<int32_t>(), v->pitch, spc->table.t[0],      \
-                                                               spc->coulomb, spc->rcSqr, spc->partials.as<double>(),   \
-                                                               spc->dResult, spc->dTicket)
-        if (dsf && water) MB_SPC_LAUNCH(true, true);
-        else if (dsf) MB_SPC_LAUNCH(true, false);
-        else if (water) MB_SPC_LAUNCH(false, true);
-        else MB_SPC_LAUNCH(false, false);
-#undef MB_SPC_LAUNCH
+        if (spc->coulomb.kind == 1)
+            spcForceKernel<true><<<blocks, SPC_THREADS, 0, st>>>(m->v, a->v, m->numLocal, v->counts.as<int32_t>(),
+                                                                 v->neigh.as<int32_t>(), v->pitch, spc->table.t[0], spc->coulomb,
+                                                                 spc->rcSqr, spc->partials.as<double>(), spc->dResult, spc->dTicket);
+        else
+            spcForceKernel<false><<<blocks, SPC_THREADS, 0, st>>>(m->v, a->v, m->numLocal, v->counts.as<int32_t>(),
+                                                                  v->neigh.as<int32_t>(), v->pitch, spc->table.t[0], spc->coulomb,
+                                                                  spc->rcSqr, spc->partials.as<double>(), spc->dResult, spc->dTicket);
         MB_LAUNCHED();
     }
     if (energyLJ != nullptr || energyCoulomb != nullptr)
