@@ -687,6 +687,8 @@ public:
         detail::check(mrmd_b200_adress_create(&h, cappingDistance.data(), rc.data(), sigma.data(), epsilon.data(), numTypes, doShift), "LJ_IdealGas");
         h_.reset(h, [](mrmd_b200_adress* p) { mrmd_b200_adress_destroy(p); });
     }
+    /// extension: promise that every molecule has this many atoms; 4 selects the four-lanes-per-molecule kernel
+    void setAtomsPerMolecule(const idx_t& atomsPerMolecule) { detail::check(mrmd_b200_adress_set_atoms_per_molecule(h_.get(), atomsPerMolecule), "setAtomsPerMolecule"); }
     void setCompensationEnergySamplingInterval(const idx_t& interval) { sampling_ = interval; detail::check(mrmd_b200_adress_set_intervals(h_.get(), sampling_, update_), "interval"); }
     void setCompensationEnergyUpdateInterval(const idx_t& interval) { update_ = interval; detail::check(mrmd_b200_adress_set_intervals(h_.get(), sampling_, update_), "interval"); }
     /// 200 x numTypes doubles, row-major (getMeanCompensationEnergy().data on the host)

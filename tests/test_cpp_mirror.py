@@ -46,7 +46,8 @@ def test_reference_header_paths_exist():
         assert os.path.exists(os.path.join(INC, h)), h
 
 
-@pytest.mark.parametrize("name", ["lennard_jones_nve", "adress_ideal_gas", "restart_io", "constraints_step", "spc_water"])
+@pytest.mark.parametrize("name", ["lennard_jones_nve", "adress_ideal_gas", "restart_io", "constraints_step", "spc_water",
+                                  "tetramer_adress"])
 def test_example_compiles_and_fails_loudly_without_gpu(name, tmp_path):
     import torch
 
@@ -239,3 +240,51 @@ def test_spc_water_driver_matches_oracle(tmp_path):
     assert abs(out["ECoulomb"] - st["energyCoulomb"]) <= 1e-8 * abs(st["energyCoulomb"])
     assert np.allclose(out["x0"], md.atoms["pos"][0], rtol=0, atol=1e-9)
     assert out["maxBondError"] < 1e-5 and 0 <= out["bondEnergy"] < 1e-6
+
+
+def _lcg_tetramers(sites, spacing=1.98425):
+    """the start configuration of examples/tetramer_adress.cpp (48-bit LCG, same draw order)"""
+    state = [0x1234ABCD330E]
+
+    def rnd():
+        state[0] = (state[0] * 0x5DEECE66D + 0xB) & ((1 << 48) - 1)
+        return state[0] / float(1 << 48)
+
+    a = 1.0 / (2.0 * np.sqrt(2.0))
+    tet = np.array([(a, a, a), (a, -a, -a), (-a, a, -a), (-a, -a, a)])
+    m = sites ** 3
+    pos, vel = np.zeros((4 * m, 3)), np.zeros((4 * m, 3))
+    idx = 0
+    for i in range(sites):
+        for j in range(sites):
+            for k in range(sites):
+                v = [rnd() - 0.5 for _ in range(3)]
+                pos[4 * idx:4 * idx + 4] = (np.array([i, j, k]) + 0.5) * spacing + tet
+                vel[4 * idx:4 * idx + 4] = v
+                idx += 1
+    return pos, vel, np.full(3, sites * spacing)
+
+
+@pytest.mark.gpu
+def test_tetramer_driver_matches_oracle(tmp_path):
+    """BASELINE.json configs[3] through the mirror: AdResS tetramers, spherical region, Langevin, SHAKE / RATTLE; 60 steps
+    against the oracle's loop of the same operators"""
+    from oracle import pyoracle as orc
+    from oracle.md_loop import OracleAdressMD
+
+    sites, steps = 10, 60
+    exe = _compile("tetramer_adress", tmp_path)
+    res = subprocess.run([exe, str(sites), str(steps)], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    out = json.loads(res.stdout.strip().splitlines()[-1])
+    pos, vel, box = _lcg_tetramers(sites)
+    w = orc.make_weight(orc.WEIGHT_SPHERICAL, 0.5 * box, 60.0 / 317.48 * box[0], 30.0 / 317.48 * box[0], 2)
+    md = OracleAdressMD(pos, vel, box, w, langevin=True, zeta=20.0, temperature=1.5, seed=1234, max_neigh=40,
+                        atoms_per_mol=4, constraint_iterations=3, bond_length=1.0)
+    st = md.run(steps)
+    assert out["atoms"] == 4 * sites ** 3 and out["rebuilds"] == st["rebuilds"] >= 2
+    assert out["ghostAtoms"] == md.ng
+    assert abs(out["E"] - st["energy"]) <= 1e-8 * abs(st["energy"])
+    assert np.allclose(out["x0"], md.atoms["pos"][0], rtol=0, atol=1e-9)
+    assert np.allclose(out["v0"], md.atoms["vel"][0], rtol=0, atol=1e-8)
+    assert out["maxBondError"] < 5e-3

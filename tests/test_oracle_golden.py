@@ -796,3 +796,26 @@ def test_spc_kats(oracle):
     far["force"] = 0.0
     L.or_spc_apply_forces(mfar.ctypes.data, 2, counts.ctypes.data, neigh.ctypes.data, 1, far.ctypes.data, 0, plain.ctypes.data)
     assert abs(plain[1]) > 1.0
+
+
+def test_oracle_molecule_loops_hold_their_bonds(oracle):
+    """the oracle's constrained step loops (oracle/md_loop.py: SPC water, AdResS tetramers) keep the bond lengths that
+    SHAKE / RATTLE enforce and stay finite: the GPU parity tests of rows (f)2 / (f)4 and configs[3] compare against them"""
+    from mrmd_b200.workloads import tetramer_system
+    from oracle.md_loop import OracleAdressMD, OracleSpcMD, spc_water_box
+
+    pos, vel, mass, q, rm, typ, box = spc_water_box(6)
+    md = OracleSpcMD(pos, vel, mass, q, rm, typ, box, dt=0.0005, skin=0.02)
+    st = md.run(8)
+    p = md.atoms["pos"][:md.n].reshape(-1, 3, 3)
+    assert np.abs(np.linalg.norm(p[:, 0] - p[:, 1], axis=1) - 0.1).max() < 1e-5
+    assert np.isfinite(st["energyCoulomb"]) and st["energyLJ"] < 0 and st["rebuilds"] >= 1
+
+    pos, vel, box = tetramer_system(6)
+    w = oracle.make_weight(oracle.WEIGHT_SPHERICAL, 0.5 * box, 3.0, 2.0, 2)
+    md = OracleAdressMD(pos, vel, box, w, atoms_per_mol=4, constraint_iterations=3, langevin=True, max_neigh=40)
+    st = md.run(20)
+    p = md.atoms["pos"][:md.n].reshape(-1, 4, 3)
+    iu = np.triu_indices(4, 1)
+    d = np.linalg.norm(p[:, :, None, :] - p[:, None, :, :], axis=-1)[:, iu[0], iu[1]]
+    assert np.abs(d - 1.0).max() < 5e-3 and st["rebuilds"] >= 2 and st["pairInteractions"] > 0
