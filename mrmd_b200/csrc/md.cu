@@ -31,8 +31,9 @@ struct mrmd_b200_md
     std::vector<cudaEvent_t> events;
     // host-buffer path (mrmd_b200_md_run_host): copy streams, staging buffers and the events that order them
     cudaStream_t sIn = nullptr, sOut = nullptr;
-    cudaEvent_t evUpPos = nullptr, evUpVel = nullptr, evPosReady = nullptr, evStepDone = nullptr, evDownPos = nullptr,
-                evDownVel = nullptr;
+    cudaEvent_t evUpPos = nullptr, evUpVel = nullptr, evPosReady = nullptr, evStepDone = nullptr;
+    static constexpr int HB_CHUNKS = 4;  // the PCIe copies move in chunks so that upload i+1 trails download i
+    cudaEvent_t evDownPos[HB_CHUNKS] = {}, evDownVel[HB_CHUNKS] = {};
     bool recordPosReady = false;  // oneStep records evPosReady once the positions (and the atom order) are final
     mrmd_b200::DevBuf posIn, velIn, posOut, velOut;
 };
@@ -357,8 +358,11 @@ int mrmd_b200_md_destroy(mrmd_b200_md* md)
     if (md == nullptr) return 0;
     cudaDeviceSynchronize();
     for (auto e : md->events) cudaEventDestroy(e);
-    for (cudaEvent_t e : {md->evUpPos, md->evUpVel, md->evPosReady, md->evStepDone, md->evDownPos, md->evDownVel})
+    for (cudaEvent_t e : {md->evUpPos, md->evUpVel, md->evPosReady, md->evStepDone})
         if (e != nullptr) cudaEventDestroy(e);
+    for (int c = 0; c < mrmd_b200_md::HB_CHUNKS; ++c)
+        for (cudaEvent_t e : {md->evDownPos[c], md->evDownVel[c]})
+            if (e != nullptr) cudaEventDestroy(e);
     if (md->sIn != nullptr) cudaStreamDestroy(md->sIn);
     if (md->sOut != nullptr) cudaStreamDestroy(md->sOut);
     for (mrmd_b200::DevBuf* b : {&md->posIn, &md->velIn, &md->posOut, &md->velOut}) b->release();
@@ -406,8 +410,9 @@ int mrmd_b200_md_run(mrmd_b200_md* md, int64_t nsteps, int timeForceKernel, mrmd
 
 // Host-buffer path.  Per step: pos and vel come from the host buffers, one step runs, pos, vel and the scalars go
 // back.  PCIe is full duplex and the positions are final before the force kernel starts, so the copies run on two
-// extra streams: the download of the positions overlaps the force kernel, the upload of the next step's positions
-// overlaps the download of the velocities.  Every host buffer is read only after the previous step's write to it.
+// extra streams and in HB_CHUNKS pieces: the download of the positions overlaps the force kernel, and chunk c of the
+// next step's upload starts as soon as chunk c of this step's download has landed, so both directions of the link
+// stay busy.  Every byte of a host buffer is read only after the previous step's write to it.
 int mrmd_b200_md_run_host(mrmd_b200_md* md, int64_t nsteps, double* posHost, double* velHost, double* scalarsHost,
                           mrmd_b200_md_stats* stats, void* stream)
 {
@@ -425,9 +430,29 @@ int mrmd_b200_md_run_host(mrmd_b200_md* md, int64_t nsteps, double* posHost, dou
     {
         MB_CUDA(cudaStreamCreateWithFlags(&md->sIn, cudaStreamNonBlocking));
         MB_CUDA(cudaStreamCreateWithFlags(&md->sOut, cudaStreamNonBlocking));
-        for (cudaEvent_t* e : {&md->evUpPos, &md->evUpVel, &md->evPosReady, &md->evStepDone, &md->evDownPos, &md->evDownVel})
+        for (cudaEvent_t* e : {&md->evUpPos, &md->evUpVel, &md->evPosReady, &md->evStepDone})
             MB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        for (int c = 0; c < mrmd_b200_md::HB_CHUNKS; ++c)
+            for (cudaEvent_t* e : {&md->evDownPos[c], &md->evDownVel[c]})
+                MB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     }
+    constexpr int K = mrmd_b200_md::HB_CHUNKS;
+    size_t off[K + 1];
+    for (int c = 0; c <= K; ++c) off[c] = (c == K) ? bytes : ((bytes * size_t(c) / K) & ~size_t(255));
+    // one direction of one array: chunk c waits for gate[c] (if any) and records done[c] (if any)
+    auto copyChunks = [&](void* dst, const void* src, cudaMemcpyKind kind, cudaStream_t cs, cudaEvent_t* gate,
+                          cudaEvent_t* done) -> int
+    {
+        for (int c = 0; c < K; ++c)
+        {
+            if (off[c + 1] == off[c]) continue;
+            if (gate != nullptr) MB_CUDA(cudaStreamWaitEvent(cs, gate[c], 0));
+            MB_CUDA(cudaMemcpyAsync(static_cast<char*>(dst) + off[c], static_cast<const char*>(src) + off[c], off[c + 1] - off[c],
+                                    kind, cs));
+            if (done != nullptr) MB_CUDA(cudaEventRecord(done[c], cs));
+        }
+        return 0;
+    };
     for (mrmd_b200::DevBuf* b : {&md->posIn, &md->velIn, &md->posOut, &md->velOut}) MB_TRY(b->reserve(std::max<size_t>(bytes, 8)));
     double* dRes = md->cfg.adress ? md->adress->dResult : md->lj->dResult;
     md->recordPosReady = true;
@@ -435,11 +460,9 @@ int mrmd_b200_md_run_host(mrmd_b200_md* md, int64_t nsteps, double* posHost, dou
     auto step = [&](int64_t i) -> int
     {
         // host -> device: this step's inputs (the host buffers were last written by the previous step's download)
-        if (i > 0) MB_CUDA(cudaStreamWaitEvent(md->sIn, md->evDownPos, 0));
-        MB_CUDA(cudaMemcpyAsync(md->posIn.p, posHost, bytes, cudaMemcpyHostToDevice, md->sIn));
+        MB_TRY(copyChunks(md->posIn.p, posHost, cudaMemcpyHostToDevice, md->sIn, i > 0 ? md->evDownPos : nullptr, nullptr));
         MB_CUDA(cudaEventRecord(md->evUpPos, md->sIn));
-        if (i > 0) MB_CUDA(cudaStreamWaitEvent(md->sIn, md->evDownVel, 0));
-        MB_CUDA(cudaMemcpyAsync(md->velIn.p, velHost, bytes, cudaMemcpyHostToDevice, md->sIn));
+        MB_TRY(copyChunks(md->velIn.p, velHost, cudaMemcpyHostToDevice, md->sIn, i > 0 ? md->evDownVel : nullptr, nullptr));
         MB_CUDA(cudaEventRecord(md->evUpVel, md->sIn));
         MB_CUDA(cudaStreamWaitEvent(st, md->evUpPos, 0));
         MB_TRY(atomsFieldFromDense(a, MRMD_B200_ATOM_POS, md->posIn.as<double>(), n, st));
@@ -450,19 +473,17 @@ int mrmd_b200_md_run_host(mrmd_b200_md* md, int64_t nsteps, double* posHost, dou
         // device -> host: positions while the force kernel runs ...
         MB_CUDA(cudaStreamWaitEvent(md->sOut, md->evPosReady, 0));
         MB_TRY(atomsFieldToDense(a, MRMD_B200_ATOM_POS, md->posOut.as<double>(), n, md->sOut));
-        MB_CUDA(cudaMemcpyAsync(posHost, md->posOut.p, bytes, cudaMemcpyDeviceToHost, md->sOut));
-        MB_CUDA(cudaEventRecord(md->evDownPos, md->sOut));
+        MB_TRY(copyChunks(posHost, md->posOut.p, cudaMemcpyDeviceToHost, md->sOut, nullptr, md->evDownPos));
         // ... velocities and scalars after postForceIntegrate
         MB_CUDA(cudaEventRecord(md->evStepDone, st));
         MB_CUDA(cudaStreamWaitEvent(md->sOut, md->evStepDone, 0));
         MB_TRY(atomsFieldToDense(a, MRMD_B200_ATOM_VEL, md->velOut.as<double>(), n, md->sOut));
-        MB_CUDA(cudaMemcpyAsync(velHost, md->velOut.p, bytes, cudaMemcpyDeviceToHost, md->sOut));
+        MB_TRY(copyChunks(velHost, md->velOut.p, cudaMemcpyDeviceToHost, md->sOut, nullptr, md->evDownVel));
         if (scalarsHost != nullptr)
         {
             MB_CUDA(cudaMemcpyAsync(scalarsHost, dRes, 16, cudaMemcpyDeviceToHost, md->sOut));
             scalarsHost[2] = md->maxDisplacement;
         }
-        MB_CUDA(cudaEventRecord(md->evDownVel, md->sOut));
         return 0;
     };
     for (int64_t i = 0; i < nsteps && rc == 0; ++i) rc = step(i);

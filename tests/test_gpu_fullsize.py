@@ -73,10 +73,13 @@ def test_lj_1m_step_vs_oracle(api, oracle):
 
     # stored neighbour sets: the reference's full list over local + ghost atoms, partners mapped to (real atom, image)
     fc, fn = oracle.verlet_build(oa, 13, n + ng, 0, n, cutoff, 1.0, gmin, gmax, half=False, width=80)
-    nb = np.where(fn[:n] >= 0, fn[:n], 0).astype(np.int64)
-    real = np.where(nb < n, nb, corr[nb])
-    shift = np.rint((oa["pos"][nb] - oa["pos"][real]) / box).astype(np.int64)
-    okeys = (real * 27 + (shift[..., 0] + 1) + 3 * (shift[..., 1] + 1) + 9 * (shift[..., 2] + 1)).astype(np.int32)
+    okeys = np.empty((n, fn.shape[1]), dtype=np.int32)
+    for lo in range(0, n, 65536):  # row blocks keep the temporaries below 1 GB
+        hi = min(n, lo + 65536)
+        nb = np.where(fn[lo:hi] >= 0, fn[lo:hi], 0).astype(np.int64)
+        real = np.where(nb < n, nb, corr[nb])
+        shift = np.rint((oa["pos"][nb] - oa["pos"][real]) / box).astype(np.int64)
+        okeys[lo:hi] = real * 27 + (shift[..., 0] + 1) + 3 * (shift[..., 1] + 1) + 9 * (shift[..., 2] + 1)
     del nb, real, shift
     gc, gp, gcode = vl.to_host_periodic(atoms)
     assert np.array_equal(gc[:n], fc[:n])
