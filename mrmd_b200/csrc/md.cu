@@ -32,7 +32,7 @@ struct mrmd_b200_md
     // host-buffer path (mrmd_b200_md_run_host): copy streams, staging buffers and the events that order them
     cudaStream_t sIn = nullptr, sOut = nullptr;
     cudaEvent_t evUpPos = nullptr, evUpVel = nullptr, evPosReady = nullptr, evStepDone = nullptr;
-    static constexpr int HB_CHUNKS = 4;  // the PCIe copies move in chunks so that upload i+1 trails download i
+    static constexpr int HB_CHUNKS = 8;  // the PCIe copies move in up to 8 chunks so that upload i+1 trails download i
     cudaEvent_t evDownPos[HB_CHUNKS] = {}, evDownVel[HB_CHUNKS] = {};
     bool recordPosReady = false;  // oneStep records evPosReady once the positions (and the atom order) are final
     mrmd_b200::DevBuf posIn, velIn, posOut, velOut;
@@ -428,16 +428,22 @@ int mrmd_b200_md_run_host(mrmd_b200_md* md, int64_t nsteps, double* posHost, dou
     const size_t bytes = size_t(n) * 24;
     if (md->sIn == nullptr)
     {
-        MB_CUDA(cudaStreamCreateWithFlags(&md->sIn, cudaStreamNonBlocking));
-        MB_CUDA(cudaStreamCreateWithFlags(&md->sOut, cudaStreamNonBlocking));
+        // highest priority: the pack kernel in front of a download must not queue behind the blocks of the force
+        // kernel it is meant to overlap
+        int prioLow = 0, prioHigh = 0;
+        MB_CUDA(cudaDeviceGetStreamPriorityRange(&prioLow, &prioHigh));
+        MB_CUDA(cudaStreamCreateWithPriority(&md->sIn, cudaStreamNonBlocking, prioHigh));
+        MB_CUDA(cudaStreamCreateWithPriority(&md->sOut, cudaStreamNonBlocking, prioHigh));
         for (cudaEvent_t* e : {&md->evUpPos, &md->evUpVel, &md->evPosReady, &md->evStepDone})
             MB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         for (int c = 0; c < mrmd_b200_md::HB_CHUNKS; ++c)
             for (cudaEvent_t* e : {&md->evDownPos[c], &md->evDownVel[c]})
                 MB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     }
-    constexpr int K = mrmd_b200_md::HB_CHUNKS;
-    size_t off[K + 1];
+    // chunks per array and direction (MRMD_B200_HB_CHUNKS overrides the default of 4 for measurements)
+    int K = 4;
+    if (const char* e = std::getenv("MRMD_B200_HB_CHUNKS")) K = std::max(1, std::min(int(mrmd_b200_md::HB_CHUNKS), std::atoi(e)));
+    size_t off[mrmd_b200_md::HB_CHUNKS + 1];
     for (int c = 0; c <= K; ++c) off[c] = (c == K) ? bytes : ((bytes * size_t(c) / K) & ~size_t(255));
     // one direction of one array: chunk c waits for gate[c] (if any) and records done[c] (if any)
     auto copyChunks = [&](void* dst, const void* src, cudaMemcpyKind kind, cudaStream_t cs, cudaEvent_t* gate,
