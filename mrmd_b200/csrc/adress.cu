@@ -109,9 +109,14 @@ __global__ void __launch_bounds__(AD_THREADS)
                       double* hist, double* partials, double* result, unsigned int* ticket,
                       const int32_t* __restrict__ activeList, const int* __restrict__ activeCount)
 {
+    // the grid is sized for the case that every molecule has work; blocks past the list leave at once and stay out
+    // of the reduction
+    const int64_t numActive = min(numLocalMols, int64_t(*activeCount));
+    const unsigned int workBlocks = static_cast<unsigned int>((numActive + AD_THREADS - 1) / AD_THREADS);
+    if (blockIdx.x >= workBlocks) return;
     const int64_t slot = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
     double sumEnergy = 0.0, pairs = 0.0, activePairs = 0.0;
-    if (slot < min(numLocalMols, int64_t(*activeCount)))
+    if (slot < numActive)
     {
         const int64_t alpha = activeList[slot];
         const int64_t T = numTypes;
@@ -219,7 +224,7 @@ __global__ void __launch_bounds__(AD_THREADS)
             atomicAdd(m.force[2] + alpha, fAz);
         }
     }
-    gridReduce3<AD_THREADS>(sumEnergy, pairs, activePairs, partials, result, ticket);
+    gridReduce3<AD_THREADS>(sumEnergy, pairs, activePairs, partials, result, ticket, workBlocks);
 }
 
 // The same operator for molecules of exactly four atoms (the tetramers of BASELINE.json configs[3]): four lanes share
@@ -229,18 +234,21 @@ __global__ void __launch_bounds__(AD_THREADS)
 // region and 8 instead of 20 force atomics per molecule pair.  A molecule with another atom count raises *error.
 constexpr int AD_LANES = 4;
 template <bool SAMPLING>
-__global__ void __launch_bounds__(AD_THREADS)
+__global__ void __launch_bounds__(AD_THREADS, 5)
     adressForceLanes4Kernel(MolsView m, AtomsView a, int64_t numLocalMols, const int32_t* __restrict__ counts,
                             const int32_t* __restrict__ neigh, int64_t pitch, LJTable table, double rcSqr, int64_t numTypes,
                             double* hist, double* partials, double* result, unsigned int* ticket, int* error,
                             const int32_t* __restrict__ activeList, const int* __restrict__ activeCount)
 {
+    const int64_t numActive = min(numLocalMols, int64_t(*activeCount));
+    const unsigned int workBlocks = static_cast<unsigned int>((numActive * AD_LANES + AD_THREADS - 1) / AD_THREADS);
+    if (blockIdx.x >= workBlocks) return;  // see adressForceKernel
     const int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
     const int64_t slot = t / AD_LANES;
     const int li = int(t % AD_LANES);
     const unsigned gmask = 0xFu << ((threadIdx.x & 31) & ~3);
     double sumEnergy = 0.0, pairs = 0.0, activePairs = 0.0;
-    bool valid = slot < min(numLocalMols, int64_t(*activeCount));
+    bool valid = slot < numActive;
     const int64_t alpha = valid ? activeList[slot] : 0;
     longlong2 ocA = make_longlong2(0, 0);
     if (valid)
@@ -384,7 +392,7 @@ __global__ void __launch_bounds__(AD_THREADS)
             }
         }
     }
-    gridReduce3<AD_THREADS>(sumEnergy, pairs, activePairs, partials, result, ticket);
+    gridReduce3<AD_THREADS>(sumEnergy, pairs, activePairs, partials, result, ticket, workBlocks);
 }
 
 // updateMeanCompensationEnergy, LJ_IdealGas.cpp:21-50 (runningAverageFactor = 10)

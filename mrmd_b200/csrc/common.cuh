@@ -353,10 +353,13 @@ __device__ __forceinline__ long long warpSumLL(long long v)
 // Deterministic grid-wide sum of three per-thread scalars: warp shuffle -> block -> per-block partial;
 // the last block to arrive (ticket counter) adds the partials in a fixed order and resets the ticket.
 // partials holds 3 * gridDim.x doubles; result 6 doubles: [0..2] this launch, [3..5] running sums.
+// numBlocks (0: the whole grid): only blocks [0, numBlocks) take part -- the others must have returned before the
+// call, and with numBlocks == 0 participants nothing is written (the caller zeroes result[0..2] before the launch).
 template <int THREADS>
 __device__ __forceinline__ void gridReduce3(double e, double v, double c, double* partials, double* result,
-                                            unsigned int* ticket)
+                                            unsigned int* ticket, unsigned int numBlocks = 0)
 {
+    if (numBlocks == 0) numBlocks = gridDim.x;
     __shared__ double sRed[3][THREADS / 32];
     __shared__ bool sLast;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -384,13 +387,13 @@ __device__ __forceinline__ void gridReduce3(double e, double v, double c, double
         partials[2 * gridDim.x + blockIdx.x] = sc;
         __threadfence();
         const unsigned int t = atomicAdd(ticket, 1u);
-        sLast = (t == gridDim.x - 1);
+        sLast = (t == numBlocks - 1);
     }
     __syncthreads();
     if (!sLast) return;
     __threadfence();
     double acc[3] = {0, 0, 0};
-    for (unsigned int b = threadIdx.x; b < gridDim.x; b += THREADS)
+    for (unsigned int b = threadIdx.x; b < numBlocks; b += THREADS)
     {
         acc[0] += __ldcg(partials + b);
         acc[1] += __ldcg(partials + gridDim.x + b);

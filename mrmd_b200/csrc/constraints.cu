@@ -20,6 +20,8 @@ struct mrmd_b200_constraints
     mrmd_b200::DevBuf bondDist;     // double eqDistance per bond
     mrmd_b200::DevBuf updatedPos;   // double4 per atom (impl::Shake::updatedPos_)
     int* dErr = nullptr;            // set by a kernel that meets a bond outside its molecule
+    // set by the step-loop drivers only: every local molecule has exactly maxBondAtoms atoms and owns all local atoms
+    bool uniformMolecules = false;
 };
 
 namespace mrmd_b200
@@ -215,10 +217,12 @@ __global__ void shakeVelocityKernel(MolsView m, AtomsView a, int64_t numLocalMol
 
 // enforceVelocityConstraints for bonds among the first NA <= 4 atoms of a molecule: {pos, vel, 1 / mass} of the
 // molecule in shared memory, the bonds walked in order, the velocities written back once
-template <int NA>
+// KICK: VelocityVerlet::postForceIntegrate (action/VelocityVerlet.cpp:72-90, the arithmetic of integratePostKernel)
+// is applied to the velocities as they are loaded -- for molecules of exactly NA atoms this replaces the separate pass
+template <int NA, bool KICK>
 __global__ void __launch_bounds__(SHAKE_FUSED_THREADS)
     rattleFusedKernel(MolsView m, AtomsView a, int64_t numLocalMols, const long long* __restrict__ bondIdx, int64_t numBonds,
-                      int* error)
+                      double halfDt, int* error)
 {
     __shared__ double sm[7 * NA * SHAKE_FUSED_THREADS];
     const int64_t mol = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
@@ -238,9 +242,16 @@ __global__ void __launch_bounds__(SHAKE_FUSED_THREADS)
         at(POS, k) = p.x;
         at(POS + 1, k) = p.y;
         at(POS + 2, k) = p.z;
+        const double mass = a.mass[oc.x + k];
+        const double dtfm = halfDt / mass;
 #pragma unroll
-        for (int d = 0; d < 3; ++d) at(VEL + d, k) = a.vel[d][oc.x + k];
-        at(INVMASS, k) = 1.0 / a.mass[oc.x + k];
+        for (int d = 0; d < 3; ++d)
+        {
+            double v = a.vel[d][oc.x + k];
+            if (KICK) v = __dadd_rn(v, __dmul_rn(dtfm, a.force[d][oc.x + k]));
+            at(VEL + d, k) = v;
+        }
+        at(INVMASS, k) = 1.0 / mass;
     }
     for (int64_t b = 0; b < numBonds; ++b)  // Shake::enforceVelocityConstraint, Shake.hpp:56-82
     {
@@ -313,16 +324,32 @@ int constraintsEnforcePositional(mrmd_b200_constraints* c, const mrmd_b200_molec
     return 0;
 }
 
-int constraintsEnforceVelocity(mrmd_b200_constraints* c, const mrmd_b200_molecules* m, mrmd_b200_atoms* a, cudaStream_t st)
+void constraintsSetUniformMolecules(mrmd_b200_constraints* c, bool uniform) { c->uniformMolecules = uniform; }
+
+// postDt > 0: postForceIntegrate(atoms, postDt) first.  It rides along in the fused kernel when every local atom belongs
+// to a local molecule of exactly maxBondAtoms atoms (the step-loop drivers' uniform molecules), else it is its own pass.
+int constraintsEnforceVelocity(mrmd_b200_constraints* c, const mrmd_b200_molecules* m, mrmd_b200_atoms* a, cudaStream_t st,
+                               double postDt)
 {
     MB_CUDA(cudaMemsetAsync(c->dErr, 0, 4, st));
+    const bool fusedKernel = c->maxBondAtoms >= 2 && c->maxBondAtoms <= 4 && m->numLocal > 0 && c->numBonds > 0;
+    const bool kick = postDt > 0.0 && fusedKernel && c->uniformMolecules && a->numLocal == m->numLocal * c->maxBondAtoms;
+    if (postDt > 0.0 && !kick) MB_TRY(mrmd_b200_vv_post(a, postDt, st));
     if (m->numLocal == 0 || c->numBonds == 0) return 0;
-    if (c->maxBondAtoms >= 2 && c->maxBondAtoms <= 4)
+    if (fusedKernel)
     {
         const int blocks = gridFor(m->numLocal, SHAKE_FUSED_THREADS);
-#define MB_RATTLE_FUSED(NA)                                                                                            \
-    rattleFusedKernel<NA><<<blocks, SHAKE_FUSED_THREADS, 0, st>>>(m->v, a->v, m->numLocal, c->bondIdx.as<long long>(),  \
-                                                                  c->numBonds, c->dErr)
+        const double halfDt = 0.5 * postDt;
+#define MB_RATTLE_FUSED(NA)                                                                                               \
+    do                                                                                                                    \
+    {                                                                                                                     \
+        if (kick)                                                                                                         \
+            rattleFusedKernel<NA, true><<<blocks, SHAKE_FUSED_THREADS, 0, st>>>(                                          \
+                m->v, a->v, m->numLocal, c->bondIdx.as<long long>(), c->numBonds, halfDt, c->dErr);                       \
+        else                                                                                                              \
+            rattleFusedKernel<NA, false><<<blocks, SHAKE_FUSED_THREADS, 0, st>>>(                                         \
+                m->v, a->v, m->numLocal, c->bondIdx.as<long long>(), c->numBonds, 0.0, c->dErr);                          \
+    } while (0)
         if (c->maxBondAtoms == 2) MB_RATTLE_FUSED(2);
         else if (c->maxBondAtoms == 3) MB_RATTLE_FUSED(3);
         else MB_RATTLE_FUSED(4);
@@ -440,7 +467,7 @@ int mrmd_b200_constraints_enforce_velocity(mrmd_b200_constraints* c, const mrmd_
     MB_TRY(checkDevice());
     MB_REQUIRE(c != nullptr && m != nullptr && a != nullptr, "constraints_enforce_velocity");
     (void)dt;  // Shake(atoms, dt) only feeds the positional update (Shake.hpp:139-150)
-    MB_TRY(constraintsEnforceVelocity(c, m, a, S(stream)));
+    MB_TRY(constraintsEnforceVelocity(c, m, a, S(stream), 0.0));
     return checkBondError(c->dErr, S(stream));
 }
 

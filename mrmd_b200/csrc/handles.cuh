@@ -87,7 +87,10 @@ int adressRunPeriodic(mrmd_b200_adress* ad, mrmd_b200_atoms* a, const mrmd_b200_
 // constraints.cu: SHAKE / RATTLE launches without the bond-range read-back and its stream synchronisation
 int constraintsEnforcePositional(mrmd_b200_constraints* c, const mrmd_b200_molecules* m, mrmd_b200_atoms* a, double dt,
                                  cudaStream_t st);
-int constraintsEnforceVelocity(mrmd_b200_constraints* c, const mrmd_b200_molecules* m, mrmd_b200_atoms* a, cudaStream_t st);
+int constraintsEnforceVelocity(mrmd_b200_constraints* c, const mrmd_b200_molecules* m, mrmd_b200_atoms* a, cudaStream_t st,
+                               double postDt);
+// promise of the step-loop drivers: uniform molecules that own every local atom (lets postForceIntegrate ride along)
+void constraintsSetUniformMolecules(mrmd_b200_constraints* c, bool uniform);
 int verletBuildTiled(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, const mrmd_b200_subdomain* s, double radius,
                      double cellRatio, int64_t maxNeigh, const int32_t* haloLeft, const int32_t* haloRight,
                      cudaStream_t st);

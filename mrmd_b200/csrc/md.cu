@@ -123,9 +123,9 @@ static int postIntegrate(mrmd_b200_md* md, bool deferPost, cudaStream_t st)
 {
     if (md->constraints != nullptr)
     {
-        // RATTLE needs the kicked velocities: no deferral (tests/Constraints/Constraints.cpp:62-64)
-        MB_TRY(mrmd_b200_vv_post(md->atoms, md->cfg.dt, st));
-        return constraintsEnforceVelocity(md->constraints, md->mols, md->atoms, st);
+        // RATTLE needs the kicked velocities: no deferral (tests/Constraints/Constraints.cpp:62-64); the kick rides
+        // along in the RATTLE kernel when the molecules fit it
+        return constraintsEnforceVelocity(md->constraints, md->mols, md->atoms, st, md->cfg.dt);
     }
     if (deferPost)
     {
@@ -339,6 +339,7 @@ int mrmd_b200_md_create(mrmd_b200_md** out, const mrmd_b200_md_config* cfg, cons
                     eq.push_back(cfg->bondLength);
                 }
             if (rc == 0) rc = mrmd_b200_constraints_set(md->constraints, bi.data(), bj.data(), eq.data(), int64_t(eq.size()));
+            if (rc == 0) constraintsSetUniformMolecules(md->constraints, true);
         }
         if (rc == 0 && cfg->useThermoForce)
             rc = mrmd_b200_thermo_create(&md->thermo, &cfg->thermoTargetDensity, 1, s, cfg->thermoBinWidth,

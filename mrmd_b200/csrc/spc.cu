@@ -169,7 +169,7 @@ __device__ __forceinline__ void spcGenericPair(const AtomsView& a, longlong2 ocA
 // SPC::operator()(CalcInteractions, alpha, sumEnergy), SPC.hpp:143-236.  Pairs of three-atom molecules (water) take
 // the register-resident path; any other pair is walked atom range by atom range as the reference does.
 template <bool DSF>
-__global__ void __launch_bounds__(SPC_THREADS)
+__global__ void __launch_bounds__(SPC_THREADS, 4)
     spcForceKernel(MolsView m, AtomsView a, int64_t numLocalMols, const int32_t* __restrict__ counts,
                    const int32_t* __restrict__ neigh, int64_t pitch, LJType lj, CoulombDev coulomb, double rcSqr,
                    double* partials, double* result, unsigned int* ticket)
