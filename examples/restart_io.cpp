@@ -5,6 +5,7 @@
 //   ./a.out <in.gro> <out.gro> <thermoForce.txt> <steps>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 
 #include "action/LennardJones.hpp"
 #include "action/ThermodynamicForce.hpp"
@@ -13,6 +14,7 @@
 #include "data/Atoms.hpp"
 #include "data/Subdomain.hpp"
 #include "datatypes.hpp"
+#include "io/DumpCSV.hpp"
 #include "io/DumpGRO.hpp"
 #include "io/DumpThermoForce.hpp"
 #include "io/RestoreGRO.hpp"
@@ -67,6 +69,7 @@ int main(int argc, char* argv[])
         action::VelocityVerlet::postForceIntegrate(atoms, dt);
     }
     io::dumpGRO(argv[2], atoms, subdomain, real_c(nsteps) * dt, "restart_io", "Argon", {"Ar"}, false, true);
+    io::dumpCSV(std::string(argv[2]) + ".csv", atoms, false);
 
     // thermodynamic force profile: forces(i, j) = (i + 1)(j + 1) as in mrmd/io/ThermoForce.test.cpp:38-44
     const idx_t numBins = 100, numForces = 2;

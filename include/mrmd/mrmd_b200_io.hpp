@@ -126,6 +126,30 @@ inline void dumpGRO(const std::string& filename, data::Atoms& atoms, const data:
     fout << "    " << subdomain.diameter[0] << " " << subdomain.diameter[1] << " " << subdomain.diameter[2] << std::endl;
 }
 
+/// io::dumpCSV (io/DumpCSV.cpp:26-52): "idx, mol, type, ghost, pos_x, ..., vel_z" with mol = idx / 3 as the reference writes it
+inline void dumpCSV(const std::string& filename, data::Atoms& atoms, bool dumpGhosts = true)
+{
+    data::HostAtoms at(0);
+    data::deep_copy(at, atoms);
+    auto pos = at.getPos();
+    auto vel = at.getVel();
+    auto type = at.getType();
+    std::ofstream fout(filename);
+    if (!fout.is_open())
+    {
+        std::cerr << "Could not open file: " << filename << std::endl;
+        std::exit(EXIT_FAILURE);
+    }
+    fout << "idx, mol, type, ghost, pos_x, pos_y, pos_z, vel_x, vel_y, vel_z" << std::endl;
+    const idx_t lastAtomIdx = atoms.numLocalAtoms + (dumpGhosts ? atoms.numGhostAtoms : 0);
+    for (idx_t idx = 0; idx < lastAtomIdx; ++idx)
+    {
+        fout << idx << ", " << idx / 3 << ", " << type(idx) << ", " << ((idx < atoms.numLocalAtoms) ? 0 : 1) << ", " << pos(idx, 0)
+             << ", " << pos(idx, 1) << ", " << pos(idx, 2) << ", " << vel(idx, 0) << ", " << vel(idx, 1) << ", " << vel(idx, 2)
+             << std::endl;
+    }
+}
+
 /// io::restoreAtoms (io/RestoreTXT.cpp:24-74): whitespace separated "x y z" triples, mass 1, type 0
 inline data::Atoms restoreAtoms(const std::string& filename)
 {

@@ -25,7 +25,7 @@ REFERENCE_HEADERS = [
     "analysis/MeanSquareDisplacement.hpp", "io/RestoreGRO.hpp", "io/DumpGRO.hpp", "io/RestoreTXT.hpp",
     "io/DumpThermoForce.hpp", "io/RestoreThermoForce.hpp", "action/BerendsenThermostat.hpp",
     "action/BerendsenBarostat.hpp", "action/Shake.hpp", "data/Bond.hpp", "action/SPC.hpp", "action/Coulomb.hpp",
-    "action/CoulombDSF.hpp",
+    "action/CoulombDSF.hpp", "io/DumpCSV.hpp",
 ]
 
 
@@ -161,6 +161,11 @@ def test_gro_restart_and_thermo_force_files(tmp_path, golden_dir):
     assert np.allclose(b2, box)
     assert np.abs(p2 - md.atoms["pos"][:md.n]).max() <= 0.5e-3 + 1e-9
     assert np.abs(v2 - md.atoms["vel"][:md.n]).max() <= 0.5e-4 + 1e-9
+    csv = open(gout + ".csv").read().splitlines()  # io::dumpCSV (mrmd/io/DumpCSV.cpp:26-52), local atoms only
+    assert csv[0] == "idx, mol, type, ghost, pos_x, pos_y, pos_z, vel_x, vel_y, vel_z" and len(csv) == len(pos) + 1
+    row = [float(x) for x in csv[6].split(",")]
+    assert row[:4] == [5.0, 1.0, 0.0, 0.0] and np.allclose(row[4:7], md.atoms["pos"][5], rtol=1e-5, atol=1e-5)
+    assert np.allclose(row[7:], md.atoms["vel"][5], rtol=1e-5, atol=1e-5)
     assert out["tfBins"] == out["tfBinsRestored"] == 100
     assert out["maxForceDiff"] <= 1e-3 and out["maxGridDiff"] <= 1e-5  # default ostream precision: 6 significant digits
     lines = open(tf).read().splitlines()
