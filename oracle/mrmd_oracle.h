@@ -16,7 +16,9 @@
  *     criterion and pair counts are pinned by the 1 310 403-pair golden; the
  *     inclusive list cutoff (<=), the grid arithmetic and in-cell ordering are
  *     "parity unpinned".  The Langevin random stream is parity unpinned as well
- *     (Kokkos XorShift1024 pool is scheduling dependent); we define Philox4x32-10.
+ *     (Kokkos XorShift1024 pool is scheduling dependent); we define Philox4x32-10,
+ *     pinned statistically by the reference's thermostat integration test
+ *     (tests/test_oracle_integration.py).
  *
  * Layouts follow the reference's default build (MRMD_VECTOR_LENGTH=1, i.e. an
  * array of 104-byte records, mrmd/data/Atoms.hpp:47-53, Molecules.hpp:41-47).

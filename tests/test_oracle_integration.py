@@ -1,0 +1,124 @@
+"""The reference's integration tests on the path, run through the CPU oracle with the reference's own acceptance
+criteria (statistical: they do not depend on the random stream that fills the box).  CPU only.
+
+tests/NVT/NVT.cpp:123-191: 4 095 Lennard-Jones atoms at rho = 0.8442 thrown uniformly into the box, 2 001 steps of
+velocity Verlet (dt = 0.005) with the Berendsen thermostat (gamma = 1) applied between the force and the post-force
+kick; the exponentially averaged pressure has to follow the equation of state
+p(T) = -0.89528939 T^2 + 7.48553466 T - 4.00636731 within 0.3 and the temperature its target within 0.1."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+
+class Ema:
+    """util::ExponentialMovingAverage (mrmd/util/ExponentialMovingAverage.hpp:23-54)"""
+
+    def __init__(self, alpha):
+        self.alpha, self.beta, self.val, self.first = alpha, 1.0 - alpha, 0.0, True
+
+    def append(self, v):
+        if self.first:
+            self.first, self.val = False, v
+        else:
+            self.val = v * self.alpha + self.val * self.beta
+
+
+@pytest.mark.parametrize("target", [0.8, 1.2, 1.6])
+def test_reference_nvt_equation_of_state(oracle, target):
+    from oracle.md_loop import OracleMD
+
+    lx, rho, dt, nsteps, gamma = 16.92926877476863, 0.8442, 0.005, 2001, 1.0
+    volume = lx ** 3
+    n = int(rho * volume)
+    rng = np.random.default_rng(1234)
+    pos = rng.random((n, 3)) * lx
+    vel = (rng.random((n, 3)) - 0.5) * 1.0
+    md = OracleMD(pos, vel, np.full(3, lx), dt=dt, rc=2.5, skin=0.3, sigma=1.0, epsilon=1.0, cap=0.7, max_neigh=60,
+                  langevin=False, cell_sort=True)
+    L, a = md.L, md.atoms
+    p, t = Ema(0.01), Ema(0.01)
+    for step in range(nsteps):
+        md.max_disp += L.or_vv_pre(a.ctypes.data, n, dt)
+        if md.max_disp >= md.skin * 0.5:
+            md.max_disp = 0.0
+            md._rebuild()
+        else:
+            L.or_ghost_update_pos(a.ctypes.data, n, md.ng, md.corr.ctypes.data, C.byref(md.sub))
+        L.or_zero_force(a.ctypes.data, n + md.ng)
+        L.or_lj_apply(a.ctypes.data, n, md.counts.ctypes.data, md.neigh.ctypes.data, md.neigh.shape[1], C.addressof(md.table),
+                      md.rc * md.rc, 1, None, md.energy_virial.ctypes.data)
+        if step < 201:  # NVT.cpp:165-169: the averages restart every step while the box melts
+            p, t = Ema(0.1), Ema(0.1)
+        ek = L.or_kinetic_energy(a.ctypes.data, n)
+        p.append(2.0 * (ek - md.energy_virial[1]) / (3.0 * volume))
+        t.append((2.0 / 3.0) * ek / n)
+        L.or_berendsen_thermostat(a.ctypes.data, n, t.val, target, gamma)
+        L.or_ghost_fold_force(a.ctypes.data, n, md.ng, md.corr.ctypes.data)
+        L.or_vv_post(a.ctypes.data, n, dt)
+    assert abs(p.val - (-0.89528939 * target * target + 7.48553466 * target - 4.00636731)) < 0.3  # EXPECT_NEAR(p, ..., 0.3_r)
+    assert abs(t.val - target) < 0.1                                                                 # EXPECT_NEAR(T, ..., 0.1_r)
+
+
+@pytest.mark.parametrize("target_t,target_p", [(2.8, 9.1), (2.5, 8.5), (2.0, 8.0)])
+def test_reference_npt(oracle, target_t, target_p):
+    """tests/NPT/NPT.cpp:134-212: the same box with the Berendsen thermostat (gamma = 0.1) right after the pre-force step
+    and the Berendsen barostat (gamma = 0.01) every 100 steps after step 200; T within 0.1, p within 0.2 of the targets"""
+    from oracle.md_loop import OracleMD
+
+    lx, rho, dt, nsteps, gamma, wf = 16.92926877476863, 0.8442, 0.005, 2001, 0.1, 0.02
+    volume = lx ** 3
+    n = int(rho * volume)
+    rng = np.random.default_rng(1234)
+    pos = rng.random((n, 3)) * lx
+    vel = (rng.random((n, 3)) - 0.5) * 1.0
+    md = OracleMD(pos, vel, np.full(3, lx), dt=dt, rc=2.5, skin=0.3, sigma=1.0, epsilon=1.0, cap=0.7, max_neigh=60,
+                  langevin=False, cell_sort=True, ghost_capacity_factor=3.0)
+    L, a = md.L, md.atoms
+    p, t = Ema(wf), Ema(wf)
+    t.append(L.or_kinetic_energy(a.ctypes.data, n) / n * 2.0 / 3.0)
+    for step in range(nsteps):
+        md.max_disp += L.or_vv_pre(a.ctypes.data, n, dt)
+        if step > 200 and step % 100 == 0:
+            L.or_berendsen_barostat(a.ctypes.data, n, p.val, target_p, gamma * 0.1, C.byref(md.sub), 1, 1, 1)
+            md.box = np.array(md.sub.maxCorner)
+            volume = float(np.prod(md.box))
+            md.max_disp = np.finfo(np.float64).max
+        L.or_berendsen_thermostat(a.ctypes.data, n, t.val, target_t, gamma)
+        if md.max_disp >= md.skin * 0.5:
+            md.max_disp = 0.0
+            md._rebuild()
+        else:
+            L.or_ghost_update_pos(a.ctypes.data, n, md.ng, md.corr.ctypes.data, C.byref(md.sub))
+        L.or_zero_force(a.ctypes.data, n + md.ng)
+        L.or_lj_apply(a.ctypes.data, n, md.counts.ctypes.data, md.neigh.ctypes.data, md.neigh.shape[1], C.addressof(md.table),
+                      md.rc * md.rc, 1, None, md.energy_virial.ctypes.data)
+        if step < 201:
+            p, t = Ema(wf), Ema(wf)
+        ek = L.or_kinetic_energy(a.ctypes.data, n)
+        p.append(2.0 * (ek - md.energy_virial[1]) / (3.0 * volume))
+        t.append((2.0 / 3.0) * ek / n)
+        L.or_ghost_fold_force(a.ctypes.data, n, md.ng, md.corr.ctypes.data)
+        L.or_vv_post(a.ctypes.data, n, dt)
+    assert abs(t.val - target_t) < 0.1  # EXPECT_NEAR(T, targetTemperature, 0.1_r)
+    assert abs(p.val - target_p) < 0.2  # EXPECT_NEAR(p, targetPressure, 0.2_r)
+
+
+@pytest.mark.parametrize("local", [False, True])
+def test_reference_langevin_thermostat(oracle, local):
+    """tests/LangevinThermostat/LangevinThermostat.cpp:83-136: 100 000 free atoms, zeta = 1e5, 21 steps of dt = 0.001; the
+    temperature has to sit within 0.01 of 1.12 -- the statistical pin of the Philox stream that replaces the reference's
+    (scheduling dependent) XorShift pool.  local: preForceIntegrate_apply_if with IsInSymmetricSlab(centre, 0, 5)."""
+    L = oracle.lib()
+    n, lx, dt, temperature = 100000, 10.0, 0.001, 1.12
+    rng = np.random.default_rng(1234)
+    a = np.zeros(n, dtype=oracle.ATOM)
+    a["pos"], a["vel"], a["mass"] = rng.random((n, 3)) * lx, (rng.random((n, 3)) - 0.5) * 10.0, 1.0
+    pred = oracle.make_pred(oracle.PRED_SLAB, 0, 5.0, 0.0, 5.0, 0.0) if local else None
+    for step in range(21):
+        L.or_langevin_pre(a.ctypes.data, n, dt, 1e5, temperature, 1234, step, C.byref(pred) if local else None)
+        if local:
+            L.or_zero_force(a.ctypes.data, n)
+        L.or_vv_post(a.ctypes.data, n, dt)
+    t = (2.0 / 3.0) * L.or_kinetic_energy(a.ctypes.data, n) / n
+    assert abs(t - temperature) < 0.01  # EXPECT_NEAR(T, config.temperature, 0.01_r)
