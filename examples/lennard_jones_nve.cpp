@@ -52,6 +52,8 @@ struct Lcg
 
 int main(int argc, char* argv[])
 {
+    Kokkos::ScopeGuard scope_guard(argc, argv);  // examples/02:242
+    Kokkos::Timer timer;                         // examples/02:117
     Config config;
     const idx_t sites = argc > 1 ? std::atoll(argv[1]) : 16;
     if (argc > 2) config.nsteps = std::atoll(argv[2]);
@@ -123,9 +125,15 @@ int main(int argc, char* argv[])
     const auto systemMomentum = analysis::getSystemMomentum(atoms);
     const auto msd = meanSquareDisplacement.calc(atoms, subdomain);
 
+    // neighbours of the first atom through the reference's accessors (HalfNeighborList, datatypes.hpp:193)
+    idx_t neighborSum = 0;
+    for (idx_t n = 0; n < HalfNeighborList::numNeighbor(verletList, 0); ++n) neighborSum += HalfNeighborList::getNeighbor(verletList, 0, n);
+
     data::deep_copy(h_atoms, atoms);
     auto pos = h_atoms.getPos();
-    std::printf("{\"atoms\": %lld, \"ghosts\": %lld, \"steps\": %lld, \"rebuilds\": %lld, \"pairs\": %zu, "
+    std::printf("{\"seconds\": %.6f, \"neighbors0\": %lld, \"neighborSum0\": %lld, ", timer.seconds(),
+                static_cast<long long>(HalfNeighborList::numNeighbor(verletList, 0)), static_cast<long long>(neighborSum));
+    std::printf("\"atoms\": %lld, \"ghosts\": %lld, \"steps\": %lld, \"rebuilds\": %lld, \"pairs\": %zu, "
                 "\"E0\": %.17g, \"Ek\": %.17g, \"T\": %.17g, \"p\": %.17g, \"msd\": %.17g, \"momentum\": [%.17g, %.17g, %.17g], "
                 "\"x0\": [%.17g, %.17g, %.17g]}\n",
                 static_cast<long long>(atoms.numLocalAtoms), static_cast<long long>(atoms.numGhostAtoms),

@@ -18,6 +18,7 @@
 #pragma once
 
 #include <array>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -406,6 +407,7 @@ public:
                const real_t gridMax[3], idx_t maxNeigh = 64)
     {
         pos.owner->push();
+        hostValid_ = false;
         check(mrmd_b200_verlet_build_atoms(h_.get(), pos.owner->handle(), begin, end, radius, cellRatio, gridMin, gridMax,
                                            maxNeigh, defaultStream), "VerletList::build");
     }
@@ -413,6 +415,7 @@ public:
                const real_t gridMax[3], idx_t maxNeigh = 64)
     {
         pos.owner->push();
+        hostValid_ = false;
         check(mrmd_b200_verlet_build_molecules(h_.get(), pos.owner->handle(), begin, end, radius, cellRatio, gridMin, gridMax,
                                                maxNeigh, defaultStream), "VerletList::build");
     }
@@ -420,6 +423,7 @@ public:
     void buildPeriodic(const data::Atoms& atoms, const data::Subdomain& subdomain, real_t radius, real_t cellRatio = 1_r, idx_t maxNeigh = 64)
     {
         atoms.push();
+        hostValid_ = false;
         const auto s = subdomain.c();
         check(mrmd_b200_verlet_build_periodic(h_.get(), atoms.handle(), &s, radius, cellRatio, maxNeigh, defaultStream), "buildPeriodic");
     }
@@ -441,13 +445,43 @@ public:
         check(mrmd_b200_verlet_read(h_.get(), counts.data(), neighbors.data(), MRMD_B200_MEM_HOST, defaultStream), "verlet_read");
     }
     mrmd_b200_verlet* handle() const { return h_.get(); }
+    /// host-side element access behind Cabana::NeighborList<...>::numNeighbor / getNeighbor (a host copy of the table
+    /// is fetched once per build; lists from buildPeriodic are read through toHostPeriodic instead)
+    idx_t numNeighbor(idx_t particle) const
+    {
+        fetch();
+        return hostCounts_[static_cast<size_t>(particle)];
+    }
+    idx_t getNeighbor(idx_t particle, idx_t n) const
+    {
+        fetch();
+        return hostNeighbors_[static_cast<size_t>(particle * hostWidth_ + n)];
+    }
 
 private:
+    void fetch() const
+    {
+        if (hostValid_) return;
+        toHost(hostCounts_, hostNeighbors_, hostWidth_);
+        hostValid_ = true;
+    }
     std::shared_ptr<mrmd_b200_verlet> h_;
+    mutable bool hostValid_ = false;
+    mutable std::vector<int32_t> hostCounts_, hostNeighbors_;
+    mutable idx_t hostWidth_ = 0;
+};
+/// Cabana::NeighborList<VerletList>: the static accessors the reference's kernels use (datatypes.hpp:192-193)
+template <bool HALF>
+struct NeighborListT
+{
+    static idx_t numNeighbor(const VerletListT<HALF>& list, idx_t particle) { return list.numNeighbor(particle); }
+    static idx_t getNeighbor(const VerletListT<HALF>& list, idx_t particle, idx_t n) { return list.getNeighbor(particle, n); }
 };
 }  // namespace detail
 using HalfVerletList = detail::VerletListT<true>;   // datatypes.hpp:184-187
 using FullVerletList = detail::VerletListT<false>;  // datatypes.hpp:188-191
+using HalfNeighborList = detail::NeighborListT<true>;
+using FullNeighborList = detail::NeighborListT<false>;
 
 // ------------------------------------------------------------------------------------------------------
 namespace action
@@ -1035,7 +1069,32 @@ private:
 }  // namespace analysis
 }  // namespace mrmd
 
-/// stand-ins for the two third-party calls every reference driver makes
+/// stand-ins for the third-party calls the reference's drivers make themselves
+namespace Kokkos
+{
+/// Kokkos::ScopeGuard scope_guard(argc, argv) (examples/02_LennardJones_NVE.cpp:242): nothing to initialise here
+struct ScopeGuard
+{
+    ScopeGuard() = default;
+    ScopeGuard(int&, char**) {}
+    ScopeGuard(const ScopeGuard&) = delete;
+    ScopeGuard& operator=(const ScopeGuard&) = delete;
+};
+/// Kokkos::fence(): every wrapper call is asynchronous on mrmd::defaultStream
+inline void fence() { mrmd::fence(); }
+/// Kokkos::Timer (examples/02:117): wall clock since construction / reset
+class Timer
+{
+public:
+    Timer() : start_(std::chrono::steady_clock::now()) {}
+    double seconds() const { return std::chrono::duration<double>(std::chrono::steady_clock::now() - start_).count(); }
+    void reset() { start_ = std::chrono::steady_clock::now(); }
+
+private:
+    std::chrono::steady_clock::time_point start_;
+};
+}  // namespace Kokkos
+
 namespace Cabana
 {
 /// Cabana::deep_copy(force, value) (examples/02_LennardJones_NVE.cpp:174-175)

@@ -99,6 +99,9 @@ def test_nve_driver_matches_oracle(tmp_path):
     assert out["rebuilds"] == st["rebuilds"]
     assert out["ghosts"] == md.ng
     assert out["pairs"] == int(md.counts.sum())
+    # HalfNeighborList::numNeighbor / getNeighbor (host accessors of the mirror) on the first atom's row
+    assert out["neighbors0"] == int(md.counts[0]) and out["neighborSum0"] == int(md.neigh[0, :md.counts[0]].sum())
+    assert out["seconds"] > 0
     # NVE trajectories through the same neighbour lists: summation order is the only difference
     assert abs(out["E0"] - st["energy"]) <= 1e-9 * abs(st["energy"])
     v = md.atoms["vel"][:md.n]
