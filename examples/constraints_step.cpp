@@ -9,6 +9,8 @@
 
 #include "action/BerendsenBarostat.hpp"
 #include "action/BerendsenThermostat.hpp"
+#include "action/LimitAcceleration.hpp"
+#include "action/LimitVelocity.hpp"
 #include "action/Shake.hpp"
 #include "action/VelocityVerlet.hpp"
 #include "analysis/KineticEnergy.hpp"
@@ -18,6 +20,7 @@
 #include "data/Molecules.hpp"
 #include "data/Subdomain.hpp"
 #include "datatypes.hpp"
+#include "util/ExponentialMovingAverage.hpp"
 
 using namespace mrmd;
 
@@ -57,6 +60,9 @@ int main()
     mc.enforcePositionalConstraints(molecules, atoms, dt);
     action::VelocityVerlet::preForceIntegrate(atoms, dt);
     atoms.setForce(0_r);
+    // the limiters every reference driver includes (examples/02:28-29); wide open here
+    action::limitAccelerationPerComponent(atoms, 1e9_r);
+    action::limitVelocityPerComponent(atoms, 1e9_r);
     action::VelocityVerlet::postForceIntegrate(atoms, dt);
     mc.enforceVelocityConstraints(molecules, atoms, dt);
 
@@ -73,7 +79,9 @@ int main()
     const real_t relVel = (dx[0] * dv[0] + dx[1] * dv[1] + dx[2] * dv[2]) / dist;
 
     data::Subdomain subdomain({-2_r, -2_r, -2_r}, {2_r, 2_r, 2_r}, 0.5_r);
-    const real_t T0 = analysis::getMeanKineticEnergy(atoms) * (2_r / 3_r);
+    util::ExponentialMovingAverage averageT(0.5_r);  // tests/NVT/NVT.cpp:132
+    averageT << analysis::getMeanKineticEnergy(atoms) * (2_r / 3_r);
+    const real_t T0 = averageT;
     action::BerendsenThermostat::apply(atoms, T0, 2_r * T0, 1_r);
     const real_t T1 = analysis::getMeanKineticEnergy(atoms) * (2_r / 3_r);
     const real_t p = analysis::getPressure(atoms, subdomain);

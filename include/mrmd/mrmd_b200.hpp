@@ -69,6 +69,31 @@ inline void fence() { detail::check(mrmd_b200_sync(defaultStream), "sync"); }
 // ------------------------------------------------------------------------------------------------------
 namespace util
 {
+/// util::ExponentialMovingAverage (util/ExponentialMovingAverage.hpp:23-60): host-side running average of the drivers'
+/// statistics (tests/NVT/NVT.cpp:131-132)
+class ExponentialMovingAverage
+{
+public:
+    explicit ExponentialMovingAverage(const real_t& weightingFactor) : alpha_(weightingFactor), beta_(1_r - weightingFactor) {}
+    operator real_t() const { return val_; }
+    real_t toReal() const { return val_; }
+    void append(const real_t& val)
+    {
+        val_ = isFirstVal_ ? val : val * alpha_ + val_ * beta_;
+        isFirstVal_ = false;
+    }
+
+private:
+    real_t alpha_, beta_;
+    real_t val_ = 0_r;
+    bool isFirstVal_ = true;
+};
+inline ExponentialMovingAverage& operator<<(ExponentialMovingAverage& lhs, const real_t& rhs)
+{
+    lhs.append(rhs);
+    return lhs;
+}
+
 /// util::IsInSymmetricSlab (util/IsInSymmetricSlab.hpp:24-64) as a parametric predicate
 class IsInSymmetricSlab
 {
@@ -829,6 +854,19 @@ using BondView = std::vector<Bond>;  ///< host side stand-in for Kokkos::View<Bo
 
 namespace action
 {
+/// action::limitAccelerationPerComponent (action/LimitAcceleration.cpp:21-45)
+inline void limitAccelerationPerComponent(data::Atoms& atoms, const real_t& maxAccelerationPerComponent)
+{
+    atoms.push();
+    detail::check(mrmd_b200_limit_acceleration(atoms.handle(), maxAccelerationPerComponent, defaultStream), "limitAccelerationPerComponent");
+}
+/// action::limitVelocityPerComponent (action/LimitVelocity.cpp:23-43)
+inline void limitVelocityPerComponent(data::Atoms& atoms, const real_t& maxVelocityPerComponent)
+{
+    atoms.push();
+    detail::check(mrmd_b200_limit_velocity(atoms.handle(), maxVelocityPerComponent, defaultStream), "limitVelocityPerComponent");
+}
+
 /// action::BerendsenThermostat::apply (action/BerendsenThermostat.cpp:25-50)
 namespace BerendsenThermostat
 {

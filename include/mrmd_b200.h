@@ -369,6 +369,11 @@ int mrmd_b200_berendsen_thermostat(mrmd_b200_atoms* a, double currentTemperature
  * the chosen axes of the subdomain (Subdomain::scaleDim) and of the local atoms' positions */
 int mrmd_b200_berendsen_barostat(mrmd_b200_atoms* a, double currentPressure, double targetPressure, double gamma,
                                  mrmd_b200_subdomain* s, int stretchX, int stretchY, int stretchZ, void* stream);
+/* replace limitAccelerationPerComponent (action/LimitAcceleration.cpp:21-45) and limitVelocityPerComponent
+ * (action/LimitVelocity.cpp:23-43): per-component clamps of force / mass and of the velocity of the local atoms (the
+ * headers every reference driver includes) */
+int mrmd_b200_limit_acceleration(mrmd_b200_atoms* a, double maxAccelerationPerComponent, void* stream);
+int mrmd_b200_limit_velocity(mrmd_b200_atoms* a, double maxVelocityPerComponent, void* stream);
 /* MoleculeConstraints(atomsPerMolecule, numConstraintIterations) (:247-250) */
 int mrmd_b200_constraints_create(mrmd_b200_constraints** out, int64_t atomsPerMolecule, int64_t numConstraintIterations);
 int mrmd_b200_constraints_destroy(mrmd_b200_constraints* c);

@@ -145,6 +145,8 @@ SIGNATURES = {
     "mrmd_b200_msd_calc_molecules": (C.c_int, [vp, vp, pSub, pdbl, vp]),
     "mrmd_b200_berendsen_thermostat": (C.c_int, [vp, dbl, dbl, dbl, vp]),
     "mrmd_b200_berendsen_barostat": (C.c_int, [vp, dbl, dbl, dbl, pSub, C.c_int, C.c_int, C.c_int, vp]),
+    "mrmd_b200_limit_acceleration": (C.c_int, [vp, dbl, vp]),
+    "mrmd_b200_limit_velocity": (C.c_int, [vp, dbl, vp]),
     "mrmd_b200_constraints_create": (C.c_int, [pvp, i64, i64]),
     "mrmd_b200_constraints_destroy": (C.c_int, [vp]),
     "mrmd_b200_constraints_set": (C.c_int, [vp, vp, vp, vp, i64]),

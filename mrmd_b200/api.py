@@ -648,6 +648,16 @@ class BerendsenBarostat:
                                                int(stretchX), int(stretchY), int(stretchZ), _stream(stream)))
 
 
+def limitAccelerationPerComponent(atoms, maxAccelerationPerComponent, stream=None):
+    """action::limitAccelerationPerComponent (action/LimitAcceleration.cpp:21-45)"""
+    check(L().mrmd_b200_limit_acceleration(atoms.h, maxAccelerationPerComponent, _stream(stream)))
+
+
+def limitVelocityPerComponent(atoms, maxVelocityPerComponent, stream=None):
+    """action::limitVelocityPerComponent (action/LimitVelocity.cpp:23-43)"""
+    check(L().mrmd_b200_limit_velocity(atoms.h, maxVelocityPerComponent, _stream(stream)))
+
+
 class MoleculeConstraints:
     """action::MoleculeConstraints (action/Shake.hpp:159-251): SHAKE / RATTLE over the bonds of every local molecule"""
 

@@ -35,6 +35,32 @@ __global__ void scaleVelocityKernel(AtomsView a, int64_t n, double beta)
     a.vel[2][idx] *= beta;
 }
 
+// limitAccelerationPerComponent, action/LimitAcceleration.cpp:21-45 (min then max, each on force * invM, times m)
+__global__ void limitAccelerationKernel(AtomsView a, int64_t n, double maxAcc)
+{
+    const int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (idx >= n) return;
+    const double m = a.mass[idx];
+    const double invM = 1.0 / m;
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+    {
+        double f = a.force[d][idx];
+        f = fmin(f * invM, +maxAcc) * m;
+        f = fmax(f * invM, -maxAcc) * m;
+        a.force[d][idx] = f;
+    }
+}
+
+// limitVelocityPerComponent, action/LimitVelocity.cpp:23-43
+__global__ void limitVelocityKernel(AtomsView a, int64_t n, double maxVel)
+{
+    const int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (idx >= n) return;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) a.vel[d][idx] = fmax(fmin(a.vel[d][idx], +maxVel), -maxVel);
+}
+
 __global__ void scalePositionKernel(double4* pos, int64_t n, double mu, int sx, int sy, int sz)
 {
     const int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
@@ -394,6 +420,26 @@ int mrmd_b200_berendsen_barostat(mrmd_b200_atoms* a, double currentPressure, dou
     if (a->numLocal == 0) return 0;
     scalePositionKernel<<<gridFor(a->numLocal, 256), 256, 0, S(stream)>>>(a->v.pos, a->numLocal, mu, stretchX, stretchY,
                                                                           stretchZ);
+    MB_LAUNCHED();
+    return 0;
+}
+
+int mrmd_b200_limit_acceleration(mrmd_b200_atoms* a, double maxAccelerationPerComponent, void* stream)
+{
+    MB_TRY(checkDevice());
+    MB_REQUIRE(a != nullptr, "limit_acceleration");
+    if (a->numLocal == 0) return 0;
+    limitAccelerationKernel<<<gridFor(a->numLocal, 256), 256, 0, S(stream)>>>(a->v, a->numLocal, maxAccelerationPerComponent);
+    MB_LAUNCHED();
+    return 0;
+}
+
+int mrmd_b200_limit_velocity(mrmd_b200_atoms* a, double maxVelocityPerComponent, void* stream)
+{
+    MB_TRY(checkDevice());
+    MB_REQUIRE(a != nullptr, "limit_velocity");
+    if (a->numLocal == 0) return 0;
+    limitVelocityKernel<<<gridFor(a->numLocal, 256), 256, 0, S(stream)>>>(a->v, a->numLocal, maxVelocityPerComponent);
     MB_LAUNCHED();
     return 0;
 }

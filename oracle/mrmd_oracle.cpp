@@ -1114,6 +1114,30 @@ void or_berendsen_thermostat(or_atom_t* atoms, int64_t numLocal, double currentT
         for (int d = 0; d < 3; ++d) atoms[idx].vel[d] *= beta;
 }
 
+// action/LimitAcceleration.cpp:21-45, action/LimitVelocity.cpp:23-43
+void or_limit_acceleration(or_atom_t* atoms, int64_t numLocal, double maxAcc)
+{
+    for (int64_t i = 0; i < numLocal; ++i)
+    {
+        const double m = atoms[i].mass, invM = 1.0 / m;
+        for (int d = 0; d < 3; ++d)
+        {
+            atoms[i].force[d] = std::min(atoms[i].force[d] * invM, +maxAcc) * m;
+            atoms[i].force[d] = std::max(atoms[i].force[d] * invM, -maxAcc) * m;
+        }
+    }
+}
+
+void or_limit_velocity(or_atom_t* atoms, int64_t numLocal, double maxVel)
+{
+    for (int64_t i = 0; i < numLocal; ++i)
+        for (int d = 0; d < 3; ++d)
+        {
+            atoms[i].vel[d] = std::min(atoms[i].vel[d], +maxVel);
+            atoms[i].vel[d] = std::max(atoms[i].vel[d], -maxVel);
+        }
+}
+
 // action/BerendsenBarostat.cpp:23-50
 void or_berendsen_barostat(or_atom_t* atoms, int64_t numLocal, double currentPressure, double targetPressure, double gamma,
                            or_subdomain_t* s, int stretchX, int stretchY, int stretchZ)

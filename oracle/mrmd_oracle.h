@@ -218,6 +218,8 @@ void or_hist_gradient(const double* in, double* out, double min, double max, int
                       int periodic);
 void or_hist_smoothen(const double* in, double* out, double min, double max, int64_t numBins, int64_t numHist,
                       double sigma, double range, int periodic);
+void or_limit_acceleration(or_atom_t* atoms, int64_t numLocal, double maxAccelerationPerComponent);
+void or_limit_velocity(or_atom_t* atoms, int64_t numLocal, double maxVelocityPerComponent);
 void or_berendsen_thermostat(or_atom_t* atoms, int64_t numLocal, double currentTemperature, double targetTemperature,
                              double gamma);
 void or_berendsen_barostat(or_atom_t* atoms, int64_t numLocal, double currentPressure, double targetPressure, double gamma,

@@ -129,6 +129,8 @@ def lib():
         "or_hist_make_symmetric": (None, [vp, i64, i64]),
         "or_hist_gradient": (None, [vp, vp, C.c_double, C.c_double, i64, i64, C.c_int]),
         "or_hist_smoothen": (None, [vp, vp, C.c_double, C.c_double, i64, i64, C.c_double, C.c_double, C.c_int]),
+        "or_limit_acceleration": (None, [vp, i64, C.c_double]),
+        "or_limit_velocity": (None, [vp, i64, C.c_double]),
         "or_berendsen_thermostat": (None, [vp, i64, C.c_double, C.c_double, C.c_double]),
         "or_berendsen_barostat": (None, [vp, i64, C.c_double, C.c_double, C.c_double, C.POINTER(Subdomain), C.c_int,
                                         C.c_int, C.c_int]),

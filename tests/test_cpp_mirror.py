@@ -25,7 +25,8 @@ REFERENCE_HEADERS = [
     "analysis/MeanSquareDisplacement.hpp", "io/RestoreGRO.hpp", "io/DumpGRO.hpp", "io/RestoreTXT.hpp",
     "io/DumpThermoForce.hpp", "io/RestoreThermoForce.hpp", "action/BerendsenThermostat.hpp",
     "action/BerendsenBarostat.hpp", "action/Shake.hpp", "data/Bond.hpp", "action/SPC.hpp", "action/Coulomb.hpp",
-    "action/CoulombDSF.hpp", "io/DumpCSV.hpp",
+    "action/CoulombDSF.hpp", "io/DumpCSV.hpp", "action/LimitAcceleration.hpp", "action/LimitVelocity.hpp",
+    "util/ExponentialMovingAverage.hpp", "Cabana_NeighborList.hpp",
 ]
 
 

@@ -168,3 +168,28 @@ def test_constraints_vs_oracle(api, oracle, a_per):
     assert np.abs(atoms.getPos() - oa["pos"]).max() < 1e-12
     assert np.allclose(list(sub.maxCorner), list(osub.maxCorner), rtol=1e-15)
     assert np.allclose(list(sub.minGhostCorner), list(osub.minGhostCorner), rtol=1e-15)
+
+
+def test_limit_acceleration_and_velocity(api, oracle):
+    """LimitAcceleration.test.cpp:27-38, LimitVelocity.test.cpp:27-38, then 100 000 random atoms against the oracle"""
+    atoms = single_atom(api)
+    api.limitAccelerationPerComponent(atoms, 0.5)
+    assert np.allclose(atoms.getForce()[0], 0.75, rtol=1e-7)  # EXPECT_FLOAT_EQ(force(0, d), 0.75_r)
+    api.limitVelocityPerComponent(atoms, 0.5)
+    assert np.array_equal(atoms.getVel()[0], [0.5, 0.5, 0.5])
+
+    rng = np.random.default_rng(21)
+    n = 100000
+    pos, vel, force = rng.random((n, 3)), rng.normal(size=(n, 3)) * 2, rng.normal(size=(n, 3)) * 5
+    mass = 0.5 + rng.random(n)
+    atoms = api.Atoms.from_arrays(pos, vel, mass=mass)
+    atoms.set("force", force)
+    oa = np.zeros(n, dtype=oracle.ATOM)
+    oa["pos"], oa["vel"], oa["force"], oa["mass"] = pos, vel, force, mass
+    api.limitAccelerationPerComponent(atoms, 1.5)
+    api.limitVelocityPerComponent(atoms, 1.0)
+    oracle.lib().or_limit_acceleration(oa.ctypes.data, n, 1.5)
+    oracle.lib().or_limit_velocity(oa.ctypes.data, n, 1.0)
+    assert np.array_equal(atoms.getVel()[:n], oa["vel"])
+    assert np.abs(atoms.getForce()[:n] - oa["force"]).max() <= 1e-15 * np.abs(oa["force"]).max()
+    assert np.abs(atoms.getForce()[:n] / mass[:, None]).max() <= 1.5 * (1 + 1e-15)

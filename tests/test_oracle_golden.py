@@ -819,3 +819,18 @@ def test_oracle_molecule_loops_hold_their_bonds(oracle):
     iu = np.triu_indices(4, 1)
     d = np.linalg.norm(p[:, :, None, :] - p[:, None, :, :], axis=-1)[:, iu[0], iu[1]]
     assert np.abs(d - 1.0).max() < 5e-3 and st["rebuilds"] >= 2 and st["pairInteractions"] > 0
+
+
+def test_limit_acceleration_and_velocity_kats(oracle):
+    """mrmd/action/LimitAcceleration.test.cpp:27-38, LimitVelocity.test.cpp:27-38 on mrmd/test/SingleAtom.hpp:28-55"""
+    L = oracle.lib()
+    a = np.zeros(1, dtype=oracle.ATOM)
+    a["pos"], a["vel"], a["force"], a["mass"] = (2.0, 3.0, 4.0), (7.0, 5.0, 3.0), (9.0, 7.0, 8.0), 1.5
+    L.or_limit_acceleration(a.ctypes.data, 1, 0.5)
+    assert all(float_eq(v, 0.75) for v in a["force"][0])
+    L.or_limit_velocity(a.ctypes.data, 1, 0.5)
+    assert all(float_eq(v, 0.5) for v in a["vel"][0])
+    a["vel"], a["force"] = (-7.0, 0.25, -0.5), (-9.0, 0.3, -0.75)
+    L.or_limit_acceleration(a.ctypes.data, 1, 0.5)
+    L.or_limit_velocity(a.ctypes.data, 1, 0.5)
+    assert np.allclose(a["force"][0], (-0.75, 0.3, -0.75), rtol=1e-15) and np.array_equal(a["vel"][0], (-0.5, 0.25, -0.5))
