@@ -102,7 +102,11 @@ enum
     MRMD_B200_ATOM_TYPE = 3, /* int64 */
     MRMD_B200_ATOM_MASS = 4,
     MRMD_B200_ATOM_CHARGE = 5,
-    MRMD_B200_ATOM_RELATIVE_MASS = 6
+    MRMD_B200_ATOM_RELATIVE_MASS = 6,
+    /* int64; not a reference field: the global atom id that keys the Langevin noise (Philox counter), so that a run
+       gives the same trajectory whatever the atom order and however many GPUs share it.  A new container numbers its
+       atoms 0, 1, ...; the id travels with the atom through permute, ghost creation and slab migration. */
+    MRMD_B200_ATOM_ID = 7
 };
 enum
 {
@@ -455,6 +459,10 @@ typedef struct
     int64_t atomsPerMolecule;
     int64_t numConstraintIterations;
     double bondLength;
+    /* 0: energy and virial are reduced on the last step of a run only (they are not observable earlier; the force and
+     * the pair count are the same); 1: on every step, like LennardJones::apply (LennardJones.hpp:187-188) */
+    int32_t energyEveryStep;
+    int32_t reserved0;
 } mrmd_b200_md_config;
 typedef struct
 {
@@ -479,6 +487,8 @@ int mrmd_b200_md_run(mrmd_b200_md* md, int64_t nsteps, int timeForceKernel, mrmd
  * pageable) to the device, runs one step and copies pos, vel and {energy, virial, maxDisplacement} back. */
 int mrmd_b200_md_run_host(mrmd_b200_md* md, int64_t nsteps, double* posHost, double* velHost,
                           double* scalarsHost, mrmd_b200_md_stats* stats, void* stream);
+/* mrmd_b200_md_config::energyEveryStep of an existing driver (LennardJones.hpp:187-188 reduces on every apply) */
+int mrmd_b200_md_set_energy_every_step(mrmd_b200_md* md, int enabled);
 /* ---- x-slab decomposition over the GPUs of one node ---------------------------------------------
  * New functionality (the reference's communication layer is single-process periodic self-ghosting,
  * communication/MultiResRealAtomsExchange.hpp:26): one process per GPU, rank r owns the slab
@@ -503,6 +513,13 @@ int mrmd_b200_slab_destroy(mrmd_b200_slab* sl);
  * a slab face counts one half on either side), the other fields are per rank */
 int mrmd_b200_slab_run(mrmd_b200_slab* sl, int64_t nsteps, int timeForceKernel, mrmd_b200_md_stats* stats,
                        void* stream);
+int mrmd_b200_slab_set_energy_every_step(mrmd_b200_slab* sl, int enabled);
+/* mrmd_b200_md_run_host on a slab (collective): every step copies this rank's pos and vel (numLocal x 3 doubles each,
+ * in the rank's current atom order) from the host buffers, runs one step and copies pos, vel and scalarsHost =
+ * {this rank's energy, virial, maxDisplacement, numLocal after the step} back.  The buffers must hold the largest
+ * number of resident atoms (atoms migrate at a rebuild); stats: steps, rebuilds, storedPairs, numLocal, numGhost. */
+int mrmd_b200_slab_run_host(mrmd_b200_slab* sl, int64_t nsteps, double* posHost, double* velHost, double* scalarsHost,
+                            mrmd_b200_md_stats* stats, void* stream);
 
 /* pinned host memory for the host-buffer path */
 int mrmd_b200_host_alloc(void** ptr, int64_t bytes);

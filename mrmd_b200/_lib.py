@@ -8,6 +8,9 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmrmd_b200.so")
+# measurement only (profiles/variants.py): a side-by-side build of the same sources with other tuning constants
+if os.environ.get("MRMD_B200_LIB_VARIANT"):
+    LIB_PATH = os.path.join(_HERE, "variants", f"libmrmd_b200_{os.environ['MRMD_B200_LIB_VARIANT']}.so")
 
 
 class Subdomain(C.Structure):
@@ -35,7 +38,8 @@ class MdConfig(C.Structure):
                 ("thermoBinWidth", C.c_double), ("thermoModulation", C.c_double),
                 ("thermoSampleInterval", C.c_int64), ("thermoUpdateInterval", C.c_int64),
                 ("thermoSmoothingSigma", C.c_double), ("thermoSmoothingIntensity", C.c_double),
-                ("atomsPerMolecule", C.c_int64), ("numConstraintIterations", C.c_int64), ("bondLength", C.c_double)]
+                ("atomsPerMolecule", C.c_int64), ("numConstraintIterations", C.c_int64), ("bondLength", C.c_double),
+                ("energyEveryStep", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class MdStats(C.Structure):
@@ -163,6 +167,9 @@ SIGNATURES = {
     "mrmd_b200_md_destroy": (C.c_int, [vp]),
     "mrmd_b200_md_run": (C.c_int, [vp, i64, C.c_int, C.POINTER(MdStats), vp]),
     "mrmd_b200_md_run_host": (C.c_int, [vp, i64, vp, vp, vp, C.POINTER(MdStats), vp]),
+    "mrmd_b200_md_set_energy_every_step": (C.c_int, [vp, C.c_int]),
+    "mrmd_b200_slab_set_energy_every_step": (C.c_int, [vp, C.c_int]),
+    "mrmd_b200_slab_run_host": (C.c_int, [vp, i64, vp, vp, vp, C.POINTER(MdStats), vp]),
     "mrmd_b200_nccl_unique_id": (C.c_int, [vp]),
     "mrmd_b200_slab_create": (C.c_int, [pvp, C.POINTER(MdConfig), vp, vp, C.c_int, C.c_int, vp, vp, vp]),
     "mrmd_b200_slab_create_cuts": (C.c_int, [pvp, C.POINTER(MdConfig), vp, vp, vp, C.c_int, C.c_int, vp, vp, vp]),

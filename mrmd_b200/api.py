@@ -18,7 +18,7 @@ from ._lib import Pred, Weight, check
 HOST, DEVICE = 0, 1
 ATOM_FIELDS = {"pos": (0, 3, np.float64), "vel": (1, 3, np.float64), "force": (2, 3, np.float64),
                "type": (3, 1, np.int64), "mass": (4, 1, np.float64), "charge": (5, 1, np.float64),
-               "relativeMass": (6, 1, np.float64)}
+               "relativeMass": (6, 1, np.float64), "id": (7, 1, np.int64)}
 MOL_FIELDS = {"pos": (0, 3, np.float64), "force": (1, 3, np.float64), "lambda": (2, 1, np.float64),
               "modulatedLambda": (3, 1, np.float64), "gradLambda": (4, 3, np.float64),
               "atomsOffset": (5, 1, np.int64), "numAtoms": (6, 1, np.int64)}
@@ -168,6 +168,9 @@ class Atoms(_Container):
     def getMass(self):
         return self.get("mass")
 
+    def getId(self):
+        return self.get("id")
+
     def setForce(self, value, stream=None):
         """Atoms::setForce / Cabana::deep_copy(force, value)"""
         self.fill("force", value, stream)
@@ -184,7 +187,7 @@ class Atoms(_Container):
                                             lc.gmax.ctypes.data, None, _stream(stream)))
 
     @classmethod
-    def from_arrays(cls, pos, vel=None, mass=1.0, type=None, relativeMass=None, capacity=None):
+    def from_arrays(cls, pos, vel=None, mass=1.0, type=None, relativeMass=None, capacity=None, ids=None):
         n = len(pos)
         a = cls(capacity or n)
         a.resize(n)
@@ -196,6 +199,8 @@ class Atoms(_Container):
             a.set("type", type)
         if relativeMass is not None:
             a.set("relativeMass", np.broadcast_to(np.asarray(relativeMass, dtype=np.float64), (n,)))
+        if ids is not None:  # global atom ids (default: the index), the Philox counter of the Langevin thermostat
+            a.set("id", ids)
         a.numLocalAtoms = n
         return a
 
@@ -855,18 +860,25 @@ class MolecularDynamics:
         check(L().mrmd_b200_md_run(self.h, nsteps, int(timeForceKernel), C.byref(st), _stream(stream)))
         return {f: getattr(st, f) for f, _ in st._fields_}
 
+    def setEnergyEveryStep(self, enabled):
+        """reduce energy and virial on every step (LennardJones.hpp:187-188) instead of on a run's last step only"""
+        check(L().mrmd_b200_md_set_energy_every_step(self.h, int(enabled)))
+
     def run_host(self, nsteps, posHostPtr, velHostPtr, scalarsHostPtr=None, stream=None):
         st = _lib.MdStats()
         check(L().mrmd_b200_md_run_host(self.h, nsteps, posHostPtr, velHostPtr, scalarsHostPtr, C.byref(st), _stream(stream)))
         return {f: getattr(st, f) for f, _ in st._fields_}
 
-    def __del__(self):
+    def close(self):
         h, self.h = getattr(self, "h", None), None
         if h:
-            try:
-                L().mrmd_b200_md_destroy(h)
-            except Exception:
-                pass
+            L().mrmd_b200_md_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class PinnedBuffer:

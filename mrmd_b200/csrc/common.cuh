@@ -5,6 +5,7 @@
 //   atoms      pos4[cap]   32-byte records {x, y, z, type-as-int64-bits}: one 256-bit load per gather
 //              vel, force  three planes each (x[cap], y[cap], z[cap]), streamed coalesced
 //              mass, charge, relMass   one plane each
+//              gid         int64 plane: global atom id, travels with the record (permute, ghost copy, migration)
 //   molecules  pos4[cap]   {X, Y, Z, unused}
 //              w4[cap]     {lambda^mod, dlambda/dx, dlambda/dy, dlambda/dz}: everything the AdResS pair
 //                          loop needs about the partner molecule in one 256-bit gather
@@ -109,6 +110,7 @@ struct AtomsView
     double* mass;
     double* charge;
     double* relMass;
+    long long* gid;  // global atom id: the Philox counter of the Langevin integrator (initialised to the index)
 };
 
 struct MolsView
@@ -192,6 +194,11 @@ struct mrmd_b200_atoms
     int64_t lcBegin = 0, lcEnd = 0;
     int64_t lcNumCells = 0;
     int64_t lcEpoch = 0;
+    // every operator that writes local positions bumps posEpoch; a cell sort records it.  The index ranges of the
+    // sort stay usable while the atoms keep their order (lcValid), but a NEW tiled list may only be built from them
+    // while the positions are the sorted ones (lcPosEpoch == posEpoch): drifted atoms sit in the wrong cells.
+    int64_t posEpoch = 0;
+    int64_t lcPosEpoch = -1;
     mrmd_b200::DevBuf lcCellStart;  // int32[numCells + 1]
 };
 
@@ -233,6 +240,9 @@ struct mrmd_b200_verlet
     mrmd_b200_weight tiledCgWeight{};
     int tiledCH = 0;
     int tiledSlots = 0;
+    int tiledGridN[3] = {0, 0, 0};  // grid the tile geometry (CH, slots) was chosen for: re-used while it stays the same
+    mrmd_b200::DevBuf tstats;    // int32[4]: max slots per tile, -, overflow flag
+    int* hTstats = nullptr;      // pinned
     mrmd_b200::DevBuf keys[2];  // radix sort ping-pong
     mrmd_b200::DevBuf vals[2];
     mrmd_b200::DevBuf scratch;

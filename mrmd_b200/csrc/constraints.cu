@@ -413,6 +413,7 @@ int mrmd_b200_berendsen_barostat(mrmd_b200_atoms* a, double currentPressure, dou
 {
     MB_TRY(checkDevice());
     MB_REQUIRE(a != nullptr && s != nullptr, "berendsen_barostat");
+    a->posEpoch += 1;
     const double mu = std::cbrt(1.0 + gamma * (currentPressure - targetPressure));
     if (stretchX) mrmd_b200_subdomain_scale_dim(s, mu, 0);
     if (stretchY) mrmd_b200_subdomain_scale_dim(s, mu, 1);

@@ -32,7 +32,7 @@ int checkDevice()
 // slab carving: one allocation per view, planes 256-byte aligned
 static size_t alignUp(size_t v) { return (v + 255) & ~size_t(255); }
 
-static size_t atomsSlabBytes(int64_t cap) { return alignUp(size_t(cap) * 32) + 9 * alignUp(size_t(cap) * 8); }
+static size_t atomsSlabBytes(int64_t cap) { return alignUp(size_t(cap) * 32) + 10 * alignUp(size_t(cap) * 8); }
 static void carveAtoms(void* slab, int64_t cap, AtomsView& v)
 {
     char* p = static_cast<char*>(slab);
@@ -45,6 +45,7 @@ static void carveAtoms(void* slab, int64_t cap, AtomsView& v)
         *pl = reinterpret_cast<double*>(p);
         p += alignUp(size_t(cap) * 8);
     }
+    v.gid = reinterpret_cast<long long*>(p);
 }
 static size_t molsSlabBytes(int64_t cap)
 {
@@ -76,7 +77,15 @@ static int copyAtomsView(const AtomsView& dst, const AtomsView& src, int64_t n, 
     double* d[9] = {dst.vel[0], dst.vel[1], dst.vel[2], dst.force[0], dst.force[1], dst.force[2], dst.mass,
                     dst.charge, dst.relMass};
     for (int i = 0; i < 9; ++i) MB_CUDA(cudaMemcpyAsync(d[i], s[i], size_t(n) * 8, cudaMemcpyDeviceToDevice, st));
+    MB_CUDA(cudaMemcpyAsync(dst.gid, src.gid, size_t(n) * 8, cudaMemcpyDeviceToDevice, st));
     return 0;
+}
+
+// a fresh container numbers its atoms 0, 1, ...: the default global id is the index
+__global__ void iotaIdKernel(long long* gid, int64_t first, int64_t n)
+{
+    const int64_t i = first + blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (i < n) gid[i] = i;
 }
 static int copyMolsView(const MolsView& dst, const MolsView& src, int64_t n, cudaStream_t st)
 {
@@ -101,6 +110,11 @@ int atomsEnsureCapacity(mrmd_b200_atoms* a, int64_t capacity, cudaStream_t st)
     AtomsView nv;
     carveAtoms(slab, cap, nv);
     MB_TRY(copyAtomsView(nv, a->v, a->size, st));
+    if (cap > a->size)
+    {
+        iotaIdKernel<<<gridFor(cap - a->size, 256), 256, 0, st>>>(nv.gid, a->size, cap);
+        MB_LAUNCHED();
+    }
     if (a->v.pos != nullptr)
     {
         MB_CUDA(cudaStreamSynchronize(st));
@@ -124,6 +138,8 @@ int atomsEnsureAlt(mrmd_b200_atoms* a, cudaStream_t st)
     MB_CUDA(cudaMalloc(&slab, atomsSlabBytes(a->capacity)));
     MB_CUDA(cudaMemsetAsync(slab, 0, atomsSlabBytes(a->capacity), st));
     carveAtoms(slab, a->capacity, a->alt);
+    iotaIdKernel<<<gridFor(a->capacity, 256), 256, 0, st>>>(a->alt.gid, 0, a->capacity);
+    MB_LAUNCHED();
     a->altCapacity = a->capacity;
     return 0;
 }
@@ -209,6 +225,13 @@ __global__ void atomFieldKernel(AtomsView v, int field, double* buf, int64_t fir
                 if (WRITE) pl[d][i] = buf[sliceIndex(j, d, stride, vlen)];
                 else buf[sliceIndex(j, d, stride, vlen)] = pl[d][i];
             }
+            break;
+        }
+        case MRMD_B200_ATOM_ID:
+        {
+            double* p = reinterpret_cast<double*>(v.gid + i);  // raw 64-bit copy of the int64
+            if (WRITE) *p = buf[sliceIndex(j, 0, stride, vlen)];
+            else buf[sliceIndex(j, 0, stride, vlen)] = *p;
             break;
         }
         default:
@@ -322,7 +345,7 @@ static int transfer(Handle* h, bool isAtoms, int field, void* buf, int64_t first
 {
     MB_TRY(checkDevice());
     MB_REQUIRE(h != nullptr, "null handle");
-    MB_REQUIRE(field >= 0 && field <= 6, "unknown field");
+    MB_REQUIRE(field >= 0 && field <= (isAtoms ? 7 : 6), "unknown field");
     MB_REQUIRE(first >= 0 && count >= 0 && first + count <= h->size, "range outside the container");
     MB_REQUIRE(vlen >= 1, "vector length must be >= 1");
     if (count == 0) return 0;
@@ -360,6 +383,7 @@ int atomsFieldToDense(const mrmd_b200_atoms* a, int field, double* devBuf, int64
 }
 int atomsFieldFromDense(mrmd_b200_atoms* a, int field, const double* devBuf, int64_t n, cudaStream_t st)
 {
+    if (field == MRMD_B200_ATOM_POS) a->posEpoch += 1;
     if (n <= 0) return 0;
     atomFieldKernel<true><<<gridFor(n, 256), 256, 0, st>>>(a->v, field, const_cast<double*>(devBuf), 0, n,
                                                           ncompOf(true, field), 1);
@@ -511,6 +535,7 @@ int mrmd_b200_atoms_write(mrmd_b200_atoms* a, int field, const void* src, int64_
                           int64_t stride, int64_t vlen, int memKind, void* stream)
 {
     cudaStream_t st = S(stream);
+    if (a != nullptr && field == MRMD_B200_ATOM_POS) a->posEpoch += 1;
     return transfer(a, true, field, const_cast<void*>(src), first, count, stride, vlen, memKind, true, st,
                     [&](double* dbuf) {
                         atomFieldKernel<true><<<gridFor(count, 256), 256, 0, st>>>(a->v, field, dbuf, first, count,
@@ -553,6 +578,7 @@ int mrmd_b200_atoms_fill(mrmd_b200_atoms* a, int field, double value, void* stre
     switch (field)
     {
         case MRMD_B200_ATOM_POS:
+            a->posEpoch += 1;
             fillPos4Kernel<<<g, 256, 0, st>>>(a->v.pos, n, value, 0, 2);
             MB_LAUNCHED();
             break;
@@ -589,6 +615,8 @@ int mrmd_b200_atoms_copy(mrmd_b200_atoms* dst, const mrmd_b200_atoms* src, void*
     dst->size = src->size;
     dst->numLocal = src->numLocal;
     dst->numGhost = src->numGhost;
+    dst->posEpoch += 1;
+    dst->lcValid = false;
     return copyAtomsView(dst->v, src->v, src->size, S(stream));
 }
 

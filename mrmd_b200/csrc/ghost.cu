@@ -162,6 +162,7 @@ __device__ __forceinline__ void copyAtomRecord(const AtomsView& a, int64_t dst, 
     a.mass[dst] = a.mass[src];
     a.charge[dst] = a.charge[src];
     a.relMass[dst] = a.relMass[src];
+    a.gid[dst] = a.gid[src];
 }
 
 __device__ __forceinline__ int64_t rootOf(const int64_t* corr, int64_t realIdx)
@@ -482,6 +483,7 @@ int mrmd_b200_ghost_map_into_domain(mrmd_b200_atoms* a, const mrmd_b200_subdomai
 {
     MB_TRY(checkDevice());
     MB_REQUIRE(a != nullptr && s != nullptr, "ghost_map_into_domain");
+    a->posEpoch += 1;
     if (a->numLocal == 0) return 0;
     mapIntoDomainKernel<<<gridFor(a->numLocal, 256), 256, 0, S(stream)>>>(a->v.pos, a->numLocal, toDev(*s));
     MB_LAUNCHED();
@@ -566,6 +568,7 @@ int mrmd_b200_ghost_mr_map_into_domain(mrmd_b200_molecules* m, mrmd_b200_atoms* 
 {
     MB_TRY(checkDevice());
     MB_REQUIRE(m != nullptr && a != nullptr && s != nullptr, "ghost_mr_map_into_domain");
+    a->posEpoch += 1;
     if (m->numLocal == 0) return 0;
     mrMapIntoDomainKernel<<<gridFor(m->numLocal, 256), 256, 0, S(stream)>>>(m->v, a->v, m->numLocal, toDev(*s));
     MB_LAUNCHED();

@@ -33,7 +33,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     out[3] = c3;
 }
 
-// three standard normals for (seed, step, idx): 32-bit uniforms, Box-Muller
+// three standard normals for (seed, step, global atom id): 32-bit uniforms, Box-Muller
 __device__ __forceinline__ void philoxNormals3(uint64_t seed, uint64_t step, uint64_t idx, double& n0, double& n1,
                                                double& n2)
 {
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256)
             if (pred1(pred, p.x, p.y, p.z))
             {
                 double r0, r1, r2;
-                philoxNormals3(seed, step, uint64_t(idx), r0, r1, r2);
+                philoxNormals3(seed, step, uint64_t(a.gid[idx]), r0, r1, r2);
                 const double dtm = dt / m;  // updateOrnsteinUhlenbeck, UpdateSteps.hpp:68-78
                 const double damping = exp(-zeta * dtm);
                 const double sigma = sqrt(temperature / m * (1.0 - exp(-2.0 * zeta * dtm)));
@@ -137,6 +137,8 @@ __global__ void __launch_bounds__(256)
         a.vel[2][idx] = vz;
         const double dx = ox - p.x, dy = oy - p.y, dz = oz - p.z;
         distSqr = dx * dx + dy * dy + dz * dz;
+        // a NaN force or position must not vanish in the maximum: report it as an infinite displacement
+        if (!(distSqr == distSqr)) distSqr = __longlong_as_double(0x7ff0000000000000LL);
     }
     blockMaxToGlobal(distSqr, dMax);
 }
@@ -165,6 +167,7 @@ int integratePre(mrmd_b200_atoms* a, double dt, bool langevin, double zeta, doub
                  uint64_t step, const mrmd_b200_pred* pred, bool fusedPost, cudaStream_t st)
 {
     MB_CUDA(cudaMemsetAsync(a->dMaxDisp, 0, 8, st));
+    a->posEpoch += 1;
     if (a->numLocal == 0) return 0;
     mrmd_b200_pred p{};
     if (pred != nullptr) p = *pred;

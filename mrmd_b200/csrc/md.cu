@@ -5,10 +5,12 @@
 // unit-test usage of the operators.
 #include <algorithm>
 #include <cfloat>
+#include <cmath>
 #include <cstdlib>
 #include <vector>
 
 #include "handles.cuh"
+#include "hostpipe.cuh"
 
 struct mrmd_b200_md
 {
@@ -29,13 +31,7 @@ struct mrmd_b200_md
     double active0 = 0.0;  // running active-pair count when the current run started
     bool postPending = false;  // the last step's postForceIntegrate is fused into the next preForceIntegrate
     std::vector<cudaEvent_t> events;
-    // host-buffer path (mrmd_b200_md_run_host): copy streams, staging buffers and the events that order them
-    cudaStream_t sIn = nullptr, sOut = nullptr;
-    cudaEvent_t evUpPos = nullptr, evUpVel = nullptr, evPosReady = nullptr, evStepDone = nullptr;
-    static constexpr int HB_CHUNKS = 8;  // the PCIe copies move in up to 8 chunks so that upload i+1 trails download i
-    cudaEvent_t evDownPos[HB_CHUNKS] = {}, evDownVel[HB_CHUNKS] = {};
-    bool recordPosReady = false;  // oneStep records evPosReady once the positions (and the atom order) are final
-    mrmd_b200::DevBuf posIn, velIn, posOut, velOut;
+    mrmd_b200::HostPipe hp;  // host-buffer path (mrmd_b200_md_run_host)
 };
 
 namespace mrmd_b200
@@ -93,7 +89,7 @@ static int rebuild(mrmd_b200_md* md, cudaStream_t st)
         MB_TRY(mrmd_b200_ghost_map_into_domain(a, &md->sub, st));  // ghostLayer.exchangeRealAtoms (examples/02:150)
         a->numGhost = 0;
         a->size = a->numLocal;
-        if (c.cellSort)  // tests/NVT/NVT.cpp:136-144
+        if (c.cellSort || c.fullList == 2)  // tests/NVT/NVT.cpp:136-144; the tiled list is built from the fresh sort
             MB_TRY(mrmd_b200_atoms_cell_sort(a, 0, a->numLocal, delta, md->sub.minCorner, md->sub.maxCorner, nullptr, st));
         if (c.fullList == 2)
         {
@@ -137,7 +133,7 @@ static int postIntegrate(mrmd_b200_md* md, bool deferPost, cudaStream_t st)
 
 // deferPost: leave postForceIntegrate to the next step's fused kernel (the caller flushes it when the run ends)
 static int oneStep(mrmd_b200_md* md, cudaStream_t st, cudaEvent_t evStart, cudaEvent_t evStop, bool deferPost,
-                   bool wantEnergy)
+                   bool wantEnergy, cudaEvent_t evPosReady = nullptr)
 {
     const mrmd_b200_md_config& c = md->cfg;
     mrmd_b200_atoms* a = md->atoms;
@@ -148,6 +144,7 @@ static int oneStep(mrmd_b200_md* md, cudaStream_t st, cudaEvent_t evStart, cudaE
     md->postPending = false;
     MB_CUDA(cudaMemcpyAsync(a->hMaxDisp, a->dMaxDisp, 8, cudaMemcpyDeviceToHost, st));
     MB_CUDA(cudaStreamSynchronize(st));
+    MB_REQUIRE(std::isfinite(*a->hMaxDisp), "md_run: non-finite position, velocity or force (the system blew up)");
     md->maxDisplacement += std::sqrt(*a->hMaxDisp);  // examples/02:138, VelocityVerlet.cpp:66
     if (md->maxDisplacement >= c.skin * 0.5)  // :141-143
     {
@@ -159,7 +156,7 @@ static int oneStep(mrmd_b200_md* md, cudaStream_t st, cudaEvent_t evStart, cudaE
         MB_TRY(mrmd_b200_ghost_update(md->ghost, a, &md->sub, st));  // :170
         if (c.adress) MB_TRY(mrmd_b200_molecules_update(md->mols, a, &c.weight, st));
     }
-    if (md->recordPosReady) MB_CUDA(cudaEventRecord(md->evPosReady, st));
+    if (evPosReady != nullptr) MB_CUDA(cudaEventRecord(evPosReady, st));  // positions and atom order are final
     if (c.fullList == 2 && c.adress)
     {
         // tiled AdResS step: thermodynamic force on the zeroed force, then UpdateMolecules + LJ_IdealGas +
@@ -359,14 +356,7 @@ int mrmd_b200_md_destroy(mrmd_b200_md* md)
     if (md == nullptr) return 0;
     cudaDeviceSynchronize();
     for (auto e : md->events) cudaEventDestroy(e);
-    for (cudaEvent_t e : {md->evUpPos, md->evUpVel, md->evPosReady, md->evStepDone})
-        if (e != nullptr) cudaEventDestroy(e);
-    for (int c = 0; c < mrmd_b200_md::HB_CHUNKS; ++c)
-        for (cudaEvent_t e : {md->evDownPos[c], md->evDownVel[c]})
-            if (e != nullptr) cudaEventDestroy(e);
-    if (md->sIn != nullptr) cudaStreamDestroy(md->sIn);
-    if (md->sOut != nullptr) cudaStreamDestroy(md->sOut);
-    for (mrmd_b200::DevBuf* b : {&md->posIn, &md->velIn, &md->posOut, &md->velOut}) b->release();
+    md->hp.destroy();
     mrmd_b200_ghost_destroy(md->ghost);
     mrmd_b200_verlet_destroy(md->list);
     mrmd_b200_lj_destroy(md->lj);
@@ -398,7 +388,7 @@ int mrmd_b200_md_run(mrmd_b200_md* md, int64_t nsteps, int timeForceKernel, mrmd
     {
         cudaEvent_t e0 = (i < nTimed) ? md->events[2 * i] : nullptr;
         cudaEvent_t e1 = (i < nTimed) ? md->events[2 * i + 1] : nullptr;
-        MB_TRY(oneStep(md, st, e0, e1, true, i == nsteps - 1));
+        MB_TRY(oneStep(md, st, e0, e1, true, i == nsteps - 1 || md->cfg.energyEveryStep != 0));
         storedSum += md->storedPairsNow;
     }
     if (md->postPending)
@@ -409,97 +399,34 @@ int mrmd_b200_md_run(mrmd_b200_md* md, int64_t nsteps, int timeForceKernel, mrmd
     return collectStats(md, nsteps, rebuilds0, storedSum, pairs0, nTimed, stats, st);
 }
 
-// Host-buffer path.  Per step: pos and vel come from the host buffers, one step runs, pos, vel and the scalars go
-// back.  PCIe is full duplex and the positions are final before the force kernel starts, so the copies run on two
-// extra streams and in HB_CHUNKS pieces: the download of the positions overlaps the force kernel, and chunk c of the
-// next step's upload starts as soon as chunk c of this step's download has landed, so both directions of the link
-// stay busy.  Every byte of a host buffer is read only after the previous step's write to it.
+// Host-buffer path (hostpipe.cuh): per step pos and vel come from the host buffers, one step runs, pos, vel and
+// {energy, virial, maxDisplacement} go back, copies chunked on two extra streams so that both PCIe directions stay busy.
 int mrmd_b200_md_run_host(mrmd_b200_md* md, int64_t nsteps, double* posHost, double* velHost, double* scalarsHost,
                           mrmd_b200_md_stats* stats, void* stream)
 {
     MB_TRY(checkDevice());
     MB_REQUIRE(md != nullptr && nsteps >= 0 && posHost != nullptr && velHost != nullptr, "md_run_host");
     cudaStream_t st = S(stream);
-    mrmd_b200_atoms* a = md->atoms;
     const int64_t rebuilds0 = md->rebuilds;
     double pairs0 = 0.0;
     MB_TRY(runningPairs(md, &pairs0, st));
     int64_t storedSum = 0;
-    const int64_t n = a->numLocal;
-    const size_t bytes = size_t(n) * 24;
-    if (md->sIn == nullptr)
-    {
-        // highest priority: the pack kernel in front of a download must not queue behind the blocks of the force
-        // kernel it is meant to overlap
-        int prioLow = 0, prioHigh = 0;
-        MB_CUDA(cudaDeviceGetStreamPriorityRange(&prioLow, &prioHigh));
-        MB_CUDA(cudaStreamCreateWithPriority(&md->sIn, cudaStreamNonBlocking, prioHigh));
-        MB_CUDA(cudaStreamCreateWithPriority(&md->sOut, cudaStreamNonBlocking, prioHigh));
-        for (cudaEvent_t* e : {&md->evUpPos, &md->evUpVel, &md->evPosReady, &md->evStepDone})
-            MB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
-        for (int c = 0; c < mrmd_b200_md::HB_CHUNKS; ++c)
-            for (cudaEvent_t* e : {&md->evDownPos[c], &md->evDownVel[c]})
-                MB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
-    }
-    // chunks per array and direction (MRMD_B200_HB_CHUNKS overrides the default of 4 for measurements)
-    int K = 4;
-    if (const char* e = std::getenv("MRMD_B200_HB_CHUNKS")) K = std::max(1, std::min(int(mrmd_b200_md::HB_CHUNKS), std::atoi(e)));
-    size_t off[mrmd_b200_md::HB_CHUNKS + 1];
-    for (int c = 0; c <= K; ++c) off[c] = (c == K) ? bytes : ((bytes * size_t(c) / K) & ~size_t(255));
-    // one direction of one array: chunk c waits for gate[c] (if any) and records done[c] (if any)
-    auto copyChunks = [&](void* dst, const void* src, cudaMemcpyKind kind, cudaStream_t cs, cudaEvent_t* gate,
-                          cudaEvent_t* done) -> int
-    {
-        for (int c = 0; c < K; ++c)
-        {
-            if (off[c + 1] == off[c]) continue;
-            if (gate != nullptr) MB_CUDA(cudaStreamWaitEvent(cs, gate[c], 0));
-            MB_CUDA(cudaMemcpyAsync(static_cast<char*>(dst) + off[c], static_cast<const char*>(src) + off[c], off[c + 1] - off[c],
-                                    kind, cs));
-            if (done != nullptr) MB_CUDA(cudaEventRecord(done[c], cs));
-        }
-        return 0;
-    };
-    for (mrmd_b200::DevBuf* b : {&md->posIn, &md->velIn, &md->posOut, &md->velOut}) MB_TRY(b->reserve(std::max<size_t>(bytes, 8)));
-    double* dRes = md->cfg.adress ? md->adress->dResult : md->lj->dResult;
-    md->recordPosReady = true;
-    int rc = 0;
-    auto step = [&](int64_t i) -> int
-    {
-        // host -> device: this step's inputs (the host buffers were last written by the previous step's download)
-        MB_TRY(copyChunks(md->posIn.p, posHost, cudaMemcpyHostToDevice, md->sIn, i > 0 ? md->evDownPos : nullptr, nullptr));
-        MB_CUDA(cudaEventRecord(md->evUpPos, md->sIn));
-        MB_TRY(copyChunks(md->velIn.p, velHost, cudaMemcpyHostToDevice, md->sIn, i > 0 ? md->evDownVel : nullptr, nullptr));
-        MB_CUDA(cudaEventRecord(md->evUpVel, md->sIn));
-        MB_CUDA(cudaStreamWaitEvent(st, md->evUpPos, 0));
-        MB_TRY(atomsFieldFromDense(a, MRMD_B200_ATOM_POS, md->posIn.as<double>(), n, st));
-        MB_CUDA(cudaStreamWaitEvent(st, md->evUpVel, 0));
-        MB_TRY(atomsFieldFromDense(a, MRMD_B200_ATOM_VEL, md->velIn.as<double>(), n, st));
-        MB_TRY(oneStep(md, st, nullptr, nullptr, false, true));  // records evPosReady in front of the force kernel
-        storedSum += md->storedPairsNow;
-        // device -> host: positions while the force kernel runs ...
-        MB_CUDA(cudaStreamWaitEvent(md->sOut, md->evPosReady, 0));
-        MB_TRY(atomsFieldToDense(a, MRMD_B200_ATOM_POS, md->posOut.as<double>(), n, md->sOut));
-        MB_TRY(copyChunks(posHost, md->posOut.p, cudaMemcpyDeviceToHost, md->sOut, nullptr, md->evDownPos));
-        // ... velocities and scalars after postForceIntegrate
-        MB_CUDA(cudaEventRecord(md->evStepDone, st));
-        MB_CUDA(cudaStreamWaitEvent(md->sOut, md->evStepDone, 0));
-        MB_TRY(atomsFieldToDense(a, MRMD_B200_ATOM_VEL, md->velOut.as<double>(), n, md->sOut));
-        MB_TRY(copyChunks(velHost, md->velOut.p, cudaMemcpyDeviceToHost, md->sOut, nullptr, md->evDownVel));
-        if (scalarsHost != nullptr)
-        {
-            MB_CUDA(cudaMemcpyAsync(scalarsHost, dRes, 16, cudaMemcpyDeviceToHost, md->sOut));
-            scalarsHost[2] = md->maxDisplacement;
-        }
-        return 0;
-    };
-    for (int64_t i = 0; i < nsteps && rc == 0; ++i) rc = step(i);
-    md->recordPosReady = false;
-    const cudaError_t e1 = cudaStreamSynchronize(md->sOut), e2 = cudaStreamSynchronize(md->sIn);
-    if (rc != 0) return rc;
-    MB_CUDA(e1);
-    MB_CUDA(e2);
+    const double* dRes = md->cfg.adress ? md->adress->dResult : md->lj->dResult;
+    MB_TRY(hostPipeRun(md->hp, md->atoms, nsteps, posHost, velHost, scalarsHost, dRes, &md->maxDisplacement, false, st,
+                       [&](cudaEvent_t evPosReady) -> int
+                       {
+                           MB_TRY(oneStep(md, st, nullptr, nullptr, false, true, evPosReady));
+                           storedSum += md->storedPairsNow;
+                           return 0;
+                       }));
     return collectStats(md, nsteps, rebuilds0, storedSum, pairs0, 0, stats, st);
+}
+
+int mrmd_b200_md_set_energy_every_step(mrmd_b200_md* md, int enabled)
+{
+    MB_REQUIRE(md != nullptr, "md_set_energy_every_step");
+    md->cfg.energyEveryStep = enabled ? 1 : 0;
+    return 0;
 }
 
 int mrmd_b200_host_alloc(void** ptr, int64_t bytes)

@@ -255,6 +255,7 @@ __global__ void permuteAtomsKernel(AtomsView dst, AtomsView src, const uint32_t*
     dst.mass[i] = src.mass[s];
     dst.charge[i] = src.charge[s];
     dst.relMass[i] = src.relMass[s];
+    dst.gid[i] = src.gid[s];
 }
 
 __global__ void permuteMolsKernel(MolsView dst, MolsView src, const uint32_t* perm, int64_t begin, int64_t end,
@@ -538,6 +539,7 @@ static int atomsCellSortImpl(mrmd_b200_atoms* a, int64_t begin, int64_t end, con
     a->lcEnd = end;
     a->lcNumCells = numCells;
     a->lcEpoch += 1;
+    a->lcPosEpoch = a->posEpoch;
     return 0;
 }
 }  // namespace mrmd_b200
@@ -603,7 +605,9 @@ int mrmd_b200_verlet_destroy(mrmd_b200_verlet* v)
     v->cellStart.release();
     v->sortedPos.release();
     v->stats.release();
+    v->tstats.release();
     if (v->hStats) cudaFreeHost(v->hStats);
+    if (v->hTstats) cudaFreeHost(v->hTstats);
     delete v;
     return 0;
 }

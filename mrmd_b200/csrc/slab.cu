@@ -25,9 +25,11 @@
 #include <cstdlib>
 #include <ctime>
 #include <cfloat>
+#include <cmath>
 #include <vector>
 
 #include "handles.cuh"
+#include "hostpipe.cuh"
 
 namespace mrmd_b200
 {
@@ -92,7 +94,7 @@ static int loadNccl()
     } while (0)
 
 constexpr int SL_THREADS = 256;
-constexpr int SL_RECORD = 13;  // doubles per migrating atom: pos3, type bits, vel3, force3, mass, charge, relMass
+constexpr int SL_RECORD = 14;  // doubles per migrating atom: pos3, type bits, vel3, force3, mass, charge, relMass, id bits
 
 // y / z periodic wrap (PeriodicMapping.cpp:36-51 arithmetic) and the x migration flag: -1 left, +1 right, 0 stays
 __global__ void slabWrapFlagKernel(double4* pos, int64_t n, SubdomainDev s, signed char* flag)
@@ -263,6 +265,7 @@ __global__ void packRecordsKernel(AtomsView a, const int32_t* idx, int64_t n, do
     r[10] = a.mass[i];
     r[11] = a.charge[i];
     r[12] = a.relMass[i];
+    r[13] = __longlong_as_double(a.gid[i]);
 }
 
 __global__ void unpackRecordsKernel(AtomsView a, int64_t first, int64_t n, const double* buf, signed char* flag)
@@ -280,6 +283,7 @@ __global__ void unpackRecordsKernel(AtomsView a, int64_t first, int64_t n, const
     a.mass[i] = r[10];
     a.charge[i] = r[11];
     a.relMass[i] = r[12];
+    a.gid[i] = __double_as_longlong(r[13]);
     flag[i] = 0;
 }
 
@@ -455,6 +459,7 @@ struct mrmd_b200_slab
     double* dScalars = nullptr;  // allreduce scratch
     double* hScalars = nullptr;  // pinned
     std::vector<cudaEvent_t> events;
+    mrmd_b200::HostPipe hp;  // host-buffer path (mrmd_b200_slab_run_host)
 };
 
 namespace mrmd_b200
@@ -780,14 +785,15 @@ static double profMark(mrmd_b200_slab* sl, cudaStream_t st, double& last)
     return d;
 }
 
-static int slabStep(mrmd_b200_slab* sl, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, bool wantEnergy)
+static int slabStep(mrmd_b200_slab* sl, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, bool wantEnergy,
+                    bool deferPost = true, cudaEvent_t evPosReady = nullptr)
 {
     const mrmd_b200_md_config& c = sl->cfg;
     mrmd_b200_atoms* a = sl->atoms;
     double last = 0.0;
     profMark(sl, st, last);
     // the previous step's postForceIntegrate rides in front of this kick (flushed when a run returns)
-    MB_TRY(integratePre(a, c.dt, c.integrator == 1, c.zeta, c.temperature, c.seed + uint64_t(sl->rank),
+    MB_TRY(integratePre(a, c.dt, c.integrator == 1, c.zeta, c.temperature, c.seed,
                         uint64_t(sl->step), nullptr, sl->postPending, st));
     sl->postPending = false;
     sl->prof[0] += profMark(sl, st, last);
@@ -818,6 +824,7 @@ static int slabStep(mrmd_b200_slab* sl, cudaStream_t st, cudaEvent_t e0, cudaEve
         MB_CUDA(cudaMemcpyAsync(a->hMaxDisp, a->dMaxDisp, 8, cudaMemcpyDeviceToHost, st));
         MB_CUDA(cudaStreamSynchronize(st));
     }
+    MB_REQUIRE(std::isfinite(*a->hMaxDisp), "slab_run: non-finite position, velocity or force (the system blew up)");
     sl->maxDisplacement += std::sqrt(*a->hMaxDisp);
     sl->prof[1] += profMark(sl, st, last);
     if (sl->maxDisplacement >= c.skin * 0.5)
@@ -831,6 +838,7 @@ static int slabStep(mrmd_b200_slab* sl, cudaStream_t st, cudaEvent_t e0, cudaEve
         MB_TRY(haloRefresh(sl, st));
         sl->prof[3] += profMark(sl, st, last);
     }
+    if (evPosReady != nullptr) MB_CUDA(cudaEventRecord(evPosReady, st));  // positions and atom order are final
     if (c.adress)
     {
         // SURVEY.md section 3.5 on a slab: thermodynamic force (density histogram all-reduced over the ranks
@@ -861,7 +869,8 @@ static int slabStep(mrmd_b200_slab* sl, cudaStream_t st, cudaEvent_t e0, cudaEve
     }
     sl->prof[4] += profMark(sl, st, last);
     sl->prof[5] += 1.0;
-    sl->postPending = true;
+    if (deferPost) sl->postPending = true;  // rides in front of the next step's kick
+    else MB_TRY(mrmd_b200_vv_post(a, c.dt, st));
     sl->step += 1;
     return 0;
 }
@@ -1005,6 +1014,7 @@ int mrmd_b200_slab_destroy(mrmd_b200_slab* sl)
                      sl->rank, sl->prof[5], static_cast<long long>(sl->rebuilds), sl->prof[0] / sl->prof[5],
                      sl->prof[1] / sl->prof[5], sl->prof[2] / sl->prof[5], sl->prof[3] / sl->prof[5], sl->prof[4] / sl->prof[5]);
     for (auto e : sl->events) cudaEventDestroy(e);
+    sl->hp.destroy();
     if (sl->comm != nullptr) g_nccl.commDestroy(sl->comm);
     mrmd_b200_verlet_destroy(sl->list);
     for (int r = 0; r < SL_MAX_PEERS && r < sl->nranks; ++r)
@@ -1023,6 +1033,51 @@ int mrmd_b200_slab_destroy(mrmd_b200_slab* sl)
                                  &sl->haloKeys, &sl->haloStartLeft, &sl->haloStartRight})
         b->release();
     delete sl;
+    return 0;
+}
+
+// every rank: nsteps collective steps through this rank's HOST buffers (hostpipe.cuh).  The resident atoms change at
+// a rebuild (migration, re-sort): the buffers hold numLocal rows in the rank's current atom order, scalarsHost[3]
+// reports the count after each step.
+int mrmd_b200_slab_run_host(mrmd_b200_slab* sl, int64_t nsteps, double* posHost, double* velHost, double* scalarsHost,
+                            mrmd_b200_md_stats* stats, void* stream)
+{
+    MB_TRY(checkDevice());
+    MB_REQUIRE(sl != nullptr && nsteps >= 0 && posHost != nullptr && velHost != nullptr, "slab_run_host");
+    cudaStream_t st = S(stream);
+    if (sl->postPending)
+    {
+        MB_TRY(mrmd_b200_vv_post(sl->atoms, sl->cfg.dt, st));
+        sl->postPending = false;
+    }
+    const int64_t rebuilds0 = sl->rebuilds;
+    const double* dRes = sl->cfg.adress ? sl->adress->dResult : sl->lj->dResult;
+    int64_t storedSum = 0;
+    MB_TRY(hostPipeRun(sl->hp, sl->atoms, nsteps, posHost, velHost, scalarsHost, dRes, &sl->maxDisplacement, true, st,
+                       [&](cudaEvent_t evPosReady) -> int
+                       {
+                           MB_TRY(slabStep(sl, st, nullptr, nullptr, true, false, evPosReady));
+                           storedSum += sl->storedPairsNow;
+                           return 0;
+                       }));
+    MB_CUDA(cudaStreamSynchronize(st));
+    if (stats != nullptr)
+    {
+        *stats = mrmd_b200_md_stats{};
+        stats->steps = nsteps;
+        stats->rebuilds = sl->rebuilds - rebuilds0;
+        stats->storedPairs = storedSum;
+        stats->numLocal = sl->atoms->numLocal;
+        stats->numGhost = sl->atoms->numGhost;
+        stats->maxDisplacement = sl->maxDisplacement;
+    }
+    return 0;
+}
+
+int mrmd_b200_slab_set_energy_every_step(mrmd_b200_slab* sl, int enabled)
+{
+    MB_REQUIRE(sl != nullptr, "slab_set_energy_every_step");
+    sl->cfg.energyEveryStep = enabled ? 1 : 0;
     return 0;
 }
 
@@ -1050,7 +1105,7 @@ int mrmd_b200_slab_run(mrmd_b200_slab* sl, int64_t nsteps, int timeForceKernel, 
     for (int64_t i = 0; i < nsteps; ++i)
     {
         MB_TRY(slabStep(sl, st, i < nTimed ? sl->events[2 * i] : nullptr, i < nTimed ? sl->events[2 * i + 1] : nullptr,
-                        i == nsteps - 1));
+                        i == nsteps - 1 || sl->cfg.energyEveryStep != 0));
         storedSum += sl->storedPairsNow;
     }
     if (sl->postPending)

@@ -33,8 +33,18 @@
 
 namespace mrmd_b200
 {
-constexpr int TL_THREADS_BUILD = 256;  // neighbour build / decode (measured: 256 -> 461 us, 128 -> 568 us per 1M atoms)
-constexpr int TL_THREADS_FORCE = 128;  // force kernels (measured: 256 -> 194 us, 128 -> 184 us)
+// measurement knobs (profiles/variants.py builds side-by-side libraries with -D overrides); the defaults are the product
+#ifndef MRMD_TL_THREADS_BUILD
+#define MRMD_TL_THREADS_BUILD 256
+#endif
+#ifndef MRMD_TL_THREADS_FORCE
+#define MRMD_TL_THREADS_FORCE 128
+#endif
+#ifndef MRMD_LJT_PREFETCH
+#define MRMD_LJT_PREFETCH 16
+#endif
+constexpr int TL_THREADS_BUILD = MRMD_TL_THREADS_BUILD;  // neighbour build / decode
+constexpr int TL_THREADS_FORCE = MRMD_TL_THREADS_FORCE;  // force kernels (measured: 256 -> 194 us, 128 -> 184 us)
 constexpr int TL_GROUP = 2;                       // lanes per home atom
 constexpr int TL_PIECES = 27;                     // 9 columns x {low z-wrap, main, high z-wrap}
 constexpr int TL_MAX_CH = 64;                     // home cells per tile along z
@@ -139,7 +149,7 @@ __global__ void __launch_bounds__(32) tileDescKernel(TileParams tp, const int32_
         desc[tile * TL_DESC_INTS + 55] = homeCount;
         desc[tile * TL_DESC_INTS + 56] = before + (homeStart - centreStart);
         desc[tile * TL_DESC_INTS + 57] = total;
-        atomicMax(maxSlots, total);
+        if (maxSlots != nullptr) atomicMax(maxSlots, total);
     }
 }
 
@@ -248,6 +258,14 @@ __device__ __forceinline__ bool tileAllCoarseGrained(const TileParams& tp, const
     return (lo - w.center[0] > reach) || (w.center[0] - hi > reach);
 }
 
+// Measured in round 2 and dropped (profiles/r02_build_experiments.md): (a) walking the nine ranges of a home as ONE flat
+// candidate sequence, so that a warp's trip count is max_h(sum_r c[h][r]) instead of sum_r max_h(c[h][r]) (548 instead of
+// 787 warp iterations per 110-atom tile): some lane crosses a column boundary in almost every iteration and the divergent
+// advance costs more than the saved iterations (838 vs 461 us per 1M atoms); (b) taking the homes of a tile up in order
+// of candidate count / row length (whole tile or windows of 32 / 64 homes): the homes of a warp are then no longer
+// neighbours in z, their shared-memory reads scatter over the staged set, bank conflicts eat the balance (build +5 %,
+// force +0.5 %); (c) tiles sized for a 55 KB budget including the per-home tables of (a): half the homes per tile, twice
+// the staging (build 694 us, force 213 us).
 // Neighbour build on tiles: TL_GROUP lanes scan the candidates of one home atom (in each of the nine columns the z
 // interval the cutoff sphere reaches is one contiguous slot range), accepted slots are appended in scan order
 // through a ballot over the group -> deterministic rows, no atomics.
@@ -255,19 +273,29 @@ template <bool HALF>
 __global__ void __launch_bounds__(TL_THREADS_BUILD, 4)
     verletBuildTiledKernel(TileParams tp, GridDev cabanaGrid, const double4* __restrict__ pos,
                            const int32_t* __restrict__ cellLo, const int* __restrict__ desc, double rsqr, int width,
-                           int32_t* __restrict__ counts, uint16_t* __restrict__ enc, int32_t* stats, int cgSkip,
-                           mrmd_b200_weight cgWeight)
+                           int32_t* __restrict__ counts, uint16_t* __restrict__ enc, int32_t* stats, int32_t* tstats,
+                           int cgSkip, mrmd_b200_weight cgWeight)
 {
     extern __shared__ double sTile[];
     __shared__ TileDesc td;
     __shared__ int cellSlot[9][TL_CELLS];  // slot where virtual cell v (= k0 - 1 + v) of column r starts
-    if (cgSkip && tileAllCoarseGrained(tp, cgWeight, blockIdx.x))
     {
-        // AdResS step loops: no pair of this tile is ever evaluated, its rows stay empty
         const int* d = desc + size_t(blockIdx.x) * TL_DESC_INTS;
         const int homeStart = d[54], homeCount = d[55];
-        for (int h = threadIdx.x; h < homeCount; h += blockDim.x) counts[homeStart + h] = 0;
-        return;
+        // the tile geometry is re-used from the previous rebuild without a host round trip: a tile that outgrew the
+        // staged capacity raises a flag (the host rebuilds with measured tiles) and leaves its rows empty
+        const bool overflow = d[57] > tp.cap;
+        if (threadIdx.x == 0)
+        {
+            atomicMax(tstats, d[57]);  // sizes the next rebuild's tiles
+            if (overflow) tstats[2] = 1;
+        }
+        if (overflow || (cgSkip && tileAllCoarseGrained(tp, cgWeight, blockIdx.x)))
+        {
+            // AdResS step loops: no pair of a coarse-grained tile is ever evaluated, its rows stay empty
+            for (int h = threadIdx.x; h < homeCount; h += blockDim.x) counts[homeStart + h] = 0;
+            return;
+        }
     }
     loadTileDesc(desc, td);
     double* sx_ = sTile;
@@ -423,17 +451,23 @@ __global__ void __launch_bounds__(TL_THREADS_BUILD, 4)
     }
 }
 
-// reciprocal with two Newton steps on the hardware seed: <= 1 ulp, no slow-path branch (the force is compared
-// to 1e-10 relative; the cutoff decisions never use it)
+// reciprocal from the hardware seed (20 mantissa bits, error e <= 2^-20) with one cubically convergent step
+// r (1 + e + e^2): relative error e^3 < 1e-18, three DFMA, no slow-path branch (the force is compared to 1e-10 relative;
+// the cutoff decisions never use it)
 __device__ __forceinline__ double fastRcp(double x)
 {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#ifdef MRMD_RCP_NEWTON2  // measurement knob: the round-1 variant, two Newton steps (four DFMA)
     double e = fma(-x, r, 1.0);
     r = fma(r, e, r);
     e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    return r;
+    return fma(r, e, r);
+#else
+    const double e = fma(-x, r, 1.0);
+    const double t = fma(e, e, e);
+    return fma(r, t, r);
+#endif
 }
 
 // Sums four per-lane values over the TL_GROUP lanes of a group.  Every step halves the number of values a lane carries
@@ -482,7 +516,7 @@ __device__ __forceinline__ int groupSumLane(int v) { return (TL_GROUP == 8) ? 2 
 __device__ __forceinline__ int groupSumSlot(int v) { return v % TL_VPL; }
 
 // list steps (of TL_GROUP entries) whose slots are loaded into registers up front with 16-byte loads
-constexpr int LJT_PREFETCH = (64 / TL_GROUP < 16) ? 64 / TL_GROUP : 16;
+constexpr int LJT_PREFETCH = (64 / TL_GROUP < MRMD_LJT_PREFETCH) ? 64 / TL_GROUP : MRMD_LJT_PREFETCH;  // multiple of 8
 
 // one pair of LennardJones::apply_if's inner loop (LennardJones.hpp:176-196) against a staged partner
 template <bool SINGLE_TYPE, bool ENERGY>
@@ -490,7 +524,7 @@ __device__ __forceinline__ void ljPair(const double* sx_, const double* sy_, con
                                        const unsigned char* sType, int slot, bool valid, double xi, double yi, double zi,
                                        int typeI, const LJType& t0, const LJTable& table, int64_t numTypesQuirk,
                                        double rcSqr, double& fx, double& fy, double& fz, double& energy, double& virial,
-                                       double& pairs)
+                                       int& pairs)
 {
     // predicated, not branched: consecutive list entries are independent, and without a branch around every pair
     // the compiler interleaves their dependent FP64 chains (an invalid entry reads slot 0 and contributes zero)
@@ -518,7 +552,7 @@ __device__ __forceinline__ void ljPair(const double* sx_, const double* sy_, con
         energy += in ? e : 0.0;
         virial -= 0.5 * ff * d2;
     }
-    pairs += in ? 1.0 : 0.0;
+    pairs += in ? 1 : 0;  // integer pipe: the FP64 pipe is the busy one
     fx += dx * ff;
     fy += dy * ff;
     fz += dz * ff;
@@ -544,7 +578,8 @@ __global__ void __launch_bounds__(TL_THREADS_FORCE)
 
     // warp-uniform control flow, see verletBuildTiledKernel
     const int group = threadIdx.x / TL_GROUP, gl = threadIdx.x % TL_GROUP;
-    double energy = 0.0, virial = 0.0, pairs = 0.0;
+    double energy = 0.0, virial = 0.0;
+    int pairs = 0;
     const LJType t0 = table.t[0];
     for (int hBase = 0; hBase < td.homeCount; hBase += blockDim.x / TL_GROUP)
     {
@@ -601,7 +636,7 @@ __global__ void __launch_bounds__(TL_THREADS_FORCE)
         }
     }
     // every pair is visited from both sides
-    gridReduce3<TL_THREADS_FORCE>(0.5 * energy, 0.5 * virial, 0.5 * pairs, partials, result, ticket);
+    gridReduce3<TL_THREADS_FORCE>(0.5 * energy, 0.5 * virial, 0.5 * double(pairs), partials, result, ticket);
 }
 
 // ---- AdResS on tiles ----------------------------------------------------------------------------------------
@@ -863,7 +898,7 @@ static int makeTileParams(const mrmd_b200_atoms* a, const mrmd_b200_subdomain* s
 
 constexpr int TL_SMEM_PER_SLOT_BUILD = 24;  // x, y, z
 constexpr int TL_SMEM_PER_SLOT_FORCE = 25;  // x, y, z + type byte
-constexpr int TL_SMEM_BUDGET = 48 * 1024;   // preferred per-tile budget (several tiles per SM)
+constexpr int TL_SMEM_BUDGET = 48 * 1024;   // preferred budget of a tile's staged positions (several tiles per SM)
 constexpr int TL_SMEM_MAX = 200 * 1024;
 
 int tiledConfigure()
@@ -995,6 +1030,9 @@ int verletBuildTiled(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, const mrmd_b
     MB_REQUIRE(radius > 0.0 && cellRatio > 0.0 && maxNeigh > 0, "verlet_build_periodic: bad radius / ratio / width");
     MB_REQUIRE(a->lcValid && a->lcBegin == 0 && a->lcEnd == a->numLocal,
                "verlet_build_periodic: sort the local atoms first (LinkedCellList + permute over [0, numLocalAtoms))");
+    MB_REQUIRE(a->lcPosEpoch == a->posEpoch,
+               "verlet_build_periodic: positions changed since the last LinkedCellList + permute (the atoms no longer sit in "
+               "the cells of the sort): sort again before building");
     const GridDev& g = a->lcGrid;
     // cells are at least one radius wide along x and y (3 x 3 columns around a tile); along z they may be finer: a
     // LinkedCellList with gridDelta = (r, r, r / 4) keeps the atoms of a column in finer z order and lets the
@@ -1016,7 +1054,9 @@ int verletBuildTiled(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, const mrmd_b
     MB_TRY(tiledConfigure());
     const int64_t n = a->numLocal;
     if (v->hStats == nullptr) MB_CUDA(cudaMallocHost(&v->hStats, 16));
+    if (v->hTstats == nullptr) MB_CUDA(cudaMallocHost(&v->hTstats, 16));
     MB_TRY(v->stats.reserve(16));
+    MB_TRY(v->tstats.reserve(16));
     v->numParticles = n;
     v->begin = 0;
     v->end = n;
@@ -1026,7 +1066,6 @@ int verletBuildTiled(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, const mrmd_b
     v->tiled = true;
     v->tiledSub = *s;
     v->tiledEpoch = a->lcEpoch;
-    v->tiledHaloX = haloX;
     {
         const int64_t perX = int64_t(g.n[1]) * g.n[2];
         const int64_t extCells = a->lcNumCells + (haloX ? 2 * perX : 0);
@@ -1043,62 +1082,92 @@ int verletBuildTiled(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, const mrmd_b
     const double gs = radius * cellRatio;
     const double delta[3] = {gs, gs, gs};
     const GridDev cabanaGrid = makeGrid(s->minGhostCorner, s->maxGhostCorner, delta);
-
-    // choose CH: ~110 home atoms per tile, at least ~2 tiles per SM, staged slots within the smem budget
-    const double perCell = double(n) / double(std::max<int64_t>(a->lcNumCells, 1));
-    int CH = std::max(1, std::min({TL_MAX_CH, g.n[2], static_cast<int>(std::ceil(110.0 / std::max(perCell, 0.1)))}));
-    while (CH > 1 && int64_t(g.n[0]) * g.n[1] * ((g.n[2] + CH - 1) / CH) < 2 * 148) CH = (CH + 1) / 2;
-    TileParams tp;
-    int tiles = 0;
-    for (;;)
-    {
-        MB_TRY(makeTileParams(a, s, CH, 0, haloX, R, tp));
-        tiles = g.n[0] * g.n[1] * tp.numChunks;
-        MB_TRY(v->tileDesc.reserve(size_t(tiles) * TL_DESC_INTS * 4));
-        MB_CUDA(cudaMemsetAsync(v->stats.p, 0, 16, st));
-        tileDescKernel<<<tiles, 32, 0, st>>>(tp, cellLo, cellHi, v->tileDesc.as<int>(), v->stats.as<int>());
-        MB_LAUNCHED();
-        MB_CUDA(cudaMemcpyAsync(v->hStats, v->stats.p, 4, cudaMemcpyDeviceToHost, st));
-        MB_CUDA(cudaStreamSynchronize(st));
-        const int slots = v->hStats[0];
-        if (slots * TL_SMEM_PER_SLOT_BUILD <= TL_SMEM_BUDGET || CH == 1)
-        {
-            MB_REQUIRE(slots * TL_SMEM_PER_SLOT_BUILD + 64 <= TL_SMEM_MAX && slots < 65535,
-                       "verlet_build_periodic: a tile exceeds shared memory");
-            v->tiledSlots = (std::max(slots, 1) + 1) & ~1;  // even: keeps the int / byte arrays 8-byte aligned
-            break;
-        }
-        CH = (CH + 1) / 2;
-    }
-    v->tiledCH = CH;
-    tp.cap = v->tiledSlots;
     const double rsqr = radius * radius;
     int64_t width = (std::max<int64_t>(maxNeigh, 1) + 63) & ~int64_t(63);  // tiledRowIndex: eight lanes x 16-byte words
     if (v->width > width && v->enc.bytes >= size_t(v->width) * std::max<int64_t>(n, 1) * 2) width = v->width;
-    for (int attempt = 0; attempt < 3; ++attempt)
+    MB_REQUIRE(width <= 1024, "verlet_build_periodic: more than 1024 neighbours per atom");
+    // shared memory of the builder: positions + one staged row per group of TL_GROUP lanes (width x 2 bytes each)
+    auto buildSmem = [&](int slots, int64_t w)
+    { return size_t(slots) * TL_SMEM_PER_SLOT_BUILD + 16 + size_t(TL_THREADS_BUILD / TL_GROUP) * size_t(w) * 2; };
+
+    // Tile geometry (CH cells per tile, staged-slot capacity).  The first build measures the tiles (one host round
+    // trip); later builds on the same grid re-use CH with the largest tile of the previous build plus head room as the
+    // capacity and verify after the fact (tstats[2], read back together with the list statistics): no extra
+    // synchronisation per rebuild.
+    const bool sameGrid = v->tiledCH > 0 && v->tiledHaloX == haloX && v->tiledGridN[0] == g.n[0] &&
+                          v->tiledGridN[1] == g.n[1] && v->tiledGridN[2] == g.n[2] && v->hTstats[0] > 0;
+    for (int attempt = 0; attempt < 4; ++attempt)
     {
+        TileParams tp;
+        int tiles = 0, CH = 0;
+        if (sameGrid && attempt == 0)
+        {
+            CH = v->tiledCH;
+            MB_TRY(makeTileParams(a, s, CH, 0, haloX, R, tp));
+            tiles = g.n[0] * g.n[1] * tp.numChunks;
+            // 3 % head room over the last build's largest tile (atoms move by less than the skin between rebuilds)
+            v->tiledSlots = (std::min(v->hTstats[0] + v->hTstats[0] / 32 + 8, 65534) + 1) & ~1;
+            MB_TRY(v->tileDesc.reserve(size_t(tiles) * TL_DESC_INTS * 4));
+            tileDescKernel<<<tiles, 32, 0, st>>>(tp, cellLo, cellHi, v->tileDesc.as<int>(), nullptr);
+            MB_LAUNCHED();
+        }
+        else
+        {
+            // choose CH: ~110 home atoms per tile, at least ~2 tiles per SM, staged slots within the smem budget
+            const double perCell = double(n) / double(std::max<int64_t>(a->lcNumCells, 1));
+            CH = std::max(1, std::min({TL_MAX_CH, g.n[2], static_cast<int>(std::ceil(110.0 / std::max(perCell, 0.1)))}));
+            while (CH > 1 && int64_t(g.n[0]) * g.n[1] * ((g.n[2] + CH - 1) / CH) < 2 * 148) CH = (CH + 1) / 2;
+            for (;;)
+            {
+                MB_TRY(makeTileParams(a, s, CH, 0, haloX, R, tp));
+                tiles = g.n[0] * g.n[1] * tp.numChunks;
+                MB_TRY(v->tileDesc.reserve(size_t(tiles) * TL_DESC_INTS * 4));
+                MB_CUDA(cudaMemsetAsync(v->tstats.p, 0, 16, st));
+                tileDescKernel<<<tiles, 32, 0, st>>>(tp, cellLo, cellHi, v->tileDesc.as<int>(), v->tstats.as<int>());
+                MB_LAUNCHED();
+                MB_CUDA(cudaMemcpyAsync(v->hTstats, v->tstats.p, 16, cudaMemcpyDeviceToHost, st));
+                MB_CUDA(cudaStreamSynchronize(st));
+                const int slots = v->hTstats[0];
+                if (slots * TL_SMEM_PER_SLOT_BUILD <= TL_SMEM_BUDGET || CH == 1)
+                {
+                    MB_REQUIRE(buildSmem(slots, width) + 64 <= size_t(TL_SMEM_MAX) && slots < 65535,
+                               "verlet_build_periodic: a tile exceeds shared memory");
+                    v->tiledSlots = (std::max(slots, 1) + 1) & ~1;  // even: keeps the arrays behind the positions 16-byte aligned
+                    break;
+                }
+                CH = (CH + 1) / 2;
+            }
+        }
+        v->tiledCH = CH;
+        v->tiledHaloX = haloX;
+        for (int d = 0; d < 3; ++d) v->tiledGridN[d] = g.n[d];
+        tp.cap = v->tiledSlots;
         MB_TRY(v->enc.reserve(size_t(width) * std::max<int64_t>(n, 1) * 2));
         v->width = width;
         MB_CUDA(cudaMemsetAsync(v->stats.p, 0, 16, st));
-        MB_REQUIRE(width <= 1024, "verlet_build_periodic: more than 1024 neighbours per atom");
-        // positions + one staged row per group of TL_GROUP lanes (width x 2 bytes each)
-        const size_t smem = size_t(v->tiledSlots) * TL_SMEM_PER_SLOT_BUILD + 16 +
-                            size_t(TL_THREADS_BUILD / TL_GROUP) * size_t(width) * 2;
-        if (v->half)
-            verletBuildTiledKernel<true><<<tiles, TL_THREADS_BUILD, smem, st>>>(
-                tp, cabanaGrid, a->v.pos, cellLo, v->tileDesc.as<int>(), rsqr,
-                static_cast<int>(width), v->counts.as<int32_t>(), v->enc.as<uint16_t>(), v->stats.as<int32_t>(),
-                v->tiledCgSkip ? 1 : 0, v->tiledCgWeight);
-        else
-            verletBuildTiledKernel<false><<<tiles, TL_THREADS_BUILD, smem, st>>>(
-                tp, cabanaGrid, a->v.pos, cellLo, v->tileDesc.as<int>(), rsqr,
-                static_cast<int>(width), v->counts.as<int32_t>(), v->enc.as<uint16_t>(), v->stats.as<int32_t>(),
-                v->tiledCgSkip ? 1 : 0, v->tiledCgWeight);
+        MB_CUDA(cudaMemsetAsync(v->tstats.p, 0, 16, st));
+        const size_t smem = buildSmem(v->tiledSlots, width);
+        MB_REQUIRE(smem <= size_t(TL_SMEM_MAX), "verlet_build_periodic: a tile exceeds shared memory");
+#define VBT_LAUNCH(H)                                                                                                  \
+    verletBuildTiledKernel<H><<<tiles, TL_THREADS_BUILD, smem, st>>>(                                                  \
+        tp, cabanaGrid, a->v.pos, cellLo, v->tileDesc.as<int>(), rsqr, static_cast<int>(width), v->counts.as<int32_t>(), \
+        v->enc.as<uint16_t>(), v->stats.as<int32_t>(), v->tstats.as<int32_t>(), v->tiledCgSkip ? 1 : 0, v->tiledCgWeight)
+        if (v->half) VBT_LAUNCH(true);
+        else VBT_LAUNCH(false);
+#undef VBT_LAUNCH
         MB_LAUNCHED();
         MB_CUDA(cudaMemcpyAsync(v->hStats, v->stats.p, 16, cudaMemcpyDeviceToHost, st));
+        MB_CUDA(cudaMemcpyAsync(v->hTstats, v->tstats.p, 16, cudaMemcpyDeviceToHost, st));
         MB_CUDA(cudaStreamSynchronize(st));
+        if (v->hTstats[2] != 0)
+        {
+            v->tiledCH = 0;  // a tile outgrew the re-used geometry: measure again
+            v->hTstats[0] = 0;
+            continue;
+        }
         if (v->hStats[0] <= width) return 0;
         width = (int64_t(v->hStats[0]) + 63) & ~int64_t(63);
+        MB_REQUIRE(width <= 1024, "verlet_build_periodic: more than 1024 neighbours per atom");
     }
     setLastError("verlet_build_periodic: neighbour table overflow after refill");
     return MRMD_B200_ECAPACITY;

@@ -123,6 +123,15 @@ class SlabMolecularDynamics:
                                             C.c_void_p(stream) if stream else None))
         return {f: getattr(st, f) for f, _ in st._fields_}
 
+    def run_host(self, nsteps, posHostPtr, velHostPtr, scalarsHostPtr=None, stream=None):
+        st = _lib.MdStats()
+        check(_lib.load().mrmd_b200_slab_run_host(self.h, nsteps, posHostPtr, velHostPtr, scalarsHostPtr, C.byref(st),
+                                                 C.c_void_p(stream) if stream else None))
+        return {f: getattr(st, f) for f, _ in st._fields_}
+
+    def setEnergyEveryStep(self, enabled):
+        check(_lib.load().mrmd_b200_slab_set_energy_every_step(self.h, int(enabled)))
+
     def close(self):
         h, self.h = getattr(self, "h", None), None
         if h:
@@ -133,3 +142,98 @@ class SlabMolecularDynamics:
             self.close()
         except Exception:
             pass
+
+
+def parity_check(rank, world, steps=40, mode="lj", langevin=True, stream=None, sites_x_per_rank=12, sites_yz=10):
+    """x-slab run over `world` ranks against the single-GPU periodic run of the same global system (computed on rank 0's
+    GPU): atoms matched by their global ids, positions / velocities compared atom by atom, pair counts and rebuild
+    counts equal, energy within 1e-9.  torch.distributed (NCCL) must be initialised; collective.  Langevin noise is
+    keyed by the global atom id (Philox counter), so the thermostatted trajectories are comparable too.
+    mode: "lj", "adress" (slab region across a rank boundary, thermodynamic force updated during the run),
+    "adress-cuts" (uneven slab widths), "tetramer" (4-atom molecules with SHAKE / RATTLE, spherical region).
+    Returns the result dict on rank 0 ({"ok": ...}), {"ok": <broadcast flag>} elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    from . import api
+
+    tetramer = mode == "tetramer"
+    adress = mode.startswith("adress") or tetramer
+    nx, ny = sites_x_per_rank * world, sites_yz
+    rng = np.random.default_rng(42)
+    g = np.stack(np.meshgrid(np.arange(nx), np.arange(ny), np.arange(ny), indexing="ij"), axis=-1).reshape(-1, 3)
+    apm = 4 if tetramer else 1
+    if tetramer:
+        spacing = 1.98425
+        sites = (g + 0.5) * spacing + (rng.random(g.shape) - 0.5) * 0.3
+        tet = np.array([(1, 1, 1), (1, -1, -1), (-1, 1, -1), (-1, -1, 1)], dtype=np.float64) / (2.0 * np.sqrt(2.0))
+        pos = (sites[:, None, :] + tet[None, :, :]).reshape(-1, 3)
+        vmol = (rng.random(g.shape) - 0.5) * 1.5
+        vmol -= vmol.mean(axis=0)
+        vel = np.repeat(vmol, 4, axis=0)
+        owner_pos = sites
+    else:
+        spacing = 1.25
+        pos = (g + 0.5) * spacing + (rng.random(g.shape) - 0.5) * 0.5
+        vel = (rng.random(g.shape) - 0.5) * 1.5
+        vel -= vel.mean(axis=0)
+        owner_pos = pos
+    gmin, gmax = np.zeros(3), np.array([nx, ny, ny]) * spacing
+    phys = dict(dt=0.002, rc=2.5, skin=0.1, sigma=1.0, epsilon=1.0, cappingDistance=0.7,
+                maxNeighbors=40 if tetramer else 60, langevin=langevin, zeta=20.0, temperature=1.5, seed=4321)
+    extra = {}
+    if tetramer:
+        extra = dict(adress=True, weight=api.Spherical(gmax / 2, 0.25 * gmax[1], 0.15 * gmax[1], 2), doShift=True,
+                     atomsPerMolecule=4, numConstraintIterations=3, bondLength=1.0)
+    elif adress:
+        extra = dict(adress=True, weight=api.Slab(gmax / 2, 0.2 * gmax[0], 0.1 * gmax[0], 2), doShift=True,
+                     thermo=dict(targetDensity=0.512, binWidth=0.5, modulation=2.0, sampleInterval=2, updateInterval=10,
+                                 sigma=2.0, range=2.0))
+    cuts = None
+    if mode == "adress-cuts":
+        cuts = balanced_cuts(gmin, gmax, world, 0.3 * gmax[0], 0.7 * gmax[0], 2.0, quantum=spacing, min_width=5.2)
+        if world == 2:  # the balanced cut of a symmetric region is the middle: take an uneven one instead
+            cuts = np.array([0.0, round(0.4 * nx) * spacing, gmax[0]])
+    mols = select_slab(owner_pos, gmin, gmax, rank, world, cuts)
+    mine = (mols[:, None] * apm + np.arange(apm)[None, :]).reshape(-1)
+    atoms = api.Atoms.from_arrays(pos[mine], vel[mine], mass=1.0, relativeMass=1.0 / apm, ids=mine)
+    uid = broadcast_unique_id(rank)
+    md = SlabMolecularDynamics(atoms, gmin, gmax, rank, world, uid, cuts=cuts, **phys, **extra)
+    st = md.run(steps, stream=stream)
+    n = st["numLocal"]
+    my = (atoms.get("id")[:n], atoms.getPos()[:n], atoms.getVel()[:n], st["pairInteractions"], st["rebuilds"], st["energy"])
+    gathered = [None] * world
+    dist.all_gather_object(gathered, my)
+    md.close()
+    ok, msg = True, {}
+    if rank == 0:
+        ids = np.concatenate([x[0] for x in gathered])
+        all_pos = np.concatenate([x[1] for x in gathered])
+        all_vel = np.concatenate([x[2] for x in gathered])
+        pairs = gathered[0][3]  # already the sum over the ranks
+        sub = api.Subdomain(gmin, gmax, phys["rc"] + phys["skin"])
+        ref_atoms = api.Atoms.from_arrays(pos, vel, mass=1.0, relativeMass=1.0 / apm)
+        ref = api.MolecularDynamics(ref_atoms, sub, cellSort=not tetramer, fullList=0 if tetramer else 2, **phys, **extra)
+        rst = ref.run(steps, stream=stream)
+        rid = ref_atoms.get("id")[:len(pos)]
+        rp, rv = ref_atoms.getPos()[:len(pos)], ref_atoms.getVel()[:len(pos)]
+        bijective = bool(len(ids) == len(pos) and np.array_equal(np.sort(ids), np.arange(len(pos))))
+        msg = {"mode": mode, "ranks": world, "steps": steps, "langevin": bool(langevin), "atoms": int(len(ids)),
+               "expected": int(len(pos)), "bijective": bijective}
+        if bijective:
+            a, b = np.argsort(ids), np.argsort(rid)
+            box = gmax - gmin
+            d = all_pos[a] - rp[b]
+            d -= box * np.round(d / box)  # the two runs may hold different periodic images of an atom
+            msg.update({"max_pos_err": float(np.abs(d).max()), "max_vel_err": float(np.abs(all_vel[a] - rv[b]).max())})
+        msg.update({"pairs": int(pairs), "pairs_ref": int(rst["pairInteractions"]), "energy": st["energy"],
+                    "energy_ref": rst["energy"], "rebuilds": [int(x[4]) for x in gathered],
+                    "rebuilds_ref": int(rst["rebuilds"]), "per_rank": [int(len(x[0])) for x in gathered]})
+        ok = bool(bijective and msg["max_pos_err"] < 1e-9 and msg["max_vel_err"] < 1e-7 and
+                  msg["pairs"] == msg["pairs_ref"] and
+                  abs(msg["energy"] - msg["energy_ref"]) <= 1e-9 * abs(msg["energy_ref"]) and
+                  all(x[3] == pairs for x in gathered) and all(r == msg["rebuilds_ref"] for r in msg["rebuilds"]))
+        msg = {"ok": ok, **msg}
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    return msg if rank == 0 else {"ok": bool(int(flag) == 1)}

@@ -31,11 +31,12 @@ CONFIGS = {
 TETRAMER_SPACING = 1.98425  # molecule density 0.128 -> atom density 0.512
 
 
-def tetramer_system(n_side, spacing=TETRAMER_SPACING, seed=1234, max_velocity=1.0):
+def tetramer_system(n_side, spacing=TETRAMER_SPACING, seed=1234, max_velocity=1.0, n_side_x=None):
     """n_side^3 tetramers: centres of mass on a simple-cubic lattice, each a regular tetrahedron of edge 1 centred on its
     site, atoms of a molecule contiguous (atomsOffset = 4 m); one velocity per molecule (no velocity along the bonds),
     net momentum removed.  Returns pos[4M,3], vel[4M,3], box."""
-    idx = np.stack(np.meshgrid(*[np.arange(n_side)] * 3, indexing="ij"), axis=-1).reshape(-1, 3)
+    nx = n_side_x or n_side
+    idx = np.stack(np.meshgrid(np.arange(nx), np.arange(n_side), np.arange(n_side), indexing="ij"), axis=-1).reshape(-1, 3)
     sites = (idx + 0.5) * spacing
     tet = np.array([(1, 1, 1), (1, -1, -1), (-1, 1, -1), (-1, -1, 1)], dtype=np.float64) / (2.0 * np.sqrt(2.0))
     pos = (sites[:, None, :] + tet[None, :, :]).reshape(-1, 3)
@@ -43,4 +44,4 @@ def tetramer_system(n_side, spacing=TETRAMER_SPACING, seed=1234, max_velocity=1.
     vmol = (rng.random(sites.shape) - 0.5) * max_velocity
     vmol -= vmol.mean(axis=0, keepdims=True)
     vel = np.repeat(vmol, 4, axis=0)
-    return pos, vel, np.full(3, n_side * spacing)
+    return pos, vel, np.array([nx * spacing, n_side * spacing, n_side * spacing])

@@ -14,7 +14,8 @@ from . import pyoracle as orc
 
 class OracleMD:
     def __init__(self, pos, vel, box, dt=0.002, rc=2.5, skin=0.1, sigma=1.0, epsilon=1.0, cap=0.7, max_neigh=60,
-                 langevin=False, zeta=20.0, temperature=1.5, seed=1234, cell_sort=True, ghost_capacity_factor=None):
+                 langevin=False, zeta=20.0, temperature=1.5, seed=1234, cell_sort=True, ghost_capacity_factor=None,
+                 ids=None):
         self.L = orc.lib()
         self.n = n = len(pos)
         self.box = np.asarray(box, dtype=np.float64)
@@ -41,6 +42,8 @@ class OracleMD:
         self.energy_virial = np.zeros(2)
         self._cid = np.zeros(n, dtype=np.int32)
         self._perm = np.zeros(n, dtype=np.int64)
+        # global atom ids: the Philox counter of the Langevin noise, permuted with the records
+        self.ids = np.arange(n, dtype=np.int64) if ids is None else np.ascontiguousarray(ids, dtype=np.int64).copy()
 
     def _rebuild(self):
         L, a, n = self.L, self.atoms, self.n
@@ -53,6 +56,7 @@ class OracleMD:
             off = np.zeros(nc + 1, dtype=np.int64)
             L.or_cell_perm(self._cid.ctypes.data, 0, n, nc, self._perm.ctypes.data, off.ctypes.data)
             L.or_permute_atoms(a.ctypes.data, 0, n, self._perm.ctypes.data)
+            self.ids = self.ids[self._perm]
         self.ng = L.or_ghost_create_xyz(a.ctypes.data, n, len(a), C.byref(self.sub), self.corr.ctypes.data)
         assert self.ng >= 0, "oracle ghost capacity exceeded"
         self.counts, self.neigh = orc.verlet_build(a, 13, n + self.ng, 0, n, self.cutoff, 1.0,
@@ -63,7 +67,8 @@ class OracleMD:
     def one_step(self):
         L, a, n = self.L, self.atoms, self.n
         if self.langevin:
-            d = L.or_langevin_pre(a.ctypes.data, n, self.dt, self.zeta, self.temperature, self.seed, self.step, None)
+            d = L.or_langevin_pre_ids(a.ctypes.data, n, self.dt, self.zeta, self.temperature, self.seed, self.step, None,
+                                      self.ids.ctypes.data)
         else:
             d = L.or_vv_pre(a.ctypes.data, n, self.dt)
         self.max_disp += d
@@ -133,6 +138,7 @@ class OracleAdressMD:
         self.step = self.ng = self.mg = self.rebuilds = self.pairs = 0
         self.energy = 0.0
         self._cid, self._perm = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int64)
+        self.ids = np.arange(n, dtype=np.int64)
 
     def _rebuild(self):
         L, a, m, n, nm = self.L, self.atoms, self.mols, self.n, self.nm
@@ -146,6 +152,7 @@ class OracleAdressMD:
             off = np.zeros(nc + 1, dtype=np.int64)
             L.or_cell_perm(self._cid.ctypes.data, 0, n, nc, self._perm.ctypes.data, off.ctypes.data)
             L.or_permute_atoms(a.ctypes.data, 0, n, self._perm.ctypes.data)  # one atom per molecule: offsets stay i -> i
+            self.ids = self.ids[self._perm]
             L.or_update_molecules(m.ctypes.data, nm, a.ctypes.data, C.byref(self.weight))
         out = np.zeros(2, dtype=np.int64)
         rc = L.or_mr_ghost_create_xyz(m.ctypes.data, nm, len(m), a.ctypes.data, n, len(a), C.byref(self.sub),
@@ -164,7 +171,8 @@ class OracleAdressMD:
             assert L.or_shake_positional(m.ctypes.data, nm, a.ctypes.data, n + self.ng, self.bond_idx.ctypes.data,
                                          self.bond_eq.ctypes.data, len(self.bond_eq), self.constraint_iterations, self.dt) == 0
         if self.langevin:
-            d = L.or_langevin_pre(a.ctypes.data, n, self.dt, self.zeta, self.temperature, self.seed, self.step, None)
+            d = L.or_langevin_pre_ids(a.ctypes.data, n, self.dt, self.zeta, self.temperature, self.seed, self.step, None,
+                                      self.ids.ctypes.data)
         else:
             d = L.or_vv_pre(a.ctypes.data, n, self.dt)
         self.max_disp += d

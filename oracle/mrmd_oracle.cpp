@@ -751,6 +751,14 @@ void or_philox_normals(uint64_t seed, uint64_t step, uint64_t idx, double* out4)
 double or_langevin_pre(or_atom_t* atoms, int64_t numLocal, double dt, double zeta, double temperature, uint64_t seed,
                        uint64_t step, const or_pred_t* pred)
 {
+    return or_langevin_pre_ids(atoms, numLocal, dt, zeta, temperature, seed, step, pred, nullptr);
+}
+
+// ids (optional): the global atom id that keys the noise instead of the index, so that a trajectory does not depend on
+// the atom order (spatial sort) or on how many ranks share the system
+double or_langevin_pre_ids(or_atom_t* atoms, int64_t numLocal, double dt, double zeta, double temperature, uint64_t seed,
+                           uint64_t step, const or_pred_t* pred, const int64_t* ids)
+{
     const double dtHalf = 0.5 * dt;
     const double dtFull = dt;
     double maxDistSqr = 0.0;
@@ -765,7 +773,7 @@ double or_langevin_pre(or_atom_t* atoms, int64_t numLocal, double dt, double zet
         if (pred1(pred, a.pos[0], a.pos[1], a.pos[2]))
         {
             double rnd[4];
-            or_philox_normals(seed, step, uint64_t(idx), rnd);
+            or_philox_normals(seed, step, uint64_t(ids != nullptr ? ids[idx] : idx), rnd);
             const double dtm = dtFull / a.mass;
             const double damping = std::exp(-zeta * dtm);
             const double sigma = std::sqrt(temperature / a.mass * (1.0 - std::exp(-2.0 * zeta * dtm)));

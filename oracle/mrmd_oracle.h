@@ -180,6 +180,9 @@ void or_vv_post(or_atom_t* atoms, int64_t numLocal, double dt);
  * counter=(idx lo, idx hi, step lo, step hi), 32-bit uniforms, Box-Muller. */
 double or_langevin_pre(or_atom_t* atoms, int64_t numLocal, double dt, double zeta, double temperature,
                        uint64_t seed, uint64_t step, const or_pred_t* pred);
+/* the same with the counter taken from ids[idx] (global atom ids; NULL: the index) */
+double or_langevin_pre_ids(or_atom_t* atoms, int64_t numLocal, double dt, double zeta, double temperature,
+                           uint64_t seed, uint64_t step, const or_pred_t* pred, const int64_t* ids);
 void or_philox_normals(uint64_t seed, uint64_t step, uint64_t idx, double* out4);
 void or_philox4x32(const uint32_t* ctr, const uint32_t* key, uint32_t* out);
 

@@ -115,6 +115,8 @@ def lib():
         "or_vv_post": (None, [vp, i64, C.c_double]),
         "or_langevin_pre": (C.c_double, [vp, i64, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_uint64,
                                          C.POINTER(Pred)]),
+        "or_langevin_pre_ids": (C.c_double, [vp, i64, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_uint64,
+                                             C.POINTER(Pred), vp]),
         "or_philox_normals": (None, [C.c_uint64, C.c_uint64, C.c_uint64, vp]),
         "or_philox4x32": (None, [vp, vp, vp]),
         "or_weight_eval": (None, [C.POINTER(Weight), C.c_double, C.c_double, C.c_double, dp, dp, vp]),
