@@ -305,9 +305,14 @@ __global__ void packPositionsKernel(const double4* pos, const int32_t* idx, int6
 // buffer, no host involvement in the per-step exchange.  A region is only rewritten after the rank-wide allreduce of
 // the next step, which the reader's stream reaches only after its pull (and force kernel) have finished.
 constexpr int SL_MAX_PEERS = 8;    // ranks of one node
-// double4 slots in front of the regions: [0] halo flags {fromLeft, fromRight}, [1 ..] the slots of the displacement
-// all-gather: 2 parities x SL_MAX_PEERS x {value, sequence number}
-constexpr int SL_P2P_HEADER = 1 + SL_MAX_PEERS;
+// Header of a peer buffer, in 8-byte words (all written by OTHER ranks over NVLink, read by the owner):
+//   [0..3]   halo flags {fromLeft, fromRight} for the two parities of the per-step halo (sequence numbers)
+//   [4..35]  displacement all-gather: 2 parities x SL_MAX_PEERS x {value, sequence number}
+//   [36..39] migration at a rebuild: {count fromLeft, seq, count fromRight, seq}
+//   [40..43] halo lists at a rebuild: {count fromLeft, seq, count fromRight, seq}
+// behind it (in double4 units): four halo regions (parity x side, p2pCap unit records each), then two migration regions
+constexpr int SL_HW_HALO = 0, SL_HW_DECIDE = 4, SL_HW_MIG = 36, SL_HW_HALOCOUNT = 40;
+constexpr int SL_P2P_HEADER = 12;  // double4 slots (48 words)
 struct PeerBuffers
 {
     double4* p[SL_MAX_PEERS];
@@ -323,7 +328,7 @@ __global__ void maxDisplacementGatherKernel(const double* myMaxSqr, PeerBuffers 
                                             int parity, double* outDevice, volatile double* outHost)
 {
     const int t = threadIdx.x;
-    const int slotBase = 4 * 1 + parity * 2 * SL_MAX_PEERS;  // in doubles from the start of the buffer (header slot 1 ...)
+    const int slotBase = SL_HW_DECIDE + parity * 2 * SL_MAX_PEERS;  // in 8-byte words from the start of the buffer
     if (t < nranks)
     {
         volatile double* slot = reinterpret_cast<double*>(peers.p[t]) + slotBase + 2 * rank;
@@ -405,6 +410,351 @@ __global__ void __launch_bounds__(SL_THREADS)
     }
 }
 
+// ---- rebuild-time exchange over peer memory ---------------------------------------------------------------------
+// Everything a rebuild sends (migrating atoms, the lists of face atoms) travels through the same IPC-mapped peer
+// buffers as the per-step halo, with the counts published next to the sequence flags, so that a rebuild costs two host
+// round trips (after the migration, to learn the new number of local atoms; after the neighbour build, for the list
+// statistics) instead of three NCCL rounds and eight stream synchronisations.  The unit of selection is a block of
+// `apm` consecutive atoms positioned by upos[] (the atom itself, or the centre of mass of a molecule).
+//
+// Two stable selections A and B of units, by one launch each of count / scan / index (blockIdx.y = list):
+//   MODE 0  migration: both over [0, n): A = flag < 0 (leaves to the left), B = flag > 0
+//   MODE 1  halo faces: A = units of the first cell column with x < lowBound, B = units of the last cell column with
+//           x >= highBound; the column ranges are read from the device-side cell prefix array (no host round trip)
+struct SelArgs
+{
+    const double4* upos;
+    const signed char* flag;
+    const int32_t* rangeA0;  // MODE 1: first / one-past-last unit of list A and B (device pointers)
+    const int32_t* rangeA1;
+    const int32_t* rangeB0;
+    const int32_t* rangeB1;
+    int64_t n;               // MODE 0: units
+    double lowBound, highBound;
+};
+
+template <int MODE>
+__device__ __forceinline__ bool selPredicate(const SelArgs& g, int list, int64_t j, int64_t& unit)
+{
+    if (MODE == 0)
+    {
+        unit = j;
+        if (j >= g.n) return false;
+        const signed char f = g.flag[j];
+        return list == 0 ? (f < 0) : (f > 0);
+    }
+    const int64_t first = list == 0 ? *g.rangeA0 : *g.rangeB0, last = list == 0 ? *g.rangeA1 : *g.rangeB1;
+    unit = first + j;
+    if (unit >= last) return false;
+    const double x = ld4nc(g.upos + unit).x;
+    return list == 0 ? (x < g.lowBound) : (x >= g.highBound);  // GhostExchange.cpp:80 / :89
+}
+
+__device__ __forceinline__ long long blockScan1(long long v, long long& total)
+{
+    __shared__ long long sWarp1[SL_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const long long y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) sWarp1[warp] = x;
+    __syncthreads();
+    long long off = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < SL_THREADS / 32; ++w)
+    {
+        const long long c = sWarp1[w];
+        if (w < warp) off += c;
+        tot += c;
+    }
+    __syncthreads();
+    total = tot;
+    return off + x - v;  // exclusive
+}
+
+// blockCounts[list * gridDim.x + block]
+template <int MODE>
+__global__ void __launch_bounds__(SL_THREADS) selCountKernel(SelArgs g, int64_t* blockCounts, int* err)
+{
+    const int list = blockIdx.y;
+    if (MODE == 1 && blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        // the grid was sized from an estimate of the column population: a fuller column must not go unnoticed
+        const int64_t len = list == 0 ? int64_t(*g.rangeA1) - *g.rangeA0 : int64_t(*g.rangeB1) - *g.rangeB0;
+        if (len > int64_t(gridDim.x) * blockDim.x) *err = 1;
+    }
+    const int64_t j = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    int64_t unit;
+    long long total;
+    blockScan1(selPredicate<MODE>(g, list, j, unit) ? 1 : 0, total);
+    if (threadIdx.x == 0) blockCounts[list * int64_t(gridDim.x) + blockIdx.x] = total;
+}
+
+// one block per list: exclusive scan of its block counts in place, total -> totals[list]
+__global__ void __launch_bounds__(SL_THREADS) selScanKernel(int64_t* blockCounts, int64_t numBlocks, int64_t* totals)
+{
+    int64_t* bc = blockCounts + blockIdx.x * numBlocks;
+    __shared__ long long sCarry;
+    if (threadIdx.x == 0) sCarry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < numBlocks; base += SL_THREADS)
+    {
+        const int64_t b = base + threadIdx.x;
+        const long long v = (b < numBlocks) ? bc[b] : 0;
+        long long total;
+        const long long excl = blockScan1(v, total);
+        if (b < numBlocks) bc[b] = excl + sCarry;
+        __syncthreads();
+        if (threadIdx.x == 0) sCarry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) totals[blockIdx.x] = sCarry;
+}
+
+// idx[list] receives the selected units in order; a list longer than cap raises err (the count stays the true one)
+template <int MODE>
+__global__ void __launch_bounds__(SL_THREADS)
+    selIndexKernel(SelArgs g, const int64_t* blockOffsets, int32_t* idxA, int32_t* idxB, int64_t cap, int* err)
+{
+    const int list = blockIdx.y;
+    const int64_t j = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    int64_t unit;
+    const bool sel = selPredicate<MODE>(g, list, j, unit);
+    long long total;
+    const long long at = blockOffsets[list * int64_t(gridDim.x) + blockIdx.x] + blockScan1(sel ? 1 : 0, total);
+    if (sel)
+    {
+        if (at < cap) (list == 0 ? idxA : idxB)[at] = static_cast<int32_t>(unit);
+        else *err = 1;
+    }
+}
+
+__device__ __forceinline__ void publishWhenLast(unsigned int* ticket, volatile long long* hdrL, volatile long long* hdrR,
+                                                long long countL, long long countR, long long seq)
+{
+    // the last block to finish publishes: every block's records are visible system wide before the flags are
+    __threadfence_system();
+    __shared__ bool sLastBlock;
+    __syncthreads();
+    if (threadIdx.x == 0) sLastBlock = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (sLastBlock && threadIdx.x == 0)
+    {
+        __threadfence_system();
+        hdrL[0] = countL;
+        hdrR[0] = countR;
+        __threadfence_system();
+        hdrL[1] = seq;
+        hdrR[1] = seq;
+        *ticket = 0;
+    }
+}
+
+// full records of the units leaving to the left / right -> the neighbours' migration regions, counts + sequence number
+// behind them.  counts: device {toLeft, toRight}; the grid covers 2 * cap units.
+__global__ void __launch_bounds__(SL_THREADS)
+    migratePushKernel(AtomsView a, int apm, const int32_t* __restrict__ idxA, const int32_t* __restrict__ idxB,
+                      const int64_t* __restrict__ counts, int64_t cap, double shiftL, double shiftR, double* dstL, double* dstR,
+                      long long* hdrL, long long* hdrR, long long seq, unsigned int* ticket)
+{
+    const int64_t k = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    const int64_t perList = cap * apm;
+    const int list = k < perList ? 0 : 1;
+    const int64_t kk = k - list * perList, unit = kk / apm;
+    const int64_t cnt = min(counts[list], cap);
+    if (kk < perList && unit < cnt)
+    {
+        const int64_t i = int64_t((list == 0 ? idxA : idxB)[unit]) * apm + kk % apm;
+        const double4 p = ld4(a.pos + i);
+        double* r = (list == 0 ? dstL : dstR) + kk * SL_RECORD;
+        r[0] = p.x + (list == 0 ? shiftL : shiftR);
+        r[1] = p.y;
+        r[2] = p.z;
+        r[3] = p.w;
+        for (int d = 0; d < 3; ++d)
+        {
+            r[4 + d] = a.vel[d][i];
+            r[7 + d] = a.force[d][i];
+        }
+        r[10] = a.mass[i];
+        r[11] = a.charge[i];
+        r[12] = a.relMass[i];
+        r[13] = __longlong_as_double(a.gid[i]);
+    }
+    publishWhenLast(ticket, hdrL, hdrR, counts[0], counts[1], seq);
+}
+
+// waits for both neighbours' records, appends them behind the n resident atoms (right neighbour's first, as the NCCL
+// path does), clears the flags of the arrivals and reports {toLeft, toRight, fromLeft, fromRight, seq} to pinned host
+// memory.  hdr: own header words SL_HW_MIG...; report: device copy of the counts for the kernels that follow.
+__global__ void __launch_bounds__(SL_THREADS)
+    migrateUnpackKernel(AtomsView a, int apm, int64_t n, const double* fromLeft, const double* fromRight,
+                        const long long* hdr, long long seq, int64_t cap, signed char* unitFlag, const int64_t* sent,
+                        int64_t* recvDev, volatile long long* hReport, int* err)
+{
+    if (threadIdx.x == 0)
+    {
+        const volatile long long* h = hdr;
+        while (h[1] < seq) {}
+        while (h[3] < seq) {}
+    }
+    __syncthreads();
+    __threadfence_system();
+    const long long cL = __ldcv(hdr), cR = __ldcv(hdr + 2);
+    const bool bad = cL > cap || cR > cap || sent[0] > cap || sent[1] > cap;
+    const int64_t k = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (!bad && k < (cL + cR) * apm)
+    {
+        const double* r = (k < cR * apm) ? fromRight + k * SL_RECORD : fromLeft + (k - cR * apm) * SL_RECORD;
+        double v[SL_RECORD];
+#pragma unroll
+        for (int q = 0; q < SL_RECORD; q += 2)
+        {
+            const double2 w = __ldcv(reinterpret_cast<const double2*>(r + q));  // written by another GPU: past L1
+            v[q] = w.x;
+            v[q + 1] = w.y;
+        }
+        const int64_t i = n + k;
+        st4(a.pos + i, make_double4(v[0], v[1], v[2], v[3]));
+        for (int d = 0; d < 3; ++d)
+        {
+            a.vel[d][i] = v[4 + d];
+            a.force[d][i] = v[7 + d];
+        }
+        a.mass[i] = v[10];
+        a.charge[i] = v[11];
+        a.relMass[i] = v[12];
+        a.gid[i] = __double_as_longlong(v[13]);
+        if (k % apm == 0) unitFlag[i / apm] = 0;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        recvDev[0] = cL;
+        recvDev[1] = cR;
+        if (bad) *err = 1;
+        hReport[0] = sent[0];
+        hReport[1] = sent[1];
+        hReport[2] = cL;
+        hReport[3] = cR;
+        hReport[5] = bad ? 1 : 0;
+        __threadfence_system();
+        hReport[4] = seq;
+    }
+}
+
+// the per-step halo with the counts on the device (rebuild flavour of haloPushKernel): also publishes the counts
+__global__ void __launch_bounds__(SL_THREADS)
+    haloPushCountedKernel(const double4* __restrict__ pos, const double4* __restrict__ upos, int apm,
+                          const int32_t* __restrict__ idxLow, const int32_t* __restrict__ idxHigh,
+                          const int64_t* __restrict__ counts, int64_t cap, double shiftL, double shiftR, double4* dstL,
+                          double4* dstR, unsigned long long* flagL, unsigned long long* flagR, long long* cntL, long long* cntR,
+                          unsigned long long seq, unsigned int* ticket)
+{
+    const int rec = apm + (apm > 1 ? 1 : 0);  // double4 per unit: the atoms' positions (+ the centre of mass)
+    const int64_t k = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    const int64_t perList = cap * rec;
+    const int list = k < perList ? 0 : 1;
+    const int64_t kk = k - list * perList, unit = kk / rec;
+    const int part = static_cast<int>(kk % rec);
+    if (kk < perList && unit < min(counts[list], cap))
+    {
+        const int64_t u = (list == 0 ? idxLow : idxHigh)[unit];
+        double4 p = (part < apm) ? ld4(pos + u * apm + part) : ld4(upos + u);
+        p.x += (list == 0 ? shiftL : shiftR);
+        st4((list == 0 ? dstL : dstR) + kk, p);
+    }
+    __threadfence_system();
+    __shared__ bool sLast;
+    __syncthreads();
+    if (threadIdx.x == 0) sLast = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (sLast && threadIdx.x == 0)
+    {
+        __threadfence_system();
+        *reinterpret_cast<volatile long long*>(cntL) = counts[0];
+        *reinterpret_cast<volatile long long*>(cntR) = counts[1];
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long*>(flagL) = seq;
+        *reinterpret_cast<volatile unsigned long long*>(flagR) = seq;
+        *ticket = 0;
+    }
+}
+
+// rebuild flavour of haloPullKernel: the counts come with the records; reports {sendLow, sendHigh, fromLeft, fromRight}
+__global__ void __launch_bounds__(SL_THREADS)
+    haloPullCountedKernel(const double4* fromLeft, const double4* fromRight, const unsigned long long* flags,
+                          const long long* cnt, unsigned long long seq, int apm, int64_t cap, double4* dstAtoms,
+                          double4* dstUnits, const int64_t* sent, int64_t* recvDev, volatile long long* hReport, int* err)
+{
+    if (threadIdx.x == 0)
+    {
+        const volatile unsigned long long* f = flags;
+        while (f[0] < seq) {}
+        while (f[1] < seq) {}
+    }
+    __syncthreads();
+    __threadfence_system();
+    const long long cL = __ldcv(cnt), cR = __ldcv(cnt + 2);
+    const bool bad = cL > cap || cR > cap || sent[0] > cap || sent[1] > cap;
+    const int rec = apm + (apm > 1 ? 1 : 0);
+    const int64_t k = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (!bad && k < (cL + cR) * rec)
+    {
+        const bool left = k < cL * rec;
+        const int64_t kk = left ? k : k - cL * rec;
+        const double2* q = reinterpret_cast<const double2*>((left ? fromLeft : fromRight) + kk);
+        const double2 lo = __ldcv(q), hi = __ldcv(q + 1);
+        const int64_t unit = (left ? 0 : cL) + kk / rec;
+        const int part = static_cast<int>(kk % rec);
+        if (part < apm) st4(dstAtoms + unit * apm + part, make_double4(lo.x, lo.y, hi.x, hi.y));
+        else st4(dstUnits + unit, make_double4(lo.x, lo.y, hi.x, hi.y));
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        recvDev[0] = cL;
+        recvDev[1] = cR;
+        if (bad) *err = 1;
+        hReport[8] = sent[0];
+        hReport[9] = sent[1];
+        hReport[10] = cL;
+        hReport[11] = cR;
+        hReport[13] = bad ? 1 : 0;
+        __threadfence_system();
+        hReport[12] = static_cast<long long>(seq);
+    }
+}
+
+// (j, k) cell keys of the received halo units and the prefix arrays of the two halo columns, counts on the device
+__global__ void haloKeyCountedKernel(const double4* upos, int64_t first, const int64_t* recv, GridDev g, uint32_t* keys)
+{
+    const int64_t k = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (k >= recv[0] + recv[1]) return;
+    const double4 p = ld4nc(upos + first + k);
+    keys[k] = static_cast<uint32_t>(locate1(g, p.y, 1) * g.n[2] + locate1(g, p.z, 2));
+}
+__global__ void haloCellStartCountedKernel(const uint32_t* keys, const int64_t* recv, int64_t numCells, int64_t first,
+                                           int32_t* startLeft, int32_t* startRight)
+{
+    const int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (c > numCells) return;
+    for (int side = 0; side < 2; ++side)
+    {
+        const uint32_t* ks = keys + (side == 0 ? 0 : recv[0]);
+        int64_t lo = 0, hi = recv[side];
+        while (lo < hi)
+        {
+            const int64_t mid = (lo + hi) >> 1;
+            if (int64_t(ks[mid]) < c) lo = mid + 1;
+            else hi = mid;
+        }
+        (side == 0 ? startLeft : startRight)[c] = static_cast<int32_t>(first + (side == 0 ? 0 : recv[0]) + lo);
+    }
+}
+
 // (j, k) cell of a halo atom in the receiver's grid (identical y / z grid on every rank)
 __global__ void haloKeyKernel(const double4* pos, int64_t first, int64_t n, GridDev g, uint32_t* keys)
 {
@@ -447,7 +797,14 @@ struct mrmd_b200_slab
     int64_t* hTotals = nullptr;  // pinned, 8 entries
     // per-step halo over peer memory (IPC): own buffer, the neighbours' buffers mapped into this process
     bool p2p = false;
-    int64_t p2pCap = 0;  // atoms per region
+    int apm = 1;             // atoms per unit of selection (1, or the atoms of a molecule)
+    int64_t p2pCap = 0;      // units per halo region
+    int64_t migCap = 0;      // units per migration region
+    int64_t colBound = 0;    // upper bound of the units in one cell column (grid of the face selection)
+    long long migSeq = 0;
+    long long* hReport = nullptr;  // pinned, 16 words: [0..5] migration {toL, toR, fromL, fromR, seq, err}, [8..13] halo lists
+    int* dErr = nullptr;
+    mrmd_b200::DevBuf migIdxA, migIdxB;
     double4* p2pBuf = nullptr;
     mrmd_b200::PeerBuffers peers{};  // every rank's buffer (own entry = p2pBuf)
     double4* peerLeftBuf = nullptr;
@@ -617,31 +974,92 @@ static int haloExchange(mrmd_b200_slab* sl, cudaStream_t st)
     return 0;
 }
 
-// positions of the boundary atoms -> neighbours' halo slots [n, n + haloLeft) and [n + haloLeft, ...)
+// ---- peer-memory data plane (host side) ------------------------------------------------------------------------
+static int unitRecord(const mrmd_b200_slab* sl) { return sl->apm + (sl->apm > 1 ? 1 : 0); }  // double4 per halo unit
+static int64_t haloRegionOffset(const mrmd_b200_slab* sl, int parity, int side)
+{
+    return SL_P2P_HEADER + int64_t(parity * 2 + side) * sl->p2pCap * unitRecord(sl);
+}
+static int64_t migRegionDoubles(const mrmd_b200_slab* sl) { return ((sl->migCap * sl->apm * SL_RECORD + 3) / 4) * 4; }
+static int64_t migRegionOffset(const mrmd_b200_slab* sl, int side)
+{
+    return haloRegionOffset(sl, 2, 0) + side * (migRegionDoubles(sl) / 4);
+}
+static long long* headerWords(double4* buf) { return reinterpret_cast<long long*>(buf); }
+// the position array the units are selected by, and its halo destination behind the local units
+static double4* unitPositions(mrmd_b200_slab* sl);
+
+// my face units -> the neighbours' halo regions of this sequence number's parity.  countsDev != nullptr (rebuild): the
+// counts were just produced on the device; otherwise the lists of the last rebuild are re-sent.
+static int haloPush(mrmd_b200_slab* sl, bool rebuild, cudaStream_t st)
+{
+    mrmd_b200_atoms* a = sl->atoms;
+    const unsigned long long seq = ++sl->haloSeq;
+    const int parity = static_cast<int>(seq & 1);
+    const int rec = unitRecord(sl);
+    if (!rebuild)
+        MB_REQUIRE(sl->sendLeftCount <= sl->p2pCap && sl->sendRightCount <= sl->p2pCap, "slab: the position halo exceeds the peer buffer");
+    // my low face goes to the left neighbour's "from right" region, my high face to the right neighbour's "from left"
+    double4* dstL = sl->peerLeftBuf + haloRegionOffset(sl, parity, 1);
+    double4* dstR = sl->peerRightBuf + haloRegionOffset(sl, parity, 0);
+    long long* hL = headerWords(sl->peerLeftBuf);
+    long long* hR = headerWords(sl->peerRightBuf);
+    const int64_t units = rebuild ? 2 * sl->p2pCap : sl->p2pCap + sl->sendRightCount;  // list 1 starts at unit p2pCap
+    haloPushCountedKernel<<<std::max(1, gridFor(units * rec, SL_THREADS)), SL_THREADS, 0, st>>>(
+        a->v.pos, unitPositions(sl), sl->apm, sl->idxLow.as<int32_t>(), sl->idxHigh.as<int32_t>(), sl->dTotals + 2, sl->p2pCap,
+        sl->shiftToLeft, sl->shiftToRight, dstL, dstR, reinterpret_cast<unsigned long long*>(hL + SL_HW_HALO + parity * 2 + 1),
+        reinterpret_cast<unsigned long long*>(hR + SL_HW_HALO + parity * 2 + 0), hL + SL_HW_HALOCOUNT + parity * 4 + 2,
+        hR + SL_HW_HALOCOUNT + parity * 4 + 0, seq, sl->dPushTicket);
+    MB_LAUNCHED();
+    return 0;
+}
+
+// the neighbours' face units of the current sequence number -> behind my local units
+static int haloPull(mrmd_b200_slab* sl, bool rebuild, cudaStream_t st)
+{
+    mrmd_b200_atoms* a = sl->atoms;
+    const unsigned long long seq = sl->haloSeq;
+    const int parity = static_cast<int>(seq & 1);
+    const int rec = unitRecord(sl);
+    const int64_t units = rebuild ? 2 * sl->p2pCap : sl->haloLeftCount + sl->haloRightCount;
+    const int64_t nUnits = a->numLocal / sl->apm;
+    long long* h = headerWords(sl->p2pBuf);
+    haloPullCountedKernel<<<std::max(1, gridFor(units * rec, SL_THREADS)), SL_THREADS, 0, st>>>(
+        sl->p2pBuf + haloRegionOffset(sl, parity, 0), sl->p2pBuf + haloRegionOffset(sl, parity, 1),
+        reinterpret_cast<const unsigned long long*>(h + SL_HW_HALO + parity * 2), h + SL_HW_HALOCOUNT + parity * 4, seq, sl->apm,
+        sl->p2pCap, a->v.pos + a->numLocal, unitPositions(sl) + nUnits, sl->dTotals + 2, sl->dTotals + 6, sl->hReport, sl->dErr);
+    MB_LAUNCHED();
+    return 0;
+}
+
+static int pollReport(mrmd_b200_slab* sl, int word, long long seq, cudaStream_t st, const char* what)
+{
+    volatile long long* h = sl->hReport;
+    for (unsigned spin = 0; h[word] != seq; ++spin)
+    {
+        if ((spin & 0xfff) == 0xfff)
+        {
+            const cudaError_t q = cudaStreamQuery(st);
+            if (q != cudaSuccess && q != cudaErrorNotReady) MB_CUDA(q);
+            if (q == cudaSuccess && h[word] != seq)
+            {
+                setLastError(std::string("slab: ") + what + " finished without a report");
+                return MRMD_B200_EINVAL;
+            }
+        }
+    }
+    return 0;
+}
+
+// positions of the boundary atoms -> neighbours' halo slots [n, n + haloLeft) and [n + haloLeft, ...) (NCCL path)
 static int haloRefresh(mrmd_b200_slab* sl, cudaStream_t st)
 {
     mrmd_b200_atoms* a = sl->atoms;
     const int64_t n = a->numLocal, nl = sl->sendLeftCount, nh = sl->sendRightCount;
     if (sl->p2p)
     {
-        MB_REQUIRE(nl <= sl->p2pCap && nh <= sl->p2pCap && sl->haloLeftCount <= sl->p2pCap && sl->haloRightCount <= sl->p2pCap,
-                   "slab: the position halo exceeds the peer buffer (density more than tripled since slab_create)");
-        const unsigned long long seq = ++sl->haloSeq;
-        // my low face goes to the left neighbour's "from right" region, my high face to the right neighbour's "from left"
-        double4* dstL = sl->peerLeftBuf + SL_P2P_HEADER + sl->p2pCap;
-        double4* dstR = sl->peerRightBuf + SL_P2P_HEADER;
-        unsigned long long* flagL = reinterpret_cast<unsigned long long*>(sl->peerLeftBuf) + 1;
-        unsigned long long* flagR = reinterpret_cast<unsigned long long*>(sl->peerRightBuf);
-        haloPushKernel<<<std::max(1, gridFor(nl + nh, SL_THREADS)), SL_THREADS, 0, st>>>(
-            a->v.pos, sl->idxLow.as<int32_t>(), nl, sl->shiftToLeft, dstL, flagL, sl->idxHigh.as<int32_t>(), nh,
-            sl->shiftToRight, dstR, flagR, seq, sl->dPushTicket);
-        MB_LAUNCHED();
-        const int64_t nIn = sl->haloLeftCount + sl->haloRightCount;
-        haloPullKernel<<<std::max(1, gridFor(nIn, SL_THREADS)), SL_THREADS, 0, st>>>(
-            sl->p2pBuf + SL_P2P_HEADER, sl->haloLeftCount, sl->p2pBuf + SL_P2P_HEADER + sl->p2pCap, sl->haloRightCount,
-            reinterpret_cast<const unsigned long long*>(sl->p2pBuf), seq, a->v.pos + n);
-        MB_LAUNCHED();
-        return 0;
+        MB_TRY(haloPush(sl, false, st));
+        return haloPull(sl, false, st);
     }
     MB_TRY(sl->sendBuf.reserve(size_t(std::max<int64_t>(nl + nh, 1)) * 32));
     double4* sb = sl->sendBuf.as<double4>();
@@ -668,9 +1086,127 @@ static int haloRefresh(mrmd_b200_slab* sl, cudaStream_t st)
     return 0;
 }
 
+static double4* unitPositions(mrmd_b200_slab* sl) { return sl->atoms->v.pos; }
+
+// The rebuild over peer memory: two host round trips (the migration counts, the list statistics).
+static int slabRebuildP2P(mrmd_b200_slab* sl, cudaStream_t st)
+{
+    mrmd_b200_atoms* a = sl->atoms;
+    const int apm = sl->apm;
+    const int64_t n = a->numLocal, nUnits = n / apm;
+    a->numGhost = 0;
+    a->size = n;
+    // room for the arrivals of the migration and, after it, for the halo units
+    MB_TRY(atomsEnsureCapacity(a, n + 2 * std::max(sl->migCap, sl->p2pCap) * apm, st));
+    MB_TRY(sl->flags.reserve(size_t(a->capacity) + 64));
+    const int blocksAll = std::max(1, gridFor(nUnits, SL_THREADS));
+    MB_TRY(sl->blockCounts.reserve(size_t(std::max<int64_t>(blocksAll, gridFor(sl->colBound, SL_THREADS))) * 16 + 64));
+    int64_t* bc = sl->blockCounts.as<int64_t>();
+    signed char* flag = sl->flags.as<signed char>();
+    MB_CUDA(cudaMemsetAsync(sl->dErr, 0, 4, st));
+    // ---- 1. wrap y / z, flag and list the leavers, push their records, take in the arrivals
+    if (n > 0)
+    {
+        slabWrapFlagKernel<<<gridFor(n, 256), 256, 0, st>>>(a->v.pos, n, toDev(sl->sub), flag);
+        MB_LAUNCHED();
+    }
+    SelArgs mig{};
+    mig.upos = unitPositions(sl);
+    mig.flag = flag;
+    mig.n = nUnits;
+    selCountKernel<0><<<dim3(blocksAll, 2), SL_THREADS, 0, st>>>(mig, bc, sl->dErr);
+    MB_LAUNCHED();
+    selScanKernel<<<2, SL_THREADS, 0, st>>>(bc, blocksAll, sl->dTotals);
+    MB_LAUNCHED();
+    selIndexKernel<0><<<dim3(blocksAll, 2), SL_THREADS, 0, st>>>(mig, bc, sl->migIdxA.as<int32_t>(), sl->migIdxB.as<int32_t>(),
+                                                                sl->migCap, sl->dErr);
+    MB_LAUNCHED();
+    const long long mseq = ++sl->migSeq;
+    {
+        double* dstL = reinterpret_cast<double*>(sl->peerLeftBuf + migRegionOffset(sl, 1));   // the left rank's "from right"
+        double* dstR = reinterpret_cast<double*>(sl->peerRightBuf + migRegionOffset(sl, 0));  // the right rank's "from left"
+        migratePushKernel<<<std::max(1, gridFor(2 * sl->migCap * apm, SL_THREADS)), SL_THREADS, 0, st>>>(
+            a->v, apm, sl->migIdxA.as<int32_t>(), sl->migIdxB.as<int32_t>(), sl->dTotals, sl->migCap, sl->shiftToLeft,
+            sl->shiftToRight, dstL, dstR, headerWords(sl->peerLeftBuf) + SL_HW_MIG + 2, headerWords(sl->peerRightBuf) + SL_HW_MIG,
+            mseq, sl->dPushTicket);
+        MB_LAUNCHED();
+        migrateUnpackKernel<<<std::max(1, gridFor(2 * sl->migCap * apm, SL_THREADS)), SL_THREADS, 0, st>>>(
+            a->v, apm, n, reinterpret_cast<const double*>(sl->p2pBuf + migRegionOffset(sl, 0)),
+            reinterpret_cast<const double*>(sl->p2pBuf + migRegionOffset(sl, 1)), headerWords(sl->p2pBuf) + SL_HW_MIG, mseq,
+            sl->migCap, flag, sl->dTotals, sl->dTotals + 4, sl->hReport, sl->dErr);
+        MB_LAUNCHED();
+    }
+    MB_TRY(pollReport(sl, 4, mseq, st, "migration"));  // host round trip 1: the new number of local atoms
+    MB_REQUIRE(sl->hReport[5] == 0, "slab: more atoms migrate in one rebuild than the peer buffer holds");
+    const int64_t nSend = (sl->hReport[0] + sl->hReport[1]) * apm, nRecv = (sl->hReport[2] + sl->hReport[3]) * apm;
+    // ---- 2. sort by linked cell; the leavers sort behind the last cell and are dropped
+    a->size = n + nRecv;
+    const double cutoff = sl->cfg.rc + sl->cfg.skin;
+    const double delta[3] = {cutoff, cutoff, 0.25 * cutoff};  // as md.cu: fine z order inside a cell column
+    MB_TRY(atomsCellSortDrop(a, 0, n + nRecv, delta, sl->sub.minCorner, sl->sub.maxCorner, flag, st));
+    a->numLocal = n + nRecv - nSend;
+    a->size = a->numLocal;
+    a->lcEnd = a->numLocal;
+    MB_TRY(atomsEnsureCapacity(a, a->numLocal + 2 * sl->p2pCap * apm, st));
+    // ---- 3. face lists from the first / last cell column (ranges read on the device), push, pull
+    const GridDev& g = a->lcGrid;
+    const int64_t perX = int64_t(g.n[1]) * g.n[2];
+    {
+        const int32_t* cs = a->lcCellStart.as<int32_t>();
+        SelArgs face{};
+        face.upos = unitPositions(sl);
+        face.rangeA0 = cs;
+        face.rangeA1 = cs + perX;
+        face.rangeB0 = cs + (int64_t(g.n[0]) - 1) * perX;
+        face.rangeB1 = cs + a->lcNumCells;
+        face.lowBound = sl->sub.minInnerCorner[0];   // low face: x < minInner within column 0
+        face.highBound = sl->sub.maxInnerCorner[0];  // high face: x >= maxInner within column nx-1
+        const int blocksCol = std::max(1, gridFor(sl->colBound, SL_THREADS));
+        selCountKernel<1><<<dim3(blocksCol, 2), SL_THREADS, 0, st>>>(face, bc, sl->dErr);
+        MB_LAUNCHED();
+        selScanKernel<<<2, SL_THREADS, 0, st>>>(bc, blocksCol, sl->dTotals + 2);
+        MB_LAUNCHED();
+        selIndexKernel<1><<<dim3(blocksCol, 2), SL_THREADS, 0, st>>>(face, bc, sl->idxLow.as<int32_t>(), sl->idxHigh.as<int32_t>(),
+                                                                    sl->p2pCap, sl->dErr);
+        MB_LAUNCHED();
+    }
+    MB_TRY(haloPush(sl, true, st));
+    MB_TRY(haloPull(sl, true, st));
+    // ---- 4. linked cells of the received halo units (they arrive in (j, k) order), tiled neighbour build
+    MB_TRY(sl->haloKeys.reserve(size_t(2 * sl->p2pCap) * 4));
+    MB_TRY(sl->haloStartLeft.reserve(size_t(perX + 1) * 4));
+    MB_TRY(sl->haloStartRight.reserve(size_t(perX + 1) * 4));
+    haloKeyCountedKernel<<<gridFor(2 * sl->p2pCap, 256), 256, 0, st>>>(unitPositions(sl), a->numLocal / apm, sl->dTotals + 6, g,
+                                                                      sl->haloKeys.as<uint32_t>());
+    MB_LAUNCHED();
+    haloCellStartCountedKernel<<<gridFor(perX + 1, 256), 256, 0, st>>>(sl->haloKeys.as<uint32_t>(), sl->dTotals + 6, perX,
+                                                                      a->numLocal / apm, sl->haloStartLeft.as<int32_t>(),
+                                                                      sl->haloStartRight.as<int32_t>());
+    MB_LAUNCHED();
+    MB_TRY(verletBuildTiled(sl->list, a, &sl->sub, cutoff, 1.0, sl->cfg.maxNeighbors, sl->haloStartLeft.as<int32_t>(),
+                            sl->haloStartRight.as<int32_t>(), st));  // host round trip 2 (list statistics)
+    MB_TRY(pollReport(sl, 12, static_cast<long long>(sl->haloSeq), st, "halo exchange"));
+    MB_REQUIRE(sl->hReport[13] == 0, "slab: the position halo exceeds the peer buffer (density more than tripled since slab_create)");
+    MB_CUDA(cudaMemcpyAsync(sl->hTotals, sl->dErr, 4, cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaStreamSynchronize(st));
+    MB_REQUIRE(*reinterpret_cast<int*>(sl->hTotals) == 0, "slab: a selection list exceeded its capacity during the rebuild");
+    sl->sendLeftCount = sl->hReport[8];
+    sl->sendRightCount = sl->hReport[9];
+    sl->haloLeftCount = sl->hReport[10];
+    sl->haloRightCount = sl->hReport[11];
+    a->numGhost = (sl->haloLeftCount + sl->haloRightCount) * apm;
+    a->size = a->numLocal + a->numGhost;
+    int64_t total = 0;
+    MB_TRY(mrmd_b200_verlet_info(sl->list, nullptr, nullptr, &total, nullptr));
+    sl->storedPairsNow = total;
+    sl->rebuilds += 1;
+    return 0;
+}
+
 static int slabRebuild(mrmd_b200_slab* sl, cudaStream_t st)
 {
     mrmd_b200_atoms* a = sl->atoms;
+    if (sl->p2p) return slabRebuildP2P(sl, st);
     MB_TRY(migrate(sl, st));
     MB_TRY(haloExchange(sl, st));
     MB_TRY(haloRefresh(sl, st));
@@ -705,13 +1241,19 @@ static int slabRebuild(mrmd_b200_slab* sl, cudaStream_t st)
 static int setupPeerHalo(mrmd_b200_slab* sl, double cutoff, double width)
 {
     // face atoms ~ numLocal * cutoff / width; three times that, the same on every rank
-    const double estimate = 3.0 * double(sl->atoms->numLocal) * cutoff / std::max(width, cutoff) + 4096.0;
+    const double estimate = 3.0 * double(sl->atoms->numLocal / sl->apm) * cutoff / std::max(width, cutoff) + 4096.0;
     sl->hScalars[0] = estimate;
     MB_CUDA(cudaMemcpy(sl->dScalars, sl->hScalars, 8, cudaMemcpyHostToDevice));
     MB_NCCL(g_nccl.allReduce(sl->dScalars, sl->dScalars, 1, ncclDouble, ncclMax, sl->comm, nullptr));
     MB_CUDA(cudaMemcpy(sl->hScalars, sl->dScalars, 8, cudaMemcpyDeviceToHost));
-    const int64_t cap = (static_cast<int64_t>(sl->hScalars[0]) + 63) & ~int64_t(63);
-    const size_t bytes = size_t(SL_P2P_HEADER + 2 * cap) * 32;
+    const int64_t cap = (static_cast<int64_t>(sl->hScalars[0]) + 63) & ~int64_t(63);  // units per halo region
+    sl->p2pCap = cap;
+    // migrating units per rebuild and face: those within the displacement bound of a face, a small fraction of the face
+    // layer; sized like it anyway (the same on every rank)
+    sl->migCap = cap / 4 + 4096;
+    // units of one cell column (the face selection runs over the first and last column): three times the mean
+    sl->colBound = cap + 4096;
+    const size_t bytes = size_t(migRegionOffset(sl, 2)) * 32;
     double4* buf = nullptr;
     cudaIpcMemHandle_t mine;
     bool ok = cudaMalloc(&buf, bytes) == cudaSuccess && cudaMemset(buf, 0, bytes) == cudaSuccess &&
@@ -753,10 +1295,17 @@ static int setupPeerHalo(mrmd_b200_slab* sl, double cutoff, double width)
     sl->p2pBuf = buf;
     sl->peerLeftBuf = static_cast<double4*>(pl);
     sl->peerRightBuf = static_cast<double4*>(pr);
-    sl->p2pCap = cap;
     sl->p2p = sl->hScalars[0] > 0.5;
     if (sl->p2p)
     {
+        MB_CUDA(cudaMallocHost(&sl->hReport, 16 * 8));
+        std::memset(sl->hReport, 0, 16 * 8);
+        MB_CUDA(cudaMalloc(&sl->dErr, 4));
+        MB_CUDA(cudaMemset(sl->dErr, 0, 4));
+        MB_TRY(sl->migIdxA.reserve(size_t(sl->migCap) * 4));
+        MB_TRY(sl->migIdxB.reserve(size_t(sl->migCap) * 4));
+        MB_TRY(sl->idxLow.reserve(size_t(sl->p2pCap) * 4));
+        MB_TRY(sl->idxHigh.reserve(size_t(sl->p2pCap) * 4));
         MB_CUDA(cudaMalloc(&sl->dPushTicket, 4));
         MB_CUDA(cudaMemset(sl->dPushTicket, 0, 4));
         MB_CUDA(cudaMallocHost(&sl->hDecide, 16));
@@ -797,6 +1346,11 @@ static int slabStep(mrmd_b200_slab* sl, cudaStream_t st, cudaEvent_t e0, cudaEve
                         uint64_t(sl->step), nullptr, sl->postPending, st));
     sl->postPending = false;
     sl->prof[0] += profMark(sl, st, last);
+    // the positions are final: the face atoms leave for the neighbours right away, so that the NVLink transfer overlaps
+    // the rebuild decision (double-buffered regions; a push that a rebuild supersedes is simply never pulled).  Before
+    // the first rebuild there are no lists yet.
+    const bool earlyPush = sl->p2p && sl->rebuilds > 0;
+    if (earlyPush) MB_TRY(haloPush(sl, false, st));
     // the rebuild decision is collective: global maximum of the squared displacement
     if (sl->p2p)
     {
@@ -835,7 +1389,8 @@ static int slabStep(mrmd_b200_slab* sl, cudaStream_t st, cudaEvent_t e0, cudaEve
     }
     else
     {
-        MB_TRY(haloRefresh(sl, st));
+        if (earlyPush) MB_TRY(haloPull(sl, false, st));
+        else MB_TRY(haloRefresh(sl, st));
         sl->prof[3] += profMark(sl, st, last);
     }
     if (evPosReady != nullptr) MB_CUDA(cudaEventRecord(evPosReady, st));  // positions and atom order are final
@@ -1020,6 +1575,10 @@ int mrmd_b200_slab_destroy(mrmd_b200_slab* sl)
     for (int r = 0; r < SL_MAX_PEERS && r < sl->nranks; ++r)
         if (sl->peers.p[r] != nullptr && r != sl->rank) cudaIpcCloseMemHandle(sl->peers.p[r]);
     if (sl->hDecide != nullptr) cudaFreeHost(sl->hDecide);
+    if (sl->hReport != nullptr) cudaFreeHost(sl->hReport);
+    if (sl->dErr != nullptr) cudaFree(sl->dErr);
+    sl->migIdxA.release();
+    sl->migIdxB.release();
     if (sl->p2pBuf != nullptr) cudaFree(sl->p2pBuf);
     if (sl->dPushTicket != nullptr) cudaFree(sl->dPushTicket);
     mrmd_b200_lj_destroy(sl->lj);
