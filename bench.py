@@ -272,8 +272,8 @@ def workload_config(workload, side, side_x, equil, full_list, gpus, replicas, n_
     tet = ("AdResS Lennard-Jones tetramers (configs[3]): molecule centres on an sc lattice of spacing 1.98425 (atom density "
            "0.512), regular tetrahedra of edge 1, 4 atoms per molecule (relMass 1/4), Spherical(centre, R 0.189 L, h 0.0945 "
            "L, exponent 2) = R 60 / h 30 at 16.4M atoms, LJ_IdealGas(cap 0.7, rc 2.5, shift), MoleculeConstraints(4, 3) "
-           "on the six bonds (SHAKE / RATTLE), Langevin gamma=20 T=1.5, dt=0.002, skin 0.1, Verlet list of molecules, "
-           "maxNeighbors 40")
+           "on the six bonds (SHAKE / RATTLE), Langevin gamma=20 T=1.5, dt=0.002, skin 0.1, tiled Verlet list of the "
+           "molecules' centres of mass, maxNeighbors 40")
     sp = SPACING[workload]
     sx = side_x or side
     if gpus == 1:
@@ -342,8 +342,6 @@ def run_case(ctx, workload, side, side_x, steps, warmup, equil, full_list=2, bal
     tetramer = workload == "tetramer"
     adress = workload in ("adress", "tetramer")
     apm = 4 if tetramer else 1
-    if tetramer and not slab_mode:
-        full_list = 0  # single GPU: half Verlet list of molecules over materialised ghost molecules (reference semantics)
     sites_x = side_x or side
     spacing = SPACING[workload]
     global_lx = world * sites_x * spacing if slab_mode else sites_x * spacing
@@ -391,7 +389,8 @@ def run_case(ctx, workload, side, side_x, steps, warmup, equil, full_list=2, bal
         uid = slabs.broadcast_unique_id(rank)
         md = slabs.SlabMolecularDynamics(atoms, np.zeros(3), global_box, rank, world, uid, cuts=cuts, **common, **extra)
     else:
-        md = api.MolecularDynamics(atoms, sub, cellSort=not tetramer, fullList=int(full_list), **common, **extra)
+        md = api.MolecularDynamics(atoms, sub, cellSort=not (tetramer and full_list == 0), fullList=int(full_list), **common,
+                                   **extra)
 
     md.run(equil, stream=stream)            # untimed: melt the lattice
     md.run(max(warmup, 3), stream=stream)   # warm-up
@@ -447,7 +446,7 @@ def run_case(ctx, workload, side, side_x, steps, warmup, equil, full_list=2, bal
     if tetramer:
         # the same formula with a = 4 and M = n / 4 molecules
         algo_bytes = (84.0 + 224.0) * (n / 4) * steps + 12.0 * stored_half + 288.0 * stats["activePairs"]
-        kernel_name = ("tetramerForceTiledKernel" if full_list == 2 else
+        kernel_name = ("moleculeForceTiledKernel" if full_list == 2 else
                        "adressActiveMoleculesKernel + adressForceLanes4Kernel")
     force_ms = stats["forceKernelMs"]
     n_kernel, kernel_rank, stored_kernel = n, rank, stats["storedPairs"]

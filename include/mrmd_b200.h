@@ -256,6 +256,19 @@ int mrmd_b200_verlet_build_periodic(mrmd_b200_verlet* v, const mrmd_b200_atoms* 
  * host buffers of numLocal (x width) int32, -1 padded */
 int mrmd_b200_verlet_read_periodic(const mrmd_b200_verlet* v, const mrmd_b200_atoms* a, int32_t* countsHost,
                                    int32_t* partnerHost, int32_t* shiftCodeHost, void* stream);
+/* The periodic list for molecules of atomsPerMolecule consecutive atoms (atomsOffset = atomsPerMolecule * m): the reference
+ * builds the molecule list on the centres of mass over MultiResGhostLayer ghosts; here
+ * mrmd_b200_molecules_cell_sort_with_atoms is LinkedCellList + permute on the centres of mass of the local molecules (the
+ * atoms move in blocks of atomsPerMolecule, all members; the centres of mass move along), and the list is built on
+ * tiles of the sorted centres of mass with the periodic images generated on the fly, like
+ * mrmd_b200_verlet_build_periodic.  UpdateMolecules::update must have filled the centres of mass before the sort. */
+int mrmd_b200_molecules_cell_sort_with_atoms(mrmd_b200_molecules* m, mrmd_b200_atoms* a, int atomsPerMolecule,
+                                             const double* delta, const double* gridMin, const double* gridMax, void* stream);
+int mrmd_b200_verlet_build_periodic_molecules(mrmd_b200_verlet* v, mrmd_b200_molecules* m, const mrmd_b200_subdomain* s,
+                                              double radius, double cellRatio, int64_t maxNeigh, int atomsPerMolecule,
+                                              void* stream);
+int mrmd_b200_verlet_read_periodic_molecules(const mrmd_b200_verlet* v, const mrmd_b200_molecules* m, int32_t* countsHost,
+                                             int32_t* partnerHost, int32_t* shiftCodeHost, void* stream);
 /* list._data.counts / neighbors as a Cabana VerletLayout2D table: counts[numParticles] int32 and
  * neighbors[numParticles][width] int32 (row-major).  Pass NULL to query sizes only. */
 int mrmd_b200_verlet_info(const mrmd_b200_verlet* v, int64_t* numParticles, int64_t* width, int64_t* totalPairs,
@@ -312,6 +325,14 @@ int mrmd_b200_adress_run(mrmd_b200_adress* ad, mrmd_b200_molecules* m, const mrm
  * periodic faces the weight depends on (x for Slab, all for Spherical); otherwise MRMD_B200_EINVAL. */
 int mrmd_b200_adress_run_periodic(mrmd_b200_adress* ad, mrmd_b200_atoms* a, const mrmd_b200_verlet* v,
                                   const mrmd_b200_weight* w, double* energy, int64_t* numPairs, void* stream);
+/* The same fast path for molecules of atomsPerMolecule (4: the tetramers of BASELINE.json configs[3]) consecutive atoms
+ * with atomsOffset = atomsPerMolecule * m: v is a list from mrmd_b200_verlet_build_periodic_molecules on the centres of
+ * mass in m (UpdateMolecules::update must have run: pos holds them), the force kernel stages all atoms of a molecule
+ * per list slot, evaluates the weight at the (image) centre of mass and runs LJ_IdealGas::run (LJ_IdealGas.cpp:96-225)
+ * and ContributeMoleculeForceToAtoms::update from the row owner's side: no atomics on forces, no ghost molecules. */
+int mrmd_b200_adress_run_periodic_molecules(mrmd_b200_adress* ad, const mrmd_b200_molecules* m, mrmd_b200_atoms* a,
+                                            const mrmd_b200_verlet* v, const mrmd_b200_weight* w, int atomsPerMolecule,
+                                            double* energy, int64_t* numPairs, void* stream);
 /* getMeanCompensationEnergy() and the two accumulation histograms, 200 x numTypes doubles each
  * (kind 0 mean, 1 compensationEnergy, 2 compensationEnergyCounter) */
 int mrmd_b200_adress_read_histogram(const mrmd_b200_adress* ad, int kind, double* dstHost, void* stream);

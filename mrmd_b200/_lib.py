@@ -167,6 +167,10 @@ SIGNATURES = {
     "mrmd_b200_md_destroy": (C.c_int, [vp]),
     "mrmd_b200_md_run": (C.c_int, [vp, i64, C.c_int, C.POINTER(MdStats), vp]),
     "mrmd_b200_md_run_host": (C.c_int, [vp, i64, vp, vp, vp, C.POINTER(MdStats), vp]),
+    "mrmd_b200_molecules_cell_sort_with_atoms": (C.c_int, [vp, vp, C.c_int, vp, vp, vp, vp]),
+    "mrmd_b200_verlet_build_periodic_molecules": (C.c_int, [vp, vp, pSub, dbl, dbl, i64, C.c_int, vp]),
+    "mrmd_b200_verlet_read_periodic_molecules": (C.c_int, [vp, vp, vp, vp, vp, vp]),
+    "mrmd_b200_adress_run_periodic_molecules": (C.c_int, [vp, vp, vp, vp, pWeight, C.c_int, pdbl, pi64, vp]),
     "mrmd_b200_md_set_energy_every_step": (C.c_int, [vp, C.c_int]),
     "mrmd_b200_slab_set_energy_every_step": (C.c_int, [vp, C.c_int]),
     "mrmd_b200_slab_run_host": (C.c_int, [vp, i64, vp, vp, vp, C.POINTER(MdStats), vp]),

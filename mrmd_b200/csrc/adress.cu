@@ -636,9 +636,50 @@ int adressRunPeriodic(mrmd_b200_adress* ad, mrmd_b200_atoms* a, const mrmd_b200_
     ad->runCounter += 1;
     return 0;
 }
+
+int adressRunPeriodicMolecules(mrmd_b200_adress* ad, const mrmd_b200_molecules* m, mrmd_b200_atoms* a,
+                               const mrmd_b200_verlet* v, const mrmd_b200_weight* w, int atomsPerMolecule, bool energy,
+                               cudaStream_t st)
+{
+    MB_REQUIRE(ad != nullptr && m != nullptr && a != nullptr && v != nullptr && w != nullptr, "adress_run_periodic_molecules");
+    MB_REQUIRE(v->tiled, "adress_run_periodic_molecules: needs a list from mrmd_b200_verlet_build_periodic_molecules");
+    MB_REQUIRE(v->numParticles == m->numLocal && m->numLocal * atomsPerMolecule == a->numLocal,
+               "adress_run_periodic_molecules: list rows != local molecules, or atoms != atomsPerMolecule x molecules");
+    const bool sampling = (ad->runCounter % ad->samplingInterval) == 0;
+    if (m->numLocal > 0)
+        MB_TRY(moleculeApplyTiled(ad, m, a, v, w, atomsPerMolecule, sampling, energy, st));
+    else
+        MB_CUDA(cudaMemsetAsync(ad->dResult, 0, 24, st));
+    if (ad->runCounter % ad->updateInterval == 0)
+    {
+        const int64_t n = COMPENSATION_ENERGY_BINS * ad->numTypes;
+        if (ad->preUpdateHook != nullptr) MB_TRY(ad->preUpdateHook(ad->hookCtx, ad->hist, 2 * n, st));
+        updateMeanCompensationKernel<<<gridFor(n, 128), 128, 0, st>>>(ad->hist, n, 10.0);
+        MB_LAUNCHED();
+    }
+    ad->runCounter += 1;
+    return 0;
+}
 }  // namespace mrmd_b200
 
 extern "C" {
+
+int mrmd_b200_adress_run_periodic_molecules(mrmd_b200_adress* ad, const mrmd_b200_molecules* m, mrmd_b200_atoms* a,
+                                            const mrmd_b200_verlet* v, const mrmd_b200_weight* w, int atomsPerMolecule,
+                                            double* energy, int64_t* numPairs, void* stream)
+{
+    MB_TRY(checkDevice());
+    cudaStream_t st = S(stream);
+    MB_TRY(adressRunPeriodicMolecules(ad, m, a, v, w, atomsPerMolecule, energy != nullptr, st));
+    if (energy != nullptr || numPairs != nullptr)
+    {
+        MB_CUDA(cudaMemcpyAsync(ad->hResult, ad->dResult, 24, cudaMemcpyDeviceToHost, st));
+        MB_CUDA(cudaStreamSynchronize(st));
+        if (energy) *energy = ad->hResult[0];
+        if (numPairs) *numPairs = static_cast<int64_t>(ad->hResult[1] + 0.5);
+    }
+    return 0;
+}
 
 int mrmd_b200_adress_read_histogram(const mrmd_b200_adress* ad, int kind, double* dstHost, void* stream)
 {

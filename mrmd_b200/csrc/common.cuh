@@ -213,6 +213,10 @@ struct mrmd_b200_molecules
     int64_t altCapacity = 0;
     mrmd_b200::DevBuf staging;
     mrmd_b200::DevBuf sortScratch;
+    // Linked-cell structure of the molecules' centres of mass left behind by moleculesCellSortWithAtoms, kept in an
+    // atoms-shaped view (pos = the molecules' pos plane, numLocal = local molecules, no other plane) so that the tiled
+    // neighbour build runs on molecules unchanged.  Created on first use, owned by the molecules handle.
+    mrmd_b200_atoms* lcView = nullptr;
 };
 
 struct mrmd_b200_verlet
@@ -241,6 +245,10 @@ struct mrmd_b200_verlet
     int tiledCH = 0;
     int tiledSlots = 0;
     int tiledGridN[3] = {0, 0, 0};  // grid the tile geometry (CH, slots) was chosen for: re-used while it stays the same
+    // tile sizing: home units per tile aimed at, and the shared-memory bytes per staged slot of the largest consumer
+    // (24 for atoms; molecule lists stage all atoms of a molecule per slot in the force kernel)
+    int tiledTargetHomes = 110;
+    int tiledSlotBytes = 24;
     mrmd_b200::DevBuf tstats;    // int32[4]: max slots per tile, -, overflow flag
     int* hTstats = nullptr;      // pinned
     mrmd_b200::DevBuf keys[2];  // radix sort ping-pong

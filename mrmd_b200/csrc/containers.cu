@@ -646,6 +646,11 @@ int mrmd_b200_molecules_destroy(mrmd_b200_molecules* m)
     if (m->alt.pos) cudaFree(m->alt.pos);
     m->staging.release();
     m->sortScratch.release();
+    if (m->lcView != nullptr)
+    {
+        m->lcView->lcCellStart.release();
+        delete m->lcView;
+    }
     delete m;
     return 0;
 }

@@ -78,6 +78,16 @@ int ljApplyTiled(mrmd_b200_lj* lj, mrmd_b200_atoms* a, const mrmd_b200_verlet* v
                  cudaStream_t st);
 int adressApplyTiled(mrmd_b200_adress* ad, mrmd_b200_atoms* a, const mrmd_b200_verlet* v, const mrmd_b200_weight* w,
                      bool sampling, bool energy, cudaStream_t st);
+// tiled.cu / adress.cu: LJ_IdealGas over a tiled list of the centres of mass of molecules of atomsPerMolecule atoms
+int moleculeApplyTiled(mrmd_b200_adress* ad, const mrmd_b200_molecules* m, mrmd_b200_atoms* a, const mrmd_b200_verlet* v,
+                       const mrmd_b200_weight* w, int atomsPerMolecule, bool sampling, bool energy, cudaStream_t st);
+int adressRunPeriodicMolecules(mrmd_b200_adress* ad, const mrmd_b200_molecules* m, mrmd_b200_atoms* a,
+                               const mrmd_b200_verlet* v, const mrmd_b200_weight* w, int atomsPerMolecule, bool energy,
+                               cudaStream_t st);
+// tiled.cu: the tiled list on the cell-sorted centres of mass (moleculesCellSortWithAtoms); halo arguments as verletBuildTiled
+int verletBuildTiledMolecules(mrmd_b200_verlet* v, mrmd_b200_molecules* m, const mrmd_b200_subdomain* s, double radius,
+                              double cellRatio, int64_t maxNeigh, int atomsPerMolecule, const int32_t* haloLeft,
+                              const int32_t* haloRight, cudaStream_t st);
 // adress.cu: mrmd_b200_adress_run_periodic with the energy accumulation optional (the drivers want it on the last
 // step of a run only)
 // adress.cu: reads the atoms-per-molecule flag of the four-lane kernel back (synchronises the stream)
@@ -91,6 +101,9 @@ int constraintsEnforceVelocity(mrmd_b200_constraints* c, const mrmd_b200_molecul
                                double postDt);
 // promise of the step-loop drivers: uniform molecules that own every local atom (lets postForceIntegrate ride along)
 void constraintsSetUniformMolecules(mrmd_b200_constraints* c, bool uniform);
+// neighbor.cu: LinkedCellList + permute on the centres of mass of molecules of apm consecutive atoms (see there)
+int moleculesCellSortWithAtoms(mrmd_b200_molecules* m, mrmd_b200_atoms* a, int64_t count, int apm, const double* delta,
+                               const double* gridMin, const double* gridMax, const signed char* dropFlags, cudaStream_t st);
 int verletBuildTiled(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, const mrmd_b200_subdomain* s, double radius,
                      double cellRatio, int64_t maxNeigh, const int32_t* haloLeft, const int32_t* haloRight,
                      cudaStream_t st);

@@ -61,6 +61,21 @@ static int rebuild(mrmd_b200_md* md, cudaStream_t st)
         a->size = a->numLocal;
         MB_TRY(mrmd_b200_molecules_update(m, a, &c.weight, st));
         MB_TRY(mrmd_b200_ghost_mr_map_into_domain(m, a, &md->sub, st));
+        if (c.fullList == 2 && c.atomsPerMolecule > 1)
+        {
+            // fast path for molecules of atomsPerMolecule consecutive atoms: the centres of mass of the wrapped atoms
+            // (UpdateMolecules::update, as the reference recomputes them before its list build), LinkedCellList +
+            // permute on them with the atoms moving in blocks, the tiled list on the sorted centres of mass
+            const int apm = static_cast<int>(c.atomsPerMolecule);
+            MB_TRY(mrmd_b200_molecules_update(m, a, &c.weight, st));
+            MB_TRY(moleculesCellSortWithAtoms(m, a, m->numLocal, apm, delta, md->sub.minCorner, md->sub.maxCorner, nullptr, st));
+            MB_TRY(verletBuildTiledMolecules(md->list, m, &md->sub, cutoff, 1.0, c.maxNeighbors, apm, nullptr, nullptr, st));
+            int64_t total = 0;
+            MB_TRY(mrmd_b200_verlet_info(md->list, nullptr, nullptr, &total, nullptr));
+            md->storedPairsNow = total;
+            md->rebuilds += 1;
+            return 0;
+        }
         if (c.fullList == 2)
         {
             // fast path: one-atom molecules are their atoms, the tiled list over the sorted atoms is the molecule
@@ -157,6 +172,20 @@ static int oneStep(mrmd_b200_md* md, cudaStream_t st, cudaEvent_t evStart, cudaE
         if (c.adress) MB_TRY(mrmd_b200_molecules_update(md->mols, a, &c.weight, st));
     }
     if (evPosReady != nullptr) MB_CUDA(cudaEventRecord(evPosReady, st));  // positions and atom order are final
+    if (c.fullList == 2 && c.adress && c.atomsPerMolecule > 1)
+    {
+        // tiled AdResS step for multi-atom molecules: centres of mass, then LJ_IdealGas + ContributeMoleculeForceToAtoms
+        // as one kernel over the molecule list (mrmd_b200_adress_run_periodic_molecules)
+        MB_TRY(mrmd_b200_molecules_update(md->mols, a, &c.weight, st));
+        MB_TRY(mrmd_b200_atoms_fill(a, MRMD_B200_ATOM_FORCE, 0.0, st));
+        if (evStart) MB_CUDA(cudaEventRecord(evStart, st));
+        MB_TRY(adressRunPeriodicMolecules(md->adress, md->mols, a, md->list, &c.weight, static_cast<int>(c.atomsPerMolecule),
+                                          wantEnergy, st));
+        if (evStop) MB_CUDA(cudaEventRecord(evStop, st));
+        MB_TRY(postIntegrate(md, deferPost, st));
+        md->step += 1;
+        return 0;
+    }
     if (c.fullList == 2 && c.adress)
     {
         // tiled AdResS step: thermodynamic force on the zeroed force, then UpdateMolecules + LJ_IdealGas +
@@ -285,8 +314,10 @@ int mrmd_b200_md_create(mrmd_b200_md** out, const mrmd_b200_md_config* cfg, cons
     MB_REQUIRE(cfg->dt > 0.0 && cfg->rc > 0.0 && cfg->skin >= 0.0 && cfg->maxNeighbors > 0, "md_create: bad config");
     MB_REQUIRE(!(cfg->adress && cfg->fullList == 1), "md_create: LJ_IdealGas takes a half list (0) or the tiled list (2)");
     const int64_t apm = std::max<int64_t>(cfg->atomsPerMolecule, 1);
-    MB_REQUIRE(apm == 1 || (cfg->adress && cfg->fullList == 0 && cfg->cellSort == 0),
-               "md_create: multi-atom molecules need adress = 1, fullList = 0, cellSort = 0");
+    MB_REQUIRE(apm == 1 || (cfg->adress && ((cfg->fullList == 0 && cfg->cellSort == 0) || (cfg->fullList == 2 && apm == 4))),
+               "md_create: multi-atom molecules need adress = 1 and fullList = 0 with cellSort = 0, or fullList = 2 (tiled "
+               "list on the centres of mass) with four atoms per molecule");
+    MB_REQUIRE(!(apm > 1 && cfg->fullList == 2 && cfg->useThermoForce), "md_create: no thermodynamic force on the tiled molecule path");
     MB_REQUIRE(atoms->numLocal % apm == 0, "md_create: local atoms are not a multiple of atomsPerMolecule");
     MB_REQUIRE(cfg->numConstraintIterations >= 0 && (cfg->numConstraintIterations == 0 || (apm > 1 && cfg->bondLength > 0.0)),
                "md_create: constraints need multi-atom molecules and a positive bond length");
@@ -309,7 +340,7 @@ int mrmd_b200_md_create(mrmd_b200_md** out, const mrmd_b200_md_config* cfg, cons
         rc = mrmd_b200_adress_create(&md->adress, &cfg->cappingDistance, &cfg->rc, &cfg->sigma, &cfg->epsilon, 1,
                                      cfg->doShift);
         // four-lane kernel; MRMD_B200_ADRESS_NO_LANES=1 keeps the thread-per-molecule kernel (diagnostics)
-        if (rc == 0 && apm == 4 && std::getenv("MRMD_B200_ADRESS_NO_LANES") == nullptr)
+        if (rc == 0 && apm == 4 && cfg->fullList == 0 && std::getenv("MRMD_B200_ADRESS_NO_LANES") == nullptr)
             rc = mrmd_b200_adress_set_atoms_per_molecule(md->adress, 4);
         const int64_t numMols = atoms->numLocal / apm;
         if (rc == 0) rc = mrmd_b200_molecules_create(&md->mols, std::max<int64_t>(numMols, 1));

@@ -258,6 +258,30 @@ __global__ void permuteAtomsKernel(AtomsView dst, AtomsView src, const uint32_t*
     dst.gid[i] = src.gid[s];
 }
 
+// molecules of apm consecutive atoms: atom block k of the new arrays receives block perm[k] (all members)
+__global__ void permuteAtomBlocksKernel(AtomsView dst, AtomsView src, const uint32_t* perm, int64_t numBlocks, int apm)
+{
+    const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (i >= numBlocks * apm) return;
+    const int64_t s = int64_t(perm[i / apm]) * apm + i % apm;
+    st4(dst.pos + i, ld4nc(src.pos + s));
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+    {
+        dst.vel[d][i] = src.vel[d][s];
+        dst.force[d][i] = src.force[d][s];
+    }
+    dst.mass[i] = src.mass[s];
+    dst.charge[i] = src.charge[s];
+    dst.relMass[i] = src.relMass[s];
+    dst.gid[i] = src.gid[s];
+}
+__global__ void permutePos4Kernel(double4* dst, const double4* src, const uint32_t* perm, int64_t n)
+{
+    const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (i < n) st4(dst + i, ld4nc(src + perm[i]));
+}
+
 __global__ void permuteMolsKernel(MolsView dst, MolsView src, const uint32_t* perm, int64_t begin, int64_t end,
                                   int64_t size)
 {
@@ -507,6 +531,59 @@ int cellStartFromKeys(const uint32_t* sortedKeys, int64_t n, int64_t numCells, i
     return 0;
 }
 
+// LinkedCellList over the centres of mass of the molecules [0, count) + permute for molecules of apm consecutive atoms
+// (atomsOffset = apm * m for every molecule, before and after): the atoms move in blocks, the centres of mass are
+// permuted along, and the linked-cell structure is left in m->lcView for the tiled neighbour build on molecules.
+// dropFlags (optional, per molecule): flagged molecules sort behind the last cell (they migrated to another rank).
+int moleculesCellSortWithAtoms(mrmd_b200_molecules* m, mrmd_b200_atoms* a, int64_t count, int apm, const double* delta,
+                               const double* gridMin, const double* gridMax, const signed char* dropFlags, cudaStream_t st)
+{
+    MB_REQUIRE(m != nullptr && a != nullptr && apm >= 1 && count >= 0, "molecules_cell_sort_with_atoms");
+    MB_REQUIRE(count <= m->capacity && count * apm <= a->capacity, "molecules_cell_sort_with_atoms: range outside the containers");
+    if (m->lcView == nullptr) m->lcView = new mrmd_b200_atoms;
+    mrmd_b200_atoms* lv = m->lcView;
+    const GridDev g = makeGrid(gridMin, gridMax, delta);
+    const int64_t numCells = int64_t(g.n[0]) * g.n[1] * g.n[2];
+    MB_REQUIRE(numCells < (int64_t(1) << 31) - 1, "molecules_cell_sort_with_atoms: too many cells");
+    MB_TRY(lv->lcCellStart.reserve(size_t(numCells + 1) * 4));
+    if (count > 0)
+    {
+        uint32_t *k0, *v0, *k1, *v1, *hist;
+        MB_TRY(cellSortPrepare(m->sortScratch, count, &k0, &v0, &k1, &v1, &hist));
+        MB_TRY(atomsEnsureAlt(a, st));
+        MB_TRY(molsEnsureAlt(m, st));
+        cellKeyKernel<<<gridFor(count, 256), 256, 0, st>>>(m->v.pos, 0, count, g, k0, v0, nullptr, dropFlags,
+                                                           static_cast<uint32_t>(numCells));
+        MB_LAUNCHED();
+        uint32_t *sortedKeys, *perm;
+        MB_TRY(radixSortPairs(k0, v0, k1, v1, hist, count, bitsFor(numCells + 1), &sortedKeys, &perm, st));
+        permuteAtomBlocksKernel<<<gridFor(count * apm, 256), 256, 0, st>>>(a->alt, a->v, perm, count, apm);
+        MB_LAUNCHED();
+        std::swap(a->v, a->alt);
+        // only the centres of mass travel with the molecules: offsets stay apm * m, lambda / force are per-step values
+        permutePos4Kernel<<<gridFor(count, 256), 256, 0, st>>>(m->alt.pos, m->v.pos, perm, count);
+        MB_LAUNCHED();
+        MB_CUDA(cudaMemcpyAsync(m->v.pos, m->alt.pos, size_t(count) * 32, cudaMemcpyDeviceToDevice, st));
+        cellStartKernel<<<gridFor(numCells + 1, 256), 256, 0, st>>>(sortedKeys, count, numCells, lv->lcCellStart.as<int32_t>(), 0);
+        MB_LAUNCHED();
+    }
+    else
+        MB_CUDA(cudaMemsetAsync(lv->lcCellStart.p, 0, size_t(numCells + 1) * 4, st));
+    a->posEpoch += 1;
+    a->lcValid = false;  // the atoms are in molecule order, not in an atom cell order
+    lv->v.pos = m->v.pos;
+    lv->lcValid = true;
+    lv->lcGrid = g;
+    lv->lcBegin = 0;
+    lv->lcEnd = count;
+    lv->numLocal = count;
+    lv->size = count;
+    lv->lcNumCells = numCells;
+    lv->lcEpoch += 1;
+    lv->lcPosEpoch = lv->posEpoch;
+    return 0;
+}
+
 static int atomsCellSortImpl(mrmd_b200_atoms* a, int64_t begin, int64_t end, const double* delta, const double* gridMin,
                              const double* gridMax, int32_t* cellIdOut, const signed char* dropFlags, cudaStream_t st)
 {
@@ -551,6 +628,17 @@ int mrmd_b200_atoms_cell_sort(mrmd_b200_atoms* a, int64_t begin, int64_t end, co
 {
     MB_TRY(checkDevice());
     return atomsCellSortImpl(a, begin, end, delta, gridMin, gridMax, cellIdOut, nullptr, S(stream));
+}
+
+int mrmd_b200_molecules_cell_sort_with_atoms(mrmd_b200_molecules* m, mrmd_b200_atoms* a, int atomsPerMolecule,
+                                             const double* delta, const double* gridMin, const double* gridMax, void* stream)
+{
+    MB_TRY(checkDevice());
+    MB_REQUIRE(m != nullptr && a != nullptr && delta != nullptr && gridMin != nullptr && gridMax != nullptr,
+               "molecules_cell_sort_with_atoms");
+    MB_REQUIRE(atomsPerMolecule >= 1 && m->numLocal * atomsPerMolecule == a->numLocal,
+               "molecules_cell_sort_with_atoms: local atoms != atomsPerMolecule x local molecules");
+    return moleculesCellSortWithAtoms(m, a, m->numLocal, atomsPerMolecule, delta, gridMin, gridMax, nullptr, S(stream));
 }
 
 int mrmd_b200_molecules_cell_sort(mrmd_b200_molecules* m, int64_t begin, int64_t end, const double* delta,

@@ -121,6 +121,55 @@ __global__ void slabWrapFlagKernel(double4* pos, int64_t n, SubdomainDev s, sign
     flag[idx] = (p.x < s.minCorner[0]) ? -1 : ((p.x >= s.maxCorner[0]) ? 1 : 0);
 }
 
+// the same for molecules of apm consecutive atoms, positioned by their centre of mass: the y / z wrap moves the molecule
+// with all its atoms by +-L without a clamp (MultiResRealAtomsExchange.cpp:23-73), the x flag follows the centre of mass
+__global__ void slabWrapFlagMolKernel(double4* com, double4* pos, int64_t nm, int apm, SubdomainDev s, signed char* flag)
+{
+    const int64_t mi = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (mi >= nm) return;
+    double4 c = ld4(com + mi);
+    double* cx = &c.x;
+    double shift[3] = {0.0, 0.0, 0.0};
+    bool moved = false;
+#pragma unroll
+    for (int dim = 1; dim < 3; ++dim)
+    {
+        if (s.maxCorner[dim] <= cx[dim])
+        {
+            cx[dim] -= s.diameter[dim];
+            shift[dim] -= 1.0;
+            moved = true;
+        }
+        if (cx[dim] < s.minCorner[dim])
+        {
+            cx[dim] += s.diameter[dim];
+            shift[dim] += 1.0;
+            moved = true;
+        }
+    }
+    flag[mi] = (c.x < s.minCorner[0]) ? -1 : ((c.x >= s.maxCorner[0]) ? 1 : 0);
+    if (!moved) return;
+    st4(com + mi, c);
+    for (int j = 0; j < apm; ++j)
+    {
+        double4 p = ld4(pos + mi * apm + j);
+        double* x = &p.x;
+#pragma unroll
+        for (int dim = 1; dim < 3; ++dim)
+        {
+            if (shift[dim] < 0.0) x[dim] -= s.diameter[dim];
+            if (shift[dim] > 0.0) x[dim] += s.diameter[dim];
+        }
+        st4(pos + mi * apm + j, p);
+    }
+}
+
+__global__ void slabMoleculeInitKernel(MolsView m, int64_t n, int64_t apm)
+{
+    const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (i < n) m.oc[i] = make_longlong2(i * apm, apm);
+}
+
 // stable selection of two subsets of [first, first + n): block counts -> scan -> ranked index lists
 template <int MODE>  // 0: migration flags, 1: halo faces by position
 __device__ __forceinline__ void selectPredicates(const double4* pos, const signed char* flag, int64_t idx, double lowBound,
@@ -718,6 +767,7 @@ __global__ void __launch_bounds__(SL_THREADS)
         recvDev[0] = cL;
         recvDev[1] = cR;
         if (bad) *err = 1;
+        hReport[14] = *err;  // raised by the selections in front of this kernel (list or column capacity)
         hReport[8] = sent[0];
         hReport[9] = sent[1];
         hReport[10] = cL;
@@ -782,13 +832,16 @@ struct mrmd_b200_slab
     mrmd_b200_atoms* atoms = nullptr;  // not owned
     mrmd_b200_verlet* list = nullptr;
     mrmd_b200_lj* lj = nullptr;
-    mrmd_b200_adress* adress = nullptr;  // AdResS mode (one-atom molecules, tiled kernel)
+    mrmd_b200_adress* adress = nullptr;  // AdResS mode (tiled kernels)
+    mrmd_b200_molecules* mols = nullptr;            // apm > 1: molecules of apm consecutive atoms (centres of mass, SHAKE)
+    mrmd_b200_constraints* constraints = nullptr;   // apm > 1 with numConstraintIterations > 0
     mrmd_b200_thermo* thermo = nullptr;  // bins over the GLOBAL box, density all-reduced before every update
     double maxDisplacement = DBL_MAX;
     bool postPending = false;
     // MRMD_B200_SLAB_PROFILE=1: phases separated by stream syncs, wall-clock sums printed at destroy (diagnostic only)
     bool profile = false;
     double prof[6] = {0, 0, 0, 0, 0, 0};  // pre, decision, rebuild, halo refresh, force, steps
+    double profRebuild[4] = {0, 0, 0, 0};  // migration (to the first host round trip), sort, face lists + halo, list build
     int64_t step = 0, rebuilds = 0, storedPairsNow = 0;
     int64_t haloLeftCount = 0, haloRightCount = 0;   // received
     int64_t sendLeftCount = 0, sendRightCount = 0;   // boundary atoms sent every step
@@ -1086,7 +1139,34 @@ static int haloRefresh(mrmd_b200_slab* sl, cudaStream_t st)
     return 0;
 }
 
-static double4* unitPositions(mrmd_b200_slab* sl) { return sl->atoms->v.pos; }
+static double profMark(mrmd_b200_slab* sl, cudaStream_t st, double& last)
+{
+    if (!sl->profile) return 0.0;
+    cudaStreamSynchronize(st);
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    const double now = ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+    const double d = now - last;
+    last = now;
+    return d;
+}
+
+static double4* unitPositions(mrmd_b200_slab* sl) { return sl->apm > 1 ? sl->mols->v.pos : sl->atoms->v.pos; }
+
+// apm > 1: room for `units` molecules with atomsOffset = apm * m, numAtoms = apm for every slot (arrivals and halo
+// molecules use the slots behind the local ones)
+static int slabEnsureMolecules(mrmd_b200_slab* sl, int64_t units, cudaStream_t st)
+{
+    if (sl->apm <= 1) return 0;
+    mrmd_b200_molecules* m = sl->mols;
+    if (units > m->capacity)
+    {
+        MB_TRY(molsEnsureCapacity(m, units, st));
+        slabMoleculeInitKernel<<<gridFor(m->capacity, 256), 256, 0, st>>>(m->v, m->capacity, sl->apm);
+        MB_LAUNCHED();
+    }
+    return 0;
+}
 
 // The rebuild over peer memory: two host round trips (the migration counts, the list statistics).
 static int slabRebuildP2P(mrmd_b200_slab* sl, cudaStream_t st)
@@ -1098,6 +1178,7 @@ static int slabRebuildP2P(mrmd_b200_slab* sl, cudaStream_t st)
     a->size = n;
     // room for the arrivals of the migration and, after it, for the halo units
     MB_TRY(atomsEnsureCapacity(a, n + 2 * std::max(sl->migCap, sl->p2pCap) * apm, st));
+    MB_TRY(slabEnsureMolecules(sl, nUnits + 2 * std::max(sl->migCap, sl->p2pCap), st));
     MB_TRY(sl->flags.reserve(size_t(a->capacity) + 64));
     const int blocksAll = std::max(1, gridFor(nUnits, SL_THREADS));
     MB_TRY(sl->blockCounts.reserve(size_t(std::max<int64_t>(blocksAll, gridFor(sl->colBound, SL_THREADS))) * 16 + 64));
@@ -1105,7 +1186,21 @@ static int slabRebuildP2P(mrmd_b200_slab* sl, cudaStream_t st)
     signed char* flag = sl->flags.as<signed char>();
     MB_CUDA(cudaMemsetAsync(sl->dErr, 0, 4, st));
     // ---- 1. wrap y / z, flag and list the leavers, push their records, take in the arrivals
-    if (n > 0)
+    if (apm > 1)
+    {
+        mrmd_b200_molecules* m = sl->mols;
+        m->numLocal = nUnits;
+        m->numGhost = 0;
+        m->size = nUnits;
+        MB_TRY(mrmd_b200_molecules_update(m, a, &sl->cfg.weight, st));  // the current centres of mass
+        if (nUnits > 0)
+        {
+            slabWrapFlagMolKernel<<<gridFor(nUnits, 256), 256, 0, st>>>(m->v.pos, a->v.pos, nUnits, apm, toDev(sl->sub), flag);
+            MB_LAUNCHED();
+        }
+        a->posEpoch += 1;
+    }
+    else if (n > 0)
     {
         slabWrapFlagKernel<<<gridFor(n, 256), 256, 0, st>>>(a->v.pos, n, toDev(sl->sub), flag);
         MB_LAUNCHED();
@@ -1136,29 +1231,57 @@ static int slabRebuildP2P(mrmd_b200_slab* sl, cudaStream_t st)
             sl->migCap, flag, sl->dTotals, sl->dTotals + 4, sl->hReport, sl->dErr);
         MB_LAUNCHED();
     }
+    double last = 0.0;
+    profMark(sl, st, last);
     MB_TRY(pollReport(sl, 4, mseq, st, "migration"));  // host round trip 1: the new number of local atoms
+    sl->profRebuild[0] += profMark(sl, st, last);
     MB_REQUIRE(sl->hReport[5] == 0, "slab: more atoms migrate in one rebuild than the peer buffer holds");
     const int64_t nSend = (sl->hReport[0] + sl->hReport[1]) * apm, nRecv = (sl->hReport[2] + sl->hReport[3]) * apm;
     // ---- 2. sort by linked cell; the leavers sort behind the last cell and are dropped
     a->size = n + nRecv;
     const double cutoff = sl->cfg.rc + sl->cfg.skin;
     const double delta[3] = {cutoff, cutoff, 0.25 * cutoff};  // as md.cu: fine z order inside a cell column
-    MB_TRY(atomsCellSortDrop(a, 0, n + nRecv, delta, sl->sub.minCorner, sl->sub.maxCorner, flag, st));
-    a->numLocal = n + nRecv - nSend;
+    const mrmd_b200_atoms* lc = a;  // the linked-cell structure of the units
+    if (apm > 1)
+    {
+        // centres of mass of the wrapped residents and of the arrivals (UpdateMolecules::update, as the reference
+        // recomputes them before its list build), then LinkedCellList + permute on them, the atoms moving in blocks
+        mrmd_b200_molecules* m = sl->mols;
+        const int64_t units = (n + nRecv) / apm;
+        m->numLocal = units;
+        m->size = units;
+        MB_TRY(mrmd_b200_molecules_update(m, a, &sl->cfg.weight, st));
+        MB_TRY(moleculesCellSortWithAtoms(m, a, units, apm, delta, sl->sub.minCorner, sl->sub.maxCorner, flag, st));
+        a->numLocal = n + nRecv - nSend;
+        m->numLocal = a->numLocal / apm;
+        m->size = m->numLocal;
+        m->lcView->numLocal = m->numLocal;
+        m->lcView->size = m->numLocal;
+        m->lcView->lcEnd = m->numLocal;
+        lc = m->lcView;
+    }
+    else
+    {
+        MB_TRY(atomsCellSortDrop(a, 0, n + nRecv, delta, sl->sub.minCorner, sl->sub.maxCorner, flag, st));
+        a->numLocal = n + nRecv - nSend;
+        a->lcEnd = a->numLocal;
+    }
     a->size = a->numLocal;
-    a->lcEnd = a->numLocal;
     MB_TRY(atomsEnsureCapacity(a, a->numLocal + 2 * sl->p2pCap * apm, st));
+    MB_TRY(slabEnsureMolecules(sl, a->numLocal / apm + 2 * sl->p2pCap, st));
+    if (apm > 1) sl->mols->lcView->v.pos = sl->mols->v.pos;
+    sl->profRebuild[1] += profMark(sl, st, last);
     // ---- 3. face lists from the first / last cell column (ranges read on the device), push, pull
-    const GridDev& g = a->lcGrid;
+    const GridDev& g = lc->lcGrid;
     const int64_t perX = int64_t(g.n[1]) * g.n[2];
     {
-        const int32_t* cs = a->lcCellStart.as<int32_t>();
+        const int32_t* cs = lc->lcCellStart.as<int32_t>();
         SelArgs face{};
         face.upos = unitPositions(sl);
         face.rangeA0 = cs;
         face.rangeA1 = cs + perX;
         face.rangeB0 = cs + (int64_t(g.n[0]) - 1) * perX;
-        face.rangeB1 = cs + a->lcNumCells;
+        face.rangeB1 = cs + lc->lcNumCells;
         face.lowBound = sl->sub.minInnerCorner[0];   // low face: x < minInner within column 0
         face.highBound = sl->sub.maxInnerCorner[0];  // high face: x >= maxInner within column nx-1
         const int blocksCol = std::max(1, gridFor(sl->colBound, SL_THREADS));
@@ -1172,6 +1295,7 @@ static int slabRebuildP2P(mrmd_b200_slab* sl, cudaStream_t st)
     }
     MB_TRY(haloPush(sl, true, st));
     MB_TRY(haloPull(sl, true, st));
+    sl->profRebuild[2] += profMark(sl, st, last);
     // ---- 4. linked cells of the received halo units (they arrive in (j, k) order), tiled neighbour build
     MB_TRY(sl->haloKeys.reserve(size_t(2 * sl->p2pCap) * 4));
     MB_TRY(sl->haloStartLeft.reserve(size_t(perX + 1) * 4));
@@ -1183,13 +1307,17 @@ static int slabRebuildP2P(mrmd_b200_slab* sl, cudaStream_t st)
                                                                       a->numLocal / apm, sl->haloStartLeft.as<int32_t>(),
                                                                       sl->haloStartRight.as<int32_t>());
     MB_LAUNCHED();
-    MB_TRY(verletBuildTiled(sl->list, a, &sl->sub, cutoff, 1.0, sl->cfg.maxNeighbors, sl->haloStartLeft.as<int32_t>(),
-                            sl->haloStartRight.as<int32_t>(), st));  // host round trip 2 (list statistics)
+    // host round trip 2 (list statistics)
+    if (apm > 1)
+        MB_TRY(verletBuildTiledMolecules(sl->list, sl->mols, &sl->sub, cutoff, 1.0, sl->cfg.maxNeighbors, apm,
+                                         sl->haloStartLeft.as<int32_t>(), sl->haloStartRight.as<int32_t>(), st));
+    else
+        MB_TRY(verletBuildTiled(sl->list, a, &sl->sub, cutoff, 1.0, sl->cfg.maxNeighbors, sl->haloStartLeft.as<int32_t>(),
+                                sl->haloStartRight.as<int32_t>(), st));
+    sl->profRebuild[3] += profMark(sl, st, last);
     MB_TRY(pollReport(sl, 12, static_cast<long long>(sl->haloSeq), st, "halo exchange"));
     MB_REQUIRE(sl->hReport[13] == 0, "slab: the position halo exceeds the peer buffer (density more than tripled since slab_create)");
-    MB_CUDA(cudaMemcpyAsync(sl->hTotals, sl->dErr, 4, cudaMemcpyDeviceToHost, st));
-    MB_CUDA(cudaStreamSynchronize(st));
-    MB_REQUIRE(*reinterpret_cast<int*>(sl->hTotals) == 0, "slab: a selection list exceeded its capacity during the rebuild");
+    MB_REQUIRE(sl->hReport[14] == 0, "slab: a selection list exceeded its capacity during the rebuild");
     sl->sendLeftCount = sl->hReport[8];
     sl->sendRightCount = sl->hReport[9];
     sl->haloLeftCount = sl->hReport[10];
@@ -1207,6 +1335,7 @@ static int slabRebuild(mrmd_b200_slab* sl, cudaStream_t st)
 {
     mrmd_b200_atoms* a = sl->atoms;
     if (sl->p2p) return slabRebuildP2P(sl, st);
+    MB_REQUIRE(sl->apm == 1, "slab: multi-atom molecules need the peer-memory data plane (CUDA IPC between the ranks)");
     MB_TRY(migrate(sl, st));
     MB_TRY(haloExchange(sl, st));
     MB_TRY(haloRefresh(sl, st));
@@ -1322,18 +1451,6 @@ static int sumOverRanks(void* ctx, double* sums, int64_t count, cudaStream_t st)
     return 0;
 }
 
-static double profMark(mrmd_b200_slab* sl, cudaStream_t st, double& last)
-{
-    if (!sl->profile) return 0.0;
-    cudaStreamSynchronize(st);
-    timespec ts;
-    clock_gettime(CLOCK_MONOTONIC, &ts);
-    const double now = ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
-    const double d = now - last;
-    last = now;
-    return d;
-}
-
 static int slabStep(mrmd_b200_slab* sl, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, bool wantEnergy,
                     bool deferPost = true, cudaEvent_t evPosReady = nullptr)
 {
@@ -1341,6 +1458,8 @@ static int slabStep(mrmd_b200_slab* sl, cudaStream_t st, cudaEvent_t e0, cudaEve
     mrmd_b200_atoms* a = sl->atoms;
     double last = 0.0;
     profMark(sl, st, last);
+    if (sl->constraints != nullptr)  // tests/Constraints/Constraints.cpp:53-54
+        MB_TRY(constraintsEnforcePositional(sl->constraints, sl->mols, a, c.dt, st));
     // the previous step's postForceIntegrate rides in front of this kick (flushed when a run returns)
     MB_TRY(integratePre(a, c.dt, c.integrator == 1, c.zeta, c.temperature, c.seed,
                         uint64_t(sl->step), nullptr, sl->postPending, st));
@@ -1350,6 +1469,8 @@ static int slabStep(mrmd_b200_slab* sl, cudaStream_t st, cudaEvent_t e0, cudaEve
     // the rebuild decision (double-buffered regions; a push that a rebuild supersedes is simply never pulled).  Before
     // the first rebuild there are no lists yet.
     const bool earlyPush = sl->p2p && sl->rebuilds > 0;
+    if (sl->apm > 1 && sl->rebuilds > 0)  // the centres of mass travel with the face molecules
+        MB_TRY(mrmd_b200_molecules_update(sl->mols, a, &c.weight, st));
     if (earlyPush) MB_TRY(haloPush(sl, false, st));
     // the rebuild decision is collective: global maximum of the squared displacement
     if (sl->p2p)
@@ -1394,7 +1515,16 @@ static int slabStep(mrmd_b200_slab* sl, cudaStream_t st, cudaEvent_t e0, cudaEve
         sl->prof[3] += profMark(sl, st, last);
     }
     if (evPosReady != nullptr) MB_CUDA(cudaEventRecord(evPosReady, st));  // positions and atom order are final
-    if (c.adress)
+    if (sl->apm > 1)
+    {
+        // AdResS on molecules of apm atoms: LJ_IdealGas + ContributeMoleculeForceToAtoms as one kernel over the tiled
+        // list of the centres of mass (local + halo molecules), SHAKE / RATTLE stay rank-local (whole molecules migrate)
+        for (int d = 0; d < 3; ++d) MB_CUDA(cudaMemsetAsync(a->v.force[d], 0, size_t(a->numLocal) * 8, st));
+        if (e0) MB_CUDA(cudaEventRecord(e0, st));
+        MB_TRY(adressRunPeriodicMolecules(sl->adress, sl->mols, a, sl->list, &c.weight, sl->apm, wantEnergy, st));
+        if (e1) MB_CUDA(cudaEventRecord(e1, st));
+    }
+    else if (c.adress)
     {
         // SURVEY.md section 3.5 on a slab: thermodynamic force (density histogram all-reduced over the ranks
         // before an update, table replicated), then the tiled AdResS kernel over local + halo atoms
@@ -1424,7 +1554,9 @@ static int slabStep(mrmd_b200_slab* sl, cudaStream_t st, cudaEvent_t e0, cudaEve
     }
     sl->prof[4] += profMark(sl, st, last);
     sl->prof[5] += 1.0;
-    if (deferPost) sl->postPending = true;  // rides in front of the next step's kick
+    if (sl->constraints != nullptr)
+        MB_TRY(constraintsEnforceVelocity(sl->constraints, sl->mols, a, st, c.dt));  // RATTLE with the kick riding along
+    else if (deferPost) sl->postPending = true;  // rides in front of the next step's kick
     else MB_TRY(mrmd_b200_vv_post(a, c.dt, st));
     sl->step += 1;
     return 0;
@@ -1461,8 +1593,12 @@ int mrmd_b200_slab_create_cuts(mrmd_b200_slab** out, const mrmd_b200_md_config* 
     MB_TRY(checkDevice());
     MB_REQUIRE(out && cfg && globalMin && globalMax && uniqueId128 && atoms, "slab_create");
     MB_REQUIRE(nranks >= 2 && rank >= 0 && rank < nranks, "slab_create: needs at least two ranks");
-    MB_REQUIRE(cfg->atomsPerMolecule <= 1 && cfg->numConstraintIterations == 0,
-               "slab_create: the x-slab decomposition handles one-atom molecules only");
+    const int64_t apmCfg = std::max<int64_t>(cfg->atomsPerMolecule, 1);
+    MB_REQUIRE(apmCfg == 1 || (apmCfg == 4 && cfg->adress && !cfg->useThermoForce),
+               "slab_create: molecules of one or four atoms (four: AdResS without thermodynamic force)");
+    MB_REQUIRE(atoms->numLocal % apmCfg == 0, "slab_create: local atoms are not a multiple of atomsPerMolecule");
+    MB_REQUIRE(cfg->numConstraintIterations >= 0 && (cfg->numConstraintIterations == 0 || (apmCfg > 1 && cfg->bondLength > 0.0)),
+               "slab_create: constraints need multi-atom molecules and a positive bond length");
     if (cfg->adress)
     {
         // the tiled AdResS kernel evaluates lambda at image positions: across the global periodic x faces (and y, z
@@ -1504,6 +1640,7 @@ int mrmd_b200_slab_create_cuts(mrmd_b200_slab** out, const mrmd_b200_md_config* 
     sl->shiftToLeft = (rank == 0) ? lx : 0.0;             // crossing the low end of the box: x + Lx
     sl->shiftToRight = (rank == nranks - 1) ? -lx : 0.0;  // crossing the high end: x - Lx
     sl->atoms = atoms;
+    sl->apm = static_cast<int>(apmCfg);
     sl->profile = std::getenv("MRMD_B200_SLAB_PROFILE") != nullptr;
     int rc = 0;
     if (width < cutoff)
@@ -1543,6 +1680,40 @@ int mrmd_b200_slab_create_cuts(mrmd_b200_slab** out, const mrmd_b200_md_config* 
                                          &cfg->thermoModulation, 0, 0);
         }
     }
+    if (rc == 0 && sl->apm > 1)
+    {
+        const int64_t numMols = atoms->numLocal / sl->apm;
+        rc = mrmd_b200_molecules_create(&sl->mols, std::max<int64_t>(numMols, 1));
+        if (rc == 0)
+        {
+            sl->mols->size = numMols;
+            sl->mols->numLocal = numMols;
+            slabMoleculeInitKernel<<<gridFor(sl->mols->capacity, 256), 256>>>(sl->mols->v, sl->mols->capacity, sl->apm);
+            g_launchCount.fetch_add(1);
+            if (cudaDeviceSynchronize() != cudaSuccess) rc = MRMD_B200_EINVAL;
+        }
+        if (rc == 0 && cfg->numConstraintIterations > 0)
+        {
+            // MoleculeConstraints(apm, iterations) with a bond between every two atoms of a molecule (as md.cu)
+            rc = mrmd_b200_constraints_create(&sl->constraints, sl->apm, cfg->numConstraintIterations);
+            std::vector<int64_t> bi, bj;
+            std::vector<double> eq;
+            for (int64_t i = 0; i < sl->apm; ++i)
+                for (int64_t j = i + 1; j < sl->apm; ++j)
+                {
+                    bi.push_back(i);
+                    bj.push_back(j);
+                    eq.push_back(cfg->bondLength);
+                }
+            if (rc == 0) rc = mrmd_b200_constraints_set(sl->constraints, bi.data(), bj.data(), eq.data(), int64_t(eq.size()));
+            if (rc == 0) constraintsSetUniformMolecules(sl->constraints, true);
+        }
+        if (rc == 0 && std::getenv("MRMD_B200_SLAB_NO_P2P") != nullptr)
+        {
+            setLastError("slab_create: multi-atom molecules need the peer-memory data plane");
+            rc = MRMD_B200_EINVAL;
+        }
+    }
     if (rc == 0 && cudaMalloc(&sl->dTotals, 64) != cudaSuccess) rc = MRMD_B200_ENOMEM;
     if (rc == 0 && cudaMallocHost(&sl->hTotals, 64) != cudaSuccess) rc = MRMD_B200_ENOMEM;
     if (rc == 0 && cudaMalloc(&sl->dScalars, 64) != cudaSuccess) rc = MRMD_B200_ENOMEM;
@@ -1568,6 +1739,10 @@ int mrmd_b200_slab_destroy(mrmd_b200_slab* sl)
                      "halo refresh %.1f, force %.1f\n",
                      sl->rank, sl->prof[5], static_cast<long long>(sl->rebuilds), sl->prof[0] / sl->prof[5],
                      sl->prof[1] / sl->prof[5], sl->prof[2] / sl->prof[5], sl->prof[3] / sl->prof[5], sl->prof[4] / sl->prof[5]);
+    if (sl->profile && sl->rebuilds > 0)
+        std::fprintf(stderr, "[mrmd_b200 slab rank %d] us per rebuild: migration %.1f, sort %.1f, face lists + halo %.1f, list build %.1f\n",
+                     sl->rank, sl->profRebuild[0] / sl->rebuilds, sl->profRebuild[1] / sl->rebuilds,
+                     sl->profRebuild[2] / sl->rebuilds, sl->profRebuild[3] / sl->rebuilds);
     for (auto e : sl->events) cudaEventDestroy(e);
     sl->hp.destroy();
     if (sl->comm != nullptr) g_nccl.commDestroy(sl->comm);
@@ -1584,6 +1759,8 @@ int mrmd_b200_slab_destroy(mrmd_b200_slab* sl)
     mrmd_b200_lj_destroy(sl->lj);
     mrmd_b200_adress_destroy(sl->adress);
     mrmd_b200_thermo_destroy(sl->thermo);
+    mrmd_b200_constraints_destroy(sl->constraints);
+    mrmd_b200_molecules_destroy(sl->mols);
     if (sl->dTotals) cudaFree(sl->dTotals);
     if (sl->hTotals) cudaFreeHost(sl->hTotals);
     if (sl->dScalars) cudaFree(sl->dScalars);

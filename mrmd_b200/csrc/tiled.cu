@@ -250,12 +250,26 @@ __device__ __forceinline__ bool cabanaCellReachable(const GridDev& cg, double px
 // the neighbour build (their rows stay empty); both use this one criterion.
 __device__ __forceinline__ bool tileAllCoarseGrained(const TileParams& tp, const mrmd_b200_weight& w, int tile)
 {
-    if (w.kind != MRMD_B200_WEIGHT_SLAB) return false;
-    const int ci = (tile / tp.numChunks) / tp.g.n[1];
+    const int col = tile / tp.numChunks;
+    const int ci = col / tp.g.n[1];
     const double lo = tp.g.min[0] + double(ci - 2) * tp.g.dx[0];
     const double hi = tp.g.min[0] + double(ci + 3) * tp.g.dx[0];
-    const double reach = 0.5 * w.atRegion + w.hyRegion;
-    return (lo - w.center[0] > reach) || (w.center[0] - hi > reach);
+    if (w.kind == MRMD_B200_WEIGHT_SLAB)
+    {
+        const double reach = 0.5 * w.atRegion + w.hyRegion;
+        return (lo - w.center[0] > reach) || (w.center[0] - hi > reach);
+    }
+    // spherical region: distance from the centre to the box of everything the tile stages (in the tile's own image
+    // frame), padded by one more cell on every side
+    const int cj = col % tp.g.n[1], chunk = tile % tp.numChunks;
+    const int k0 = chunk * tp.CH, k1 = min(k0 + tp.CH, tp.g.n[2]) - 1;
+    const double ylo = tp.g.min[1] + double(cj - 2) * tp.g.dx[1], yhi = tp.g.min[1] + double(cj + 3) * tp.g.dx[1];
+    const double zlo = tp.g.min[2] + double(k0 - tp.R - 1) * tp.g.dx[2], zhi = tp.g.min[2] + double(k1 + tp.R + 2) * tp.g.dx[2];
+    const double dx = fmax(fmax(lo - w.center[0], w.center[0] - hi), 0.0);
+    const double dy = fmax(fmax(ylo - w.center[1], w.center[1] - yhi), 0.0);
+    const double dz = fmax(fmax(zlo - w.center[2], w.center[2] - zhi), 0.0);
+    const double reach = w.atRegion + w.hyRegion;
+    return dx * dx + dy * dy + dz * dz > reach * reach;
 }
 
 // Measured in round 2 and dropped (profiles/r02_build_experiments.md): (a) walking the nine ranges of a home as ONE flat
@@ -828,6 +842,166 @@ __global__ void __launch_bounds__(TL_THREADS_FORCE, 6)
     gridReduce3<TL_THREADS_FORCE>(0.5 * energy, 0.5 * pairs, 0.5 * activePairs, partials, result, ticket);
 }
 
+// ---- AdResS on tiles for molecules of NA atoms (the tetramers of BASELINE.json configs[3]) --------------------------
+// The tiled list is built on the molecules' centres of mass (mrmd_b200_verlet_build_periodic_molecules: the same builder
+// on the cell-sorted centres of mass); a staged slot is a molecule: its NA atom positions and lambda^mod at its centre of
+// mass (images: positions + the image shift, the weight at the shifted centre of mass).  NA lanes share one home
+// molecule alpha, lane i owns atom i of alpha: per partner molecule it evaluates its atom against the partner's NA atoms
+// (LJ_IdealGas.cpp:96-205 seen from the row owner), sum(V_ij) is combined over the lanes for the drift force
+// -sum(V_ij) grad(lambda_alpha) and the drift compensation (:209-222), and ContributeMoleculeForceToAtoms hands the
+// molecule force to the atoms by relative mass.  Full list: no atomics on forces, no ghost molecules, no reverse halo.
+constexpr int TL_THREADS_MOL = 128;
+template <int NA>
+constexpr int molSlotDoubles() { return 3 * NA + 1; }
+template <int NA>
+constexpr int molSlotBytes() { return molSlotDoubles<NA>() * 8 + NA; }  // + one type byte per atom
+
+template <int NA, bool SAMPLING, bool ENERGY>
+__global__ void __launch_bounds__(TL_THREADS_MOL)
+    moleculeForceTiledKernel(TileParams tp, AtomsView a, const double4* __restrict__ com, const int* __restrict__ desc,
+                             const int32_t* __restrict__ counts, const uint16_t* __restrict__ enc, int width, LJTable table,
+                             double rcSqr, int64_t numTypes, mrmd_b200_weight w, double* hist, double* partials,
+                             double* result, unsigned int* ticket)
+{
+    static_assert(NA == 2 || NA == 4 || NA == 8, "lanes per molecule: a power of two");
+    constexpr int REC = molSlotDoubles<NA>();
+    extern __shared__ double sTile[];
+    __shared__ TileDesc td;
+    double energy = 0.0;
+    int pairs = 0, activePairs = 0;
+    if (!tileAllCoarseGrained(tp, w, blockIdx.x))
+    {
+        loadTileDesc(desc, td);
+        double* rec = sTile;
+        unsigned char* sType = reinterpret_cast<unsigned char*>(rec + size_t(REC) * tp.cap);
+        {
+            // staging: one piece per warp, a lane per (molecule, atom)
+            const int col = blockIdx.x / tp.numChunks;
+            const int ci = col / tp.g.n[1], cj = col % tp.g.n[1];
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            for (int p = warp; p < TL_PIECES; p += blockDim.x / 32)
+            {
+                const int len = td.pieceLen[p];
+                if (len == 0) continue;
+                int ix, iy, iz;
+                pieceShift(tp, ci, cj, p, ix, iy, iz);
+                const double shx = double(ix) * tp.L[0], shy = double(iy) * tp.L[1], shz = double(iz) * tp.L[2];
+                const int start = td.pieceStart[p], slot0 = td.pieceSlot[p];
+                for (int e = lane; e < len * NA; e += 32)
+                {
+                    const int k = e / NA, j = e % NA;
+                    const double4 raw = ld4nc(a.pos + (size_t(start) + k) * NA + j);
+                    double* r = rec + size_t(REC) * (slot0 + k);
+                    r[3 * j] = raw.x + shx;
+                    r[3 * j + 1] = raw.y + shy;
+                    r[3 * j + 2] = raw.z + shz;
+                    sType[(slot0 + k) * NA + j] = static_cast<unsigned char>(typeOf(raw));
+                    if (j == 0)
+                    {
+                        const double4 c = ld4nc(com + start + k);
+                        r[3 * NA] = weightModLambda(w, c.x + shx, c.y + shy, c.z + shz);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        const int group = threadIdx.x / NA, li = threadIdx.x % NA;
+        const int64_t T = numTypes;
+        const double inverseBinSize = 1.0 / ((1.0 - 0.0) / double(TL_COMPENSATION_BINS));
+        for (int hBase = 0; hBase < td.homeCount; hBase += blockDim.x / NA)
+        {
+            const int h = hBase + group;
+            const bool active = h < td.homeCount;
+            const int u = td.homeStart + (active ? h : 0);  // molecule
+            const int selfSlot = td.selfSlot0 + (active ? h : 0);
+            const double* me = rec + size_t(REC) * selfSlot + 3 * li;
+            const double xi = me[0], yi = me[1], zi = me[2];
+            const int typeI = sType[selfSlot * NA + li];
+            const double4 c = ld4nc(com + u);
+            double lambda, modA, gx, gy, gz;
+            weightEval(w, c.x, c.y, c.z, lambda, modA, gx, gy, gz);
+            const bool hyA = inHY(modA), cgA = inCG(modA);
+            double fx = 0.0, fy = 0.0, fz = 0.0, vsum = 0.0;
+            const int numNeighbors = active ? min(counts[u], width) : 0;
+            const uint16_t* row = enc + size_t(u) * width;
+            const int iters = __reduce_max_sync(0xffffffffu, numNeighbors);
+            for (int n = 0; n < iters; ++n)
+            {
+                if (n >= numNeighbors) continue;
+                const int slot = row[tiledRowIndex(n, width)];
+                const double* q = rec + size_t(REC) * slot;
+                const double modB = q[3 * NA];
+                if (cgA && inCG(modB)) continue;  // ideal gas, LJ_IdealGas.cpp:102-107
+                if (li == 0) activePairs += 1;
+                const double weighting = 0.5 * (modA + modB);
+#pragma unroll
+                for (int j = 0; j < NA; ++j)
+                {
+                    const double dx = xi - q[3 * j];
+                    const double dy = yi - q[3 * j + 1];
+                    const double dz = zi - q[3 * j + 2];
+                    const double distSqr = distSqrExact(dx, dy, dz);
+                    if (distSqr > rcSqr) continue;  // :137
+                    const LJType& t = table.t[typeI * T + sType[slot * NA + j]];
+                    double ff, e;
+                    if (distSqr >= t.cappingDistanceSqr)
+                    {
+                        const double frac2 = fastRcp(distSqr);
+                        const double frac6 = frac2 * frac2 * frac2;
+                        ff = frac6 * (t.ff1 * frac6 - t.ff2) * frac2;
+                        e = frac6 * (t.ef1 * frac6 - t.ef2) - t.shift;
+                    }
+                    else
+                        ljForceEnergy(t, distSqr, ff, e);
+                    const double ffactor = ff * weighting;
+                    fx += dx * ffactor;
+                    fy += dy * ffactor;
+                    fz += dz * ffactor;
+                    pairs += 1;
+                    if (ENERGY) energy += e * weighting;
+                    if (hyA) vsum += 0.5 * e;  // V_ij of the drift force and of the compensation sampling, :160-200
+                }
+            }
+            // drift force -sum(V_ij) grad(lambda) (:163-169) plus the drift compensation mean[bin] grad(lambda) of the
+            // molecule's FIRST atom type (:209-222); the molecule force goes to the atoms by relative mass
+            // (ContributeMoleculeForceToAtoms.cpp:34-45)
+            double vAll = vsum;
+#pragma unroll
+            for (int o = NA / 2; o > 0; o >>= 1) vAll += __shfl_xor_sync(0xffffffffu, vAll, o);
+            if (active)
+            {
+                const int64_t ai = int64_t(u) * NA + li;
+                if (hyA)
+                {
+                    double scale = -vAll;
+                    const long long bin = histBin(0.0, inverseBinSize, TL_COMPENSATION_BINS, lambda);
+                    if (bin != -1)
+                    {
+                        scale += hist[2 * TL_COMPENSATION_BINS * T + bin * T + sType[selfSlot * NA]];
+                        if (SAMPLING)
+                        {
+                            atomicAdd(hist + bin * T + typeI, vsum);
+                            atomicAdd(hist + TL_COMPENSATION_BINS * T + bin * T + typeI, 1.0);
+                        }
+                    }
+                    const double rm = a.relMass[ai];
+                    fx += rm * (scale * gx);
+                    fy += rm * (scale * gy);
+                    fz += rm * (scale * gz);
+                }
+                if (fx != 0.0 || fy != 0.0 || fz != 0.0)
+                {
+                    a.force[0][ai] += fx;
+                    a.force[1][ai] += fy;
+                    a.force[2][ai] += fz;
+                }
+            }
+        }
+    }
+    // every pair is visited from both sides
+    gridReduce3<TL_THREADS_MOL>(0.5 * energy, 0.5 * double(pairs), 0.5 * double(activePairs), partials, result, ticket);
+}
+
 // decode the 16-bit slots back to (local partner index, image shift code) in Cabana's row-major layout
 __global__ void __launch_bounds__(TL_THREADS_BUILD)
     decodeTiledKernel(TileParams tp, const int* __restrict__ desc, const int32_t* __restrict__ counts,
@@ -928,6 +1102,10 @@ int tiledConfigure()
     TL_SET((adressForceTiledKernel<false, true, false>));
     TL_SET((adressForceTiledKernel<false, false, true>));
     TL_SET((adressForceTiledKernel<false, false, false>));
+    TL_SET((moleculeForceTiledKernel<4, true, true>));
+    TL_SET((moleculeForceTiledKernel<4, true, false>));
+    TL_SET((moleculeForceTiledKernel<4, false, true>));
+    TL_SET((moleculeForceTiledKernel<4, false, false>));
 #undef TL_SET
     done = true;
     return 0;
@@ -1012,6 +1190,49 @@ int adressApplyTiled(mrmd_b200_adress* ad, mrmd_b200_atoms* a, const mrmd_b200_v
         else { if (energy) ADT_LAUNCH(false, false, true); else ADT_LAUNCH(false, false, false); }
     }
 #undef ADT_LAUNCH
+    MB_LAUNCHED();
+    return 0;
+}
+
+// LJ_IdealGas for molecules of atomsPerMolecule consecutive atoms over a tiled list of their centres of mass
+// (mrmd_b200_adress_run_periodic_molecules; adress.cu owns the run counter and the histogram update)
+int moleculeApplyTiled(mrmd_b200_adress* ad, const mrmd_b200_molecules* m, mrmd_b200_atoms* a, const mrmd_b200_verlet* v,
+                       const mrmd_b200_weight* w, int atomsPerMolecule, bool sampling, bool energy, cudaStream_t st)
+{
+    MB_REQUIRE(atomsPerMolecule == 4, "adress_run_periodic_molecules: four atoms per molecule");
+    const mrmd_b200_atoms* lv = m->lcView;
+    MB_REQUIRE(lv != nullptr && lv->lcValid && lv->lcEpoch == v->tiledEpoch,
+               "adress_run_periodic_molecules: the molecules were re-sorted after this tiled list was built");
+    MB_REQUIRE(!v->half, "adress_run_periodic_molecules: tiled lists are full lists");
+    MB_REQUIRE(ad->numTypes <= 255, "adress_run_periodic_molecules: more than 255 atom types");
+    {
+        // as adressApplyTiled: images near a periodic boundary must be coarse grained like their originals
+        const mrmd_b200_subdomain& s = v->tiledSub;
+        const int axes = (w->kind == MRMD_B200_WEIGHT_SLAB) ? 1 : 3;
+        const double reach = (w->kind == MRMD_B200_WEIGHT_SLAB) ? 0.5 * w->atRegion + w->hyRegion : w->atRegion + w->hyRegion;
+        for (int d = 0; d < axes; ++d)
+        {
+            if (s.ghostLayerThickness[d] == 0.0 || (d == 0 && v->tiledHaloX)) continue;
+            MB_REQUIRE(w->center[d] - reach >= s.minCorner[d] + s.ghostLayerThickness[d] &&
+                           w->center[d] + reach <= s.maxCorner[d] - s.ghostLayerThickness[d],
+                       "adress_run_periodic_molecules: the AT/HY region reaches a periodic boundary (use the generic path)");
+        }
+    }
+    MB_TRY(tiledConfigure());
+    TileParams tp;
+    MB_TRY(makeTileParams(lv, &v->tiledSub, v->tiledCH, v->tiledSlots, v->tiledHaloX, v->tiledR, tp));
+    const int tiles = tp.g.n[0] * tp.g.n[1] * tp.numChunks;
+    MB_TRY(ad->partials.reserve(size_t(tiles) * 3 * 8));
+    MB_CUDA(cudaMemsetAsync(ad->dResult, 0, 24, st));
+    const size_t smem = size_t(v->tiledSlots) * molSlotBytes<4>() + 16;
+    MB_REQUIRE(smem <= size_t(TL_SMEM_MAX), "adress_run_periodic_molecules: a tile exceeds shared memory");
+#define MOL_LAUNCH(SAMP, EN)                                                                                             \
+    moleculeForceTiledKernel<4, SAMP, EN><<<tiles, TL_THREADS_MOL, smem, st>>>(                                          \
+        tp, a->v, m->v.pos, v->tileDesc.as<int>(), v->counts.as<int32_t>(), v->enc.as<uint16_t>(), static_cast<int>(v->width), \
+        ad->table, ad->rcSqr, ad->numTypes, *w, ad->hist, ad->partials.as<double>(), ad->dResult, ad->dTicket)
+    if (sampling) { if (energy) MOL_LAUNCH(true, true); else MOL_LAUNCH(true, false); }
+    else { if (energy) MOL_LAUNCH(false, true); else MOL_LAUNCH(false, false); }
+#undef MOL_LAUNCH
     MB_LAUNCHED();
     return 0;
 }
@@ -1115,7 +1336,8 @@ int verletBuildTiled(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, const mrmd_b
         {
             // choose CH: ~110 home atoms per tile, at least ~2 tiles per SM, staged slots within the smem budget
             const double perCell = double(n) / double(std::max<int64_t>(a->lcNumCells, 1));
-            CH = std::max(1, std::min({TL_MAX_CH, g.n[2], static_cast<int>(std::ceil(110.0 / std::max(perCell, 0.1)))}));
+            CH = std::max(1, std::min({TL_MAX_CH, g.n[2],
+                                       static_cast<int>(std::ceil(double(v->tiledTargetHomes) / std::max(perCell, 0.1)))}));
             while (CH > 1 && int64_t(g.n[0]) * g.n[1] * ((g.n[2] + CH - 1) / CH) < 2 * 148) CH = (CH + 1) / 2;
             for (;;)
             {
@@ -1128,7 +1350,7 @@ int verletBuildTiled(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, const mrmd_b
                 MB_CUDA(cudaMemcpyAsync(v->hTstats, v->tstats.p, 16, cudaMemcpyDeviceToHost, st));
                 MB_CUDA(cudaStreamSynchronize(st));
                 const int slots = v->hTstats[0];
-                if (slots * TL_SMEM_PER_SLOT_BUILD <= TL_SMEM_BUDGET || CH == 1)
+                if (slots * std::max(TL_SMEM_PER_SLOT_BUILD, v->tiledSlotBytes) <= TL_SMEM_BUDGET || CH == 1)
                 {
                     MB_REQUIRE(buildSmem(slots, width) + 64 <= size_t(TL_SMEM_MAX) && slots < 65535,
                                "verlet_build_periodic: a tile exceeds shared memory");
@@ -1174,9 +1396,41 @@ int verletBuildTiled(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, const mrmd_b
 }
 }  // namespace mrmd_b200
 
+namespace mrmd_b200
+{
+int verletBuildTiledMolecules(mrmd_b200_verlet* v, mrmd_b200_molecules* m, const mrmd_b200_subdomain* s, double radius,
+                              double cellRatio, int64_t maxNeigh, int atomsPerMolecule, const int32_t* haloLeft,
+                              const int32_t* haloRight, cudaStream_t st)
+{
+    MB_REQUIRE(v != nullptr && m != nullptr && m->lcView != nullptr,
+               "verlet_build_periodic_molecules: sort the molecules first (mrmd_b200_molecules_cell_sort_with_atoms)");
+    MB_REQUIRE(atomsPerMolecule == 4, "verlet_build_periodic_molecules: four atoms per molecule");
+    m->lcView->v.pos = m->v.pos;
+    // a staged slot of the force kernel holds all atoms of a molecule: fewer homes per tile than for atoms
+    v->tiledTargetHomes = 28;
+    v->tiledSlotBytes = molSlotBytes<4>();
+    return verletBuildTiled(v, m->lcView, s, radius, cellRatio, maxNeigh, haloLeft, haloRight, st);
+}
+}  // namespace mrmd_b200
+
 using namespace mrmd_b200;
 
 extern "C" {
+
+int mrmd_b200_verlet_build_periodic_molecules(mrmd_b200_verlet* v, mrmd_b200_molecules* m, const mrmd_b200_subdomain* s,
+                                              double radius, double cellRatio, int64_t maxNeigh, int atomsPerMolecule,
+                                              void* stream)
+{
+    MB_TRY(checkDevice());
+    return verletBuildTiledMolecules(v, m, s, radius, cellRatio, maxNeigh, atomsPerMolecule, nullptr, nullptr, S(stream));
+}
+
+int mrmd_b200_verlet_read_periodic_molecules(const mrmd_b200_verlet* v, const mrmd_b200_molecules* m, int32_t* countsHost,
+                                             int32_t* partnerHost, int32_t* shiftCodeHost, void* stream)
+{
+    MB_REQUIRE(m != nullptr && m->lcView != nullptr, "verlet_read_periodic_molecules: not a molecule list");
+    return mrmd_b200_verlet_read_periodic(v, m->lcView, countsHost, partnerHost, shiftCodeHost, stream);
+}
 
 int mrmd_b200_verlet_build_periodic(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, const mrmd_b200_subdomain* s,
                                     double radius, double cellRatio, int64_t maxNeigh, void* stream)

@@ -92,8 +92,10 @@ class SlabMolecularDynamics:
 
     def __init__(self, atoms, global_min, global_max, rank, nranks, unique_id, dt=0.002, rc=2.5, skin=0.1, sigma=1.0,
                  epsilon=1.0, cappingDistance=0.7, maxNeighbors=60, langevin=False, zeta=20.0, temperature=1.5,
-                 seed=1234, adress=False, weight=None, doShift=True, thermo=None, cuts=None):
+                 seed=1234, adress=False, weight=None, doShift=True, thermo=None, cuts=None, atomsPerMolecule=1,
+                 numConstraintIterations=0, bondLength=1.0):
         cfg = _lib.MdConfig()
+        cfg.atomsPerMolecule, cfg.numConstraintIterations, cfg.bondLength = atomsPerMolecule, numConstraintIterations, bondLength
         cfg.dt, cfg.rc, cfg.skin, cfg.sigma, cfg.epsilon, cfg.cappingDistance = dt, rc, skin, sigma, epsilon, cappingDistance
         cfg.maxNeighbors, cfg.integrator, cfg.cellSort, cfg.fullList = maxNeighbors, int(langevin), 1, 2
         cfg.zeta, cfg.temperature, cfg.seed = zeta, temperature, seed
@@ -183,7 +185,7 @@ def parity_check(rank, world, steps=40, mode="lj", langevin=True, stream=None, s
                 maxNeighbors=40 if tetramer else 60, langevin=langevin, zeta=20.0, temperature=1.5, seed=4321)
     extra = {}
     if tetramer:
-        extra = dict(adress=True, weight=api.Spherical(gmax / 2, 0.25 * gmax[1], 0.15 * gmax[1], 2), doShift=True,
+        extra = dict(adress=True, weight=api.Spherical(gmax / 2, 0.2 * gmax[1], 0.12 * gmax[1], 2), doShift=True,
                      atomsPerMolecule=4, numConstraintIterations=3, bondLength=1.0)
     elif adress:
         extra = dict(adress=True, weight=api.Slab(gmax / 2, 0.2 * gmax[0], 0.1 * gmax[0], 2), doShift=True,
