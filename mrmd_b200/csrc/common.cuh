@@ -249,7 +249,11 @@ struct mrmd_b200_verlet
     // (24 for atoms; molecule lists stage all atoms of a molecule per slot in the force kernel)
     int tiledTargetHomes = 110;
     int tiledSlotBytes = 24;
-    mrmd_b200::DevBuf tstats;    // int32[4]: max slots per tile, -, overflow flag
+    int tiledSmemBudget = 48 * 1024;  // preferred shared memory of a tile's staged slots (several tiles per SM)
+    mrmd_b200::DevBuf tstats;    // int32[4]: max slots per tile, -, overflow flag, tiles with work
+    mrmd_b200::DevBuf tileActive;   // uint8[tiles]: 0 for the tiles the build left empty (coarse-grained bulk)
+    mrmd_b200::DevBuf activeTiles;  // int32[numActiveTiles], ascending
+    int numActiveTiles = 0;
     int* hTstats = nullptr;      // pinned
     mrmd_b200::DevBuf keys[2];  // radix sort ping-pong
     mrmd_b200::DevBuf vals[2];

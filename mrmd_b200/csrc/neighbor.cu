@@ -694,6 +694,8 @@ int mrmd_b200_verlet_destroy(mrmd_b200_verlet* v)
     v->sortedPos.release();
     v->stats.release();
     v->tstats.release();
+    v->tileActive.release();
+    v->activeTiles.release();
     if (v->hStats) cudaFreeHost(v->hStats);
     if (v->hTstats) cudaFreeHost(v->hTstats);
     delete v;

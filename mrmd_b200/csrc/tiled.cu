@@ -27,6 +27,7 @@
 // (local partner, image shift) and compare with the oracle's list mapped through correspondingRealAtom.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "handles.cuh"
 #include "weight.cuh"
@@ -153,10 +154,10 @@ __global__ void __launch_bounds__(32) tileDescKernel(TileParams tp, const int32_
     }
 }
 
-__device__ __forceinline__ void loadTileDesc(const int* __restrict__ desc, TileDesc& td)
+__device__ __forceinline__ void loadTileDesc(const int* __restrict__ desc, TileDesc& td, int tile)
 {
     const int t = threadIdx.x;
-    const int* d = desc + size_t(blockIdx.x) * TL_DESC_INTS;
+    const int* d = desc + size_t(tile) * TL_DESC_INTS;
     if (t < TL_PIECES)
     {
         td.pieceStart[t] = d[t];
@@ -187,9 +188,8 @@ __device__ __forceinline__ void loadTileDesc(const int* __restrict__ desc, TileD
 // shift (x < minInner for +L, x >= maxInner for -L: GhostExchange.cpp:80,89).
 template <bool BUILD, bool TYPES>
 __device__ __forceinline__ void stageTile(const TileParams& tp, const TileDesc& td, const double4* __restrict__ pos,
-                                          double* sx_, double* sy_, double* sz_, int* sIdx, unsigned char* sType)
+                                          double* sx_, double* sy_, double* sz_, int* sIdx, unsigned char* sType, int tile)
 {
-    const int tile = blockIdx.x;
     const int col = tile / tp.numChunks;
     const int ci = col / tp.g.n[1], cj = col % tp.g.n[1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(TL_THREADS_BUILD, 4)
     verletBuildTiledKernel(TileParams tp, GridDev cabanaGrid, const double4* __restrict__ pos,
                            const int32_t* __restrict__ cellLo, const int* __restrict__ desc, double rsqr, int width,
                            int32_t* __restrict__ counts, uint16_t* __restrict__ enc, int32_t* stats, int32_t* tstats,
-                           int cgSkip, mrmd_b200_weight cgWeight)
+                           unsigned char* __restrict__ tileActive, int cgSkip, mrmd_b200_weight cgWeight)
 {
     extern __shared__ double sTile[];
     __shared__ TileDesc td;
@@ -304,14 +304,16 @@ __global__ void __launch_bounds__(TL_THREADS_BUILD, 4)
             atomicMax(tstats, d[57]);  // sizes the next rebuild's tiles
             if (overflow) tstats[2] = 1;
         }
-        if (overflow || (cgSkip && tileAllCoarseGrained(tp, cgWeight, blockIdx.x)))
+        const bool skipTile = overflow || (cgSkip && tileAllCoarseGrained(tp, cgWeight, blockIdx.x));
+        if (threadIdx.x == 0) tileActive[blockIdx.x] = skipTile ? 0 : 1;
+        if (skipTile)
         {
             // AdResS step loops: no pair of a coarse-grained tile is ever evaluated, its rows stay empty
             for (int h = threadIdx.x; h < homeCount; h += blockDim.x) counts[homeStart + h] = 0;
             return;
         }
     }
-    loadTileDesc(desc, td);
+    loadTileDesc(desc, td, blockIdx.x);
     double* sx_ = sTile;
     double* sy_ = sx_ + 1;  // interleaved {x, y, z} records: one address per slot, conflict-free for consecutive slots
     double* sz_ = sx_ + 2;
@@ -347,7 +349,7 @@ __global__ void __launch_bounds__(TL_THREADS_BUILD, 4)
         }
         cellSlot[r][v] = slot;
     }
-    stageTile<true, false>(tp, td, pos, sx_, sy_, sz_, sIdx, nullptr);
+    stageTile<true, false>(tp, td, pos, sx_, sy_, sz_, sIdx, nullptr, tile);
 
     // all control flow below is warp uniform (trip counts are the maximum over the warp's four groups, lanes are
     // predicated): sub-warp *_sync masks that differ between groups would be serialised by the compiler
@@ -463,6 +465,37 @@ __global__ void __launch_bounds__(TL_THREADS_BUILD, 4)
         atomicMax(stats, mx);
         atomicAdd(reinterpret_cast<unsigned long long*>(stats + 2), static_cast<unsigned long long>(total));
     }
+}
+
+// ordered list of the tiles with work (one block): the AdResS force kernels launch over it instead of over all tiles
+__global__ void __launch_bounds__(1024) compactActiveTilesKernel(const unsigned char* __restrict__ tileActive, int tiles,
+                                                                 int32_t* __restrict__ activeTiles, int32_t* count)
+{
+    __shared__ int sWarp[32];
+    __shared__ int sBase;
+    if (threadIdx.x == 0) sBase = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < tiles; base += blockDim.x)
+    {
+        const int t = base + threadIdx.x;
+        const bool on = t < tiles && tileActive[t] != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, on);
+        if (lane == 0) sWarp[warp] = __popc(m);
+        __syncthreads();
+        int off = sBase;
+        for (int w = 0; w < warp; ++w) off += sWarp[w];
+        if (on) activeTiles[off + __popc(m & ((1u << lane) - 1u))] = t;
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            int tot = 0;
+            for (int w = 0; w < int(blockDim.x >> 5); ++w) tot += sWarp[w];
+            sBase += tot;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = sBase;
 }
 
 // reciprocal from the hardware seed (20 mantissa bits, error e <= 2^-20) with one cubically convergent step
@@ -583,12 +616,12 @@ __global__ void __launch_bounds__(TL_THREADS_FORCE)
 {
     extern __shared__ double sTile[];
     __shared__ TileDesc td;
-    loadTileDesc(desc, td);
+    loadTileDesc(desc, td, blockIdx.x);
     double* sx_ = sTile;
     double* sy_ = sx_ + 1;  // interleaved {x, y, z} records: one address per slot, conflict-free for consecutive slots
     double* sz_ = sx_ + 2;
     unsigned char* sType = reinterpret_cast<unsigned char*>(sx_ + 3 * tp.cap);
-    stageTile<false, !SINGLE_TYPE>(tp, td, a.pos, sx_, sy_, sz_, nullptr, sType);
+    stageTile<false, !SINGLE_TYPE>(tp, td, a.pos, sx_, sy_, sz_, nullptr, sType, blockIdx.x);
 
     // warp-uniform control flow, see verletBuildTiledKernel
     const int group = threadIdx.x / TL_GROUP, gl = threadIdx.x % TL_GROUP;
@@ -667,9 +700,8 @@ constexpr int TL_SMEM_PER_SLOT_ADRESS = 33;  // x, y, z, lambda^mod + type byte
 // reference's ghost molecules
 template <bool TYPES>
 __device__ __forceinline__ void stageTileAdress(const TileParams& tp, const TileDesc& td, const double4* __restrict__ pos,
-                                                const mrmd_b200_weight& w, double* rec, unsigned char* sType)
+                                                const mrmd_b200_weight& w, double* rec, unsigned char* sType, int tile)
 {
-    const int tile = blockIdx.x;
     const int col = tile / tp.numChunks;
     const int ci = col / tp.g.n[1], cj = col % tp.g.n[1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -738,20 +770,23 @@ template <bool SINGLE_TYPE, bool SAMPLING, bool ENERGY>
 __global__ void __launch_bounds__(TL_THREADS_FORCE, 6)
     adressForceTiledKernel(TileParams tp, AtomsView a, const int* __restrict__ desc, const int32_t* __restrict__ counts,
                            const uint16_t* __restrict__ enc, int width, LJTable table, double rcSqr, int64_t numTypes,
-                           mrmd_b200_weight w, double* hist, double* partials, double* result, unsigned int* ticket)
+                           mrmd_b200_weight w, double* hist, const int32_t* __restrict__ activeTiles, double* partials,
+                           double* result, unsigned int* ticket)
 {
     extern __shared__ double sTile[];
     __shared__ TileDesc td;
     double energy = 0.0, pairs = 0.0, activePairs = 0.0;
+    // activeTiles (step-loop drivers): the tiles the neighbour build found outside the coarse-grained bulk
+    const int tile = (activeTiles != nullptr) ? activeTiles[blockIdx.x] : blockIdx.x;
     // slab weighting: when the three staged columns (padded by one more cell on each side for the drift since the
     // last sort) lie beyond the hybrid region, every pair of the tile is an ideal-gas pair
-    const bool skip = tileAllCoarseGrained(tp, w, blockIdx.x);
+    const bool skip = tileAllCoarseGrained(tp, w, tile);
     if (!skip)
     {
-        loadTileDesc(desc, td);
+        loadTileDesc(desc, td, tile);
         double* rec = sTile;
         unsigned char* sType = reinterpret_cast<unsigned char*>(rec + 4 * tp.cap);
-        stageTileAdress<!SINGLE_TYPE>(tp, td, a.pos, w, rec, sType);
+        stageTileAdress<!SINGLE_TYPE>(tp, td, a.pos, w, rec, sType, tile);
 
         const int group = threadIdx.x / TL_GROUP, gl = threadIdx.x % TL_GROUP;
         const LJType t0 = table.t[0];
@@ -850,18 +885,21 @@ __global__ void __launch_bounds__(TL_THREADS_FORCE, 6)
 // (LJ_IdealGas.cpp:96-205 seen from the row owner), sum(V_ij) is combined over the lanes for the drift force
 // -sum(V_ij) grad(lambda_alpha) and the drift compensation (:209-222), and ContributeMoleculeForceToAtoms hands the
 // molecule force to the atoms by relative mass.  Full list: no atomics on forces, no ghost molecules, no reverse halo.
-constexpr int TL_THREADS_MOL = 128;
+#ifndef MRMD_TL_THREADS_MOL
+#define MRMD_TL_THREADS_MOL 128
+#endif
+constexpr int TL_THREADS_MOL = MRMD_TL_THREADS_MOL;
 template <int NA>
 constexpr int molSlotDoubles() { return 3 * NA + 1; }
 template <int NA>
 constexpr int molSlotBytes() { return molSlotDoubles<NA>() * 8 + NA; }  // + one type byte per atom
 
-template <int NA, bool SAMPLING, bool ENERGY>
+template <int NA, bool SINGLE_TYPE, bool SAMPLING, bool ENERGY>
 __global__ void __launch_bounds__(TL_THREADS_MOL)
     moleculeForceTiledKernel(TileParams tp, AtomsView a, const double4* __restrict__ com, const int* __restrict__ desc,
                              const int32_t* __restrict__ counts, const uint16_t* __restrict__ enc, int width, LJTable table,
-                             double rcSqr, int64_t numTypes, mrmd_b200_weight w, double* hist, double* partials,
-                             double* result, unsigned int* ticket)
+                             double rcSqr, int64_t numTypes, mrmd_b200_weight w, double* hist, int maxHomes,
+                             const int32_t* __restrict__ activeTiles, double* partials, double* result, unsigned int* ticket)
 {
     static_assert(NA == 2 || NA == 4 || NA == 8, "lanes per molecule: a power of two");
     constexpr int REC = molSlotDoubles<NA>();
@@ -869,14 +907,25 @@ __global__ void __launch_bounds__(TL_THREADS_MOL)
     __shared__ TileDesc td;
     double energy = 0.0;
     int pairs = 0, activePairs = 0;
-    if (!tileAllCoarseGrained(tp, w, blockIdx.x))
+    const int tile = (activeTiles != nullptr) ? activeTiles[blockIdx.x] : blockIdx.x;
+    if (!tileAllCoarseGrained(tp, w, tile))
     {
-        loadTileDesc(desc, td);
+        loadTileDesc(desc, td, tile);
         double* rec = sTile;
-        unsigned char* sType = reinterpret_cast<unsigned char*>(rec + size_t(REC) * tp.cap);
+        // behind the slots: the list rows of the tile's home molecules (copied with 16-byte loads, read as broadcasts by
+        // the lanes of a molecule), then the type bytes
+        uint16_t* sRows = reinterpret_cast<uint16_t*>(rec + size_t(REC) * tp.cap);
+        unsigned char* sType = reinterpret_cast<unsigned char*>(sRows + size_t(maxHomes) * width);
+        {
+            const int wordsPerRow = width / 8;
+            const uint4* src = reinterpret_cast<const uint4*>(enc + size_t(td.homeStart) * width);
+            uint4* dst = reinterpret_cast<uint4*>(sRows);
+            const int homesHere = min(td.homeCount, maxHomes);
+            for (int e = threadIdx.x; e < homesHere * wordsPerRow; e += blockDim.x) dst[e] = src[e];
+        }
         {
             // staging: one piece per warp, a lane per (molecule, atom)
-            const int col = blockIdx.x / tp.numChunks;
+            const int col = tile / tp.numChunks;
             const int ci = col / tp.g.n[1], cj = col % tp.g.n[1];
             const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
             for (int p = warp; p < TL_PIECES; p += blockDim.x / 32)
@@ -895,7 +944,7 @@ __global__ void __launch_bounds__(TL_THREADS_MOL)
                     r[3 * j] = raw.x + shx;
                     r[3 * j + 1] = raw.y + shy;
                     r[3 * j + 2] = raw.z + shz;
-                    sType[(slot0 + k) * NA + j] = static_cast<unsigned char>(typeOf(raw));
+                    if (!SINGLE_TYPE) sType[(slot0 + k) * NA + j] = static_cast<unsigned char>(typeOf(raw));
                     if (j == 0)
                     {
                         const double4 c = ld4nc(com + start + k);
@@ -907,6 +956,7 @@ __global__ void __launch_bounds__(TL_THREADS_MOL)
         }
         const int group = threadIdx.x / NA, li = threadIdx.x % NA;
         const int64_t T = numTypes;
+        const LJType t0 = table.t[0];
         const double inverseBinSize = 1.0 / ((1.0 - 0.0) / double(TL_COMPENSATION_BINS));
         for (int hBase = 0; hBase < td.homeCount; hBase += blockDim.x / NA)
         {
@@ -916,14 +966,15 @@ __global__ void __launch_bounds__(TL_THREADS_MOL)
             const int selfSlot = td.selfSlot0 + (active ? h : 0);
             const double* me = rec + size_t(REC) * selfSlot + 3 * li;
             const double xi = me[0], yi = me[1], zi = me[2];
-            const int typeI = sType[selfSlot * NA + li];
+            const int typeI = SINGLE_TYPE ? 0 : sType[selfSlot * NA + li];
             const double4 c = ld4nc(com + u);
             double lambda, modA, gx, gy, gz;
             weightEval(w, c.x, c.y, c.z, lambda, modA, gx, gy, gz);
             const bool hyA = inHY(modA), cgA = inCG(modA);
             double fx = 0.0, fy = 0.0, fz = 0.0, vsum = 0.0;
             const int numNeighbors = active ? min(counts[u], width) : 0;
-            const uint16_t* row = enc + size_t(u) * width;
+            // rows of homes beyond the staged ones (a tile with more homes than any tile of the build) come from global
+            const uint16_t* row = (h < maxHomes) ? sRows + size_t(active ? h : 0) * width : enc + size_t(u) * width;
             const int iters = __reduce_max_sync(0xffffffffu, numNeighbors);
             for (int n = 0; n < iters; ++n)
             {
@@ -934,6 +985,7 @@ __global__ void __launch_bounds__(TL_THREADS_MOL)
                 if (cgA && inCG(modB)) continue;  // ideal gas, LJ_IdealGas.cpp:102-107
                 if (li == 0) activePairs += 1;
                 const double weighting = 0.5 * (modA + modB);
+                // the NA partner atoms are evaluated predicated, not branched: their FP64 chains interleave
 #pragma unroll
                 for (int j = 0; j < NA; ++j)
                 {
@@ -941,25 +993,26 @@ __global__ void __launch_bounds__(TL_THREADS_MOL)
                     const double dy = yi - q[3 * j + 1];
                     const double dz = zi - q[3 * j + 2];
                     const double distSqr = distSqrExact(dx, dy, dz);
-                    if (distSqr > rcSqr) continue;  // :137
-                    const LJType& t = table.t[typeI * T + sType[slot * NA + j]];
+                    const bool in = distSqr <= rcSqr;  // :137 skips distSqr > rcSqr
+                    const LJType& t = SINGLE_TYPE ? t0 : table.t[typeI * T + sType[slot * NA + j]];
+                    const double d2 = in ? distSqr : rcSqr;  // keeps the arithmetic of a skipped pair finite
                     double ff, e;
-                    if (distSqr >= t.cappingDistanceSqr)
+                    if (d2 >= t.cappingDistanceSqr)
                     {
-                        const double frac2 = fastRcp(distSqr);
+                        const double frac2 = fastRcp(d2);
                         const double frac6 = frac2 * frac2 * frac2;
                         ff = frac6 * (t.ff1 * frac6 - t.ff2) * frac2;
                         e = frac6 * (t.ef1 * frac6 - t.ef2) - t.shift;
                     }
                     else
-                        ljForceEnergy(t, distSqr, ff, e);
-                    const double ffactor = ff * weighting;
+                        ljForceEnergy(t, d2, ff, e);
+                    const double ffactor = in ? ff * weighting : 0.0;
                     fx += dx * ffactor;
                     fy += dy * ffactor;
                     fz += dz * ffactor;
-                    pairs += 1;
-                    if (ENERGY) energy += e * weighting;
-                    if (hyA) vsum += 0.5 * e;  // V_ij of the drift force and of the compensation sampling, :160-200
+                    pairs += in ? 1 : 0;
+                    if (ENERGY) energy += in ? e * weighting : 0.0;
+                    if (hyA) vsum += in ? 0.5 * e : 0.0;  // V_ij of the drift force and of the compensation sampling, :160-200
                 }
             }
             // drift force -sum(V_ij) grad(lambda) (:163-169) plus the drift compensation mean[bin] grad(lambda) of the
@@ -977,7 +1030,7 @@ __global__ void __launch_bounds__(TL_THREADS_MOL)
                     const long long bin = histBin(0.0, inverseBinSize, TL_COMPENSATION_BINS, lambda);
                     if (bin != -1)
                     {
-                        scale += hist[2 * TL_COMPENSATION_BINS * T + bin * T + sType[selfSlot * NA]];
+                        scale += hist[2 * TL_COMPENSATION_BINS * T + bin * T + (SINGLE_TYPE ? 0 : sType[selfSlot * NA])];
                         if (SAMPLING)
                         {
                             atomicAdd(hist + bin * T + typeI, vsum);
@@ -1008,7 +1061,7 @@ __global__ void __launch_bounds__(TL_THREADS_BUILD)
                       const uint16_t* __restrict__ enc, int width, int32_t* partner, int32_t* shiftCode)
 {
     __shared__ TileDesc td;
-    loadTileDesc(desc, td);
+    loadTileDesc(desc, td, blockIdx.x);
     const int col = blockIdx.x / tp.numChunks;
     const int ci = col / tp.g.n[1], cj = col % tp.g.n[1];
     for (int h = threadIdx.x; h < td.homeCount; h += blockDim.x)
@@ -1102,10 +1155,14 @@ int tiledConfigure()
     TL_SET((adressForceTiledKernel<false, true, false>));
     TL_SET((adressForceTiledKernel<false, false, true>));
     TL_SET((adressForceTiledKernel<false, false, false>));
-    TL_SET((moleculeForceTiledKernel<4, true, true>));
-    TL_SET((moleculeForceTiledKernel<4, true, false>));
-    TL_SET((moleculeForceTiledKernel<4, false, true>));
-    TL_SET((moleculeForceTiledKernel<4, false, false>));
+    TL_SET((moleculeForceTiledKernel<4, true, true, true>));
+    TL_SET((moleculeForceTiledKernel<4, true, true, false>));
+    TL_SET((moleculeForceTiledKernel<4, true, false, true>));
+    TL_SET((moleculeForceTiledKernel<4, true, false, false>));
+    TL_SET((moleculeForceTiledKernel<4, false, true, true>));
+    TL_SET((moleculeForceTiledKernel<4, false, true, false>));
+    TL_SET((moleculeForceTiledKernel<4, false, false, true>));
+    TL_SET((moleculeForceTiledKernel<4, false, false, false>));
 #undef TL_SET
     done = true;
     return 0;
@@ -1169,16 +1226,19 @@ int adressApplyTiled(mrmd_b200_adress* ad, mrmd_b200_atoms* a, const mrmd_b200_v
     MB_TRY(tiledConfigure());
     TileParams tp;
     MB_TRY(makeTileParams(a, &v->tiledSub, v->tiledCH, v->tiledSlots, v->tiledHaloX, v->tiledR, tp));
-    const int tiles = tp.g.n[0] * tp.g.n[1] * tp.numChunks;
-    MB_TRY(ad->partials.reserve(size_t(tiles) * 3 * 8));
+    // the step-loop drivers' lists know their tiles outside the coarse-grained bulk: launch over those only
+    const int tiles = v->tiledCgSkip ? v->numActiveTiles : tp.g.n[0] * tp.g.n[1] * tp.numChunks;
+    const int32_t* activeTiles = v->tiledCgSkip ? v->activeTiles.as<int32_t>() : nullptr;
+    MB_TRY(ad->partials.reserve(size_t(std::max(tiles, 1)) * 3 * 8));
     MB_CUDA(cudaMemsetAsync(ad->dResult, 0, 24, st));
+    if (tiles == 0) return 0;
     const size_t smem = size_t(v->tiledSlots) * TL_SMEM_PER_SLOT_ADRESS + 16;
     MB_REQUIRE(smem <= size_t(TL_SMEM_MAX), "adress_run_periodic: a tile exceeds shared memory");
     const bool single = (ad->numTypes == 1);
 #define ADT_LAUNCH(S1, SAMP, EN)                                                                                      \
     adressForceTiledKernel<S1, SAMP, EN><<<tiles, TL_THREADS_FORCE, smem, st>>>(                                      \
         tp, a->v, v->tileDesc.as<int>(), v->counts.as<int32_t>(), v->enc.as<uint16_t>(), static_cast<int>(v->width), \
-        ad->table, ad->rcSqr, ad->numTypes, *w, ad->hist, ad->partials.as<double>(), ad->dResult, ad->dTicket)
+        ad->table, ad->rcSqr, ad->numTypes, *w, ad->hist, activeTiles, ad->partials.as<double>(), ad->dResult, ad->dTicket)
     if (single)
     {
         if (sampling) { if (energy) ADT_LAUNCH(true, true, true); else ADT_LAUNCH(true, true, false); }
@@ -1221,17 +1281,31 @@ int moleculeApplyTiled(mrmd_b200_adress* ad, const mrmd_b200_molecules* m, mrmd_
     MB_TRY(tiledConfigure());
     TileParams tp;
     MB_TRY(makeTileParams(lv, &v->tiledSub, v->tiledCH, v->tiledSlots, v->tiledHaloX, v->tiledR, tp));
-    const int tiles = tp.g.n[0] * tp.g.n[1] * tp.numChunks;
-    MB_TRY(ad->partials.reserve(size_t(tiles) * 3 * 8));
+    const int tiles = v->tiledCgSkip ? v->numActiveTiles : tp.g.n[0] * tp.g.n[1] * tp.numChunks;
+    const int32_t* activeTiles = v->tiledCgSkip ? v->activeTiles.as<int32_t>() : nullptr;
+    MB_TRY(ad->partials.reserve(size_t(std::max(tiles, 1)) * 3 * 8));
     MB_CUDA(cudaMemsetAsync(ad->dResult, 0, 24, st));
-    const size_t smem = size_t(v->tiledSlots) * molSlotBytes<4>() + 16;
+    if (tiles == 0) return 0;
+    // homes whose list rows are staged: the tallest tile holds about twice the aimed-at number (the rest reads global)
+    const int maxHomes = std::min(2 * v->tiledTargetHomes + 16, 64);
+    const size_t smem = size_t(v->tiledSlots) * molSlotBytes<4>() + size_t(maxHomes) * size_t(v->width) * 2 + 16;
     MB_REQUIRE(smem <= size_t(TL_SMEM_MAX), "adress_run_periodic_molecules: a tile exceeds shared memory");
-#define MOL_LAUNCH(SAMP, EN)                                                                                             \
-    moleculeForceTiledKernel<4, SAMP, EN><<<tiles, TL_THREADS_MOL, smem, st>>>(                                          \
+    const bool single = (ad->numTypes == 1);
+#define MOL_LAUNCH(S1, SAMP, EN)                                                                                         \
+    moleculeForceTiledKernel<4, S1, SAMP, EN><<<tiles, TL_THREADS_MOL, smem, st>>>(                                      \
         tp, a->v, m->v.pos, v->tileDesc.as<int>(), v->counts.as<int32_t>(), v->enc.as<uint16_t>(), static_cast<int>(v->width), \
-        ad->table, ad->rcSqr, ad->numTypes, *w, ad->hist, ad->partials.as<double>(), ad->dResult, ad->dTicket)
-    if (sampling) { if (energy) MOL_LAUNCH(true, true); else MOL_LAUNCH(true, false); }
-    else { if (energy) MOL_LAUNCH(false, true); else MOL_LAUNCH(false, false); }
+        ad->table, ad->rcSqr, ad->numTypes, *w, ad->hist, maxHomes, activeTiles, ad->partials.as<double>(), ad->dResult,    \
+        ad->dTicket)
+    if (single)
+    {
+        if (sampling) { if (energy) MOL_LAUNCH(true, true, true); else MOL_LAUNCH(true, true, false); }
+        else { if (energy) MOL_LAUNCH(true, false, true); else MOL_LAUNCH(true, false, false); }
+    }
+    else
+    {
+        if (sampling) { if (energy) MOL_LAUNCH(false, true, true); else MOL_LAUNCH(false, true, false); }
+        else { if (energy) MOL_LAUNCH(false, false, true); else MOL_LAUNCH(false, false, false); }
+    }
 #undef MOL_LAUNCH
     MB_LAUNCHED();
     return 0;
@@ -1350,7 +1424,7 @@ int verletBuildTiled(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, const mrmd_b
                 MB_CUDA(cudaMemcpyAsync(v->hTstats, v->tstats.p, 16, cudaMemcpyDeviceToHost, st));
                 MB_CUDA(cudaStreamSynchronize(st));
                 const int slots = v->hTstats[0];
-                if (slots * std::max(TL_SMEM_PER_SLOT_BUILD, v->tiledSlotBytes) <= TL_SMEM_BUDGET || CH == 1)
+                if (slots * std::max(TL_SMEM_PER_SLOT_BUILD, v->tiledSlotBytes) <= v->tiledSmemBudget || CH == 1)
                 {
                     MB_REQUIRE(buildSmem(slots, width) + 64 <= size_t(TL_SMEM_MAX) && slots < 65535,
                                "verlet_build_periodic: a tile exceeds shared memory");
@@ -1365,6 +1439,8 @@ int verletBuildTiled(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, const mrmd_b
         for (int d = 0; d < 3; ++d) v->tiledGridN[d] = g.n[d];
         tp.cap = v->tiledSlots;
         MB_TRY(v->enc.reserve(size_t(width) * std::max<int64_t>(n, 1) * 2));
+        MB_TRY(v->tileActive.reserve(size_t(tiles)));
+        MB_TRY(v->activeTiles.reserve(size_t(tiles) * 4));
         v->width = width;
         MB_CUDA(cudaMemsetAsync(v->stats.p, 0, 16, st));
         MB_CUDA(cudaMemsetAsync(v->tstats.p, 0, 16, st));
@@ -1373,10 +1449,14 @@ int verletBuildTiled(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, const mrmd_b
 #define VBT_LAUNCH(H)                                                                                                  \
     verletBuildTiledKernel<H><<<tiles, TL_THREADS_BUILD, smem, st>>>(                                                  \
         tp, cabanaGrid, a->v.pos, cellLo, v->tileDesc.as<int>(), rsqr, static_cast<int>(width), v->counts.as<int32_t>(), \
-        v->enc.as<uint16_t>(), v->stats.as<int32_t>(), v->tstats.as<int32_t>(), v->tiledCgSkip ? 1 : 0, v->tiledCgWeight)
+        v->enc.as<uint16_t>(), v->stats.as<int32_t>(), v->tstats.as<int32_t>(), v->tileActive.as<unsigned char>(),     \
+        v->tiledCgSkip ? 1 : 0, v->tiledCgWeight)
         if (v->half) VBT_LAUNCH(true);
         else VBT_LAUNCH(false);
 #undef VBT_LAUNCH
+        MB_LAUNCHED();
+        compactActiveTilesKernel<<<1, 1024, 0, st>>>(v->tileActive.as<unsigned char>(), tiles, v->activeTiles.as<int32_t>(),
+                                                     v->tstats.as<int32_t>() + 3);
         MB_LAUNCHED();
         MB_CUDA(cudaMemcpyAsync(v->hStats, v->stats.p, 16, cudaMemcpyDeviceToHost, st));
         MB_CUDA(cudaMemcpyAsync(v->hTstats, v->tstats.p, 16, cudaMemcpyDeviceToHost, st));
@@ -1387,6 +1467,7 @@ int verletBuildTiled(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, const mrmd_b
             v->hTstats[0] = 0;
             continue;
         }
+        v->numActiveTiles = v->hTstats[3];
         if (v->hStats[0] <= width) return 0;
         width = (int64_t(v->hStats[0]) + 63) & ~int64_t(63);
         MB_REQUIRE(width <= 1024, "verlet_build_periodic: more than 1024 neighbours per atom");
@@ -1407,8 +1488,12 @@ int verletBuildTiledMolecules(mrmd_b200_verlet* v, mrmd_b200_molecules* m, const
     MB_REQUIRE(atomsPerMolecule == 4, "verlet_build_periodic_molecules: four atoms per molecule");
     m->lcView->v.pos = m->v.pos;
     // a staged slot of the force kernel holds all atoms of a molecule: fewer homes per tile than for atoms
-    v->tiledTargetHomes = 28;
+    v->tiledTargetHomes = 56;  // measured 16 / 28 / 56: 0.44 / 0.35 / 0.32 ms per 4M atoms (TL_MAX_CH caps the tile height)
     v->tiledSlotBytes = molSlotBytes<4>();
+    v->tiledSmemBudget = TL_SMEM_BUDGET;
+    // measurement knobs: homes per tile aimed at, shared-memory budget of a tile in KB
+    if (const char* e = std::getenv("MRMD_B200_MOL_HOMES")) v->tiledTargetHomes = std::max(4, std::atoi(e));
+    if (const char* e = std::getenv("MRMD_B200_MOL_SMEM_KB")) v->tiledSmemBudget = std::min(TL_SMEM_MAX, std::max(16, std::atoi(e)) * 1024);
     return verletBuildTiled(v, m->lcView, s, radius, cellRatio, maxNeigh, haloLeft, haloRight, st);
 }
 }  // namespace mrmd_b200
