@@ -82,7 +82,7 @@ int main(int argc, char* argv[])
     tf1.setForce(forces);
     io::dumpThermoForce(argv[3], tf1);
     auto tf2 = io::restoreThermoForce(argv[3], tfDomain, {1_r, 1_r}, {1_r, 1_r});
-    const auto back = tf2.getForce();
+    const auto back = tf2.getForce().data.toHost();  // data::MultiHistogram, numBins x numTypes row-major
     const auto grid1 = tf1.createGrid(), grid2 = tf2.createGrid();
     real_t maxForceDiff = 0_r, maxGridDiff = 0_r;
     for (size_t k = 0; k < forces.size(); ++k) maxForceDiff = std::max(maxForceDiff, std::abs(back[k] - forces[k]));

@@ -378,6 +378,141 @@ inline Molecules createMoleculeForEachAtom(Atoms& atoms)
     m.pull();
     return m;
 }
+
+/// data::MultiHistogram (data/MultiHistogram.hpp:29-92): numBins x numHistograms values over [min, max) on the device.
+/// `data` stands in for the Kokkos MultiView: data(bin, histogram) reads one entry, toHost() / fromHost() are
+/// create_mirror_view_and_copy / deep_copy with a dense row-major host vector.
+struct MultiHistogram
+{
+    struct View
+    {
+        std::shared_ptr<mrmd_b200_hist> h;
+        idx_t numBins = 0, numHistograms = 0;
+        std::vector<real_t> toHost() const
+        {
+            std::vector<real_t> out(static_cast<size_t>(numBins * numHistograms));
+            detail::check(mrmd_b200_hist_read(h.get(), out.data(), MRMD_B200_MEM_HOST, defaultStream), "MultiHistogram::data");
+            return out;
+        }
+        void fromHost(const std::vector<real_t>& values) const
+        {
+            if (idx_c(values.size()) != numBins * numHistograms) detail::fail(MRMD_B200_EINVAL, "MultiHistogram::data: extents differ");
+            detail::check(mrmd_b200_hist_write(h.get(), values.data(), MRMD_B200_MEM_HOST, defaultStream), "MultiHistogram::data");
+        }
+        real_t operator()(idx_t bin, idx_t histogram) const { return toHost()[static_cast<size_t>(bin * numHistograms + histogram)]; }
+        idx_t extent(int dim) const { return dim == 0 ? numBins : numHistograms; }
+    };
+
+    MultiHistogram(const std::string& label, const real_t minArg, const real_t maxArg, idx_t numBinsArg, idx_t numHistogramsArg)
+        : min(minArg), max(maxArg), numBins(numBinsArg), numHistograms(numHistogramsArg),
+          binSize((maxArg - minArg) / real_c(numBinsArg)), inverseBinSize(1_r / ((maxArg - minArg) / real_c(numBinsArg))), label_(label)
+    {
+        mrmd_b200_hist* h = nullptr;
+        detail::check(mrmd_b200_hist_create(&h, minArg, maxArg, numBinsArg, numHistogramsArg), "MultiHistogram");
+        adopt(h);
+    }
+    MultiHistogram(const std::string& label, const MultiHistogram& histogram)
+        : min(histogram.min), max(histogram.max), numBins(histogram.numBins), numHistograms(histogram.numHistograms),
+          binSize(histogram.binSize), inverseBinSize(histogram.inverseBinSize), label_(label)
+    {
+        mrmd_b200_hist* h = nullptr;
+        detail::check(mrmd_b200_hist_clone(&h, histogram.handle(), defaultStream), "MultiHistogram");
+        adopt(h);
+    }
+    /// takes over a handle produced by the C ABI (gradient, smoothen, ThermodynamicForce::getForce)
+    MultiHistogram(const std::string& label, mrmd_b200_hist* h) : min(info(h, 0)), max(info(h, 1)), numBins(extent(h, 0)),
+          numHistograms(extent(h, 1)), binSize(info(h, 2)), inverseBinSize(info(h, 3)), label_(label)
+    {
+        adopt(h);
+    }
+
+    idx_t getBin(const real_t& val) const { return mrmd_b200_hist_get_bin(handle(), val); }
+    real_t getBinPosition(idx_t binIdx) const { return mrmd_b200_hist_get_bin_position(handle(), binIdx); }
+
+    const real_t min;
+    const real_t max;
+    const idx_t numBins;
+    const idx_t numHistograms;
+    const real_t binSize;
+    const real_t inverseBinSize;
+    View data;
+
+    MultiHistogram& operator+=(const MultiHistogram& rhs) { return transform(rhs, 0); }
+    MultiHistogram& operator-=(const MultiHistogram& rhs) { return transform(rhs, 1); }
+    MultiHistogram& operator*=(const MultiHistogram& rhs) { return transform(rhs, 2); }
+    MultiHistogram& operator/=(const MultiHistogram& rhs) { return transform(rhs, 3); }
+    void scale(const real_t& scalingFactor) { detail::check(mrmd_b200_hist_scale(handle(), scalingFactor, defaultStream), "MultiHistogram::scale"); }
+    void scale(const std::vector<real_t>& scalingFactor)
+    {
+        detail::check(mrmd_b200_hist_scale_per_histogram(handle(), scalingFactor.data(), idx_c(scalingFactor.size()), defaultStream), "MultiHistogram::scale");
+    }
+    void makeSymmetric() { detail::check(mrmd_b200_hist_make_symmetric(handle(), defaultStream), "MultiHistogram::makeSymmetric"); }
+    mrmd_b200_hist* handle() const { return data.h.get(); }
+    const std::string& label() const { return label_; }
+
+private:
+    void adopt(mrmd_b200_hist* h)
+    {
+        data.h.reset(h, [](mrmd_b200_hist* p) { mrmd_b200_hist_destroy(p); });
+        data.numBins = numBins;
+        data.numHistograms = numHistograms;
+    }
+    MultiHistogram& transform(const MultiHistogram& rhs, int op)
+    {
+        detail::check(mrmd_b200_hist_transform(handle(), rhs.handle(), op, defaultStream), "MultiHistogram::transform");
+        return *this;
+    }
+    static real_t info(const mrmd_b200_hist* h, int which)
+    {
+        double v[4] = {0, 0, 0, 0};
+        detail::check(mrmd_b200_hist_info(h, &v[0], &v[1], nullptr, nullptr, &v[2], &v[3]), "MultiHistogram");
+        return v[which];
+    }
+    static idx_t extent(const mrmd_b200_hist* h, int which)
+    {
+        int64_t n[2] = {0, 0};
+        detail::check(mrmd_b200_hist_info(h, nullptr, nullptr, &n[0], &n[1], nullptr, nullptr), "MultiHistogram");
+        return n[which];
+    }
+    std::string label_;
+};
+
+/// data/MultiHistogram.cpp:92-111
+inline void cumulativeMovingAverage(MultiHistogram& average, const MultiHistogram& current, const real_t movingAverageFactor = 10_r)
+{
+    detail::check(mrmd_b200_hist_cumulative_moving_average(average.handle(), current.handle(), movingAverageFactor, defaultStream), "cumulativeMovingAverage");
+}
+/// :113-161
+inline MultiHistogram gradient(const MultiHistogram& input, const bool periodic = false)
+{
+    mrmd_b200_hist* h = nullptr;
+    detail::check(mrmd_b200_hist_gradient(&h, input.handle(), periodic, defaultStream), "gradient");
+    return MultiHistogram("gradient", h);
+}
+/// :163-212
+inline MultiHistogram smoothen(MultiHistogram& input, const real_t& sigma, const real_t& range, const bool periodic = false)
+{
+    mrmd_b200_hist* h = nullptr;
+    detail::check(mrmd_b200_hist_smoothen(&h, input.handle(), sigma, range, periodic, defaultStream), "smoothen");
+    return MultiHistogram("smooth-input", h);
+}
+/// :214-227 (the ScalarView of bin positions, on the host)
+inline std::vector<real_t> createGrid(const MultiHistogram& input)
+{
+    std::vector<real_t> grid(static_cast<size_t>(input.numBins));
+    detail::check(mrmd_b200_hist_create_grid(input.handle(), grid.data(), defaultStream), "createGrid");
+    return grid;
+}
+/// data/MultiHistogram.hpp:176-191 with a parametric one-coordinate predicate (util::IsInSymmetricSlab, or any
+/// mrmd_b200_pred such as MRMD_B200_PRED_INTERVAL) in place of the device lambda
+inline void replace_if_bin_position(MultiHistogram& hist, const mrmd_b200_pred& pred, real_t newValue)
+{
+    detail::check(mrmd_b200_hist_replace_if_bin_position(hist.handle(), &pred, newValue, defaultStream), "replace_if_bin_position");
+}
+inline void replace_if_bin_position(MultiHistogram& hist, const util::IsInSymmetricSlab& pred, real_t newValue)
+{
+    replace_if_bin_position(hist, pred.desc(), newValue);
+}
 }  // namespace data
 
 // ------------------------------------------------------------------------------------------------------
@@ -811,14 +946,30 @@ public:
         for (size_t i = 0; i < grid.size(); ++i) grid[i] = gridMin_ + (real_c(i) + 0.5_r) * b;
         return grid;
     }
-    /// numBins x numTypes, row-major
-    std::vector<real_t> getForce() const { return read(0); }
-    std::vector<real_t> getDensityProfile() const { return read(1); }
+    /// ThermodynamicForce.hpp:57-63: the table / the running density profile as a data::MultiHistogram (a copy)
+    data::MultiHistogram getForce() const { return hist(0, "thermodynamic-force"); }
+    data::MultiHistogram getDensityProfile() const { return hist(1, "density-profile"); }
+    /// getForce(typeId) / getDensityProfile(typeId) (:58, :64): one histogram, on the host
+    std::vector<real_t> getForce(const idx_t& typeId) const { return column(read(0), typeId); }
+    std::vector<real_t> getDensityProfile(const idx_t& typeId) const { return column(read(1), typeId); }
     void setForce(const std::vector<real_t>& forces) const { detail::check(mrmd_b200_thermo_write_force(h_.get(), forces.data(), defaultStream), "setForce"); }
     std::vector<real_t> getMuLeft() const { return mu().first; }
     std::vector<real_t> getMuRight() const { return mu().second; }
 
 private:
+    data::MultiHistogram hist(int kind, const char* label) const
+    {
+        mrmd_b200_hist* h = nullptr;
+        detail::check(mrmd_b200_thermo_get_hist(h_.get(), kind, &h, defaultStream), label);
+        return data::MultiHistogram(label, h);
+    }
+    std::vector<real_t> column(const std::vector<real_t>& all, idx_t typeId) const
+    {
+        const idx_t nb = numBins(), nt = numTypes();
+        std::vector<real_t> out(static_cast<size_t>(nb));
+        for (idx_t i = 0; i < nb; ++i) out[static_cast<size_t>(i)] = all[static_cast<size_t>(i * nt + typeId)];
+        return out;
+    }
     std::vector<real_t> read(int kind) const
     {
         int64_t nb = 0, nt = 0;

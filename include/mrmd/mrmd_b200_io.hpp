@@ -192,11 +192,7 @@ inline void dumpLine(std::ofstream& f, const std::vector<real_t>& values, real_t
 }
 inline std::vector<real_t> forceOfType(const action::ThermodynamicForce& tf, idx_t typeId)
 {
-    const auto all = tf.getForce();  // numBins x numTypes, row-major
-    const idx_t nb = tf.numBins(), nt = tf.numTypes();
-    std::vector<real_t> out(static_cast<size_t>(nb));
-    for (idx_t i = 0; i < nb; ++i) out[static_cast<size_t>(i)] = all[static_cast<size_t>(i * nt + typeId)];
-    return out;
+    return tf.getForce(typeId);
 }
 }  // namespace detail
 

@@ -337,6 +337,45 @@ int mrmd_b200_adress_run_periodic_molecules(mrmd_b200_adress* ad, const mrmd_b20
  * (kind 0 mean, 1 compensationEnergy, 2 compensationEnergyCounter) */
 int mrmd_b200_adress_read_histogram(const mrmd_b200_adress* ad, int kind, double* dstHost, void* stream);
 
+/* ---- data::MultiHistogram ---------------------------------------------------------------------
+ * data/MultiHistogram.hpp:29-194, MultiHistogram.cpp:27-227: numBins x numHistograms doubles over [min, max) on the
+ * device, data(bin, histogram) row-major.  Every entry point replaces the member / free function it is named after. */
+typedef struct mrmd_b200_hist mrmd_b200_hist;
+/* MultiHistogram(label, min, max, numBins, numHistograms): zero filled (:31-47) */
+int mrmd_b200_hist_create(mrmd_b200_hist** out, double min, double max, int64_t numBins, int64_t numHistograms);
+/* MultiHistogram(label, histogram): deep copy (:49-54) */
+int mrmd_b200_hist_clone(mrmd_b200_hist** out, const mrmd_b200_hist* src, void* stream);
+int mrmd_b200_hist_destroy(mrmd_b200_hist* h);
+/* min, max, numBins, numHistograms, binSize, inverseBinSize (:76-81); NULL skips a field */
+int mrmd_b200_hist_info(const mrmd_b200_hist* h, double* min, double* max, int64_t* numBins, int64_t* numHistograms,
+                        double* binSize, double* inverseBinSize);
+/* the MultiView `data`: device pointer, and copies from / to a dense row-major buffer (memKind as for the slices) */
+void* mrmd_b200_hist_device_data(mrmd_b200_hist* h);
+int mrmd_b200_hist_write(mrmd_b200_hist* h, const double* src, int memKind, void* stream);
+int mrmd_b200_hist_read(const mrmd_b200_hist* h, double* dst, int memKind, void* stream);
+/* getBin (:60-66, -1 outside the range) and getBinPosition (:68-74): host arithmetic */
+int64_t mrmd_b200_hist_get_bin(const mrmd_b200_hist* h, double val);
+double mrmd_b200_hist_get_bin_position(const mrmd_b200_hist* h, int64_t binIdx);
+/* operator+= (op 0), -= (1), *= (2), /= (3) (MultiHistogram.cpp:27-46) */
+int mrmd_b200_hist_transform(mrmd_b200_hist* h, const mrmd_b200_hist* rhs, int op, void* stream);
+/* scale(real_t) (:48-59) and scale(ScalarView): one factor per histogram, numFactors >= numHistograms (:61-74) */
+int mrmd_b200_hist_scale(mrmd_b200_hist* h, double factor, void* stream);
+int mrmd_b200_hist_scale_per_histogram(mrmd_b200_hist* h, const double* factorsHost, int64_t numFactors, void* stream);
+/* makeSymmetric (:76-90) */
+int mrmd_b200_hist_make_symmetric(mrmd_b200_hist* h, void* stream);
+/* cumulativeMovingAverage(average, current, factor) (:92-111) */
+int mrmd_b200_hist_cumulative_moving_average(mrmd_b200_hist* average, const mrmd_b200_hist* current,
+                                             double movingAverageFactor, void* stream);
+/* gradient(input, periodic) (:113-161) and smoothen(input, sigma, range, periodic) (:163-212): a new histogram */
+int mrmd_b200_hist_gradient(mrmd_b200_hist** out, const mrmd_b200_hist* in, int periodic, void* stream);
+int mrmd_b200_hist_smoothen(mrmd_b200_hist** out, const mrmd_b200_hist* in, double sigma, double range, int periodic,
+                            void* stream);
+/* replace_if_bin_position(hist, pred, newValue) (MultiHistogram.hpp:176-191); the predicate is parametric (its axis
+ * coordinate is the bin position): device lambdas cannot cross a C ABI */
+int mrmd_b200_hist_replace_if_bin_position(mrmd_b200_hist* h, const mrmd_b200_pred* pred, double newValue, void* stream);
+/* createGrid (:214-227): the numBins bin positions, to the host */
+int mrmd_b200_hist_create_grid(const mrmd_b200_hist* h, double* gridHost, void* stream);
+
 /* ---- action::ThermodynamicForce ------------------------------------------------------------- */
 /* replaces the ctor (action/ThermodynamicForce.cpp:25-57) */
 int mrmd_b200_thermo_create(mrmd_b200_thermo** out, const double* targetDensity, int64_t numTypes,
@@ -355,6 +394,9 @@ int mrmd_b200_thermo_apply(const mrmd_b200_thermo* t, mrmd_b200_atoms* a, const 
                            int interpolated, void* stream);
 /* getForce()/setForce()/getDensityProfile(): numBins x numTypes doubles, host buffers (kind 0 force, 1 density) */
 int mrmd_b200_thermo_read(const mrmd_b200_thermo* t, int kind, double* dstHost, void* stream);
+/* getForce() (kind 0) / getDensityProfile() (kind 1) as the data::MultiHistogram the reference returns
+ * (ThermodynamicForce.hpp:57-63): a copy over [minCorner_x, maxCorner_x) with numTypes histograms */
+int mrmd_b200_thermo_get_hist(const mrmd_b200_thermo* t, int kind, mrmd_b200_hist** out, void* stream);
 int mrmd_b200_thermo_write_force(mrmd_b200_thermo* t, const double* srcHost, void* stream);
 /* all-reduce hooks for the x-slab decomposition: raw device pointer of the density histogram */
 int mrmd_b200_thermo_density_ptr(mrmd_b200_thermo* t, double** devicePtr, int64_t* count);

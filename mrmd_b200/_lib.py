@@ -171,6 +171,25 @@ SIGNATURES = {
     "mrmd_b200_verlet_build_periodic_molecules": (C.c_int, [vp, vp, pSub, dbl, dbl, i64, C.c_int, vp]),
     "mrmd_b200_verlet_read_periodic_molecules": (C.c_int, [vp, vp, vp, vp, vp, vp]),
     "mrmd_b200_adress_run_periodic_molecules": (C.c_int, [vp, vp, vp, vp, pWeight, C.c_int, pdbl, pi64, vp]),
+    "mrmd_b200_hist_create": (C.c_int, [pvp, dbl, dbl, i64, i64]),
+    "mrmd_b200_hist_clone": (C.c_int, [pvp, vp, vp]),
+    "mrmd_b200_hist_destroy": (C.c_int, [vp]),
+    "mrmd_b200_hist_info": (C.c_int, [vp, pdbl, pdbl, pi64, pi64, pdbl, pdbl]),
+    "mrmd_b200_hist_device_data": (vp, [vp]),
+    "mrmd_b200_hist_write": (C.c_int, [vp, vp, C.c_int, vp]),
+    "mrmd_b200_hist_read": (C.c_int, [vp, vp, C.c_int, vp]),
+    "mrmd_b200_hist_get_bin": (i64, [vp, dbl]),
+    "mrmd_b200_hist_get_bin_position": (dbl, [vp, i64]),
+    "mrmd_b200_hist_transform": (C.c_int, [vp, vp, C.c_int, vp]),
+    "mrmd_b200_hist_scale": (C.c_int, [vp, dbl, vp]),
+    "mrmd_b200_hist_scale_per_histogram": (C.c_int, [vp, vp, i64, vp]),
+    "mrmd_b200_hist_make_symmetric": (C.c_int, [vp, vp]),
+    "mrmd_b200_hist_cumulative_moving_average": (C.c_int, [vp, vp, dbl, vp]),
+    "mrmd_b200_hist_gradient": (C.c_int, [pvp, vp, C.c_int, vp]),
+    "mrmd_b200_hist_smoothen": (C.c_int, [pvp, vp, dbl, dbl, C.c_int, vp]),
+    "mrmd_b200_hist_replace_if_bin_position": (C.c_int, [vp, pPred, dbl, vp]),
+    "mrmd_b200_hist_create_grid": (C.c_int, [vp, vp, vp]),
+    "mrmd_b200_thermo_get_hist": (C.c_int, [vp, C.c_int, pvp, vp]),
     "mrmd_b200_md_set_energy_every_step": (C.c_int, [vp, C.c_int]),
     "mrmd_b200_slab_set_energy_every_step": (C.c_int, [vp, C.c_int]),
     "mrmd_b200_slab_run_host": (C.c_int, [vp, i64, vp, vp, vp, C.POINTER(MdStats), vp]),

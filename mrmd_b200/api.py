@@ -549,6 +549,109 @@ class LJ_IdealGas:
                 pass
 
 
+class MultiHistogram:
+    """data::MultiHistogram (data/MultiHistogram.hpp:29-92) on the device; `data` is a host copy (numBins x numHistograms),
+    `set_data` uploads one."""
+
+    def __init__(self, label, min, max, numBins, numHistograms, _handle=None):
+        self.label = label
+        self.h = _handle if _handle is not None else C.c_void_p()
+        if _handle is None:
+            check(L().mrmd_b200_hist_create(C.byref(self.h), float(min), float(max), int(numBins), int(numHistograms)))
+        a, b, g, s = C.c_double(), C.c_double(), C.c_double(), C.c_double()
+        nb, nh = C.c_int64(), C.c_int64()
+        check(L().mrmd_b200_hist_info(self.h, C.byref(a), C.byref(b), C.byref(nb), C.byref(nh), C.byref(g), C.byref(s)))
+        self.min, self.max, self.numBins, self.numHistograms = a.value, b.value, nb.value, nh.value
+        self.binSize, self.inverseBinSize = g.value, s.value
+
+    @classmethod
+    def _wrap(cls, handle, label="histogram"):
+        return cls(label, 0, 1, 0, 0, _handle=handle)
+
+    def copy(self, label="copy"):
+        h = C.c_void_p()
+        check(L().mrmd_b200_hist_clone(C.byref(h), self.h, None))
+        return MultiHistogram._wrap(h, label)
+
+    @property
+    def data(self):
+        out = np.zeros((self.numBins, self.numHistograms))
+        check(L().mrmd_b200_hist_read(self.h, out.ctypes.data, HOST, None))
+        return out
+
+    def set_data(self, values):
+        arr = np.ascontiguousarray(values, dtype=np.float64).reshape(self.numBins, self.numHistograms)
+        check(L().mrmd_b200_hist_write(self.h, arr.ctypes.data, HOST, None))
+
+    def getBin(self, val):
+        return int(L().mrmd_b200_hist_get_bin(self.h, float(val)))
+
+    def getBinPosition(self, binIdx):
+        return float(L().mrmd_b200_hist_get_bin_position(self.h, int(binIdx)))
+
+    def _op(self, rhs, op):
+        check(L().mrmd_b200_hist_transform(self.h, rhs.h, op, None))
+        return self
+
+    def __iadd__(self, rhs):
+        return self._op(rhs, 0)
+
+    def __isub__(self, rhs):
+        return self._op(rhs, 1)
+
+    def __imul__(self, rhs):
+        return self._op(rhs, 2)
+
+    def __itruediv__(self, rhs):
+        return self._op(rhs, 3)
+
+    def scale(self, factor):
+        """scale(real_t) or scale(ScalarView): one factor, or one per histogram"""
+        if np.ndim(factor) == 0:
+            check(L().mrmd_b200_hist_scale(self.h, float(factor), None))
+        else:
+            f = np.ascontiguousarray(factor, dtype=np.float64)
+            check(L().mrmd_b200_hist_scale_per_histogram(self.h, f.ctypes.data, f.size, None))
+
+    def makeSymmetric(self):
+        check(L().mrmd_b200_hist_make_symmetric(self.h, None))
+
+    def __del__(self):
+        h, self.h = getattr(self, "h", None), None
+        if h:
+            try:
+                L().mrmd_b200_hist_destroy(h)
+            except Exception:
+                pass
+
+
+def cumulativeMovingAverage(average, current, movingAverageFactor=10.0):
+    check(L().mrmd_b200_hist_cumulative_moving_average(average.h, current.h, float(movingAverageFactor), None))
+
+
+def gradient(histogram, periodic=False):
+    h = C.c_void_p()
+    check(L().mrmd_b200_hist_gradient(C.byref(h), histogram.h, int(periodic), None))
+    return MultiHistogram._wrap(h, "gradient")
+
+
+def smoothen(histogram, sigma, range, periodic=False):
+    h = C.c_void_p()
+    check(L().mrmd_b200_hist_smoothen(C.byref(h), histogram.h, float(sigma), float(range), int(periodic), None))
+    return MultiHistogram._wrap(h, "smooth-input")
+
+
+def createGrid(histogram):
+    out = np.zeros(histogram.numBins)
+    check(L().mrmd_b200_hist_create_grid(histogram.h, out.ctypes.data, None))
+    return out
+
+
+def replace_if_bin_position(histogram, pred, newValue):
+    """pred: a parametric one-coordinate predicate (IsInSymmetricSlab, interval_pred, ...) evaluated at the bin position"""
+    check(L().mrmd_b200_hist_replace_if_bin_position(histogram.h, C.byref(pred), float(newValue), None))
+
+
 class ThermodynamicForce:
     """action::ThermodynamicForce (action/ThermodynamicForce.hpp:32-96)."""
 
@@ -582,6 +685,17 @@ class ThermodynamicForce:
     def getForce(self, typeId=None):
         f = self._read(0)
         return f if typeId is None else f[:, typeId]
+
+    def getForceHistogram(self):
+        """getForce() as the data::MultiHistogram the reference returns (ThermodynamicForce.hpp:57)"""
+        h = C.c_void_p()
+        check(L().mrmd_b200_thermo_get_hist(self.h, 0, C.byref(h), None))
+        return MultiHistogram._wrap(h, "thermodynamic-force")
+
+    def getDensityProfileHistogram(self):
+        h = C.c_void_p()
+        check(L().mrmd_b200_thermo_get_hist(self.h, 1, C.byref(h), None))
+        return MultiHistogram._wrap(h, "density-profile")
 
     def getDensityProfile(self, typeId=None):
         d = self._read(1)

@@ -26,7 +26,7 @@ REFERENCE_HEADERS = [
     "io/DumpThermoForce.hpp", "io/RestoreThermoForce.hpp", "action/BerendsenThermostat.hpp",
     "action/BerendsenBarostat.hpp", "action/Shake.hpp", "data/Bond.hpp", "action/SPC.hpp", "action/Coulomb.hpp",
     "action/CoulombDSF.hpp", "io/DumpCSV.hpp", "action/LimitAcceleration.hpp", "action/LimitVelocity.hpp",
-    "util/ExponentialMovingAverage.hpp", "Cabana_NeighborList.hpp",
+    "util/ExponentialMovingAverage.hpp", "Cabana_NeighborList.hpp", "data/MultiHistogram.hpp",
 ]
 
 
@@ -48,7 +48,7 @@ def test_reference_header_paths_exist():
 
 
 @pytest.mark.parametrize("name", ["lennard_jones_nve", "adress_ideal_gas", "restart_io", "constraints_step", "spc_water",
-                                  "tetramer_adress"])
+                                  "tetramer_adress", "multi_histogram"])
 def test_example_compiles_and_fails_loudly_without_gpu(name, tmp_path):
     import torch
 
@@ -297,3 +297,14 @@ def test_tetramer_driver_matches_oracle(tmp_path):
     assert np.allclose(out["x0"], md.atoms["pos"][0], rtol=0, atol=1e-9)
     assert np.allclose(out["v0"], md.atoms["vel"][0], rtol=0, atol=1e-8)
     assert out["maxBondError"] < 5e-3
+
+
+@pytest.mark.gpu
+def test_multi_histogram_reference_tests_through_the_mirror(tmp_path):
+    """row a26: every TEST of mrmd/data/MultiHistogram.test.cpp (getBin, getBinPosition, createGrid, scale, make_symmetric,
+    gradient, the four operators, smoothen, replace_if_bin_position) plus cumulativeMovingAverage, the copy constructor and
+    ThermodynamicForce::getForce() returning a data::MultiHistogram, written against include/mrmd/data/MultiHistogram.hpp"""
+    exe = _compile("multi_histogram", tmp_path)
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    out = json.loads(res.stdout.strip().splitlines()[-1])
+    assert res.returncode == 0 and out["failures"] == 0, (out, res.stderr[-1000:])
