@@ -616,14 +616,14 @@ int adressCheckUniform(mrmd_b200_adress* ad, cudaStream_t st)
 }
 
 int adressRunPeriodic(mrmd_b200_adress* ad, mrmd_b200_atoms* a, const mrmd_b200_verlet* v, const mrmd_b200_weight* w,
-                      bool energy, cudaStream_t st)
+                      bool energy, cudaStream_t st, const int* stop)
 {
     MB_REQUIRE(ad != nullptr && a != nullptr && v != nullptr && w != nullptr, "adress_run_periodic");
     MB_REQUIRE(v->tiled, "adress_run_periodic: needs a list from mrmd_b200_verlet_build_periodic");
     MB_REQUIRE(v->numParticles == a->numLocal, "adress_run_periodic: list rows != local atoms");
     const bool sampling = (ad->runCounter % ad->samplingInterval) == 0;
     if (a->numLocal > 0)
-        MB_TRY(adressApplyTiled(ad, a, v, w, sampling, energy, st));
+        MB_TRY(adressApplyTiled(ad, a, v, w, sampling, energy, st, stop));
     else
         MB_CUDA(cudaMemsetAsync(ad->dResult, 0, 24, st));
     if (ad->runCounter % ad->updateInterval == 0)

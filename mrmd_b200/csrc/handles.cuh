@@ -68,16 +68,19 @@ namespace mrmd_b200
 {
 // integrate.cu: preForceIntegrate, optionally with the previous step's postForceIntegrate fused in front; the
 // squared maximum displacement is left in a->dMaxDisp
+// stop (device int, optional): the kernel returns at once when it is set -- for steps queued ahead of the host
 int integratePre(mrmd_b200_atoms* a, double dt, bool langevin, double zeta, double temperature, uint64_t seed,
-                 uint64_t step, const mrmd_b200_pred* pred, bool fusedPost, cudaStream_t st);
+                 uint64_t step, const mrmd_b200_pred* pred, bool fusedPost, cudaStream_t st, const int* stop = nullptr);
+// integrate.cu: the displacement criterion of examples/02:138-143 evaluated on the device (see there)
+int displacementDecision(const double* dMaxDispSqr, double* dAccum, double threshold, int* dStop, int localStep, cudaStream_t st);
 // containers.cu: dense (n x ncomp) device buffer <-> one field of the container
 int atomsFieldToDense(const mrmd_b200_atoms* a, int field, double* devBuf, int64_t n, cudaStream_t st);
 int atomsFieldFromDense(mrmd_b200_atoms* a, int field, const double* devBuf, int64_t n, cudaStream_t st);
 // tiled.cu: LennardJones::apply over a tiled (periodic, shared-memory staged) full list
 int ljApplyTiled(mrmd_b200_lj* lj, mrmd_b200_atoms* a, const mrmd_b200_verlet* v, bool accumulate, bool energy,
-                 cudaStream_t st);
+                 cudaStream_t st, const int* stop = nullptr);
 int adressApplyTiled(mrmd_b200_adress* ad, mrmd_b200_atoms* a, const mrmd_b200_verlet* v, const mrmd_b200_weight* w,
-                     bool sampling, bool energy, cudaStream_t st);
+                     bool sampling, bool energy, cudaStream_t st, const int* stop = nullptr);
 // tiled.cu / adress.cu: LJ_IdealGas over a tiled list of the centres of mass of molecules of atomsPerMolecule atoms
 int moleculeApplyTiled(mrmd_b200_adress* ad, const mrmd_b200_molecules* m, mrmd_b200_atoms* a, const mrmd_b200_verlet* v,
                        const mrmd_b200_weight* w, int atomsPerMolecule, bool sampling, bool energy, cudaStream_t st);
@@ -93,7 +96,7 @@ int verletBuildTiledMolecules(mrmd_b200_verlet* v, mrmd_b200_molecules* m, const
 // adress.cu: reads the atoms-per-molecule flag of the four-lane kernel back (synchronises the stream)
 int adressCheckUniform(mrmd_b200_adress* ad, cudaStream_t st);
 int adressRunPeriodic(mrmd_b200_adress* ad, mrmd_b200_atoms* a, const mrmd_b200_verlet* v, const mrmd_b200_weight* w,
-                      bool energy, cudaStream_t st);
+                      bool energy, cudaStream_t st, const int* stop = nullptr);
 // constraints.cu: SHAKE / RATTLE launches without the bond-range read-back and its stream synchronisation
 int constraintsEnforcePositional(mrmd_b200_constraints* c, const mrmd_b200_molecules* m, mrmd_b200_atoms* a, double dt,
                                  cudaStream_t st);

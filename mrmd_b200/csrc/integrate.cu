@@ -3,7 +3,7 @@
 //            mrmd/action/VelocityVerletLangevinThermostat.hpp:63-136.
 // Streaming kernels, HBM bound: pre reads pos4(32)+vel(24)+force(24)+mass(8), writes pos4(32)+vel(24);
 // post reads vel+force+mass, writes vel.  One thread per atom, 256-bit pos4 access, planes coalesced.
-#include "common.cuh"
+#include "handles.cuh"
 
 namespace mrmd_b200
 {
@@ -78,8 +78,10 @@ __device__ __forceinline__ void blockMaxToGlobal(double v, double* dMax)
 template <bool LANGEVIN, bool FUSED_POST>
 __global__ void __launch_bounds__(256)
     integratePreKernel(AtomsView a, int64_t n, double dt, double zeta, double temperature, uint64_t seed,
-                       uint64_t step, mrmd_b200_pred pred, double* dMax)
+                       uint64_t step, mrmd_b200_pred pred, double* dMax, const int* __restrict__ stop)
 {
+    // speculatively queued steps (md.cu / slab.cu): a step behind the one that asked for a rebuild must not run
+    if (stop != nullptr && *stop != 0) return;
     const int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
     double distSqr = 0.0;
     if (idx < n)
@@ -163,9 +165,41 @@ static int fetchMaxDisp(mrmd_b200_atoms* a, double* maxDisplacement, cudaStream_
 }
 
 // shared by the C ABI and the step-loop drivers (fusedPost: see integratePreKernel)
-int integratePre(mrmd_b200_atoms* a, double dt, bool langevin, double zeta, double temperature, uint64_t seed,
-                 uint64_t step, const mrmd_b200_pred* pred, bool fusedPost, cudaStream_t st)
+// the rebuild decision of examples/02:138-143 on the device, for steps queued ahead of the host: accumulates
+// sqrt(max |dx|^2) and raises stop = {1, localStep} when the sum reaches the threshold (skin / 2) -- the kernels of the
+// steps queued behind it then return at once.  A non-finite displacement stops with stop[2] = 1.
+__global__ void displacementDecisionKernel(const double* __restrict__ maxDispSqr, double* accum, double threshold, int* stop,
+                                           int localStep)
 {
+    if (stop[0] != 0) return;
+    const double v = *maxDispSqr;
+    if (!(v == v) || v > 1.7e308)
+    {
+        stop[0] = 1;
+        stop[1] = localStep;
+        stop[2] = 1;
+        return;
+    }
+    const double sum = *accum + sqrt(v);  // the host's  maxDisplacement += sqrt(max)  in the same order
+    *accum = sum;
+    if (sum >= threshold)
+    {
+        stop[0] = 1;
+        stop[1] = localStep;
+    }
+}
+
+int displacementDecision(const double* dMaxDispSqr, double* dAccum, double threshold, int* dStop, int localStep, cudaStream_t st)
+{
+    displacementDecisionKernel<<<1, 1, 0, st>>>(dMaxDispSqr, dAccum, threshold, dStop, localStep);
+    MB_LAUNCHED();
+    return 0;
+}
+
+int integratePre(mrmd_b200_atoms* a, double dt, bool langevin, double zeta, double temperature, uint64_t seed,
+                 uint64_t step, const mrmd_b200_pred* pred, bool fusedPost, cudaStream_t st, const int* stop)
+{
+    // (a queued step that is stopped leaves the scalar cleared: its decision kernel is stopped as well)
     MB_CUDA(cudaMemsetAsync(a->dMaxDisp, 0, 8, st));
     a->posEpoch += 1;
     if (a->numLocal == 0) return 0;
@@ -173,7 +207,7 @@ int integratePre(mrmd_b200_atoms* a, double dt, bool langevin, double zeta, doub
     if (pred != nullptr) p = *pred;
     const int blocks = gridFor(a->numLocal, 256);
 #define PRE_LAUNCH(L, F) \
-    integratePreKernel<L, F><<<blocks, 256, 0, st>>>(a->v, a->numLocal, dt, zeta, temperature, seed, step, p, a->dMaxDisp)
+    integratePreKernel<L, F><<<blocks, 256, 0, st>>>(a->v, a->numLocal, dt, zeta, temperature, seed, step, p, a->dMaxDisp, stop)
     if (langevin) { if (fusedPost) PRE_LAUNCH(true, true); else PRE_LAUNCH(true, false); }
     else { if (fusedPost) PRE_LAUNCH(false, true); else PRE_LAUNCH(false, false); }
 #undef PRE_LAUNCH

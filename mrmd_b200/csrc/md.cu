@@ -32,6 +32,11 @@ struct mrmd_b200_md
     bool postPending = false;  // the last step's postForceIntegrate is fused into the next preForceIntegrate
     std::vector<cudaEvent_t> events;
     mrmd_b200::HostPipe hp;  // host-buffer path (mrmd_b200_md_run_host)
+    // steps queued ahead of the host (runQueued): the displacement criterion is evaluated on the device
+    int* dStop = nullptr;      // {stop, local step that stopped, non-finite displacement}
+    double* dAccum = nullptr;  // accumulated displacement (the device copy of maxDisplacement)
+    int* hStop = nullptr;      // pinned: dStop, and behind it the accumulated displacement
+    int64_t stepsSinceRebuild = 0, lastRebuildInterval = 4;
 };
 
 namespace mrmd_b200
@@ -146,6 +151,9 @@ static int postIntegrate(mrmd_b200_md* md, bool deferPost, cudaStream_t st)
     return mrmd_b200_vv_post(md->atoms, md->cfg.dt, st);
 }
 
+static int stepAfterPre(mrmd_b200_md* md, cudaStream_t st, cudaEvent_t evStart, cudaEvent_t evStop, bool deferPost,
+                        bool wantEnergy, cudaEvent_t evPosReady, bool rebuildNow, const int* stop);
+
 // deferPost: leave postForceIntegrate to the next step's fused kernel (the caller flushes it when the run ends)
 static int oneStep(mrmd_b200_md* md, cudaStream_t st, cudaEvent_t evStart, cudaEvent_t evStop, bool deferPost,
                    bool wantEnergy, cudaEvent_t evPosReady = nullptr)
@@ -161,9 +169,21 @@ static int oneStep(mrmd_b200_md* md, cudaStream_t st, cudaEvent_t evStart, cudaE
     MB_CUDA(cudaStreamSynchronize(st));
     MB_REQUIRE(std::isfinite(*a->hMaxDisp), "md_run: non-finite position, velocity or force (the system blew up)");
     md->maxDisplacement += std::sqrt(*a->hMaxDisp);  // examples/02:138, VelocityVerlet.cpp:66
-    if (md->maxDisplacement >= c.skin * 0.5)  // :141-143
+    return stepAfterPre(md, st, evStart, evStop, deferPost, wantEnergy, evPosReady, md->maxDisplacement >= c.skin * 0.5, nullptr);
+}
+
+// the step behind preForceIntegrate: rebuild or ghost refresh, force, postForceIntegrate.  stop (device, optional): the
+// step is queued ahead of the host and its kernels return at once when an earlier queued step asked for a rebuild.
+static int stepAfterPre(mrmd_b200_md* md, cudaStream_t st, cudaEvent_t evStart, cudaEvent_t evStop, bool deferPost,
+                        bool wantEnergy, cudaEvent_t evPosReady, bool rebuildNow, const int* stop)
+{
+    const mrmd_b200_md_config& c = md->cfg;
+    mrmd_b200_atoms* a = md->atoms;
+    if (rebuildNow)  // :141-143
     {
         md->maxDisplacement = 0.0;
+        if (md->stepsSinceRebuild > 0) md->lastRebuildInterval = md->stepsSinceRebuild;
+        md->stepsSinceRebuild = 0;
         MB_TRY(rebuild(md, st));
     }
     else if (c.fullList != 2)
@@ -201,10 +221,11 @@ static int oneStep(mrmd_b200_md* md, cudaStream_t st, cudaEvent_t evStart, cudaE
             MB_TRY(mrmd_b200_thermo_apply(md->thermo, a, nullptr, 0, st));
         }
         if (evStart) MB_CUDA(cudaEventRecord(evStart, st));
-        MB_TRY(adressRunPeriodic(md->adress, a, md->list, &c.weight, wantEnergy, st));
+        MB_TRY(adressRunPeriodic(md->adress, a, md->list, &c.weight, wantEnergy, st, stop));
         if (evStop) MB_CUDA(cudaEventRecord(evStop, st));
         MB_TRY(postIntegrate(md, deferPost, st));
         md->step += 1;
+        md->stepsSinceRebuild += 1;
         return 0;
     }
     if (c.fullList == 2)
@@ -213,10 +234,11 @@ static int oneStep(mrmd_b200_md* md, cudaStream_t st, cudaEvent_t evStart, cudaE
         // no ghost atom receives force: no ghost refresh, no force reset, no fold-back inside the loop
         if (evStart) MB_CUDA(cudaEventRecord(evStart, st));
         // energy and virial are only observable after the run returns: accumulate them on its last step
-        MB_TRY(ljApplyTiled(md->lj, a, md->list, false, wantEnergy, st));
+        MB_TRY(ljApplyTiled(md->lj, a, md->list, false, wantEnergy, st, stop));
         if (evStop) MB_CUDA(cudaEventRecord(evStop, st));
         MB_TRY(postIntegrate(md, deferPost, st));
         md->step += 1;
+        md->stepsSinceRebuild += 1;
         return 0;
     }
     MB_TRY(mrmd_b200_atoms_fill(a, MRMD_B200_ATOM_FORCE, 0.0, st));  // :174-175
@@ -247,6 +269,77 @@ static int oneStep(mrmd_b200_md* md, cudaStream_t st, cudaEvent_t evStart, cudaE
     }
     MB_TRY(postIntegrate(md, deferPost, st));  // :184
     md->step += 1;
+    md->stepsSinceRebuild += 1;
+    return 0;
+}
+
+// Steps queued ahead of the host.  The loop of examples/02:135-216 asks the host after every preForceIntegrate whether to
+// rebuild (one device -> host scalar and a synchronisation per step: the GPU idles while the answer travels).  Here up to
+// `count` steps are enqueued back to back with the criterion evaluated on the device (displacementDecisionKernel); the
+// step that reaches skin / 2 raises a flag and every kernel queued behind it returns at once.  The host synchronises once
+// per chunk: *done steps ran completely; if *stopped, the positions are those after preForceIntegrate of step *done and
+// the caller finishes that step the usual way (rebuild, force).  Only for the tiled paths without per-step host
+// bookkeeping (no constraints, no thermodynamic-force sampling / update and no compensation-energy sampling / update in
+// the chunk: canQueue).
+static bool canQueue(const mrmd_b200_md* md, int64_t ahead)
+{
+    const mrmd_b200_md_config& c = md->cfg;
+    if (c.fullList != 2 || md->constraints != nullptr || c.atomsPerMolecule > 1 || md->rebuilds == 0) return false;
+    if (std::getenv("MRMD_B200_NO_QUEUED_STEPS") != nullptr) return false;
+    const int64_t step = md->step + ahead;
+    if (c.adress)
+    {
+        if (md->thermo != nullptr)
+        {
+            if (c.thermoSampleInterval > 0 && step % c.thermoSampleInterval == 0) return false;
+            if (c.thermoUpdateInterval > 0 && step > 0 && step % c.thermoUpdateInterval == 0) return false;
+        }
+        const int64_t run = md->adress->runCounter + ahead;
+        if (run % md->adress->samplingInterval == 0 || run % md->adress->updateInterval == 0) return false;
+    }
+    return true;
+}
+
+static int runQueued(mrmd_b200_md* md, int64_t count, cudaStream_t st, cudaEvent_t* events, bool energyOnLast, bool energyAlways,
+                     int64_t* done, bool* stopped)
+{
+    const mrmd_b200_md_config& c = md->cfg;
+    mrmd_b200_atoms* a = md->atoms;
+    if (md->dStop == nullptr)
+    {
+        MB_CUDA(cudaMalloc(&md->dStop, 16));
+        MB_CUDA(cudaMalloc(&md->dAccum, 8));
+        MB_CUDA(cudaMallocHost(&md->hStop, 32));
+    }
+    double* hAccum = reinterpret_cast<double*>(md->hStop + 4);
+    *hAccum = md->maxDisplacement;
+    MB_CUDA(cudaMemsetAsync(md->dStop, 0, 16, st));
+    MB_CUDA(cudaMemcpyAsync(md->dAccum, hAccum, 8, cudaMemcpyHostToDevice, st));
+    const int64_t step0 = md->step, since0 = md->stepsSinceRebuild, run0 = c.adress ? md->adress->runCounter : 0;
+    const bool pending0 = md->postPending;
+    for (int64_t k = 0; k < count; ++k)
+    {
+        MB_TRY(integratePre(a, c.dt, c.integrator == 1, c.zeta, c.temperature, c.seed, uint64_t(md->step), nullptr,
+                            md->postPending, st, md->dStop));
+        md->postPending = false;
+        MB_TRY(displacementDecision(a->dMaxDisp, md->dAccum, c.skin * 0.5, md->dStop, static_cast<int>(k), st));
+        const bool wantEnergy = energyAlways || (energyOnLast && k == count - 1);
+        MB_TRY(stepAfterPre(md, st, events ? events[2 * k] : nullptr, events ? events[2 * k + 1] : nullptr, true, wantEnergy,
+                            nullptr, false, md->dStop));
+    }
+    MB_CUDA(cudaMemcpyAsync(md->hStop, md->dStop, 16, cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaMemcpyAsync(hAccum, md->dAccum, 8, cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaStreamSynchronize(st));
+    MB_REQUIRE(md->hStop[2] == 0, "md_run: non-finite position, velocity or force (the system blew up)");
+    *stopped = md->hStop[0] != 0;
+    *done = *stopped ? md->hStop[1] : count;
+    md->maxDisplacement = *hAccum;
+    // the host-side counters follow the steps that really ran
+    md->step = step0 + *done;
+    md->stepsSinceRebuild = since0 + *done;
+    if (c.adress) md->adress->runCounter = run0 + *done;
+    // the stopped step's preForceIntegrate ran (with the previous step's kick fused in front if one was pending)
+    md->postPending = *stopped ? false : (count > 0 ? true : pending0);
     return 0;
 }
 
@@ -388,6 +481,9 @@ int mrmd_b200_md_destroy(mrmd_b200_md* md)
     cudaDeviceSynchronize();
     for (auto e : md->events) cudaEventDestroy(e);
     md->hp.destroy();
+    if (md->dStop != nullptr) cudaFree(md->dStop);
+    if (md->dAccum != nullptr) cudaFree(md->dAccum);
+    if (md->hStop != nullptr) cudaFreeHost(md->hStop);
     mrmd_b200_ghost_destroy(md->ghost);
     mrmd_b200_verlet_destroy(md->list);
     mrmd_b200_lj_destroy(md->lj);
@@ -415,12 +511,37 @@ int mrmd_b200_md_run(mrmd_b200_md* md, int64_t nsteps, int timeForceKernel, mrmd
         md->events.push_back(e);
     }
     int64_t storedSum = 0;
-    for (int64_t i = 0; i < nsteps; ++i)
+    const bool energyAlways = md->cfg.energyEveryStep != 0;
+    for (int64_t i = 0; i < nsteps;)
     {
         cudaEvent_t e0 = (i < nTimed) ? md->events[2 * i] : nullptr;
         cudaEvent_t e1 = (i < nTimed) ? md->events[2 * i + 1] : nullptr;
-        MB_TRY(oneStep(md, st, e0, e1, true, i == nsteps - 1 || md->cfg.energyEveryStep != 0));
+        // as many steps as the last rebuild interval suggests are queued ahead of the host (see runQueued)
+        int64_t count = 0;
+        const int64_t want = std::max<int64_t>(1, std::min<int64_t>(16, md->lastRebuildInterval - md->stepsSinceRebuild + 1));
+        while (count < want && i + count < nsteps && canQueue(md, count)) ++count;
+        if (count >= 1)
+        {
+            int64_t done = 0;
+            bool stopped = false;
+            MB_TRY(runQueued(md, count, st, (i + count <= nTimed) ? md->events.data() + 2 * i : nullptr, i + count == nsteps,
+                             energyAlways, &done, &stopped));
+            storedSum += md->storedPairsNow * done;
+            i += done;
+            if (stopped)
+            {
+                // step i: preForceIntegrate ran on the device and reached skin / 2 -> rebuild, force, postForceIntegrate
+                e0 = (i < nTimed) ? md->events[2 * i] : nullptr;
+                e1 = (i < nTimed) ? md->events[2 * i + 1] : nullptr;
+                MB_TRY(stepAfterPre(md, st, e0, e1, true, i == nsteps - 1 || energyAlways, nullptr, true, nullptr));
+                storedSum += md->storedPairsNow;
+                i += 1;
+            }
+            continue;
+        }
+        MB_TRY(oneStep(md, st, e0, e1, true, i == nsteps - 1 || energyAlways));
         storedSum += md->storedPairsNow;
+        ++i;
     }
     if (md->postPending)
     {

@@ -373,9 +373,14 @@ struct PeerBuffers
 // one single-warp kernel per step.  The result also goes to pinned host memory (zero copy) with the step number
 // behind it, so the host learns it without a stream synchronisation.  Slots alternate between two sets by step parity:
 // a rank can be at most one decision ahead of the slowest one (it needs that rank's value to finish its own).
+// Queued steps (slabRunQueued): accum / stop are given, the kernel also evaluates the criterion of examples/02:138-143 on
+// the global maximum -- every rank accumulates the same values and stops at the same step -- and returns at once when an
+// earlier queued step already stopped.
 __global__ void maxDisplacementGatherKernel(const double* myMaxSqr, PeerBuffers peers, int rank, int nranks, double seq,
-                                            int parity, double* outDevice, volatile double* outHost)
+                                            int parity, double* outDevice, volatile double* outHost, double* accum,
+                                            double threshold, int* stop, int localStep)
 {
+    if (stop != nullptr && stop[0] != 0) return;
     const int t = threadIdx.x;
     const int slotBase = SL_HW_DECIDE + parity * 2 * SL_MAX_PEERS;  // in 8-byte words from the start of the buffer
     if (t < nranks)
@@ -401,6 +406,25 @@ __global__ void maxDisplacementGatherKernel(const double* myMaxSqr, PeerBuffers 
         outHost[0] = m;
         __threadfence_system();
         outHost[1] = seq;
+        if (accum != nullptr)
+        {
+            if (!(m == m) || m > 1.7e308)
+            {
+                stop[0] = 1;
+                stop[1] = localStep;
+                stop[2] = 1;
+            }
+            else
+            {
+                const double sum = *accum + sqrt(m);
+                *accum = sum;
+                if (sum >= threshold)
+                {
+                    stop[0] = 1;
+                    stop[1] = localStep;
+                }
+            }
+        }
     }
 }
 
@@ -585,11 +609,15 @@ __global__ void __launch_bounds__(SL_THREADS)
 __device__ __forceinline__ void publishWhenLast(unsigned int* ticket, volatile long long* hdrL, volatile long long* hdrR,
                                                 long long countL, long long countR, long long seq)
 {
-    // the last block to finish publishes: every block's records are visible system wide before the flags are
-    __threadfence_system();
+    // the last block to finish publishes: every block's records are visible system wide before the flags are (one
+    // cumulative system-scope fence per block behind the block barrier)
     __shared__ bool sLastBlock;
     __syncthreads();
-    if (threadIdx.x == 0) sLastBlock = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    if (threadIdx.x == 0)
+    {
+        __threadfence_system();
+        sLastBlock = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
     __syncthreads();
     if (sLastBlock && threadIdx.x == 0)
     {
@@ -701,25 +729,33 @@ __global__ void __launch_bounds__(SL_THREADS)
                           const int32_t* __restrict__ idxLow, const int32_t* __restrict__ idxHigh,
                           const int64_t* __restrict__ counts, int64_t cap, double shiftL, double shiftR, double4* dstL,
                           double4* dstR, unsigned long long* flagL, unsigned long long* flagR, long long* cntL, long long* cntR,
-                          unsigned long long seq, unsigned int* ticket)
+                          unsigned long long seq, unsigned int* ticket, const int* __restrict__ stop)
 {
+    if (stop != nullptr && *stop != 0) return;  // a step queued behind the one that asked for a rebuild
     const int rec = apm + (apm > 1 ? 1 : 0);  // double4 per unit: the atoms' positions (+ the centre of mass)
     const int64_t k = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-    const int64_t perList = cap * rec;
-    const int list = k < perList ? 0 : 1;
-    const int64_t kk = k - list * perList, unit = kk / rec;
-    const int part = static_cast<int>(kk % rec);
-    if (kk < perList && unit < min(counts[list], cap))
+    // list 0 occupies the first min(counts[0], cap) * rec threads, list 1 follows directly (the grid covers 2 * cap units
+    // at a rebuild, exactly the two lists otherwise)
+    const int64_t n0 = min(counts[0], cap) * rec, n1 = min(counts[1], cap) * rec;
+    if (k < n0 + n1)
     {
+        const int list = k < n0 ? 0 : 1;
+        const int64_t kk = k - list * n0, unit = kk / rec;
+        const int part = static_cast<int>(kk % rec);
         const int64_t u = (list == 0 ? idxLow : idxHigh)[unit];
         double4 p = (part < apm) ? ld4(pos + u * apm + part) : ld4(upos + u);
         p.x += (list == 0 ? shiftL : shiftR);
         st4((list == 0 ? dstL : dstR) + kk, p);
     }
-    __threadfence_system();
+    // one system-scope fence per block behind the block barrier (cumulative: it orders the stores of the whole block
+    // before the ticket), then the last block to take a ticket publishes
     __shared__ bool sLast;
     __syncthreads();
-    if (threadIdx.x == 0) sLast = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    if (threadIdx.x == 0)
+    {
+        __threadfence_system();
+        sLast = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
     __syncthreads();
     if (sLast && threadIdx.x == 0)
     {
@@ -737,8 +773,10 @@ __global__ void __launch_bounds__(SL_THREADS)
 __global__ void __launch_bounds__(SL_THREADS)
     haloPullCountedKernel(const double4* fromLeft, const double4* fromRight, const unsigned long long* flags,
                           const long long* cnt, unsigned long long seq, int apm, int64_t cap, double4* dstAtoms,
-                          double4* dstUnits, const int64_t* sent, int64_t* recvDev, volatile long long* hReport, int* err)
+                          double4* dstUnits, const int64_t* sent, int64_t* recvDev, volatile long long* hReport, int* err,
+                          const int* __restrict__ stop)
 {
+    if (stop != nullptr && *stop != 0) return;  // a step queued behind the one that asked for a rebuild
     if (threadIdx.x == 0)
     {
         const volatile unsigned long long* f = flags;
@@ -870,6 +908,18 @@ struct mrmd_b200_slab
     double* hScalars = nullptr;  // pinned
     std::vector<cudaEvent_t> events;
     mrmd_b200::HostPipe hp;  // host-buffer path (mrmd_b200_slab_run_host)
+    // steps queued ahead of the host (slabRunQueued): the displacement criterion is evaluated by the gather kernel
+    int* dStop = nullptr;      // {stop, local step that stopped, non-finite displacement}
+    double* dAccum = nullptr;  // accumulated displacement (the device copy of maxDisplacement)
+    int* hStop = nullptr;      // pinned: dStop, and behind it the accumulated displacement
+    int64_t stepsSinceRebuild = 0, lastRebuildInterval = 4;
+    // MRMD_B200_SLAB_EVENTS=1: CUDA events at the phase boundaries of every step (no synchronisation added); the mean
+    // in-stream time of every phase is printed at destroy (diagnostic only)
+    // the per-step halo push runs on its own stream next to the displacement gather (both only need the new positions)
+    cudaStream_t sPush = nullptr;
+    cudaEvent_t evPreDone = nullptr, evPushDone = nullptr;
+    bool evProfile = false;
+    std::vector<std::pair<int, cudaEvent_t>> evMarks;
 };
 
 namespace mrmd_b200
@@ -1044,7 +1094,7 @@ static double4* unitPositions(mrmd_b200_slab* sl);
 
 // my face units -> the neighbours' halo regions of this sequence number's parity.  countsDev != nullptr (rebuild): the
 // counts were just produced on the device; otherwise the lists of the last rebuild are re-sent.
-static int haloPush(mrmd_b200_slab* sl, bool rebuild, cudaStream_t st)
+static int haloPush(mrmd_b200_slab* sl, bool rebuild, cudaStream_t st, const int* stop = nullptr)
 {
     mrmd_b200_atoms* a = sl->atoms;
     const unsigned long long seq = ++sl->haloSeq;
@@ -1057,18 +1107,18 @@ static int haloPush(mrmd_b200_slab* sl, bool rebuild, cudaStream_t st)
     double4* dstR = sl->peerRightBuf + haloRegionOffset(sl, parity, 0);
     long long* hL = headerWords(sl->peerLeftBuf);
     long long* hR = headerWords(sl->peerRightBuf);
-    const int64_t units = rebuild ? 2 * sl->p2pCap : sl->p2pCap + sl->sendRightCount;  // list 1 starts at unit p2pCap
+    const int64_t units = rebuild ? 2 * sl->p2pCap : sl->sendLeftCount + sl->sendRightCount;
     haloPushCountedKernel<<<std::max(1, gridFor(units * rec, SL_THREADS)), SL_THREADS, 0, st>>>(
         a->v.pos, unitPositions(sl), sl->apm, sl->idxLow.as<int32_t>(), sl->idxHigh.as<int32_t>(), sl->dTotals + 2, sl->p2pCap,
         sl->shiftToLeft, sl->shiftToRight, dstL, dstR, reinterpret_cast<unsigned long long*>(hL + SL_HW_HALO + parity * 2 + 1),
         reinterpret_cast<unsigned long long*>(hR + SL_HW_HALO + parity * 2 + 0), hL + SL_HW_HALOCOUNT + parity * 4 + 2,
-        hR + SL_HW_HALOCOUNT + parity * 4 + 0, seq, sl->dPushTicket);
+        hR + SL_HW_HALOCOUNT + parity * 4 + 0, seq, sl->dPushTicket, stop);
     MB_LAUNCHED();
     return 0;
 }
 
 // the neighbours' face units of the current sequence number -> behind my local units
-static int haloPull(mrmd_b200_slab* sl, bool rebuild, cudaStream_t st)
+static int haloPull(mrmd_b200_slab* sl, bool rebuild, cudaStream_t st, const int* stop = nullptr)
 {
     mrmd_b200_atoms* a = sl->atoms;
     const unsigned long long seq = sl->haloSeq;
@@ -1080,7 +1130,8 @@ static int haloPull(mrmd_b200_slab* sl, bool rebuild, cudaStream_t st)
     haloPullCountedKernel<<<std::max(1, gridFor(units * rec, SL_THREADS)), SL_THREADS, 0, st>>>(
         sl->p2pBuf + haloRegionOffset(sl, parity, 0), sl->p2pBuf + haloRegionOffset(sl, parity, 1),
         reinterpret_cast<const unsigned long long*>(h + SL_HW_HALO + parity * 2), h + SL_HW_HALOCOUNT + parity * 4, seq, sl->apm,
-        sl->p2pCap, a->v.pos + a->numLocal, unitPositions(sl) + nUnits, sl->dTotals + 2, sl->dTotals + 6, sl->hReport, sl->dErr);
+        sl->p2pCap, a->v.pos + a->numLocal, unitPositions(sl) + nUnits, sl->dTotals + 2, sl->dTotals + 6, sl->hReport, sl->dErr,
+        stop);
     MB_LAUNCHED();
     return 0;
 }
@@ -1137,6 +1188,54 @@ static int haloRefresh(mrmd_b200_slab* sl, cudaStream_t st)
         MB_NCCL(g_nccl.recv(a->v.pos + n, size_t(sl->haloLeftCount) * 4, ncclDouble, sl->left, sl->comm, st));
     MB_NCCL(g_nccl.groupEnd());
     return 0;
+}
+
+static const char* const EV_NAMES[] = {"(step start)", "kick/drift", "halo push", "displacement gather", "halo pull", "force",
+                                       "post", "rb: wrap+select+migrate", "rb: host round trip 1", "rb: sort", "rb: face lists",
+                                       "rb: halo push+pull", "rb: halo cells", "rb: list build (+round trip 2)"};
+static void evMark(mrmd_b200_slab* sl, int tag, cudaStream_t st)
+{
+    if (!sl->evProfile || sl->evMarks.size() > 40000) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    sl->evMarks.emplace_back(tag, e);
+}
+static void evReport(mrmd_b200_slab* sl)
+{
+    if (!sl->evProfile || sl->evMarks.size() < 2) return;
+    cudaDeviceSynchronize();
+    double sum[16] = {0};
+    long cnt[16] = {0};
+    long steps = 0;
+    // the first quarter is warm-up (lattice melting, first-touch allocations)
+    const size_t first = sl->evMarks.size() / 4;
+    for (size_t k = first + 1; k < sl->evMarks.size(); ++k)
+    {
+        float ms = 0.f;
+        const int tag = sl->evMarks[k].first;
+        if (tag == 0)
+        {
+            ++steps;
+            // the gap between the end of a step and the start of the next one (host work between slabStep calls)
+            if (cudaEventElapsedTime(&ms, sl->evMarks[k - 1].second, sl->evMarks[k].second) == cudaSuccess) sum[0] += ms * 1e3;
+            continue;
+        }
+        if (cudaEventElapsedTime(&ms, sl->evMarks[k - 1].second, sl->evMarks[k].second) != cudaSuccess) continue;
+        sum[tag] += ms * 1e3;
+        cnt[tag] += 1;
+    }
+    std::fprintf(stderr, "[mrmd_b200 slab rank %d] in-stream us per step over %ld steps:", sl->rank, steps);
+    double total = 0.0;
+    for (int t = 0; t < 14; ++t)
+        if (sum[t] > 0.0)
+        {
+            std::fprintf(stderr, " %s %.1f (x%ld)%s", EV_NAMES[t], sum[t] / std::max(steps, 1L), cnt[t], t < 13 ? "," : "");
+            total += sum[t];
+        }
+    std::fprintf(stderr, " | total %.1f\n", total / std::max(steps, 1L));
+    for (auto& m : sl->evMarks) cudaEventDestroy(m.second);
+    sl->evMarks.clear();
 }
 
 static double profMark(mrmd_b200_slab* sl, cudaStream_t st, double& last)
@@ -1233,10 +1332,12 @@ static int slabRebuildP2P(mrmd_b200_slab* sl, cudaStream_t st)
     }
     double last = 0.0;
     profMark(sl, st, last);
+    evMark(sl, 7, st);
     MB_TRY(pollReport(sl, 4, mseq, st, "migration"));  // host round trip 1: the new number of local atoms
     sl->profRebuild[0] += profMark(sl, st, last);
     MB_REQUIRE(sl->hReport[5] == 0, "slab: more atoms migrate in one rebuild than the peer buffer holds");
     const int64_t nSend = (sl->hReport[0] + sl->hReport[1]) * apm, nRecv = (sl->hReport[2] + sl->hReport[3]) * apm;
+    evMark(sl, 8, st);
     // ---- 2. sort by linked cell; the leavers sort behind the last cell and are dropped
     a->size = n + nRecv;
     const double cutoff = sl->cfg.rc + sl->cfg.skin;
@@ -1271,6 +1372,7 @@ static int slabRebuildP2P(mrmd_b200_slab* sl, cudaStream_t st)
     MB_TRY(slabEnsureMolecules(sl, a->numLocal / apm + 2 * sl->p2pCap, st));
     if (apm > 1) sl->mols->lcView->v.pos = sl->mols->v.pos;
     sl->profRebuild[1] += profMark(sl, st, last);
+    evMark(sl, 9, st);
     // ---- 3. face lists from the first / last cell column (ranges read on the device), push, pull
     const GridDev& g = lc->lcGrid;
     const int64_t perX = int64_t(g.n[1]) * g.n[2];
@@ -1293,9 +1395,11 @@ static int slabRebuildP2P(mrmd_b200_slab* sl, cudaStream_t st)
                                                                     sl->p2pCap, sl->dErr);
         MB_LAUNCHED();
     }
+    evMark(sl, 10, st);
     MB_TRY(haloPush(sl, true, st));
     MB_TRY(haloPull(sl, true, st));
     sl->profRebuild[2] += profMark(sl, st, last);
+    evMark(sl, 11, st);
     // ---- 4. linked cells of the received halo units (they arrive in (j, k) order), tiled neighbour build
     MB_TRY(sl->haloKeys.reserve(size_t(2 * sl->p2pCap) * 4));
     MB_TRY(sl->haloStartLeft.reserve(size_t(perX + 1) * 4));
@@ -1307,6 +1411,7 @@ static int slabRebuildP2P(mrmd_b200_slab* sl, cudaStream_t st)
                                                                       a->numLocal / apm, sl->haloStartLeft.as<int32_t>(),
                                                                       sl->haloStartRight.as<int32_t>());
     MB_LAUNCHED();
+    evMark(sl, 12, st);
     // host round trip 2 (list statistics)
     if (apm > 1)
         MB_TRY(verletBuildTiledMolecules(sl->list, sl->mols, &sl->sub, cutoff, 1.0, sl->cfg.maxNeighbors, apm,
@@ -1315,6 +1420,7 @@ static int slabRebuildP2P(mrmd_b200_slab* sl, cudaStream_t st)
         MB_TRY(verletBuildTiled(sl->list, a, &sl->sub, cutoff, 1.0, sl->cfg.maxNeighbors, sl->haloStartLeft.as<int32_t>(),
                                 sl->haloStartRight.as<int32_t>(), st));
     sl->profRebuild[3] += profMark(sl, st, last);
+    evMark(sl, 13, st);
     MB_TRY(pollReport(sl, 12, static_cast<long long>(sl->haloSeq), st, "halo exchange"));
     MB_REQUIRE(sl->hReport[13] == 0, "slab: the position halo exceeds the peer buffer (density more than tripled since slab_create)");
     MB_REQUIRE(sl->hReport[14] == 0, "slab: a selection list exceeded its capacity during the rebuild");
@@ -1451,6 +1557,9 @@ static int sumOverRanks(void* ctx, double* sums, int64_t count, cudaStream_t st)
     return 0;
 }
 
+static int slabAfterDecision(mrmd_b200_slab* sl, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, bool wantEnergy,
+                             bool deferPost, cudaEvent_t evPosReady, bool rebuildNow, bool pushed, const int* stop, double last);
+
 static int slabStep(mrmd_b200_slab* sl, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, bool wantEnergy,
                     bool deferPost = true, cudaEvent_t evPosReady = nullptr)
 {
@@ -1458,6 +1567,7 @@ static int slabStep(mrmd_b200_slab* sl, cudaStream_t st, cudaEvent_t e0, cudaEve
     mrmd_b200_atoms* a = sl->atoms;
     double last = 0.0;
     profMark(sl, st, last);
+    evMark(sl, 0, st);
     if (sl->constraints != nullptr)  // tests/Constraints/Constraints.cpp:53-54
         MB_TRY(constraintsEnforcePositional(sl->constraints, sl->mols, a, c.dt, st));
     // the previous step's postForceIntegrate rides in front of this kick (flushed when a run returns)
@@ -1471,15 +1581,32 @@ static int slabStep(mrmd_b200_slab* sl, cudaStream_t st, cudaEvent_t e0, cudaEve
     const bool earlyPush = sl->p2p && sl->rebuilds > 0;
     if (sl->apm > 1 && sl->rebuilds > 0)  // the centres of mass travel with the face molecules
         MB_TRY(mrmd_b200_molecules_update(sl->mols, a, &c.weight, st));
-    if (earlyPush) MB_TRY(haloPush(sl, false, st));
+    evMark(sl, 1, st);
+    if (earlyPush)
+    {
+        if (sl->sPush == nullptr)
+        {
+            int prioLow = 0, prioHigh = 0;
+            MB_CUDA(cudaDeviceGetStreamPriorityRange(&prioLow, &prioHigh));
+            MB_CUDA(cudaStreamCreateWithPriority(&sl->sPush, cudaStreamNonBlocking, prioHigh));
+            MB_CUDA(cudaEventCreateWithFlags(&sl->evPreDone, cudaEventDisableTiming));
+            MB_CUDA(cudaEventCreateWithFlags(&sl->evPushDone, cudaEventDisableTiming));
+        }
+        MB_CUDA(cudaEventRecord(sl->evPreDone, st));
+        MB_CUDA(cudaStreamWaitEvent(sl->sPush, sl->evPreDone, 0));
+        MB_TRY(haloPush(sl, false, sl->sPush));
+        MB_CUDA(cudaEventRecord(sl->evPushDone, sl->sPush));
+    }
+    evMark(sl, 2, st);
     // the rebuild decision is collective: global maximum of the squared displacement
     if (sl->p2p)
     {
         sl->decideSeq += 1.0;
         const int parity = static_cast<int>(static_cast<long long>(sl->decideSeq) & 1);
         maxDisplacementGatherKernel<<<1, 32, 0, st>>>(a->dMaxDisp, sl->peers, sl->rank, sl->nranks, sl->decideSeq, parity,
-                                                      a->dMaxDisp, sl->hDecide);
+                                                      a->dMaxDisp, sl->hDecide, nullptr, 0.0, nullptr, 0);
         MB_LAUNCHED();
+        evMark(sl, 3, st);
         // the kernel writes {max, step} into pinned memory: poll it instead of synchronising the stream
         volatile double* h = sl->hDecide;
         for (unsigned spin = 0; h[1] != sl->decideSeq; ++spin)
@@ -1499,20 +1626,36 @@ static int slabStep(mrmd_b200_slab* sl, cudaStream_t st, cudaEvent_t e0, cudaEve
         MB_CUDA(cudaMemcpyAsync(a->hMaxDisp, a->dMaxDisp, 8, cudaMemcpyDeviceToHost, st));
         MB_CUDA(cudaStreamSynchronize(st));
     }
+    // whatever follows (halo pull, or a rebuild that re-orders the atoms and pushes again) is ordered behind the push
+    if (earlyPush) MB_CUDA(cudaStreamWaitEvent(st, sl->evPushDone, 0));
     MB_REQUIRE(std::isfinite(*a->hMaxDisp), "slab_run: non-finite position, velocity or force (the system blew up)");
     sl->maxDisplacement += std::sqrt(*a->hMaxDisp);
     sl->prof[1] += profMark(sl, st, last);
-    if (sl->maxDisplacement >= c.skin * 0.5)
+    return slabAfterDecision(sl, st, e0, e1, wantEnergy, deferPost, evPosReady, sl->maxDisplacement >= c.skin * 0.5, earlyPush,
+                             nullptr, last);
+}
+
+// the step behind the rebuild decision: rebuild or halo pull, force, postForceIntegrate.  stop (device, optional): the step
+// is queued ahead of the host, its kernels return at once when an earlier queued step asked for a rebuild.
+static int slabAfterDecision(mrmd_b200_slab* sl, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, bool wantEnergy,
+                             bool deferPost, cudaEvent_t evPosReady, bool rebuildNow, bool pushed, const int* stop, double last)
+{
+    const mrmd_b200_md_config& c = sl->cfg;
+    mrmd_b200_atoms* a = sl->atoms;
+    if (rebuildNow)
     {
         sl->maxDisplacement = 0.0;
+        if (sl->stepsSinceRebuild > 0) sl->lastRebuildInterval = sl->stepsSinceRebuild;
+        sl->stepsSinceRebuild = 0;
         MB_TRY(slabRebuild(sl, st));
         sl->prof[2] += profMark(sl, st, last);
     }
     else
     {
-        if (earlyPush) MB_TRY(haloPull(sl, false, st));
+        if (pushed) MB_TRY(haloPull(sl, false, st, stop));
         else MB_TRY(haloRefresh(sl, st));
         sl->prof[3] += profMark(sl, st, last);
+        evMark(sl, 4, st);
     }
     if (evPosReady != nullptr) MB_CUDA(cudaEventRecord(evPosReady, st));  // positions and atom order are final
     if (sl->apm > 1)
@@ -1543,22 +1686,102 @@ static int slabStep(mrmd_b200_slab* sl, cudaStream_t st, cudaEvent_t e0, cudaEve
             MB_TRY(mrmd_b200_thermo_apply(t, a, nullptr, 0, st));
         }
         if (e0) MB_CUDA(cudaEventRecord(e0, st));
-        MB_TRY(adressRunPeriodic(sl->adress, a, sl->list, &c.weight, wantEnergy, st));
+        MB_TRY(adressRunPeriodic(sl->adress, a, sl->list, &c.weight, wantEnergy, st, stop));
         if (e1) MB_CUDA(cudaEventRecord(e1, st));
     }
     else
     {
         if (e0) MB_CUDA(cudaEventRecord(e0, st));
-        MB_TRY(ljApplyTiled(sl->lj, a, sl->list, false, wantEnergy, st));
+        MB_TRY(ljApplyTiled(sl->lj, a, sl->list, false, wantEnergy, st, stop));
         if (e1) MB_CUDA(cudaEventRecord(e1, st));
     }
     sl->prof[4] += profMark(sl, st, last);
     sl->prof[5] += 1.0;
+    evMark(sl, 5, st);
     if (sl->constraints != nullptr)
         MB_TRY(constraintsEnforceVelocity(sl->constraints, sl->mols, a, st, c.dt));  // RATTLE with the kick riding along
     else if (deferPost) sl->postPending = true;  // rides in front of the next step's kick
     else MB_TRY(mrmd_b200_vv_post(a, c.dt, st));
     sl->step += 1;
+    sl->stepsSinceRebuild += 1;
+    return 0;
+}
+
+// Steps queued ahead of the host (as md.cu:runQueued, collective): up to `count` steps are enqueued back to back -- kick /
+// drift, halo push, displacement gather WITH the rebuild criterion evaluated on the device, halo pull, force -- and the
+// step whose accumulated global displacement reaches skin / 2 raises a flag on every rank (all ranks see the same
+// maxima), after which the kernels queued behind it return at once.  One host synchronisation per chunk instead of one
+// host poll per step: the ranks no longer wait for each other's hosts.
+static bool slabCanQueue(const mrmd_b200_slab* sl, int64_t ahead)
+{
+    const mrmd_b200_md_config& c = sl->cfg;
+    if (!sl->p2p || sl->apm > 1 || sl->rebuilds == 0 || sl->profile || sl->evProfile) return false;
+    // measured on 2 GPUs (1M atoms each): 0.489 ms / step queued against 0.482 with the per-step host poll -- the host
+    // round trip is not what the slab step waits for, and the kernels queued behind a stop cost a little: opt-in
+    if (std::getenv("MRMD_B200_SLAB_QUEUED_STEPS") == nullptr) return false;
+    const int64_t step = sl->step + ahead;
+    if (c.adress)
+    {
+        if (sl->thermo != nullptr)
+        {
+            if (c.thermoSampleInterval > 0 && step % c.thermoSampleInterval == 0) return false;
+            if (c.thermoUpdateInterval > 0 && step > 0 && step % c.thermoUpdateInterval == 0) return false;
+        }
+        const int64_t run = sl->adress->runCounter + ahead;
+        if (run % sl->adress->samplingInterval == 0 || run % sl->adress->updateInterval == 0) return false;
+    }
+    return true;
+}
+
+static int slabRunQueued(mrmd_b200_slab* sl, int64_t count, cudaStream_t st, cudaEvent_t* events, bool energyOnLast,
+                         bool energyAlways, int64_t* done, bool* stopped)
+{
+    const mrmd_b200_md_config& c = sl->cfg;
+    mrmd_b200_atoms* a = sl->atoms;
+    if (sl->dStop == nullptr)
+    {
+        MB_CUDA(cudaMalloc(&sl->dStop, 16));
+        MB_CUDA(cudaMalloc(&sl->dAccum, 8));
+        MB_CUDA(cudaMallocHost(&sl->hStop, 32));
+    }
+    double* hAccum = reinterpret_cast<double*>(sl->hStop + 4);
+    *hAccum = sl->maxDisplacement;
+    MB_CUDA(cudaMemsetAsync(sl->dStop, 0, 16, st));
+    MB_CUDA(cudaMemcpyAsync(sl->dAccum, hAccum, 8, cudaMemcpyHostToDevice, st));
+    const int64_t step0 = sl->step, since0 = sl->stepsSinceRebuild, run0 = c.adress ? sl->adress->runCounter : 0;
+    const unsigned long long haloSeq0 = sl->haloSeq;
+    const double decideSeq0 = sl->decideSeq;
+    for (int64_t k = 0; k < count; ++k)
+    {
+        MB_TRY(integratePre(a, c.dt, c.integrator == 1, c.zeta, c.temperature, c.seed, uint64_t(sl->step), nullptr,
+                            sl->postPending, st, sl->dStop));
+        sl->postPending = false;
+        MB_TRY(haloPush(sl, false, st, sl->dStop));
+        sl->decideSeq += 1.0;
+        const int parity = static_cast<int>(static_cast<long long>(sl->decideSeq) & 1);
+        maxDisplacementGatherKernel<<<1, 32, 0, st>>>(a->dMaxDisp, sl->peers, sl->rank, sl->nranks, sl->decideSeq, parity,
+                                                      a->dMaxDisp, sl->hDecide, sl->dAccum, c.skin * 0.5, sl->dStop,
+                                                      static_cast<int>(k));
+        MB_LAUNCHED();
+        const bool wantEnergy = energyAlways || (energyOnLast && k == count - 1);
+        MB_TRY(slabAfterDecision(sl, st, events ? events[2 * k] : nullptr, events ? events[2 * k + 1] : nullptr, wantEnergy, true,
+                                 nullptr, false, true, sl->dStop, 0.0));
+    }
+    MB_CUDA(cudaMemcpyAsync(sl->hStop, sl->dStop, 16, cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaMemcpyAsync(hAccum, sl->dAccum, 8, cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaStreamSynchronize(st));
+    MB_REQUIRE(sl->hStop[2] == 0, "slab_run: non-finite position, velocity or force (the system blew up)");
+    *stopped = sl->hStop[0] != 0;
+    *done = *stopped ? sl->hStop[1] : count;
+    sl->maxDisplacement = *hAccum;
+    // the host-side counters follow the steps that really ran: a stopped step ran its kick / drift, push and gather
+    const int64_t ran = *done + (*stopped ? 1 : 0);
+    sl->haloSeq = haloSeq0 + static_cast<unsigned long long>(ran);
+    sl->decideSeq = decideSeq0 + double(ran);
+    sl->step = step0 + *done;
+    sl->stepsSinceRebuild = since0 + *done;
+    if (c.adress) sl->adress->runCounter = run0 + *done;
+    sl->postPending = !*stopped;
     return 0;
 }
 }  // namespace mrmd_b200
@@ -1642,6 +1865,7 @@ int mrmd_b200_slab_create_cuts(mrmd_b200_slab** out, const mrmd_b200_md_config* 
     sl->atoms = atoms;
     sl->apm = static_cast<int>(apmCfg);
     sl->profile = std::getenv("MRMD_B200_SLAB_PROFILE") != nullptr;
+    sl->evProfile = std::getenv("MRMD_B200_SLAB_EVENTS") != nullptr;
     int rc = 0;
     if (width < cutoff)
     {
@@ -1733,6 +1957,7 @@ int mrmd_b200_slab_destroy(mrmd_b200_slab* sl)
 {
     if (sl == nullptr) return 0;
     cudaDeviceSynchronize();
+    evReport(sl);
     if (sl->profile && sl->prof[5] > 0)
         std::fprintf(stderr,
                      "[mrmd_b200 slab rank %d] us/step over %.0f steps (%lld rebuilds): pre %.1f, decision %.1f, rebuild %.1f, "
@@ -1745,11 +1970,17 @@ int mrmd_b200_slab_destroy(mrmd_b200_slab* sl)
                      sl->profRebuild[2] / sl->rebuilds, sl->profRebuild[3] / sl->rebuilds);
     for (auto e : sl->events) cudaEventDestroy(e);
     sl->hp.destroy();
+    if (sl->sPush != nullptr) cudaStreamDestroy(sl->sPush);
+    if (sl->evPreDone != nullptr) cudaEventDestroy(sl->evPreDone);
+    if (sl->evPushDone != nullptr) cudaEventDestroy(sl->evPushDone);
     if (sl->comm != nullptr) g_nccl.commDestroy(sl->comm);
     mrmd_b200_verlet_destroy(sl->list);
     for (int r = 0; r < SL_MAX_PEERS && r < sl->nranks; ++r)
         if (sl->peers.p[r] != nullptr && r != sl->rank) cudaIpcCloseMemHandle(sl->peers.p[r]);
     if (sl->hDecide != nullptr) cudaFreeHost(sl->hDecide);
+    if (sl->dStop != nullptr) cudaFree(sl->dStop);
+    if (sl->dAccum != nullptr) cudaFree(sl->dAccum);
+    if (sl->hStop != nullptr) cudaFreeHost(sl->hStop);
     if (sl->hReport != nullptr) cudaFreeHost(sl->hReport);
     if (sl->dErr != nullptr) cudaFree(sl->dErr);
     sl->migIdxA.release();
@@ -1838,11 +2069,36 @@ int mrmd_b200_slab_run(mrmd_b200_slab* sl, int64_t nsteps, int timeForceKernel, 
         sl->events.push_back(e);
     }
     int64_t storedSum = 0;
-    for (int64_t i = 0; i < nsteps; ++i)
+    const bool energyAlways = sl->cfg.energyEveryStep != 0;
+    for (int64_t i = 0; i < nsteps;)
     {
+        // as many steps as the last rebuild interval suggests are queued ahead of the host (see slabRunQueued); every
+        // rank takes the same decisions from the same counters
+        int64_t count = 0;
+        const int64_t want = std::max<int64_t>(1, std::min<int64_t>(16, sl->lastRebuildInterval - sl->stepsSinceRebuild + 1));
+        while (count < want && i + count < nsteps && slabCanQueue(sl, count)) ++count;
+        if (count >= 1)
+        {
+            int64_t done = 0;
+            bool stopped = false;
+            MB_TRY(slabRunQueued(sl, count, st, (i + count <= nTimed) ? sl->events.data() + 2 * i : nullptr, i + count == nsteps,
+                                 energyAlways, &done, &stopped));
+            storedSum += sl->storedPairsNow * done;
+            i += done;
+            if (stopped)
+            {
+                // step i ran kick / drift, push and gather on the device and reached skin / 2: rebuild, force, kick
+                MB_TRY(slabAfterDecision(sl, st, i < nTimed ? sl->events[2 * i] : nullptr, i < nTimed ? sl->events[2 * i + 1] : nullptr,
+                                         i == nsteps - 1 || energyAlways, true, nullptr, true, true, nullptr, 0.0));
+                storedSum += sl->storedPairsNow;
+                i += 1;
+            }
+            continue;
+        }
         MB_TRY(slabStep(sl, st, i < nTimed ? sl->events[2 * i] : nullptr, i < nTimed ? sl->events[2 * i + 1] : nullptr,
-                        i == nsteps - 1 || sl->cfg.energyEveryStep != 0));
+                        i == nsteps - 1 || energyAlways));
         storedSum += sl->storedPairsNow;
+        ++i;
     }
     if (sl->postPending)
     {

@@ -612,8 +612,9 @@ template <bool SINGLE_TYPE, bool ACCUMULATE, bool ENERGY>
 __global__ void __launch_bounds__(TL_THREADS_FORCE)
     ljForceTiledKernel(TileParams tp, AtomsView a, const int* __restrict__ desc, const int32_t* __restrict__ counts,
                        const uint16_t* __restrict__ enc, int width, LJTable table, double rcSqr, int64_t numTypesQuirk,
-                       double* partials, double* result, unsigned int* ticket)
+                       double* partials, double* result, unsigned int* ticket, const int* __restrict__ stop)
 {
+    if (stop != nullptr && *stop != 0) return;  // a step queued behind the one that asked for a rebuild
     extern __shared__ double sTile[];
     __shared__ TileDesc td;
     loadTileDesc(desc, td, blockIdx.x);
@@ -771,8 +772,9 @@ __global__ void __launch_bounds__(TL_THREADS_FORCE, 6)
     adressForceTiledKernel(TileParams tp, AtomsView a, const int* __restrict__ desc, const int32_t* __restrict__ counts,
                            const uint16_t* __restrict__ enc, int width, LJTable table, double rcSqr, int64_t numTypes,
                            mrmd_b200_weight w, double* hist, const int32_t* __restrict__ activeTiles, double* partials,
-                           double* result, unsigned int* ticket)
+                           double* result, unsigned int* ticket, const int* __restrict__ stop)
 {
+    if (stop != nullptr && *stop != 0) return;  // a step queued behind the one that asked for a rebuild
     extern __shared__ double sTile[];
     __shared__ TileDesc td;
     double energy = 0.0, pairs = 0.0, activePairs = 0.0;
@@ -1169,7 +1171,7 @@ int tiledConfigure()
 }
 
 int ljApplyTiled(mrmd_b200_lj* lj, mrmd_b200_atoms* a, const mrmd_b200_verlet* v, bool accumulate, bool energy,
-                 cudaStream_t st)
+                 cudaStream_t st, const int* stop)
 {
     MB_REQUIRE(a->lcValid && a->lcEpoch == v->tiledEpoch, "lj_apply: the atoms were re-sorted after this tiled list was built");
     MB_REQUIRE(!v->half, "lj_apply: tiled lists are full lists");
@@ -1184,7 +1186,7 @@ int ljApplyTiled(mrmd_b200_lj* lj, mrmd_b200_atoms* a, const mrmd_b200_verlet* v
 #define LJT_LAUNCH(S1, ACC, EN)                                                                                       \
     ljForceTiledKernel<S1, ACC, EN><<<tiles, TL_THREADS_FORCE, smem, st>>>(                                           \
         tp, a->v, v->tileDesc.as<int>(), v->counts.as<int32_t>(), v->enc.as<uint16_t>(), static_cast<int>(v->width), \
-        lj->table, lj->rcSqr, lj->numTypesQuirk, lj->partials.as<double>(), lj->dResult, lj->dTicket)
+        lj->table, lj->rcSqr, lj->numTypesQuirk, lj->partials.as<double>(), lj->dResult, lj->dTicket, stop)
     if (single)
     {
         if (accumulate) { if (energy) LJT_LAUNCH(true, true, true); else LJT_LAUNCH(true, true, false); }
@@ -1202,7 +1204,7 @@ int ljApplyTiled(mrmd_b200_lj* lj, mrmd_b200_atoms* a, const mrmd_b200_verlet* v
 
 // the force kernel of mrmd_b200_adress_run_periodic (adress.cu owns the run counter and the histogram update)
 int adressApplyTiled(mrmd_b200_adress* ad, mrmd_b200_atoms* a, const mrmd_b200_verlet* v, const mrmd_b200_weight* w,
-                     bool sampling, bool energy, cudaStream_t st)
+                     bool sampling, bool energy, cudaStream_t st, const int* stop)
 {
     MB_REQUIRE(a->lcValid && a->lcEpoch == v->tiledEpoch,
                "adress_run_periodic: the atoms were re-sorted after this tiled list was built");
@@ -1238,7 +1240,8 @@ int adressApplyTiled(mrmd_b200_adress* ad, mrmd_b200_atoms* a, const mrmd_b200_v
 #define ADT_LAUNCH(S1, SAMP, EN)                                                                                      \
     adressForceTiledKernel<S1, SAMP, EN><<<tiles, TL_THREADS_FORCE, smem, st>>>(                                      \
         tp, a->v, v->tileDesc.as<int>(), v->counts.as<int32_t>(), v->enc.as<uint16_t>(), static_cast<int>(v->width), \
-        ad->table, ad->rcSqr, ad->numTypes, *w, ad->hist, activeTiles, ad->partials.as<double>(), ad->dResult, ad->dTicket)
+        ad->table, ad->rcSqr, ad->numTypes, *w, ad->hist, activeTiles, ad->partials.as<double>(), ad->dResult, ad->dTicket, \
+        stop)
     if (single)
     {
         if (sampling) { if (energy) ADT_LAUNCH(true, true, true); else ADT_LAUNCH(true, true, false); }
