@@ -238,6 +238,39 @@ __global__ void cellKeyKernel(const double4* pos, int64_t first, int64_t count, 
     if (cellIdOut != nullptr) cellIdOut[first + j] = c;
 }
 
+// x-slab decomposition (slab.cu): the key kernel of the rebuild also applies the y / z periodic wrap
+// (PeriodicMapping.cpp:36-51 arithmetic, written back) and gives the atoms that left the slab in x the key numCells, so
+// that they sort behind the last cell and are dropped -- one pass over the positions instead of three
+__global__ void cellKeySlabKernel(double4* pos, int64_t count, GridDev g, SubdomainDev s, uint32_t* keys, uint32_t* vals,
+                                  uint32_t dropKey)
+{
+    const int64_t j = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (j >= count) return;
+    double4 p = ld4(pos + j);
+    double* x = &p.x;
+    bool moved = false;
+#pragma unroll
+    for (int dim = 1; dim < 3; ++dim)
+    {
+        if (s.maxCorner[dim] <= x[dim])
+        {
+            x[dim] -= s.diameter[dim];
+            x[dim] = fmax(x[dim], s.minCorner[dim]);
+            moved = true;
+        }
+        if (x[dim] < s.minCorner[dim])
+        {
+            x[dim] += s.diameter[dim];
+            if (s.maxCorner[dim] <= x[dim]) x[dim] = s.minCorner[dim];
+            moved = true;
+        }
+    }
+    if (moved) st4(pos + j, p);
+    const bool gone = (p.x < s.minCorner[0]) || (p.x >= s.maxCorner[0]);
+    keys[j] = gone ? dropKey : static_cast<uint32_t>(cardinal(g, locate1(g, p.x, 0), locate1(g, p.y, 1), locate1(g, p.z, 2)));
+    vals[j] = static_cast<uint32_t>(j);
+}
+
 // slot i of the new arrays receives record src(i): perm inside [begin,end), identity outside
 __global__ void permuteAtomsKernel(AtomsView dst, AtomsView src, const uint32_t* perm, int64_t begin, int64_t end,
                                    int64_t size)
@@ -513,7 +546,15 @@ extern "C" {
 namespace mrmd_b200
 {
 static int atomsCellSortImpl(mrmd_b200_atoms* a, int64_t begin, int64_t end, const double* delta, const double* gridMin,
-                             const double* gridMax, int32_t* cellIdOut, const signed char* dropFlags, cudaStream_t st);
+                             const double* gridMax, int32_t* cellIdOut, const signed char* dropFlags, cudaStream_t st,
+                             const SubdomainDev* slabWrap = nullptr);
+
+// the slab rebuild's sort over [0, end): y / z wrap, drop of the atoms outside [min_x, max_x), cell sort (cellKeySlabKernel)
+int atomsCellSortSlab(mrmd_b200_atoms* a, int64_t end, const double* delta, const mrmd_b200_subdomain* sub, cudaStream_t st)
+{
+    const SubdomainDev sd = toDev(*sub);
+    return atomsCellSortImpl(a, 0, end, delta, sub->minCorner, sub->maxCorner, nullptr, nullptr, st, &sd);
+}
 
 // cell sort that also removes the atoms flagged in dropFlags: they end up behind lcCellStart[numCells]
 int atomsCellSortDrop(mrmd_b200_atoms* a, int64_t begin, int64_t end, const double* delta, const double* gridMin,
@@ -585,7 +626,8 @@ int moleculesCellSortWithAtoms(mrmd_b200_molecules* m, mrmd_b200_atoms* a, int64
 }
 
 static int atomsCellSortImpl(mrmd_b200_atoms* a, int64_t begin, int64_t end, const double* delta, const double* gridMin,
-                             const double* gridMax, int32_t* cellIdOut, const signed char* dropFlags, cudaStream_t st)
+                             const double* gridMax, int32_t* cellIdOut, const signed char* dropFlags, cudaStream_t st,
+                             const SubdomainDev* slabWrap)
 {
     MB_REQUIRE(a != nullptr && delta != nullptr && gridMin != nullptr && gridMax != nullptr, "atoms_cell_sort");
     MB_REQUIRE(begin >= 0 && begin <= end && end <= a->size, "atoms_cell_sort: range outside the container");
@@ -597,8 +639,11 @@ static int atomsCellSortImpl(mrmd_b200_atoms* a, int64_t begin, int64_t end, con
     uint32_t *k0, *v0, *k1, *v1, *hist;
     MB_TRY(cellSortPrepare(a->sortScratch, count, &k0, &v0, &k1, &v1, &hist));
     MB_TRY(atomsEnsureAlt(a, st));
-    cellKeyKernel<<<gridFor(count, 256), 256, 0, st>>>(a->v.pos, begin, count, g, k0, v0, cellIdOut, dropFlags,
-                                                       static_cast<uint32_t>(numCells));
+    if (slabWrap != nullptr)
+        cellKeySlabKernel<<<gridFor(count, 256), 256, 0, st>>>(a->v.pos, count, g, *slabWrap, k0, v0, static_cast<uint32_t>(numCells));
+    else
+        cellKeyKernel<<<gridFor(count, 256), 256, 0, st>>>(a->v.pos, begin, count, g, k0, v0, cellIdOut, dropFlags,
+                                                           static_cast<uint32_t>(numCells));
     MB_LAUNCHED();
     uint32_t *sortedKeys, *perm;
     MB_TRY(radixSortPairs(k0, v0, k1, v1, hist, count, bitsFor(numCells + 1), &sortedKeys, &perm, st));

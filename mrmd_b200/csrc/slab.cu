@@ -494,6 +494,8 @@ __global__ void __launch_bounds__(SL_THREADS)
 //   MODE 0  migration: both over [0, n): A = flag < 0 (leaves to the left), B = flag > 0
 //   MODE 1  halo faces: A = units of the first cell column with x < lowBound, B = units of the last cell column with
 //           x >= highBound; the column ranges are read from the device-side cell prefix array (no host round trip)
+//   MODE 2  migration by position over the same two columns of the PREVIOUS sort (bounds = the slab corners): a unit
+//           moves by less than the skin between two rebuilds, so a leaver sat in a boundary column
 struct SelArgs
 {
     const double4* upos;
@@ -520,7 +522,9 @@ __device__ __forceinline__ bool selPredicate(const SelArgs& g, int list, int64_t
     unit = first + j;
     if (unit >= last) return false;
     const double x = ld4nc(g.upos + unit).x;
-    return list == 0 ? (x < g.lowBound) : (x >= g.highBound);  // GhostExchange.cpp:80 / :89
+    // MODE 1: GhostExchange.cpp:80 / :89 (x < minInnerCorner, x >= maxInnerCorner); MODE 2: the units that left the slab
+    // (x < minCorner, x >= maxCorner), looked for in the boundary columns of the previous sort only
+    return list == 0 ? (x < g.lowBound) : (x >= g.highBound);
 }
 
 __device__ __forceinline__ long long blockScan1(long long v, long long& total)
@@ -554,7 +558,7 @@ template <int MODE>
 __global__ void __launch_bounds__(SL_THREADS) selCountKernel(SelArgs g, int64_t* blockCounts, int* err)
 {
     const int list = blockIdx.y;
-    if (MODE == 1 && blockIdx.x == 0 && threadIdx.x == 0)
+    if (MODE != 0 && blockIdx.x == 0 && threadIdx.x == 0)
     {
         // the grid was sized from an estimate of the column population: a fuller column must not go unnoticed
         const int64_t len = list == 0 ? int64_t(*g.rangeA1) - *g.rangeA0 : int64_t(*g.rangeB1) - *g.rangeB0;
@@ -857,6 +861,7 @@ int atomsCellSortDrop(mrmd_b200_atoms* a, int64_t begin, int64_t end, const doub
                       const double* gridMax, const signed char* dropFlags, cudaStream_t st);
 int cellStartFromKeys(const uint32_t* sortedKeys, int64_t n, int64_t numCells, int32_t* cellStart, int32_t offset,
                       cudaStream_t st);
+int atomsCellSortSlab(mrmd_b200_atoms* a, int64_t end, const double* delta, const mrmd_b200_subdomain* sub, cudaStream_t st);
 }  // namespace mrmd_b200
 
 struct mrmd_b200_slab
@@ -893,6 +898,9 @@ struct mrmd_b200_slab
     int64_t migCap = 0;      // units per migration region
     int64_t colBound = 0;    // upper bound of the units in one cell column (grid of the face selection)
     long long migSeq = 0;
+    // a->posEpoch at the last sort and the kick / drift kernels since: any other change of the positions (an upload
+    // through the host-buffer path, a caller's atoms_write) makes the rebuild fall back to the full selection
+    int64_t posEpochAtSort = -1, presSinceSort = 0;
     long long* hReport = nullptr;  // pinned, 16 words: [0..5] migration {toL, toR, fromL, fromR, seq, err}, [8..13] halo lists
     int* dErr = nullptr;
     mrmd_b200::DevBuf migIdxA, migIdxB;
@@ -1285,7 +1293,34 @@ static int slabRebuildP2P(mrmd_b200_slab* sl, cudaStream_t st)
     signed char* flag = sl->flags.as<signed char>();
     MB_CUDA(cudaMemsetAsync(sl->dErr, 0, 4, st));
     // ---- 1. wrap y / z, flag and list the leavers, push their records, take in the arrivals
-    if (apm > 1)
+    // Atoms that leave in x sat in the first / last cell column of the previous sort (they moved by less than the skin
+    // since): the leavers are selected there by position, the y / z wrap and the drop of the leavers ride in the sort's
+    // key kernel -- no pass over all atoms before the migration.  Needs the previous sort's cell ranges and positions
+    // that only the step loop changed.
+    const bool columnsOnly = apm == 1 && sl->rebuilds > 0 && a->lcValid && a->lcEnd == n && a->posEpoch == sl->posEpochAtSort + sl->presSinceSort;
+    if (columnsOnly)
+    {
+        const GridDev& g0 = a->lcGrid;
+        const int64_t perX0 = int64_t(g0.n[1]) * g0.n[2];
+        const int32_t* cs = a->lcCellStart.as<int32_t>();
+        SelArgs leave{};
+        leave.upos = a->v.pos;
+        leave.rangeA0 = cs;
+        leave.rangeA1 = cs + perX0;
+        leave.rangeB0 = cs + (int64_t(g0.n[0]) - 1) * perX0;
+        leave.rangeB1 = cs + a->lcNumCells;
+        leave.lowBound = sl->sub.minCorner[0];
+        leave.highBound = sl->sub.maxCorner[0];
+        const int blocksCol = std::max(1, gridFor(sl->colBound, SL_THREADS));
+        selCountKernel<2><<<dim3(blocksCol, 2), SL_THREADS, 0, st>>>(leave, bc, sl->dErr);
+        MB_LAUNCHED();
+        selScanKernel<<<2, SL_THREADS, 0, st>>>(bc, blocksCol, sl->dTotals);
+        MB_LAUNCHED();
+        selIndexKernel<2><<<dim3(blocksCol, 2), SL_THREADS, 0, st>>>(leave, bc, sl->migIdxA.as<int32_t>(), sl->migIdxB.as<int32_t>(),
+                                                                    sl->migCap, sl->dErr);
+        MB_LAUNCHED();
+    }
+    else if (apm > 1)
     {
         mrmd_b200_molecules* m = sl->mols;
         m->numLocal = nUnits;
@@ -1304,17 +1339,20 @@ static int slabRebuildP2P(mrmd_b200_slab* sl, cudaStream_t st)
         slabWrapFlagKernel<<<gridFor(n, 256), 256, 0, st>>>(a->v.pos, n, toDev(sl->sub), flag);
         MB_LAUNCHED();
     }
-    SelArgs mig{};
-    mig.upos = unitPositions(sl);
-    mig.flag = flag;
-    mig.n = nUnits;
-    selCountKernel<0><<<dim3(blocksAll, 2), SL_THREADS, 0, st>>>(mig, bc, sl->dErr);
-    MB_LAUNCHED();
-    selScanKernel<<<2, SL_THREADS, 0, st>>>(bc, blocksAll, sl->dTotals);
-    MB_LAUNCHED();
-    selIndexKernel<0><<<dim3(blocksAll, 2), SL_THREADS, 0, st>>>(mig, bc, sl->migIdxA.as<int32_t>(), sl->migIdxB.as<int32_t>(),
-                                                                sl->migCap, sl->dErr);
-    MB_LAUNCHED();
+    if (!columnsOnly)
+    {
+        SelArgs mig{};
+        mig.upos = unitPositions(sl);
+        mig.flag = flag;
+        mig.n = nUnits;
+        selCountKernel<0><<<dim3(blocksAll, 2), SL_THREADS, 0, st>>>(mig, bc, sl->dErr);
+        MB_LAUNCHED();
+        selScanKernel<<<2, SL_THREADS, 0, st>>>(bc, blocksAll, sl->dTotals);
+        MB_LAUNCHED();
+        selIndexKernel<0><<<dim3(blocksAll, 2), SL_THREADS, 0, st>>>(mig, bc, sl->migIdxA.as<int32_t>(), sl->migIdxB.as<int32_t>(),
+                                                                    sl->migCap, sl->dErr);
+        MB_LAUNCHED();
+    }
     const long long mseq = ++sl->migSeq;
     {
         double* dstL = reinterpret_cast<double*>(sl->peerLeftBuf + migRegionOffset(sl, 1));   // the left rank's "from right"
@@ -1363,11 +1401,14 @@ static int slabRebuildP2P(mrmd_b200_slab* sl, cudaStream_t st)
     }
     else
     {
-        MB_TRY(atomsCellSortDrop(a, 0, n + nRecv, delta, sl->sub.minCorner, sl->sub.maxCorner, flag, st));
+        if (columnsOnly) MB_TRY(atomsCellSortSlab(a, n + nRecv, delta, &sl->sub, st));
+        else MB_TRY(atomsCellSortDrop(a, 0, n + nRecv, delta, sl->sub.minCorner, sl->sub.maxCorner, flag, st));
         a->numLocal = n + nRecv - nSend;
         a->lcEnd = a->numLocal;
     }
     a->size = a->numLocal;
+    sl->posEpochAtSort = a->posEpoch;
+    sl->presSinceSort = 0;
     MB_TRY(atomsEnsureCapacity(a, a->numLocal + 2 * sl->p2pCap * apm, st));
     MB_TRY(slabEnsureMolecules(sl, a->numLocal / apm + 2 * sl->p2pCap, st));
     if (apm > 1) sl->mols->lcView->v.pos = sl->mols->v.pos;
@@ -1574,6 +1615,7 @@ static int slabStep(mrmd_b200_slab* sl, cudaStream_t st, cudaEvent_t e0, cudaEve
     MB_TRY(integratePre(a, c.dt, c.integrator == 1, c.zeta, c.temperature, c.seed,
                         uint64_t(sl->step), nullptr, sl->postPending, st));
     sl->postPending = false;
+    sl->presSinceSort += 1;
     sl->prof[0] += profMark(sl, st, last);
     // the positions are final: the face atoms leave for the neighbours right away, so that the NVLink transfer overlaps
     // the rebuild decision (double-buffered regions; a push that a rebuild supersedes is simply never pulled).  Before
@@ -1756,6 +1798,7 @@ static int slabRunQueued(mrmd_b200_slab* sl, int64_t count, cudaStream_t st, cud
         MB_TRY(integratePre(a, c.dt, c.integrator == 1, c.zeta, c.temperature, c.seed, uint64_t(sl->step), nullptr,
                             sl->postPending, st, sl->dStop));
         sl->postPending = false;
+        sl->presSinceSort += 1;
         MB_TRY(haloPush(sl, false, st, sl->dStop));
         sl->decideSeq += 1.0;
         const int parity = static_cast<int>(static_cast<long long>(sl->decideSeq) & 1);
