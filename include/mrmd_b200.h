@@ -277,7 +277,14 @@ int mrmd_b200_verlet_read(const mrmd_b200_verlet* v, int32_t* counts, int32_t* n
 
 /* ---- action::LennardJones ------------------------------------------------------------------- */
 /* replaces LennardJones(cappingDistance[], rc[], sigma[], epsilon[], numTypes, isShifted)
- * (action/LennardJones.cpp:46-56, :81-116); arrays hold numTypes^2 entries */
+ * (action/LennardJones.cpp:46-56, :81-116); arrays hold numTypes^2 entries.
+ * Reference quirk kept on purpose: LennardJones::numTypes_ is initialised to 1 (LennardJones.cpp:52), so apply() indexes
+ * the table with  type_i * 1 + type_j : with more than one type, pair (1, 1) reads the entry of (1, 0) and so on
+ * (LJ_IdealGas indexes type_i * numTypes + type_j and does not have the quirk).  mrmd_b200_lj_create reproduces that for
+ * parity and leaves a note in mrmd_b200_last_error() when numTypes > 1; single-type systems are unaffected.
+ * Handles are single-stream objects: an operator handle (lj, adress, thermo, verlet, md, slab) owns its reduction
+ * scratch, ticket counter and result buffers, so two calls on the same handle must be ordered on one stream (or by an
+ * event); different handles may run on different streams concurrently. */
 int mrmd_b200_lj_create(mrmd_b200_lj** out, const double* cappingDistance, const double* rc, const double* sigma,
                         const double* epsilon, int64_t numTypes, int isShifted);
 int mrmd_b200_lj_destroy(mrmd_b200_lj* lj);

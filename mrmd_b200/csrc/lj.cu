@@ -169,6 +169,9 @@ int mrmd_b200_lj_create(mrmd_b200_lj** out, const double* cappingDistance, const
     cudaMemset(lj->dResult, 0, 48);
     cudaMemset(lj->dTicket, 0, 4);
     lj->numTypes = numTypes;
+    if (numTypes > 1)
+        setLastError("note: LennardJones indexes its table with type_i + type_j (numTypes_ is 1 in the reference, "
+                     "LennardJones.cpp:52): with several types pair (1, 1) uses the parameters of (1, 0)");
     *out = lj;
     return 0;
 }

@@ -352,6 +352,7 @@ static int collectStats(mrmd_b200_md* md, int64_t nsteps, int64_t rebuilds0, int
     MB_CUDA(cudaStreamSynchronize(st));
     if (md->cfg.adress && md->adress->uniformAtoms > 0) MB_TRY(adressCheckUniform(md->adress, st));
     if (stats == nullptr) return 0;
+    *stats = mrmd_b200_md_stats{};
     stats->steps = nsteps;
     stats->rebuilds = md->rebuilds - rebuilds0;
     stats->storedPairs = storedSum;
@@ -359,6 +360,12 @@ static int collectStats(mrmd_b200_md* md, int64_t nsteps, int64_t rebuilds0, int
     stats->numGhost = md->atoms->numGhost;
     stats->maxDisplacement = md->maxDisplacement;
     stats->activePairs = 0;
+    if (nsteps == 0)
+    {
+        // nothing ran: no energy / virial / pair counts of an earlier run are reported as this run's
+        stats->forceKernelMs = 0.0;
+        return 0;
+    }
     if (md->cfg.adress)
     {
         stats->energy = hRes[0];
