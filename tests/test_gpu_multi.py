@@ -31,3 +31,8 @@ def test_two_gpu_slabs_match_single_gpu(mode):
     assert res.returncode == 0, (res.stdout[-2000:], res.stderr[-2000:])
     out = json.loads(lines[-1])
     assert out["ok"], out
+
+
+def test_two_gpu_tetramer_slabs_match_single_gpu():
+    """configs[3] physics over x-slabs: whole molecules migrate and travel in the halo, SHAKE / RATTLE stay rank-local"""
+    test_two_gpu_slabs_match_single_gpu("tetramer")

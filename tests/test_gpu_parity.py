@@ -446,3 +446,59 @@ def test_nve_trajectory_vs_oracle(api, oracle, golden_dir):
     # chaotic divergence bound after 60 steps from ~1e-16 seeds
     assert np.abs(atoms.getPos()[:n] - oa["pos"][:n]).max() < 1e-9
     assert np.abs(atoms.getVel()[:n] - oa["vel"][:n]).max() < 1e-8
+
+
+def test_langevin_noise_follows_the_global_atom_id(api):
+    """Philox is keyed by (seed, step, global atom id): the same system handed over in another atom order (ids given)
+    runs the same thermostatted trajectory atom by atom, through spatial sorts and rebuilds"""
+    from mrmd_b200.workloads import lattice_system
+
+    pos, vel, box = lattice_system(12, seed=9)
+    n = len(pos)
+    sub = api.Subdomain([0, 0, 0], box, 2.6)
+    kw = dict(langevin=True, zeta=20.0, temperature=1.5, seed=77, cellSort=True, fullList=2)
+    a = api.Atoms.from_arrays(pos, vel, mass=1.0)
+    api.MolecularDynamics(a, sub, **kw).run(30)
+    perm = np.random.default_rng(3).permutation(n)
+    b = api.Atoms.from_arrays(pos[perm], vel[perm], mass=1.0, ids=perm)
+    api.MolecularDynamics(b, sub, **kw).run(30)
+    ia, ib = a.get("id")[:n], b.get("id")[:n]
+    assert np.array_equal(np.sort(ia), np.arange(n)) and np.array_equal(np.sort(ib), np.arange(n))
+    pa, pb = a.getPos()[:n][np.argsort(ia)], b.getPos()[:n][np.argsort(ib)]
+    va, vb = a.getVel()[:n][np.argsort(ia)], b.getVel()[:n][np.argsort(ib)]
+    # the neighbour rows are summed in another order: equal up to rounding that 30 steps do not amplify visibly
+    assert np.abs(pa - pb).max() < 1e-10 and np.abs(va - vb).max() < 1e-9
+
+
+@pytest.mark.parametrize("adress", [False, True])
+def test_steps_queued_ahead_of_the_host_change_nothing(api, adress, monkeypatch):
+    """mrmd_b200_md_run queues steps ahead of the host with the rebuild criterion evaluated on the device
+    (md.cu:runQueued); the trajectory, the rebuild steps and the statistics are those of the step-by-step loop, bit for
+    bit"""
+    from mrmd_b200.workloads import lattice_system
+
+    pos, vel, box = lattice_system(14, seed=4)
+    n = len(pos)
+    sub = api.Subdomain([0, 0, 0], box, 2.6)
+    extra = {}
+    if adress:
+        extra = dict(adress=True, weight=api.Slab(0.5 * box, 0.25 * box[0], 0.12 * box[0], 1),
+                     thermo=dict(targetDensity=0.512, binWidth=0.5, modulation=2.0, sampleInterval=4, updateInterval=12,
+                                 sigma=2.0, range=2.0))
+    out = []
+    for queued in (True, False):
+        if queued:
+            monkeypatch.delenv("MRMD_B200_NO_QUEUED_STEPS", raising=False)
+        else:
+            monkeypatch.setenv("MRMD_B200_NO_QUEUED_STEPS", "1")
+        atoms = api.Atoms.from_arrays(pos, vel, mass=1.0)
+        md = api.MolecularDynamics(atoms, sub, langevin=True, zeta=20.0, temperature=1.5, seed=5, cellSort=True, fullList=2,
+                                   **extra)
+        stats = [md.run(k) for k in (1, 17, 30)]  # a first step alone (always rebuilds), then runs of uneven length
+        out.append((stats, atoms.getPos()[:n], atoms.getVel()[:n], atoms.get("id")[:n]))
+    (sa, pa, va, ia), (sb, pb, vb, ib) = out
+    for x, y in zip(sa, sb):
+        assert x["rebuilds"] == y["rebuilds"] and x["pairInteractions"] == y["pairInteractions"]
+        assert x["energy"] == y["energy"] and x["storedPairs"] == y["storedPairs"] and x["steps"] == y["steps"]
+    assert sum(s["rebuilds"] for s in sa) >= 5
+    assert np.array_equal(ia, ib) and np.array_equal(pa, pb) and np.array_equal(va, vb)
