@@ -372,6 +372,46 @@ __device__ __forceinline__ long long warpSumLL(long long v)
     return v;
 }
 
+// Grid-wide sums of per-thread counts (integers or halves, far below 2^52 in total): every partial sum is exact in
+// double precision, so the order in which the blocks' fire-and-forget REDs land does not matter -- deterministic
+// without the fence / ticket / last-block pass of gridReduce3 (which kept every block of the tiled force kernels
+// resident for a device-wide memory fence: 11 % of the stall samples of ljForceTiledKernel).  slotA / slotB (either
+// may be nullptr) point at the value of this launch (zeroed by the caller); the running sum sits three doubles
+// behind, as in gridReduce3's result layout.
+template <int THREADS>
+__device__ __forceinline__ void gridAddExact(double a, double b, double* slotA, double* slotB)
+{
+    __shared__ double sAdd[2][THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    a = warpSum(a);
+    if (slotB != nullptr) b = warpSum(b);
+    if (lane == 0)
+    {
+        sAdd[0][warp] = a;
+        sAdd[1][warp] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        double sa = 0, sb = 0;
+        for (int w = 0; w < THREADS / 32; ++w)
+        {
+            sa += sAdd[0][w];
+            sb += sAdd[1][w];
+        }
+        if (slotA != nullptr && sa != 0.0)
+        {
+            atomicAdd(slotA, sa);
+            atomicAdd(slotA + 3, sa);
+        }
+        if (slotB != nullptr && sb != 0.0)
+        {
+            atomicAdd(slotB, sb);
+            atomicAdd(slotB + 3, sb);
+        }
+    }
+}
+
 // Deterministic grid-wide sum of three per-thread scalars: warp shuffle -> block -> per-block partial;
 // the last block to arrive (ticket counter) adds the partials in a fixed order and resets the ticket.
 // partials holds 3 * gridDim.x doubles; result 6 doubles: [0..2] this launch, [3..5] running sums.

@@ -36,7 +36,7 @@ namespace mrmd_b200
 {
 // measurement knobs (profiles/variants.py builds side-by-side libraries with -D overrides); the defaults are the product
 #ifndef MRMD_TL_THREADS_BUILD
-#define MRMD_TL_THREADS_BUILD 256
+#define MRMD_TL_THREADS_BUILD 128
 #endif
 #ifndef MRMD_TL_THREADS_FORCE
 #define MRMD_TL_THREADS_FORCE 128
@@ -47,6 +47,14 @@ namespace mrmd_b200
 constexpr int TL_THREADS_BUILD = MRMD_TL_THREADS_BUILD;  // neighbour build / decode
 constexpr int TL_THREADS_FORCE = MRMD_TL_THREADS_FORCE;  // force kernels (measured: 256 -> 194 us, 128 -> 184 us)
 constexpr int TL_GROUP = 2;                       // lanes per home atom
+#ifndef MRMD_TL_BUILD_BATCH
+#define MRMD_TL_BUILD_BATCH 4
+#endif
+constexpr int TL_BUILD_BATCH = MRMD_TL_BUILD_BATCH;  // candidates a lane of the neighbour build tests per step
+#ifndef MRMD_TL_BUILD_GROUP
+#define MRMD_TL_BUILD_GROUP 8
+#endif
+constexpr int TL_BUILD_GROUP = MRMD_TL_BUILD_GROUP;  // consecutive homes (lanes) that sweep the same candidates
 constexpr int TL_PIECES = 27;                     // 9 columns x {low z-wrap, main, high z-wrap}
 constexpr int TL_MAX_CH = 64;                     // home cells per tile along z
 constexpr int TL_MAX_R = 4;                       // the list radius spans at most this many cells along z
@@ -280,9 +288,19 @@ __device__ __forceinline__ bool tileAllCoarseGrained(const TileParams& tp, const
 // neighbours in z, their shared-memory reads scatter over the staged set, bank conflicts eat the balance (build +5 %,
 // force +0.5 %); (c) tiles sized for a 55 KB budget including the per-home tables of (a): half the homes per tile, twice
 // the staging (build 694 us, force 213 us).
-// Neighbour build on tiles: TL_GROUP lanes scan the candidates of one home atom (in each of the nine columns the z
-// interval the cutoff sphere reaches is one contiguous slot range), accepted slots are appended in scan order
-// through a ballot over the group -> deterministic rows, no atomics.
+__device__ __forceinline__ void stSharedU16(unsigned addr, uint16_t v)
+{
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+
+// Neighbour build on tiles, one lane per home atom.  The homes of a warp are 32 consecutive atoms of the column (z
+// order); in each of the nine columns a lane sweeps the slot range that the cutoff sphere around its home cuts out of
+// the column, all lanes in lock step, so the lanes of a warp read staged records a few slots apart (mostly the same
+// shared-memory lines) and the loop body is the bare criterion: three loads, the uncontracted distance, one predicated
+// 2-byte store into the lane's row buffer.  Rows fill in scan order (column by column, slots ascending): deterministic,
+// no atomics, no ballots.  The trip count of a column is the longest range of the warp (about 25 slots against a mean of
+// 15).  The round-1 kernel gave two lanes to a home and compacted through a warp ballot per step: 52 issued instructions
+// per step against 17 here (profiles/r02_build_ncu.txt: 379 M warp instructions per 1 M atoms, issue bound).
 template <bool HALF>
 __global__ void __launch_bounds__(TL_THREADS_BUILD, 4)
     verletBuildTiledKernel(TileParams tp, GridDev cabanaGrid, const double4* __restrict__ pos,
@@ -317,7 +335,6 @@ __global__ void __launch_bounds__(TL_THREADS_BUILD, 4)
     double* sx_ = sTile;
     double* sy_ = sx_ + 1;  // interleaved {x, y, z} records: one address per slot, conflict-free for consecutive slots
     double* sz_ = sx_ + 2;
-    int* sIdx = reinterpret_cast<int*>(sx_ + 3 * tp.cap);
     const int tile = blockIdx.x;
     const int col = tile / tp.numChunks, chunk = tile % tp.numChunks;
     const int ci = col / tp.g.n[1], cj = col % tp.g.n[1];
@@ -349,18 +366,23 @@ __global__ void __launch_bounds__(TL_THREADS_BUILD, 4)
         }
         cellSlot[r][v] = slot;
     }
-    stageTile<true, false>(tp, td, pos, sx_, sy_, sz_, sIdx, nullptr, tile);
+    stageTile<true, false>(tp, td, pos, sx_, sy_, sz_, nullptr, nullptr, tile);
 
-    // all control flow below is warp uniform (trip counts are the maximum over the warp's four groups, lanes are
-    // predicated): sub-warp *_sync masks that differ between groups would be serialised by the compiler
-    const int group = threadIdx.x / TL_GROUP, gl = threadIdx.x % TL_GROUP;
-    const int shiftInWarp = (threadIdx.x & 31) - gl;  // first lane of the group inside its warp
-    constexpr unsigned GROUP_BITS = (1u << TL_GROUP) - 1u;
+    const int lane = threadIdx.x & 31;
     int mx = 0;
     long long total = 0;
     const double rsqrSafe = rsqr * (1.0 - 1e-9);
-    // accepted slots are collected in a shared-memory row per group and leave with 16-byte stores
-    uint16_t* sRow = reinterpret_cast<uint16_t*>(sx_ + 3 * tp.cap) + group * width;
+    // Accepted slots are collected in the lane's own shared-memory row, in the layout of the list (tiledRowIndex), and
+    // leave as coalesced 4-byte words.  The row pitch is an odd number of words: lanes with equal counts hit different
+    // banks, and the copy-out below reads consecutive words.
+    const int rowWords = (width >> 1) + 1;
+    uint32_t* const sRows = reinterpret_cast<uint32_t*>(sx_ + 3 * (tp.cap + TL_BUILD_BATCH));
+    uint16_t* sRow = reinterpret_cast<uint16_t*>(sRows + threadIdx.x * rowWords);
+    const unsigned rowBegin = static_cast<unsigned>(__cvta_generic_to_shared(sRow)), rowEnd = rowBegin + 2u * unsigned(width);
+    const int halfWidth = width / TL_GROUP;
+    const int safeHi = __double2hiint(rsqrSafe);  // d2 > 0: the high words order like the values
+    const int wordsPerLane = halfWidth >> 1;  // 4-byte words of the entries of one of the TL_GROUP list lanes
+    const int eFirst = lane / wordsPerLane + TL_GROUP * ((lane % wordsPerLane) << 1);  // first entry of row word `lane`
     // The z interval of a column that the cutoff sphere reaches is bookkeeping, not the list criterion: it is computed
     // in single precision on coordinates relative to the home column / tile (float error ~1e-6) and widened by 0.2 % of
     // r^2 and 1e-3 of a cell, far more than that error and than the ulp by which an atom may sit outside its cell.
@@ -371,15 +393,18 @@ __global__ void __launch_bounds__(TL_THREADS_BUILD, 4)
     const int vBase = k0 - R;  // cell index of virtual cell 0
     const double zBase = tp.g.min[2] + double(vBase) * tp.g.dx[2];
     const bool clampZ = !tp.periodic[2];  // atoms beyond a non-periodic face are binned into the boundary cells
-    for (int hBase = 0; hBase < td.homeCount; hBase += blockDim.x / TL_GROUP)
+    for (int hBase = 0; hBase < td.homeCount; hBase += blockDim.x)
     {
-        const int h = hBase + group;
+        const int h = hBase + threadIdx.x;
         const bool active = h < td.homeCount;
         const int i = td.homeStart + h;
         const int selfSlot = active ? td.selfSlot0 + h : -1;
         const int safeSlot = active ? selfSlot : 0;
-        const double px = active ? sx_[3 * selfSlot] : 0.0, py = active ? sy_[3 * selfSlot] : 0.0, pz = active ? sz_[3 * selfSlot] : 0.0;
-        int count = 0;
+        // (a lane without a home sits at x = +inf: it accepts nothing)
+        const double px = active ? sx_[3 * safeSlot] : __longlong_as_double(0x7ff0000000000000LL);
+        const double py = sy_[3 * safeSlot], pz = sz_[3 * safeSlot];
+        unsigned rowAt = rowBegin;  // shared-memory byte address of the next entry of the lane's row
+        unsigned borderAcc = 0xffffffffu;
         // A column is scanned only over the z interval that the sphere around the home atom cuts out of it: with
         // (bx, by) the distance to the nearest face of the column, partners have |dz| <= sqrt(r^2 - bx^2 - by^2).
         // Atoms are in cell order along z, so the interval is one slot range.
@@ -388,11 +413,14 @@ __global__ void __launch_bounds__(TL_THREADS_BUILD, 4)
         const float dyl = fmaxf(fy, 0.f), dyh = fmaxf(fdy - fy, 0.f);
         const float bx2[3] = {dxl * dxl, 0.f, dxh * dxh}, by2[3] = {dyl * dyl, 0.f, dyh * dyh};
         const float zCells = static_cast<float>((pz - zBase) * tp.g.rdx[2]);  // z in cells, relative to virtual cell 0
+        // the nine ranges first (independent chains of float arithmetic, table look-ups and group reductions), then the
+        // nine sweeps
+        int rs0[9], rs1[9], rIters[9];
 #pragma unroll
         for (int r = 0; r < 9; ++r)
         {
             const float h2 = rPrune - (bx2[r / 3] + by2[r % 3]);
-            int s0 = 0, s1 = 0;
+            int s0 = 0x7fffffff, s1 = 0;
             if (active && h2 >= 0.f)
             {
                 const float hz = h2 * rsqrtf(h2 + 1e-30f) * frdz + 1e-3f;  // sqrt(h2) in cells
@@ -405,54 +433,114 @@ __global__ void __launch_bounds__(TL_THREADS_BUILD, 4)
                 }
                 const int vA = max(kA - vBase, 0);
                 const int vB = min(kB - vBase, nv - 2);
-                s0 = cellSlot[r][vA];
-                s1 = cellSlot[r][max(vB + 1, vA)];
+                const int a0 = cellSlot[r][vA], a1 = cellSlot[r][max(vB + 1, vA)];
+                if (a1 > a0) { s0 = a0; s1 = a1; }
             }
-            const int iters = __reduce_max_sync(0xffffffffu, (s1 - s0 + TL_GROUP - 1) / TL_GROUP);
-#pragma unroll 1
-            for (int it = 0, s = s0 + gl; it < iters; ++it, s += TL_GROUP)
+            // the TL_BUILD_GROUP lanes of a group sweep the union of their ranges in lock step: a load instruction of
+            // the warp then touches 32 / TL_BUILD_GROUP records instead of 32 (shared-memory bandwidth, 128 B per
+            // clock and SM, is what bounds a sweep over per-lane ranges: 24 B x 32 lanes per step)
+#pragma unroll
+            for (int o = 1; o < TL_BUILD_GROUP; o <<= 1)
             {
-                const bool inRange = s < s1;
-                const double* q = sx_ + 3 * (inRange ? s : safeSlot);  // always a valid record: no branch
+                s0 = min(s0, __shfl_xor_sync(0xffffffffu, s0, o));
+                s1 = max(s1, __shfl_xor_sync(0xffffffffu, s1, o));
+            }
+            if (s1 <= s0) { s0 = 0; s1 = 0; }
+            rs0[r] = s0;
+            rs1[r] = s1;
+            rIters[r] = __reduce_max_sync(0xffffffffu, s1 - s0);
+        }
+#pragma unroll
+        for (int r = 0; r < 9; ++r)
+        {
+            const int s0 = rs0[r], s1 = rs1[r], iters = rIters[r];
+            // Candidates are taken TL_BUILD_BATCH at a time: all loads and distances first, then the (predicated)
+            // stores, so that the dependent chains interleave (the compiler does not move shared-memory loads across the
+            // stores).  Steps past the end of a group's range read the records behind it (the staged set ends with
+            // TL_BUILD_BATCH spare records) and are rejected by their position in the range.
+            const int len = s1 - s0;
+            const int selfAt = (r == 4) ? selfSlot - s0 : -1;  // only the centre column holds the home atom itself
+            const double* q = sx_ + 3 * s0;
+            for (int it = 0; it < iters; it += TL_BUILD_BATCH, q += 3 * TL_BUILD_BATCH)
+            {
+                double d2[TL_BUILD_BATCH];
+                bool ok[TL_BUILD_BATCH];
+#pragma unroll
+                for (int u = 0; u < TL_BUILD_BATCH; ++u)
+                {
+                    const double qx = q[3 * u], qy = q[3 * u + 1], qz = q[3 * u + 2];
+                    d2[u] = distSqrExact(px - qx, py - qy, pz - qz);
+                    ok[u] = (it + u < len) && (d2[u] <= rsqr);
+                    if (r == 4) ok[u] = ok[u] && (it + u != selfAt);
+                    if (HALF) ok[u] = ok[u] && ((qx > px) || ((qx == px) && ((qy > py) || ((qy == py) && (qz > pz)))));
+                }
+#pragma unroll
+                for (int u = 0; u < TL_BUILD_BATCH; ++u)
+                {
+                    // smallest high word of d2 above that of (1 - 1e-9) r^2 (wrapping below it): integer pipe, one
+                    // instruction; candidates that are not accepted may raise the flag too, the filter below is exact
+                    borderAcc = min(borderAcc, unsigned(__double2hiint(d2[u]) - safeHi));
+                    if (ok[u] && rowAt < rowEnd) stSharedU16(rowAt, static_cast<uint16_t>(s0 + it + u));
+                    rowAt += ok[u] ? 2u : 0u;
+                }
+            }
+        }
+        const unsigned count = (rowAt - rowBegin) >> 1;
+        const bool border = borderAcc <= unsigned(__double2hiint(rsqr) - safeHi);
+        static_assert(TL_GROUP == 2, "verletBuildTiledKernel writes the row layout of two list lanes per home");
+        // Cabana prunes stencil cells by their distance to p; the cell holding n can only fail that test when d2 is
+        // within rounding of r^2 (the cell contains n): rows that accepted a partner with d2 > (1 - 1e-9) r^2 are
+        // filtered once more, in place (rare)
+        unsigned dropped = 0;
+        if (border)
+        {
+            const unsigned stored = min(count, unsigned(width));
+            unsigned kept = 0;
+            for (unsigned n = 0; n < stored; ++n)
+            {
+                const uint16_t s = sRow[n];
+                const double* q = sx_ + 3 * s;
                 const double qx = q[0], qy = q[1], qz = q[2];
                 const double d2 = distSqrExact(px - qx, py - qy, pz - qz);
-                bool ok = inRange && (s != selfSlot) && (d2 <= rsqr);
-                if (HALF) ok = ok && ((qx > px) || ((qx == px) && ((qy > py) || ((qy == py) && (qz > pz)))));
-                // Cabana prunes stencil cells by their distance to p; the cell holding n can only fail that test
-                // when d2 is within rounding of r^2 (the cell contains n), so the exact re-check is needed for
-                // d2 > (1 - 1e-9) r^2 only
-                if (ok && d2 > rsqrSafe) ok = cabanaCellReachable(cabanaGrid, px, py, pz, qx, qy, qz, rsqr);
-                const unsigned m = (__ballot_sync(0xffffffffu, ok) >> shiftInWarp) & GROUP_BITS;
-                if (ok)
-                {
-                    const int at = count + __popc(m & ((1u << gl) - 1u));
-                    if (at < width) sRow[tiledRowIndex(at, width)] = static_cast<uint16_t>(s);
-                }
-                count += __popc(m);
+                if (d2 > rsqrSafe && !cabanaCellReachable(cabanaGrid, px, py, pz, qx, qy, qz, rsqr)) continue;
+                sRow[kept] = s;
+                kept += 1;
             }
+            // rows longer than the buffer are rebuilt with a wider list anyway (the host grows width to the longest count)
+            dropped = stored - kept;
         }
-        // the group's row goes out as 16-byte words: word c belongs to lane c / (width / 64) and holds its entries
-        // 8 (c % (width / 64)) ...; words without a stored entry are skipped, entries past count are never read
+        const int finalCount = int(count - dropped);
+        if (active)
+        {
+            counts[i] = finalCount;
+            mx = max(mx, finalCount);
+            total += finalCount;
+        }
+        // The rows of the warp's 32 homes leave one after the other, a 4-byte word per lane, in the layout of the list
+        // (tiledRowIndex: the entries n, n + TL_GROUP, ... of one list lane are contiguous); words without a stored
+        // entry are skipped (entries past count are never read).  The stored count travels in the padding word of the row.
+        sRows[threadIdx.x * rowWords + (width >> 1)] = active ? unsigned(min(finalCount, width)) : 0u;
         __syncwarp();
         {
-            const int stored = min(count, width);
-            const int wordsPerLane = width / (8 * TL_GROUP);
-            uint4* dst = reinterpret_cast<uint4*>(enc + size_t(active ? i : 0) * width);
-            const uint4* src = reinterpret_cast<const uint4*>(sRow);
-            for (int c = gl; c < (width >> 3); c += TL_GROUP)
+            const int warpFirst = threadIdx.x - lane;
+            const uint32_t* cntp = sRows + warpFirst * rowWords + (width >> 1);
+            const uint16_t* sp = reinterpret_cast<const uint16_t*>(sRows + warpFirst * rowWords) + eFirst;
+            uint32_t* dp = reinterpret_cast<uint32_t*>(enc + size_t(td.homeStart + hBase + warpFirst) * width) + lane;
+#pragma unroll 4
+            for (int rr = 0; rr < 32; ++rr, cntp += rowWords, sp += 2 * rowWords, dp += (width >> 1))
             {
-                // word c holds the entries lane + TL_GROUP * (first ... first + 7) of that lane
-                const int lane = c / wordsPerLane, first = (c % wordsPerLane) << 3;
-                if (lane + TL_GROUP * first < stored) dst[c] = src[c];
+                const int cnt = int(*cntp);  // same word for all lanes
+                if (eFirst < cnt) *dp = uint32_t(sp[0]) | (uint32_t(sp[TL_GROUP]) << 16);
+                if (width > 64)  // rows wider than 64 entries: the words 32, 33, ... of the row
+                    for (int c = lane + 32; c < (width >> 1); c += 32)
+                    {
+                        // word c holds the entries e and e + TL_GROUP of list lane c / wordsPerLane
+                        const int e = c / wordsPerLane + TL_GROUP * ((c % wordsPerLane) << 1);
+                        if (e < cnt) dp[c - lane] = uint32_t(sp[e - eFirst]) | (uint32_t(sp[e - eFirst + TL_GROUP]) << 16);
+                    }
             }
         }
         __syncwarp();
-        if (active && gl == 0)
-        {
-            counts[i] = count;
-            mx = max(mx, count);
-            total += count;
-        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
@@ -460,7 +548,7 @@ __global__ void __launch_bounds__(TL_THREADS_BUILD, 4)
         mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         total += __shfl_xor_sync(0xffffffffu, total, o);
     }
-    if ((threadIdx.x & 31) == 0 && total > 0)
+    if (lane == 0 && total > 0)
     {
         atomicMax(stats, mx);
         atomicAdd(reinterpret_cast<unsigned long long*>(stats + 2), static_cast<unsigned long long>(total));
@@ -562,8 +650,34 @@ __device__ __forceinline__ int groupSumValue(int gl, int k)
 __device__ __forceinline__ int groupSumLane(int v) { return (TL_GROUP == 8) ? 2 * v : v / TL_VPL; }
 __device__ __forceinline__ int groupSumSlot(int v) { return v % TL_VPL; }
 
+// 16-byte words (eight entries each) of a lane's half of a list row that the LJ kernel loads a pass ahead
+#ifndef MRMD_LJT_WORDS
+#define MRMD_LJT_WORDS 1
+#endif
+constexpr int LJT_WORDS = (MRMD_LJT_WORDS * 8 * TL_GROUP <= 64) ? MRMD_LJT_WORDS : 64 / (8 * TL_GROUP);
+// ... and further words, also loaded a pass ahead, that a rolled loop walks (rows are at least 64 entries wide)
+#ifndef MRMD_LJT_MORE_WORDS
+#define MRMD_LJT_MORE_WORDS 3
+#endif
+constexpr int LJT_MORE = ((MRMD_LJT_WORDS + MRMD_LJT_MORE_WORDS) * 8 * TL_GROUP <= 64) ? MRMD_LJT_MORE_WORDS : 64 / (8 * TL_GROUP) - LJT_WORDS;
 // list steps (of TL_GROUP entries) whose slots are loaded into registers up front with 16-byte loads
 constexpr int LJT_PREFETCH = (64 / TL_GROUP < MRMD_LJT_PREFETCH) ? 64 / TL_GROUP : MRMD_LJT_PREFETCH;  // multiple of 8
+
+// row length and list words of the home that lane (group, gl) works on in the pass starting at home hBase
+__device__ __forceinline__ void prefetchListRows(const TileDesc& td, const int32_t* __restrict__ counts,
+                                                 const uint16_t* __restrict__ enc, int width, int hBase, int group, int gl,
+                                                 int& count, uint4 (&words)[LJT_WORDS])
+{
+    const int h = hBase + group;
+    const bool active = h < td.homeCount;
+    const size_t i = size_t(td.homeStart + (active ? h : 0));
+    count = active ? counts[i] : 0;
+    // lane gl owns the entries gl, gl + TL_GROUP, ... of the row; the row layout keeps them contiguous
+    // (tiledRowIndex), so they arrive as 16-byte words
+    const uint4* row = reinterpret_cast<const uint4*>(enc + i * width + gl * (width / TL_GROUP));
+#pragma unroll
+    for (int k = 0; k < LJT_WORDS; ++k) words[k] = row[k];
+}
 
 // one pair of LennardJones::apply_if's inner loop (LennardJones.hpp:176-196) against a staged partner
 template <bool SINGLE_TYPE, bool ENERGY>
@@ -608,8 +722,11 @@ __device__ __forceinline__ void ljPair(const double* sx_, const double* sy_, con
 // LennardJones::apply over the tiled list (full list: row owners only).  ACCUMULATE = false stores the force
 // (the driver then skips the force reset); true adds like the reference.  ENERGY = false skips the energy /
 // virial accumulation (the driver asks for them on the last step of a run only).
+#ifndef MRMD_LJT_MINBLOCKS
+#define MRMD_LJT_MINBLOCKS 6
+#endif
 template <bool SINGLE_TYPE, bool ACCUMULATE, bool ENERGY>
-__global__ void __launch_bounds__(TL_THREADS_FORCE)
+__global__ void __launch_bounds__(TL_THREADS_FORCE, MRMD_LJT_MINBLOCKS)
     ljForceTiledKernel(TileParams tp, AtomsView a, const int* __restrict__ desc, const int32_t* __restrict__ counts,
                        const uint16_t* __restrict__ enc, int width, LJTable table, double rcSqr, int64_t numTypesQuirk,
                        double* partials, double* result, unsigned int* ticket, const int* __restrict__ stop)
@@ -622,14 +739,21 @@ __global__ void __launch_bounds__(TL_THREADS_FORCE)
     double* sy_ = sx_ + 1;  // interleaved {x, y, z} records: one address per slot, conflict-free for consecutive slots
     double* sz_ = sx_ + 2;
     unsigned char* sType = reinterpret_cast<unsigned char*>(sx_ + 3 * tp.cap);
-    stageTile<false, !SINGLE_TYPE>(tp, td, a.pos, sx_, sy_, sz_, nullptr, sType, blockIdx.x);
 
     // warp-uniform control flow, see verletBuildTiledKernel
     const int group = threadIdx.x / TL_GROUP, gl = threadIdx.x % TL_GROUP;
     double energy = 0.0, virial = 0.0;
     int pairs = 0;
     const LJType t0 = table.t[0];
-    for (int hBase = 0; hBase < td.homeCount; hBase += blockDim.x / TL_GROUP)
+    // The row length and the list words of a pass are loaded one pass ahead (those of the first pass while the tile is
+    // staged): a dependent global load at the head of every pass and one per entry behind the prefetched words were
+    // 11 % of the kernel's stall samples (profiles/r02_lj_force_ncu.txt).
+    const int homesPerPass = blockDim.x / TL_GROUP;
+    int countNext = 0;
+    uint4 wordsNext[LJT_WORDS];
+    prefetchListRows(td, counts, enc, width, 0, group, gl, countNext, wordsNext);
+    stageTile<false, !SINGLE_TYPE>(tp, td, a.pos, sx_, sy_, sz_, nullptr, sType, blockIdx.x);
+    for (int hBase = 0; hBase < td.homeCount; hBase += homesPerPass)
     {
         const int h = hBase + group;
         const bool active = h < td.homeCount;
@@ -638,35 +762,68 @@ __global__ void __launch_bounds__(TL_THREADS_FORCE)
         const double xi = sx_[3 * selfSlot], yi = sy_[3 * selfSlot], zi = sz_[3 * selfSlot];
         const int typeI = SINGLE_TYPE ? 0 : sType[selfSlot];
         double fx = 0.0, fy = 0.0, fz = 0.0;
-        const int numNeighbors = active ? min(counts[i], width) : 0;
-        // lane gl owns the entries gl, gl + 8, ... of the row; the row layout keeps them contiguous (tiledRowIndex), so
-        // the first eight arrive with one 16-byte load per lane (128 contiguous bytes per group)
-        const uint16_t* mineRow = enc + size_t(active ? i : 0) * width + gl * (width / TL_GROUP);
+        const int numNeighbors = min(countNext, width);
+        unsigned words[4 * (LJT_WORDS + LJT_MORE)];
+#pragma unroll
+        for (int k = 0; k < LJT_WORDS; ++k)
+        {
+            words[4 * k] = wordsNext[k].x;
+            words[4 * k + 1] = wordsNext[k].y;
+            words[4 * k + 2] = wordsNext[k].z;
+            words[4 * k + 3] = wordsNext[k].w;
+        }
+        // the words behind the unrolled steps are loaded now and used after them
+        {
+            const uint4* row = reinterpret_cast<const uint4*>(enc + size_t(active ? i : 0) * width + gl * (width / TL_GROUP));
+#pragma unroll
+            for (int k = LJT_WORDS; k < LJT_WORDS + LJT_MORE; ++k)
+            {
+                const uint4 w = row[k];
+                words[4 * k] = w.x;
+                words[4 * k + 1] = w.y;
+                words[4 * k + 2] = w.z;
+                words[4 * k + 3] = w.w;
+            }
+        }
+        if (hBase + homesPerPass < td.homeCount)  // block uniform
+            prefetchListRows(td, counts, enc, width, hBase + homesPerPass, group, gl, countNext, wordsNext);
         const int mine = (numNeighbors - gl + TL_GROUP - 1) / TL_GROUP;  // entries of this lane
         const int iters = __reduce_max_sync(0xffffffffu, (numNeighbors + TL_GROUP - 1) / TL_GROUP);
-        unsigned words[LJT_PREFETCH / 2];
 #pragma unroll
-        for (int k = 0; k < LJT_PREFETCH / 8; ++k)
-        {
-            const uint4 head = reinterpret_cast<const uint4*>(mineRow)[k];
-            words[4 * k] = head.x;
-            words[4 * k + 1] = head.y;
-            words[4 * k + 2] = head.z;
-            words[4 * k + 3] = head.w;
-        }
-#pragma unroll
-        for (int it = 0; it < LJT_PREFETCH; ++it)
+        for (int it = 0; it < 8 * LJT_WORDS; ++it)
         {
             const int slot = (words[it >> 1] >> (16 * (it & 1))) & 0xffffu;
             if (it < iters)  // warp uniform
                 ljPair<SINGLE_TYPE, ENERGY>(sx_, sy_, sz_, sType, slot, it < mine, xi, yi, zi, typeI, t0, table, numTypesQuirk,
                                             rcSqr, fx, fy, fz, energy, virial, pairs);
         }
-        for (int it = LJT_PREFETCH; it < iters; ++it)
+        // the entries behind the unrolled steps: a rolled loop that takes two entries per trip from the lowest of the
+        // remaining prefetched words and moves the others down (registers cannot be indexed)
+        if (LJT_MORE > 0)
         {
-            if (it < mine)
-                ljPair<SINGLE_TYPE, ENERGY>(sx_, sy_, sz_, sType, mineRow[it], true, xi, yi, zi, typeI, t0, table,
+            const int more = min(iters, 8 * (LJT_WORDS + LJT_MORE));
+#pragma unroll 1
+            for (int it = 8 * LJT_WORDS; it < more; it += 2)
+            {
+                const unsigned w = words[4 * LJT_WORDS];
+#pragma unroll
+                for (int k = 4 * LJT_WORDS; k + 1 < 4 * (LJT_WORDS + LJT_MORE); ++k) words[k] = words[k + 1];
+                ljPair<SINGLE_TYPE, ENERGY>(sx_, sy_, sz_, sType, w & 0xffffu, it < mine, xi, yi, zi, typeI, t0, table,
                                             numTypesQuirk, rcSqr, fx, fy, fz, energy, virial, pairs);
+                if (it + 1 < iters)
+                    ljPair<SINGLE_TYPE, ENERGY>(sx_, sy_, sz_, sType, w >> 16, it + 1 < mine, xi, yi, zi, typeI, t0, table,
+                                                numTypesQuirk, rcSqr, fx, fy, fz, energy, virial, pairs);
+            }
+        }
+        if (iters > 8 * (LJT_WORDS + LJT_MORE))  // rows longer than the prefetched words (lists wider than 64 entries)
+        {
+            const uint16_t* mineRow = enc + size_t(active ? i : 0) * width + gl * (width / TL_GROUP);
+            for (int it = 8 * (LJT_WORDS + LJT_MORE); it < iters; ++it)
+            {
+                if (it < mine)
+                    ljPair<SINGLE_TYPE, ENERGY>(sx_, sy_, sz_, sType, mineRow[it], true, xi, yi, zi, typeI, t0, table,
+                                                numTypesQuirk, rcSqr, fx, fy, fz, energy, virial, pairs);
+            }
         }
         // three lanes of the group end up with the x / y / z total and store it
         double f[TL_VPL];
@@ -684,7 +841,8 @@ __global__ void __launch_bounds__(TL_THREADS_FORCE)
         }
     }
     // every pair is visited from both sides
-    gridReduce3<TL_THREADS_FORCE>(0.5 * energy, 0.5 * virial, 0.5 * double(pairs), partials, result, ticket);
+    if (ENERGY) gridReduce3<TL_THREADS_FORCE>(0.5 * energy, 0.5 * virial, 0.5 * double(pairs), partials, result, ticket);
+    else gridAddExact<TL_THREADS_FORCE>(0.5 * double(pairs), 0.0, result + 2, nullptr);
 }
 
 // ---- AdResS on tiles ----------------------------------------------------------------------------------------
@@ -1125,7 +1283,7 @@ static int makeTileParams(const mrmd_b200_atoms* a, const mrmd_b200_subdomain* s
     return 0;
 }
 
-constexpr int TL_SMEM_PER_SLOT_BUILD = 24;  // x, y, z
+constexpr int TL_SMEM_PER_SLOT_BUILD = 24;  // x, y, z (the builder adds TL_BUILD_BATCH spare records)
 constexpr int TL_SMEM_PER_SLOT_FORCE = 25;  // x, y, z + type byte
 constexpr int TL_SMEM_BUDGET = 48 * 1024;   // preferred budget of a tile's staged positions (several tiles per SM)
 constexpr int TL_SMEM_MAX = 200 * 1024;
@@ -1384,9 +1542,9 @@ int verletBuildTiled(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, const mrmd_b
     int64_t width = (std::max<int64_t>(maxNeigh, 1) + 63) & ~int64_t(63);  // tiledRowIndex: eight lanes x 16-byte words
     if (v->width > width && v->enc.bytes >= size_t(v->width) * std::max<int64_t>(n, 1) * 2) width = v->width;
     MB_REQUIRE(width <= 1024, "verlet_build_periodic: more than 1024 neighbours per atom");
-    // shared memory of the builder: positions + one staged row per group of TL_GROUP lanes (width x 2 bytes each)
+    // shared memory of the builder: positions + one row buffer per lane (width x 2 bytes + one padding word each)
     auto buildSmem = [&](int slots, int64_t w)
-    { return size_t(slots) * TL_SMEM_PER_SLOT_BUILD + 16 + size_t(TL_THREADS_BUILD / TL_GROUP) * size_t(w) * 2; };
+    { return size_t(slots + TL_BUILD_BATCH) * TL_SMEM_PER_SLOT_BUILD + 16 + size_t(TL_THREADS_BUILD) * size_t(w / 2 + 1) * 4; };
 
     // Tile geometry (CH cells per tile, staged-slot capacity).  The first build measures the tiles (one host round
     // trip); later builds on the same grid re-use CH with the largest tile of the previous build plus head room as the

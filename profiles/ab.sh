@@ -17,5 +17,5 @@ except Exception as e:
 PY
   MRMD_PROFILE_RANGE=1 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
      --log-file gpurun_out/ll_${tag}_$v.csv python bench.py --only-headline --no-e2e --no-cpu-baseline --steps 40 --warmup 5 ${AB_ARGS} > /dev/null 2> gpurun_out/ll_${tag}_$v.err
-  python profiles/launch_summary.py gpurun_out/ll_${tag}_$v.csv 40 | head -8
+  python profiles/launch_summary.py gpurun_out/ll_${tag}_$v.csv 40 | head -6 || true
 done
