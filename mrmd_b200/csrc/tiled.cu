@@ -925,6 +925,10 @@ __device__ __forceinline__ void adressPair(const double* rec, const unsigned cha
     if (hyA) vsum += 0.5 * e;  // V_ij of the drift force and of the compensation sampling, :160-200
 }
 
+#ifndef MRMD_ADT_MORE_WORDS
+#define MRMD_ADT_MORE_WORDS 1
+#endif
+constexpr int ADT_MORE = (MRMD_ADT_MORE_WORDS < LJT_MORE) ? MRMD_ADT_MORE_WORDS : LJT_MORE;  // rolled-loop words of the AdResS kernel
 template <bool SINGLE_TYPE, bool SAMPLING, bool ENERGY>
 __global__ void __launch_bounds__(TL_THREADS_FORCE, 6)
     adressForceTiledKernel(TileParams tp, AtomsView a, const int* __restrict__ desc, const int32_t* __restrict__ counts,
@@ -946,13 +950,18 @@ __global__ void __launch_bounds__(TL_THREADS_FORCE, 6)
         loadTileDesc(desc, td, tile);
         double* rec = sTile;
         unsigned char* sType = reinterpret_cast<unsigned char*>(rec + 4 * tp.cap);
+        const int group = threadIdx.x / TL_GROUP, gl = threadIdx.x % TL_GROUP;
+        // row length and first list words a pass ahead, as in ljForceTiledKernel
+        const int homesPerPass = blockDim.x / TL_GROUP;
+        int countNext = 0;
+        uint4 wordsNext[LJT_WORDS];
+        prefetchListRows(td, counts, enc, width, 0, group, gl, countNext, wordsNext);
         stageTileAdress<!SINGLE_TYPE>(tp, td, a.pos, w, rec, sType, tile);
 
-        const int group = threadIdx.x / TL_GROUP, gl = threadIdx.x % TL_GROUP;
         const LJType t0 = table.t[0];
         const int64_t T = numTypes;
         const double inverseBinSize = 1.0 / ((1.0 - 0.0) / double(TL_COMPENSATION_BINS));
-        for (int hBase = 0; hBase < td.homeCount; hBase += blockDim.x / TL_GROUP)
+        for (int hBase = 0; hBase < td.homeCount; hBase += homesPerPass)
         {
             const int h = hBase + group;
             const bool active = h < td.homeCount;
@@ -964,30 +973,57 @@ __global__ void __launch_bounds__(TL_THREADS_FORCE, 6)
             weightEval(w, xi, yi, zi, lambda, modA, gx, gy, gz);
             const bool hyA = inHY(modA), cgA = inCG(modA);
             double fx = 0.0, fy = 0.0, fz = 0.0, vsum = 0.0;
-            const int numNeighbors = active ? min(counts[i], width) : 0;
-            // row layout and per-lane 16-byte head load as in ljForceTiledKernel
+            const int numNeighbors = min(countNext, width);
+            unsigned words[4 * (LJT_WORDS + ADT_MORE)];
+#pragma unroll
+            for (int k = 0; k < LJT_WORDS; ++k)
+            {
+                words[4 * k] = wordsNext[k].x;
+                words[4 * k + 1] = wordsNext[k].y;
+                words[4 * k + 2] = wordsNext[k].z;
+                words[4 * k + 3] = wordsNext[k].w;
+            }
             const uint16_t* mineRow = enc + size_t(active ? i : 0) * width + gl * (width / TL_GROUP);
+            // the words behind the unrolled steps are loaded now and used after them
+#pragma unroll
+            for (int k = LJT_WORDS; k < LJT_WORDS + ADT_MORE; ++k)
+            {
+                const uint4 wk = reinterpret_cast<const uint4*>(mineRow)[k];
+                words[4 * k] = wk.x;
+                words[4 * k + 1] = wk.y;
+                words[4 * k + 2] = wk.z;
+                words[4 * k + 3] = wk.w;
+            }
+            if (hBase + homesPerPass < td.homeCount)  // block uniform
+                prefetchListRows(td, counts, enc, width, hBase + homesPerPass, group, gl, countNext, wordsNext);
             const int mine = (numNeighbors - gl + TL_GROUP - 1) / TL_GROUP;
             const int iters = __reduce_max_sync(0xffffffffu, (numNeighbors + TL_GROUP - 1) / TL_GROUP);
-            unsigned words[LJT_PREFETCH / 2];
 #pragma unroll
-            for (int k = 0; k < LJT_PREFETCH / 8; ++k)
-            {
-                const uint4 head = reinterpret_cast<const uint4*>(mineRow)[k];
-                words[4 * k] = head.x;
-                words[4 * k + 1] = head.y;
-                words[4 * k + 2] = head.z;
-                words[4 * k + 3] = head.w;
-            }
-#pragma unroll
-            for (int it = 0; it < LJT_PREFETCH; ++it)
+            for (int it = 0; it < 8 * LJT_WORDS; ++it)
             {
                 const int slot = (words[it >> 1] >> (16 * (it & 1))) & 0xffffu;
                 if (it < mine)
                     adressPair<SINGLE_TYPE, ENERGY>(rec, sType, slot, xi, yi, zi, typeI, modA, cgA, hyA, t0, table, T, rcSqr, fx,
                                                     fy, fz, energy, vsum, pairs, activePairs);
             }
-            for (int it = LJT_PREFETCH; it < iters; ++it)
+            if (ADT_MORE > 0)
+            {
+                const int more = min(iters, 8 * (LJT_WORDS + ADT_MORE));
+#pragma unroll 1
+                for (int it = 8 * LJT_WORDS; it < more; it += 2)
+                {
+                    const unsigned wq = words[4 * LJT_WORDS];
+#pragma unroll
+                    for (int k = 4 * LJT_WORDS; k + 1 < 4 * (LJT_WORDS + ADT_MORE); ++k) words[k] = words[k + 1];
+                    if (it < mine)
+                        adressPair<SINGLE_TYPE, ENERGY>(rec, sType, wq & 0xffffu, xi, yi, zi, typeI, modA, cgA, hyA, t0, table, T,
+                                                        rcSqr, fx, fy, fz, energy, vsum, pairs, activePairs);
+                    if (it + 1 < mine)
+                        adressPair<SINGLE_TYPE, ENERGY>(rec, sType, wq >> 16, xi, yi, zi, typeI, modA, cgA, hyA, t0, table, T,
+                                                        rcSqr, fx, fy, fz, energy, vsum, pairs, activePairs);
+                }
+            }
+            for (int it = 8 * (LJT_WORDS + ADT_MORE); it < iters; ++it)  // lists wider than 64 entries
             {
                 if (it < mine)
                     adressPair<SINGLE_TYPE, ENERGY>(rec, sType, mineRow[it], xi, yi, zi, typeI, modA, cgA, hyA, t0, table, T, rcSqr,
@@ -1034,7 +1070,8 @@ __global__ void __launch_bounds__(TL_THREADS_FORCE, 6)
         }
     }
     // every pair is visited from both sides
-    gridReduce3<TL_THREADS_FORCE>(0.5 * energy, 0.5 * pairs, 0.5 * activePairs, partials, result, ticket);
+    if (ENERGY) gridReduce3<TL_THREADS_FORCE>(0.5 * energy, 0.5 * pairs, 0.5 * activePairs, partials, result, ticket);
+    else gridAddExact<TL_THREADS_FORCE>(0.5 * pairs, 0.5 * activePairs, result + 1, result + 2);
 }
 
 // ---- AdResS on tiles for molecules of NA atoms (the tetramers of BASELINE.json configs[3]) --------------------------
