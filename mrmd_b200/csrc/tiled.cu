@@ -41,18 +41,19 @@ namespace mrmd_b200
 #ifndef MRMD_TL_THREADS_FORCE
 #define MRMD_TL_THREADS_FORCE 128
 #endif
-#ifndef MRMD_LJT_PREFETCH
-#define MRMD_LJT_PREFETCH 16
-#endif
 constexpr int TL_THREADS_BUILD = MRMD_TL_THREADS_BUILD;  // neighbour build / decode
 constexpr int TL_THREADS_FORCE = MRMD_TL_THREADS_FORCE;  // force kernels (measured: 256 -> 194 us, 128 -> 184 us)
 constexpr int TL_GROUP = 2;                       // lanes per home atom
 #ifndef MRMD_TL_BUILD_BATCH
 #define MRMD_TL_BUILD_BATCH 4
 #endif
+#ifndef MRMD_TL_STAGE_UNROLL
+#define MRMD_TL_STAGE_UNROLL 4
+#endif
+constexpr int TL_STAGE_UNROLL = MRMD_TL_STAGE_UNROLL;  // loads a lane keeps in flight while staging a tile
 constexpr int TL_BUILD_BATCH = MRMD_TL_BUILD_BATCH;  // candidates a lane of the neighbour build tests per step
 #ifndef MRMD_TL_BUILD_GROUP
-#define MRMD_TL_BUILD_GROUP 8
+#define MRMD_TL_BUILD_GROUP 4
 #endif
 constexpr int TL_BUILD_GROUP = MRMD_TL_BUILD_GROUP;  // consecutive homes (lanes) that sweep the same candidates
 constexpr int TL_PIECES = 27;                     // 9 columns x {low z-wrap, main, high z-wrap}
@@ -210,27 +211,38 @@ __device__ __forceinline__ void stageTile(const TileParams& tp, const TileDesc& 
         // x + (+-L) is the ghost layer's single addition; x + 0.0 leaves x bit-identical
         const double shx = double(ix) * tp.L[0], shy = double(iy) * tp.L[1], shz = double(iz) * tp.L[2];
         const int start = td.pieceStart[p], slot0 = td.pieceSlot[p];
-        for (int k = lane; k < len; k += 32)
+        // TL_STAGE_UNROLL loads in flight per lane: the pieces of a warp are walked one after the other, and one load per
+        // trip left the staging phase waiting out a full memory latency per 32 atoms
+        for (int k0 = lane; k0 < len; k0 += 32 * TL_STAGE_UNROLL)
         {
-            const double4 raw = ld4nc(pos + start + k);
-            double qx = raw.x + shx;
-            if (BUILD)
+            double4 raw[TL_STAGE_UNROLL];
+#pragma unroll
+            for (int u = 0; u < TL_STAGE_UNROLL; ++u)
+                if (k0 + 32 * u < len) raw[u] = ld4nc(pos + start + k0 + 32 * u);
+#pragma unroll
+            for (int u = 0; u < TL_STAGE_UNROLL; ++u)
             {
-                // an atom that the reference would not have turned into this ghost image is parked at
-                // x = +inf: it fails every distance test without a separate flag
-                bool ok = true;
-                if (ix > 0) ok = ok && (raw.x < tp.minInner[0]);
-                if (ix < 0) ok = ok && (raw.x >= tp.maxInner[0]);
-                if (iy > 0) ok = ok && (raw.y < tp.minInner[1]);
-                if (iy < 0) ok = ok && (raw.y >= tp.maxInner[1]);
-                if (iz > 0) ok = ok && (raw.z < tp.minInner[2]);
-                if (iz < 0) ok = ok && (raw.z >= tp.maxInner[2]);
-                if (!ok) qx = __longlong_as_double(0x7ff0000000000000LL);
+                const int k = k0 + 32 * u;
+                if (k >= len) break;
+                double qx = raw[u].x + shx;
+                if (BUILD)
+                {
+                    // an atom that the reference would not have turned into this ghost image is parked at
+                    // x = +inf: it fails every distance test without a separate flag
+                    bool ok = true;
+                    if (ix > 0) ok = ok && (raw[u].x < tp.minInner[0]);
+                    if (ix < 0) ok = ok && (raw[u].x >= tp.maxInner[0]);
+                    if (iy > 0) ok = ok && (raw[u].y < tp.minInner[1]);
+                    if (iy < 0) ok = ok && (raw[u].y >= tp.maxInner[1]);
+                    if (iz > 0) ok = ok && (raw[u].z < tp.minInner[2]);
+                    if (iz < 0) ok = ok && (raw[u].z >= tp.maxInner[2]);
+                    if (!ok) qx = __longlong_as_double(0x7ff0000000000000LL);
+                }
+                sx_[3 * (slot0 + k)] = qx;
+                sy_[3 * (slot0 + k)] = raw[u].y + shy;
+                sz_[3 * (slot0 + k)] = raw[u].z + shz;
+                if (TYPES) sType[slot0 + k] = static_cast<unsigned char>(typeOf(raw[u]));
             }
-            sx_[3 * (slot0 + k)] = qx;
-            sy_[3 * (slot0 + k)] = raw.y + shy;
-            sz_[3 * (slot0 + k)] = raw.z + shz;
-            if (TYPES) sType[slot0 + k] = static_cast<unsigned char>(typeOf(raw));
         }
     }
     __syncthreads();
@@ -344,27 +356,54 @@ __global__ void __launch_bounds__(TL_THREADS_BUILD, 4)
     const int nk = k1 - k0 + 1;
     const int R = tp.R;
     const int nv = nk + 2 * R + 1;  // virtual cells k0-R .. k1+R plus the end sentinel
-    for (int e = threadIdx.x; e < 9 * nv; e += blockDim.x)
+    // a warp takes every (blockDim.x / 32)-th column, its lanes the virtual cells; the loads of a thread are independent
+    // and issued together (no division, one memory latency)
     {
-        const int r = e / nv, v = e % nv;
-        const int kv = k0 - R + v;
-        // virtual cells below 0 / beyond nz-1 live in the low / high z-wrap piece (cells nz+kv / kv-nz of the column)
-        const int piece = r * 3 + ((kv < 0) ? 0 : ((kv >= nz) ? 2 : 1));
-        int slot;
-        if (v == nv - 1) slot = td.pieceSlot[r * 3 + 3];
-        else if (td.pieceLen[piece] == 0) slot = td.pieceSlot[piece];
-        else
+        constexpr int V_TRIPS = (TL_CELLS + 31) / 32;
+        const int warp = threadIdx.x >> 5, lane32 = threadIdx.x & 31, warps = blockDim.x >> 5;
+        for (int r0 = warp; r0 < 9; r0 += 3 * warps)
         {
-            int ii = ci + r / 3 - 1, jj = cj + r % 3 - 1;
-            if (!tp.haloX)
+            int slotOf[3][V_TRIPS];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
             {
-                if (ii < 0) ii += tp.g.n[0]; else if (ii >= tp.g.n[0]) ii -= tp.g.n[0];
+                const int r = r0 + c * warps;
+                int ii = ci + r / 3 - 1, jj = cj + r % 3 - 1;
+                if (!tp.haloX)
+                {
+                    if (ii < 0) ii += tp.g.n[0]; else if (ii >= tp.g.n[0]) ii -= tp.g.n[0];
+                }
+                if (jj < 0) jj += tp.g.n[1]; else if (jj >= tp.g.n[1]) jj -= tp.g.n[1];
+#pragma unroll
+                for (int t = 0; t < V_TRIPS; ++t)
+                {
+                    const int v = lane32 + 32 * t;
+                    const int kv = k0 - R + v;
+                    // virtual cells below 0 / beyond nz-1 live in the low / high z-wrap piece (cells nz+kv / kv-nz of the column)
+                    const int piece = r * 3 + ((kv < 0) ? 0 : ((kv >= nz) ? 2 : 1));
+                    int slot = 0;
+                    if (r < 9 && v < nv)
+                    {
+                        if (v == nv - 1) slot = td.pieceSlot[r * 3 + 3];
+                        else if (td.pieceLen[piece] == 0) slot = td.pieceSlot[piece];
+                        else
+                        {
+                            const int kk = (kv < 0) ? kv + nz : ((kv >= nz) ? kv - nz : kv);
+                            slot = td.pieceSlot[piece] + (cellLo[extCell(tp, ii, jj, kk)] - td.pieceStart[piece]);
+                        }
+                    }
+                    slotOf[c][t] = slot;
+                }
             }
-            if (jj < 0) jj += tp.g.n[1]; else if (jj >= tp.g.n[1]) jj -= tp.g.n[1];
-            const int kk = (kv < 0) ? kv + nz : ((kv >= nz) ? kv - nz : kv);
-            slot = td.pieceSlot[piece] + (cellLo[extCell(tp, ii, jj, kk)] - td.pieceStart[piece]);
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int t = 0; t < V_TRIPS; ++t)
+                {
+                    const int r = r0 + c * warps, v = lane32 + 32 * t;
+                    if (r < 9 && v < nv) cellSlot[r][v] = slotOf[c][t];
+                }
         }
-        cellSlot[r][v] = slot;
     }
     stageTile<true, false>(tp, td, pos, sx_, sy_, sz_, nullptr, nullptr, tile);
 
@@ -383,13 +422,7 @@ __global__ void __launch_bounds__(TL_THREADS_BUILD, 4)
     const int safeHi = __double2hiint(rsqrSafe);  // d2 > 0: the high words order like the values
     const int wordsPerLane = halfWidth >> 1;  // 4-byte words of the entries of one of the TL_GROUP list lanes
     const int eFirst = lane / wordsPerLane + TL_GROUP * ((lane % wordsPerLane) << 1);  // first entry of row word `lane`
-    // The z interval of a column that the cutoff sphere reaches is bookkeeping, not the list criterion: it is computed
-    // in single precision on coordinates relative to the home column / tile (float error ~1e-6) and widened by 0.2 % of
-    // r^2 and 1e-3 of a cell, far more than that error and than the ulp by which an atom may sit outside its cell.
-    const float rPrune = static_cast<float>(rsqr) * 1.002f;
-    const double xlo = tp.g.min[0] + double(ci) * tp.g.dx[0], ylo = tp.g.min[1] + double(cj) * tp.g.dx[1];
-    const float fdx = static_cast<float>(tp.g.dx[0]), fdy = static_cast<float>(tp.g.dx[1]);
-    const float frdz = static_cast<float>(tp.g.rdx[2]);
+    const float hzMax = sqrtf(static_cast<float>(rsqr)) * 1.001f * static_cast<float>(tp.g.rdx[2]) + 1e-3f;  // list radius in cells
     const int vBase = k0 - R;  // cell index of virtual cell 0
     const double zBase = tp.g.min[2] + double(vBase) * tp.g.dx[2];
     const bool clampZ = !tp.periodic[2];  // atoms beyond a non-periodic face are binned into the boundary cells
@@ -405,47 +438,47 @@ __global__ void __launch_bounds__(TL_THREADS_BUILD, 4)
         const double py = sy_[3 * safeSlot], pz = sz_[3 * safeSlot];
         unsigned rowAt = rowBegin;  // shared-memory byte address of the next entry of the lane's row
         unsigned borderAcc = 0xffffffffu;
-        // A column is scanned only over the z interval that the sphere around the home atom cuts out of it: with
-        // (bx, by) the distance to the nearest face of the column, partners have |dz| <= sqrt(r^2 - bx^2 - by^2).
-        // Atoms are in cell order along z, so the interval is one slot range.
-        const float fx = static_cast<float>(px - xlo), fy = static_cast<float>(py - ylo);
-        const float dxl = fmaxf(fx, 0.f), dxh = fmaxf(fdx - fx, 0.f);
-        const float dyl = fmaxf(fy, 0.f), dyh = fmaxf(fdy - fy, 0.f);
-        const float bx2[3] = {dxl * dxl, 0.f, dxh * dxh}, by2[3] = {dyl * dyl, 0.f, dyh * dyh};
+        // The TL_BUILD_GROUP lanes of a group (consecutive homes of the column, i.e. neighbours in z) sweep the same
+        // candidates in lock step, so that a load instruction of the warp touches 32 / TL_BUILD_GROUP records instead of
+        // 32 (shared-memory bandwidth, 128 B per clock and SM, is what bounds a sweep over per-lane ranges: 24 B x 32
+        // lanes per step).  In every column the group scans the cells within the list radius of its lowest and highest
+        // home along z.  Atoms are in cell order along z, so that is one slot range per column.  (Cutting the range of a
+        // column down by the homes' distance to it gains nothing for a group: one of eight homes is always close to the
+        // column's face; the nine per-lane range computations it takes were 20 % of the kernel's stall samples.)  This
+        // is bookkeeping, not the list criterion: single precision on coordinates relative to the tile (float error
+        // ~1e-6), widened by 0.1 % of r and 1e-3 of a cell, far more than that error and than the ulp by which an atom
+        // may sit outside its cell.
         const float zCells = static_cast<float>((pz - zBase) * tp.g.rdx[2]);  // z in cells, relative to virtual cell 0
-        // the nine ranges first (independent chains of float arithmetic, table look-ups and group reductions), then the
-        // nine sweeps
+        float zLo = active ? zCells : 3.0e38f, zHi = active ? zCells : -3.0e38f;
+#pragma unroll
+        for (int o = 1; o < TL_BUILD_GROUP; o <<= 1)
+        {
+            zLo = fminf(zLo, __shfl_xor_sync(0xffffffffu, zLo, o));
+            zHi = fmaxf(zHi, __shfl_xor_sync(0xffffffffu, zHi, o));
+        }
+        int vA = 0, vB = -1;
+        if (zHi >= zLo)  // a group with a home
+        {
+            int kA = static_cast<int>(floorf(zLo - hzMax)) + vBase;
+            int kB = static_cast<int>(floorf(zHi + hzMax)) + vBase;
+            if (clampZ)
+            {
+                kA = max(0, min(kA, nz - 1));
+                kB = max(0, min(kB, nz - 1));
+            }
+            vA = max(kA - vBase, 0);
+            vB = min(kB - vBase, nv - 2);
+        }
         int rs0[9], rs1[9], rIters[9];
 #pragma unroll
         for (int r = 0; r < 9; ++r)
         {
-            const float h2 = rPrune - (bx2[r / 3] + by2[r % 3]);
-            int s0 = 0x7fffffff, s1 = 0;
-            if (active && h2 >= 0.f)
+            int s0 = 0, s1 = 0;
+            if (vB >= vA)
             {
-                const float hz = h2 * rsqrtf(h2 + 1e-30f) * frdz + 1e-3f;  // sqrt(h2) in cells
-                int kA = static_cast<int>(floorf(zCells - hz)) + vBase;
-                int kB = static_cast<int>(floorf(zCells + hz)) + vBase;
-                if (clampZ)
-                {
-                    kA = max(0, min(kA, nz - 1));
-                    kB = max(0, min(kB, nz - 1));
-                }
-                const int vA = max(kA - vBase, 0);
-                const int vB = min(kB - vBase, nv - 2);
-                const int a0 = cellSlot[r][vA], a1 = cellSlot[r][max(vB + 1, vA)];
-                if (a1 > a0) { s0 = a0; s1 = a1; }
+                s0 = cellSlot[r][vA];
+                s1 = cellSlot[r][vB + 1];
             }
-            // the TL_BUILD_GROUP lanes of a group sweep the union of their ranges in lock step: a load instruction of
-            // the warp then touches 32 / TL_BUILD_GROUP records instead of 32 (shared-memory bandwidth, 128 B per
-            // clock and SM, is what bounds a sweep over per-lane ranges: 24 B x 32 lanes per step)
-#pragma unroll
-            for (int o = 1; o < TL_BUILD_GROUP; o <<= 1)
-            {
-                s0 = min(s0, __shfl_xor_sync(0xffffffffu, s0, o));
-                s1 = max(s1, __shfl_xor_sync(0xffffffffu, s1, o));
-            }
-            if (s1 <= s0) { s0 = 0; s1 = 0; }
             rs0[r] = s0;
             rs1[r] = s1;
             rIters[r] = __reduce_max_sync(0xffffffffu, s1 - s0);
@@ -660,8 +693,6 @@ constexpr int LJT_WORDS = (MRMD_LJT_WORDS * 8 * TL_GROUP <= 64) ? MRMD_LJT_WORDS
 #define MRMD_LJT_MORE_WORDS 3
 #endif
 constexpr int LJT_MORE = ((MRMD_LJT_WORDS + MRMD_LJT_MORE_WORDS) * 8 * TL_GROUP <= 64) ? MRMD_LJT_MORE_WORDS : 64 / (8 * TL_GROUP) - LJT_WORDS;
-// list steps (of TL_GROUP entries) whose slots are loaded into registers up front with 16-byte loads
-constexpr int LJT_PREFETCH = (64 / TL_GROUP < MRMD_LJT_PREFETCH) ? 64 / TL_GROUP : MRMD_LJT_PREFETCH;  // multiple of 8
 
 // row length and list words of the home that lane (group, gl) works on in the pass starting at home hBase
 __device__ __forceinline__ void prefetchListRows(const TileDesc& td, const int32_t* __restrict__ counts,
