@@ -710,13 +710,15 @@ __device__ __forceinline__ void prefetchListRows(const TileDesc& td, const int32
     for (int k = 0; k < LJT_WORDS; ++k) words[k] = row[k];
 }
 
-// one pair of LennardJones::apply_if's inner loop (LennardJones.hpp:176-196) against a staged partner
-template <bool SINGLE_TYPE, bool ENERGY>
+// one pair of LennardJones::apply_if's inner loop (LennardJones.hpp:176-196) against a staged partner.
+// CAPPED_BRANCH = false: the force law without its capped branch (LennardJones.hpp:56-67), straight-line code; a pair
+// closer than the capping distance raises cappedSeen and the caller evaluates the row again with the branch.
+template <bool SINGLE_TYPE, bool ENERGY, bool CAPPED_BRANCH>
 __device__ __forceinline__ void ljPair(const double* sx_, const double* sy_, const double* sz_,
                                        const unsigned char* sType, int slot, bool valid, double xi, double yi, double zi,
                                        int typeI, const LJType& t0, const LJTable& table, int64_t numTypesQuirk,
                                        double rcSqr, double& fx, double& fy, double& fz, double& energy, double& virial,
-                                       int& pairs)
+                                       int& pairs, int& minHi)
 {
     // predicated, not branched: consecutive list entries are independent, and without a branch around every pair
     // the compiler interleaves their dependent FP64 chains (an invalid entry reads slot 0 and contributes zero)
@@ -729,12 +731,14 @@ __device__ __forceinline__ void ljPair(const double* sx_, const double* sy_, con
     const LJType& t = SINGLE_TYPE ? t0 : table.t[typeI * numTypesQuirk + sType[s]];
     const double d2 = in ? distSqr : rcSqr;  // keeps the arithmetic of a skipped pair finite
     double ff, e;
-    if (d2 >= t.cappingDistanceSqr)  // LennardJones.hpp:56-67
+    if (!CAPPED_BRANCH || d2 >= t.cappingDistanceSqr)  // LennardJones.hpp:56-67
     {
         const double frac2 = fastRcp(d2);
         const double frac6 = frac2 * frac2 * frac2;
         ff = frac6 * (t.ff1 * frac6 - t.ff2) * frac2;
         e = frac6 * (t.ef1 * frac6 - t.ef2) - t.shift;
+        // (the smallest high word of d2 tells the caller whether a pair came closer than the capping distance)
+        if (!CAPPED_BRANCH) minHi = min(minHi, __double2hiint(d2));
     }
     else
         ljForceEnergy(t, d2, ff, e);
@@ -776,6 +780,10 @@ __global__ void __launch_bounds__(TL_THREADS_FORCE, MRMD_LJT_MINBLOCKS)
     double energy = 0.0, virial = 0.0;
     int pairs = 0;
     const LJType t0 = table.t[0];
+    // high word of the largest capping distance (squared) of the table: a row with a smaller d2 takes the slow path
+    int capHi = __double2hiint(t0.cappingDistanceSqr);
+    if (!SINGLE_TYPE)
+        for (int k = 1; k < MAX_LJ_TYPES * MAX_LJ_TYPES; ++k) capHi = max(capHi, __double2hiint(table.t[k].cappingDistanceSqr));
     // The row length and the list words of a pass are loaded one pass ahead (those of the first pass while the tile is
     // staged): a dependent global load at the head of every pass and one per entry behind the prefetched words were
     // 11 % of the kernel's stall samples (profiles/r02_lj_force_ncu.txt).
@@ -792,7 +800,9 @@ __global__ void __launch_bounds__(TL_THREADS_FORCE, MRMD_LJT_MINBLOCKS)
         const int selfSlot = active ? td.selfSlot0 + h : 0;
         const double xi = sx_[3 * selfSlot], yi = sy_[3 * selfSlot], zi = sz_[3 * selfSlot];
         const int typeI = SINGLE_TYPE ? 0 : sType[selfSlot];
-        double fx = 0.0, fy = 0.0, fz = 0.0;
+        double fx = 0.0, fy = 0.0, fz = 0.0, ePass = 0.0, vPass = 0.0;
+        int pPass = 0;
+        int minHi = 0x7fffffff;
         const int numNeighbors = min(countNext, width);
         unsigned words[4 * (LJT_WORDS + LJT_MORE)];
 #pragma unroll
@@ -820,13 +830,16 @@ __global__ void __launch_bounds__(TL_THREADS_FORCE, MRMD_LJT_MINBLOCKS)
             prefetchListRows(td, counts, enc, width, hBase + homesPerPass, group, gl, countNext, wordsNext);
         const int mine = (numNeighbors - gl + TL_GROUP - 1) / TL_GROUP;  // entries of this lane
         const int iters = __reduce_max_sync(0xffffffffu, (numNeighbors + TL_GROUP - 1) / TL_GROUP);
-#pragma unroll
-        for (int it = 0; it < 8 * LJT_WORDS; ++it)
+        // the first words without a test per step (a row shorter than them is padded with predicated-off steps)
+        if (iters > 0)  // warp uniform
         {
-            const int slot = (words[it >> 1] >> (16 * (it & 1))) & 0xffffu;
-            if (it < iters)  // warp uniform
-                ljPair<SINGLE_TYPE, ENERGY>(sx_, sy_, sz_, sType, slot, it < mine, xi, yi, zi, typeI, t0, table, numTypesQuirk,
-                                            rcSqr, fx, fy, fz, energy, virial, pairs);
+#pragma unroll
+            for (int it = 0; it < 8 * LJT_WORDS; ++it)
+            {
+                const int slot = (words[it >> 1] >> (16 * (it & 1))) & 0xffffu;
+                ljPair<SINGLE_TYPE, ENERGY, false>(sx_, sy_, sz_, sType, slot, it < mine, xi, yi, zi, typeI, t0, table,
+                                                   numTypesQuirk, rcSqr, fx, fy, fz, ePass, vPass, pPass, minHi);
+            }
         }
         // the entries behind the unrolled steps: a rolled loop that takes two entries per trip from the lowest of the
         // remaining prefetched words and moves the others down (registers cannot be indexed)
@@ -839,11 +852,13 @@ __global__ void __launch_bounds__(TL_THREADS_FORCE, MRMD_LJT_MINBLOCKS)
                 const unsigned w = words[4 * LJT_WORDS];
 #pragma unroll
                 for (int k = 4 * LJT_WORDS; k + 1 < 4 * (LJT_WORDS + LJT_MORE); ++k) words[k] = words[k + 1];
-                ljPair<SINGLE_TYPE, ENERGY>(sx_, sy_, sz_, sType, w & 0xffffu, it < mine, xi, yi, zi, typeI, t0, table,
-                                            numTypesQuirk, rcSqr, fx, fy, fz, energy, virial, pairs);
+                ljPair<SINGLE_TYPE, ENERGY, false>(sx_, sy_, sz_, sType, w & 0xffffu, it < mine, xi, yi, zi, typeI, t0, table,
+                                            numTypesQuirk, rcSqr, fx, fy, fz, ePass, vPass, pPass, minHi);
+#ifdef MRMD_LJT_TAIL_BRANCH
                 if (it + 1 < iters)
-                    ljPair<SINGLE_TYPE, ENERGY>(sx_, sy_, sz_, sType, w >> 16, it + 1 < mine, xi, yi, zi, typeI, t0, table,
-                                                numTypesQuirk, rcSqr, fx, fy, fz, energy, virial, pairs);
+#endif
+                    ljPair<SINGLE_TYPE, ENERGY, false>(sx_, sy_, sz_, sType, w >> 16, it + 1 < mine, xi, yi, zi, typeI, t0, table,
+                                                numTypesQuirk, rcSqr, fx, fy, fz, ePass, vPass, pPass, minHi);
             }
         }
         if (iters > 8 * (LJT_WORDS + LJT_MORE))  // rows longer than the prefetched words (lists wider than 64 entries)
@@ -852,10 +867,24 @@ __global__ void __launch_bounds__(TL_THREADS_FORCE, MRMD_LJT_MINBLOCKS)
             for (int it = 8 * (LJT_WORDS + LJT_MORE); it < iters; ++it)
             {
                 if (it < mine)
-                    ljPair<SINGLE_TYPE, ENERGY>(sx_, sy_, sz_, sType, mineRow[it], true, xi, yi, zi, typeI, t0, table,
-                                                numTypesQuirk, rcSqr, fx, fy, fz, energy, virial, pairs);
+                    ljPair<SINGLE_TYPE, ENERGY, false>(sx_, sy_, sz_, sType, mineRow[it], true, xi, yi, zi, typeI, t0, table,
+                                                numTypesQuirk, rcSqr, fx, fy, fz, ePass, vPass, pPass, minHi);
             }
         }
+        // a pair inside the capping distance (a lattice that melts, an overlap): the warp evaluates its rows again with
+        // the capped branch of the force law
+        if (__any_sync(0xffffffffu, minHi <= capHi))
+        {
+            fx = fy = fz = ePass = vPass = 0.0;
+            pPass = 0;
+            const uint16_t* mineRow = enc + size_t(active ? i : 0) * width + gl * (width / TL_GROUP);
+            for (int it = 0; it < mine; ++it)
+                ljPair<SINGLE_TYPE, ENERGY, true>(sx_, sy_, sz_, sType, mineRow[it], true, xi, yi, zi, typeI, t0, table,
+                                                  numTypesQuirk, rcSqr, fx, fy, fz, ePass, vPass, pPass, minHi);
+        }
+        energy += ePass;
+        virial += vPass;
+        pairs += pPass;
         // three lanes of the group end up with the x / y / z total and store it
         double f[TL_VPL];
         groupSum4(fx, fy, fz, 0.0, gl, f);
@@ -1280,7 +1309,8 @@ __global__ void __launch_bounds__(TL_THREADS_MOL)
         }
     }
     // every pair is visited from both sides
-    gridReduce3<TL_THREADS_MOL>(0.5 * energy, 0.5 * double(pairs), 0.5 * double(activePairs), partials, result, ticket);
+    if (ENERGY) gridReduce3<TL_THREADS_MOL>(0.5 * energy, 0.5 * double(pairs), 0.5 * double(activePairs), partials, result, ticket);
+    else gridAddExact<TL_THREADS_MOL>(0.5 * double(pairs), 0.5 * double(activePairs), result + 1, result + 2);
 }
 
 // decode the 16-bit slots back to (local partner index, image shift code) in Cabana's row-major layout
