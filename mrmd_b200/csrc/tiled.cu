@@ -985,8 +985,46 @@ __device__ __forceinline__ void adressPair(const double* rec, const unsigned cha
     if (hyA) vsum += 0.5 * e;  // V_ij of the drift force and of the compensation sampling, :160-200
 }
 
+// adressPair as straight-line code for the pair loop: ideal-gas pairs, pairs beyond the cutoff and entries past the end
+// of a lane's row are predicated off (they read a valid record and contribute zero), the capped branch of the force law
+// is left to the caller (minHi: smallest high word of the d2 seen, see ljForceTiledKernel).  Three branches per pair in
+// adressPair kept the dependent FP64 chains of consecutive pairs from overlapping.
+template <bool SINGLE_TYPE, bool ENERGY>
+__device__ __forceinline__ void adressPairFlat(const double* rec, const unsigned char* sType, int slot, bool valid, double xi,
+                                               double yi, double zi, int typeI, double modA, bool cgA, bool hyA,
+                                               const LJType& t0, const LJTable& table, int64_t numTypes, double rcSqr,
+                                               double& fx, double& fy, double& fz, double& energy, double& vsum, int& pairs,
+                                               int& activePairs, int& minHi)
+{
+    const int s = valid ? slot : 0;
+    const double* q = rec + 4 * s;
+    const double modB = q[3];
+    const bool act = valid && !(cgA && inCG(modB));  // ideal gas, :102-107
+    activePairs += act ? 1 : 0;
+    const double dx = xi - q[0];
+    const double dy = yi - q[1];
+    const double dz = zi - q[2];
+    const double distSqr = distSqrExact(dx, dy, dz);
+    const bool in = act && (distSqr <= rcSqr);  // :137
+    const double d2 = in ? distSqr : rcSqr;
+    const LJType& t = SINGLE_TYPE ? t0 : table.t[typeI * numTypes + sType[s]];
+    const double frac2 = fastRcp(d2);
+    const double frac6 = frac2 * frac2 * frac2;
+    const double ff = frac6 * (t.ff1 * frac6 - t.ff2) * frac2;
+    const double e = frac6 * (t.ef1 * frac6 - t.ef2) - t.shift;
+    minHi = min(minHi, __double2hiint(d2));
+    const double weighting = 0.5 * (modA + modB);
+    const double ffactor = in ? ff * weighting : 0.0;
+    fx += dx * ffactor;
+    fy += dy * ffactor;
+    fz += dz * ffactor;
+    if (ENERGY) energy += in ? e * weighting : 0.0;
+    pairs += in ? 1 : 0;
+    vsum += (in && hyA) ? 0.5 * e : 0.0;  // V_ij of the drift force and of the compensation sampling, :160-200
+}
+
 #ifndef MRMD_ADT_MORE_WORDS
-#define MRMD_ADT_MORE_WORDS 1
+#define MRMD_ADT_MORE_WORDS 3
 #endif
 constexpr int ADT_MORE = (MRMD_ADT_MORE_WORDS < LJT_MORE) ? MRMD_ADT_MORE_WORDS : LJT_MORE;  // rolled-loop words of the AdResS kernel
 template <bool SINGLE_TYPE, bool SAMPLING, bool ENERGY>
@@ -1020,6 +1058,9 @@ __global__ void __launch_bounds__(TL_THREADS_FORCE, 6)
 
         const LJType t0 = table.t[0];
         const int64_t T = numTypes;
+        int capHi = __double2hiint(t0.cappingDistanceSqr);  // see ljForceTiledKernel
+        if (!SINGLE_TYPE)
+            for (int k = 1; k < MAX_LJ_TYPES * MAX_LJ_TYPES; ++k) capHi = max(capHi, __double2hiint(table.t[k].cappingDistanceSqr));
         const double inverseBinSize = 1.0 / ((1.0 - 0.0) / double(TL_COMPENSATION_BINS));
         for (int hBase = 0; hBase < td.homeCount; hBase += homesPerPass)
         {
@@ -1032,7 +1073,8 @@ __global__ void __launch_bounds__(TL_THREADS_FORCE, 6)
             double lambda, modA, gx, gy, gz;
             weightEval(w, xi, yi, zi, lambda, modA, gx, gy, gz);
             const bool hyA = inHY(modA), cgA = inCG(modA);
-            double fx = 0.0, fy = 0.0, fz = 0.0, vsum = 0.0;
+            double fx = 0.0, fy = 0.0, fz = 0.0, vsum = 0.0, ePass = 0.0;
+            int pPass = 0, aPass = 0, minHi = 0x7fffffff;
             const int numNeighbors = min(countNext, width);
             unsigned words[4 * (LJT_WORDS + ADT_MORE)];
 #pragma unroll
@@ -1058,13 +1100,15 @@ __global__ void __launch_bounds__(TL_THREADS_FORCE, 6)
                 prefetchListRows(td, counts, enc, width, hBase + homesPerPass, group, gl, countNext, wordsNext);
             const int mine = (numNeighbors - gl + TL_GROUP - 1) / TL_GROUP;
             const int iters = __reduce_max_sync(0xffffffffu, (numNeighbors + TL_GROUP - 1) / TL_GROUP);
-#pragma unroll
-            for (int it = 0; it < 8 * LJT_WORDS; ++it)
+            if (iters > 0)  // warp uniform
             {
-                const int slot = (words[it >> 1] >> (16 * (it & 1))) & 0xffffu;
-                if (it < mine)
-                    adressPair<SINGLE_TYPE, ENERGY>(rec, sType, slot, xi, yi, zi, typeI, modA, cgA, hyA, t0, table, T, rcSqr, fx,
-                                                    fy, fz, energy, vsum, pairs, activePairs);
+#pragma unroll
+                for (int it = 0; it < 8 * LJT_WORDS; ++it)
+                {
+                    const int slot = (words[it >> 1] >> (16 * (it & 1))) & 0xffffu;
+                    adressPairFlat<SINGLE_TYPE, ENERGY>(rec, sType, slot, it < mine, xi, yi, zi, typeI, modA, cgA, hyA, t0, table, T,
+                                                        rcSqr, fx, fy, fz, ePass, vsum, pPass, aPass, minHi);
+                }
             }
             if (ADT_MORE > 0)
             {
@@ -1075,19 +1119,31 @@ __global__ void __launch_bounds__(TL_THREADS_FORCE, 6)
                     const unsigned wq = words[4 * LJT_WORDS];
 #pragma unroll
                     for (int k = 4 * LJT_WORDS; k + 1 < 4 * (LJT_WORDS + ADT_MORE); ++k) words[k] = words[k + 1];
-                    if (it < mine)
-                        adressPair<SINGLE_TYPE, ENERGY>(rec, sType, wq & 0xffffu, xi, yi, zi, typeI, modA, cgA, hyA, t0, table, T,
-                                                        rcSqr, fx, fy, fz, energy, vsum, pairs, activePairs);
-                    if (it + 1 < mine)
-                        adressPair<SINGLE_TYPE, ENERGY>(rec, sType, wq >> 16, xi, yi, zi, typeI, modA, cgA, hyA, t0, table, T,
-                                                        rcSqr, fx, fy, fz, energy, vsum, pairs, activePairs);
+                    adressPairFlat<SINGLE_TYPE, ENERGY>(rec, sType, wq & 0xffffu, it < mine, xi, yi, zi, typeI, modA, cgA, hyA, t0,
+                                                        table, T, rcSqr, fx, fy, fz, ePass, vsum, pPass, aPass, minHi);
+                    adressPairFlat<SINGLE_TYPE, ENERGY>(rec, sType, wq >> 16, it + 1 < mine, xi, yi, zi, typeI, modA, cgA, hyA, t0,
+                                                        table, T, rcSqr, fx, fy, fz, ePass, vsum, pPass, aPass, minHi);
                 }
             }
-            for (int it = 8 * (LJT_WORDS + ADT_MORE); it < iters; ++it)  // lists wider than 64 entries
+            for (int it = 8 * (LJT_WORDS + ADT_MORE); it < iters; ++it)  // the entries behind the prefetched words
             {
-                if (it < mine)
-                    adressPair<SINGLE_TYPE, ENERGY>(rec, sType, mineRow[it], xi, yi, zi, typeI, modA, cgA, hyA, t0, table, T, rcSqr,
-                                                    fx, fy, fz, energy, vsum, pairs, activePairs);
+                const bool valid = it < mine;
+                adressPairFlat<SINGLE_TYPE, ENERGY>(rec, sType, valid ? mineRow[it] : 0, valid, xi, yi, zi, typeI, modA, cgA, hyA,
+                                                    t0, table, T, rcSqr, fx, fy, fz, ePass, vsum, pPass, aPass, minHi);
+            }
+            // a pair inside the capping distance: the warp evaluates its rows again with the reference's branches
+            {
+                double eP = ePass, pP = double(pPass), aP = double(aPass);
+                if (__any_sync(0xffffffffu, minHi <= capHi))
+                {
+                    fx = fy = fz = vsum = eP = pP = aP = 0.0;
+                    for (int it = 0; it < mine; ++it)
+                        adressPair<SINGLE_TYPE, ENERGY>(rec, sType, mineRow[it], xi, yi, zi, typeI, modA, cgA, hyA, t0, table, T,
+                                                        rcSqr, fx, fy, fz, eP, vsum, pP, aP);
+                }
+                energy += eP;
+                pairs += pP;
+                activePairs += aP;
             }
             // three lanes (slots) of the group end up with the x / y / z total, a fourth with sum(V_ij), which the storing
             // lanes fetch from it
