@@ -22,6 +22,9 @@ struct mrmd_b200_constraints
     int* dErr = nullptr;            // set by a kernel that meets a bond outside its molecule
     // set by the step-loop drivers only: every local molecule has exactly maxBondAtoms atoms and owns all local atoms
     bool uniformMolecules = false;
+    // the bonds are all pairs (i, j), i < j, of the first maxBondAtoms atoms in lexicographic order (a rigid triangle or
+    // tetrahedron): the register-resident kernels apply
+    bool allPairs = false;
 };
 
 namespace mrmd_b200
@@ -172,7 +175,7 @@ __global__ void __launch_bounds__(SHAKE_FUSED_THREADS)
 #pragma unroll
         for (int k = 0; k < NA; ++k)  // Shake::operator()(UnconstraintUpdate, idx), Shake.hpp:131-137
         {
-            const double dtfm = dtf / at(MASS, k);
+            const double dtfm = dtf * at(INVMASS, k);  // dtf / mass up to an ulp (the divisions bound this kernel)
 #pragma unroll
             for (int d = 0; d < 3; ++d) at(UPD + d, k) = at(BASE + d, k) + dtfm * at(FORCE + d, k);
         }
@@ -191,10 +194,12 @@ __global__ void __launch_bounds__(SHAKE_FUSED_THREADS)
             double determinant = qb * qb - 4.0 * qa * qc;
             determinant = fmax(0.0, determinant);
             const double root = sqrt(determinant);
-            const double lambda1 = (-qb + root) / (2.0 * qa);
-            const double lambda2 = (-qb - root) / (2.0 * qa);
-            double lambda = (fabs(lambda1) < fabs(lambda2)) ? lambda1 : lambda2;
-            lambda /= dtf;
+            // one division per bond instead of three: both roots share the denominator, and 1 / dtf joins it (the
+            // quotients agree with the reference's to an ulp; FP64 divisions and the root are what this kernel costs)
+            const double inv = 1.0 / (2.0 * qa * dtf);
+            const double lambda1 = (-qb + root) * inv;
+            const double lambda2 = (-qb - root) * inv;
+            const double lambda = (fabs(lambda1) < fabs(lambda2)) ? lambda1 : lambda2;
 #pragma unroll
             for (int d = 0; d < 3; ++d)
             {
@@ -207,6 +212,91 @@ __global__ void __launch_bounds__(SHAKE_FUSED_THREADS)
     for (int k = 0; k < NA; ++k)
 #pragma unroll
         for (int d = 0; d < 3; ++d) a.force[d][oc.x + k] = at(FORCE + d, k);
+}
+
+// shakeFusedKernel for molecules whose bonds are ALL pairs of their NA atoms in lexicographic order (the rigid tetramers of
+// BASELINE.json configs[3], three-site water): the atom indices of every bond are compile-time constants, so the whole
+// molecule state lives in registers -- no shared memory (the shared-memory traffic of the indexable state, ~600 accesses per
+// molecule, bounded the generic kernel) -- and the bonds of an iteration, whose inputs do not depend on each other
+// (Shake.hpp:84-128 reads pos and updatedPos, both fixed during the bond loop), overlap.  The forces are accumulated in the
+// reference's bond order.
+template <int NA>
+__global__ void __launch_bounds__(128)
+    shakeAllPairsKernel(MolsView m, AtomsView a, int64_t numLocalMols, const double* __restrict__ bondDist,
+                        int64_t numIterations, double dtv, double dtf, int* error)
+{
+    constexpr int NB = NA * (NA - 1) / 2;
+    const int64_t mol = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (mol >= numLocalMols) return;
+    const longlong2 oc = m.oc[mol];
+    if (oc.y < NA)  // some bond names an atom the molecule does not have
+    {
+        *error = 1;
+        return;
+    }
+    double pos[NA][3], base[NA][3], frc[NA][3], upd[NA][3], invMass[NA], eqSq[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+    {
+        const double eq = bondDist[b];
+        eqSq[b] = eq * eq;
+    }
+#pragma unroll
+    for (int k = 0; k < NA; ++k)
+    {
+        const double4 p = ld4(a.pos + oc.x + k);
+        pos[k][0] = p.x;
+        pos[k][1] = p.y;
+        pos[k][2] = p.z;
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+        {
+            base[k][d] = pos[k][d] + dtv * a.vel[d][oc.x + k];
+            frc[k][d] = a.force[d][oc.x + k];
+        }
+        invMass[k] = 1.0 / a.mass[oc.x + k];  // the same quotient for every bond of the atom
+    }
+    for (int64_t it = 0; it < numIterations; ++it)
+    {
+#pragma unroll
+        for (int k = 0; k < NA; ++k)  // Shake::operator()(UnconstraintUpdate, idx), Shake.hpp:131-137
+        {
+            const double dtfm = dtf * invMass[k];  // dtf / mass up to an ulp
+#pragma unroll
+            for (int d = 0; d < 3; ++d) upd[k][d] = base[k][d] + dtfm * frc[k][d];
+        }
+        int b = 0;
+#pragma unroll
+        for (int i = 0; i < NA; ++i)
+#pragma unroll
+            for (int j = i + 1; j < NA; ++j, ++b)  // Shake::enforcePositionalConstraint, :84-128
+            {
+                const double dist[3] = {pos[i][0] - pos[j][0], pos[i][1] - pos[j][1], pos[i][2] - pos[j][2]};
+                const double distSq = dist[0] * dist[0] + dist[1] * dist[1] + dist[2] * dist[2];
+                const double du[3] = {upd[i][0] - upd[j][0], upd[i][1] - upd[j][1], upd[i][2] - upd[j][2]};
+                const double updSq = du[0] * du[0] + du[1] * du[1] + du[2] * du[2];
+                const double im = invMass[i] + invMass[j];
+                const double qa = im * im * distSq;
+                const double qb = 2.0 * im * (du[0] * dist[0] + du[1] * dist[1] + du[2] * dist[2]);
+                const double qc = updSq - eqSq[b];
+                const double determinant = fmax(0.0, qb * qb - 4.0 * qa * qc);
+                const double root = sqrt(determinant);
+                const double inv = 1.0 / (2.0 * qa * dtf);  // one division per bond, see shakeFusedKernel
+                const double lambda1 = (-qb + root) * inv;
+                const double lambda2 = (-qb - root) * inv;
+                const double lambda = (fabs(lambda1) < fabs(lambda2)) ? lambda1 : lambda2;
+#pragma unroll
+                for (int d = 0; d < 3; ++d)
+                {
+                    frc[i][d] += lambda * dist[d];
+                    frc[j][d] -= lambda * dist[d];
+                }
+            }
+    }
+#pragma unroll
+    for (int k = 0; k < NA; ++k)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) a.force[d][oc.x + k] = frc[k][d];
 }
 
 // MoleculeConstraints::enforceVelocityConstraints lambda (Shake.hpp:215-231) with
@@ -285,9 +375,9 @@ __global__ void __launch_bounds__(SHAKE_FUSED_THREADS)
         const double dist[3] = {at(POS, i) - at(POS, j), at(POS + 1, i) - at(POS + 1, j), at(POS + 2, i) - at(POS + 2, j)};
         const double distSq = dist[0] * dist[0] + dist[1] * dist[1] + dist[2] * dist[2];
         const double invMassI = at(INVMASS, i), invMassJ = at(INVMASS, j);
-        const double reducedMass = 1.0 / (invMassI + invMassJ);
         const double relVel[3] = {at(VEL, i) - at(VEL, j), at(VEL + 1, i) - at(VEL + 1, j), at(VEL + 2, i) - at(VEL + 2, j)};
-        const double factor = (relVel[0] * dist[0] + relVel[1] * dist[1] + relVel[2] * dist[2]) / distSq * reducedMass;
+        // (relVel . dist) / distSq * reducedMass with reducedMass = 1 / (invMassI + invMassJ), as one division
+        const double factor = (relVel[0] * dist[0] + relVel[1] * dist[1] + relVel[2] * dist[2]) / (distSq * (invMassI + invMassJ));
 #pragma unroll
         for (int d = 0; d < 3; ++d)
         {
@@ -299,6 +389,61 @@ __global__ void __launch_bounds__(SHAKE_FUSED_THREADS)
     for (int k = 0; k < NA; ++k)
 #pragma unroll
         for (int d = 0; d < 3; ++d) a.vel[d][oc.x + k] = at(VEL + d, k);
+}
+
+// rattleFusedKernel for all-pairs molecules (see shakeAllPairsKernel): state in registers.  The bonds stay sequential
+// (every bond reads the velocities the previous one wrote, Shake.hpp:56-82).
+template <int NA, bool KICK>
+__global__ void __launch_bounds__(128)
+    rattleAllPairsKernel(MolsView m, AtomsView a, int64_t numLocalMols, double halfDt, int* error)
+{
+    const int64_t mol = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (mol >= numLocalMols) return;
+    const longlong2 oc = m.oc[mol];
+    if (oc.y < NA)
+    {
+        *error = 1;
+        return;
+    }
+    double pos[NA][3], vel[NA][3], invMass[NA];
+#pragma unroll
+    for (int k = 0; k < NA; ++k)
+    {
+        const double4 p = ld4(a.pos + oc.x + k);
+        pos[k][0] = p.x;
+        pos[k][1] = p.y;
+        pos[k][2] = p.z;
+        const double mass = a.mass[oc.x + k];
+        const double dtfm = halfDt / mass;
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+        {
+            double v = a.vel[d][oc.x + k];
+            if (KICK) v = __dadd_rn(v, __dmul_rn(dtfm, a.force[d][oc.x + k]));
+            vel[k][d] = v;
+        }
+        invMass[k] = 1.0 / mass;
+    }
+#pragma unroll
+    for (int i = 0; i < NA; ++i)
+#pragma unroll
+        for (int j = i + 1; j < NA; ++j)  // Shake::enforceVelocityConstraint, Shake.hpp:56-82
+        {
+            const double dist[3] = {pos[i][0] - pos[j][0], pos[i][1] - pos[j][1], pos[i][2] - pos[j][2]};
+            const double distSq = dist[0] * dist[0] + dist[1] * dist[1] + dist[2] * dist[2];
+            const double relVel[3] = {vel[i][0] - vel[j][0], vel[i][1] - vel[j][1], vel[i][2] - vel[j][2]};
+            const double factor = (relVel[0] * dist[0] + relVel[1] * dist[1] + relVel[2] * dist[2]) / (distSq * (invMass[i] + invMass[j]));
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+            {
+                vel[i][d] -= factor * dist[d] * invMass[i];
+                vel[j][d] += factor * dist[d] * invMass[j];
+            }
+        }
+#pragma unroll
+    for (int k = 0; k < NA; ++k)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) a.vel[d][oc.x + k] = vel[k][d];
 }
 
 static int checkBondError(int* dErr, cudaStream_t st)
@@ -322,6 +467,18 @@ int constraintsEnforcePositional(mrmd_b200_constraints* c, const mrmd_b200_molec
     if (c->maxBondAtoms >= 2 && c->maxBondAtoms <= 4)
     {
         if (m->numLocal == 0 || c->numBonds == 0) return 0;
+        if (c->allPairs && c->maxBondAtoms >= 3)
+        {
+            const int blocksAll = gridFor(m->numLocal, 128);
+            if (c->maxBondAtoms == 3)
+                shakeAllPairsKernel<3><<<blocksAll, 128, 0, st>>>(m->v, a->v, m->numLocal, c->bondDist.as<double>(),
+                                                                 c->numIterations, dtv, dtf, c->dErr);
+            else
+                shakeAllPairsKernel<4><<<blocksAll, 128, 0, st>>>(m->v, a->v, m->numLocal, c->bondDist.as<double>(),
+                                                                 c->numIterations, dtv, dtf, c->dErr);
+            MB_LAUNCHED();
+            return 0;
+        }
         const int blocks = gridFor(m->numLocal, SHAKE_FUSED_THREADS);
 #define MB_SHAKE_FUSED(NA)                                                                                              \
     shakeFusedKernel<NA><<<blocks, SHAKE_FUSED_THREADS, 0, st>>>(m->v, a->v, m->numLocal, c->bondIdx.as<long long>(),   \
@@ -366,6 +523,21 @@ int constraintsEnforceVelocity(mrmd_b200_constraints* c, const mrmd_b200_molecul
     {
         const int blocks = gridFor(m->numLocal, SHAKE_FUSED_THREADS);
         const double halfDt = 0.5 * postDt;
+        if (c->allPairs && c->maxBondAtoms >= 3)
+        {
+            const int blocksAll = gridFor(m->numLocal, 128);
+#define MB_RATTLE_ALL(NA)                                                                                             \
+    do                                                                                                                \
+    {                                                                                                                 \
+        if (kick) rattleAllPairsKernel<NA, true><<<blocksAll, 128, 0, st>>>(m->v, a->v, m->numLocal, halfDt, c->dErr); \
+        else rattleAllPairsKernel<NA, false><<<blocksAll, 128, 0, st>>>(m->v, a->v, m->numLocal, 0.0, c->dErr);       \
+    } while (0)
+            if (c->maxBondAtoms == 3) MB_RATTLE_ALL(3);
+            else MB_RATTLE_ALL(4);
+#undef MB_RATTLE_ALL
+            MB_LAUNCHED();
+            return 0;
+        }
 #define MB_RATTLE_FUSED(NA)                                                                                               \
     do                                                                                                                    \
     {                                                                                                                     \
@@ -496,6 +668,14 @@ int mrmd_b200_constraints_set(mrmd_b200_constraints* c, const int64_t* idx, cons
         MB_CUDA(cudaMemcpy(c->bondDist.p, eqDistance, size_t(numBonds) * 8, cudaMemcpyHostToDevice));
     }
     c->numBonds = numBonds;
+    {
+        const int64_t na = c->maxBondAtoms;
+        bool all = na >= 2 && na <= 4 && numBonds == na * (na - 1) / 2;
+        int64_t b = 0;
+        for (int64_t i = 0; all && i < na; ++i)
+            for (int64_t j = i + 1; all && j < na; ++j, ++b) all = (idx[b] == i && jdx[b] == j);
+        c->allPairs = all;
+    }
     return 0;
 }
 

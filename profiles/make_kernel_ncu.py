@@ -48,6 +48,7 @@ def main(src):
             "fp64_pipe_frac": num(m, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
             "issue_active_frac": num(m, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
             "dram_throughput_frac": num(m, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+            "l1tex_throughput_frac": num(m, "l1tex__throughput.avg.pct_of_peak_sustained_elapsed"),
             "warp_instructions": num(m, "smsp__inst_executed.sum"),
             "registers_per_thread": num(m, "launch__registers_per_thread"),
         }

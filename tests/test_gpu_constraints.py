@@ -118,11 +118,12 @@ def test_shake_molecules_kat(api):
         mc.enforcePositionalConstraints(mols, atoms, 0.1)
 
 
-@pytest.mark.parametrize("a_per", [4, 6])
-def test_constraints_vs_oracle(api, oracle, a_per):
+@pytest.mark.parametrize("a_per,order", [(4, "lexicographic"), (4, "reversed"), (6, "lexicographic")])
+def test_constraints_vs_oracle(api, oracle, a_per, order):
     """20 000 tetramers with six bonds each, three SHAKE iterations and the RATTLE projection, against the oracle.
-    a_per = 4 takes the fused shared-memory kernels (bonds among the first four atoms of a molecule); a_per = 6 hangs
-    two more atoms on every tetramer (bonds 3-4, 4-5) and takes the kernel sequence of the reference."""
+    a_per = 4 with the six bonds listed as all pairs in lexicographic order takes the register-resident all-pairs kernels,
+    the same bonds listed backwards the fused shared-memory kernels (any bonds among the first four atoms of a molecule);
+    a_per = 6 hangs two more atoms on every tetramer (bonds 3-4, 4-5) and takes the kernel sequence of the reference."""
     rng = np.random.default_rng(8)
     M = 20000
     N = M * a_per
@@ -132,6 +133,8 @@ def test_constraints_vs_oracle(api, oracle, a_per):
     vel, force = rng.normal(size=(N, 3)), rng.normal(size=(N, 3)) * 3
     mass = 0.5 + rng.random(N)
     bonds = [(i, j, 1.0) for i in range(4) for j in range(i + 1, 4)] + [(i, i + 1, 0.6) for i in range(3, a_per - 1)]
+    if order == "reversed":
+        bonds = bonds[::-1]
     dt = 0.002
 
     atoms = api.Atoms.from_arrays(pos, vel, mass=mass)
