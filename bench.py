@@ -309,8 +309,14 @@ class Ctx:
         self.rank, self.local_rank, self.world = env_rank()
         torch.cuda.set_device(self.local_rank)
         self.dist = None
+        self.numa_bound = False
         if self.world > 1:
             import torch.distributed as dist
+            from mrmd_b200.slabs import bind_host_to_gpu
+
+            # one process per GPU: host threads and pinned buffers on the GPU's NUMA node (the cpu_baseline leg runs at
+            # N = 1 only and keeps all cores)
+            self.numa_bound = bind_host_to_gpu(self.local_rank) is not None
 
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
             self.dist = dist
@@ -514,7 +520,8 @@ def run_case(ctx, workload, side, side_x, steps, warmup, equil, full_list=2, bal
                        ": pinned host pos+vel of the resident atoms -> device, one step, pos+vel+{E,virial,maxDisp} "
                        "back; chunked copies on two copy streams, step i+1's upload trails step i's download; "
                        "bytes are per GPU; value_one_step_per_call = the same with one call per step (no overlap "
-                       "across steps)"}
+                       "across steps)",
+               "host_numa_bound": bool(ctx.numa_bound)}
         del hpos, hvel, hsc
 
     cpu = None

@@ -71,6 +71,36 @@ def select_slab(pos, global_min, global_max, rank, nranks, cuts=None):
     return np.nonzero((pos[:, 0] >= lo) & (pos[:, 0] < hi))[0]
 
 
+def bind_host_to_gpu(device_index):
+    """Pins this process to the CPU cores of the NUMA node the GPU hangs on, so that the pinned host buffers of the
+    host-buffer path (mrmd_b200_slab_run_host) are allocated node-local (first touch) and the copy streams are fed from
+    that node: with one process per GPU and no binding, every rank's buffers end up on the node the launcher started on and
+    half of the GPUs copy across the socket link.  Returns the previous affinity (restore with os.sched_setaffinity), or
+    None when the topology cannot be read (no sysfs entry, node -1) -- then nothing is changed."""
+    import os
+
+    try:
+        import torch
+
+        props = torch.cuda.get_device_properties(device_index)
+        bus = "%04x:%02x:%02x.0" % (getattr(props, "pci_domain_id", 0), props.pci_bus_id, props.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        before = os.sched_getaffinity(0)
+        cpus &= before  # stay inside the cpuset the container grants
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return before
+    except Exception:
+        return None
+
+
 def broadcast_unique_id(rank):
     """128-byte NCCL unique id of rank 0 on every rank (torch.distributed must be initialised)"""
     import torch
