@@ -932,16 +932,26 @@ __device__ __forceinline__ void stageTileAdress(const TileParams& tp, const Tile
         pieceShift(tp, ci, cj, p, ix, iy, iz);
         const double shx = double(ix) * tp.L[0], shy = double(iy) * tp.L[1], shz = double(iz) * tp.L[2];
         const int start = td.pieceStart[p], slot0 = td.pieceSlot[p];
-        for (int k = lane; k < len; k += 32)
+        // TL_STAGE_UNROLL loads in flight per lane, as in stageTile
+        for (int k0 = lane; k0 < len; k0 += 32 * TL_STAGE_UNROLL)
         {
-            const double4 raw = ld4nc(pos + start + k);
-            const double qx = raw.x + shx, qy = raw.y + shy, qz = raw.z + shz;
-            double* r = rec + 4 * (slot0 + k);
-            r[0] = qx;
-            r[1] = qy;
-            r[2] = qz;
-            r[3] = weightModLambda(w, qx, qy, qz);
-            if (TYPES) sType[slot0 + k] = static_cast<unsigned char>(typeOf(raw));
+            double4 raw[TL_STAGE_UNROLL];
+#pragma unroll
+            for (int u = 0; u < TL_STAGE_UNROLL; ++u)
+                if (k0 + 32 * u < len) raw[u] = ld4nc(pos + start + k0 + 32 * u);
+#pragma unroll
+            for (int u = 0; u < TL_STAGE_UNROLL; ++u)
+            {
+                const int k = k0 + 32 * u;
+                if (k >= len) break;
+                const double qx = raw[u].x + shx, qy = raw[u].y + shy, qz = raw[u].z + shz;
+                double* r = rec + 4 * (slot0 + k);
+                r[0] = qx;
+                r[1] = qy;
+                r[2] = qz;
+                r[3] = weightModLambda(w, qx, qy, qz);
+                if (TYPES) sType[slot0 + k] = static_cast<unsigned char>(typeOf(raw[u]));
+            }
         }
     }
     __syncthreads();
@@ -1023,6 +1033,9 @@ __device__ __forceinline__ void adressPairFlat(const double* rec, const unsigned
     vsum += (in && hyA) ? 0.5 * e : 0.0;  // V_ij of the drift force and of the compensation sampling, :160-200
 }
 
+#ifndef MRMD_ADT_PREFETCH_FORCE
+#define MRMD_ADT_PREFETCH_FORCE 1
+#endif
 #ifndef MRMD_ADT_MORE_WORDS
 #define MRMD_ADT_MORE_WORDS 3
 #endif
@@ -1075,6 +1088,18 @@ __global__ void __launch_bounds__(TL_THREADS_FORCE, 6)
             const bool hyA = inHY(modA), cgA = inCG(modA);
             double fx = 0.0, fy = 0.0, fz = 0.0, vsum = 0.0, ePass = 0.0;
             int pPass = 0, aPass = 0, minHi = 0x7fffffff;
+            // the force the row owner adds to (zero, or what the thermodynamic force left) is fetched now, not at the store
+            double fOld[TL_VPL];
+#pragma unroll
+            for (int k = 0; k < TL_VPL; ++k)
+            {
+                const int comp = groupSumValue(gl, k);
+                fOld[k] = 0.0;
+#if MRMD_ADT_PREFETCH_FORCE
+                if (active && comp >= 0 && comp < 3)
+                    fOld[k] = ((comp == 0) ? a.force[0] : ((comp == 1) ? a.force[1] : a.force[2]))[i];
+#endif
+            }
             const int numNeighbors = min(countNext, width);
             unsigned words[4 * (LJT_WORDS + ADT_MORE)];
 #pragma unroll
@@ -1179,7 +1204,11 @@ __global__ void __launch_bounds__(TL_THREADS_FORCE, 6)
                     if (out != 0.0)
                     {
                         double* plane = (comp == 0) ? a.force[0] : ((comp == 1) ? a.force[1] : a.force[2]);
+#if MRMD_ADT_PREFETCH_FORCE
+                        plane[i] = fOld[k] + out;
+#else
                         plane[i] += out;
+#endif
                     }
                 }
             }
