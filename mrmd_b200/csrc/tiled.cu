@@ -1799,9 +1799,12 @@ int verletBuildTiled(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, const mrmd_b
         else VBT_LAUNCH(false);
 #undef VBT_LAUNCH
         MB_LAUNCHED();
-        compactActiveTilesKernel<<<1, 1024, 0, st>>>(v->tileActive.as<unsigned char>(), tiles, v->activeTiles.as<int32_t>(),
-                                                     v->tstats.as<int32_t>() + 3);
-        MB_LAUNCHED();
+        if (v->tiledCgSkip)  // the list of tiles with work is only used by the AdResS step loops
+        {
+            compactActiveTilesKernel<<<1, 1024, 0, st>>>(v->tileActive.as<unsigned char>(), tiles, v->activeTiles.as<int32_t>(),
+                                                         v->tstats.as<int32_t>() + 3);
+            MB_LAUNCHED();
+        }
         MB_CUDA(cudaMemcpyAsync(v->hStats, v->stats.p, 16, cudaMemcpyDeviceToHost, st));
         MB_CUDA(cudaMemcpyAsync(v->hTstats, v->tstats.p, 16, cudaMemcpyDeviceToHost, st));
         MB_CUDA(cudaStreamSynchronize(st));
