@@ -588,7 +588,7 @@ int mrmd_b200_adress_run_periodic(mrmd_b200_adress* ad, mrmd_b200_atoms* a, cons
 {
     MB_TRY(checkDevice());
     cudaStream_t st = S(stream);
-    MB_TRY(adressRunPeriodic(ad, a, v, w, energy != nullptr, st));
+    MB_TRY(adressRunPeriodic(ad, a, v, w, energy != nullptr || numPairs != nullptr, st));  // per-launch values: <ENERGY>
     if (energy != nullptr || numPairs != nullptr)
     {
         MB_CUDA(cudaMemcpyAsync(ad->hResult, ad->dResult, 24, cudaMemcpyDeviceToHost, st));
@@ -670,7 +670,7 @@ int mrmd_b200_adress_run_periodic_molecules(mrmd_b200_adress* ad, const mrmd_b20
 {
     MB_TRY(checkDevice());
     cudaStream_t st = S(stream);
-    MB_TRY(adressRunPeriodicMolecules(ad, m, a, v, w, atomsPerMolecule, energy != nullptr, st));
+    MB_TRY(adressRunPeriodicMolecules(ad, m, a, v, w, atomsPerMolecule, energy != nullptr || numPairs != nullptr, st));
     if (energy != nullptr || numPairs != nullptr)
     {
         MB_CUDA(cudaMemcpyAsync(ad->hResult, ad->dResult, 24, cudaMemcpyDeviceToHost, st));

@@ -376,8 +376,9 @@ __device__ __forceinline__ long long warpSumLL(long long v)
 // double precision, so the order in which the blocks' fire-and-forget REDs land does not matter -- deterministic
 // without the fence / ticket / last-block pass of gridReduce3 (which kept every block of the tiled force kernels
 // resident for a device-wide memory fence: 11 % of the stall samples of ljForceTiledKernel).  slotA / slotB (either
-// may be nullptr) point at the value of this launch (zeroed by the caller); the running sum sits three doubles
-// behind, as in gridReduce3's result layout.
+// may be nullptr) name the per-launch slots of gridReduce3's result layout; only the RUNNING sums three doubles behind
+// them are updated: the step-loop drivers read nothing else between the launches that ask for energies, and a per-launch
+// value would need the slot zeroed in front of every launch (one more node in the stream per step).
 template <int THREADS>
 __device__ __forceinline__ void gridAddExact(double a, double b, double* slotA, double* slotB)
 {
@@ -399,16 +400,8 @@ __device__ __forceinline__ void gridAddExact(double a, double b, double* slotA, 
             sa += sAdd[0][w];
             sb += sAdd[1][w];
         }
-        if (slotA != nullptr && sa != 0.0)
-        {
-            atomicAdd(slotA, sa);
-            atomicAdd(slotA + 3, sa);
-        }
-        if (slotB != nullptr && sb != 0.0)
-        {
-            atomicAdd(slotB, sb);
-            atomicAdd(slotB + 3, sb);
-        }
+        if (slotA != nullptr && sa != 0.0) atomicAdd(slotA + 3, sa);
+        if (slotB != nullptr && sb != 0.0) atomicAdd(slotB + 3, sb);
     }
 }
 

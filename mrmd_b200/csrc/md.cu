@@ -235,6 +235,12 @@ static int stepAfterPre(mrmd_b200_md* md, cudaStream_t st, cudaEvent_t evStart, 
         if (evStart) MB_CUDA(cudaEventRecord(evStart, st));
         // energy and virial are only observable after the run returns: accumulate them on its last step
         MB_TRY(ljApplyTiled(md->lj, a, md->list, false, wantEnergy, st, stop));
+        {
+            // measurement knob (profiles/r02_build_experiments.md): the force is stored, not accumulated, so repeating the
+            // launch changes nothing but the time -- the marginal cost of the kernel inside the step loop
+            static const int repeat = std::getenv("MRMD_B200_REPEAT_FORCE") ? std::atoi(std::getenv("MRMD_B200_REPEAT_FORCE")) : 1;
+            for (int r = 1; r < repeat; ++r) MB_TRY(ljApplyTiled(md->lj, a, md->list, false, wantEnergy, st, stop));
+        }
         if (evStop) MB_CUDA(cudaEventRecord(evStop, st));
         MB_TRY(postIntegrate(md, deferPost, st));
         md->step += 1;

@@ -1521,7 +1521,7 @@ int ljApplyTiled(mrmd_b200_lj* lj, mrmd_b200_atoms* a, const mrmd_b200_verlet* v
     MB_TRY(makeTileParams(a, &v->tiledSub, v->tiledCH, v->tiledSlots, v->tiledHaloX, v->tiledR, tp));
     const int tiles = tp.g.n[0] * tp.g.n[1] * tp.numChunks;
     MB_TRY(lj->partials.reserve(size_t(tiles) * 3 * 8));
-    MB_CUDA(cudaMemsetAsync(lj->dResult, 0, 24, st));
+    if (energy) MB_CUDA(cudaMemsetAsync(lj->dResult, 0, 24, st));  // without energy only the running sums move (gridAddExact)
     const size_t smem = size_t(v->tiledSlots) * TL_SMEM_PER_SLOT_FORCE + 16;
     const bool single = (lj->numTypes == 1);
 #define LJT_LAUNCH(S1, ACC, EN)                                                                                       \
@@ -1573,7 +1573,7 @@ int adressApplyTiled(mrmd_b200_adress* ad, mrmd_b200_atoms* a, const mrmd_b200_v
     const int tiles = v->tiledCgSkip ? v->numActiveTiles : tp.g.n[0] * tp.g.n[1] * tp.numChunks;
     const int32_t* activeTiles = v->tiledCgSkip ? v->activeTiles.as<int32_t>() : nullptr;
     MB_TRY(ad->partials.reserve(size_t(std::max(tiles, 1)) * 3 * 8));
-    MB_CUDA(cudaMemsetAsync(ad->dResult, 0, 24, st));
+    if (energy) MB_CUDA(cudaMemsetAsync(ad->dResult, 0, 24, st));  // without energy only the running sums move
     if (tiles == 0) return 0;
     const size_t smem = size_t(v->tiledSlots) * TL_SMEM_PER_SLOT_ADRESS + 16;
     MB_REQUIRE(smem <= size_t(TL_SMEM_MAX), "adress_run_periodic: a tile exceeds shared memory");
@@ -1628,7 +1628,7 @@ int moleculeApplyTiled(mrmd_b200_adress* ad, const mrmd_b200_molecules* m, mrmd_
     const int tiles = v->tiledCgSkip ? v->numActiveTiles : tp.g.n[0] * tp.g.n[1] * tp.numChunks;
     const int32_t* activeTiles = v->tiledCgSkip ? v->activeTiles.as<int32_t>() : nullptr;
     MB_TRY(ad->partials.reserve(size_t(std::max(tiles, 1)) * 3 * 8));
-    MB_CUDA(cudaMemsetAsync(ad->dResult, 0, 24, st));
+    if (energy) MB_CUDA(cudaMemsetAsync(ad->dResult, 0, 24, st));  // without energy only the running sums move
     if (tiles == 0) return 0;
     // homes whose list rows are staged: the tallest tile holds about twice the aimed-at number (the rest reads global)
     const int maxHomes = std::min(2 * v->tiledTargetHomes + 16, 64);

@@ -13,7 +13,7 @@ def main(path, steps=None):
         return
     hdr = rows[0]
     ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
-    agg = collections.defaultdict(lambda: [0, 0.0])
+    agg = collections.defaultdict(lambda: [0, 0.0, []])
     for r in rows[1:]:
         v = float(r[vi].replace(",", ""))
         u = r[ui]
@@ -21,11 +21,14 @@ def main(path, steps=None):
         a = agg[r[ki].split("(")[0][:70]]
         a[0] += 1
         a[1] += v
-    total = sum(t for _, t in agg.values())
+        a[2].append(v)
+    total = sum(t for _, t, _ in agg.values())
     print(f"{len(rows) - 1} launches, {total:.1f} us of kernel time" + (f", {total / steps:.1f} us per step" if steps else ""))
-    for k, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
+    print("(mean includes the launches queued behind a rebuild decision, which return at once: read the median for a kernel's duration)")
+    for k, (c, t, vs) in sorted(agg.items(), key=lambda x: -x[1][1]):
         per = f" {t / steps:8.1f} us/step" if steps else ""
-        print(f"{t:10.1f} us {100 * t / total:5.1f}% {c:5d} x {t / c:8.1f} us{per}  {k}")
+        med = sorted(vs)[len(vs) // 2]
+        print(f"{t:10.1f} us {100 * t / total:5.1f}% {c:5d} x mean {t / c:8.1f} median {med:8.1f} us{per}  {k}")
 
 
 if __name__ == "__main__":
