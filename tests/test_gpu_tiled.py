@@ -29,7 +29,7 @@ def system(n_side, jitter, seed, spacing=1.25, box_scale=(1, 1, 1)):
     return np.mod(pos, box), rng.random(g.shape) - 0.5, box
 
 
-def reference_pairs(oracle, pos_sorted, box, thickness, radius, half):
+def reference_pairs(oracle, pos_sorted, box, thickness, radius, half, width=128):
     """oracle: ghosts + Cabana list, partners mapped to (real atom, image shift code)"""
     L = oracle.lib()
     n = len(pos_sorted)
@@ -41,7 +41,7 @@ def reference_pairs(oracle, pos_sorted, box, thickness, radius, half):
     ng = L.or_ghost_create_xyz(oa.ctypes.data, n, len(oa), C.byref(sub), corr.ctypes.data)
     assert ng >= 0
     counts, neigh = oracle.verlet_build(oa, 13, n + ng, 0, n, radius, 1.0, np.array(sub.minGhostCorner),
-                                        np.array(sub.maxGhostCorner), half=half, width=128)
+                                        np.array(sub.maxGhostCorner), half=half, width=width)
     rows = []
     for i in range(n):
         nb = neigh[i, :counts[i]].astype(np.int64)
@@ -76,6 +76,47 @@ def test_periodic_list_equals_ghost_list(api, oracle, n_side, jitter, thickness,
     for i in range(n):
         got = sorted(zip(partner[i, :gc[i]].tolist(), code[i, :gc[i]].tolist()))
         assert got == rows[i], i
+
+
+def test_dense_region_tiles_take_several_passes(api, oracle):
+    """A third of the box holds all atoms at almost four times the mean density: the tiles of that region hold more home
+    atoms than the builder has lanes (several passes per tile), and the rows are wider than 64 entries (the words of a row
+    behind the prefetched ones in the builder's copy-out and in the force kernel).  Pair sets bit-exact, forces 1e-10."""
+    rng = np.random.default_rng(77)
+    box = np.array([20.8, 20.8, 83.2])
+    n = 23040
+    pos = rng.random((n, 3)) * np.array([box[0], box[1], box[2] / 3.0])
+    # keep pairs apart (the force law is capped, but the comparison is relative to the largest force)
+    pos = pos[np.argsort(pos[:, 2])]
+    vel = np.zeros_like(pos)
+    radius, rc, cap = 2.6, 2.5, 0.7
+    sub = api.Subdomain([0, 0, 0], box, radius)
+    atoms = api.Atoms.from_arrays(pos, vel)
+    api.GhostLayer().exchangeRealAtoms(atoms, sub)
+    atoms.permute(api.LinkedCellList(0, n, [radius, radius, radius / 4], sub.minCorner, sub.maxCorner))
+    sorted_pos = atoms.getPos()[:n]
+    vl = api.FullVerletList()
+    vl.build_periodic(atoms, sub, radius, 1.0, 250)
+    gc, partner, code = vl.to_host_periodic(atoms)
+    oa, corr, ng, oc, on, rows, osub = reference_pairs(oracle, sorted_pos, box, radius, radius, False, width=320)
+    assert gc.max() > 128 and np.array_equal(gc, oc[:n])
+    for i in range(n):
+        got = sorted(zip(partner[i, :gc[i]].tolist(), code[i, :gc[i]].tolist()))
+        assert got == rows[i], i
+    lj = api.LennardJones(rc, 1.0, 1.0, cap)
+    atoms.setForce(0.0)
+    lj.apply(atoms, vl)
+    # the reference path: half list over local + ghost atoms, ghost forces folded back
+    oa, corr, ng, oc, on, rows, osub = reference_pairs(oracle, sorted_pos, box, radius, radius, True, width=320)
+    table = oracle.lj_table(cap, rc, 1.0, 1.0)
+    ev = np.zeros(2)
+    pairs = oracle.lib().or_lj_apply(oa.ctypes.data, n, oc.ctypes.data, on.ctypes.data, on.shape[1],
+                                     C.addressof(table), rc * rc, 1, None, ev.ctypes.data)
+    oracle.lib().or_ghost_fold_force(oa.ctypes.data, n, ng, corr.ctypes.data)
+    f, f_ref = atoms.getForce()[:n], oa["force"][:n]
+    assert np.abs(f - f_ref).max() <= 1e-10 * np.abs(f_ref).max()
+    e, v, p = lj._get()
+    assert p == pairs and abs(e - ev[0]) <= 1e-11 * abs(ev[0])
 
 
 @pytest.mark.parametrize("n_side,jitter,box_scale", [(12, 0.7, (1, 1, 1)), (20, 0.0, (1, 1, 1)), (8, 0.9, (3, 1, 2))])
