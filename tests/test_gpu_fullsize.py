@@ -97,6 +97,9 @@ def test_lj_1m_step_vs_oracle(api, oracle):
     L.or_ghost_fold_force(oa.ctypes.data, n, ng, corr.ctypes.data)
     assert p == pairs
     assert np.abs(f - oa["force"][:n]).max() <= 1e-10 * np.abs(oa["force"][:n]).max()
+    # and atom by atom against the atom's own force (floor: 1e-3 of the largest force in the system)
+    norm, err = np.linalg.norm(oa["force"][:n], axis=1), np.linalg.norm(f - oa["force"][:n], axis=1)
+    assert np.all(err <= 1e-10 * np.maximum(norm, 1e-3 * norm.max()))
     assert abs(e - ev[0]) <= 1e-12 * abs(ev[0]) and abs(v - ev[1]) <= 1e-12 * abs(ev[1])
     assert np.abs(f.sum(axis=0)).max() <= 1e-9 * np.abs(f).sum()  # Newton's third law over the periodic box
 
@@ -164,3 +167,67 @@ def test_adress_8m_tiled_vs_operator_sequence(api):
     assert pairs_tiled == generic.lastNumPairs > 0
     assert abs(e_tiled - e_generic) <= 1e-11 * abs(e_generic)
     assert np.abs(f_tiled - f_generic).max() <= 1e-10 * np.abs(f_generic).max()
+
+
+def test_adress_8m_tiled_vs_oracle(api, oracle):
+    """configs[2] size against the ORACLE (not against another CUDA path): 200^3 atoms, Slab(AT 0.2 L, HY 0.1 L), one
+    evaluation of UpdateMolecules + LJ_IdealGas::run + ContributeMoleculeForceToAtoms.  The oracle runs the reference's
+    step over ghost molecules (half list, forces folded back) on the atoms in the GPU's sorted order.  Forces are compared
+    atom by atom against the atom's own force (with a floor of 1e-3 of the largest), not only against the largest."""
+    import ctypes as C
+
+    pos, vel, box = jittered_lattice(200, 0.6, 9)
+    n = len(pos)
+    cutoff = RC + SKIN
+    sub = api.Subdomain([0, 0, 0], box, cutoff)
+    centre = [0.5 * float(b) for b in box]
+    w = api.Slab(0.5 * box, 0.2 * box[0], 0.1 * box[0], 1)
+    ow = oracle.make_weight(oracle.WEIGHT_SLAB, centre, 0.2 * float(box[0]), 0.1 * float(box[0]), 1)
+    atoms = api.Atoms.from_arrays(pos, vel, mass=1.0, relativeMass=1.0, capacity=int(1.08 * n))
+    del pos, vel
+    api.GhostLayer().exchangeRealAtoms(atoms, sub)
+    atoms.permute(api.LinkedCellList(0, n, [cutoff, cutoff, 0.25 * cutoff], sub.minCorner, sub.maxCorner))
+    spos = atoms.getPos()[:n]
+    vl = api.FullVerletList()
+    vl.build_periodic(atoms, sub, cutoff, 1.0, 60)
+    tiled = api.LJ_IdealGas(CAP, RC, 1.0, 1.0, True)
+    atoms.setForce(0.0)
+    e_tiled = tiled.run_periodic(atoms, vl, w)
+    pairs_tiled = tiled.lastNumPairs
+    total_pairs = vl.info()["totalPairs"]
+    f = atoms.getForce()[:n]
+    del vl, atoms
+
+    L = oracle.lib()
+    osub = oracle.subdomain([0, 0, 0], [float(b) for b in box], cutoff)
+    cap_rows = int(1.10 * n)
+    oa = np.zeros(cap_rows, dtype=oracle.ATOM)
+    oa["pos"][:n], oa["mass"][:n], oa["relMass"][:n] = spos, 1.0, 1.0
+    om = np.zeros(cap_rows, dtype=oracle.MOLECULE)
+    om["atomsOffset"][:n], om["numAtoms"][:n] = np.arange(n), 1
+    L.or_update_molecules(om.ctypes.data, n, oa.ctypes.data, C.byref(ow))
+    corr = np.zeros(cap_rows, dtype=np.int64)
+    out = np.zeros(2, dtype=np.int64)
+    assert L.or_mr_ghost_create_xyz(om.ctypes.data, n, cap_rows, oa.ctypes.data, n, cap_rows, C.byref(osub),
+                                    corr.ctypes.data, out.ctypes.data) == 0
+    mg, ag = int(out[0]), int(out[1])
+    oc, on = oracle.verlet_build(om, 13, n + mg, 0, n, cutoff, 1.0, np.array(osub.minGhostCorner),
+                                 np.array(osub.maxGhostCorner), half=True, width=40)
+    assert total_pairs == 2 * int(oc[:n].sum())
+    one = np.ones(1)
+    arrs = [np.ascontiguousarray(x) for x in (CAP * one, RC * one, one, one)]
+    oh = L.or_adress_create(*[x.ctypes.data for x in arrs], 1, 1)
+    L.or_update_molecules(om.ctypes.data, n + mg, oa.ctypes.data, C.byref(ow))
+    nact = C.c_int64()
+    oe = L.or_adress_run(oh, om.ctypes.data, n, oc.ctypes.data, on.ctypes.data, on.shape[1], oa.ctypes.data, C.byref(nact))
+    L.or_contribute_molecule_force(om.ctypes.data, n + mg, oa.ctypes.data)
+    L.or_ghost_fold_force(oa.ctypes.data, n, ag, corr.ctypes.data)
+    L.or_adress_destroy(oh)
+    f_ref = oa["force"][:n]
+    assert pairs_tiled == nact.value > 0
+    assert abs(e_tiled - oe) <= 1e-11 * abs(oe)
+    fmax = np.abs(f_ref).max()
+    assert np.abs(f - f_ref).max() <= 1e-10 * fmax
+    norm = np.linalg.norm(f_ref, axis=1)
+    err = np.linalg.norm(f - f_ref, axis=1)
+    assert np.all(err <= 1e-10 * np.maximum(norm, 1e-3 * fmax))
