@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "mrmd_b200", "libmrmd_b200.so")
 HOT = ["ljForceTiledKernelILb1ELb0ELb0E", "verletBuildTiledKernelILb0E", "adressForceTiledKernelILb1ELb0ELb0E",
        "moleculeForceTiledKernelILi4ELb1ELb0ELb0E", "integratePreKernelILb1ELb1E", "haloPushCountedKernel",
-       "maxDisplacementGatherKernel", "rsScatterKernel", "permuteAtomsKernel", "shakeFusedKernelILi4E"]
+       "maxDisplacementGatherKernel", "rsScatterKernel", "permuteAtomsKernel", "shakeFusedKernelILi4E", "shakeAllPairsKernelILi4E", "rattleAllPairsKernelILi4ELb1E"]
 
 out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
 kernels, name = collections.OrderedDict(), None
