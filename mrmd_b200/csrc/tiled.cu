@@ -9,18 +9,21 @@
 // columns are nine contiguous index ranges: they are copied once, coalesced, into shared memory as 24-byte
 // {x, y, z} records (periodic images are produced on the fly by adding +-L exactly as GhostExchange /
 // UpdateGhostAtoms do, so the staged coordinates are bit-identical to the ghost atoms' coordinates) and every
-// neighbour of a home atom becomes a 16-bit shared-memory slot.  TL_GROUP lanes share one home atom (measured on
-// B200 for 8 / 4 / 2 / 1 lanes: force kernel 225 / 203 / 200 / 308 us, build 553 / 510 / 462 / 628 us per 1M atoms;
-// fewer lanes amortise the per-home work over more homes per warp until shared-memory conflicts and row-length
-// imbalance take over): each lane owns every TL_GROUP-th list entry, stored contiguously (tiledRowIndex) so that
-// its first entries arrive with 16-byte loads; the force components are combined with warp shuffles.
+// neighbour of a home atom becomes a 16-bit shared-memory slot.
+// Force kernels: TL_GROUP lanes share one home atom (measured on B200 for 8 / 4 / 2 / 1 lanes in round 1: 225 / 203 / 200 /
+// 308 us per 1M atoms; fewer lanes amortise the per-home work over more homes per warp until shared-memory conflicts and
+// row-length imbalance take over): each lane owns every TL_GROUP-th list entry, stored contiguously (tiledRowIndex) so
+// that its entries arrive with 16-byte loads a pass ahead; the force components are combined with warp shuffles.
+// Build kernel: one lane per home atom, groups of TL_BUILD_GROUP consecutive homes sweep the same candidates in lock step
+// (see verletBuildTiledKernel).
 // No atomics (full list: an atom accumulates only its own force), no ghost refresh / fold-back in the step,
 // 2 bytes of list traffic per pair.
 // Tried and dropped (measured slower): dealing the staged slots round-robin over all threads instead of one piece
 // per warp; persistent blocks that prefetch the next tile's raw records with cp.async while computing (the extra
 // 32 B/slot of shared memory costs a resident block: 230 vs 194 us); tiles of 80 or 145 instead of 110 home atoms;
 // a single-precision candidate filter in the build (12-byte records, double-precision re-check inside a margin around
-// r^2): pair sets stayed bit exact, the build took 470 instead of 461 us -- its scan loop is not bound by the FP64 pipe.
+// r^2): pair sets stayed bit exact, no gain; several pairs per lane evaluated phase by phase in the force kernel
+// (registers cost a resident block).  Round-2 measurements: profiles/r02_build_experiments.md.
 //
 // Pair set: identical to the reference's list over local + ghost atoms (same criterion, same uncontracted
 // distance arithmetic, Cabana's stencil pruning re-checked on accepted pairs): tests decode the slots back to
