@@ -1785,7 +1785,13 @@ int verletBuildTiled(mrmd_b200_verlet* v, const mrmd_b200_atoms* a, const mrmd_b
         v->tiledHaloX = haloX;
         for (int d = 0; d < 3; ++d) v->tiledGridN[d] = g.n[d];
         tp.cap = v->tiledSlots;
-        MB_TRY(v->enc.reserve(size_t(width) * std::max<int64_t>(n, 1) * 2));
+        {
+            // rows are loaded in whole 16-byte words, also behind the stored entries (never used, but they should not be
+            // uninitialised memory either): a fresh allocation is cleared once
+            const void* before = v->enc.p;
+            MB_TRY(v->enc.reserve(size_t(width) * std::max<int64_t>(n, 1) * 2));
+            if (v->enc.p != before) MB_CUDA(cudaMemsetAsync(v->enc.p, 0, v->enc.bytes, st));
+        }
         MB_TRY(v->tileActive.reserve(size_t(tiles)));
         MB_TRY(v->activeTiles.reserve(size_t(tiles) * 4));
         v->width = width;
