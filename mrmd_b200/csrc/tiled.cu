@@ -704,7 +704,7 @@ __device__ __forceinline__ void prefetchListRows(const TileDesc& td, const int32
 {
     const int h = hBase + group;
     const bool active = h < td.homeCount;
-    const size_t i = size_t(td.homeStart + (active ? h : 0));
+    const size_t i = active ? size_t(td.homeStart + h) : 0;  // lanes without a home read row 0 (always there)
     count = active ? counts[i] : 0;
     // lane gl owns the entries gl, gl + TL_GROUP, ... of the row; the row layout keeps them contiguous
     // (tiledRowIndex), so they arrive as 16-byte words
