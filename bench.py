@@ -147,7 +147,24 @@ def ncu_profile(kernel, n_atoms):
     path = os.path.join(ROOT, "profiles", "kernel_ncu.json")
     if os.path.exists(path):
         try:
-            return json.load(open(path)).get(f"{kernel}@{int(n_atoms)}")
+            table = json.load(open(path))
+            exact = table.get(f"{kernel}@{int(n_atoms)}")
+            if exact is not None:
+                return exact
+            # no capture at this size (e.g. a cost-balanced slab): the capture of the same kernel at the nearest size, its
+            # byte counts scaled by the number of atoms (the pipe / issue fractions are intensive)
+            sizes = [(int(k.split("@")[1]), v) for k, v in table.items() if k.split("@")[0] == kernel]
+            if sizes and n_atoms > 0:
+                ref_atoms, ref = min(sizes, key=lambda kv: abs(kv[0] - n_atoms))
+                if not 0.25 <= float(n_atoms) / ref_atoms <= 4.0:
+                    return None  # another regime (e.g. the 4096-atom case is latency bound)
+                scaled = dict(ref)
+                for key in ("dram_bytes_read", "dram_bytes_write", "dram_bytes_per_launch", "warp_instructions"):
+                    if key in scaled:
+                        scaled[key] = scaled[key] * float(n_atoms) / ref_atoms
+                scaled.pop("duration_us_under_ncu", None)
+                scaled["source"] = f"{ref.get('source')}; byte counts scaled from {ref_atoms} to {int(n_atoms)} atoms"
+                return scaled
         except Exception:
             pass
     return None
