@@ -90,3 +90,12 @@ def test_slab_bounds_cover_the_box():
         assert edges[0][0] == gmin[0] and edges[-1][1] == gmax[0]
         for a, b in zip(edges[:-1], edges[1:]):
             assert a[1] == b[0]
+
+
+def test_bind_host_to_gpu_is_a_noop_without_topology():
+    """no CUDA device / no sysfs entry: the helper leaves the affinity alone and says so"""
+    from mrmd_b200 import slabs
+
+    before = os.sched_getaffinity(0)
+    assert slabs.bind_host_to_gpu(0) is None
+    assert os.sched_getaffinity(0) == before
