@@ -1266,7 +1266,17 @@ __global__ void __launch_bounds__(TL_THREADS_MOL)
             const uint4* src = reinterpret_cast<const uint4*>(enc + size_t(td.homeStart) * width);
             uint4* dst = reinterpret_cast<uint4*>(sRows);
             const int homesHere = min(td.homeCount, maxHomes);
-            for (int e = threadIdx.x; e < homesHere * wordsPerRow; e += blockDim.x) dst[e] = src[e];
+            // (the loads first: several in flight per thread)
+            for (int e0 = threadIdx.x; e0 < homesHere * wordsPerRow; e0 += TL_STAGE_UNROLL * blockDim.x)
+            {
+                uint4 v[TL_STAGE_UNROLL];
+#pragma unroll
+                for (int u = 0; u < TL_STAGE_UNROLL; ++u)
+                    if (e0 + u * blockDim.x < homesHere * wordsPerRow) v[u] = src[e0 + u * blockDim.x];
+#pragma unroll
+                for (int u = 0; u < TL_STAGE_UNROLL; ++u)
+                    if (e0 + u * blockDim.x < homesHere * wordsPerRow) dst[e0 + u * blockDim.x] = v[u];
+            }
         }
         {
             // staging: one piece per warp, a lane per (molecule, atom)
@@ -1281,19 +1291,33 @@ __global__ void __launch_bounds__(TL_THREADS_MOL)
                 pieceShift(tp, ci, cj, p, ix, iy, iz);
                 const double shx = double(ix) * tp.L[0], shy = double(iy) * tp.L[1], shz = double(iz) * tp.L[2];
                 const int start = td.pieceStart[p], slot0 = td.pieceSlot[p];
-                for (int e = lane; e < len * NA; e += 32)
+                // TL_STAGE_UNROLL loads in flight per lane (as in stageTile): the staging phase of this kernel was its
+                // largest stall (long scoreboard + the barrier behind it, profiles/r02_molecule_force_ncu.txt)
+                for (int e0 = lane; e0 < len * NA; e0 += 32 * TL_STAGE_UNROLL)
                 {
-                    const int k = e / NA, j = e % NA;
-                    const double4 raw = ld4nc(a.pos + (size_t(start) + k) * NA + j);
-                    double* r = rec + size_t(REC) * (slot0 + k);
-                    r[3 * j] = raw.x + shx;
-                    r[3 * j + 1] = raw.y + shy;
-                    r[3 * j + 2] = raw.z + shz;
-                    if (!SINGLE_TYPE) sType[(slot0 + k) * NA + j] = static_cast<unsigned char>(typeOf(raw));
-                    if (j == 0)
+                    double4 raw[TL_STAGE_UNROLL], cm[TL_STAGE_UNROLL];
+#pragma unroll
+                    for (int u = 0; u < TL_STAGE_UNROLL; ++u)
                     {
-                        const double4 c = ld4nc(com + start + k);
-                        r[3 * NA] = weightModLambda(w, c.x + shx, c.y + shy, c.z + shz);
+                        const int e = e0 + 32 * u;
+                        if (e < len * NA)
+                        {
+                            raw[u] = ld4nc(a.pos + size_t(start) * NA + e);
+                            if (e % NA == 0) cm[u] = ld4nc(com + start + e / NA);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < TL_STAGE_UNROLL; ++u)
+                    {
+                        const int e = e0 + 32 * u;
+                        if (e >= len * NA) break;
+                        const int k = e / NA, j = e % NA;
+                        double* r = rec + size_t(REC) * (slot0 + k);
+                        r[3 * j] = raw[u].x + shx;
+                        r[3 * j + 1] = raw[u].y + shy;
+                        r[3 * j + 2] = raw[u].z + shz;
+                        if (!SINGLE_TYPE) sType[(slot0 + k) * NA + j] = static_cast<unsigned char>(typeOf(raw[u]));
+                        if (j == 0) r[3 * NA] = weightModLambda(w, cm[u].x + shx, cm[u].y + shy, cm[u].z + shz);
                     }
                 }
             }
