@@ -214,6 +214,37 @@ __global__ void __launch_bounds__(SHAKE_FUSED_THREADS)
         for (int d = 0; d < 3; ++d) a.force[d][oc.x + k] = at(FORCE + d, k);
 }
 
+// NA consecutive doubles of a per-atom plane: one 32-byte access when a four-atom molecule starts on a multiple of four
+// atoms (uniform molecules do), instead of four 8-byte accesses a 32-byte stride apart from the neighbouring lanes'
+template <int NA>
+__device__ __forceinline__ void loadPlane(const double* plane, long long first, double (&v)[NA])
+{
+    if (NA == 4 && (reinterpret_cast<uintptr_t>(plane + first) & 31) == 0)
+    {
+        const double4 q = ld4(reinterpret_cast<const double4*>(plane + first));
+        v[0] = q.x;
+        v[1] = q.y;
+        v[2 % NA] = q.z;
+        v[3 % NA] = q.w;
+    }
+    else
+    {
+#pragma unroll
+        for (int k = 0; k < NA; ++k) v[k] = plane[first + k];
+    }
+}
+template <int NA>
+__device__ __forceinline__ void storePlane(double* plane, long long first, const double (&v)[NA])
+{
+    if (NA == 4 && (reinterpret_cast<uintptr_t>(plane + first) & 31) == 0)
+        st4(reinterpret_cast<double4*>(plane + first), make_double4(v[0], v[1], v[2 % NA], v[3 % NA]));
+    else
+    {
+#pragma unroll
+        for (int k = 0; k < NA; ++k) plane[first + k] = v[k];
+    }
+}
+
 // shakeFusedKernel for molecules whose bonds are ALL pairs of their NA atoms in lexicographic order (the rigid tetramers of
 // BASELINE.json configs[3], three-site water): the atom indices of every bond are compile-time constants, so the whole
 // molecule state lives in registers -- no shared memory (the shared-memory traffic of the indexable state, ~600 accesses per
@@ -241,20 +272,30 @@ __global__ void __launch_bounds__(128)
         const double eq = bondDist[b];
         eqSq[b] = eq * eq;
     }
-#pragma unroll
-    for (int k = 0; k < NA; ++k)
     {
-        const double4 p = ld4(a.pos + oc.x + k);
-        pos[k][0] = p.x;
-        pos[k][1] = p.y;
-        pos[k][2] = p.z;
+        double vel[3][NA], f[3][NA], mass[NA];
 #pragma unroll
         for (int d = 0; d < 3; ++d)
         {
-            base[k][d] = pos[k][d] + dtv * a.vel[d][oc.x + k];
-            frc[k][d] = a.force[d][oc.x + k];
+            loadPlane<NA>(a.vel[d], oc.x, vel[d]);
+            loadPlane<NA>(a.force[d], oc.x, f[d]);
         }
-        invMass[k] = 1.0 / a.mass[oc.x + k];  // the same quotient for every bond of the atom
+        loadPlane<NA>(a.mass, oc.x, mass);
+#pragma unroll
+        for (int k = 0; k < NA; ++k)
+        {
+            const double4 p = ld4(a.pos + oc.x + k);
+            pos[k][0] = p.x;
+            pos[k][1] = p.y;
+            pos[k][2] = p.z;
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+            {
+                base[k][d] = pos[k][d] + dtv * vel[d][k];
+                frc[k][d] = f[d][k];
+            }
+            invMass[k] = 1.0 / mass[k];  // the same quotient for every bond of the atom
+        }
     }
     for (int64_t it = 0; it < numIterations; ++it)
     {
@@ -294,9 +335,13 @@ __global__ void __launch_bounds__(128)
             }
     }
 #pragma unroll
-    for (int k = 0; k < NA; ++k)
+    for (int d = 0; d < 3; ++d)
+    {
+        double out[NA];
 #pragma unroll
-        for (int d = 0; d < 3; ++d) a.force[d][oc.x + k] = frc[k][d];
+        for (int k = 0; k < NA; ++k) out[k] = frc[k][d];
+        storePlane<NA>(a.force[d], oc.x, out);
+    }
 }
 
 // MoleculeConstraints::enforceVelocityConstraints lambda (Shake.hpp:215-231) with
@@ -406,23 +451,32 @@ __global__ void __launch_bounds__(128)
         return;
     }
     double pos[NA][3], vel[NA][3], invMass[NA];
-#pragma unroll
-    for (int k = 0; k < NA; ++k)
     {
-        const double4 p = ld4(a.pos + oc.x + k);
-        pos[k][0] = p.x;
-        pos[k][1] = p.y;
-        pos[k][2] = p.z;
-        const double mass = a.mass[oc.x + k];
-        const double dtfm = halfDt / mass;
+        double v0[3][NA], f[3][NA], mass[NA];
 #pragma unroll
         for (int d = 0; d < 3; ++d)
         {
-            double v = a.vel[d][oc.x + k];
-            if (KICK) v = __dadd_rn(v, __dmul_rn(dtfm, a.force[d][oc.x + k]));
-            vel[k][d] = v;
+            loadPlane<NA>(a.vel[d], oc.x, v0[d]);
+            if (KICK) loadPlane<NA>(a.force[d], oc.x, f[d]);
         }
-        invMass[k] = 1.0 / mass;
+        loadPlane<NA>(a.mass, oc.x, mass);
+#pragma unroll
+        for (int k = 0; k < NA; ++k)
+        {
+            const double4 p = ld4(a.pos + oc.x + k);
+            pos[k][0] = p.x;
+            pos[k][1] = p.y;
+            pos[k][2] = p.z;
+            const double dtfm = halfDt / mass[k];
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+            {
+                double v = v0[d][k];
+                if (KICK) v = __dadd_rn(v, __dmul_rn(dtfm, f[d][k]));
+                vel[k][d] = v;
+            }
+            invMass[k] = 1.0 / mass[k];
+        }
     }
 #pragma unroll
     for (int i = 0; i < NA; ++i)
@@ -441,9 +495,13 @@ __global__ void __launch_bounds__(128)
             }
         }
 #pragma unroll
-    for (int k = 0; k < NA; ++k)
+    for (int d = 0; d < 3; ++d)
+    {
+        double out[NA];
 #pragma unroll
-        for (int d = 0; d < 3; ++d) a.vel[d][oc.x + k] = vel[k][d];
+        for (int k = 0; k < NA; ++k) out[k] = vel[k][d];
+        storePlane<NA>(a.vel[d], oc.x, out);
+    }
 }
 
 static int checkBondError(int* dErr, cudaStream_t st)
