@@ -446,8 +446,8 @@ __global__ void __launch_bounds__(TL_THREADS_BUILD, 4)
         // 32 (shared-memory bandwidth, 128 B per clock and SM, is what bounds a sweep over per-lane ranges: 24 B x 32
         // lanes per step).  In every column the group scans the cells within the list radius of its lowest and highest
         // home along z.  Atoms are in cell order along z, so that is one slot range per column.  (Cutting the range of a
-        // column down by the homes' distance to it gains nothing for a group: one of eight homes is always close to the
-        // column's face; the nine per-lane range computations it takes were 20 % of the kernel's stall samples.)  This
+        // column down by the homes' distance to it was measured and dropped: the nine per-lane range computations and
+        // group reductions it takes were 20 % of the kernel's stall samples, more than the shorter sweeps gave back.)  This
         // is bookkeeping, not the list criterion: single precision on coordinates relative to the tile (float error
         // ~1e-6), widened by 0.1 % of r and 1e-3 of a cell, far more than that error and than the ulp by which an atom
         // may sit outside its cell.
