@@ -56,7 +56,7 @@ constexpr int TL_GROUP = 2;                       // lanes per home atom
 constexpr int TL_STAGE_UNROLL = MRMD_TL_STAGE_UNROLL;  // loads a lane keeps in flight while staging a tile
 constexpr int TL_BUILD_BATCH = MRMD_TL_BUILD_BATCH;  // candidates a lane of the neighbour build tests per step
 #ifndef MRMD_TL_BUILD_GROUP
-#define MRMD_TL_BUILD_GROUP 2
+#define MRMD_TL_BUILD_GROUP 4
 #endif
 constexpr int TL_BUILD_GROUP = MRMD_TL_BUILD_GROUP;  // consecutive homes (lanes) that sweep the same candidates
 constexpr int TL_PIECES = 27;                     // 9 columns x {low z-wrap, main, high z-wrap}
